@@ -1,0 +1,304 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the BESO denoiser hot path.
+
+A functional (no nn.Module, no Hydra) restatement of the reference algorithm
+over a plain ``state_dict``.  The reference substrate is PyTorch ATen in fp32
+(SURVEY.md section 8c), so the restatement uses the same ATen ops in the same
+order on CPU; that makes it *bit-comparable* with the reference when both run
+on the same torch build, which is how it is pinned (tests/test_oracle.py,
+oracle/make_golden.py).  Parity status: PINNED against outputs of the
+reference itself run in the build container (random-weight fixtures under
+tests/golden/ plus all 12 shipped checkpoints when /root/reference is
+present).  The reference's own test-suite holds no vectors for this path.
+
+Every function cites the reference file:line it follows; paths are relative
+to ``beso/agents/diffusion_agents/k_diffusion/`` in intuitive-robots/beso.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline /
+--impl reference) may import this module.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+P = "inner_model."
+
+
+@dataclass(frozen=True)
+class OracleCfg:
+    """Hyper-parameters of DiffusionGPT.__init__ (score_gpts.py:121-139)."""
+    obs_dim: int
+    act_dim: int
+    window: int          # obs_seq_len
+    goal_len: int        # goal_seq_len
+    d: int               # embed_dim
+    n_layers: int
+    n_heads: int
+    sigma_data: float = 0.5
+    linear_output: bool = True
+    goal_conditioned: bool = True
+
+    @property
+    def block_size(self) -> int:          # score_gpts.py:148
+        g = self.goal_len if self.goal_conditioned else 0
+        return g + 2 * self.window + 1
+
+
+def as_module_params(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """The reference holds its weights as ``nn.Parameter`` (requires_grad=True) even in
+    eval/no_grad, and ATen's ``linear`` picks its kernel on that flag for non-contiguous
+    inputs (the action head, score_gpts.py:353-354).  Marking the oracle's weights the same
+    way makes the restatement bit-exact with the reference on the same torch build."""
+    return {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("attn.mask")
+                else v) for k, v in sd.items()}
+
+
+# --------------------------------------------------------------------------- #
+# utils.py:165-170
+def append_dims(x: Tensor, target_dims: int) -> Tensor:
+    dims_to_append = target_dims - x.ndim
+    if dims_to_append < 0:
+        raise ValueError("input has more dims than target")
+    return x[(...,) + (None,) * dims_to_append]
+
+
+# score_wrappers.py:31-43
+def get_scalings(sigma: Tensor, sigma_data: float):
+    c_skip = sigma_data ** 2 / (sigma ** 2 + sigma_data ** 2)
+    c_out = sigma * sigma_data / (sigma ** 2 + sigma_data ** 2) ** 0.5
+    c_in = 1 / (sigma ** 2 + sigma_data ** 2) ** 0.5
+    return c_skip, c_out, c_in
+
+
+# score_gpts.py:50-80
+def causal_self_attention(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int,
+                          attn_drop_mask: Optional[Tensor] = None) -> Tensor:
+    B, T, C = x.size()
+    k = F.linear(x, sd[pre + "key.weight"], sd[pre + "key.bias"]).view(B, T, n_head, C // n_head).transpose(1, 2)
+    q = F.linear(x, sd[pre + "query.weight"], sd[pre + "query.bias"]).view(B, T, n_head, C // n_head).transpose(1, 2)
+    v = F.linear(x, sd[pre + "value.weight"], sd[pre + "value.bias"]).view(B, T, n_head, C // n_head).transpose(1, 2)
+    att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(k.size(-1)))
+    mask = torch.tril(torch.ones(T, T)).view(1, 1, T, T)          # score_gpts.py:42-47
+    att = att.masked_fill(mask == 0, float("-inf"))
+    att = F.softmax(att, dim=-1)
+    if attn_drop_mask is not None:                                # eval: identity
+        att = att * attn_drop_mask
+    y = att @ v
+    y = y.transpose(1, 2).contiguous().view(B, T, C)
+    return F.linear(y, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+
+
+# score_gpts.py:96-115
+def block(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int) -> Tensor:
+    d = x.shape[-1]
+    h = F.layer_norm(x, (d,), sd[pre + "ln1.weight"], sd[pre + "ln1.bias"], 1e-5)
+    x = x + causal_self_attention(h, sd, pre + "attn.", n_head)
+    h = F.layer_norm(x, (d,), sd[pre + "ln2.weight"], sd[pre + "ln2.bias"], 1e-5)
+    h = F.linear(h, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"])
+    h = F.gelu(h)                                                 # nn.GELU() default = exact erf
+    h = F.linear(h, sd[pre + "mlp.2.weight"], sd[pre + "mlp.2.bias"])
+    return x + h
+
+
+# score_gpts.py:272-358
+def gpt_forward(sd: Dict[str, Tensor], cfg: OracleCfg, states: Tensor, actions: Tensor,
+                goals: Tensor, sigma: Tensor, uncond: bool = False,
+                keep_last_actions: bool = False, goal_keep: Optional[Tensor] = None) -> Tensor:
+    """``goal_keep`` (B,G,obs) in {0,1} restates mask_cond (score_gpts.py:360-371)
+    with the Bernoulli draw made by the caller: goals * goal_keep, goal_keep = 1 - mask."""
+    b, t, _ = states.size()
+    assert t <= cfg.block_size, "Cannot forward, model block size is exhausted."
+    G = cfg.goal_len if cfg.goal_conditioned else 0
+    sigmas = sigma.log() / 4                                      # :284
+    sigmas = sigmas.view(b, 1)
+    emb_t = F.linear(sigmas.to(torch.float32), sd[P + "sigma_emb.weight"], sd[P + "sigma_emb.bias"])
+    emb_t = emb_t.view(b, 1, cfg.d)
+    if goal_keep is not None:                                     # :298-299 (training only)
+        goals = goals * goal_keep
+    if uncond:                                                    # :301-302
+        goals = torch.zeros_like(goals)
+    state_embed = F.linear(states, sd[P + "tok_emb.weight"], sd[P + "tok_emb.bias"])      # :305
+    goal_embed = F.linear(goals, sd[P + "tok_emb.weight"], sd[P + "tok_emb.bias"])        # :306
+    action_embed = F.linear(actions, sd[P + "action_emb.weight"], sd[P + "action_emb.bias"])  # :307
+    pos = sd[P + "pos_emb"][:, :(t + G), :]                       # :311-318
+    state_x = state_embed + pos[:, G:, :]
+    action_x = action_embed + pos[:, G:, :]
+    sa_seq = torch.stack([state_x, action_x], dim=1).permute(0, 2, 1, 3).reshape(b, 2 * t, cfg.d)  # :330-331
+    if cfg.goal_conditioned:
+        goal_x = goal_embed + pos[:, :G, :]
+        x = torch.cat([emb_t, goal_x, sa_seq], dim=1)             # :335
+    else:
+        x = torch.cat([emb_t, sa_seq], dim=1)
+    for l in range(cfg.n_layers):                                 # :340
+        x = block(x, sd, f"{P}blocks.{l}.", cfg.n_heads)
+    x = F.layer_norm(x, (cfg.d,), sd[P + "ln_f.weight"], sd[P + "ln_f.bias"], 1e-5)       # :341
+    x = x[:, G + 1:, :]                                           # :344
+    x_len = x.size(1) // 2 if x.size(1) < 2 * cfg.window else cfg.window      # :347-351
+    x = x.reshape(b, x_len, 2, cfg.d).permute(0, 2, 1, 3)
+    action_outputs = x[:, 1]
+    if cfg.linear_output:                                         # :183-190
+        pred = F.linear(action_outputs, sd[P + "action_pred.weight"], sd[P + "action_pred.bias"])
+    else:
+        h = F.linear(action_outputs, sd[P + "action_pred.0.weight"], sd[P + "action_pred.0.bias"])
+        pred = F.linear(F.silu(h), sd[P + "action_pred.2.weight"], sd[P + "action_pred.2.bias"])
+    if keep_last_actions:                                         # :355-356 (B == 1 only)
+        pred = torch.cat([actions[:, :-1, :], pred[:, -1, :].reshape(1, 1, -1)], dim=1)
+    return pred
+
+
+# score_wrappers.py:81-96
+def denoiser_forward(sd, cfg: OracleCfg, state, action, goal, sigma, **kwargs) -> Tensor:
+    c_skip, c_out, c_in = [append_dims(x, action.ndim) for x in get_scalings(sigma, cfg.sigma_data)]
+    return gpt_forward(sd, cfg, state, action * c_in, goal, sigma, **kwargs) * c_out + action * c_skip
+
+
+# score_wrappers.py:45-79
+def denoiser_loss(sd, cfg: OracleCfg, state, action, goal, noise, sigma,
+                  pred_last_action_only: bool = False, **kwargs) -> Tensor:
+    if pred_last_action_only:
+        noise[:, :-1, :] = 0                                      # in place, like :63
+    noised_input = action + noise * append_dims(sigma, action.ndim)
+    c_skip, c_out, c_in = [append_dims(x, action.ndim) for x in get_scalings(sigma, cfg.sigma_data)]
+    model_output = gpt_forward(sd, cfg, state, noised_input * c_in, goal, sigma, **kwargs)
+    target = (action - c_skip * noised_input) / c_out
+    if pred_last_action_only:
+        return (model_output[:, -1, :] - target[:, -1, :]).pow(2).mean()
+    return (model_output - target).pow(2).flatten(1).mean()
+
+
+def loss_and_grads(sd, cfg: OracleCfg, state, action, goal, noise, sigma, **kwargs):
+    """Loss plus d(loss)/d(param) for every floating parameter, by autograd through
+    the restated forward -- what ``loss.backward()`` does at beso_agent.py:236-240."""
+    leaf = {k: (v.detach().clone().requires_grad_(True) if not k.endswith("attn.mask") else v)
+            for k, v in sd.items()}
+    loss = denoiser_loss(leaf, cfg, state, action, goal, noise, sigma, **kwargs)
+    names = [k for k in leaf if not k.endswith("attn.mask")]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(leaf[k])) for k, g in zip(names, grads)}
+
+
+# classifier_free_sampler.py:35-49
+def cfg_forward(sd, cfg: OracleCfg, cond_lambda: float, state, action, goal, sigma) -> Tensor:
+    if cond_lambda == 1:
+        return denoiser_forward(sd, cfg, state, action, goal, sigma)
+    if cond_lambda == 0:
+        return denoiser_forward(sd, cfg, state, action, goal, sigma, uncond=True)
+    out = denoiser_forward(sd, cfg, state, action, goal, sigma)
+    out_uncond = denoiser_forward(sd, cfg, state, action, goal, sigma, uncond=True)
+    return out_uncond + cond_lambda * (out - out_uncond)
+
+
+# --------------------------------------------------------------------------- #
+# gc_sampling.py:22-95  noise schedules
+def append_zero(x: Tensor) -> Tensor:
+    return torch.cat([x, x.new_zeros([1])])
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0):
+    ramp = torch.linspace(0, 1, n)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    return append_zero((max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho)
+
+
+def get_sigmas_exponential(n, sigma_min, sigma_max):
+    return append_zero(torch.linspace(math.log(sigma_max), math.log(sigma_min), n).exp())
+
+
+def get_sigmas_linear(n, sigma_min, sigma_max):
+    return append_zero(torch.linspace(sigma_max, sigma_min, n))
+
+
+def get_sigmas_ve(n, sigma_min=0.02, sigma_max=100):
+    steps = n + 1
+    t = torch.linspace(0, steps, n)
+    t = (sigma_max ** 2) * ((sigma_min ** 2 / sigma_max ** 2) ** (t / (n - 1)))
+    return append_zero(torch.sqrt(t))
+
+
+def get_sigmas_vp(n, beta_d=19.9, beta_min=0.1, eps_s=1e-3):
+    t = torch.linspace(1, eps_s, n)
+    return append_zero(torch.sqrt(torch.exp(beta_d * t ** 2 / 2 + beta_min * t) - 1))
+
+
+# gc_sampling.py:98-100
+def to_d(action, sigma, denoised):
+    return (action - denoised) / append_dims(sigma, action.ndim)
+
+
+def _model(sd, cfg, cond_lambda):
+    if cond_lambda is None:
+        return lambda s, a, g, sig: denoiser_forward(sd, cfg, s, a, g, sig)
+    return lambda s, a, g, sig: cfg_forward(sd, cfg, cond_lambda, s, a, g, sig)
+
+
+# gc_sampling.py:895-924
+def sample_ddim(sd, cfg, state, action, goal, sigmas, cond_lambda=None, trace=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in)
+        t, t_next = sigmas[i].log().neg(), sigmas[i + 1].log().neg()
+        h = t_next - t
+        action = (t_next.neg().exp() / t.neg().exp()) * action - (-h).expm1() * denoised
+        if trace is not None:
+            trace.append(action.clone())
+    return action
+
+
+# gc_sampling.py:167-213
+def sample_euler(sd, cfg, state, action, goal, sigmas, cond_lambda=None,
+                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, eps_list=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        eps = (eps_list[i] if eps_list is not None else torch.randn_like(action)) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * s_in)
+        d = to_d(action, sigma_hat, denoised)
+        dt = sigmas[i + 1] - sigma_hat
+        action = action + d * dt
+    return action
+
+
+# gc_sampling.py:259-314
+def sample_heun(sd, cfg, state, action, goal, sigmas, cond_lambda=None,
+                s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, eps_list=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        eps = (eps_list[i] if eps_list is not None else torch.randn_like(action)) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * s_in)
+        d = to_d(action, sigma_hat, denoised)
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            action = action + d * dt
+        else:
+            action_2 = action + d * dt
+            denoised_2 = model(state, action_2, goal, sigmas[i + 1] * s_in)
+            d_2 = to_d(action_2, sigmas[i + 1], denoised_2)
+            d_prime = (d + d_2) / 2
+            action = action + d_prime * dt
+    return action
+
+
+SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun}
+
+
+def n_model_evals(sampler: str, n_steps: int, last_sigma_zero: bool = True) -> int:
+    """Model evaluations per sequence of one sample loop."""
+    if sampler == "heun":
+        return 2 * n_steps - (1 if last_sigma_zero else 0)
+    return n_steps

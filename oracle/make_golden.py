@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz with the REAL reference.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Every fixture is produced by calling the unmodified reference modules
+(GCDenoiser / DiffusionGPT / gc_sampling / ClassifierFreeSampleModel) on CPU in
+fp32 with weights from ``beso_b200.synth.synthetic_state_dict`` (regenerated
+from the seed at test time; a float64 checksum of the weights is stored so a
+drift of the generator is caught).  The reference cannot travel to the GPU box;
+these files are what pins parity there.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from beso_b200.config import ModelConfig, K256, B256, T16          # noqa: E402
+from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
+from oracle import ref_import                                      # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SMALL_KITCHEN = ModelConfig(obs_dim=30, act_dim=9, window=4, goal_len=2, d=360, n_layers=2, n_heads=6)
+SMALL_PUSH = ModelConfig(obs_dim=10, act_dim=2, window=5, goal_len=1, d=240, n_layers=2, n_heads=12)
+MLP_HEAD = ModelConfig(obs_dim=12, act_dim=3, window=3, goal_len=1, d=64, n_layers=1, n_heads=2, linear_output=False)
+NO_GOAL = ModelConfig(obs_dim=12, act_dim=3, window=3, goal_len=2, d=64, n_layers=1, n_heads=2, goal_conditioned=False)
+
+FWD_CASES = [  # name, cfg, weight seed, batch, t (None = W)
+    ("fwd_K256", K256, 1, 8, None),
+    ("fwd_K256_t1", K256, 1, 3, 1),
+    ("fwd_K256_t4", K256, 1, 3, 4),
+    ("fwd_T16", T16, 2, 8, None),
+    ("fwd_B256", B256, 3, 8, None),
+    ("fwd_small_kitchen", SMALL_KITCHEN, 4, 5, None),
+    ("fwd_small_push", SMALL_PUSH, 5, 5, None),
+    ("fwd_mlp_head", MLP_HEAD, 6, 4, None),
+]
+
+
+def cfg_dict(cfg: ModelConfig):
+    return {k: getattr(cfg, k) for k in ("obs_dim", "act_dim", "window", "goal_len", "d", "n_layers",
+                                        "n_heads", "sigma_data", "linear_output", "goal_conditioned")}
+
+
+def weight_checksum(sd) -> float:
+    return float(sum(v.double().sum().item() for k, v in sd.items() if not k.endswith("attn.mask")))
+
+
+def build(ns, cfg, seed):
+    m = ref_import.make_reference_model(ns, cfg)
+    sd = synthetic_state_dict(cfg, seed)
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m, sd
+
+
+def save(name, cfg, seed, sd, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    meta = dict(cfg_dict(cfg), weight_seed=seed, weight_checksum=weight_checksum(sd),
+                torch=torch.__version__)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=np.array(repr(meta)),
+                        **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                           for k, v in arrays.items()})
+    print("wrote", name, {k: tuple(np.shape(v)) for k, v in arrays.items()})
+
+
+@torch.no_grad()
+def gen_forward(ns):
+    for name, cfg, seed, B, t in FWD_CASES:
+        m, sd = build(ns, cfg, seed)
+        x = synthetic_inputs(cfg, B, seed=100 + seed, t=t)
+        out = m(x["state"], x["action"], x["goal"], x["sigma"])
+        out_u = m(x["state"], x["action"], x["goal"], x["sigma"], uncond=True)
+        inner = m.inner_model(x["state"], x["action"], x["goal"], x["sigma"])
+        save(name, cfg, seed, sd, state=x["state"], action=x["action"], goal=x["goal"], sigma=x["sigma"],
+             out=out, out_uncond=out_u, inner=inner)
+    # not goal conditioned (score_gpts.py:143-144,317-320,336-337); the reference indexes
+    # pos_emb[:, goal_seq_len:] with the ORIGINAL goal_seq_len attribute overwritten to 0.
+    cfg, seed = NO_GOAL, 7
+    m, sd = build(ns, cfg, seed)
+    x = synthetic_inputs(cfg, 4, seed=107)
+    out = m(x["state"], x["action"], x["goal"], x["sigma"])
+    save("fwd_no_goal", cfg, seed, sd, state=x["state"], action=x["action"], goal=x["goal"],
+         sigma=x["sigma"], out=out)
+
+
+@torch.no_grad()
+def gen_samplers(ns):
+    gs = ns.gc_sampling
+    cfg, seed, B = K256, 1, 4
+    m, sd = build(ns, cfg, seed)
+    x = synthetic_inputs(cfg, B, seed=201)
+    x_t = x["noise"] * 1.0
+    arrays = dict(state=x["state"], goal=x["goal"], x_t=x_t)
+    for n in (1, 3, 5):
+        sig = gs.get_sigmas_exponential(n, 0.005, 1.0)
+        arrays[f"sigmas_{n}"] = sig
+        trace = []
+        arrays[f"ddim_{n}"] = gs.sample_ddim(m, x["state"], x_t, x["goal"], sig, disable=True,
+                                             callback=lambda d: trace.append(d["denoised"].clone()))
+        if n == 5:
+            arrays["ddim_5_denoised_trace"] = torch.stack(trace)
+        arrays[f"euler_{n}"] = gs.sample_euler(m, x["state"], x_t, x["goal"], sig, disable=True)
+        arrays[f"heun_{n}"] = gs.sample_heun(m, x["state"], x_t, x["goal"], sig, disable=True)
+    sigk = gs.get_sigmas_karras(4, 0.005, 1.0, 5.0)
+    arrays["sigmas_karras_4"] = sigk
+    arrays["heun_karras_4"] = gs.sample_heun(m, x["state"], x_t, x["goal"], sigk, disable=True)
+    # classifier-free guidance wrapper (classifier_free_sampler.py:12-52)
+    CF = ns.classifier_free_sampler.ClassifierFreeSampleModel
+    sig = gs.get_sigmas_exponential(4, 0.005, 1.0)
+    arrays["sigmas_cfg_4"] = sig
+    for lam in (0.0, 1.0, 1.5, 2.0):
+        w = CF(m, cond_lambda=lam)
+        tag = str(lam).replace(".", "p")
+        arrays[f"cfg_fwd_{tag}"] = w(x["state"], x["action"], x["goal"], x["sigma"])
+        arrays[f"cfg_heun4_{tag}"] = gs.sample_heun(w, x["state"], x_t, x["goal"], sig, disable=True)
+        arrays[f"cfg_ddim4_{tag}"] = gs.sample_ddim(w, x["state"], x_t, x["goal"], sig, disable=True)
+    arrays["action"] = x["action"]
+    arrays["sigma"] = x["sigma"]
+    save("samplers_K256", cfg, seed, sd, **arrays)
+
+
+def gen_schedules(ns):
+    gs = ns.gc_sampling
+    arrays = {}
+    for n in (1, 3, 10, 50):
+        arrays[f"exponential_{n}"] = gs.get_sigmas_exponential(n, 0.005, 1.0)
+        arrays[f"karras_{n}"] = gs.get_sigmas_karras(n, 0.005, 1.0, 5.0)
+        arrays[f"linear_{n}"] = gs.get_sigmas_linear(n, 0.005, 1.0)
+        arrays[f"vp_{n}"] = gs.get_sigmas_vp(n)
+        if n > 1:
+            arrays[f"ve_{n}"] = gs.get_sigmas_ve(n, 0.005, 1.0)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "schedules.npz"), **{k: v.numpy() for k, v in arrays.items()})
+    print("wrote schedules", list(arrays))
+
+
+def gen_loss(ns):
+    for name, cfg, seed, B in (("loss_B256", B256, 3, 16), ("loss_K256", K256, 1, 8)):
+        m, sd = build(ns, cfg, seed)
+        m.train()                      # beso_agent.py:229-230; dropout p = 0, goal_drop = 0
+        m.training = True
+        x = synthetic_inputs(cfg, B, seed=300 + seed, sigma_min=0.05)
+        loss = m.loss(x["state"], x["clean"], x["goal"], x["noise"].clone(), x["sigma"])
+        m.zero_grad()
+        loss.backward()
+        arrays = dict(state=x["state"], action=x["clean"], goal=x["goal"], noise=x["noise"],
+                      sigma=x["sigma"], loss=loss.detach())
+        norms, names = [], []
+        for n, p in m.named_parameters():
+            g = p.grad
+            names.append(n)
+            norms.append(g.double().norm().item())
+            flat = g.reshape(-1)
+            # full gradient for small tensors, a strided sample of the big ones
+            arrays["grad::" + n] = flat if flat.numel() <= 4096 else flat[::97][:4096]
+        arrays["grad_norms"] = np.array(norms)
+        arrays["grad_names"] = np.array(names)
+        loss_last = m.loss(x["state"], x["clean"], x["goal"], x["noise"].clone(), x["sigma"],
+                           pred_last_action_only=True)
+        arrays["loss_pred_last"] = loss_last.detach()
+        save(name, cfg, seed, sd, **arrays)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ns = ref_import.load()
+    gen_schedules(ns)
+    gen_forward(ns)
+    gen_samplers(ns)
+    gen_loss(ns)
+
+
+if __name__ == "__main__":
+    main()

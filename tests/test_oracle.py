@@ -1,0 +1,133 @@
+"""CPU: the oracle restatement against (a) the committed golden vectors produced by the
+real reference and (b) the live reference incl. all shipped checkpoints when it is present."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_weights, load_golden, to_oracle_cfg
+from oracle import beso_oracle as O
+from oracle import ref_import
+
+# The oracle replays the reference's ATen ops in order; on the torch build / thread count that
+# made the fixtures it is bit-exact (asserted against the live reference below).  The tolerance
+# only absorbs a different BLAS thread split on another host.
+TOL = dict(rtol=1e-5, atol=1e-6)
+
+FWD = ["fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_kitchen",
+       "fwd_small_push", "fwd_mlp_head"]
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_forward_matches_golden(name):
+    cfg, meta, a = load_golden(name)
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    with torch.no_grad():
+        out = O.denoiser_forward(sd, oc, a["state"], a["action"], a["goal"], a["sigma"])
+        out_u = O.denoiser_forward(sd, oc, a["state"], a["action"], a["goal"], a["sigma"], uncond=True)
+        c_in = O.get_scalings(a["sigma"], oc.sigma_data)[2]
+    torch.testing.assert_close(out, a["out"], **TOL)
+    torch.testing.assert_close(out_u, a["out_uncond"], **TOL)
+    assert not torch.equal(out, out_u)
+    del c_in
+
+
+def test_forward_no_goal_conditioning():
+    cfg, meta, a = load_golden("fwd_no_goal")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    with torch.no_grad():
+        out = O.denoiser_forward(sd, oc, a["state"], a["action"], a["goal"], a["sigma"])
+    torch.testing.assert_close(out, a["out"], **TOL)
+
+
+def test_samplers_match_golden():
+    cfg, meta, a = load_golden("samplers_K256")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    with torch.no_grad():
+        for n in (1, 3, 5):
+            sig = a[f"sigmas_{n}"]
+            for s in ("ddim", "euler", "heun"):
+                got = O.SAMPLERS[s](sd, oc, a["state"], a["x_t"], a["goal"], sig)
+                torch.testing.assert_close(got, a[f"{s}_{n}"], **TOL)
+        got = O.sample_heun(sd, oc, a["state"], a["x_t"], a["goal"], a["sigmas_karras_4"])
+        torch.testing.assert_close(got, a["heun_karras_4"], **TOL)
+        for lam in (0.0, 1.0, 1.5, 2.0):
+            tag = str(lam).replace(".", "p")
+            got = O.cfg_forward(sd, oc, lam, a["state"], a["action"], a["goal"], a["sigma"])
+            torch.testing.assert_close(got, a[f"cfg_fwd_{tag}"], **TOL)
+            got = O.sample_heun(sd, oc, a["state"], a["x_t"], a["goal"], a["sigmas_cfg_4"], cond_lambda=lam)
+            torch.testing.assert_close(got, a[f"cfg_heun4_{tag}"], **TOL)
+            got = O.sample_ddim(sd, oc, a["state"], a["x_t"], a["goal"], a["sigmas_cfg_4"], cond_lambda=lam)
+            torch.testing.assert_close(got, a[f"cfg_ddim4_{tag}"], **TOL)
+
+
+def test_ddim_last_step_returns_denoised():
+    """sigma_{n}=0 -> h=+inf -> x <- denoised exactly (gc_sampling.py:921-923)."""
+    cfg, meta, a = load_golden("samplers_K256")
+    torch.testing.assert_close(a["ddim_5"], a["ddim_5_denoised_trace"][-1], rtol=0, atol=0)
+    torch.testing.assert_close(a["ddim_1"], a["euler_1"], rtol=1e-5, atol=1e-6)   # one step to sigma=0
+    torch.testing.assert_close(a["heun_1"], a["euler_1"], rtol=0, atol=0)         # Heun's last step is Euler
+
+
+def test_schedules_match_golden():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "schedules.npz"))
+    for n in (1, 3, 10, 50):
+        np.testing.assert_array_equal(O.get_sigmas_exponential(n, 0.005, 1.0).numpy(), z[f"exponential_{n}"])
+        np.testing.assert_array_equal(O.get_sigmas_karras(n, 0.005, 1.0, 5.0).numpy(), z[f"karras_{n}"])
+        np.testing.assert_array_equal(O.get_sigmas_linear(n, 0.005, 1.0).numpy(), z[f"linear_{n}"])
+        np.testing.assert_array_equal(O.get_sigmas_vp(n).numpy(), z[f"vp_{n}"])
+        if n > 1:
+            np.testing.assert_array_equal(O.get_sigmas_ve(n, 0.005, 1.0).numpy(), z[f"ve_{n}"])
+
+
+@pytest.mark.parametrize("name", ["loss_B256", "loss_K256"])
+def test_loss_and_grads_match_golden(name):
+    cfg, meta, a = load_golden(name)
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    loss, grads = O.loss_and_grads(sd, oc, a["state"], a["action"], a["goal"], a["noise"].clone(), a["sigma"])
+    torch.testing.assert_close(loss, a["loss"], rtol=1e-5, atol=1e-7)
+    names = [str(n) for n in a["grad_names"]]
+    for n, ref_norm in zip(names, a["grad_norms"]):
+        g = grads["inner_model." + n if not n.startswith("inner_model.") else n]
+        assert abs(g.double().norm().item() - ref_norm) <= 1e-4 * ref_norm + 1e-9, n
+        flat = g.reshape(-1)
+        want = a["grad::" + n]
+        got = flat if flat.numel() <= 4096 else flat[::97][:4096]
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-7)
+    with torch.no_grad():
+        l2 = O.denoiser_loss(sd, oc, a["state"], a["action"], a["goal"], a["noise"].clone(), a["sigma"],
+                             pred_last_action_only=True)
+    torch.testing.assert_close(l2, a["loss_pred_last"], rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------
+# live reference (build container only)
+needs_ref = pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("env", ["kitchen", "block_push"])
+def test_oracle_bitexact_on_shipped_checkpoints(env):
+    from beso_b200.config import BLOCKPUSH_CKPT, KITCHEN_CKPT
+    from beso_b200.synth import synthetic_inputs
+    cfg = KITCHEN_CKPT if env == "kitchen" else BLOCKPUSH_CKPT
+    ns = ref_import.load()
+    paths = sorted(glob.glob(os.path.join(ref_import.REF_ROOT, "trained_models", env, "*", "*.pth")))
+    assert len(paths) == 12
+    oc = to_oracle_cfg(cfg)
+    x = synthetic_inputs(cfg, 6, seed=5)
+    sig = ns.gc_sampling.get_sigmas_exponential(3, 0.005, 1.0)
+    for p in paths[::3]:
+        sd = torch.load(p, map_location="cpu")
+        m = ref_import.make_reference_model(ns, cfg)
+        m.load_state_dict(sd, strict=True)
+        sd = O.as_module_params(sd)
+        with torch.no_grad():
+            want = m(x["state"], x["action"], x["goal"], x["sigma"])
+            got = O.denoiser_forward(sd, oc, x["state"], x["action"], x["goal"], x["sigma"])
+            assert torch.equal(want, got), p
+            want = ns.gc_sampling.sample_ddim(m, x["state"], x["noise"], x["goal"], sig, disable=True)
+            got = O.sample_ddim(sd, oc, x["state"], x["noise"], x["goal"], sig)
+            assert torch.equal(want, got), p
