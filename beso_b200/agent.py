@@ -1,0 +1,162 @@
+"""Host-side mirror of the sampling half of ``BesoAgent`` (diffusion_agents/beso_agent.py).
+
+Only what sits directly on the hot path is here: ``sample_loop`` (beso_agent.py:390-456),
+``get_noise_schedule`` (:580-598), ``evaluate`` (:251-289) and the stateful ``predict``
+(:297-388) with its observation / action context deques.  Hydra, wandb, workspaces, data
+loading and the optimiser stay in the reference shell; to use the reference's own BesoAgent
+instead, point its model ``_target_`` at ``beso_b200.denoiser.GCDenoiser``.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Optional
+
+import torch
+
+from . import sampling
+from .cfg import ClassifierFreeSampleModel
+from .denoiser import GCDenoiser
+
+FUSED_SAMPLERS = ("ddim", "euler", "heun")
+
+
+class IdentityScaler:
+    """Stands in for networks/scaler/scaler_class.py when data is not scaled (scale_data: False)."""
+
+    def scale_input(self, x):
+        return x
+
+    def scale_output(self, x):
+        return x
+
+    def inverse_scale_output(self, x):
+        return x
+
+    def clip_action(self, x):
+        return x
+
+
+class BesoAgent:
+    def __init__(self, model: GCDenoiser, device="cuda", sampler_type: str = "ddim", num_sampling_steps: int = 3,
+                 sigma_min: float = 0.005, sigma_max: float = 1.0, rho: float = 5.0, window_size: int = 4,
+                 noise_scheduler: str = "exponential", use_ema: bool = False, ema_params=None,
+                 scaler=None, pred_last_action_only: bool = False, cond_lambda: Optional[float] = None):
+        self.model = model
+        self.device = device
+        self.sampler_type = sampler_type
+        self.num_sampling_steps = num_sampling_steps
+        self.sigma_min, self.sigma_max, self.rho = sigma_min, sigma_max, rho
+        self.window_size = window_size
+        self.noise_scheduler = noise_scheduler
+        self.use_ema = use_ema
+        self.ema_params = ema_params          # list of tensors in parameters() order, or None
+        self.scaler = scaler if scaler is not None else IdentityScaler()
+        self.pred_last_action_only = pred_last_action_only
+        self.obs_context = deque(maxlen=window_size)
+        self.action_context = deque(maxlen=window_size - 1)
+        if cond_lambda is not None:
+            self.model = ClassifierFreeSampleModel(model, cond_lambda)
+
+    # ---- beso_agent.py:580-598 --------------------------------------------------------------
+    def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):
+        s = sampling
+        if noise_schedule_type == "karras":
+            return s.get_sigmas_karras(n_sampling_steps, self.sigma_min, self.sigma_max, self.rho, self.device)
+        if noise_schedule_type == "exponential":
+            return s.get_sigmas_exponential(n_sampling_steps, self.sigma_min, self.sigma_max, self.device)
+        if noise_schedule_type == "vp":
+            return s.get_sigmas_vp(n_sampling_steps, device=self.device)
+        if noise_schedule_type == "linear":
+            return s.get_sigmas_linear(n_sampling_steps, self.sigma_min, self.sigma_max, device=self.device)
+        if noise_schedule_type == "ve":
+            return s.get_sigmas_ve(n_sampling_steps, self.sigma_min, self.sigma_max, device=self.device)
+        raise ValueError("Unknown noise schedule type")
+
+    # ---- beso_agent.py:390-456 --------------------------------------------------------------
+    def sample_loop(self, sigmas, x_t, state, goal, sampler_type, extra_args={}):
+        s_churn = extra_args["s_churn"] if "s_churn" in extra_args else 0
+        s_min = extra_args["s_min"] if "s_min" in extra_args else 0
+        use_scaler = extra_args["use_scaler"] if "use_scaler" in extra_args else False
+        if bool(extra_args):
+            _ = {k: extra_args[k] for k in ("s_churn", "keep_last_actions")}   # KeyError like the reference
+        scaler = self.scaler if use_scaler else None
+        if sampler_type == "heun":
+            return sampling.sample_heun(self.model, state, x_t, goal, sigmas, scaler=scaler, s_churn=s_churn,
+                                        s_tmin=s_min, disable=True)
+        if sampler_type == "euler":
+            return sampling.sample_euler(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "ddim":
+            return sampling.sample_ddim(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        raise ValueError("desired sampler type not found!")
+
+    def _core(self) -> GCDenoiser:
+        return self.model.model if isinstance(self.model, ClassifierFreeSampleModel) else self.model
+
+    def _use_ema_weights(self, on: bool):
+        """store/copy_to/restore of the reference EMA helper (beso_agent.py:343-345,380-381) without
+        moving a byte: the EMA copy is packed once into weight slot 1 and selected by pointer."""
+        if not (self.use_ema and self.ema_params is not None):
+            return
+        core = self._core()
+        if on:
+            if 1 not in core._packed:
+                live = [p.data.clone() for p in core.inner_model.parameters()]
+                for p, e in zip(core.inner_model.parameters(), self.ema_params):
+                    p.data.copy_(e)
+                core.refresh_weights(slot=1, force=True)
+                for p, v in zip(core.inner_model.parameters(), live):
+                    p.data.copy_(v)
+                core.refresh_weights(slot=0, force=True)
+            core.select_weights(1)
+        else:
+            core.select_weights(0)
+
+    def ema_updated(self):
+        """Call after the EMA shadow parameters changed so slot 1 is re-packed on next use."""
+        self._core()._packed.pop(1, None)
+
+    # ---- beso_agent.py:251-289 --------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, state, action, goal) -> float:
+        self._use_ema_weights(True)
+        self._core().eval()
+        sigmas = sampling.get_sigmas_exponential(self.num_sampling_steps, self.sigma_min, self.sigma_max, self.device)
+        x = torch.randn_like(action) * self.sigma_max
+        x_0 = self.sample_loop(sigmas, x, state, goal, self.sampler_type)
+        mse = torch.nn.functional.mse_loss(x_0, action, reduction="none").mean().item()
+        self._use_ema_weights(False)
+        return mse
+
+    def reset(self):
+        self.obs_context.clear()
+        self.action_context.clear()
+
+    # ---- beso_agent.py:297-388 --------------------------------------------------------------
+    @torch.no_grad()
+    def predict(self, batch: dict, new_sampler_type=None, get_mean=None, new_sampling_steps=None,
+                extra_args=None, noise_scheduler=None) -> torch.Tensor:
+        extra_args = {} if extra_args is None else extra_args
+        state = self.scaler.scale_input(batch["observation"].to(self.device))
+        goal = self.scaler.scale_input(batch["goal_observation"].to(self.device))
+        n_steps = new_sampling_steps if new_sampling_steps is not None else self.num_sampling_steps
+        sampler_type = new_sampler_type if new_sampler_type is not None else self.sampler_type
+        self.obs_context.append(state)
+        input_state = torch.stack(tuple(self.obs_context), dim=1)
+        if goal.dim() == 2:
+            goal = goal.unsqueeze(0)
+        self._use_ema_weights(True)
+        self._core().eval()
+        sigmas = self.get_noise_schedule(n_steps, noise_scheduler or self.noise_scheduler)
+        x = torch.randn((len(input_state), 1, self._core().config.act_dim), device=self.device) * self.sigma_max
+        if len(self.action_context) > 0:                     # previously executed actions are re-denoised
+            x = torch.cat([torch.cat(tuple(self.action_context), dim=1), x], dim=1)
+        x_0 = self.sample_loop(sigmas, x, input_state, goal, sampler_type, extra_args)
+        if x_0.dim() == 3 and x_0.size(1) > 1:
+            x_0 = x_0[:, -1, :]
+        x_0 = self.scaler.clip_action(x_0)
+        self._use_ema_weights(False)
+        model_pred = self.scaler.inverse_scale_output(x_0)
+        if model_pred.dim() == 2:
+            x_0 = x_0.unsqueeze(1)
+        self.action_context.append(x_0)
+        return model_pred

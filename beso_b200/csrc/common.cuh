@@ -1,0 +1,71 @@
+// Shared declarations for libbeso_b200.so (host side of the C ABI + kernel argument structs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/beso_b200.h"
+
+namespace beso {
+
+constexpr int kMaxLayers = 16;
+constexpr int kMaxSteps = 128;   // sampler steps per launch (n_sigmas - 1)
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define BESO_CUDA(expr)                                              \
+  do {                                                               \
+    cudaError_t _e = (expr);                                         \
+    if (_e != cudaSuccess) return ::beso::cuda_fail(_e, #expr);      \
+  } while (0)
+
+extern long long g_kernel_launches;
+
+// ---- PRECISE mode: transposed fp32 weights, [K][Npad] row-major ---------------------------
+struct SimtLayer {
+  const float *ln1w, *ln1b, *ln2w, *ln2b;
+  const float *wqkv, *bqkv;   // [d][3d]  columns: q | k | v      (score_gpts.py:33-35)
+  const float *wproj, *bproj; // [d][d]
+  const float *w1, *b1;       // [d][4d]                            (mlp.0)
+  const float *w2, *b2;       // [4d][d]                            (mlp.2)
+};
+struct SimtModel {
+  int obs, act, W, G, d, L, H, hs, linear_out, act_pad, hid, hid_pad;
+  float sigma_data;
+  const float *pos;            // [G+W+1][d]
+  const float *tokw, *tokb;    // [obs][d]
+  const float *sigw, *sigb;    // [d]
+  const float *actw, *actb;    // [act][d]
+  const float *lnfw, *lnfb;
+  const float *hw0, *hb0;      // head: [d][act_pad]            (linear_output)  or [d][hid_pad]
+  const float *hw1, *hb1;      //       unused                                   or [hid_pad][act_pad]
+  SimtLayer layer[kMaxLayers];
+};
+
+// Per-launch sampler description (kernel parameter, 1.5 KB).
+struct SampleArgs {
+  int n_steps;   // 0 = single model evaluation with per-sequence sigma
+  int sampler;   // BESO_SAMPLER_*
+  float sig[kMaxSteps + 1];
+  float ca[kMaxSteps];   // DDIM: sigma_fn(t_next) / sigma_fn(t)
+  float ce[kMaxSteps];   // DDIM: expm1(-h)
+};
+
+struct SimtLaunch {
+  int B, t, S;           // S = sequences per CTA
+  uint32_t flags;
+  float cond_lambda;
+  size_t smem_bytes;
+};
+
+int simt_plan_launch(const SimtModel& m, int t, int max_smem, SimtLaunch* out);
+int simt_launch(const SimtModel& m, const SimtLaunch& L, const SampleArgs& sa, const float* state,
+                const float* goal, const float* action_or_x, const float* sigma, float* out,
+                cudaStream_t stream);
+
+// weight packing helpers (pack.cu)
+int pack_transpose(const float* src, int N, int K, float* dst, int ld_dst, int col0, cudaStream_t s);
+int pack_copy(const float* src, float* dst, int64_t n, cudaStream_t s);
+
+}  // namespace beso

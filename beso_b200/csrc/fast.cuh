@@ -1,0 +1,21 @@
+// FAST mode interface: bf16 tcgen05 fused score-GPT (fast_forward.cu).
+#pragma once
+#include "common.cuh"
+
+namespace beso {
+
+struct FastWeights {
+  void* tape = nullptr;      // bf16 B-operand blocks in consumption order, pre-swizzled for UMMA
+  float* vec = nullptr;      // fp32 vectors: biases, LayerNorm affine, embeddings tables
+  size_t tape_bytes = 0, vec_floats = 0;
+};
+
+bool fast_supported(const beso_model_desc& m);
+int fast_seqs_per_tile(const beso_model_desc& m, int t);
+int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* params, cudaStream_t st);
+void fast_free(FastWeights& w);
+int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
+                const float* state, const float* goal, const float* action_or_x, const float* sigma,
+                float* out, int B, int t, uint32_t flags, float cond_lambda, cudaStream_t st);
+
+}  // namespace beso

@@ -1,0 +1,194 @@
+"""Noise schedules and the DDIM / Euler / Heun samplers of the BESO sample loop.
+
+Same call signatures as the reference's ``gc_sampling.sample_*`` (k_diffusion/gc_sampling.py) so
+``BesoAgent.sample_loop`` (beso_agent.py:390-456) can dispatch to them unchanged.  When the model
+is a beso_b200 ``GCDenoiser`` (optionally inside ``ClassifierFreeSampleModel``) and nothing needs
+per-step Python (no callback, no scaler, no churn) the whole loop is ONE persistent kernel launch;
+otherwise the loop below runs step by step and every ``model(...)`` call is one fused launch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from .denoiser import GCDenoiser
+
+
+# ---- schedules (gc_sampling.py:22-95): O(n) host scalars, evaluated with the same fp32 torch ops
+def append_zero(x: torch.Tensor) -> torch.Tensor:
+    return torch.cat([x, x.new_zeros([1])])
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
+    ramp = torch.linspace(0, 1, n)
+    lo, hi = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+    return append_zero((hi + ramp * (lo - hi)) ** rho).to(device)
+
+
+def get_sigmas_exponential(n, sigma_min, sigma_max, device="cpu"):
+    return append_zero(torch.linspace(math.log(sigma_max), math.log(sigma_min), n, device=device).exp())
+
+
+def get_sigmas_linear(n, sigma_min, sigma_max, device="cpu"):
+    return append_zero(torch.linspace(sigma_max, sigma_min, n, device=device))
+
+
+def get_sigmas_ve(n, sigma_min=0.02, sigma_max=100, device="cpu"):
+    t = torch.linspace(0, n + 1, n, device=device)
+    return append_zero(torch.sqrt((sigma_max ** 2) * ((sigma_min ** 2 / sigma_max ** 2) ** (t / (n - 1)))))
+
+
+def get_sigmas_vp(n, beta_d=19.9, beta_min=0.1, eps_s=1e-3, device="cpu"):
+    t = torch.linspace(1, eps_s, n, device=device)
+    return append_zero(torch.sqrt(torch.exp(beta_d * t ** 2 / 2 + beta_min * t) - 1))
+
+
+def get_sigmas_polyexponential(n, sigma_min, sigma_max, rho=1.0, device="cpu"):
+    ramp = torch.linspace(1, 0, n, device=device) ** rho
+    return append_zero(torch.exp(ramp * (math.log(sigma_max) - math.log(sigma_min)) + math.log(sigma_min)))
+
+
+def to_d(action, sigma, denoised):
+    """Karras ODE derivative (gc_sampling.py:98-100)."""
+    return (action - denoised) / sigma.reshape(sigma.shape + (1,) * (action.ndim - sigma.ndim))
+
+
+# ---- fused dispatch -----------------------------------------------------------------------
+def _fusable(model):
+    """Returns (denoiser, cfg_lambda, uncond) if ``model`` can run inside the persistent kernel."""
+    from .cfg import ClassifierFreeSampleModel
+    if isinstance(model, GCDenoiser):
+        return model, None, False
+    if isinstance(model, ClassifierFreeSampleModel) and isinstance(model.model, GCDenoiser):
+        if model.cond:
+            return model.model, None, False
+        if model.cond_lambda == 0:
+            return model.model, None, True
+        return model.model, float(model.cond_lambda), False
+    return None
+
+
+def _try_fused(name, model, state, action, goal, sigmas, scaler, extra_args, callback, churn, coef=None):
+    if callback is not None or scaler is not None or churn or extra_args:
+        return None
+    f = _fusable(model)
+    if f is None or not action.is_cuda or len(sigmas) < 2 or len(sigmas) > 129:
+        return None
+    den, lam, uncond = f
+    if den.inner_model.training and den.inner_model.cond_mask_prob > 0:
+        return None                       # goal masking draws from the RNG every call
+    return den.sample(name, sigmas, state, action, goal, cfg_lambda=lam, uncond=uncond, coef=coef)
+
+
+def ddim_coefficients(sigmas: torch.Tensor) -> torch.Tensor:
+    """Per-step (sigma_fn(t_next)/sigma_fn(t), expm1(-h)) evaluated with the reference's own fp32
+    tensor ops (gc_sampling.py:911-923) so the kernel applies bit-identical scalars."""
+    s = sigmas.detach().float().cpu()
+    t, t_next = s[:-1].log().neg(), s[1:].log().neg()
+    h = t_next - t
+    return torch.stack([t_next.neg().exp() / t.neg().exp(), (-h).expm1()], dim=1)
+
+
+@torch.no_grad()
+def sample_ddim(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                disable=None, eta=1.0):
+    """DPM-Solver-1 / DDIM (gc_sampling.py:895-924); ``eta`` and ``scaler`` are ignored there too."""
+    fused = _try_fused("ddim", model, state, action, goal, sigmas, None, extra_args, callback, 0.0,
+                       coef=ddim_coefficients(sigmas))
+    if fused is not None:
+        return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * ones, **extra_args)
+        if callback is not None:
+            callback({"action": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        t, t_next = sigmas[i].log().neg(), sigmas[i + 1].log().neg()
+        h = t_next - t
+        action = (t_next.neg().exp() / t.neg().exp()) * action - (-h).expm1() * denoised
+    return action
+
+
+def _gamma(s_churn, n, sigma, s_tmin, s_tmax):
+    return min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sigma <= s_tmax else 0.0
+
+
+@torch.no_grad()
+def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                 disable=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, rng_parity=False):
+    """Algorithm 2 of Karras et al. without the 2nd-order correction (gc_sampling.py:167-213).
+    ``rng_parity`` keeps the reference's one ``randn_like`` draw per step in the fused path so the
+    global RNG stream advances identically (results do not depend on it when s_churn == 0)."""
+    fused = _try_fused("euler", model, state, action, goal, sigmas, scaler, extra_args, callback, s_churn)
+    if fused is not None:
+        if rng_parity:
+            for _ in range(len(sigmas) - 1):
+                torch.randn_like(action)
+        return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    n = len(sigmas) - 1
+    for i in range(n):
+        gamma = _gamma(s_churn, n, sigmas[i], s_tmin, s_tmax)
+        eps = torch.randn_like(action) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * ones, **extra_args)
+        d = to_d(action, sigma_hat, denoised)
+        if callback is not None:
+            callback({"x": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        action = action + d * (sigmas[i + 1] - sigma_hat)
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+@torch.no_grad()
+def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                disable=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, rng_parity=False):
+    """Algorithm 2 of Karras et al. with Heun's correction; the step onto sigma = 0 is a plain Euler
+    step (gc_sampling.py:259-314)."""
+    fused = _try_fused("heun", model, state, action, goal, sigmas, scaler, extra_args, callback, s_churn)
+    if fused is not None:
+        if rng_parity:
+            for _ in range(len(sigmas) - 1):
+                torch.randn_like(action)
+        return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    n = len(sigmas) - 1
+    for i in range(n):
+        gamma = _gamma(s_churn, n, sigmas[i], s_tmin, s_tmax)
+        eps = torch.randn_like(action) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * ones, **extra_args)
+        d = to_d(action, sigma_hat, denoised)
+        if callback is not None:
+            callback({"x": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            action = action + d * dt
+        else:
+            action_2 = action + d * dt
+            denoised_2 = model(state, action_2, goal, sigmas[i + 1] * ones, **extra_args)
+            d_2 = to_d(action_2, sigmas[i + 1], denoised_2)
+            action = action + ((d + d_2) / 2) * dt
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun}
+
+
+def n_model_evals(sampler: str, sigmas) -> int:
+    """Model evaluations per sequence for one loop (Heun: 2 per step, 1 on a final sigma = 0 step)."""
+    n = len(sigmas) - 1
+    if sampler == "heun":
+        return 2 * n - (1 if float(sigmas[-1]) == 0.0 else 0)
+    return n

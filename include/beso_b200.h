@@ -1,0 +1,163 @@
+/*
+ * beso_b200.h -- C ABI of libbeso_b200.so, the B200 (sm_100a) implementation of the BESO
+ * score-based action-denoising hot path.
+ *
+ * The reference (intuitive-robots/beso) has no FFI: its seam is duck-typed Python
+ * (Hydra `_target_` classes).  Each entry point below names the reference interface it
+ * replaces (paths relative to beso/agents/diffusion_agents/); the Python classes in
+ * beso_b200/ that mirror those interfaces are thin ctypes callers of this ABI
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain C types only; every tensor argument is a raw pointer to contiguous row-major
+ *    fp32 unless stated otherwise; "dev" pointers are device memory, "host" pointers host.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - every function returns 0 on success and a negative BESO_E_* code on failure; the
+ *    message is available from beso_last_error() (thread local).  Nothing throws.
+ *  - a plan owns packed weights and workspaces; the caller owns all inputs and outputs.
+ *    A plan is bound to one device and is not re-entrant.
+ *  - no hidden device synchronisation except in the *_host entry points, which return
+ *    after their result has landed in host memory.
+ */
+#ifndef BESO_B200_H_
+#define BESO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BESO_ABI_VERSION 1
+
+enum {
+  BESO_OK = 0,
+  BESO_E_INVALID = -1,     /* bad argument / unsupported shape                 */
+  BESO_E_CUDA = -2,        /* CUDA runtime error (text in beso_last_error)      */
+  BESO_E_UNSUPPORTED = -3, /* valid request, but not by the selected mode       */
+  BESO_E_NOT_PACKED = -4,  /* plan has no weights yet                           */
+  BESO_E_NCCL = -5
+};
+
+/* Arithmetic mode of the score-GPT GEMMs. */
+enum {
+  BESO_MODE_PRECISE = 0, /* fp32 CUDA-core FMA; meets rtol 1e-3 / atol 1e-5 vs the fp32 reference   */
+  BESO_MODE_FAST = 1     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM;
+                            fp32 LayerNorm / softmax / GELU / residual.  d=256, head_dim=64 only.   */
+};
+
+/* gc_sampling.py sampler selected by BesoAgent.sample_loop (beso_agent.py:419-455). */
+enum {
+  BESO_SAMPLER_DDIM = 0,  /* gc_sampling.py:895-924 */
+  BESO_SAMPLER_EULER = 1, /* gc_sampling.py:167-213 (s_churn = 0) */
+  BESO_SAMPLER_HEUN = 2   /* gc_sampling.py:259-314 (s_churn = 0) */
+};
+
+/* flags */
+#define BESO_FLAG_UNCOND 1u /* DiffusionGPT.forward(uncond=True): goals zeroed (score_gpts.py:301-302)      */
+#define BESO_FLAG_CFG 2u    /* ClassifierFreeSampleModel.forward (classifier_free_sampler.py:35-49):
+                               out_u + cond_lambda * (out_c - out_u), both branches in one launch           */
+#define BESO_FLAG_INNER 4u  /* return DiffusionGPT.forward(state, action, goal, sigma) itself, i.e. without
+                               the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
+
+/* Constructor arguments of DiffusionGPT (k_diffusion/score_gpts.py:121-139) and
+ * GCDenoiser.sigma_data (k_diffusion/score_wrappers.py:26-29). */
+typedef struct beso_model_desc {
+  int32_t obs_dim;          /* state_dim                          */
+  int32_t act_dim;          /* action_dim                         */
+  int32_t window;           /* obs_seq_len  W                     */
+  int32_t goal_len;         /* goal_seq_len G                     */
+  int32_t d;                /* embed_dim                          */
+  int32_t n_layers;
+  int32_t n_heads;
+  int32_t linear_output;    /* 1: action_pred = Linear(d, act)    */
+  int32_t goal_conditioned; /* 0: goal tokens dropped             */
+  float sigma_data;
+} beso_model_desc;
+
+typedef struct beso_plan beso_plan;
+typedef struct beso_comm beso_comm;
+
+const char* beso_last_error(void);
+int beso_abi_version(void);
+
+/* Number of parameter tensors / scalars in nn.Module.parameters() order of the reference
+ * (score_gpts.py:150-190).  Returns <0 on an invalid description. */
+int beso_param_count(const beso_model_desc* desc);
+int64_t beso_param_numel(const beso_model_desc* desc, int index);
+int64_t beso_param_total(const beso_model_desc* desc);
+
+/* Replaces: hydra.utils.instantiate(GCDenoiser(DiffusionGPT(...))).to(device)
+ * (score_wrappers.py:26-29, base_agent.py:31). */
+int beso_plan_create(const beso_model_desc* desc, int device, beso_plan** out);
+int beso_plan_destroy(beso_plan* plan);
+
+/* Replaces: load_state_dict / optimizer.step / EMA copy_to making new weights visible to
+ * forward (beso_agent.py:343-345,380-381,462).  `params_dev` holds beso_param_count()
+ * device pointers to the fp32 parameter tensors in parameters() order.  Re-callable; the
+ * packed images (transposed fp32 for PRECISE, bf16 UMMA tape for FAST) are rebuilt on
+ * `stream`.  `slot` selects one of two resident weight sets (0 = raw, 1 = EMA) so that the
+ * EMA swap in predict()/evaluate() does not force a re-pack. */
+int beso_plan_pack_weights(beso_plan* plan, int slot, const float* const* params_dev, int n_params,
+                           void* stream);
+int beso_plan_select_weights(beso_plan* plan, int slot);
+
+/* Replaces: GCDenoiser.forward (score_wrappers.py:81-96) -> DiffusionGPT.forward
+ * (score_gpts.py:272-358); with BESO_FLAG_CFG also ClassifierFreeSampleModel.forward.
+ *   state (B,t,obs)  action (B,t,act)  goal (B,G,obs)  sigma (B)  ->  out (B,t,act)
+ * 1 <= t <= window.  One kernel launch. */
+int beso_denoise_fwd(beso_plan* plan, int mode, const float* state_dev, const float* action_dev,
+                     const float* goal_dev, const float* sigma_dev, float* out_dev, int B, int t,
+                     uint32_t flags, float cond_lambda, void* stream);
+
+/* Replaces: gc_sampling.sample_ddim / sample_euler / sample_heun called from
+ * BesoAgent.sample_loop (beso_agent.py:390-456) with s_churn = 0, scaler = None,
+ * callback = None.  The whole loop over `n_sigmas - 1` steps is ONE persistent kernel
+ * launch; x_inout (B,t,act) holds x_t on entry and x_0 on return.
+ *   sigmas_host: n_sigmas fp32 noise levels (last one may be 0), as from get_sigmas_*.
+ *   coef_host:   DDIM only, 2*(n_sigmas-1) fp32: for step i, [2i] = sigma_fn(t_next)/sigma_fn(t)
+ *                and [2i+1] = expm1(-h) evaluated by the caller exactly as gc_sampling.py:921-923
+ *                does (NULL = evaluate on the host in this library with the same fp32 formulas). */
+int beso_sample_loop(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
+                     const float* coef_host, const float* state_dev, const float* goal_dev,
+                     float* x_inout_dev, int B, int t, uint32_t flags, float cond_lambda, void* stream);
+
+/* Same two calls with HOST buffers: inputs are staged through plan-owned pinned and device
+ * buffers, the kernel runs on `stream`, the result is copied back and the call returns once it
+ * is in `out_host` / `x_inout_host`.  This is the end-to-end path bench.py times as "e2e". */
+int beso_denoise_fwd_host(beso_plan* plan, int mode, const float* state_host, const float* action_host,
+                          const float* goal_host, const float* sigma_host, float* out_host, int B, int t,
+                          uint32_t flags, float cond_lambda, void* stream);
+int beso_sample_loop_host(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
+                          const float* coef_host, const float* state_host, const float* goal_host,
+                          float* x_inout_host, int B, int t, uint32_t flags, float cond_lambda,
+                          void* stream);
+
+/* Replaces: GCDenoiser.loss (score_wrappers.py:45-79) + loss.backward() (beso_agent.py:236-240).
+ *   action = clean action a; noise n; sigma (B).  goal_keep_dev: optional (B,G,obs) {0,1} mask =
+ *   1 - Bernoulli(cond_mask_prob) drawn by the caller (score_gpts.py:360-371), NULL = keep all.
+ *   loss_dev: 1 fp32.  flat_grad_dev: beso_param_total() fp32 in parameters() order, overwritten
+ *   (NULL = forward only).  Dropout probabilities must be 0. */
+int beso_loss_fwd_bwd(beso_plan* plan, const float* state_dev, const float* action_dev,
+                      const float* goal_dev, const float* noise_dev, const float* sigma_dev,
+                      const float* goal_keep_dev, float* loss_dev, float* flat_grad_dev, int B,
+                      uint32_t flags, void* stream);
+
+/* Data-parallel gradient step (BASELINE config 4): one all-reduce(sum) of the flat fp32 gradient
+ * over NCCL on NVLink, scaled by 1/world.  The reference has no distributed path; this is the
+ * exchange step of SURVEY.md 8e.  unique_id: 128 bytes from beso_comm_unique_id on rank 0. */
+int beso_comm_unique_id(char* out128);
+int beso_comm_init(int rank, int world, const char* unique_id128, int device, beso_comm** out);
+int beso_comm_destroy(beso_comm* comm);
+int beso_allreduce_grads(beso_comm* comm, float* flat_grad_dev, size_t n, float scale, void* stream);
+
+/* Introspection used by tests and bench.py. */
+int64_t beso_kernel_launches(void);                /* kernels launched by this library so far   */
+int beso_plan_rows_per_cta(beso_plan* plan, int mode, int t); /* sequences handled per CTA      */
+int beso_device_sm_count(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BESO_B200_H_ */

@@ -1,0 +1,253 @@
+"""GPU: the CUDA path (through the C ABI) against the golden vectors made by the real reference,
+against the oracle on seeded inputs, and through size-independent properties at full size.
+
+Tolerances (written here, never loosened silently):
+  precise mode  rtol 1e-3, atol 1e-5   -- the north-star tolerance, against the fp32 reference
+  fast mode     rtol 2e-2, atol 2e-2   -- bf16 tensor-core operands (the reference's own
+                                          bf16 autocast shows max |err| 4.5e-3..2.3e-2 vs its fp32 self)
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+from conftest import golden_weights, load_golden, to_oracle_cfg
+from beso_b200 import K256, T16, _lib, sampling
+from beso_b200.agent import BesoAgent
+from beso_b200.cfg import ClassifierFreeSampleModel
+from beso_b200.denoiser import build_denoiser
+from beso_b200.synth import synthetic_inputs, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=2e-2, atol=2e-2)}
+FAST_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256"}
+FWD = ["fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_kitchen", "fwd_small_push",
+       "fwd_mlp_head", "fwd_no_goal"]
+
+
+def fast_available():
+    lib = _lib.lib()
+    h = C.c_void_p()
+    desc = _lib.ModelDesc.from_config(K256)
+    _lib.check(lib.beso_plan_create(C.byref(desc), 0, C.byref(h)))
+    ok = lib.beso_plan_rows_per_cta(h, _lib.MODE_FAST, 10) > 0
+    lib.beso_plan_destroy(h)
+    return ok
+
+
+def modes_for(name):
+    return ["precise"] + (["fast"] if name in FAST_SHAPES else [])
+
+
+def cuda(a, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in a.items()}
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_forward_matches_reference_golden(name, cuda_device):
+    cfg, meta, a = load_golden(name)
+    sd = golden_weights(cfg, meta)
+    g = cuda(a, cuda_device)
+    for mode in modes_for(name):
+        if mode == "fast" and not fast_available():
+            pytest.skip("fast mode not built")
+        m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+        launches = _lib.lib().beso_kernel_launches()
+        out = m(g["state"], g["action"], g["goal"], g["sigma"])
+        assert _lib.lib().beso_kernel_launches() == launches + 1          # one launch per denoise step
+        torch.testing.assert_close(out.cpu(), a["out"], **TOL[mode])
+        if "out_uncond" in a:
+            out_u = m(g["state"], g["action"], g["goal"], g["sigma"], uncond=True)
+            torch.testing.assert_close(out_u.cpu(), a["out_uncond"], **TOL[mode])
+            inner = m.inner_model(g["state"], g["action"], g["goal"], g["sigma"])
+            torch.testing.assert_close(inner.cpu(), a["inner"], **TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_samplers_match_reference_golden(mode, cuda_device):
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    cfg, meta, a = load_golden("samplers_K256")
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=golden_weights(cfg, meta))
+    g = cuda(a, cuda_device)
+    for n in (1, 3, 5):
+        for s in ("ddim", "euler", "heun"):
+            launches = _lib.lib().beso_kernel_launches()
+            got = sampling.SAMPLERS[s](m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{n}"], disable=True)
+            assert _lib.lib().beso_kernel_launches() == launches + 1      # whole loop = one persistent kernel
+            torch.testing.assert_close(got.cpu(), a[f"{s}_{n}"], **TOL[mode])
+    got = sampling.sample_heun(m, g["state"], g["x_t"], g["goal"], a["sigmas_karras_4"])
+    torch.testing.assert_close(got.cpu(), a["heun_karras_4"], **TOL[mode])
+    assert torch.equal(g["x_t"].cpu(), a["x_t"])                          # caller's x_t is never written
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_classifier_free_guidance_matches_reference_golden(mode, cuda_device):
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    cfg, meta, a = load_golden("samplers_K256")
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=golden_weights(cfg, meta))
+    g = cuda(a, cuda_device)
+    for lam in (0.0, 1.0, 1.5, 2.0):
+        tag = str(lam).replace(".", "p")
+        w = ClassifierFreeSampleModel(m, cond_lambda=lam)
+        launches = _lib.lib().beso_kernel_launches()
+        got = w(g["state"], g["action"], g["goal"], g["sigma"])
+        assert _lib.lib().beso_kernel_launches() == launches + 1          # both branches fused
+        torch.testing.assert_close(got.cpu(), a[f"cfg_fwd_{tag}"], **TOL[mode])
+        got = sampling.sample_heun(w, g["state"], g["x_t"], g["goal"], a["sigmas_cfg_4"])
+        torch.testing.assert_close(got.cpu(), a[f"cfg_heun4_{tag}"], **TOL[mode])
+        got = sampling.sample_ddim(w, g["state"], g["x_t"], g["goal"], a["sigmas_cfg_4"])
+        torch.testing.assert_close(got.cpu(), a[f"cfg_ddim4_{tag}"], **TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_cfg1_batch64_against_oracle(mode, cuda_device):
+    """BASELINE config 1: K256 single denoise step, batch 64, parity against the CPU oracle."""
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    from oracle import beso_oracle as O
+    cfg = K256
+    sd = synthetic_state_dict(cfg, seed=21)
+    x = synthetic_inputs(cfg, 64, seed=22)
+    with torch.no_grad():
+        want = O.denoiser_forward(sd, to_oracle_cfg(cfg), x["state"], x["action"], x["goal"], x["sigma"])
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+    g = cuda(x, cuda_device)
+    got = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
+    torch.testing.assert_close(got, want, **TOL[mode])
+    err = (got - want).abs()
+    print(f"[{mode}] cfg1 max|err|={err.max():.3e} mean|err|={err.mean():.3e} "
+          f"within(1e-3,1e-5)={(err <= 1e-5 + 1e-3 * want.abs()).float().mean():.4f}")
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_python_loop_fallback_equals_fused_loop(mode, cuda_device):
+    """With a callback the sampler runs step by step (one fused launch per model call) and must
+    agree with the persistent kernel; the callback sees every step."""
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    cfg = K256
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=synthetic_state_dict(cfg, 3))
+    g = cuda(synthetic_inputs(cfg, 16, seed=4), cuda_device)
+    sig = sampling.get_sigmas_exponential(4, 0.005, 1.0)
+    for s in ("ddim", "euler", "heun"):
+        seen = []
+        fused = sampling.SAMPLERS[s](m, g["state"], g["noise"], g["goal"], sig)
+        loop = sampling.SAMPLERS[s](m, g["state"], g["noise"], g["goal"], sig.to(cuda_device),
+                                    callback=lambda d: seen.append(int(d["i"])))
+        assert seen == [0, 1, 2, 3]
+        torch.testing.assert_close(fused, loop, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_full_size_properties_cfg2(mode, cuda_device):
+    """BASELINE config 2 (50-step DDIM, batch 512): sequences are independent, so the result must be
+    (a) deterministic, (b) equivariant under a batch permutation, (c) unchanged when the batch is
+    split, (d) equal to the first rows of the oracle on a small slice."""
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    from oracle import beso_oracle as O
+    cfg = K256
+    sd = synthetic_state_dict(cfg, 5)
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+    x = synthetic_inputs(cfg, 512, seed=6)
+    g = cuda(x, cuda_device)
+    sig = sampling.get_sigmas_exponential(50, 0.005, 1.0)
+    full = sampling.sample_ddim(m, g["state"], g["noise"], g["goal"], sig)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, sampling.sample_ddim(m, g["state"], g["noise"], g["goal"], sig))
+    perm = torch.randperm(512, generator=torch.Generator().manual_seed(0)).to(cuda_device)
+    permuted = sampling.sample_ddim(m, g["state"][perm], g["noise"][perm], g["goal"][perm], sig)
+    assert torch.equal(permuted, full[perm])
+    halves = torch.cat([sampling.sample_ddim(m, g["state"][:200], g["noise"][:200], g["goal"][:200], sig),
+                        sampling.sample_ddim(m, g["state"][200:], g["noise"][200:], g["goal"][200:], sig)])
+    assert torch.equal(halves, full)
+    with torch.no_grad():
+        want = O.sample_ddim(sd, to_oracle_cfg(cfg), x["state"][:4], x["noise"][:4], x["goal"][:4], sig)
+    torch.testing.assert_close(full[:4].cpu(), want, **TOL[mode])
+
+
+def test_uncond_equals_zeroed_goals(cuda_device):
+    cfg = T16
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=synthetic_state_dict(cfg, 7))
+    g = cuda(synthetic_inputs(cfg, 9, seed=8), cuda_device)
+    a = m(g["state"], g["action"], g["goal"], g["sigma"], uncond=True)
+    b = m(g["state"], g["action"], torch.zeros_like(g["goal"]), g["sigma"])
+    assert torch.equal(a, b)
+
+
+def test_host_buffer_entry_points_equal_device_entry_points(cuda_device):
+    cfg = K256
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=synthetic_state_dict(cfg, 9))
+    x = synthetic_inputs(cfg, 10, seed=10)
+    g = cuda(x, cuda_device)
+    dev_out = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
+    lib, plan = _lib.lib(), m._plan
+    out = torch.empty_like(x["action"])
+    _lib.check(lib.beso_denoise_fwd_host(plan, _lib.MODE_PRECISE, x["state"].data_ptr(), x["action"].data_ptr(),
+                                         x["goal"].data_ptr(), x["sigma"].data_ptr(), out.data_ptr(), 10, 10, 0,
+                                         0.0, None))
+    assert torch.equal(out, dev_out)
+    sig = sampling.get_sigmas_exponential(3, 0.005, 1.0)
+    dev_s = sampling.sample_heun(m, g["state"], g["noise"], g["goal"], sig).cpu()
+    xs = x["noise"].clone()
+    _lib.check(lib.beso_sample_loop_host(plan, _lib.MODE_PRECISE, _lib.SAMPLER_HEUN, _lib.float_array(sig.tolist()),
+                                         4, None, x["state"].data_ptr(), x["goal"].data_ptr(), xs.data_ptr(), 10, 10,
+                                         0, 0.0, None))
+    torch.testing.assert_close(xs, dev_s, rtol=0, atol=0)
+
+
+def test_weight_repack_on_change_and_ema_slots(cuda_device):
+    cfg = K256
+    sd_raw, sd_ema = synthetic_state_dict(cfg, 11), synthetic_state_dict(cfg, 12)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd_raw)
+    g = cuda(synthetic_inputs(cfg, 4, seed=13), cuda_device)
+    a = m(g["state"], g["action"], g["goal"], g["sigma"])
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.01)                                   # optimizer-like in-place update: version bump
+    b = m(g["state"], g["action"], g["goal"], g["sigma"])
+    assert not torch.equal(a, b)
+    m.load_state_dict(sd_raw)
+    assert torch.equal(m(g["state"], g["action"], g["goal"], g["sigma"]), a)
+    ema = [v.to(cuda_device) for k, v in sd_ema.items() if not k.endswith("attn.mask")]
+    agent = BesoAgent(m, device=cuda_device, window_size=cfg.window, use_ema=True, ema_params=ema,
+                      sampler_type="ddim", num_sampling_steps=3)
+    ref_ema = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd_ema)
+    torch.manual_seed(0)
+    mse_a = agent.evaluate(g["state"], g["clean"], g["goal"])
+    torch.manual_seed(0)
+    mse_b = BesoAgent(ref_ema, device=cuda_device, window_size=cfg.window, num_sampling_steps=3).evaluate(
+        g["state"], g["clean"], g["goal"])
+    assert mse_a == mse_b
+    assert torch.equal(m(g["state"], g["action"], g["goal"], g["sigma"]), a)      # raw weights restored
+
+
+def test_predict_rollout_context_growth(cuda_device):
+    """predict() at batch 1 grows t from 1 to W (beso_agent.py:323-325,357-362)."""
+    cfg = T16
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=synthetic_state_dict(cfg, 14))
+    agent = BesoAgent(m, device=cuda_device, window_size=cfg.window, num_sampling_steps=3)
+    torch.manual_seed(1)
+    for step in range(cfg.window + 3):
+        obs = torch.randn(1, cfg.obs_dim)
+        goal = torch.randn(cfg.goal_len, cfg.obs_dim)
+        act = agent.predict({"observation": obs, "goal_observation": goal}, extra_args={})
+        assert act.shape[-1] == cfg.act_dim and torch.isfinite(act).all()
+        assert len(agent.obs_context) == min(step + 1, cfg.window)
+    agent.reset()
+    assert len(agent.obs_context) == 0 and len(agent.action_context) == 0
+
+
+def test_error_paths(cuda_device):
+    cfg = K256
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=synthetic_state_dict(cfg, 15))
+    g = cuda(synthetic_inputs(cfg, 2, seed=16), cuda_device)
+    with pytest.raises((AssertionError, ValueError)):
+        m(torch.zeros(2, 30, 60, device=cuda_device), torch.zeros(2, 30, 9, device=cuda_device), g["goal"], g["sigma"])
+    with pytest.raises(ValueError):
+        m(g["state"], g["action"][:, :5], g["goal"], g["sigma"])
+    with pytest.raises(TypeError):
+        m(g["state"], g["action"], g["goal"], g["sigma"], bogus=True)

@@ -1,0 +1,156 @@
+"""CPU: host logic, the C-ABI surface and the no-fallback guarantee (no GPU compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_weights, load_golden
+from beso_b200 import B256, K256, KITCHEN_CKPT, T16, _lib, sampling
+from beso_b200.agent import BesoAgent
+from beso_b200.cfg import ClassifierFreeSampleModel
+from beso_b200.denoiser import DiffusionGPT, GCDenoiser, build_denoiser
+from beso_b200.synth import synthetic_state_dict
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "beso_b200.h")).read()
+    declared = set(re.findall(r"\b(beso_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.beso_abi_version() == 1
+
+
+@pytest.mark.parametrize("cfg", [K256, B256, T16, KITCHEN_CKPT])
+def test_param_table_matches_module(cfg):
+    lib = _lib.lib()
+    desc = _lib.ModelDesc.from_config(cfg)
+    m = build_denoiser(cfg, "cpu")
+    params = list(m.get_params())
+    assert lib.beso_param_count(C.byref(desc)) == len(params)
+    assert lib.beso_param_total(C.byref(desc)) == sum(p.numel() for p in params) == cfg.n_params()
+    for i, p in enumerate(params):
+        assert lib.beso_param_numel(C.byref(desc), i) == p.numel()
+    assert [n for n, _ in m.named_parameters()] == [n for n, _ in cfg.param_shapes()]
+
+
+def test_invalid_descriptions_are_rejected():
+    lib = _lib.lib()
+    bad = _lib.ModelDesc(60, 9, 10, 2, 250, 4, 4, 1, 1, 0.5)      # d % n_heads != 0
+    assert lib.beso_param_count(C.byref(bad)) == -1
+    assert b"invalid" in lib.beso_last_error()
+    h = C.c_void_p()
+    assert lib.beso_plan_create(C.byref(bad), 0, C.byref(h)) == -1
+
+
+def test_state_dict_schema_matches_reference_fixture_weights():
+    cfg, meta, _ = load_golden("fwd_K256")
+    sd = golden_weights(cfg, meta)
+    m = build_denoiser(cfg, "cpu")
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    assert m.state_dict()["inner_model.blocks.0.attn.mask"].shape == (1, 1, 23, 23)
+    assert m.inner_model.pos_emb.shape == (1, 13, 256)            # seq_size = G + W + 1, last row unused
+
+
+def test_state_dict_schema_matches_live_reference():
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("/root/reference not present")
+    ns = ref_import.load()
+    for cfg in (K256, KITCHEN_CKPT):
+        ref = ref_import.make_reference_model(ns, cfg)
+        ours = build_denoiser(cfg, "cpu")
+        assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == \
+               [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+        assert [n for n, _ in ref.named_parameters()] == [n for n, _ in ours.named_parameters()]
+    sd = torch.load(os.path.join(ref_import.REF_ROOT, "trained_models/kitchen/c_beso_1/model_state_dict.pth"),
+                    map_location="cpu")
+    build_denoiser(KITCHEN_CKPT, "cpu").load_state_dict(sd, strict=True)
+
+
+def test_hydra_style_instantiation():
+    spec = dict(_target_="beso_b200.denoiser.DiffusionGPT", state_dim=16, device="cpu", goal_conditioned=True,
+                action_dim=2, embed_dim=64, embed_pdrob=0, attn_pdrop=0.1, resid_pdrop=0.1, n_layers=2, n_heads=4,
+                goal_seq_len=1, obs_seq_len=5, sigma_vocab_size=3, time_embedding_fn={"x": 1}, goal_drop=0.1,
+                linear_output=True)
+    m = GCDenoiser(spec, sigma_data=0.5)
+    assert isinstance(m.inner_model, DiffusionGPT) and m.inner_model.block_size == 12
+    assert m.config.sigma_data == 0.5 and m.config.n_tokens() == 12
+    m.training = True                         # the agent assigns the attribute directly (beso_agent.py:230)
+    m.min_action = 0.0                        # arbitrary attribute set (beso_agent.py:116-117)
+    assert len(list(m.get_params())) == len(list(m.parameters()))
+
+
+def test_no_cpu_fallback():
+    m = build_denoiser(K256, "cpu")
+    with pytest.raises(_lib.BesoLibraryError):
+        m(torch.zeros(1, 10, 60), torch.zeros(1, 10, 9), torch.zeros(1, 2, 60), torch.ones(1))
+    with pytest.raises(_lib.BesoLibraryError):
+        sampling.sample_ddim(ClassifierFreeSampleModel(m, 2.0), torch.zeros(1, 10, 60), torch.zeros(1, 10, 9),
+                             torch.zeros(1, 2, 60), sampling.get_sigmas_exponential(3, 0.005, 1.0))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "beso_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("beso_oracle", "oracle") or f == "__none__", f
+                assert "/root/reference" not in src, f
+
+
+def test_schedules_match_reference_fixture():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "schedules.npz"))
+    for n in (1, 3, 10, 50):
+        np.testing.assert_array_equal(sampling.get_sigmas_exponential(n, 0.005, 1.0).numpy(), z[f"exponential_{n}"])
+        np.testing.assert_array_equal(sampling.get_sigmas_karras(n, 0.005, 1.0, 5.0).numpy(), z[f"karras_{n}"])
+        np.testing.assert_array_equal(sampling.get_sigmas_linear(n, 0.005, 1.0).numpy(), z[f"linear_{n}"])
+        np.testing.assert_array_equal(sampling.get_sigmas_vp(n).numpy(), z[f"vp_{n}"])
+        if n > 1:
+            np.testing.assert_array_equal(sampling.get_sigmas_ve(n, 0.005, 1.0).numpy(), z[f"ve_{n}"])
+
+
+def test_ddim_coefficients_last_step_is_exact_replacement():
+    c = sampling.ddim_coefficients(sampling.get_sigmas_exponential(5, 0.005, 1.0))
+    assert c.shape == (5, 2)
+    assert c[-1, 0] == 0.0 and c[-1, 1] == -1.0          # x <- 0 * x - (-1) * denoised
+
+
+def test_eval_counts():
+    s = sampling.get_sigmas_exponential(10, 0.005, 1.0)
+    assert sampling.n_model_evals("ddim", s) == 10 and sampling.n_model_evals("heun", s) == 19
+
+
+def test_python_loop_samplers_against_oracle_with_a_torch_model():
+    """The step-by-step fallback loops (used with callbacks / churn) follow the reference update
+    rules: run them around the oracle's forward and compare with the reference fixtures."""
+    from conftest import to_oracle_cfg
+    from oracle import beso_oracle as O
+    cfg, meta, a = load_golden("samplers_K256")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    model = lambda s, x, g, sig, **kw: O.denoiser_forward(sd, oc, s, x, g, sig, **kw)   # noqa: E731
+    seen = []
+    for name in ("ddim", "euler", "heun"):
+        got = sampling.SAMPLERS[name](model, a["state"], a["x_t"], a["goal"], a["sigmas_5"],
+                                      callback=lambda d: seen.append(d["i"]))
+        torch.testing.assert_close(got, a[f"{name}_5"], rtol=1e-5, atol=1e-6)
+    assert seen[:5] == [0, 1, 2, 3, 4]
+
+
+def test_agent_dispatch_and_errors():
+    m = build_denoiser(K256, "cpu")
+    agent = BesoAgent(m, device="cpu", window_size=10)
+    with pytest.raises(ValueError):
+        agent.sample_loop(torch.ones(3), torch.zeros(1, 10, 9), torch.zeros(1, 10, 60), torch.zeros(1, 2, 60), "nope")
+    with pytest.raises(ValueError):
+        agent.get_noise_schedule(3, "nope")
+    with pytest.raises(KeyError):               # non-empty extra_args must hold both keys
+        agent.sample_loop(torch.ones(3), torch.zeros(1, 10, 9), torch.zeros(1, 10, 60), torch.zeros(1, 2, 60),
+                          "ddim", {"s_churn": 1})
+    assert torch.equal(agent.get_noise_schedule(3, "exponential"), sampling.get_sigmas_exponential(3, 0.005, 1.0))
