@@ -53,6 +53,7 @@ def test_forward_matches_reference_golden(name, cuda_device):
         if mode == "fast" and not fast_available():
             pytest.skip("fast mode not built")
         m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+        m.refresh_weights()                                               # weight packing is not part of a step
         launches = _lib.lib().beso_kernel_launches()
         out = m(g["state"], g["action"], g["goal"], g["sigma"])
         assert _lib.lib().beso_kernel_launches() == launches + 1          # one launch per denoise step
@@ -71,6 +72,7 @@ def test_samplers_match_reference_golden(mode, cuda_device):
     cfg, meta, a = load_golden("samplers_K256")
     m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=golden_weights(cfg, meta))
     g = cuda(a, cuda_device)
+    m.refresh_weights()
     for n in (1, 3, 5):
         for s in ("ddim", "euler", "heun"):
             launches = _lib.lib().beso_kernel_launches()
@@ -89,6 +91,7 @@ def test_classifier_free_guidance_matches_reference_golden(mode, cuda_device):
     cfg, meta, a = load_golden("samplers_K256")
     m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=golden_weights(cfg, meta))
     g = cuda(a, cuda_device)
+    m.refresh_weights()
     for lam in (0.0, 1.0, 1.5, 2.0):
         tag = str(lam).replace(".", "p")
         w = ClassifierFreeSampleModel(m, cond_lambda=lam)
