@@ -156,6 +156,9 @@ int beso_allreduce_grads(beso_comm* comm, float* flat_grad_dev, size_t n, float 
 int64_t beso_kernel_launches(void);                /* kernels launched by this library so far   */
 int beso_plan_rows_per_cta(beso_plan* plan, int mode, int t); /* sequences handled per CTA      */
 int beso_device_sm_count(int device);
+/* Diagnostics: when trace_dev != NULL, FAST-mode launches dump the fp32 residual stream of tile 0,
+ * first evaluation, as seen by every LayerNorm pass: (2 * n_layers + 1) x 128 x 256 floats. */
+int beso_debug_set_trace(float* trace_dev);
 
 #ifdef __cplusplus
 }

@@ -94,10 +94,14 @@ def causal_self_attention(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: in
 
 
 # score_gpts.py:96-115
-def block(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int) -> Tensor:
+def block(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int, trace=None) -> Tensor:
     d = x.shape[-1]
+    if trace is not None:
+        trace.append(x)
     h = F.layer_norm(x, (d,), sd[pre + "ln1.weight"], sd[pre + "ln1.bias"], 1e-5)
     x = x + causal_self_attention(h, sd, pre + "attn.", n_head)
+    if trace is not None:
+        trace.append(x)
     h = F.layer_norm(x, (d,), sd[pre + "ln2.weight"], sd[pre + "ln2.bias"], 1e-5)
     h = F.linear(h, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"])
     h = F.gelu(h)                                                 # nn.GELU() default = exact erf
@@ -108,7 +112,7 @@ def block(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int) -> Tensor:
 # score_gpts.py:272-358
 def gpt_forward(sd: Dict[str, Tensor], cfg: OracleCfg, states: Tensor, actions: Tensor,
                 goals: Tensor, sigma: Tensor, uncond: bool = False,
-                keep_last_actions: bool = False, goal_keep: Optional[Tensor] = None) -> Tensor:
+                keep_last_actions: bool = False, goal_keep: Optional[Tensor] = None, trace=None) -> Tensor:
     """``goal_keep`` (B,G,obs) in {0,1} restates mask_cond (score_gpts.py:360-371)
     with the Bernoulli draw made by the caller: goals * goal_keep, goal_keep = 1 - mask."""
     b, t, _ = states.size()
@@ -135,7 +139,9 @@ def gpt_forward(sd: Dict[str, Tensor], cfg: OracleCfg, states: Tensor, actions: 
     else:
         x = torch.cat([emb_t, sa_seq], dim=1)
     for l in range(cfg.n_layers):                                 # :340
-        x = block(x, sd, f"{P}blocks.{l}.", cfg.n_heads)
+        x = block(x, sd, f"{P}blocks.{l}.", cfg.n_heads, trace)
+    if trace is not None:
+        trace.append(x)       # residual stream entering ln_f
     x = F.layer_norm(x, (cfg.d,), sd[P + "ln_f.weight"], sd[P + "ln_f.bias"], 1e-5)       # :341
     x = x[:, G + 1:, :]                                           # :344
     x_len = x.size(1) // 2 if x.size(1) < 2 * cfg.window else cfg.window      # :347-351
