@@ -86,7 +86,7 @@ struct __align__(8) Fill {     // one ring fill = rows x 64 bf16 of B operand + 
 
 struct FastParams {
   const uint8_t* tape;         // per-eval weight tape
-  const Fill* prog;            // fill program (n_fills entries)
+  Fill prog[kProgEntries];     // fill program: embedding | one layer | head (kernel-parameter space)
   const float* vec;            // per layer: vecA (1536) | vecM (1792); then final vecA (1536)
   int n_fills, L, G, obs, act, T, t, S, n_tiles, B, evals;
   uint32_t flags;
@@ -94,6 +94,7 @@ struct FastParams {
   const float *state, *goal, *xin, *sigma;
   float* out;
   float* trace;                // optional debug dump of X after every LayerNorm pass (tile 0, eval 0)
+  long long* timeline;         // optional clock64 stamps of block 0, second evaluation (see tools/timeline_fast.py)
 };
 
 // ================================ device code =====================================================
@@ -103,6 +104,16 @@ __device__ __forceinline__ int prog_index(int f, int n_fills) {
   return 4 + (f - 4) % 104;
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 
 // Bounded wait: a protocol bug must not hang the GPU.  ~4 s at 2 GHz, then trap with the barrier id.
 __device__ __noinline__ void wait_timeout(uint32_t bar, uint32_t parity) {
@@ -120,7 +131,22 @@ __device__ __forceinline__ void spin_wait(uint32_t bar, uint32_t parity) {
   wait_timeout(bar, parity);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU without erff(): with z = |x| / sqrt(2), 0.5 * erfc(z) = 2^q(z) to 2.1e-6 absolute for a
+// degree-5 q fitted on [0, 6] (q -> -inf beyond), so
+//   gelu(x) = x * Phi(x) = max(x, 0) - |x| * 2^q(z)          |error| <= 5.9e-7 absolute
+// 9 instructions (5 FFMA Horner, 1 MUFU.EX2) instead of ~46 for erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752440f;
+  float q = fmaf(-2.784754615e-03f, z, 2.889863029e-02f);
+  q = fmaf(q, z, -1.476386487e-01f);
+  q = fmaf(q, z, -9.191277623e-01f);
+  q = fmaf(q, z, -1.627753854e+00f);
+  q = fmaf(q, z, -1.000006080e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-ax, e, fmaxf(x, 0.f));
+}
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -141,13 +167,17 @@ struct Compute {
   uint32_t sbase, tmem;
   int wq, lane, hf, row, ctid;       // TMEM lane quadrant, lane, column half, tile row, compute thread id
   uint32_t phases;                   // parity bit per barrier id this role waits on
+  long long* tl;                     // timeline cursor (nullptr = off)
+  __device__ void stamp() { if (tl != nullptr) *tl++ = clock64(); }
   __device__ uint32_t bar(int id) const { return sbase + kSmBars + id * 8; }
   __device__ void wait(int id) { spin_wait(bar(id), (phases >> id) & 1u); phases ^= 1u << id; }
   __device__ void arrive(int id) const { __syncwarp(); if (lane == 0) mbar_arrive(bar(id)); }
   __device__ uint32_t lane_addr(uint32_t col) const { return tmem + ((uint32_t)(wq * 32) << 16) + col; }
 };
 
-// X <- X + pend ; A <- bf16(LayerNorm(X) * w + b).   vec = [pend | w | b] in shared memory.
+// A <- bf16(LayerNorm(X + pend) * w + b).   vec = [pend | w | b] in shared memory.
+// X (TMEM) is only read: every projection / MLP bias is added to X up front by the embedding GEMM and
+// `pend` holds minus the biases that are not due yet at this point of the network (see fast_pack).
 __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int trace_slot) {
   float v[32];
   float sum = 0.f, sq = 0.f;
@@ -164,14 +194,12 @@ __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int t
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
-    tmem_st32(c.lane_addr(kColX + col), v);
     if (p.trace != nullptr && blockIdx.x == 0 && trace_slot >= 0) {
       float* tr = p.trace + ((size_t)trace_slot * kRows + c.row) * kD + col;
 #pragma unroll
       for (int i = 0; i < 32; ++i) tr[i] = v[i];
     }
   }
-  tmem_wait_st();
   float2* stats = reinterpret_cast<float2*>(c.sm + kSmStats);
   stats[c.hf * kRows + c.row] = make_float2(sum, sq);
   compute_sync();
@@ -188,12 +216,13 @@ __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int t
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
+      const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
       const float4 ww = *reinterpret_cast<const float4*>(w + col + i);
       const float4 bb = *reinterpret_cast<const float4*>(b + col + i);
-      v[i] = fmaf((v[i] - mean) * rstd, ww.x, bb.x);
-      v[i + 1] = fmaf((v[i + 1] - mean) * rstd, ww.y, bb.y);
-      v[i + 2] = fmaf((v[i + 2] - mean) * rstd, ww.z, bb.z);
-      v[i + 3] = fmaf((v[i + 3] - mean) * rstd, ww.w, bb.w);
+      v[i] = fmaf((v[i] + pd.x - mean) * rstd, ww.x, bb.x);
+      v[i + 1] = fmaf((v[i + 1] + pd.y - mean) * rstd, ww.y, bb.y);
+      v[i + 2] = fmaf((v[i + 2] + pd.z - mean) * rstd, ww.z, bb.z);
+      v[i + 3] = fmaf((v[i + 3] + pd.w - mean) * rstd, ww.w, bb.w);
     }
     uint8_t* atom = c.sm + kSmA + (col >> 6) * 16384;
     const int chunk0 = (col & 63) >> 3;
@@ -348,7 +377,7 @@ __device__ void drain_gelu(Compute& c, int b, const float* b1c) {
     tmem_ld32(c.lane_addr((b ? kColS1 : kColS0) + col), v);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + b1c[col + i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i] + b1c[col + i]);
 #pragma unroll
     for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, ch * 4 + q, v + q * 8);
   }
@@ -418,7 +447,6 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   const uint32_t sbase = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kSmBars + B_COUNT * 8);
-  Fill* prog = reinterpret_cast<Fill*>(sm + kSmProg);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
@@ -428,8 +456,6 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < kProgEntries * 2; i += kThreads)
-    reinterpret_cast<uint32_t*>(prog)[i] = reinterpret_cast<const uint32_t*>(p.prog)[i];
   for (uint32_t i = threadIdx.x; i < (kSmVecA - kSmU) / 16; i += kThreads)      // padding rows must stay finite
     reinterpret_cast<uint4*>(sm + kSmU)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
@@ -440,49 +466,61 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
 
   if (warp == 0) {
     // ======================= weight-tape producer =======================
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int it = 0; it < my_tiles * p.evals; ++it) {
-        uint32_t off = 0;
-        for (int f = 0; f < p.n_fills; ++f, ++g) {
-          const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
-          const uint32_t bytes = (uint32_t)prog[prog_index(f, p.n_fills)].n8 * 8u * 128u;
-          spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
-          mbar_expect_tx(sbase + kSmBars + (B_FULL0 + slot) * 8, bytes);
-          bulk_g2s(sbase + kSmRing + slot * kSlotBytes, p.tape + off, bytes, sbase + kSmBars + (B_FULL0 + slot) * 8);
-          off += bytes;
+    // The whole warp runs the (warp-uniform) loop so that addresses stay in uniform registers;
+    // one elected lane issues the copies.
+    uint32_t g = 0;
+    for (int it = 0; it < my_tiles * p.evals; ++it) {
+      uint32_t off = 0;
+      for (int f = 0; f < p.n_fills; ++f, ++g) {
+        const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
+        const uint32_t bytes = (uint32_t)p.prog[prog_index(f, p.n_fills)].n8 * 8u * 128u;
+        const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8;
+        spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
+        if (elect_one()) {
+          if (p.timeline != nullptr && blockIdx.x == 0 && it == 1) p.timeline[3 * p.n_fills + f] = clock64();
+          mbar_expect_tx(full, bytes);
+          bulk_g2s(sbase + kSmRing + slot * kSlotBytes, p.tape + off, bytes, full);
         }
+        __syncwarp();
+        off += bytes;
       }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      uint32_t phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
-      uint32_t g = 0;
-      for (int it = 0; it < my_tiles * p.evals; ++it) {
-        for (int f = 0; f < p.n_fills; ++f, ++g) {
-          const Fill e = prog[prog_index(f, p.n_fills)];
+    // Warp-uniform control flow and operands (fill program in kernel-parameter space); one elected
+    // lane issues tcgen05.mma / tcgen05.commit.
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
+    uint32_t g = 0;
+    for (int it = 0; it < my_tiles * p.evals; ++it) {
+      for (int f = 0; f < p.n_fills; ++f, ++g) {
+        const Fill e = p.prog[prog_index(f, p.n_fills)];
+        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && it == 1 && lane == 0;
+        if (tl_on) p.timeline[3 * f] = clock64();
 #pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const uint32_t id = (e.waits >> (4 * w)) & 0xF;
-            if (id != kNone) { spin_wait(sbase + kSmBars + id * 8, (phases >> id) & 1u); phases ^= 1u << id; }
-          }
-          const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
-          spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
-          tc_fence_after();
-          const uint64_t a_desc = smem_desc_sw128(sbase + (uint32_t)e.a_off16 * 16u);
-          const uint64_t b_desc = smem_desc_sw128(sbase + kSmRing + slot * kSlotBytes);
-          const uint32_t idesc = idesc_bf16_m128((uint32_t)e.n8 * 8u);
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t id = (e.waits >> (4 * w)) & 0xF;
+          if (id != kNone) { spin_wait(sbase + kSmBars + id * 8, (phases >> id) & 1u); phases ^= 1u << id; }
+        }
+        const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
+        if (tl_on) p.timeline[3 * f + 1] = clock64();
+        spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
+        if (tl_on) p.timeline[3 * f + 2] = clock64();
+        tc_fence_after();
+        const uint64_t a_desc = smem_desc_sw128(sbase + (uint32_t)e.a_off16 * 16u);
+        const uint64_t b_desc = smem_desc_sw128(sbase + kSmRing + slot * kSlotBytes);
+        const uint32_t idesc = idesc_bf16_m128((uint32_t)e.n8 * 8u);
+        const uint32_t d_addr = tm + e.d_col;
+        const uint32_t c0 = e.commits & 0xF, c1 = (e.commits >> 4) & 0xF;
+        if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            mma_bf16(tmem + e.d_col, a_desc + 2u * j, b_desc + 2u * j, idesc, (e.acc | j) ? 1u : 0u);
+            mma_bf16(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, (e.acc | j) ? 1u : 0u);
           mma_commit(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const uint32_t id = (e.commits >> (4 * w)) & 0xF;
-            if (id != kNone) mma_commit(sbase + kSmBars + id * 8);
-          }
+          if (c0 != kNone) mma_commit(sbase + kSmBars + c0 * 8);
+          if (c1 != kNone) mma_commit(sbase + kSmBars + c1 * 8);
         }
+        __syncwarp();
       }
     }
   } else if (warp >= kComputeWarp0) {
@@ -524,7 +562,10 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         }
         compute_sync();
         const float* xsrc = second ? x2 : xcur;
+        c.tl = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 4 * p.n_fills : nullptr;
+        c.stamp();
         build_embed_input(c, p, tile, xsrc, sigv);
+        c.stamp();
 
         for (int l = 0; l < p.L; ++l) {
           // ---------------- attention half ----------------
@@ -532,31 +573,41 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           compute_sync();                                   // vecA(l) (and vecM(l)) landed for everyone
           c.wait(B_X_DONE);
           tc_fence_after();
+          c.stamp();
           ln_pass(c, vecA, p, (ev == 0 && tile == (int)blockIdx.x) ? 2 * l : -1);
+          c.stamp();
           for (int h = 0; h < kH; ++h) {
             c.wait(B_ACC_FULL0);
             tc_fence_after();
+            c.stamp();
             drain_qkv(c, vecA + 3 * kD + h * 192);
             c.arrive(B_ACC_EMPTY0);
             compute_sync();                                 // Q|K|V of this head visible to all warps
             c.wait(B_OP_EMPTY0);                            // previous head's Y consumed by its proj MMAs
+            c.stamp();
             attention_head(c, p.S, p.T);
             fence_async_smem();
             c.arrive(B_OP_READY0);
+            c.stamp();
             compute_sync();                                 // staging may be overwritten by the next drain
+            c.stamp();
           }
           // vecA is free: prefetch the next layer's (or the final block)
           load_vec_async(c, kSmVecA, p.vec + (size_t)(l + 1) * layer_stride, kVecAFloats);
           // ---------------- MLP half ----------------
           c.wait(B_X_DONE);
           tc_fence_after();
+          c.stamp();
           ln_pass(c, vecM, p, (ev == 0 && tile == (int)blockIdx.x) ? 2 * l + 1 : -1);
+          c.stamp();
           for (int ch = 0; ch < 8; ++ch) {
             const int b = ch & 1;
             c.wait(b ? B_ACC_FULL1 : B_ACC_FULL0);
             tc_fence_after();
             c.wait(b ? B_OP_EMPTY1 : B_OP_EMPTY0);          // H[b] consumed by FC2(ch-2)
+            c.stamp();
             drain_gelu(c, b, vecM + 3 * kD + ch * 128);
+            c.stamp();
             c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
             c.arrive(b ? B_OP_READY1 : B_OP_READY0);
           }
@@ -569,9 +620,12 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         compute_sync();
         c.wait(B_X_DONE);
         tc_fence_after();
+        c.stamp();
         ln_pass(c, vecA, p, (ev == 0 && tile == (int)blockIdx.x) ? 2 * p.L : -1);
+        c.stamp();
         c.wait(B_ACC_FULL0);
         tc_fence_after();
+        c.stamp();
         float pr[16];
         tmem_ld16(c.lane_addr(kColS0), pr);
         tmem_wait_ld();
@@ -664,7 +718,11 @@ __global__ void pack_tiles_kernel(const PackTile* tiles, uint8_t* tape) {
   }
 }
 
-struct EmbSrc { const float *pos, *tokw, *tokb, *sigw, *sigb, *actw, *actb; int obs, act, G, W; };
+struct EmbSrc {
+  const float *pos, *tokw, *tokb, *sigw, *sigb, *actw, *actb;
+  const float* resid_bias[2 * kMaxLayers];     // attn.proj.bias and mlp.2.bias of every layer
+  int obs, act, G, W, L;
+};
 // Embedding GEMM B operand: W_emb[n][k], n < 256, k < 128 (atom 0 = obs, atom 1 = misc), as 8 fills
 // [128 rows x 64] in (k-atom, row-half) order.
 __global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape) {
@@ -694,12 +752,28 @@ __global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape) {
           const int j = tok - 1 - s.G, step = j >> 1;
           tbl = (step < s.W) ? ((j & 1) ? s.actb[n] : s.tokb[n]) + s.pos[(size_t)(s.G + step) * kD + n] : 0.f;
         }
+        for (int i2 = 0; i2 < 2 * s.L; ++i2) tbl += s.resid_bias[i2][n];   // all residual-branch biases, up front
         const float hi = __bfloat162float(__float2bfloat16_rn(tbl));
         x = ((k - kOneHot0) & 1) ? (tbl - hi) : hi;
       }
       v[i] = x;
     }
     st_chunk(tape + (size_t)fill * 16384, r, chunk, v);
+  }
+}
+
+// pend vectors: minus the residual-branch biases that the embedding GEMM added too early.
+//   LN1(l): -(sum_{l' >= l} bproj + b2)     LN2(l): LN1(l) + bproj_l      ln_f: 0
+__global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, uint32_t m_off) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= kD) return;
+  float r = 0.f;
+  vec[(size_t)s.L * layer_stride + n] = 0.f;
+  for (int l = s.L - 1; l >= 0; --l) {
+    const float bp = s.resid_bias[2 * l][n], b2 = s.resid_bias[2 * l + 1][n];
+    vec[(size_t)l * layer_stride + m_off + n] = -(r + b2);
+    r += bp + b2;
+    vec[(size_t)l * layer_stride + n] = -r;
   }
 }
 
@@ -843,7 +917,11 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   pack_tiles_kernel<<<(unsigned)tiles.size(), 128, 0, st>>>(reinterpret_cast<const PackTile*>(scratch), tape);
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());
-  EmbSrc es{prm[0], prm[1], prm[2], prm[p_tail + 2], prm[p_tail + 3], prm[p_tail + 4], prm[p_tail + 5], m.obs_dim, m.act_dim, G, m.window};
+  EmbSrc es{};
+  es.pos = prm[0]; es.tokw = prm[1]; es.tokb = prm[2]; es.sigw = prm[p_tail + 2]; es.sigb = prm[p_tail + 3];
+  es.actw = prm[p_tail + 4]; es.actb = prm[p_tail + 5];
+  es.obs = m.obs_dim; es.act = m.act_dim; es.G = G; es.W = m.window; es.L = L;
+  for (int l = 0; l < L; ++l) { es.resid_bias[2 * l] = prm[p_layer(l, 11)]; es.resid_bias[2 * l + 1] = prm[p_layer(l, 15)]; }
   pack_emb_kernel<<<4, 256, 0, st>>>(es, tape);
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());
@@ -852,7 +930,6 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   std::vector<VecCopy> vc;
   for (int l = 0; l < L; ++l) {
     const uint32_t a = (uint32_t)(l * (kVecAFloats + kVecMFloats)), mo = a + kVecAFloats;
-    vc.push_back({l ? prm[p_layer(l - 1, 15)] : nullptr, a, kD, 1.f});          // pend = previous mlp.2 bias
     vc.push_back({prm[p_layer(l, 0)], a + kD, kD, 1.f});
     vc.push_back({prm[p_layer(l, 1)], a + 2 * kD, kD, 1.f});
     for (int h = 0; h < kH; ++h) {
@@ -860,13 +937,11 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
       vc.push_back({prm[p_layer(l, 5)] + h * 64, a + 3 * kD + h * 192 + 64, 64, 1.f});
       vc.push_back({prm[p_layer(l, 9)] + h * 64, a + 3 * kD + h * 192 + 128, 64, 1.f});
     }
-    vc.push_back({prm[p_layer(l, 11)], mo, kD, 1.f});                            // pend = proj bias
     vc.push_back({prm[p_layer(l, 2)], mo + kD, kD, 1.f});
     vc.push_back({prm[p_layer(l, 3)], mo + 2 * kD, kD, 1.f});
     vc.push_back({prm[p_layer(l, 13)], mo + 3 * kD, kFF, 1.f});
   }
   const uint32_t fa = (uint32_t)(L * (kVecAFloats + kVecMFloats));
-  vc.push_back({prm[p_layer(L - 1, 15)], fa, kD, 1.f});
   vc.push_back({prm[p_tail], fa + kD, kD, 1.f});
   vc.push_back({prm[p_tail + 1], fa + 2 * kD, kD, 1.f});
   vc.push_back({prm[p_tail + 7], fa + 3 * kD, m.act_dim, 1.f});
@@ -874,14 +949,17 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   uint8_t* scratch2 = scratch + (1 << 19);
   BESO_CUDA(cudaMemcpyAsync(scratch2, vc.data(), vc.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, st));
   pack_vec_kernel<<<(unsigned)vc.size(), 128, 0, st>>>(reinterpret_cast<const VecCopy*>(scratch2), w.vec);
-  ++g_kernel_launches;
+  pack_pend_kernel<<<1, kD, 0, st>>>(es, w.vec, kVecAFloats + kVecMFloats, kVecAFloats);
+  g_kernel_launches += 2;
   BESO_CUDA(cudaGetLastError());
   BESO_CUDA(cudaStreamSynchronize(st));                       // the host tables above go out of scope
   return BESO_OK;
 }
 
 static float* g_trace = nullptr;
+static long long* g_timeline = nullptr;
 void fast_set_trace(float* trace_dev) { g_trace = trace_dev; }
+void fast_set_timeline(long long* dev) { g_timeline = dev; }
 
 int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
                 const float* state, const float* goal, const float* x, const float* sigma, float* out,
@@ -891,7 +969,10 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   const int L = m.n_layers;
   const size_t n_fills = 4 + (size_t)L * 104 + 4;
   p.tape = reinterpret_cast<const uint8_t*>(w.tape);
-  p.prog = reinterpret_cast<const Fill*>(p.tape + w.tape_bytes);
+  {
+    const std::vector<Fill> prog = build_program();
+    memcpy(p.prog, prog.data(), sizeof(p.prog));
+  }
   p.vec = w.vec;
   p.n_fills = (int)n_fills; p.L = L; p.G = m.goal_conditioned ? m.goal_len : 0; p.obs = m.obs_dim; p.act = m.act_dim;
   p.t = t; p.T = 1 + p.G + 2 * t;
@@ -911,6 +992,7 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.flags = flags; p.lambda = lambda; p.sigma_data = m.sigma_data;
   p.state = state; p.goal = goal; p.xin = x; p.sigma = sigma; p.out = out;
   p.trace = g_trace;
+  p.timeline = g_timeline;
   static bool configured = false;
   if (!configured) {
     BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));

@@ -159,6 +159,8 @@ int beso_device_sm_count(int device);
 /* Diagnostics: when trace_dev != NULL, FAST-mode launches dump the fp32 residual stream of tile 0,
  * first evaluation, as seen by every LayerNorm pass: (2 * n_layers + 1) x 128 x 256 floats. */
 int beso_debug_set_trace(float* trace_dev);
+/* Diagnostics: clock64 stamps of block 0 during its second model evaluation (tools/timeline_fast.py). */
+int beso_debug_set_timeline(long long* timeline_dev);
 
 #ifdef __cplusplus
 }

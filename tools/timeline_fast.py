@@ -1,0 +1,116 @@
+"""GPU diagnostics: where one CTA of the FAST kernel spends its second model evaluation.
+
+    python tools/timeline_fast.py [T16|K256] > gpurun_out/timeline.txt
+
+Prints, in SM clock cycles, (a) the compute warps' phase durations and waits, (b) for the MMA
+issuer, per GEMM job, time spent waiting on barriers (compute) vs on the weight ring (producer).
+"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from beso_b200 import K256, T16, _lib                          # noqa: E402
+from beso_b200.denoiser import build_denoiser                 # noqa: E402
+from beso_b200.sampling import get_sigmas_exponential, sample_ddim  # noqa: E402
+from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "K256"
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+    cfg = {"K256": K256, "T16": T16}[name]
+    dev = torch.device("cuda:0")
+    m = build_denoiser(cfg, dev, mode="fast", state_dict=synthetic_state_dict(cfg, 1))
+    x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=2).items()}
+    sig = get_sigmas_exponential(4, 0.005, 1.0)
+    L = cfg.n_layers
+    NF = 4 + 104 * L + 4
+    tl = torch.zeros(4 * NF + 4096, dtype=torch.int64, device=dev)
+    sample_ddim(m, x["state"], x["noise"], x["goal"], sig)            # warm-up
+    _lib.lib().beso_debug_set_timeline(C.c_void_p(tl.data_ptr()))
+    sample_ddim(m, x["state"], x["noise"], x["goal"], sig)
+    torch.cuda.synchronize()
+    _lib.lib().beso_debug_set_timeline(None)
+    tl = tl.cpu().tolist()
+    mma = [tl[3 * f:3 * f + 3] for f in range(NF)]
+    prod = tl[3 * NF:4 * NF]
+    ev = [v for v in tl[4 * NF:] if v]
+    t0 = min(ev[0], mma[0][0])
+    print(f"# {name} B={B}: one evaluation = {max(ev[-1], mma[-1][2]) - t0} cycles")
+
+    # ---- compute warps ----
+    it = iter(ev)
+    def nxt():
+        return next(it) - t0
+    print("## compute warp 0 (cycles since evaluation start)")
+    a, b = nxt(), nxt()
+    print(f"embed build: {b - a}")
+    last = b
+    tot = dict(wait=0, ln=0, drain=0, attn=0, sync=0, gelu=0)
+    for l in range(L):
+        s, e = nxt(), nxt()
+        print(f"L{l} LN1: wait {s - last:6d}  run {e - s:6d}")
+        tot["wait"] += s - last; tot["ln"] += e - s
+        last = e
+        for h in range(4):
+            d0, a0, a1, a2 = nxt(), nxt(), nxt(), nxt()
+            print(f"L{l} head{h}: wait_acc {d0 - last:6d}  drain+sync {a0 - d0:6d}  attention {a1 - a0:6d}  sync {a2 - a1:6d}")
+            tot["wait"] += d0 - last; tot["drain"] += a0 - d0; tot["attn"] += a1 - a0; tot["sync"] += a2 - a1
+            last = a2
+        s, e = nxt(), nxt()
+        print(f"L{l} LN2: wait {s - last:6d}  run {e - s:6d}")
+        tot["wait"] += s - last; tot["ln"] += e - s
+        last = e
+        row = []
+        for ch in range(8):
+            s, e = nxt(), nxt()
+            row.append(f"w{s - last}/g{e - s}")
+            tot["wait"] += s - last; tot["gelu"] += e - s
+            last = e
+        print(f"L{l} FC1 chunks (wait/gelu): " + " ".join(row))
+    s, e, f = nxt(), nxt(), nxt()
+    print(f"ln_f: wait {s - last} run {e - s}; head wait {f - e}")
+    print("compute totals:", tot)
+
+    # ---- MMA issuer ----
+    print("## MMA issuer per job: [barrier wait | ring wait | total] cycles")
+    names = ["EMB"] * 4
+    layer = []
+    def qkv(h): return [f"QKV{h}"] * 8
+    def proj(h): return [f"PROJ{h}"] * 2
+    def fc1(c): return [f"FC1_{c}"] * 4
+    def fc2(c): return [f"FC2_{c}"] * 4
+    layer += qkv(0) + qkv(1) + proj(0) + qkv(2) + proj(1) + qkv(3) + proj(2) + proj(3)
+    layer += fc1(0) + fc1(1) + fc2(0)
+    for c in range(2, 8):
+        layer += fc1(c) + fc2(c - 1)
+    layer += fc2(7)
+    for l in range(L):
+        names += [f"L{l}.{n}" for n in layer]
+    names += ["HEAD"] * 4
+    agg, order = {}, []
+    for f in range(NF):
+        n = names[f]
+        if n not in agg:
+            agg[n] = [0, 0, mma[f][0], 0]
+            order.append(n)
+        agg[n][0] += mma[f][1] - mma[f][0]
+        agg[n][1] += mma[f][2] - mma[f][1]
+        agg[n][3] = (mma[f + 1][0] if f + 1 < NF else mma[f][2]) - agg[n][2]
+    tb = tr = 0
+    for n in order:
+        b, r, start, total = agg[n]
+        tb += b; tr += r
+        if n.startswith("L0.") or n.startswith("L1.FC") or not n.startswith("L"):
+            print(f"{n:10s} start {start - t0:7d}  barrier {b:6d}  ring {r:6d}  total {total:6d}")
+    print(f"MMA issuer totals: barrier-wait {tb}  ring-wait {tr}  of {mma[-1][2] - mma[0][0]}")
+    lat = [mma[f][2] - prod[f] for f in range(NF) if mma[f][2] > prod[f]]
+    print(f"fill latency (producer issue -> MMA sees full): median {sorted(lat)[len(lat) // 2]} max {max(lat)}")
+
+
+if __name__ == "__main__":
+    main()
