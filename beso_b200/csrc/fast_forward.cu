@@ -69,7 +69,8 @@ constexpr uint32_t kSmemBytes = kSmBars + 512;
 
 // barrier ids used by the fill program
 enum { B_A_READY = 0, B_X_DONE, B_ACC_FULL0, B_ACC_FULL1, B_ACC_EMPTY0, B_ACC_EMPTY1, B_OP_READY0, B_OP_READY1,
-       B_OP_EMPTY0, B_OP_EMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + 4, B_COUNT = B_EMPTY0 + 4 };
+       B_OP_EMPTY0, B_OP_EMPTY1, B_Y_READY, B_Y_EMPTY, B_FULL0, B_EMPTY0 = B_FULL0 + 4, B_COUNT = B_EMPTY0 + 4 };
+constexpr int kAttnWarps = 10;            // 8 compute warps + warps 2-3 help with attention
 constexpr uint8_t kNone = 0xF;
 
 // TMEM columns
@@ -79,7 +80,8 @@ struct __align__(8) Fill {     // one ring fill = rows x 64 bf16 of B operand + 
   uint16_t a_off16;            // A atom, shared-memory offset / 16
   uint16_t d_col;              // TMEM column of D
   uint8_t n8;                  // N / 8 (rows of the fill)
-  uint8_t acc;                 // accumulate into D on the first k-step
+  uint8_t acc;                 // bit 0: accumulate into D on the first k-step; bit 1: this fill and the next one
+                               // sit in adjacent ring slots and are consumed by ONE wider MMA per k-step
   uint8_t waits;               // two 4-bit barrier ids to wait on before issuing (0xF = none)
   uint8_t commits;             // two 4-bit barrier ids to commit to afterwards
 };
@@ -104,6 +106,7 @@ __device__ __forceinline__ int prog_index(int f, int n_fills) {
   return 4 + (f - 4) % 104;
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void attn_sync() { asm volatile("bar.sync 2, 320;" ::: "memory"); }   // compute + helper warps
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -179,27 +182,38 @@ struct Compute {
 // X (TMEM) is only read: every projection / MLP bias is added to X up front by the embedding GEMM and
 // `pend` holds minus the biases that are not due yet at this point of the network (see fast_pack).
 __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int trace_slot) {
-  float v[32];
-  float sum = 0.f, sq = 0.f;
+  float va[32], vb[32];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   const int col0 = c.hf * 128;
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    const int col = col0 + ch * 32;
-    tmem_ld32(c.lane_addr(kColX + col), v);
-    tmem_wait_ld();
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && trace_slot >= 0;
+  auto pass1 = [&](float (&v)[32], int col) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
-      v[i] += pd.x; v[i + 1] += pd.y; v[i + 2] += pd.z; v[i + 3] += pd.w;
+      const float a0 = v[i] + pd.x, a1 = v[i + 1] + pd.y, a2 = v[i + 2] + pd.z, a3 = v[i + 3] + pd.w;
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+      if (tracing) {
+        float* tr = p.trace + ((size_t)trace_slot * kRows + c.row) * kD + col + i;
+        tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3;
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
-    if (p.trace != nullptr && blockIdx.x == 0 && trace_slot >= 0) {
-      float* tr = p.trace + ((size_t)trace_slot * kRows + c.row) * kD + col;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tr[i] = v[i];
-    }
-  }
+  };
+  // the next chunk's TMEM load is in flight while the current one is reduced
+  tmem_ld32(c.lane_addr(kColX + col0), va);
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
+  pass1(va, col0);
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0 + 64), va);
+  pass1(vb, col0 + 32);
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
+  pass1(va, col0 + 64);
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0), va);          // first chunk of the second pass
+  pass1(vb, col0 + 96);
+  const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
   float2* stats = reinterpret_cast<float2*>(c.sm + kSmStats);
   stats[c.hf * kRows + c.row] = make_float2(sum, sq);
   compute_sync();
@@ -207,28 +221,36 @@ __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int t
   const float mean = (sum + o.x) * (1.0f / kD);
   const float var = fmaxf((sq + o.y) * (1.0f / kD) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
+  const float nmr = -mean * rstd;
   const float* w = vec + kD;
   const float* b = vec + 2 * kD;
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    const int col = col0 + ch * 32;
-    tmem_ld32(c.lane_addr(kColX + col), v);
-    tmem_wait_ld();
+  auto pass2 = [&](float (&v)[32], int col) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
       const float4 ww = *reinterpret_cast<const float4*>(w + col + i);
       const float4 bb = *reinterpret_cast<const float4*>(b + col + i);
-      v[i] = fmaf((v[i] + pd.x - mean) * rstd, ww.x, bb.x);
-      v[i + 1] = fmaf((v[i + 1] + pd.y - mean) * rstd, ww.y, bb.y);
-      v[i + 2] = fmaf((v[i + 2] + pd.z - mean) * rstd, ww.z, bb.z);
-      v[i + 3] = fmaf((v[i + 3] + pd.w - mean) * rstd, ww.w, bb.w);
+      v[i] = fmaf(fmaf(v[i] + pd.x, rstd, nmr), ww.x, bb.x);
+      v[i + 1] = fmaf(fmaf(v[i + 1] + pd.y, rstd, nmr), ww.y, bb.y);
+      v[i + 2] = fmaf(fmaf(v[i + 2] + pd.z, rstd, nmr), ww.z, bb.z);
+      v[i + 3] = fmaf(fmaf(v[i + 3] + pd.w, rstd, nmr), ww.w, bb.w);
     }
     uint8_t* atom = c.sm + kSmA + (col >> 6) * 16384;
     const int chunk0 = (col & 63) >> 3;
 #pragma unroll
     for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, chunk0 + q, v + q * 8);
-  }
+  };
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
+  pass2(va, col0);
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0 + 64), va);
+  pass2(vb, col0 + 32);
+  tmem_wait_ld();
+  tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
+  pass2(va, col0 + 64);
+  tmem_wait_ld();
+  pass2(vb, col0 + 96);
   fence_async_smem();
   tc_fence_before();
   c.arrive(B_A_READY);
@@ -247,11 +269,12 @@ __device__ void drain_qkv(Compute& c, const float* bqkv_h) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 u;
-      const float* bb = bqkv_h + col + q * 8;
-      u.x = pack_bf16x2(v[q * 8 + 0] + bb[0], v[q * 8 + 1] + bb[1]);
-      u.y = pack_bf16x2(v[q * 8 + 2] + bb[2], v[q * 8 + 3] + bb[3]);
-      u.z = pack_bf16x2(v[q * 8 + 4] + bb[4], v[q * 8 + 5] + bb[5]);
-      u.w = pack_bf16x2(v[q * 8 + 6] + bb[6], v[q * 8 + 7] + bb[7]);
+      const float4 b0 = *reinterpret_cast<const float4*>(bqkv_h + col + q * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bqkv_h + col + q * 8 + 4);
+      u.x = pack_bf16x2(v[q * 8 + 0] + b0.x, v[q * 8 + 1] + b0.y);
+      u.y = pack_bf16x2(v[q * 8 + 2] + b0.z, v[q * 8 + 3] + b0.w);
+      u.z = pack_bf16x2(v[q * 8 + 4] + b1.x, v[q * 8 + 5] + b1.y);
+      u.w = pack_bf16x2(v[q * 8 + 6] + b1.z, v[q * 8 + 7] + b1.w);
       *reinterpret_cast<uint4*>(dst + q * 16) = u;
     }
   }
@@ -260,13 +283,13 @@ __device__ void drain_qkv(Compute& c, const float* bqkv_h) {
 
 // Causal softmax(Q K^T) V for every sequence of the tile, one warp per sequence, mma.sync bf16.
 // Q is pre-scaled by 1/sqrt(hs) (folded into the packed weights).  Output -> Y atom (SW128 A layout).
-__device__ void attention_head(const Compute& c, int S, int T) {
-  const int warp = c.ctid >> 5, lane = c.lane;
-  const uint32_t qkv = c.sbase + kSmQkv;
+__device__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
+  const uint32_t qkv = sbase + kSmQkv;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
-  for (int s = warp; s < S; s += 8) {
+  for (int item = awarp; item < S * MT; item += kAttnWarps) {
+    const int mt = MT - 1 - item / S, s = item % S;   // later query tiles see more keys: schedule them first
     const int row0 = s * T;
-    for (int mt = 0; mt < MT; ++mt) {
+    {
       // ---- S = Q K^T over keys [0, 16*(mt+1)) (causal: later key tiles are fully masked) ----
       const int nkt = mt + 1;                    // 16-key steps needed
       float sc[2][2][4];                         // [key16][n8][frag]
@@ -350,7 +373,7 @@ __device__ void attention_head(const Compute& c, int S, int T) {
         }
       }
       const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
-      uint8_t* y = c.sm + kSmY;
+      uint8_t* y = sm + kSmY;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         const int e = n * 8 + (lane & 3) * 2;    // column within the head
@@ -377,7 +400,11 @@ __device__ void drain_gelu(Compute& c, int b, const float* b1c) {
     tmem_ld32(c.lane_addr((b ? kColS1 : kColS0) + col), v);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i] + b1c[col + i]);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(b1c + col + i);
+      v[i] = gelu_fast(v[i] + bb.x); v[i + 1] = gelu_fast(v[i + 1] + bb.y);
+      v[i + 2] = gelu_fast(v[i + 2] + bb.z); v[i + 3] = gelu_fast(v[i + 3] + bb.w);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, ch * 4 + q, v + q * 8);
   }
@@ -385,49 +412,85 @@ __device__ void drain_gelu(Compute& c, int b, const float* b1c) {
   tc_fence_before();
 }
 
-// A <- embedding-GEMM input rows: [obs atom | misc atom] (see file header), atoms 2..3 untouched.
-__device__ void build_embed_input(const Compute& c, const FastParams& p, int tile, const float* xsrc, const float* sigv) {
+// Per-thread description of the embedding-input task it owns for the whole tile: one (row, atom).
+struct EmbedTask {
+  const float* src;      // obs atom: state / goal vector of this row (nullptr = zeros)
+  int row, atom, vs, tok, xoff;   // xoff >= 0: action row, offset of its act values in the tile's x buffer
+  bool valid;
+};
+__device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int tile) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
-  const bool inner = (p.flags & BESO_FLAG_INNER) != 0;
-  const int seq_tile0 = tile * (cfg ? p.S / 2 : p.S);
-  for (int idx = c.ctid; idx < kRows * 16; idx += kComputeThreads) {
-    const int r = idx >> 4, atom = (idx >> 3) & 1, chunk = idx & 7;
-    float v[8];
+  EmbedTask e;
+  e.row = c.ctid & (kRows - 1);
+  e.atom = c.ctid >> 7;
+  e.vs = e.row / p.T;
+  e.tok = e.row - e.vs * p.T;
+  const int ls = cfg ? (e.vs >> 1) : e.vs;
+  const int seq = tile * (cfg ? p.S / 2 : p.S) + ls;
+  e.valid = e.vs < p.S && seq < p.B;
+  e.src = nullptr;
+  e.xoff = -1;
+  if (e.valid) {
+    const bool uncond = cfg ? ((e.vs & 1) != 0) : ((p.flags & BESO_FLAG_UNCOND) != 0);
+    const int j = e.tok - 1 - p.G;
+    if (e.tok >= 1 && e.tok <= p.G) { if (!uncond) e.src = p.goal + ((size_t)seq * p.G + (e.tok - 1)) * p.obs; }
+    else if (j >= 0 && (j & 1) == 0) e.src = p.state + ((size_t)seq * p.t + (j >> 1)) * p.obs;
+    else if (j >= 0) e.xoff = (ls * p.t + (j >> 1)) * p.act;
+  }
+  return e;
+}
+
+// A <- embedding-GEMM input rows: [obs atom | misc atom] (see file header), atoms 2..3 untouched.
+// One (row, atom) per thread; all global loads of a row are issued before any is used.
+__device__ void build_embed_input(const Compute& c, const FastParams& p, const EmbedTask& e, const float* xsrc,
+                                  const float* sigv) {
+  uint8_t* atom = c.sm + kSmA + e.atom * 16384;
+  if (e.atom == 0) {
+    float v[64];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    const int vs = r / p.T, tok = r - vs * p.T;
-    const int ls = cfg ? (vs >> 1) : vs;                 // sequence index within the tile
-    const int seq = seq_tile0 + ls;
-    if (vs < p.S && seq < p.B) {
-      const bool uncond = cfg ? ((vs & 1) != 0) : ((p.flags & BESO_FLAG_UNCOND) != 0);
-      if (atom == 0) {
-        const float* src = nullptr;
-        if (tok >= 1 && tok <= p.G) { if (!uncond) src = p.goal + ((size_t)seq * p.G + (tok - 1)) * p.obs; }
-        else if (tok > p.G && ((tok - 1 - p.G) & 1) == 0) src = p.state + ((size_t)seq * p.t + ((tok - 1 - p.G) >> 1)) * p.obs;
-        if (src != nullptr) {
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+    if (e.src != nullptr) {
+      if ((p.obs & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const int k = chunk * 8 + i; if (k < p.obs) v[i] = __ldg(src + k); }
-        }
-      } else {
-        const float sg = sigv[vs];
-        const int j = tok - 1 - p.G;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = chunk * 8 + i;
-          if (tok > p.G && (j & 1) && k < p.act) {
-            const float c_in = inner ? 1.0f : 1.0f / sqrtf(sg * sg + p.sigma_data * p.sigma_data);
-            v[i] = xsrc[(ls * p.t + (j >> 1)) * p.act + k] * c_in;
-          } else if (tok == 0 && k >= p.act && k < p.act + 3) {
-            const float cn = logf(sg) * 0.25f;
-            const float hi = __bfloat162float(__float2bfloat16_rn(cn));
-            v[i] = (k == p.act + 1) ? (cn - hi) : hi;
-          } else if (k == kOneHot0 + 2 * tok || k == kOneHot0 + 2 * tok + 1) {
-            v[i] = 1.0f;
+        for (int i = 0; i < 16; ++i) {
+          if (i * 4 < p.obs) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(e.src) + i);
+            v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
           }
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i < p.obs) v[i] = __ldg(e.src + i);
       }
     }
-    st_chunk(c.sm + kSmA + atom * 16384, r, chunk, v);
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) st_chunk(atom, e.row, ch, v + ch * 8);
+  } else {
+    const bool inner = (p.flags & BESO_FLAG_INNER) != 0;
+    const float sg = e.valid ? sigv[e.vs] : 1.0f;
+    const float c_in = inner ? 1.0f : 1.0f / sqrtf(sg * sg + p.sigma_data * p.sigma_data);
+    const float cn = logf(sg) * 0.25f;
+    const float cn_hi = __bfloat162float(__float2bfloat16_rn(cn));
+    const int hot = kOneHot0 + 2 * e.tok;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = ch * 8 + i;
+        float x = 0.f;
+        if (e.valid) {
+          if (k < kOneHot0) {
+            if (e.xoff >= 0 && k < p.act) x = xsrc[e.xoff + k] * c_in;
+            else if (e.tok == 0 && k >= p.act && k < p.act + 3) x = (k == p.act + 1) ? (cn - cn_hi) : cn_hi;
+          } else if (k == hot || k == hot + 1) {
+            x = 1.0f;
+          }
+        }
+        v[i] = x;
+      }
+      st_chunk(atom, e.row, ch, v);
+    }
   }
   fence_async_smem();
   tc_fence_before();
@@ -451,7 +514,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       const bool by_warps = (i == B_A_READY || i == B_ACC_EMPTY0 || i == B_ACC_EMPTY1 || i == B_OP_READY0 || i == B_OP_READY1);
-      mbar_init(sbase + kSmBars + i * 8, by_warps ? 8 : 1);
+      mbar_init(sbase + kSmBars + i * 8, i == B_Y_READY ? kAttnWarps : (by_warps ? 8 : 1));
     }
     fence_barrier_init();
   }
@@ -493,8 +556,10 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     uint32_t phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
     uint32_t g = 0;
     for (int it = 0; it < my_tiles * p.evals; ++it) {
-      for (int f = 0; f < p.n_fills; ++f, ++g) {
+      for (int f = 0; f < p.n_fills;) {
         const Fill e = p.prog[prog_index(f, p.n_fills)];
+        const bool pair = (e.acc & 2) != 0;            // the next fill sits in the adjacent slot: one wide MMA
+        const Fill e2 = p.prog[prog_index(pair ? f + 1 : f, p.n_fills)];
         const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && it == 1 && lane == 0;
         if (tl_on) p.timeline[3 * f] = clock64();
 #pragma unroll
@@ -505,32 +570,50 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
         if (tl_on) p.timeline[3 * f + 1] = clock64();
         spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
+        if (pair) spin_wait(sbase + kSmBars + (B_FULL0 + slot + 1) * 8, par);
         if (tl_on) p.timeline[3 * f + 2] = clock64();
         tc_fence_after();
         const uint64_t a_desc = smem_desc_sw128(sbase + (uint32_t)e.a_off16 * 16u);
         const uint64_t b_desc = smem_desc_sw128(sbase + kSmRing + slot * kSlotBytes);
-        const uint32_t idesc = idesc_bf16_m128((uint32_t)e.n8 * 8u);
+        const uint32_t idesc = idesc_bf16_m128(((uint32_t)e.n8 + (pair ? (uint32_t)e2.n8 : 0u)) * 8u);
         const uint32_t d_addr = tm + e.d_col;
-        const uint32_t c0 = e.commits & 0xF, c1 = (e.commits >> 4) & 0xF;
+        const uint32_t c0 = e2.commits & 0xF, c1 = (e2.commits >> 4) & 0xF;
         if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            mma_bf16(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, (e.acc | j) ? 1u : 0u);
+            mma_bf16(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, ((e.acc & 1) | j) ? 1u : 0u);
           mma_commit(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
+          if (pair) mma_commit(sbase + kSmBars + (B_EMPTY0 + slot + 1) * 8);
           if (c0 != kNone) mma_commit(sbase + kSmBars + c0 * 8);
           if (c1 != kNone) mma_commit(sbase + kSmBars + c1 * 8);
         }
         __syncwarp();
+        if (tl_on && pair) { p.timeline[3 * f + 3] = p.timeline[3 * f + 4] = p.timeline[3 * f + 5] = clock64(); }
+        f += pair ? 2 : 1;
+        g += pair ? 2 : 1;
       }
     }
-  } else if (warp >= kComputeWarp0) {
+  } else if (warp < kComputeWarp0) {
+    // ======================= attention helper warps (2, 3) =======================
+    uint32_t y_phase = 1;
+    for (int it = 0; it < my_tiles * p.evals * p.L * kH; ++it) {
+      attn_sync();
+      spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
+      y_phase ^= 1u;
+      attention_head(sm, sbase, 8 + (warp - 2), lane, p.S, p.T);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sbase + kSmBars + B_Y_READY * 8);
+      attn_sync();
+    }
+  } else {
     // ======================= compute warps =======================
     Compute c;
     c.sm = sm; c.sbase = sbase; c.tmem = tmem;
     c.ctid = threadIdx.x - kComputeWarp0 * 32;
     c.lane = lane; c.wq = warp & 3; c.hf = (warp - kComputeWarp0) >> 2;
     c.row = c.wq * 32 + lane;
-    c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1);
+    c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
     float* vecA = reinterpret_cast<float*>(sm + kSmVecA);
     float* vecM = reinterpret_cast<float*>(sm + kSmVecM);
     float* xbuf = reinterpret_cast<float*>(sm + kSmProg + kProgEntries * 8);
@@ -547,6 +630,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int seq0 = tile * nls;
       const int ns = min(nls, p.B - seq0);
+      const EmbedTask etask = make_embed_task(c, p, tile);
       compute_sync();                                        // previous tile's x fully written out
       for (int i = c.ctid; i < n_x; i += kComputeThreads)
         xcur[i] = (i < ns * p.t * p.act) ? p.xin[(size_t)seq0 * p.t * p.act + i] : 0.f;
@@ -564,7 +648,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         const float* xsrc = second ? x2 : xcur;
         c.tl = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 4 * p.n_fills : nullptr;
         c.stamp();
-        build_embed_input(c, p, tile, xsrc, sigv);
+        build_embed_input(c, p, etask, xsrc, sigv);
         c.stamp();
 
         for (int l = 0; l < p.L; ++l) {
@@ -582,14 +666,14 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             c.stamp();
             drain_qkv(c, vecA + 3 * kD + h * 192);
             c.arrive(B_ACC_EMPTY0);
-            compute_sync();                                 // Q|K|V of this head visible to all warps
-            c.wait(B_OP_EMPTY0);                            // previous head's Y consumed by its proj MMAs
+            attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
+            c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
             c.stamp();
-            attention_head(c, p.S, p.T);
+            attention_head(sm, sbase, c.ctid >> 5, lane, p.S, p.T);
             fence_async_smem();
-            c.arrive(B_OP_READY0);
+            c.arrive(B_Y_READY);
             c.stamp();
-            compute_sync();                                 // staging may be overwritten by the next drain
+            attn_sync();                                    // staging may be overwritten by the next drain
             c.stamp();
           }
           // vecA is free: prefetch the next layer's (or the final block)
@@ -797,17 +881,17 @@ std::vector<Fill> build_program() {
   // embedding: X = A_emb (atoms 0,1) * W_emb^T
   for (int kb = 0; kb < 2; ++kb)
     for (int half = 0; half < 2; ++half)
-      add(kSmA + kb * 16384, kColX + half * 128, 128, kb > 0, (kb == 0 && half == 0) ? B_A_READY : kNone, kNone,
+      add(kSmA + kb * 16384, kColX + half * 128, 128, (kb > 0) | (half == 0 ? 2 : 0), (kb == 0 && half == 0) ? B_A_READY : kNone, kNone,
           (kb == 1 && half == 1) ? B_X_DONE : kNone, kNone);
   auto qkv = [&](int h) {
     for (int kb = 0; kb < 4; ++kb) {
-      add(kSmA + kb * 16384, kColS0, 128, kb > 0, kb == 0 ? B_ACC_EMPTY0 : kNone, (kb == 0 && h == 0) ? B_A_READY : kNone, kNone, kNone);
+      add(kSmA + kb * 16384, kColS0, 128, (kb > 0) | 2, kb == 0 ? B_ACC_EMPTY0 : kNone, (kb == 0 && h == 0) ? B_A_READY : kNone, kNone, kNone);
       add(kSmA + kb * 16384, kColS1, 64, kb > 0, kNone, kNone, kb == 3 ? B_ACC_FULL0 : kNone, kNone);
     }
   };
   auto proj = [&](int h) {
-    add(kSmY, kColX, 128, 1, B_OP_READY0, kNone, kNone, kNone);
-    add(kSmY, kColX + 128, 128, 1, kNone, kNone, B_OP_EMPTY0, h == 3 ? B_X_DONE : kNone);
+    add(kSmY, kColX, 128, 1 | 2, B_Y_READY, kNone, kNone, kNone);
+    add(kSmY, kColX + 128, 128, 1, kNone, kNone, B_Y_EMPTY, h == 3 ? B_X_DONE : kNone);
   };
   auto fc1 = [&](int c) {
     const int b = c & 1;
@@ -819,7 +903,7 @@ std::vector<Fill> build_program() {
     const int b = c & 1;
     for (int kb = 0; kb < 2; ++kb)
       for (int half = 0; half < 2; ++half)
-        add((b ? kSmH1 : kSmH0) + kb * 16384, kColX + half * 128, 128, 1,
+        add((b ? kSmH1 : kSmH0) + kb * 16384, kColX + half * 128, 128, 1 | (half == 0 ? 2 : 0),
             (kb == 0 && half == 0) ? (b ? B_OP_READY1 : B_OP_READY0) : kNone, kNone,
             (kb == 1 && half == 1) ? (b ? B_OP_EMPTY1 : B_OP_EMPTY0) : kNone, (kb == 1 && half == 1 && c == 7) ? B_X_DONE : kNone);
   };
