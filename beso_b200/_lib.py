@@ -27,7 +27,7 @@ EXPORTS = [
     "beso_denoise_fwd", "beso_sample_loop", "beso_denoise_fwd_host", "beso_sample_loop_host",
     "beso_loss_fwd_bwd", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
-    "beso_debug_set_trace", "beso_debug_set_timeline",
+    "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
 ]
 
 
@@ -91,6 +91,7 @@ def _declare(lib):
     lib.beso_device_sm_count.argtypes = [i32]
     lib.beso_debug_set_trace.argtypes = [vp]
     lib.beso_debug_set_timeline.argtypes = [vp]
+    lib.beso_debug_mma_rate.argtypes = [vp, vp, i32, vp]
 
 
 def lib():

@@ -377,6 +377,7 @@ int beso_sample_loop_host(beso_plan* p, int mode, int sampler, const float* sigm
 int64_t beso_kernel_launches(void) { return g_kernel_launches; }
 int beso_debug_set_trace(float* trace_dev) { fast_set_trace(trace_dev); return BESO_OK; }
 int beso_debug_set_timeline(long long* dev) { fast_set_timeline(dev); return BESO_OK; }
+int beso_debug_mma_rate(long long* out_dev, const void* src_dev, int mode, void* stream) { return fast_mma_rate(out_dev, src_dev, mode, (cudaStream_t)stream); }
 
 int beso_plan_rows_per_cta(beso_plan* p, int mode, int t) {
   if (!p) return BESO_E_INVALID;

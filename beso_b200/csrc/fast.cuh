@@ -16,6 +16,7 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* para
 void fast_free(FastWeights& w);
 void fast_set_trace(float* trace_dev);
 void fast_set_timeline(long long* dev);
+int fast_mma_rate(long long* out_dev, const void* src_dev, int mode, cudaStream_t st);
 int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
                 const float* state, const float* goal, const float* action_or_x, const float* sigma,
                 float* out, int B, int t, uint32_t flags, float cond_lambda, cudaStream_t st);

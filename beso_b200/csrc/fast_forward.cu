@@ -25,6 +25,7 @@
 //    operand carries the raw inputs plus one-hot token-position columns whose B rows hold
 //    (bias + pos_emb) split into bf16 hi + lo, so X starts exact to ~2^-17.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -69,9 +70,9 @@ constexpr uint32_t kSmemBytes = kSmBars + 512;
 
 // barrier ids used by the fill program
 enum { B_A_READY = 0, B_X_DONE, B_ACC_FULL0, B_ACC_FULL1, B_ACC_EMPTY0, B_ACC_EMPTY1, B_OP_READY0, B_OP_READY1,
-       B_OP_EMPTY0, B_OP_EMPTY1, B_Y_READY, B_Y_EMPTY, B_FULL0, B_EMPTY0 = B_FULL0 + 4, B_COUNT = B_EMPTY0 + 4 };
+       B_OP_EMPTY0, B_OP_EMPTY1, B_Y_READY, B_Y_EMPTY, B_FULL0, B_EMPTY0 = B_FULL0 + 4, B_PFULL0 = B_EMPTY0 + 4, B_COUNT = B_PFULL0 + 4 };
 constexpr int kAttnWarps = 10;            // 8 compute warps + warps 2-3 help with attention
-constexpr uint8_t kNone = 0xF;
+constexpr uint32_t kNone = 0xF;
 
 // TMEM columns
 constexpr uint32_t kColX = 0, kColS0 = 256, kColS1 = 384;
@@ -100,6 +101,57 @@ struct FastParams {
 };
 
 // ================================ device code =====================================================
+// One ring group = the B operand of one k-block of one GEMM job (a fill or two adjacent fills) plus the
+// four K=16 MMAs that consume it.  walk_eval() enumerates the groups of one model evaluation in the
+// order the tape stores them; producer, MMA issuer and the pair forwarder all replay it.
+struct Group {
+  uint32_t a_off, d_col, n, acc;     // A atom (smem offset), TMEM column of D, N, accumulate on first k-step
+  uint32_t w0, w1, c0, c1;           // barrier ids to wait on before / commit to after (kNone = none)
+  bool pair;                         // two fills (two adjacent 16 KB ring slots when CG = 1)
+};
+template <class F>
+__device__ __forceinline__ void walk_eval(int L, F&& f) {
+#pragma unroll 1
+  for (uint32_t kb = 0; kb < 2; ++kb)                      // embedding: X = A_emb W_emb^T
+    f(Group{kSmA + kb * 16384, kColX, 256, kb > 0, kb == 0 ? (uint32_t)B_A_READY : kNone, kNone,
+            kb == 1 ? (uint32_t)B_X_DONE : kNone, kNone, true});
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    auto qkv = [&](uint32_t h) {
+#pragma unroll 1
+      for (uint32_t kb = 0; kb < 4; ++kb)
+        f(Group{kSmA + kb * 16384, kColS0, 192, kb > 0, kb == 0 ? (uint32_t)B_ACC_EMPTY0 : kNone,
+                (kb == 0 && h == 0) ? (uint32_t)B_A_READY : kNone, kb == 3 ? (uint32_t)B_ACC_FULL0 : kNone, kNone, true});
+    };
+    auto proj = [&](uint32_t h) {
+      f(Group{kSmY, kColX, 256, 1, B_Y_READY, kNone, B_Y_EMPTY, h == 3 ? (uint32_t)B_X_DONE : kNone, true});
+    };
+    auto fc1 = [&](uint32_t c) {
+      const uint32_t b = c & 1;
+#pragma unroll 1
+      for (uint32_t kb = 0; kb < 4; ++kb)
+        f(Group{kSmA + kb * 16384, b ? kColS1 : kColS0, 128, kb > 0, kb == 0 ? (uint32_t)(B_ACC_EMPTY0 + b) : kNone,
+                (kb == 0 && c == 0) ? (uint32_t)B_A_READY : kNone, kb == 3 ? (uint32_t)(B_ACC_FULL0 + b) : kNone, kNone, false});
+    };
+    auto fc2 = [&](uint32_t c) {
+      const uint32_t b = c & 1;
+#pragma unroll 1
+      for (uint32_t kb = 0; kb < 2; ++kb)
+        f(Group{(b ? kSmH1 : kSmH0) + kb * 16384, kColX, 256, 1, kb == 0 ? (uint32_t)(B_OP_READY0 + b) : kNone, kNone,
+                kb == 1 ? (uint32_t)(B_OP_EMPTY0 + b) : kNone, (kb == 1 && c == 7) ? (uint32_t)B_X_DONE : kNone, true});
+    };
+    qkv(0); qkv(1); proj(0); qkv(2); proj(1); qkv(3); proj(2); proj(3);
+    fc1(0); fc1(1); fc2(0);
+#pragma unroll 1
+    for (uint32_t c = 2; c < 8; ++c) { fc1(c); fc2(c - 1); }
+    fc2(7);
+  }
+#pragma unroll 1
+  for (uint32_t kb = 0; kb < 4; ++kb)                      // action head, N = 16
+    f(Group{kSmA + kb * 16384, kColS0, 16, kb > 0, kb == 0 ? (uint32_t)B_A_READY : kNone,
+            kb == 0 ? (uint32_t)B_ACC_EMPTY0 : kNone, kb == 3 ? (uint32_t)B_ACC_FULL0 : kNone, kNone, false});
+}
+
 __device__ __forceinline__ int prog_index(int f, int n_fills) {
   if (f < 4) return f;
   if (f >= n_fills - 4) return 108 + (f - (n_fills - 4));
@@ -129,9 +181,29 @@ __device__ __noinline__ void wait_timeout(uint32_t bar, uint32_t parity) {
     }
   }
 }
+__device__ __noinline__ void wait_timeout_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) {
+      printf("beso fast kernel: (cluster) mbarrier id %u parity %u timed out (block %d thread %d)\n",
+             (bar & 0x3FF) / 8, parity, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void spin_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;     // keep the fast path tiny: the issue loops live in the I-cache
+  wait_timeout_cluster(bar, parity);
+}
 __device__ __forceinline__ void spin_wait(uint32_t bar, uint32_t parity) {
-  for (int i = 0; i < 64; ++i) if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
   wait_timeout(bar, parity);
+}
+
+// whole-warp wait with a single polling lane
+__device__ __forceinline__ void warp_wait(int lane, uint32_t bar, uint32_t parity) {
+  if (lane == 0) spin_wait(bar, parity);
+  __syncwarp();
 }
 
 // erf-GELU without erff(): with z = |x| / sqrt(2), 0.5 * erfc(z) = 2^q(z) to 2.1e-6 absolute for a
@@ -174,18 +246,23 @@ struct Compute {
   __device__ void stamp() { if (tl != nullptr) *tl++ = clock64(); }
   __device__ uint32_t bar(int id) const { return sbase + kSmBars + id * 8; }
   __device__ void wait(int id) { spin_wait(bar(id), (phases >> id) & 1u); phases ^= 1u << id; }
-  __device__ void arrive(int id) const { __syncwarp(); if (lane == 0) mbar_arrive(bar(id)); }
+  int cg;                            // CTAs per MMA group (1 or 2)
+  // compute -> MMA barriers live in the leader CTA (rank 0) of the pair
+  __device__ void arrive(int id) const {
+    __syncwarp();
+    if (lane == 0) { if (cg == 2) mbar_arrive_cluster(bar(id), 0); else mbar_arrive(bar(id)); }
+  }
   __device__ uint32_t lane_addr(uint32_t col) const { return tmem + ((uint32_t)(wq * 32) << 16) + col; }
 };
 
 // A <- bf16(LayerNorm(X + pend) * w + b).   vec = [pend | w | b] in shared memory.
 // X (TMEM) is only read: every projection / MLP bias is added to X up front by the embedding GEMM and
 // `pend` holds minus the biases that are not due yet at this point of the network (see fast_pack).
-__device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int trace_slot) {
+__device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* trace_row) {
   float va[32], vb[32];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   const int col0 = c.hf * 128;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && trace_slot >= 0;
+  const bool tracing = trace_row != nullptr;
   auto pass1 = [&](float (&v)[32], int col) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -194,7 +271,7 @@ __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int t
       s0 += a0; s1 += a1; s2 += a2; s3 += a3;
       q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
       if (tracing) {
-        float* tr = p.trace + ((size_t)trace_slot * kRows + c.row) * kD + col + i;
+        float* tr = trace_row + col + i;
         tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3;
       }
     }
@@ -222,18 +299,15 @@ __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int t
   const float var = fmaxf((sq + o.y) * (1.0f / kD) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
-  const float* w = vec + kD;
-  const float* b = vec + 2 * kD;
+  // the LayerNorm weight / bias are folded into the Linear that consumes A (see fast_pack)
   auto pass2 = [&](float (&v)[32], int col) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
-      const float4 ww = *reinterpret_cast<const float4*>(w + col + i);
-      const float4 bb = *reinterpret_cast<const float4*>(b + col + i);
-      v[i] = fmaf(fmaf(v[i] + pd.x, rstd, nmr), ww.x, bb.x);
-      v[i + 1] = fmaf(fmaf(v[i + 1] + pd.y, rstd, nmr), ww.y, bb.y);
-      v[i + 2] = fmaf(fmaf(v[i + 2] + pd.z, rstd, nmr), ww.z, bb.z);
-      v[i + 3] = fmaf(fmaf(v[i + 3] + pd.w, rstd, nmr), ww.w, bb.w);
+      v[i] = fmaf(v[i] + pd.x, rstd, nmr);
+      v[i + 1] = fmaf(v[i + 1] + pd.y, rstd, nmr);
+      v[i + 2] = fmaf(v[i + 2] + pd.z, rstd, nmr);
+      v[i + 3] = fmaf(v[i + 3] + pd.w, rstd, nmr);
     }
     uint8_t* atom = c.sm + kSmA + (col >> 6) * 16384;
     const int chunk0 = (col & 63) >> 3;
@@ -258,7 +332,7 @@ __device__ void ln_pass(Compute& c, const float* vec, const FastParams& p, int t
 }
 
 // Accumulator of head h (Q|K at S0, V at S1[0:64)) -> + bias -> bf16 Q|K|V staging rows.
-__device__ void drain_qkv(Compute& c, const float* bqkv_h) {
+__device__ __noinline__ void drain_qkv(const Compute c, const float* bqkv_h) {
   float v[32];
 #pragma unroll 1
   for (int ch = 0; ch < 3; ++ch) {
@@ -283,7 +357,7 @@ __device__ void drain_qkv(Compute& c, const float* bqkv_h) {
 
 // Causal softmax(Q K^T) V for every sequence of the tile, one warp per sequence, mma.sync bf16.
 // Q is pre-scaled by 1/sqrt(hs) (folded into the packed weights).  Output -> Y atom (SW128 A layout).
-__device__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
+__device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
   const uint32_t qkv = sbase + kSmQkv;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
   for (int item = awarp; item < S * MT; item += kAttnWarps) {
@@ -391,7 +465,7 @@ __device__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane,
 }
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU -> bf16 -> H[b] (two K atoms).
-__device__ void drain_gelu(Compute& c, int b, const float* b1c) {
+__device__ __noinline__ void drain_gelu(const Compute c, int b, const float* b1c) {
   float v[32];
   uint8_t* atom = c.sm + (b ? kSmH1 : kSmH0) + c.hf * 16384;
 #pragma unroll 1
@@ -410,6 +484,106 @@ __device__ void drain_gelu(Compute& c, int b, const float* b1c) {
   }
   fence_async_smem();
   tc_fence_before();
+}
+
+// ---- the single-warp roles: one out-of-line step per ring group (small I-cache footprint).  All state is
+// passed and returned by value: with 227 KB of shared memory there is no L1 left, so anything that lands in
+// local memory (address-taken structs, spills) costs an L2 round trip per access.
+// The whole warp runs the (warp-uniform) schedule so that addresses stay in uniform registers; one elected
+// lane issues the copies.  CG = 2: this CTA streams only its half of the rows of each group.
+template <int CG>
+__device__ __noinline__ uint32_t producer_step(uint32_t n, uint32_t pair, uint32_t sbase, uint32_t rank,
+                                               const uint8_t* src, uint32_t g) {
+  const uint32_t bytes = n * 128u;
+  if (CG == 2) {
+    const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u, half = bytes >> 1;
+    const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8;
+    spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
+    if (elect_one()) {
+      mbar_expect_tx(full, half);
+      bulk_g2s(sbase + kSmRing + slot * kSlotBytes, src + rank * half, half, full);
+    }
+    __syncwarp();
+    return g + 1;
+  }
+  // one 16 KB slot per fill; a pair occupies two adjacent slots (even, odd)
+  const uint32_t first = pair ? kSlotBytes : bytes;
+#pragma unroll 1
+  for (uint32_t done = 0; done < bytes;) {
+    const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
+    const uint32_t len = done == 0 ? first : bytes - first;
+    const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8;
+    spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
+    if (elect_one()) {
+      mbar_expect_tx(full, len);
+      bulk_g2s(sbase + kSmRing + slot * kSlotBytes, src + done, len, full);
+    }
+    __syncwarp();
+    done += len;
+    g += 1;
+  }
+  return g;
+}
+
+// Warp-uniform control flow and operands, no memory loads on the issue path; one elected lane issues
+// tcgen05.mma / tcgen05.commit.  sync = w0 | w1 << 4 | c0 << 8 | c1 << 12; flags = acc | pair << 1.
+// Returns the updated (ring counter | barrier parities << 32).
+template <int CG>
+__device__ __noinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32_t n, uint32_t flags, uint32_t sync,
+                                          uint32_t sbase, uint32_t tm, uint32_t g, uint32_t phases, long long* tl) {
+  const uint32_t w0 = sync & 0xF, w1 = (sync >> 4) & 0xF, c0 = (sync >> 8) & 0xF, c1 = (sync >> 12) & 0xF;
+  const uint32_t acc = flags & 1u;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (tl != nullptr) t0 = clock64();
+  if (w0 != kNone) {
+    const uint32_t bar = sbase + kSmBars + w0 * 8, par = (phases >> w0) & 1u;
+    if (CG == 2) spin_wait_cluster(bar, par); else spin_wait(bar, par);
+    phases ^= 1u << w0;
+  }
+  if (w1 != kNone) {
+    const uint32_t bar = sbase + kSmBars + w1 * 8, par = (phases >> w1) & 1u;
+    if (CG == 2) spin_wait_cluster(bar, par); else spin_wait(bar, par);
+    phases ^= 1u << w1;
+  }
+  const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
+  const bool two = CG == 1 && (flags & 2u);
+  if (tl != nullptr) t1 = clock64();
+  spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
+  if (two) spin_wait(sbase + kSmBars + (B_FULL0 + slot + 1) * 8, par);
+  if (CG == 2) spin_wait_cluster(sbase + kSmBars + (B_PFULL0 + slot) * 8, par);
+  if (tl != nullptr) t2 = clock64();
+  tc_fence_after();
+  const uint64_t a_desc = smem_desc_sw128(sbase + a_off);
+  const uint64_t b_desc = smem_desc_sw128(sbase + kSmRing + slot * kSlotBytes);
+  const uint32_t idesc = CG == 2 ? idesc_bf16_m256(n) : idesc_bf16_m128(n);
+  const uint32_t d_addr = tm + d_col;
+  if (elect_one()) {
+    long long t3 = 0;
+    if (CG == 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_bf16_cg2(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, (acc | j) ? 1u : 0u);
+      if (tl != nullptr) t3 = clock64();
+      mma_commit_cg2(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
+      if (c0 != kNone) mma_commit_cg2(sbase + kSmBars + c0 * 8);
+      if (c1 != kNone) mma_commit_cg2(sbase + kSmBars + c1 * 8);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_bf16(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, (acc | j) ? 1u : 0u);
+      if (tl != nullptr) t3 = clock64();
+      mma_commit(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
+      if (two) mma_commit(sbase + kSmBars + (B_EMPTY0 + slot + 1) * 8);
+      if (c0 != kNone) mma_commit(sbase + kSmBars + c0 * 8);
+      if (c1 != kNone) mma_commit(sbase + kSmBars + c1 * 8);
+    }
+    if (tl != nullptr) {
+      const long long t4 = clock64();
+      tl[0] = t0; tl[1] = t1; tl[2] = t2; tl[3] = t3; tl[4] = t4;
+      if (flags & 2u) { tl[5] = tl[6] = tl[7] = tl[8] = tl[9] = t4; }
+    }
+  }
+  __syncwarp();
+  g += two ? 2 : 1;
+  return (uint64_t)g | ((uint64_t)phases << 32);
 }
 
 // Per-thread description of the embedding-input task it owns for the whole tile: one (row, atom).
@@ -442,33 +616,33 @@ __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int 
 
 // A <- embedding-GEMM input rows: [obs atom | misc atom] (see file header), atoms 2..3 untouched.
 // One (row, atom) per thread; all global loads of a row are issued before any is used.
-__device__ void build_embed_input(const Compute& c, const FastParams& p, const EmbedTask& e, const float* xsrc,
-                                  const float* sigv) {
+__device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask e, int obs, int act, uint32_t flags,
+                                               float sigma_data, const float* xsrc, const float* sigv) {
   uint8_t* atom = c.sm + kSmA + e.atom * 16384;
   if (e.atom == 0) {
     float v[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = 0.f;
     if (e.src != nullptr) {
-      if ((p.obs & 3) == 0) {
+      if ((obs & 3) == 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          if (i * 4 < p.obs) {
+          if (i * 4 < obs) {
             const float4 f = __ldg(reinterpret_cast<const float4*>(e.src) + i);
             v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
           }
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i < p.obs) v[i] = __ldg(e.src + i);
+        for (int i = 0; i < 64; ++i) if (i < obs) v[i] = __ldg(e.src + i);
       }
     }
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) st_chunk(atom, e.row, ch, v + ch * 8);
   } else {
-    const bool inner = (p.flags & BESO_FLAG_INNER) != 0;
+    const bool inner = (flags & BESO_FLAG_INNER) != 0;
     const float sg = e.valid ? sigv[e.vs] : 1.0f;
-    const float c_in = inner ? 1.0f : 1.0f / sqrtf(sg * sg + p.sigma_data * p.sigma_data);
+    const float c_in = inner ? 1.0f : 1.0f / sqrtf(sg * sg + sigma_data * sigma_data);
     const float cn = logf(sg) * 0.25f;
     const float cn_hi = __bfloat162float(__float2bfloat16_rn(cn));
     const int hot = kOneHot0 + 2 * e.tok;
@@ -481,8 +655,8 @@ __device__ void build_embed_input(const Compute& c, const FastParams& p, const E
         float x = 0.f;
         if (e.valid) {
           if (k < kOneHot0) {
-            if (e.xoff >= 0 && k < p.act) x = xsrc[e.xoff + k] * c_in;
-            else if (e.tok == 0 && k >= p.act && k < p.act + 3) x = (k == p.act + 1) ? (cn - cn_hi) : cn_hi;
+            if (e.xoff >= 0 && k < act) x = xsrc[e.xoff + k] * c_in;
+            else if (e.tok == 0 && k >= act && k < act + 3) x = (k == act + 1) ? (cn - cn_hi) : cn_hi;
           } else if (k == hot || k == hot + 1) {
             x = 1.0f;
           }
@@ -502,6 +676,10 @@ __device__ void load_vec_async(const Compute& c, uint32_t dst_off, const float* 
   cp_async_commit();
 }
 
+// CG = 1: every CTA issues its own M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2) run cta_group::2
+// M = 256 MMAs issued by the leader CTA; each CTA streams and holds only HALF of every B operand, which
+// halves the L2 -> SMEM weight traffic and the shared-memory bandwidth the tensor core needs for B.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
   extern __shared__ uint8_t smem_raw[];
@@ -510,87 +688,61 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   const uint32_t sbase = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kSmBars + B_COUNT * 8);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       const bool by_warps = (i == B_A_READY || i == B_ACC_EMPTY0 || i == B_ACC_EMPTY1 || i == B_OP_READY0 || i == B_OP_READY1);
-      mbar_init(sbase + kSmBars + i * 8, i == B_Y_READY ? kAttnWarps : (by_warps ? 8 : 1));
+      mbar_init(sbase + kSmBars + i * 8, i == B_Y_READY ? kAttnWarps * CG : (by_warps ? 8 * CG : 1));
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (CG == 2) cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive
+  if (warp == 1) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
   for (uint32_t i = threadIdx.x; i < (kSmVecA - kSmU) / 16; i += kThreads)      // padding rows must stay finite
     reinterpret_cast<uint4*>(sm + kSmU)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // tiles are dealt to MMA groups (CTA or CTA pair) round-robin; the second CTA of a pair may get a dummy tile
+  const int n_groups = (int)gridDim.x / CG, group = (int)blockIdx.x / CG;
+  const int n_group_tiles = (p.n_tiles + CG - 1) / CG;
+  const int my_tiles = (n_group_tiles - group + n_groups - 1) / n_groups;
 
   if (warp == 0) {
     // ======================= weight-tape producer =======================
-    // The whole warp runs the (warp-uniform) loop so that addresses stay in uniform registers;
-    // one elected lane issues the copies.
     uint32_t g = 0;
     for (int it = 0; it < my_tiles * p.evals; ++it) {
       uint32_t off = 0;
-      for (int f = 0; f < p.n_fills; ++f, ++g) {
-        const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
-        const uint32_t bytes = (uint32_t)p.prog[prog_index(f, p.n_fills)].n8 * 8u * 128u;
-        const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8;
-        spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
-        if (elect_one()) {
-          if (p.timeline != nullptr && blockIdx.x == 0 && it == 1) p.timeline[3 * p.n_fills + f] = clock64();
-          mbar_expect_tx(full, bytes);
-          bulk_g2s(sbase + kSmRing + slot * kSlotBytes, p.tape + off, bytes, full);
-        }
-        __syncwarp();
-        off += bytes;
-      }
+      walk_eval(p.L, [&](const Group& q) {
+        g = producer_step<CG>(q.n, q.pair ? 1u : 0u, sbase, rank, p.tape + off, g);
+        off += q.n * 128u;
+      });
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    // Warp-uniform control flow and operands (fill program in kernel-parameter space); one elected
-    // lane issues tcgen05.mma / tcgen05.commit.
+    // ======================= MMA issuer (leader) / full-barrier forwarder (peer CTA of a pair) ==========
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    uint32_t phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
-    uint32_t g = 0;
+    uint32_t g = 0, phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
     for (int it = 0; it < my_tiles * p.evals; ++it) {
-      for (int f = 0; f < p.n_fills;) {
-        const Fill e = p.prog[prog_index(f, p.n_fills)];
-        const bool pair = (e.acc & 2) != 0;            // the next fill sits in the adjacent slot: one wide MMA
-        const Fill e2 = p.prog[prog_index(pair ? f + 1 : f, p.n_fills)];
-        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && it == 1 && lane == 0;
-        if (tl_on) p.timeline[3 * f] = clock64();
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t id = (e.waits >> (4 * w)) & 0xF;
-          if (id != kNone) { spin_wait(sbase + kSmBars + id * 8, (phases >> id) & 1u); phases ^= 1u << id; }
-        }
-        const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
-        if (tl_on) p.timeline[3 * f + 1] = clock64();
-        spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
-        if (pair) spin_wait(sbase + kSmBars + (B_FULL0 + slot + 1) * 8, par);
-        if (tl_on) p.timeline[3 * f + 2] = clock64();
-        tc_fence_after();
-        const uint64_t a_desc = smem_desc_sw128(sbase + (uint32_t)e.a_off16 * 16u);
-        const uint64_t b_desc = smem_desc_sw128(sbase + kSmRing + slot * kSlotBytes);
-        const uint32_t idesc = idesc_bf16_m128(((uint32_t)e.n8 + (pair ? (uint32_t)e2.n8 : 0u)) * 8u);
-        const uint32_t d_addr = tm + e.d_col;
-        const uint32_t c0 = e2.commits & 0xF, c1 = (e2.commits >> 4) & 0xF;
-        if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_bf16(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, ((e.acc & 1) | j) ? 1u : 0u);
-          mma_commit(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
-          if (pair) mma_commit(sbase + kSmBars + (B_EMPTY0 + slot + 1) * 8);
-          if (c0 != kNone) mma_commit(sbase + kSmBars + c0 * 8);
-          if (c1 != kNone) mma_commit(sbase + kSmBars + c1 * 8);
-        }
-        __syncwarp();
-        if (tl_on && pair) { p.timeline[3 * f + 3] = p.timeline[3 * f + 4] = p.timeline[3 * f + 5] = clock64(); }
-        f += pair ? 2 : 1;
-        g += pair ? 2 : 1;
+      if (CG == 2 && rank != 0) {
+        // peer CTA: tell the leader when this CTA's half of each B operand has landed
+        walk_eval(p.L, [&](const Group&) {
+          const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
+          spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
+          if (elect_one()) mbar_arrive_cluster(sbase + kSmBars + (B_PFULL0 + slot) * 8, 0);
+          __syncwarp();
+          g += 1;
+        });
+      } else {
+        long long* tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
+        walk_eval(p.L, [&](const Group& q) {
+          const uint64_t r = mma_step<CG>(q.a_off, q.d_col, q.n, q.acc | (q.pair ? 2u : 0u),
+                                          q.w0 | (q.w1 << 4) | (q.c0 << 8) | (q.c1 << 12), sbase, tm, g, phases, tl);
+          g = (uint32_t)r;
+          phases = (uint32_t)(r >> 32);
+          if (tl != nullptr) tl += q.pair ? 10 : 5;
+        });
       }
     }
   } else if (warp < kComputeWarp0) {
@@ -603,7 +755,9 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       attention_head(sm, sbase, 8 + (warp - 2), lane, p.S, p.T);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sbase + kSmBars + B_Y_READY * 8);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(sbase + kSmBars + B_Y_READY * 8, 0); else mbar_arrive(sbase + kSmBars + B_Y_READY * 8);
+      }
       attn_sync();
     }
   } else {
@@ -627,9 +781,11 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     load_vec_async(c, kSmVecA, p.vec, kVecAFloats);
     load_vec_async(c, kSmVecM, p.vec + kVecAFloats, kVecMFloats);
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    c.cg = CG;
+    for (int tj = 0; tj < my_tiles; ++tj) {
+      const int tile = (group + tj * n_groups) * CG + (int)rank;     // >= n_tiles: dummy tile, protocol only
       const int seq0 = tile * nls;
-      const int ns = min(nls, p.B - seq0);
+      const int ns = max(0, min(nls, p.B - seq0));
       const EmbedTask etask = make_embed_task(c, p, tile);
       compute_sync();                                        // previous tile's x fully written out
       for (int i = c.ctid; i < n_x; i += kComputeThreads)
@@ -646,9 +802,12 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         }
         compute_sync();
         const float* xsrc = second ? x2 : xcur;
-        c.tl = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 4 * p.n_fills : nullptr;
+        auto trace_row = [&](int slot) -> float* {
+          return (p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.row) * kD : nullptr;
+        };
+        c.tl = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
         c.stamp();
-        build_embed_input(c, p, etask, xsrc, sigv);
+        build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, xsrc, sigv);
         c.stamp();
 
         for (int l = 0; l < p.L; ++l) {
@@ -658,7 +817,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           c.wait(B_X_DONE);
           tc_fence_after();
           c.stamp();
-          ln_pass(c, vecA, p, (ev == 0 && tile == (int)blockIdx.x) ? 2 * l : -1);
+          ln_pass(c, vecA, trace_row(2 * l));
           c.stamp();
           for (int h = 0; h < kH; ++h) {
             c.wait(B_ACC_FULL0);
@@ -682,7 +841,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           c.wait(B_X_DONE);
           tc_fence_after();
           c.stamp();
-          ln_pass(c, vecM, p, (ev == 0 && tile == (int)blockIdx.x) ? 2 * l + 1 : -1);
+          ln_pass(c, vecM, trace_row(2 * l + 1));
           c.stamp();
           for (int ch = 0; ch < 8; ++ch) {
             const int b = ch & 1;
@@ -705,7 +864,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         c.wait(B_X_DONE);
         tc_fence_after();
         c.stamp();
-        ln_pass(c, vecA, p, (ev == 0 && tile == (int)blockIdx.x) ? 2 * p.L : -1);
+        ln_pass(c, vecA, trace_row(2 * p.L));
         c.stamp();
         c.wait(B_ACC_FULL0);
         tc_fence_after();
@@ -781,12 +940,104 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (CG == 2) cluster_sync_all();          // the pair's MMAs read both CTAs' shared memory and TMEM
+  if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem, 512); else tmem_dealloc(tmem, 512); }
+}
+
+// ================================ tcgen05 issue-rate probe ==========================================
+// One warp issues 64 K=16 MMAs (M=128, SS operands, SW128 K-major) per variant, as straight-line code,
+// and reports SM cycles until the last one has completed: calibrates what the fused kernel can expect
+// from the tensor pipe.  CE = commit to a never-waited barrier after every CE MMAs (0 = none).
+template <int N, int CE, int DSTRIDE>
+__device__ __forceinline__ void probe_variant(uint32_t tm, uint64_t a_desc, uint64_t b_desc, uint32_t dummy_bar,
+                                              uint32_t done_bar, long long* out) {
+  constexpr uint32_t idesc = idesc_bf16_m128(N);
+  __syncwarp();
+  const long long t0 = clock64();
+  if (elect_one()) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      mma_bf16(tm + (uint32_t)((i >> 2) & 1) * DSTRIDE, a_desc + 2u * (i & 3) + (uint64_t)((i >> 2) & 3) * 1024u,
+               b_desc + 2u * (i & 3), idesc, 1u);
+      if (CE > 0 && (i % (CE > 0 ? CE : 1)) == CE - 1 && i != 63) mma_commit(dummy_bar);
+    }
+    mma_commit(done_bar);
+  }
+  __syncwarp();
+  const long long t1 = clock64();
+  spin_wait(done_bar, 0);
+  const long long t2 = clock64();
+  if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+}
+
+// warp 0: MMA issuer; warp 1 (mode & 1): streams `src` through a 4 x 16 KB bulk-copy ring as fast as it can;
+// warps 2-5 (mode & 2): hammer shared memory with 16-byte loads and stores.
+__global__ void __launch_bounds__(192, 1) mma_rate_kernel(long long* out, const uint8_t* src, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(sm);
+  const uint32_t a_off = 0, b_off = 65536, ring = 98304, junk = 163840, bars = 196608;   // A 4x[128x64], B [256x64]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + bars + 512);
+  volatile int* stop = reinterpret_cast<volatile int*>(sm + bars + 516);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < bars / 16; i += 192) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { for (int i = 0; i < 48; ++i) mbar_init(sbase + bars + i * 8, 1); *stop = 0; fence_barrier_init(); }
+  fence_async_smem();
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint64_t a_desc = smem_desc_sw128(sbase + a_off), b_desc = smem_desc_sw128(sbase + b_off);
+    const uint32_t dummy = sbase + bars + 31 * 8;
+    probe_variant<256, 0, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 0 * 8, out + 0);
+    probe_variant<256, 4, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 1 * 8, out + 2);
+    probe_variant<128, 0, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 2 * 8, out + 4);
+    probe_variant<128, 4, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 3 * 8, out + 6);
+    probe_variant<256, 0, 256>(tm, a_desc, b_desc, dummy, sbase + bars + 4 * 8, out + 8);
+    probe_variant<256, 1, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 5 * 8, out + 10);
+    probe_variant<64, 0, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 6 * 8, out + 12);
+    probe_variant<192, 0, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 7 * 8, out + 14);
+    probe_variant<256, 16, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 8 * 8, out + 16);
+    probe_variant<128, 16, 0>(tm, a_desc, b_desc, dummy, sbase + bars + 9 * 8, out + 18);
+    *stop = 1;
+    tc_fence_before();
+    __syncwarp();
+    tmem_dealloc(tm, 512);
+  } else if (warp == 1 && (mode & 1)) {
+    uint32_t g = 0, off = 0;
+    long long copies = 0;
+    while (!*stop) {
+      const uint32_t slot = g & 3, par = (g >> 2) & 1u, full = sbase + bars + (32 + slot) * 8;
+      if (g >= 4) spin_wait(full, par ^ 1u);                 // the previous copy into this slot has landed
+      if (elect_one()) { mbar_expect_tx(full, 16384); bulk_g2s(sbase + ring + slot * 16384, src + off, 16384, full); }
+      __syncwarp();
+      off = (off + 16384) & (6291456 - 1 - 16383);
+      ++g; ++copies;
+    }
+    for (uint32_t k = (g >= 4 ? g - 4 : 0); k < g; ++k) spin_wait(sbase + bars + (32 + (k & 3)) * 8, (k >> 2) & 1u);
+    if (lane == 0) out[20] = copies;
+  } else if (warp >= 2 && (mode & 2)) {
+    uint4* jb = reinterpret_cast<uint4*>(sm + junk);
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    int idx = threadIdx.x - 64;
+    while (!*stop) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 v = jb[(idx + k * 128) & 2047];
+        acc.x ^= v.x; acc.y += v.y;
+        jb[(idx + k * 128 + 64) & 2047] = acc;
+      }
+    }
+    if (acc.x == 0x12345678u) out[21] = acc.y;
+  }
 }
 
 // ================================ weight packing ===================================================
 struct PackTile {       // one [rows x 64] bf16 SW128 sub-tile of the tape from a row-major fp32 matrix
   const float* src; int ld, row0, col0, rows, valid_rows, valid_cols; float scale; uint32_t dst;
+  const float* colscale;   // optional per-input-column factor: the preceding LayerNorm's weight
 };
 __global__ void pack_tiles_kernel(const PackTile* tiles, uint8_t* tape) {
   const PackTile t = tiles[blockIdx.x];
@@ -796,7 +1047,12 @@ __global__ void pack_tiles_kernel(const PackTile* tiles, uint8_t* tape) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = chunk * 8 + i;
-      v[i] = (r < t.valid_rows && k < t.valid_cols) ? t.src[(size_t)(t.row0 + r) * t.ld + t.col0 + k] * t.scale : 0.f;
+      float x = 0.f;
+      if (r < t.valid_rows && k < t.valid_cols) {
+        x = t.src[(size_t)(t.row0 + r) * t.ld + t.col0 + k] * t.scale;
+        if (t.colscale != nullptr) x *= t.colscale[t.col0 + k];
+      }
+      v[i] = x;
     }
     st_chunk(tape + t.dst, r, chunk, v);
   }
@@ -861,10 +1117,20 @@ __global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, ui
   }
 }
 
-struct VecCopy { const float* src; uint32_t dst; int n; float scale; };
+// Bias of a Linear that follows a LayerNorm whose affine part is folded into it:
+//   W (LN0(x) * g + beta) + b = (W diag(g)) LN0(x) + (b + W beta)        dst[i] = scale * (b[i] + W[i,:] . beta)
+struct VecCopy { const float* src; uint32_t dst; int n; float scale; const float* W; const float* beta; int ld; };
 __global__ void pack_vec_kernel(const VecCopy* cp, float* vec) {
   const VecCopy c = cp[blockIdx.x];
-  for (int i = threadIdx.x; i < c.n; i += blockDim.x) vec[c.dst + i] = c.src ? c.src[i] * c.scale : 0.f;
+  for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
+    float b = c.src ? c.src[i] : 0.f;
+    if (c.W != nullptr) {
+      float acc = 0.f;
+      for (int k = 0; k < c.ld; ++k) acc = fmaf(c.W[(size_t)i * c.ld + k], c.beta[k], acc);
+      b += acc;
+    }
+    vec[c.dst + i] = b * c.scale;
+  }
 }
 
 // ---- fill program (host) ---------------------------------------------------------------------------
@@ -967,26 +1233,27 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   // ---- tape sub-tiles, in program order ----
   std::vector<PackTile> tiles;
   uint32_t off = 4 * 16384;                                   // embedding fills are written by pack_emb_kernel
-  auto tile = [&](const float* src, int ld, int row0, int col0, int rows, int vrows, float scale) {
-    tiles.push_back({src, ld, row0, col0, rows, vrows, 64, scale, off});
+  auto tile = [&](const float* src, int ld, int row0, int col0, int rows, int vrows, float scale, const float* colscale) {
+    tiles.push_back({src, ld, row0, col0, rows, vrows, 64, scale, off, colscale});
     off += rows * 128;
   };
   const float qscale = 0.125f;                                // 1 / sqrt(64): exact power of two
   for (int l = 0; l < L; ++l) {
     const float *wk = prm[p_layer(l, 4)], *wq = prm[p_layer(l, 6)], *wv = prm[p_layer(l, 8)], *wp = prm[p_layer(l, 10)];
     const float *w1 = prm[p_layer(l, 12)], *w2 = prm[p_layer(l, 14)];
+    const float *ln1w = prm[p_layer(l, 0)], *ln2w = prm[p_layer(l, 2)];
     auto qkv = [&](int h) {
       for (int kb = 0; kb < 4; ++kb) {
-        tile(wq, kD, h * 64, kb * 64, 64, 64, qscale);
-        tile(wk, kD, h * 64, kb * 64, 64, 64, 1.f);
-        tile(wv, kD, h * 64, kb * 64, 64, 64, 1.f);
+        tile(wq, kD, h * 64, kb * 64, 64, 64, qscale, ln1w);
+        tile(wk, kD, h * 64, kb * 64, 64, 64, 1.f, ln1w);
+        tile(wv, kD, h * 64, kb * 64, 64, 64, 1.f, ln1w);
       }
     };
-    auto proj = [&](int h) { for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s) tile(wp, kD, half * 128 + s * 64, h * 64, 64, 64, 1.f); };
-    auto fc1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) for (int s = 0; s < 2; ++s) tile(w1, kD, c * 128 + s * 64, kb * 64, 64, 64, 1.f); };
+    auto proj = [&](int h) { for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s) tile(wp, kD, half * 128 + s * 64, h * 64, 64, 64, 1.f, nullptr); };
+    auto fc1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) for (int s = 0; s < 2; ++s) tile(w1, kD, c * 128 + s * 64, kb * 64, 64, 64, 1.f, ln2w); };
     auto fc2 = [&](int c) {
       for (int kb = 0; kb < 2; ++kb) for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s)
-        tile(w2, kFF, half * 128 + s * 64, c * 128 + kb * 64, 64, 64, 1.f);
+        tile(w2, kFF, half * 128 + s * 64, c * 128 + kb * 64, 64, 64, 1.f, nullptr);
     };
     qkv(0); qkv(1); proj(0); qkv(2); proj(1); qkv(3); proj(2); proj(3);
     fc1(0); fc1(1); fc2(0);
@@ -994,7 +1261,7 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
     fc2(7);
   }
   const int p_tail = 3 + 16 * L;                              // ln_f.w, ln_f.b, sigma_emb.w/b, action_emb.w/b, action_pred.w/b
-  for (int kb = 0; kb < 4; ++kb) tile(prm[p_tail + 6], kD, 0, kb * 64, 16, m.act_dim, 1.f);
+  for (int kb = 0; kb < 4; ++kb) tile(prm[p_tail + 6], kD, 0, kb * 64, 16, m.act_dim, 1.f, prm[p_tail]);
   if (off != tape_bytes) { set_error("internal: tape layout mismatch"); return BESO_E_INVALID; }
   if (tiles.size() * sizeof(PackTile) > (1 << 19)) { set_error("internal: pack table too large"); return BESO_E_INVALID; }
   BESO_CUDA(cudaMemcpyAsync(scratch, tiles.data(), tiles.size() * sizeof(PackTile), cudaMemcpyHostToDevice, st));
@@ -1014,22 +1281,18 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   std::vector<VecCopy> vc;
   for (int l = 0; l < L; ++l) {
     const uint32_t a = (uint32_t)(l * (kVecAFloats + kVecMFloats)), mo = a + kVecAFloats;
-    vc.push_back({prm[p_layer(l, 0)], a + kD, kD, 1.f});
-    vc.push_back({prm[p_layer(l, 1)], a + 2 * kD, kD, 1.f});
+    const float* ln1b = prm[p_layer(l, 1)];
+    const float* ln2b = prm[p_layer(l, 3)];
     for (int h = 0; h < kH; ++h) {
-      vc.push_back({prm[p_layer(l, 7)] + h * 64, a + 3 * kD + h * 192, 64, qscale});
-      vc.push_back({prm[p_layer(l, 5)] + h * 64, a + 3 * kD + h * 192 + 64, 64, 1.f});
-      vc.push_back({prm[p_layer(l, 9)] + h * 64, a + 3 * kD + h * 192 + 128, 64, 1.f});
+      vc.push_back({prm[p_layer(l, 7)] + h * 64, a + 3 * kD + h * 192, 64, qscale, prm[p_layer(l, 6)] + (size_t)h * 64 * kD, ln1b, kD});
+      vc.push_back({prm[p_layer(l, 5)] + h * 64, a + 3 * kD + h * 192 + 64, 64, 1.f, prm[p_layer(l, 4)] + (size_t)h * 64 * kD, ln1b, kD});
+      vc.push_back({prm[p_layer(l, 9)] + h * 64, a + 3 * kD + h * 192 + 128, 64, 1.f, prm[p_layer(l, 8)] + (size_t)h * 64 * kD, ln1b, kD});
     }
-    vc.push_back({prm[p_layer(l, 2)], mo + kD, kD, 1.f});
-    vc.push_back({prm[p_layer(l, 3)], mo + 2 * kD, kD, 1.f});
-    vc.push_back({prm[p_layer(l, 13)], mo + 3 * kD, kFF, 1.f});
+    vc.push_back({prm[p_layer(l, 13)], mo + 3 * kD, kFF, 1.f, prm[p_layer(l, 12)], ln2b, kD});
   }
   const uint32_t fa = (uint32_t)(L * (kVecAFloats + kVecMFloats));
-  vc.push_back({prm[p_tail], fa + kD, kD, 1.f});
-  vc.push_back({prm[p_tail + 1], fa + 2 * kD, kD, 1.f});
-  vc.push_back({prm[p_tail + 7], fa + 3 * kD, m.act_dim, 1.f});
-  vc.push_back({nullptr, fa + 3 * kD + (uint32_t)m.act_dim, 768 - m.act_dim, 1.f});
+  vc.push_back({prm[p_tail + 7], fa + 3 * kD, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], kD});
+  vc.push_back({nullptr, fa + 3 * kD + (uint32_t)m.act_dim, 768 - m.act_dim, 1.f, nullptr, nullptr, 0});
   uint8_t* scratch2 = scratch + (1 << 19);
   BESO_CUDA(cudaMemcpyAsync(scratch2, vc.data(), vc.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, st));
   pack_vec_kernel<<<(unsigned)vc.size(), 128, 0, st>>>(reinterpret_cast<const VecCopy*>(scratch2), w.vec);
@@ -1044,6 +1307,12 @@ static float* g_trace = nullptr;
 static long long* g_timeline = nullptr;
 void fast_set_trace(float* trace_dev) { g_trace = trace_dev; }
 void fast_set_timeline(long long* dev) { g_timeline = dev; }
+int fast_mma_rate(long long* out_dev, const void* src_dev, int mode, cudaStream_t st) {
+  BESO_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
+  mma_rate_kernel<<<1, 192, 200704, st>>>(out_dev, reinterpret_cast<const uint8_t*>(src_dev), mode);
+  BESO_CUDA(cudaGetLastError());
+  return BESO_OK;
+}
 
 int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
                 const float* state, const float* goal, const float* x, const float* sigma, float* out,
@@ -1079,11 +1348,29 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.timeline = g_timeline;
   static bool configured = false;
   if (!configured) {
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
     configured = true;
   }
-  const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-  fast_sample_kernel<<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+  // CTA pairs (cta_group::2) whenever there are at least two tiles; BESO_FAST_CG=1 forces single-CTA MMAs
+  static const int forced_cg = [] { const char* e = getenv("BESO_FAST_CG"); return e ? atoi(e) : 0; }();
+  const int cg = forced_cg == 1 ? 1 : (forced_cg == 2 ? 2 : (p.n_tiles >= 2 ? 2 : 1));
+  if (cg == 2) {
+    const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
+    cudaLaunchConfig_t cfgl{};
+    cfgl.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    cfgl.blockDim = dim3(kThreads);
+    cfgl.dynamicSmemBytes = kSmemBytes + 1024;
+    cfgl.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfgl.attrs = attr; cfgl.numAttrs = 1;
+    BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2>, p, sa));
+  } else {
+    const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
+    fast_sample_kernel<1><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+  }
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());
   return BESO_OK;

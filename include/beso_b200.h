@@ -161,6 +161,8 @@ int beso_device_sm_count(int device);
 int beso_debug_set_trace(float* trace_dev);
 /* Diagnostics: clock64 stamps of block 0 during its second model evaluation (tools/timeline_fast.py). */
 int beso_debug_set_timeline(long long* timeline_dev);
+/* Diagnostics: tcgen05.mma issue / completion cycles for 10 instruction mixes (20 int64; tools/mma_rate.py). */
+int beso_debug_mma_rate(long long* out_dev, const void* src_6mb_dev, int mode, void* stream);
 
 #ifdef __cplusplus
 }

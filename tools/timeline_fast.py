@@ -29,16 +29,16 @@ def main():
     sig = get_sigmas_exponential(4, 0.005, 1.0)
     L = cfg.n_layers
     NF = 4 + 104 * L + 4
-    tl = torch.zeros(4 * NF + 4096, dtype=torch.int64, device=dev)
+    tl = torch.zeros(6 * NF + 4096, dtype=torch.int64, device=dev)
     sample_ddim(m, x["state"], x["noise"], x["goal"], sig)            # warm-up
     _lib.lib().beso_debug_set_timeline(C.c_void_p(tl.data_ptr()))
     sample_ddim(m, x["state"], x["noise"], x["goal"], sig)
     torch.cuda.synchronize()
     _lib.lib().beso_debug_set_timeline(None)
     tl = tl.cpu().tolist()
-    mma = [tl[3 * f:3 * f + 3] for f in range(NF)]
-    prod = tl[3 * NF:4 * NF]
-    ev = [v for v in tl[4 * NF:] if v]
+    mma = [tl[5 * f:5 * f + 5] for f in range(NF)]
+    prod = tl[5 * NF:6 * NF]
+    ev = [v for v in tl[6 * NF:] if v]
     t0 = min(ev[0], mma[0][0])
     print(f"# {name} B={B}: one evaluation = {max(ev[-1], mma[-1][2]) - t0} cycles")
 
@@ -96,19 +96,22 @@ def main():
     for f in range(NF):
         n = names[f]
         if n not in agg:
-            agg[n] = [0, 0, mma[f][0], 0]
+            agg[n] = [0, 0, mma[f][0], 0, 0, 0, 0]
             order.append(n)
         agg[n][0] += mma[f][1] - mma[f][0]
         agg[n][1] += mma[f][2] - mma[f][1]
         agg[n][3] = (mma[f + 1][0] if f + 1 < NF else mma[f][2]) - agg[n][2]
+        agg[n][4] += mma[f][3] - mma[f][2]          # descriptor set-up + MMA issue
+        agg[n][5] += mma[f][4] - mma[f][3]          # commits
+        agg[n][6] += (mma[f + 1][0] if f + 1 < NF else mma[f][4]) - mma[f][4]   # loop tail
     tb = tr = 0
     for n in order:
-        b, r, start, total = agg[n]
+        b, r, start, total, iss, com, tail = agg[n]
         tb += b; tr += r
         if n.startswith("L0.") or n.startswith("L1.FC") or not n.startswith("L"):
-            print(f"{n:10s} start {start - t0:7d}  barrier {b:6d}  ring {r:6d}  total {total:6d}")
+            print(f"{n:10s} start {start - t0:7d}  barrier {b:6d}  ring {r:6d}  issue {iss:6d}  commit {com:6d}  tail {tail:6d}  total {total:6d}")
     print(f"MMA issuer totals: barrier-wait {tb}  ring-wait {tr}  of {mma[-1][2] - mma[0][0]}")
-    lat = [mma[f][2] - prod[f] for f in range(NF) if mma[f][2] > prod[f]]
+    lat = [mma[f][2] - prod[f] for f in range(NF) if mma[f][2] > prod[f] > 0] or [0]
     print(f"fill latency (producer issue -> MMA sees full): median {sorted(lat)[len(lat) // 2]} max {max(lat)}")
 
 
