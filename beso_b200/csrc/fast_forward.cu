@@ -63,7 +63,8 @@ constexpr uint32_t kSmVecM = kSmVecA + kVecAFloats * 4;   // [bproj | ln2_w | ln
 constexpr uint32_t kVecMFloats = 1792;
 constexpr uint32_t kSmStats = kSmVecM + kVecMFloats * 4;  // [2][128] float2
 constexpr uint32_t kSmProg = kSmStats + 2048;
-constexpr int kProgEntries = 4 + 104 + 4;        // embedding | one layer (identical for all) | head
+constexpr int kProgEntries = 4 + 104 + 4;        // host-side fill program (tape layout): embedding | layer | head
+constexpr int kGroupEntries = 2 + 52 + 4;        // device-side group table in shared memory (uint4 each)
 constexpr uint32_t kXFloats = 832;
 constexpr uint32_t kSmBars = 230400;                // 32 mbarriers + tmem pointer
 constexpr uint32_t kSmemBytes = kSmBars + 512;
@@ -108,48 +109,76 @@ struct Group {
   uint32_t a_off, d_col, n, acc;     // A atom (smem offset), TMEM column of D, N, accumulate on first k-step
   uint32_t w0, w1, c0, c1;           // barrier ids to wait on before / commit to after (kNone = none)
   bool pair;                         // two fills (two adjacent 16 KB ring slots when CG = 1)
+  bool kk2;                          // two K blocks (8 MMAs): A atoms a_off, a_off + 16 KB; also two fills
 };
+// Job types of the per-evaluation schedule, decoded arithmetically (no tables on the issue path).
+enum { J_EMB = 0, J_QKV, J_PROJ, J_FC1, J_FC2, J_HEAD };
+__device__ __forceinline__ uint32_t job_groups(uint32_t type) {
+  return type == J_QKV || type == J_HEAD ? 4u : (type == J_PROJ ? 1u : 2u);
+}
+// layer-local job number (0..23) -> (type, index): Q0 Q1 P0 Q2 P1 Q3 P2 P3 | F1_0 F1_1 F2_0 (F1_c F2_c-1)c=2..7 F2_7
+__device__ __forceinline__ void layer_job(uint32_t lj, uint32_t& type, uint32_t& idx) {
+  if (lj < 8) {
+    const uint32_t code = (0x76352410u >> (4 * lj)) & 0xFu;     // nibble = (proj ? 4 : 0) | head
+    type = (code & 4u) ? J_PROJ : J_QKV;
+    idx = code & 3u;
+  } else {
+    const uint32_t m = lj - 8;
+    if (m < 3) { type = m == 2 ? J_FC2 : J_FC1; idx = m == 1 ? 1u : 0u; }
+    else if (m == 15) { type = J_FC2; idx = 7; }
+    else { const uint32_t t = m - 3, c = 2 + (t >> 1); type = (t & 1) ? J_FC2 : J_FC1; idx = (t & 1) ? c - 1 : c; }
+  }
+}
+__device__ __forceinline__ Group make_group(uint32_t type, uint32_t idx, uint32_t kb) {
+  Group q;
+  q.w0 = q.w1 = q.c0 = q.c1 = kNone;
+  q.pair = true; q.kk2 = false; q.acc = kb > 0;
+  q.a_off = kSmA + kb * 16384;
+  if (type == J_EMB) {                  // X = A_emb W_emb^T
+    q.d_col = kColX; q.n = 256;
+    if (kb == 0) q.w0 = B_A_READY;
+    if (kb == 1) q.c0 = B_X_DONE;
+  } else if (type == J_QKV) {           // head idx: [Q|K|V] (192 columns) of this head
+    q.d_col = kColS0; q.n = 192;
+    if (kb == 0) { q.w0 = B_ACC_EMPTY0; if (idx == 0) q.w1 = B_A_READY; }
+    if (kb == 3) q.c0 = B_ACC_FULL0;
+  } else if (type == J_PROJ) {          // X += Y_h Wproj[:, h]^T
+    q.a_off = kSmY; q.d_col = kColX; q.n = 256; q.acc = 1;
+    q.w0 = B_Y_READY; q.c0 = B_Y_EMPTY;
+    if (idx == 3) q.c1 = B_X_DONE;
+  } else if (type == J_FC1) {           // hidden chunk idx (128 wide), two K blocks per group
+    const uint32_t b = idx & 1;
+    q.a_off = kSmA + kb * 32768; q.d_col = b ? kColS1 : kColS0; q.n = 128; q.pair = false; q.kk2 = true;
+    if (kb == 0) { q.w0 = B_ACC_EMPTY0 + b; if (idx == 0) q.w1 = B_A_READY; }
+    if (kb == 1) q.c0 = B_ACC_FULL0 + b;
+  } else if (type == J_FC2) {           // X += H_idx W2[:, chunk]^T
+    const uint32_t b = idx & 1;
+    q.a_off = (b ? kSmH1 : kSmH0) + kb * 16384; q.d_col = kColX; q.n = 256; q.acc = 1;
+    if (kb == 0) q.w0 = B_OP_READY0 + b;
+    if (kb == 1) { q.c0 = B_OP_EMPTY0 + b; if (idx == 7) q.c1 = B_X_DONE; }
+  } else {                              // action head, N = 16
+    q.d_col = kColS0; q.n = 16; q.pair = false;
+    if (kb == 0) { q.w0 = B_A_READY; q.w1 = B_ACC_EMPTY0; }
+    if (kb == 3) q.c0 = B_ACC_FULL0;
+  }
+  return q;
+}
+// Calls f(group) for every ring group of one evaluation, from ONE call site (compact code for the
+// single-warp roles, everything stays in the uniform datapath).
 template <class F>
 __device__ __forceinline__ void walk_eval(int L, F&& f) {
+  const uint32_t n_jobs = 2u + 24u * (uint32_t)L;
+  uint32_t lj = 0;
 #pragma unroll 1
-  for (uint32_t kb = 0; kb < 2; ++kb)                      // embedding: X = A_emb W_emb^T
-    f(Group{kSmA + kb * 16384, kColX, 256, kb > 0, kb == 0 ? (uint32_t)B_A_READY : kNone, kNone,
-            kb == 1 ? (uint32_t)B_X_DONE : kNone, kNone, true});
+  for (uint32_t j = 0; j < n_jobs; ++j) {
+    uint32_t type, idx = 0;
+    if (j == 0) type = J_EMB;
+    else if (j == n_jobs - 1) type = J_HEAD;
+    else { layer_job(lj, type, idx); lj = lj == 23 ? 0 : lj + 1; }
+    const uint32_t nk = job_groups(type);
 #pragma unroll 1
-  for (int l = 0; l < L; ++l) {
-    auto qkv = [&](uint32_t h) {
-#pragma unroll 1
-      for (uint32_t kb = 0; kb < 4; ++kb)
-        f(Group{kSmA + kb * 16384, kColS0, 192, kb > 0, kb == 0 ? (uint32_t)B_ACC_EMPTY0 : kNone,
-                (kb == 0 && h == 0) ? (uint32_t)B_A_READY : kNone, kb == 3 ? (uint32_t)B_ACC_FULL0 : kNone, kNone, true});
-    };
-    auto proj = [&](uint32_t h) {
-      f(Group{kSmY, kColX, 256, 1, B_Y_READY, kNone, B_Y_EMPTY, h == 3 ? (uint32_t)B_X_DONE : kNone, true});
-    };
-    auto fc1 = [&](uint32_t c) {
-      const uint32_t b = c & 1;
-#pragma unroll 1
-      for (uint32_t kb = 0; kb < 4; ++kb)
-        f(Group{kSmA + kb * 16384, b ? kColS1 : kColS0, 128, kb > 0, kb == 0 ? (uint32_t)(B_ACC_EMPTY0 + b) : kNone,
-                (kb == 0 && c == 0) ? (uint32_t)B_A_READY : kNone, kb == 3 ? (uint32_t)(B_ACC_FULL0 + b) : kNone, kNone, false});
-    };
-    auto fc2 = [&](uint32_t c) {
-      const uint32_t b = c & 1;
-#pragma unroll 1
-      for (uint32_t kb = 0; kb < 2; ++kb)
-        f(Group{(b ? kSmH1 : kSmH0) + kb * 16384, kColX, 256, 1, kb == 0 ? (uint32_t)(B_OP_READY0 + b) : kNone, kNone,
-                kb == 1 ? (uint32_t)(B_OP_EMPTY0 + b) : kNone, (kb == 1 && c == 7) ? (uint32_t)B_X_DONE : kNone, true});
-    };
-    qkv(0); qkv(1); proj(0); qkv(2); proj(1); qkv(3); proj(2); proj(3);
-    fc1(0); fc1(1); fc2(0);
-#pragma unroll 1
-    for (uint32_t c = 2; c < 8; ++c) { fc1(c); fc2(c - 1); }
-    fc2(7);
+    for (uint32_t kb = 0; kb < nk; ++kb) f(make_group(type, idx, kb));
   }
-#pragma unroll 1
-  for (uint32_t kb = 0; kb < 4; ++kb)                      // action head, N = 16
-    f(Group{kSmA + kb * 16384, kColS0, 16, kb > 0, kb == 0 ? (uint32_t)B_A_READY : kNone,
-            kb == 0 ? (uint32_t)B_ACC_EMPTY0 : kNone, kb == 3 ? (uint32_t)B_ACC_FULL0 : kNone, kNone, false});
 }
 
 __device__ __forceinline__ int prog_index(int f, int n_fills) {
@@ -492,22 +521,29 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, const float* b1c
 // The whole warp runs the (warp-uniform) schedule so that addresses stay in uniform registers; one elected
 // lane issues the copies.  CG = 2: this CTA streams only its half of the rows of each group.
 template <int CG>
-__device__ __noinline__ uint32_t producer_step(uint32_t n, uint32_t pair, uint32_t sbase, uint32_t rank,
+__device__ __forceinline__ uint32_t producer_step(uint32_t n, uint32_t pair, uint32_t kk2, uint32_t sbase, uint32_t rank,
                                                const uint8_t* src, uint32_t g) {
-  const uint32_t bytes = n * 128u;
+  const uint32_t bytes = n * 128u * (kk2 ? 2u : 1u);
   if (CG == 2) {
     const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u, half = bytes >> 1;
     const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8;
+    const uint32_t dst = sbase + kSmRing + slot * kSlotBytes;
     spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
     if (elect_one()) {
       mbar_expect_tx(full, half);
-      bulk_g2s(sbase + kSmRing + slot * kSlotBytes, src + rank * half, half, full);
+      if (kk2) {          // this CTA's rows of K block 0, then of K block 1
+        const uint32_t q = half >> 1;
+        bulk_g2s(dst, src + rank * q, q, full);
+        bulk_g2s(dst + q, src + 2u * q + rank * q, q, full);
+      } else {
+        bulk_g2s(dst, src + rank * half, half, full);
+      }
     }
     __syncwarp();
     return g + 1;
   }
-  // one 16 KB slot per fill; a pair occupies two adjacent slots (even, odd)
-  const uint32_t first = pair ? kSlotBytes : bytes;
+  // one 16 KB slot per fill; a pair / double-K group occupies two adjacent slots (even, odd)
+  const uint32_t first = (pair || kk2) ? kSlotBytes : bytes;
 #pragma unroll 1
   for (uint32_t done = 0; done < bytes;) {
     const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
@@ -528,9 +564,10 @@ __device__ __noinline__ uint32_t producer_step(uint32_t n, uint32_t pair, uint32
 // Warp-uniform control flow and operands, no memory loads on the issue path; one elected lane issues
 // tcgen05.mma / tcgen05.commit.  sync = w0 | w1 << 4 | c0 << 8 | c1 << 12; flags = acc | pair << 1.
 // Returns the updated (ring counter | barrier parities << 32).
-template <int CG>
-__device__ __noinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32_t n, uint32_t flags, uint32_t sync,
-                                          uint32_t sbase, uint32_t tm, uint32_t g, uint32_t phases, long long* tl) {
+template <int CG, bool TL>
+__device__ __forceinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32_t n, uint32_t flags, uint32_t sync,
+                                             uint32_t sbase, uint32_t tm, uint32_t g, uint32_t phases, long long* tl_in) {
+  long long* tl = TL ? tl_in : nullptr;            // the timeline code compiles out of the production instantiation
   const uint32_t w0 = sync & 0xF, w1 = (sync >> 4) & 0xF, c0 = (sync >> 8) & 0xF, c1 = (sync >> 12) & 0xF;
   const uint32_t acc = flags & 1u;
   long long t0 = 0, t1 = 0, t2 = 0;
@@ -546,7 +583,8 @@ __device__ __noinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32
     phases ^= 1u << w1;
   }
   const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
-  const bool two = CG == 1 && (flags & 2u);
+  const bool kk2 = (flags & 4u) != 0;
+  const bool two = CG == 1 && (flags & 6u);
   if (tl != nullptr) t1 = clock64();
   spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
   if (two) spin_wait(sbase + kSmBars + (B_FULL0 + slot + 1) * 8, par);
@@ -562,6 +600,10 @@ __device__ __noinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32
     if (CG == 2) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) mma_bf16_cg2(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, (acc | j) ? 1u : 0u);
+      if (kk2) {          // second K block: next A atom, second half of the slot
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_bf16_cg2(d_addr, a_desc + 1024u + 2u * j, b_desc + (n * 64u >> 4) + 2u * j, idesc, 1u);
+      }
       if (tl != nullptr) t3 = clock64();
       mma_commit_cg2(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
       if (c0 != kNone) mma_commit_cg2(sbase + kSmBars + c0 * 8);
@@ -569,6 +611,10 @@ __device__ __noinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) mma_bf16(d_addr, a_desc + 2u * j, b_desc + 2u * j, idesc, (acc | j) ? 1u : 0u);
+      if (kk2) {          // second K block: next A atom, next ring slot
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_bf16(d_addr, a_desc + 1024u + 2u * j, b_desc + 1024u + 2u * j, idesc, 1u);
+      }
       if (tl != nullptr) t3 = clock64();
       mma_commit(sbase + kSmBars + (B_EMPTY0 + slot) * 8);
       if (two) mma_commit(sbase + kSmBars + (B_EMPTY0 + slot + 1) * 8);
@@ -578,7 +624,7 @@ __device__ __noinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uint32
     if (tl != nullptr) {
       const long long t4 = clock64();
       tl[0] = t0; tl[1] = t1; tl[2] = t2; tl[3] = t3; tl[4] = t4;
-      if (flags & 2u) { tl[5] = tl[6] = tl[7] = tl[8] = tl[9] = t4; }
+      if (flags & 6u) { tl[5] = tl[6] = tl[7] = tl[8] = tl[9] = t4; }
     }
   }
   __syncwarp();
@@ -697,6 +743,15 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     }
     fence_barrier_init();
   }
+  if (threadIdx.x == 32) {
+    // group table for [embedding | one layer | head]: the single-warp roles replay it with one LDS per group
+    uint4* tab = reinterpret_cast<uint4*>(sm + kSmProg);
+    int i = 0;
+    walk_eval(1, [&](const Group& q) {
+      tab[i++] = make_uint4(q.a_off, q.d_col | (q.n << 16), q.acc | (q.pair ? 2u : 0u) | (q.kk2 ? 4u : 0u),
+                            q.w0 | (q.w1 << 4) | (q.c0 << 8) | (q.c1 << 12));
+    });
+  }
   if (CG == 2) cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive
   if (warp == 1) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
   for (uint32_t i = threadIdx.x; i < (kSmVecA - kSmU) / 16; i += kThreads)      // padding rows must stay finite
@@ -710,15 +765,29 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   const int n_group_tiles = (p.n_tiles + CG - 1) / CG;
   const int my_tiles = (n_group_tiles - group + n_groups - 1) / n_groups;
 
+  const uint4* gtab = reinterpret_cast<const uint4*>(sm + kSmProg);
+  const int n_groups_eval = 6 + 52 * p.L;
+  // group i of an evaluation -> table entry: [0,2) embedding, then 52 per layer (replayed), then 4 head
+  auto table_index = [&](int i, int& li) -> int {
+    if (i < 2) return i;
+    if (i >= n_groups_eval - 4) return 54 + (i - (n_groups_eval - 4));
+    const int r = 2 + li;
+    li = li == 51 ? 0 : li + 1;
+    return r;
+  };
   if (warp == 0) {
     // ======================= weight-tape producer =======================
     uint32_t g = 0;
     for (int it = 0; it < my_tiles * p.evals; ++it) {
       uint32_t off = 0;
-      walk_eval(p.L, [&](const Group& q) {
-        g = producer_step<CG>(q.n, q.pair ? 1u : 0u, sbase, rank, p.tape + off, g);
-        off += q.n * 128u;
-      });
+      int li = 0;
+#pragma unroll 1
+      for (int i = 0; i < n_groups_eval; ++i) {
+        const uint4 e = gtab[table_index(i, li)];
+        const uint32_t n = e.y >> 16, kk2 = (e.z >> 2) & 1u;
+        g = producer_step<CG>(n, (e.z >> 1) & 1u, kk2, sbase, rank, p.tape + off, g);
+        off += n * 128u * (kk2 ? 2u : 1u);
+      }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer (leader) / full-barrier forwarder (peer CTA of a pair) ==========
@@ -727,22 +796,40 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     for (int it = 0; it < my_tiles * p.evals; ++it) {
       if (CG == 2 && rank != 0) {
         // peer CTA: tell the leader when this CTA's half of each B operand has landed
-        walk_eval(p.L, [&](const Group&) {
+#pragma unroll 1
+        for (int i = 0; i < n_groups_eval; ++i) {
           const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
           spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
           if (elect_one()) mbar_arrive_cluster(sbase + kSmBars + (B_PFULL0 + slot) * 8, 0);
           __syncwarp();
           g += 1;
-        });
+        }
       } else {
         long long* tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
-        walk_eval(p.L, [&](const Group& q) {
-          const uint64_t r = mma_step<CG>(q.a_off, q.d_col, q.n, q.acc | (q.pair ? 2u : 0u),
-                                          q.w0 | (q.w1 << 4) | (q.c0 << 8) | (q.c1 << 12), sbase, tm, g, phases, tl);
-          g = (uint32_t)r;
-          phases = (uint32_t)(r >> 32);
-          if (tl != nullptr) tl += q.pair ? 10 : 5;
-        });
+        int li = 0;
+        if (tl != nullptr) {
+#pragma unroll 1
+          for (int i = 0; i < n_groups_eval; ++i) {
+            const uint4 cur = gtab[table_index(i, li)];
+            const uint64_t r = mma_step<CG, true>(cur.x, cur.y & 0xFFFFu, cur.y >> 16, cur.z, cur.w, sbase, tm, g, phases, tl);
+            tl += (cur.z & 6u) ? 10 : 5;
+            g = (uint32_t)r;
+            phases = (uint32_t)(r >> 32);
+          }
+        } else {
+          // two groups per iteration, as straight-line code: consecutive groups then use different uniform
+          // registers for their descriptors, so setting up group i+1 does not wait for group i's MMAs to issue
+          uint4 e0 = gtab[0], e1 = gtab[1];
+#pragma unroll 1
+          for (int i = 0; i < n_groups_eval; i += 2) {      // n_groups_eval is even
+            const uint4 c0 = e0, c1 = e1;
+            if (i + 2 < n_groups_eval) { e0 = gtab[table_index(i + 2, li)]; e1 = gtab[table_index(i + 3, li)]; }
+            uint64_t r = mma_step<CG, false>(c0.x, c0.y & 0xFFFFu, c0.y >> 16, c0.z, c0.w, sbase, tm, g, phases, nullptr);
+            r = mma_step<CG, false>(c1.x, c1.y & 0xFFFFu, c1.y >> 16, c1.z, c1.w, sbase, tm, (uint32_t)r, (uint32_t)(r >> 32), nullptr);
+            g = (uint32_t)r;
+            phases = (uint32_t)(r >> 32);
+          }
+        }
       }
     }
   } else if (warp < kComputeWarp0) {
@@ -770,7 +857,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
     float* vecA = reinterpret_cast<float*>(sm + kSmVecA);
     float* vecM = reinterpret_cast<float*>(sm + kSmVecM);
-    float* xbuf = reinterpret_cast<float*>(sm + kSmProg + kProgEntries * 8);
+    float* xbuf = reinterpret_cast<float*>(sm + kSmProg + 1024);
     float* xcur = xbuf, *d1 = xbuf + kXFloats, *x2 = xbuf + 2 * kXFloats, *dU = xbuf + 3 * kXFloats;
     float* sigv = xbuf + 4 * kXFloats;                       // per virtual sequence noise level
     const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
