@@ -240,9 +240,20 @@ def main():
     sustained, burst, how = peaks()
     flops_launch = steps_per_batch * cfg.fwd_flops_per_seq()
     achieved = flops_launch / (ms_step * 1e-3) / 1e12
+    traffic = None                 # DRAM bytes per launch from the committed ncu --set full capture of this command
+    prof = os.path.join(ROOT, "profiles", "r1_fast_kernel.json")
+    if mode_name == "fast" and os.path.exists(prof):
+        try:
+            d = json.load(open(prof))
+            def _bytes(k):
+                v, u = float(d[k]["value"].replace(",", "")), d[k]["unit"].lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+            traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+        except Exception:
+            traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": None,
-                "kernel": "fast_sample_kernel" if mode_name == "fast" else "simt_denoise_kernel",
+                "frac": achieved / sustained, "traffic": traffic,
+                "kernel": "fast_sample_kernel<1>" if mode_name == "fast" else "simt_denoise_kernel",
                 "peak_source": f"bf16_tflops_sustained of {how} (kernel runs for ms inside a long step)",
                 "flops_per_launch": flops_launch,
                 "note": ("bf16 tcgen05 operands, fp32 accumulate" if mode_name == "fast" else

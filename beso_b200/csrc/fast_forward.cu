@@ -817,18 +817,22 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             phases = (uint32_t)(r >> 32);
           }
         } else {
-          // two groups per iteration, as straight-line code: consecutive groups then use different uniform
+          // four groups per iteration, as straight-line code: consecutive groups then use different uniform
           // registers for their descriptors, so setting up group i+1 does not wait for group i's MMAs to issue
-          uint4 e0 = gtab[0], e1 = gtab[1];
-#pragma unroll 1
-          for (int i = 0; i < n_groups_eval; i += 2) {      // n_groups_eval is even
-            const uint4 c0 = e0, c1 = e1;
-            if (i + 2 < n_groups_eval) { e0 = gtab[table_index(i + 2, li)]; e1 = gtab[table_index(i + 3, li)]; }
-            uint64_t r = mma_step<CG, false>(c0.x, c0.y & 0xFFFFu, c0.y >> 16, c0.z, c0.w, sbase, tm, g, phases, nullptr);
-            r = mma_step<CG, false>(c1.x, c1.y & 0xFFFFu, c1.y >> 16, c1.z, c1.w, sbase, tm, (uint32_t)r, (uint32_t)(r >> 32), nullptr);
+          auto run = [&](const uint4 c) {
+            const uint64_t r = mma_step<CG, false>(c.x, c.y & 0xFFFFu, c.y >> 16, c.z, c.w, sbase, tm, g, phases, nullptr);
             g = (uint32_t)r;
             phases = (uint32_t)(r >> 32);
+          };
+          int i = 0;
+#pragma unroll 1
+          for (; i + 4 <= n_groups_eval; i += 4) {
+            const uint4 c0 = gtab[table_index(i, li)], c1 = gtab[table_index(i + 1, li)];
+            const uint4 c2 = gtab[table_index(i + 2, li)], c3 = gtab[table_index(i + 3, li)];
+            run(c0); run(c1); run(c2); run(c3);
           }
+#pragma unroll 1
+          for (; i < n_groups_eval; ++i) run(gtab[table_index(i, li)]);
         }
       }
     }
@@ -1439,9 +1443,11 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
     BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
     configured = true;
   }
-  // CTA pairs (cta_group::2) whenever there are at least two tiles; BESO_FAST_CG=1 forces single-CTA MMAs
+  // Single-CTA MMAs (CG = 1) are the default: measured faster than CTA pairs on this workload (the pair mode
+  // halves L2 -> SMEM weight traffic but pays remote-arrive latency on every compute -> MMA hand-off; see
+  // profiles/).  BESO_FAST_CG=2 selects the cta_group::2 path, kept parity-tested for the next round.
   static const int forced_cg = [] { const char* e = getenv("BESO_FAST_CG"); return e ? atoi(e) : 0; }();
-  const int cg = forced_cg == 1 ? 1 : (forced_cg == 2 ? 2 : (p.n_tiles >= 2 ? 2 : 1));
+  const int cg = (forced_cg == 2 && p.n_tiles >= 2) ? 2 : 1;
   if (cg == 2) {
     const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
     cudaLaunchConfig_t cfgl{};

@@ -254,3 +254,17 @@ def test_error_paths(cuda_device):
         m(g["state"], g["action"][:, :5], g["goal"], g["sigma"])
     with pytest.raises(TypeError):
         m(g["state"], g["action"], g["goal"], g["sigma"], bogus=True)
+
+
+def test_cta_pair_mode_parity(cuda_device):
+    """The cta_group::2 variant of the FAST kernel (BESO_FAST_CG=2, read once per process) stays parity-tested."""
+    if not fast_available():
+        pytest.skip("fast mode not built")
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, BESO_FAST_CG="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_cg2.py")], env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "cg2 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
