@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "fast.cuh"
+#include "plan.cuh"
 
 namespace beso {
 
@@ -51,30 +52,9 @@ static std::vector<ParamInfo> param_table(const beso_model_desc& m) {
   return v;
 }
 
-struct WeightSlot {
-  float* simt_buf = nullptr;     // transposed fp32 images (PRECISE)
-  SimtModel simt{};
-  FastWeights fast{};            // bf16 UMMA tape + fp32 vectors (FAST)
-  bool packed = false;
-};
-
 }  // namespace beso
 
 using namespace beso;
-
-struct beso_plan {
-  beso_model_desc desc{};
-  int device = 0;
-  int sm_count = 0;
-  int max_smem = 0;
-  int active = 0;
-  WeightSlot slot[2];
-  size_t simt_floats = 0;
-  bool fast_ok = false;
-  // staging for the *_host entry points
-  float *h_pin = nullptr, *d_stage = nullptr;
-  size_t stage_floats = 0;
-};
 
 namespace beso {
 
@@ -251,6 +231,7 @@ int beso_plan_destroy(beso_plan* p) {
   }
   if (p->h_pin) cudaFreeHost(p->h_pin);
   if (p->d_stage) cudaFree(p->d_stage);
+  train_ws_free(p->train_ws);
   delete p;
   return BESO_OK;
 }
@@ -267,6 +248,7 @@ int beso_plan_pack_weights(beso_plan* p, int slot, const float* const* prm, int 
     BESO_CUDA(cudaMalloc(&ws.simt_buf, p->simt_floats * sizeof(float)));
     simt_layout(p->desc, ws.simt_buf, &ws.simt);
   }
+  ws.params.assign(prm, prm + n_params);
   int rc = pack_simt(p, ws, prm, st);
   if (rc) return rc;
   if (p->fast_ok) {
@@ -372,6 +354,25 @@ int beso_sample_loop_host(beso_plan* p, int mode, int sampler, const float* sigm
   rc = make_sample_args(sampler, sigmas, n_sigmas, coef, &sa);
   if (rc) return rc;
   return host_call(p, mode, sa, state, x, goal, nullptr, x, B, t, flags, lambda, (cudaStream_t)stream);
+}
+
+int beso_plan_set_params(beso_plan* p, int slot, const float* const* prm, int n_params) {
+  if (!p || !prm || slot < 0 || slot > 1) { set_error("bad argument"); return BESO_E_INVALID; }
+  if (n_params != (int)param_table(p->desc).size()) { set_error("wrong number of parameter tensors"); return BESO_E_INVALID; }
+  p->slot[slot].params.assign(prm, prm + n_params);
+  return BESO_OK;
+}
+
+int beso_loss_fwd_bwd(beso_plan* p, const float* state, const float* action, const float* goal, const float* noise,
+                      const float* sigma, const float* goal_keep, float* loss_dev, float* flat_grad_dev, int B,
+                      uint32_t flags, void* stream) {
+  if (!p || !state || !action || !noise || !sigma || !loss_dev || B < 1) { set_error("null argument or B < 1"); return BESO_E_INVALID; }
+  if (!goal && p->desc.goal_conditioned && p->desc.goal_len > 0) { set_error("null goal"); return BESO_E_INVALID; }
+  const WeightSlot& ws = p->slot[p->active];
+  if (ws.params.empty()) { set_error("no parameters registered (beso_plan_set_params / beso_plan_pack_weights)"); return BESO_E_NOT_PACKED; }
+  BESO_CUDA(cudaSetDevice(p->device));
+  return train_loss_fwd_bwd(p->train_ws, p->desc, ws.params.data(), state, action, goal, noise, sigma, goal_keep, loss_dev,
+                            flat_grad_dev, B, flags, (cudaStream_t)stream);
 }
 
 int64_t beso_kernel_launches(void) { return g_kernel_launches; }

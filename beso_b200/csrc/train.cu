@@ -1,12 +1,615 @@
-// Training path (loss forward + backward) and the data-parallel gradient exchange.
+// Training path: GCDenoiser.loss (score_wrappers.py:45-79) forward + hand-derived backward, and the
+// data-parallel gradient exchange (one NCCL all-reduce of the flat fp32 gradient over NVLink).
+//
+// fp32 throughout (the loss-parity bar is against the fp32 reference).  The dense products are plain
+// library GEMMs (cuBLAS SGEMM, fp32 math); everything else -- embeddings + interleave, LayerNorm
+// forward/backward, causal attention forward/backward, erf-GELU, bias / column reductions, the Karras
+// pre-conditioned loss -- is hand-written below.  Gradients are written into ONE flat buffer in
+// nn.Module.parameters() order, which is what the all-reduce operates on.
+//
+// Dropout probabilities must be 0 (the reference draws dropout masks from the global torch RNG in op
+// order).  The element-wise goal mask for CFG training is drawn by the caller.
+#include <cublas_v2.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <vector>
+
 #include "common.cuh"
+#include "plan.cuh"
+
+namespace beso {
+namespace {
+
+#define BESO_CUBLAS(expr)                                                                    \
+  do {                                                                                       \
+    cublasStatus_t _s = (expr);                                                              \
+    if (_s != CUBLAS_STATUS_SUCCESS) { set_error(std::string("cuBLAS error ") + std::to_string((int)_s) + " at " #expr); return BESO_E_CUDA; } \
+  } while (0)
+
+constexpr int kTB = 256;
+inline int blocks_for(size_t n, int per = kTB) { return (int)((n + per - 1) / per); }
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct Dims { int B, t, T, G, obs, act, d, H, hs, L, F, M; float sigma_data; };
+
+// ---- row-major GEMM helper: C[M][N] = alpha * op(A) * op(B) + beta * C --------------------------------
+int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, float alpha, const float* A, int lda,
+            const float* B, int ldb, float beta, float* C, int ldc) {
+  BESO_CUBLAS(cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A,
+                          lda, &beta, C, ldc));
+  return BESO_OK;
+}
+
+// ---- embeddings (score_gpts.py:284-337) ---------------------------------------------------------------
+// X[r][c] for row r = (b, tok); also writes the network input x_in = (a + n*sigma) * c_in  [B,t,act].
+__global__ void embed_fwd_kernel(Dims D, const float* __restrict__ state, const float* __restrict__ action,
+                                 const float* __restrict__ goal, const float* __restrict__ noise,
+                                 const float* __restrict__ sigma, const float* __restrict__ goal_keep, int pred_last,
+                                 const float* __restrict__ pos, const float* __restrict__ tokw, const float* __restrict__ tokb,
+                                 const float* __restrict__ sigw, const float* __restrict__ sigb,
+                                 const float* __restrict__ actw, const float* __restrict__ actb, float* __restrict__ X,
+                                 float* __restrict__ xin) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)D.M * D.d) return;
+  const int c = (int)(idx % D.d);
+  const int r = (int)(idx / D.d), b = r / D.T, tok = r - b * D.T;
+  const float sg = sigma[b];
+  float v;
+  if (tok == 0) {
+    v = fmaf(logf(sg) / 4.0f, sigw[c], sigb[c]);
+  } else if (tok <= D.G) {
+    const int g = tok - 1;
+    const float* in = goal + ((size_t)b * D.G + g) * D.obs;
+    const float* kp = goal_keep ? goal_keep + ((size_t)b * D.G + g) * D.obs : nullptr;
+    float a = 0.f;
+    for (int k = 0; k < D.obs; ++k) a = fmaf(kp ? in[k] * kp[k] : in[k], tokw[(size_t)c * D.obs + k], a);
+    v = a + tokb[c] + pos[(size_t)g * D.d + c];
+  } else {
+    const int j = tok - 1 - D.G, step = j >> 1;
+    float a = 0.f;
+    if ((j & 1) == 0) {
+      const float* in = state + ((size_t)b * D.t + step) * D.obs;
+      for (int k = 0; k < D.obs; ++k) a = fmaf(in[k], tokw[(size_t)c * D.obs + k], a);
+      v = a + tokb[c];
+    } else {
+      const float c_in = 1.0f / sqrtf(sg * sg + D.sigma_data * D.sigma_data);
+      const size_t o = ((size_t)b * D.t + step) * D.act;
+      for (int k = 0; k < D.act; ++k) {
+        const float nz = (pred_last && step != D.t - 1) ? 0.f : noise[o + k];
+        const float xi = (action[o + k] + nz * sg) * c_in;
+        if (c == 0) xin[o + k] = xi;
+        a = fmaf(xi, actw[(size_t)c * D.act + k], a);
+      }
+      v = a + actb[c];
+    }
+    v += pos[(size_t)(D.G + step) * D.d + c];
+  }
+  X[idx] = v;
+}
+
+// ---- LayerNorm (eps 1e-5, biased variance): warp per row ------------------------------------------------
+__global__ void ln_fwd_kernel(const float* __restrict__ X, int M, int d, const float* __restrict__ w,
+                              const float* __restrict__ b, float* __restrict__ Y, float* __restrict__ stats) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= M) return;
+  const float* x = X + (size_t)r * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += x[c];
+  const float mean = wsum(s) / d;
+  float v = 0.f;
+  for (int c = lane; c < d; c += 32) { const float t = x[c] - mean; v = fmaf(t, t, v); }
+  const float rstd = 1.0f / sqrtf(wsum(v) / d + 1e-5f);
+  for (int c = lane; c < d; c += 32) Y[(size_t)r * d + c] = (x[c] - mean) * rstd * w[c] + b[c];
+  if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+}
+// dX (+)= LN'(dY);  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w
+__global__ void ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X, const float* __restrict__ stats,
+                              const float* __restrict__ w, int M, int d, float* __restrict__ dX, int accumulate,
+                              float* __restrict__ dyxh) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= M) return;
+  const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+  const float* x = X + (size_t)r * d;
+  const float* dy = dY + (size_t)r * d;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < d; c += 32) { const float g = dy[c] * w[c], xh = (x[c] - mean) * rstd; s1 += g; s2 = fmaf(g, xh, s2); }
+  s1 = wsum(s1) / d; s2 = wsum(s2) / d;
+  for (int c = lane; c < d; c += 32) {
+    const float g = dy[c] * w[c], xh = (x[c] - mean) * rstd;
+    const float v = rstd * (g - s1 - xh * s2);
+    dX[(size_t)r * d + c] = accumulate ? dX[(size_t)r * d + c] + v : v;
+    dyxh[(size_t)r * d + c] = dy[c] * xh;          // column sums of this give d(loss)/d(ln.weight)
+  }
+}
+// dw[c] = sum_r dy * xhat, db[c] = sum_r dy : one block per 32 columns, rows strided over warps
+__global__ void ln_param_grad_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+                                     const float* __restrict__ stats, int M, int d, float* __restrict__ dw,
+                                     float* __restrict__ db) {
+  __shared__ float sw[8][33], sb[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, wy = threadIdx.y;
+  float aw = 0.f, ab = 0.f;
+  if (c < d)
+    for (int r = wy; r < M; r += 8) {
+      const float dy = dY[(size_t)r * d + c];
+      aw = fmaf(dy, (X[(size_t)r * d + c] - stats[2 * r]) * stats[2 * r + 1], aw);
+      ab += dy;
+    }
+  sw[wy][threadIdx.x] = aw; sb[wy][threadIdx.x] = ab;
+  __syncthreads();
+  if (wy == 0 && c < d) {
+    for (int i = 1; i < 8; ++i) { aw += sw[i][threadIdx.x]; ab += sb[i][threadIdx.x]; }
+    dw[c] = aw; db[c] = ab;
+  }
+}
+
+// ---- bias add / column sums -------------------------------------------------------------------------------
+__global__ void bias_add_kernel(float* __restrict__ C, const float* __restrict__ bias, size_t M, int N, int ldc) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const size_t r = idx / N; const int c = (int)(idx % N);
+  C[r * ldc + c] += bias[c];
+}
+__global__ void colsum_kernel(const float* __restrict__ A, int M, int N, int lda, float* __restrict__ out) {
+  __shared__ float s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, wy = threadIdx.y;
+  float a = 0.f;
+  if (c < N) for (int r = wy; r < M; r += 8) a += A[(size_t)r * lda + c];
+  s[wy][threadIdx.x] = a;
+  __syncthreads();
+  if (wy == 0 && c < N) { for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x]; out[c] = a; }
+}
+
+// ---- erf-GELU -----------------------------------------------------------------------------------------------
+__global__ void gelu_fwd_kernel(const float* __restrict__ U, float* __restrict__ G, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) { const float x = U[i]; G[i] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ U, float* __restrict__ dG, size_t n) {   // in place: dU
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float x = U[i];
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+    dG[i] *= cdf + x * pdf;
+  }
+}
+
+// ---- causal attention, one warp per (sequence, head, query row) ------------------------------------------------
+// QKV [M][3d] (q | k | v); P [B][H][T][T] saved; Y [M][d]
+__global__ void attn_fwd_kernel(Dims D, const float* __restrict__ QKV, float* __restrict__ P, float* __restrict__ Y) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (item >= D.B * D.H * D.T) return;
+  const int i = item % D.T, h = (item / D.T) % D.H, b = item / (D.T * D.H);
+  const int ld = 3 * D.d;
+  const float* q = QKV + ((size_t)b * D.T + i) * ld + h * D.hs;
+  const float scale = 1.0f / sqrtf((float)D.hs);
+  float sc[2];
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    float a = -INFINITY;
+    if (j <= i) {
+      const float* k = QKV + ((size_t)b * D.T + j) * ld + D.d + h * D.hs;
+      a = 0.f;
+      for (int e = 0; e < D.hs; ++e) a = fmaf(q[e], k[e], a);
+      a *= scale;
+    }
+    sc[u] = a;
+  }
+  float mx = fmaxf(sc[0], sc[1]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float p0 = (lane <= i) ? expf(sc[0] - mx) : 0.f, p1 = (lane + 32 <= i) ? expf(sc[1] - mx) : 0.f;
+  const float inv = 1.0f / wsum(p0 + p1);
+  p0 *= inv; p1 *= inv;
+  float* prow = P + (((size_t)b * D.H + h) * D.T + i) * D.T;
+  if (lane < D.T) prow[lane] = p0;
+  if (lane + 32 < D.T) prow[lane + 32] = p1;
+  for (int e0 = 0; e0 < D.hs; e0 += 32) {
+    const int e = e0 + lane;
+    float y = 0.f;
+    for (int j = 0; j <= i; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
+      if (e < D.hs) y = fmaf(pj, QKV[((size_t)b * D.T + j) * ld + 2 * D.d + h * D.hs + e], y);
+    }
+    if (e < D.hs) Y[((size_t)b * D.T + i) * D.d + h * D.hs + e] = y;
+  }
+}
+// One block per (sequence, head): dS in shared memory, then dQ, dK, dV.   dQKV [M][3d]
+__global__ void attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__ P,
+                                const float* __restrict__ dY, float* __restrict__ dQKV) {
+  extern __shared__ float sh[];
+  const int T = D.T, hs = D.hs, ld = 3 * D.d;
+  float* dS = sh;                                       // [T][T]
+  const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
+  const float* Pm = P + ((size_t)b * D.H + h) * T * T;
+  const float scale = 1.0f / sqrtf((float)hs);
+  const size_t row0 = (size_t)b * T;
+  // dP[i][j] = dY_i . V_j ;  dS = P * (dP - sum_j dP * P)
+  for (int idx = threadIdx.x; idx < T * T; idx += blockDim.x) {
+    const int i = idx / T, j = idx % T;
+    float a = 0.f;
+    if (j <= i) {
+      const float* dy = dY + (row0 + i) * D.d + h * hs;
+      const float* v = QKV + (row0 + j) * ld + 2 * D.d + h * hs;
+      for (int e = 0; e < hs; ++e) a = fmaf(dy[e], v[e], a);
+    }
+    dS[idx] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j <= i; ++j) s = fmaf(dS[i * T + j], Pm[i * T + j], s);
+    for (int j = 0; j < T; ++j) dS[i * T + j] = (j <= i) ? Pm[i * T + j] * (dS[i * T + j] - s) * scale : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < T * hs; idx += blockDim.x) {
+    const int i = idx / hs, e = idx % hs;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j <= i; ++j) dq = fmaf(dS[i * T + j], QKV[(row0 + j) * ld + D.d + h * hs + e], dq);
+    for (int r = i; r < T; ++r) {
+      dk = fmaf(dS[r * T + i], QKV[(row0 + r) * ld + h * hs + e], dk);
+      dv = fmaf(Pm[r * T + i], dY[(row0 + r) * D.d + h * hs + e], dv);
+    }
+    float* o = dQKV + (row0 + i) * ld + h * hs + e;
+    o[0] = dq; o[D.d] = dk; o[2 * D.d] = dv;
+  }
+}
+
+// ---- head gather / scatter, loss ----------------------------------------------------------------------------------
+__global__ void gather_action_rows_kernel(Dims D, const float* __restrict__ X, float* __restrict__ HA) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)D.B * D.t * D.d) return;
+  const int c = (int)(idx % D.d);
+  const size_t it = idx / D.d;
+  const int b = (int)(it / D.t), step = (int)(it % D.t);
+  HA[idx] = X[((size_t)b * D.T + 1 + D.G + 2 * step + 1) * D.d + c];
+}
+__global__ void scatter_action_rows_kernel(Dims D, const float* __restrict__ dHA, float* __restrict__ dX) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)D.M * D.d) return;
+  const int c = (int)(idx % D.d);
+  const int r = (int)(idx / D.d), b = r / D.T, tok = r - b * D.T, j = tok - 1 - D.G;
+  dX[idx] = (j >= 0 && (j & 1)) ? dHA[((size_t)b * D.t + (j >> 1)) * D.d + c] : 0.f;
+}
+// target = (a - c_skip * x_noised) / c_out ; loss = mean((pred - target)^2) ; dpred = 2 (pred - target) / N
+__global__ void loss_kernel(Dims D, const float* __restrict__ pred, const float* __restrict__ action,
+                            const float* __restrict__ noise, const float* __restrict__ sigma, int pred_last,
+                            float* __restrict__ dpred, float* __restrict__ partial) {
+  __shared__ float s[kTB / 32];
+  const size_t n = (size_t)D.B * D.t * D.act;
+  const float invN = 1.0f / (float)(pred_last ? (size_t)D.B * D.act : n);
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t it = i / D.act;
+    const int b = (int)(it / D.t), step = (int)(it % D.t);
+    const float sg = sigma[b], sd = D.sigma_data;
+    const float nz = (pred_last && step != D.t - 1) ? 0.f : noise[i];
+    const float xn = action[i] + nz * sg;
+    const float den = sg * sg + sd * sd;
+    const float c_skip = sd * sd / den, c_out = sg * sd / sqrtf(den);
+    const float target = (action[i] - c_skip * xn) / c_out;
+    float diff = pred[i] - target;
+    if (pred_last && step != D.t - 1) diff = 0.f;
+    acc = fmaf(diff, diff, acc);
+    dpred[i] = 2.0f * diff * invN;
+  }
+  acc = wsum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < kTB / 32; ++i) t += s[i]; partial[blockIdx.x] = t * invN; }
+}
+__global__ void fill_kernel(float* x, size_t n, float v) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) a += partial[i];
+  a = wsum(a);
+  if (threadIdx.x == 0) *out = a;
+}
+
+// ---- embedding backward --------------------------------------------------------------------------------------------
+// dpos[p][c] = sum over b of dX rows at position p (goal token p < G; state and action token of step p - G)
+__global__ void pos_grad_kernel(Dims D, const float* __restrict__ dX, int n_pos, float* __restrict__ dpos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pos * D.d) return;
+  const int c = idx % D.d, p = idx / D.d;
+  float a = 0.f;
+  if (p < D.G + D.t) {
+    for (int b = 0; b < D.B; ++b) {
+      const size_t r0 = (size_t)b * D.T;
+      if (p < D.G) a += dX[(r0 + 1 + p) * D.d + c];
+      else { const int step = p - D.G; a += dX[(r0 + 1 + D.G + 2 * step) * D.d + c] + dX[(r0 + 2 + D.G + 2 * step) * D.d + c]; }
+    }
+  }
+  dpos[idx] = a;
+}
+// gathers for the embedding weight gradients: rows of kind 0 = sigma token, 1 = state + goal tokens, 2 = action tokens
+__global__ void gather_embed_rows_kernel(Dims D, int kind, const float* __restrict__ dX, const float* __restrict__ state,
+                                         const float* __restrict__ goal, const float* __restrict__ goal_keep,
+                                         const float* __restrict__ xin, const float* __restrict__ sigma,
+                                         float* __restrict__ dRows, float* __restrict__ inRows) {
+  const int per = kind == 0 ? 1 : (kind == 1 ? D.G + D.t : D.t);
+  const int kin = kind == 0 ? 1 : (kind == 1 ? D.obs : D.act);
+  const size_t n_rows = (size_t)D.B * per;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= n_rows * (size_t)(D.d + kin)) return;
+  const size_t row = idx / (D.d + kin);
+  const int c = (int)(idx % (D.d + kin));
+  const int b = (int)(row / per), q = (int)(row % per);
+  int tok;
+  if (kind == 0) tok = 0;
+  else if (kind == 1) tok = q < D.G ? 1 + q : 1 + D.G + 2 * (q - D.G);
+  else tok = 2 + D.G + 2 * q;
+  if (c < D.d) { dRows[row * D.d + c] = dX[((size_t)b * D.T + tok) * D.d + c]; return; }
+  const int k = c - D.d;
+  float v;
+  if (kind == 0) v = logf(sigma[b]) / 4.0f;
+  else if (kind == 1) {
+    if (q < D.G) { const size_t o = ((size_t)b * D.G + q) * D.obs + k; v = goal_keep ? goal[o] * goal_keep[o] : goal[o]; }
+    else v = state[((size_t)b * D.t + (q - D.G)) * D.obs + k];
+  } else v = xin[((size_t)b * D.t + q) * D.act + k];
+  inRows[row * kin + k] = v;
+}
+
+size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
+
+}  // namespace
+
+// ================================ training workspace =======================================================
+struct TrainWs {
+  float* buf = nullptr;
+  size_t floats = 0;
+  cublasHandle_t blas = nullptr;
+};
+
+static int ensure_ws(TrainWs*& ws, size_t floats) {
+  if (!ws) ws = new TrainWs();
+  if (!ws->blas) BESO_CUBLAS(cublasCreate(&ws->blas));
+  if (floats > ws->floats) {
+    if (ws->buf) cudaFree(ws->buf);
+    ws->buf = nullptr; ws->floats = 0;
+    BESO_CUDA(cudaMalloc(&ws->buf, floats * sizeof(float)));
+    ws->floats = floats;
+  }
+  return BESO_OK;
+}
+void train_ws_free(TrainWs* ws) {
+  if (!ws) return;
+  if (ws->buf) cudaFree(ws->buf);
+  if (ws->blas) cublasDestroy(ws->blas);
+  delete ws;
+}
+
+int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* const* prm, const float* state,
+                       const float* action, const float* goal, const float* noise, const float* sigma,
+                       const float* goal_keep, float* loss_out, float* grad, int B, uint32_t flags, cudaStream_t st) {
+  if (!m.linear_output) { set_error("training path supports linear_output models only"); return BESO_E_UNSUPPORTED; }
+  Dims D;
+  D.B = B; D.t = m.window; D.G = m.goal_conditioned ? m.goal_len : 0; D.T = 1 + D.G + 2 * D.t; D.obs = m.obs_dim;
+  D.act = m.act_dim; D.d = m.d; D.H = m.n_heads; D.hs = m.d / m.n_heads; D.L = m.n_layers; D.F = 4 * m.d;
+  D.M = B * D.T; D.sigma_data = m.sigma_data;
+  if (D.T > 64) { set_error("training path supports at most 64 tokens per sequence"); return BESO_E_UNSUPPORTED; }
+  const int pred_last = (flags & BESO_FLAG_PRED_LAST) ? 1 : 0;
+  const int d = D.d, F = D.F, M = D.M, L = D.L;
+  const size_t Md = (size_t)M * d, MF = (size_t)M * F, nP = (size_t)B * D.H * D.T * D.T, nBt = (size_t)B * D.t;
+  // ---- carve the workspace ----
+  const size_t per_layer = 5 * align4(Md) + align4(3 * Md) + align4(nP) + 2 * align4(MF) + 2 * align4(2 * (size_t)M);
+  const size_t n_gather = (size_t)B * (D.G + D.t);
+  const size_t total = (size_t)L * per_layer + 2 * align4(Md) + align4(2 * (size_t)M) + align4(nBt * d) + 3 * align4(nBt * D.act) +
+                       4 * align4(Md) + align4(MF) + align4(3 * Md) + align4((size_t)M) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + 1024 + 4096;
+  int rc = ensure_ws(ws, total);
+  if (rc) return rc;
+  float* p = ws->buf;
+  auto take = [&](size_t n) { float* q = p; p += align4(n); return q; };
+  struct Layer { float *Xin, *H1, *QKV, *P, *Y, *Xmid, *H2, *U, *Gg, *st1, *st2; };
+  std::vector<Layer> A(L);
+  for (int l = 0; l < L; ++l) {
+    A[l].Xin = take(Md); A[l].H1 = take(Md); A[l].QKV = take(3 * Md); A[l].P = take(nP); A[l].Y = take(Md);
+    A[l].Xmid = take(Md); A[l].H2 = take(Md); A[l].U = take(MF); A[l].Gg = take(MF); A[l].st1 = take(2 * (size_t)M);
+    A[l].st2 = take(2 * (size_t)M);
+  }
+  float *XL = take(Md), *HF = take(Md), *stf = take(2 * (size_t)M), *HA = take(nBt * d), *pred = take(nBt * D.act),
+        *dpred = take(nBt * D.act), *xin = take(nBt * D.act);
+  float *dX = take(Md), *dT = take(Md), *dH = take(Md), *dY = take(Md), *dBig = take(MF), *dQKV = take(3 * Md);
+  float *gRows = take(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))), *partial = take(1024);
+  float* ones = take((size_t)M);
+  cublasHandle_t h = ws->blas;
+  BESO_CUBLAS(cublasSetStream(h, st));
+  BESO_CUBLAS(cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH));      // fp32 FMA, no TF32
+
+  // ---- parameter pointers and gradient slots (parameters() order) ----
+  std::vector<size_t> goff;
+  size_t acc_off = 0;
+  const int n_params = 3 + 16 * L + 8;
+  {
+    beso_model_desc mm = m;
+    for (int i = 0; i < n_params; ++i) { goff.push_back(acc_off); acc_off += (size_t)beso_param_numel(&mm, i); }
+  }
+  auto W = [&](int i) { return prm[i]; };
+  auto Gp = [&](int i) { return grad ? grad + goff[i] : nullptr; };
+  auto lp = [&](int l, int k) { return 3 + 16 * l + k; };
+  const int pt = 3 + 16 * L;
+#define LAUNCH(kernel, grid, block, smem, ...)                       \
+  do {                                                               \
+    kernel<<<grid, block, smem, st>>>(__VA_ARGS__);                  \
+    ++g_kernel_launches;                                             \
+  } while (0)
+#define GEMM(...) do { if ((rc = gemm_rm(h, __VA_ARGS__))) return rc; } while (0)
+
+  // ============================== forward ==============================
+  LAUNCH(embed_fwd_kernel, blocks_for(Md), kTB, 0, D, state, action, goal, noise, sigma, goal_keep, pred_last, W(0), W(1), W(2),
+         W(pt + 2), W(pt + 3), W(pt + 4), W(pt + 5), A[0].Xin, xin);
+  const int ln_grid = (M + 7) / 8;
+  for (int l = 0; l < L; ++l) {
+    Layer& a = A[l];
+    LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, a.Xin, M, d, W(lp(l, 0)), W(lp(l, 1)), a.H1, a.st1);
+    // q | k | v column blocks (reference parameter order: key, query, value)
+    GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 6)), d, 0.f, a.QKV, 3 * d);
+    GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 4)), d, 0.f, a.QKV + d, 3 * d);
+    GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 8)), d, 0.f, a.QKV + 2 * d, 3 * d);
+    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.QKV, W(lp(l, 7)), (size_t)M, d, 3 * d);
+    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.QKV + d, W(lp(l, 5)), (size_t)M, d, 3 * d);
+    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.QKV + 2 * d, W(lp(l, 9)), (size_t)M, d, 3 * d);
+    LAUNCH(attn_fwd_kernel, (B * D.H * D.T + 7) / 8, 256, 0, D, a.QKV, a.P, a.Y);
+    BESO_CUDA(cudaMemcpyAsync(a.Xmid, a.Xin, Md * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GEMM(false, true, M, d, d, 1.f, a.Y, d, W(lp(l, 10)), d, 1.f, a.Xmid, d);
+    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.Xmid, W(lp(l, 11)), (size_t)M, d, d);
+    LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, a.Xmid, M, d, W(lp(l, 2)), W(lp(l, 3)), a.H2, a.st2);
+    GEMM(false, true, M, F, d, 1.f, a.H2, d, W(lp(l, 12)), d, 0.f, a.U, F);
+    LAUNCH(bias_add_kernel, blocks_for(MF), kTB, 0, a.U, W(lp(l, 13)), (size_t)M, F, F);
+    LAUNCH(gelu_fwd_kernel, blocks_for(MF), kTB, 0, a.U, a.Gg, MF);
+    float* Xnext = (l + 1 < L) ? A[l + 1].Xin : XL;
+    BESO_CUDA(cudaMemcpyAsync(Xnext, a.Xmid, Md * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GEMM(false, true, M, d, F, 1.f, a.Gg, F, W(lp(l, 14)), F, 1.f, Xnext, d);
+    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, Xnext, W(lp(l, 15)), (size_t)M, d, d);
+  }
+  LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, XL, M, d, W(pt), W(pt + 1), HF, stf);
+  LAUNCH(gather_action_rows_kernel, blocks_for(nBt * d), kTB, 0, D, HF, HA);
+  GEMM(false, true, (int)nBt, D.act, d, 1.f, HA, d, W(pt + 6), d, 0.f, pred, D.act);
+  LAUNCH(bias_add_kernel, blocks_for(nBt * D.act), kTB, 0, pred, W(pt + 7), nBt, D.act, D.act);
+  const int lgrid = (int)(blocks_for(nBt * D.act) < 1024 ? blocks_for(nBt * D.act) : 1024);
+  LAUNCH(loss_kernel, lgrid, kTB, 0, D, pred, action, noise, sigma, pred_last, dpred, partial);
+  LAUNCH(sum_partials_kernel, 1, 32, 0, partial, lgrid, loss_out);
+  BESO_CUDA(cudaGetLastError());
+  if (!grad) return BESO_OK;
+
+  // ============================== backward ==============================
+  // column sums (bias gradients) as A^T 1 with a library GEMV: bandwidth-bound, full-chip parallel
+  LAUNCH(fill_kernel, blocks_for((size_t)M), kTB, 0, ones, (size_t)M, 1.0f);
+  const float one = 1.f, zero = 0.f;
+  auto colsum = [&](const float* Am, int rows, int N, int lda, float* out) -> int {
+    BESO_CUBLAS(cublasSgemv(h, CUBLAS_OP_N, N, rows, &one, Am, lda, ones, 1, &zero, out, 1));
+    return BESO_OK;
+  };
+#define COLSUM(...) do { if ((rc = colsum(__VA_ARGS__))) return rc; } while (0)
+  // LayerNorm backward: dX (+)= ..., then weight / bias gradients from column sums
+  auto ln_bwd = [&](const float* dYv, const float* Xv, const float* stv, const float* wv, int accumulate, float* dw, float* db) -> int {
+    LAUNCH(ln_bwd_kernel, ln_grid, 256, 0, dYv, Xv, stv, wv, M, d, dX, accumulate, dT);
+    int r2 = colsum(dT, M, d, d, dw);
+    if (r2) return r2;
+    return colsum(dYv, M, d, d, db);
+  };
+#define LNBWD(...) do { if ((rc = ln_bwd(__VA_ARGS__))) return rc; } while (0)
+  // head
+  GEMM(true, false, D.act, d, (int)nBt, 1.f, dpred, D.act, HA, d, 0.f, Gp(pt + 6), d);
+  COLSUM(dpred, (int)nBt, D.act, D.act, Gp(pt + 7));
+  GEMM(false, false, (int)nBt, d, D.act, 1.f, dpred, D.act, W(pt + 6), d, 0.f, HA, d);           // HA <- dHA
+  LAUNCH(scatter_action_rows_kernel, blocks_for(Md), kTB, 0, D, HA, dH);                         // dH <- dHF
+  LNBWD(dH, XL, stf, W(pt), 0, Gp(pt), Gp(pt + 1));                                              // dX = d loss / d X_L
+  for (int l = L - 1; l >= 0; --l) {
+    Layer& a = A[l];
+    // ---- MLP branch: X_next = X_mid + gelu(H2 W1^T + b1) W2^T + b2 ----
+    GEMM(true, false, d, F, M, 1.f, dX, d, a.Gg, F, 0.f, Gp(lp(l, 14)), F);                       // dW2 = dX^T G
+    COLSUM(dX, M, d, d, Gp(lp(l, 15)));
+    GEMM(false, false, M, F, d, 1.f, dX, d, W(lp(l, 14)), F, 0.f, dBig, F);                        // dG = dX W2
+    LAUNCH(gelu_bwd_kernel, blocks_for(MF), kTB, 0, a.U, dBig, MF);                               // dU
+    GEMM(true, false, F, d, M, 1.f, dBig, F, a.H2, d, 0.f, Gp(lp(l, 12)), d);                     // dW1 = dU^T H2
+    COLSUM(dBig, M, F, F, Gp(lp(l, 13)));
+    GEMM(false, false, M, d, F, 1.f, dBig, F, W(lp(l, 12)), d, 0.f, dH, d);                        // dH2 = dU W1
+    LNBWD(dH, a.Xmid, a.st2, W(lp(l, 2)), 1, Gp(lp(l, 2)), Gp(lp(l, 3)));                          // dX = d/dX_mid
+    // ---- attention branch: X_mid = X_in + Y Wp^T + bp ----
+    GEMM(true, false, d, d, M, 1.f, dX, d, a.Y, d, 0.f, Gp(lp(l, 10)), d);                         // dWp
+    COLSUM(dX, M, d, d, Gp(lp(l, 11)));
+    GEMM(false, false, M, d, d, 1.f, dX, d, W(lp(l, 10)), d, 0.f, dY, d);                          // dY = dX Wp
+    LAUNCH(attn_bwd_kernel, B * D.H, 128, (size_t)D.T * D.T * sizeof(float), D, a.QKV, a.P, dY, dQKV);
+    GEMM(true, false, d, d, M, 1.f, dQKV, 3 * d, a.H1, d, 0.f, Gp(lp(l, 6)), d);                   // dWq
+    GEMM(true, false, d, d, M, 1.f, dQKV + d, 3 * d, a.H1, d, 0.f, Gp(lp(l, 4)), d);               // dWk
+    GEMM(true, false, d, d, M, 1.f, dQKV + 2 * d, 3 * d, a.H1, d, 0.f, Gp(lp(l, 8)), d);           // dWv
+    COLSUM(dQKV, M, d, 3 * d, Gp(lp(l, 7)));
+    COLSUM(dQKV + d, M, d, 3 * d, Gp(lp(l, 5)));
+    COLSUM(dQKV + 2 * d, M, d, 3 * d, Gp(lp(l, 9)));
+    GEMM(false, false, M, d, d, 1.f, dQKV, 3 * d, W(lp(l, 6)), d, 0.f, dH, d);                     // dH1
+    GEMM(false, false, M, d, d, 1.f, dQKV + d, 3 * d, W(lp(l, 4)), d, 1.f, dH, d);
+    GEMM(false, false, M, d, d, 1.f, dQKV + 2 * d, 3 * d, W(lp(l, 8)), d, 1.f, dH, d);
+    LNBWD(dH, a.Xin, a.st1, W(lp(l, 0)), 1, Gp(lp(l, 0)), Gp(lp(l, 1)));                           // dX = d/dX_in
+  }
+  // ---- embeddings ----
+  const int n_pos = D.G + D.t + 1;
+  LAUNCH(pos_grad_kernel, blocks_for((size_t)n_pos * d), kTB, 0, D, dX, n_pos, Gp(0));
+  struct Kind { int kind, per, kin, pw, pb; };
+  const Kind kinds[3] = {{0, 1, 1, pt + 2, pt + 3}, {1, D.G + D.t, D.obs, 1, 2}, {2, D.t, D.act, pt + 4, pt + 5}};
+  for (const Kind& k : kinds) {
+    const size_t rows = (size_t)B * k.per;
+    float* dRows = gRows;
+    float* inRows = gRows + rows * d;
+    LAUNCH(gather_embed_rows_kernel, blocks_for(rows * (d + k.kin)), kTB, 0, D, k.kind, dX, state, goal, goal_keep, xin, sigma,
+           dRows, inRows);
+    GEMM(true, false, d, k.kin, (int)rows, 1.f, dRows, d, inRows, k.kin, 0.f, Gp(k.pw), k.kin);    // dW = dRows^T in
+    COLSUM(dRows, (int)rows, d, d, Gp(k.pb));
+  }
+  BESO_CUDA(cudaGetLastError());
+#undef LAUNCH
+#undef GEMM
+#undef COLSUM
+#undef LNBWD
+  return BESO_OK;
+}
+
+}  // namespace beso
+
+// ================================ NCCL gradient exchange ======================================================
+struct beso_comm { ncclComm_t comm = nullptr; int rank = 0, world = 1, device = 0; };
+
+namespace {
+__global__ void scale_kernel(float* x, size_t n, float s) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
+}
+int nccl_fail(ncclResult_t r, const char* what) {
+  beso::set_error(std::string("NCCL error: ") + ncclGetErrorString(r) + " at " + what);
+  return BESO_E_NCCL;
+}
+}  // namespace
+#define BESO_NCCL(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) return nccl_fail(_r, #expr); } while (0)
+
 extern "C" {
-int beso_loss_fwd_bwd(beso_plan*, const float*, const float*, const float*, const float*, const float*,
-                      const float*, float*, float*, int, uint32_t, void*) {
-  beso::set_error("beso_loss_fwd_bwd: not implemented in this build"); return BESO_E_UNSUPPORTED;
+
+int beso_comm_unique_id(char* out128) {
+  if (!out128) { beso::set_error("null buffer"); return BESO_E_INVALID; }
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  BESO_NCCL(ncclGetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return BESO_OK;
 }
-int beso_comm_unique_id(char*) { beso::set_error("comm: not implemented in this build"); return BESO_E_UNSUPPORTED; }
-int beso_comm_init(int, int, const char*, int, beso_comm**) { beso::set_error("comm: not implemented in this build"); return BESO_E_UNSUPPORTED; }
-int beso_comm_destroy(beso_comm*) { return BESO_OK; }
-int beso_allreduce_grads(beso_comm*, float*, size_t, float, void*) { beso::set_error("comm: not implemented in this build"); return BESO_E_UNSUPPORTED; }
+
+int beso_comm_init(int rank, int world, const char* unique_id128, int device, beso_comm** out) {
+  if (!out || !unique_id128 || world < 1 || rank < 0 || rank >= world) { beso::set_error("bad comm arguments"); return BESO_E_INVALID; }
+  BESO_CUDA(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  beso_comm* c = new beso_comm();
+  c->rank = rank; c->world = world; c->device = device;
+  ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
+  if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
+  *out = c;
+  return BESO_OK;
 }
+
+int beso_comm_destroy(beso_comm* c) {
+  if (!c) return BESO_OK;
+  if (c->comm) ncclCommDestroy(c->comm);
+  delete c;
+  return BESO_OK;
+}
+
+// One all-reduce(sum) of the flat gradient, then *scale (1/world for the global-batch mean).
+int beso_allreduce_grads(beso_comm* c, float* flat_grad_dev, size_t n, float scale, void* stream) {
+  if (!c || !flat_grad_dev) { beso::set_error("null comm or buffer"); return BESO_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->world > 1) BESO_NCCL(ncclAllReduce(flat_grad_dev, flat_grad_dev, n, ncclFloat, ncclSum, c->comm, st));
+  if (scale != 1.0f) {
+    const int grid = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+    scale_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(flat_grad_dev, n, scale);
+    ++beso::g_kernel_launches;
+    BESO_CUDA(cudaGetLastError());
+  }
+  return BESO_OK;
+}
+
+}  // extern "C"

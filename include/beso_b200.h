@@ -58,6 +58,8 @@ enum {
 #define BESO_FLAG_UNCOND 1u /* DiffusionGPT.forward(uncond=True): goals zeroed (score_gpts.py:301-302)      */
 #define BESO_FLAG_CFG 2u    /* ClassifierFreeSampleModel.forward (classifier_free_sampler.py:35-49):
                                out_u + cond_lambda * (out_c - out_u), both branches in one launch           */
+#define BESO_FLAG_PRED_LAST 8u /* GCDenoiser.loss(pred_last_action_only=True): noise only on, and loss only of, the
+                                  last step (score_wrappers.py:59-66, 76-77)                                     */
 #define BESO_FLAG_INNER 4u  /* return DiffusionGPT.forward(state, action, goal, sigma) itself, i.e. without
                                the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
 
@@ -102,6 +104,9 @@ int beso_plan_destroy(beso_plan* plan);
 int beso_plan_pack_weights(beso_plan* plan, int slot, const float* const* params_dev, int n_params,
                            void* stream);
 int beso_plan_select_weights(beso_plan* plan, int slot);
+/* Registers the raw fp32 parameter pointers of `slot` without re-packing (training steps change the
+ * weights every iteration; the loss path reads them directly). */
+int beso_plan_set_params(beso_plan* plan, int slot, const float* const* params_dev, int n_params);
 
 /* Replaces: GCDenoiser.forward (score_wrappers.py:81-96) -> DiffusionGPT.forward
  * (score_gpts.py:272-358); with BESO_FLAG_CFG also ClassifierFreeSampleModel.forward.

@@ -1,0 +1,88 @@
+"""GPU: GCDenoiser.loss + backward through the C ABI against the reference's loss and autograd gradients
+(golden fixtures), and size-independent properties at BASELINE config 3 size (batch 4096).
+
+Tolerance: fp32 path; loss rtol 1e-4, gradients rtol 2e-3 / atol 1e-6 * max|grad| (different summation
+order over up to 4096 x 23 rows than ATen's)."""
+import pytest
+import torch
+
+from conftest import golden_weights, load_golden, to_oracle_cfg
+from beso_b200 import B256
+from beso_b200.denoiser import build_denoiser
+from beso_b200.synth import synthetic_inputs, synthetic_state_dict
+from beso_b200.training import loss_and_flat_grad
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in a.items()}
+
+
+@pytest.mark.parametrize("name", ["loss_B256", "loss_K256"])
+def test_loss_and_gradients_match_reference_golden(name, cuda_device):
+    cfg, meta, a = load_golden(name)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=golden_weights(cfg, meta))
+    m.train()
+    m.training = True
+    g = cuda(a, cuda_device)
+    loss = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"])
+    torch.testing.assert_close(loss.cpu(), a["loss"], rtol=1e-4, atol=1e-7)
+    m.zero_grad()
+    loss.backward()
+    names = [str(n) for n in a["grad_names"]]
+    params = dict(m.named_parameters())
+    for n, ref_norm in zip(names, a["grad_norms"]):
+        gr = params[n].grad
+        assert gr is not None, n
+        got_norm = gr.double().norm().item()
+        assert abs(got_norm - ref_norm) <= 2e-3 * ref_norm + 1e-9, (n, got_norm, ref_norm)
+        flat = gr.reshape(-1).cpu()
+        got = flat if flat.numel() <= 4096 else flat[::97][:4096]
+        want = a["grad::" + n]
+        torch.testing.assert_close(got, want, rtol=2e-3, atol=1e-6 * float(want.abs().max()) + 1e-10)
+    loss_last = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"], pred_last_action_only=True)
+    torch.testing.assert_close(loss_last.cpu(), a["loss_pred_last"], rtol=1e-4, atol=1e-7)
+
+
+def test_cfg3_full_size_properties(cuda_device):
+    """BASELINE config 3: block-push score-GPT training step at batch 4096."""
+    from oracle import beso_oracle as O
+    cfg = B256
+    sd = synthetic_state_dict(cfg, 41)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd)
+    m.train()
+    x = synthetic_inputs(cfg, 4096, seed=42, sigma_min=0.05)
+    g = cuda(x, cuda_device)
+    loss, flat = loss_and_flat_grad(m, g["state"], g["clean"], g["goal"], g["noise"], g["sigma"])
+    assert torch.isfinite(loss) and torch.isfinite(flat).all()
+    with torch.no_grad():
+        want = O.denoiser_loss(sd, to_oracle_cfg(cfg), x["state"], x["clean"], x["goal"], x["noise"].clone(), x["sigma"])
+    torch.testing.assert_close(loss.cpu(), want, rtol=1e-4, atol=1e-7)
+    # the loss is a plain mean over sequences: the full-batch gradient is the mean of the half-batch gradients
+    halves = []
+    for sl in (slice(0, 2048), slice(2048, 4096)):
+        l_h, f_h = loss_and_flat_grad(m, g["state"][sl], g["clean"][sl], g["goal"][sl], g["noise"][sl], g["sigma"][sl])
+        halves.append((l_h, f_h))
+    torch.testing.assert_close(0.5 * (halves[0][0] + halves[1][0]), loss, rtol=1e-5, atol=1e-8)
+    mean_grad = 0.5 * (halves[0][1] + halves[1][1])
+    torch.testing.assert_close(mean_grad, flat, rtol=1e-3, atol=1e-6 * float(flat.abs().max()))
+    # deterministic
+    loss2, flat2 = loss_and_flat_grad(m, g["state"], g["clean"], g["goal"], g["noise"], g["sigma"])
+    assert torch.equal(loss, loss2)
+
+
+def test_goal_mask_changes_loss_and_matches_oracle(cuda_device):
+    """CFG training: element-wise Bernoulli goal mask (score_gpts.py:360-371), drawn by the caller."""
+    from oracle import beso_oracle as O
+    cfg, meta, a = load_golden("loss_K256")
+    sd = golden_weights(cfg, meta)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd)
+    g = cuda(a, cuda_device)
+    keep = (torch.rand(a["goal"].shape, generator=torch.Generator().manual_seed(3)) > 0.3).float()
+    loss, _ = loss_and_flat_grad(m, g["state"], g["action"], g["goal"], g["noise"], g["sigma"], goal_keep=keep.to(cuda_device))
+    with torch.no_grad():
+        want = O.denoiser_loss(sd, to_oracle_cfg(cfg), a["state"], a["action"], a["goal"], a["noise"].clone(), a["sigma"],
+                               goal_keep=keep)
+    torch.testing.assert_close(loss.cpu(), want, rtol=1e-4, atol=1e-7)
+    assert abs(float(loss.cpu()) - float(a["loss"])) > 1e-6
