@@ -36,11 +36,13 @@ def test_loss_and_gradients_match_reference_golden(name, cuda_device):
         gr = params[n].grad
         assert gr is not None, n
         got_norm = gr.double().norm().item()
-        assert abs(got_norm - ref_norm) <= 2e-3 * ref_norm + 1e-9, (n, got_norm, ref_norm)
+        assert abs(got_norm - ref_norm) <= 2e-3 * ref_norm + 1e-7, (n, got_norm, ref_norm)
         flat = gr.reshape(-1).cpu()
         got = flat if flat.numel() <= 4096 else flat[::97][:4096]
         want = a["grad::" + n]
-        torch.testing.assert_close(got, want, rtol=2e-3, atol=1e-6 * float(want.abs().max()) + 1e-10)
+        # floor: gradients that are analytically zero (attn.key.bias: softmax is shift-invariant) are pure
+        # fp32 round-off (~1e-10) in both implementations
+        torch.testing.assert_close(got, want, rtol=2e-3, atol=1e-6 * float(want.abs().max()) + 2e-8)
     loss_last = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"], pred_last_action_only=True)
     torch.testing.assert_close(loss_last.cpu(), a["loss_pred_last"], rtol=1e-4, atol=1e-7)
 
