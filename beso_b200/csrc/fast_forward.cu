@@ -25,9 +25,11 @@
 //    operand carries the raw inputs plus one-hot token-position columns whose B rows hold
 //    (bias + pos_emb) split into bf16 hi + lo, so X starts exact to ~2^-17.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "fast.cuh"
@@ -42,8 +44,11 @@ namespace {
 // ---- fixed geometry (d = 256, 4 heads of 64) ---------------------------------------------------
 constexpr int kD = 256, kH = 4, kHS = 64, kFF = 1024;
 constexpr int kRows = 128;
-constexpr int kThreads = 384;             // warp 0 producer, warp 1 MMA + TMEM alloc, 2-3 idle, 4-11 compute
-constexpr int kComputeWarp0 = 4, kComputeThreads = 256;
+constexpr int kThreads = 384;             // warps 0-7 compute, 8-9 attention helpers, 10 producer, 11 MMA + TMEM alloc
+// The warp scheduler prefers higher warp ids among eligible warps, so the two latency-critical
+// single-warp roles get the highest ids of their sub-partitions.
+constexpr int kProducerWarp = 10, kMmaWarp = 11, kHelperWarp0 = 8;
+constexpr int kComputeWarp0 = 0, kComputeThreads = 256;
 constexpr int kMaxTokens = 24;            // one-hot columns available in the misc atom
 constexpr int kOneHot0 = 16;              // first one-hot column of the misc atom
 constexpr int kMaxAct = 13, kMaxObs = 64;
@@ -275,6 +280,13 @@ struct Compute {
   __device__ void stamp() { if (tl != nullptr) *tl++ = clock64(); }
   __device__ uint32_t bar(int id) const { return sbase + kSmBars + id * 8; }
   __device__ void wait(int id) { spin_wait(bar(id), (phases >> id) & 1u); phases ^= 1u << id; }
+  __device__ void wait2(int a, int b) {          // two barriers, tests issued back to back
+    const uint32_t pa = (phases >> a) & 1u, pb = (phases >> b) & 1u;
+    const bool ra = mbar_try_wait(bar(a), pa), rb = mbar_try_wait(bar(b), pb);
+    if (!ra) wait_timeout(bar(a), pa);
+    if (!rb) wait_timeout(bar(b), pb);
+    phases ^= (1u << a) | (1u << b);
+  }
   int cg;                            // CTAs per MMA group (1 or 2)
   // compute -> MMA barriers live in the leader CTA (rank 0) of the pair
   __device__ void arrive(int id) const {
@@ -288,17 +300,24 @@ struct Compute {
 // X (TMEM) is only read: every projection / MLP bias is added to X up front by the embedding GEMM and
 // `pend` holds minus the biases that are not due yet at this point of the network (see fast_pack).
 __device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* trace_row) {
+  // X is read from TMEM ONCE (TMEM reads are the scarce resource of this phase, ~64 B/clk per SM): the
+  // 128 values of this thread, with the pending biases already added, wait for the row statistics as
+  // 64 packed fp16 pairs in registers (2^-11 relative, well below the bf16 rounding of the result).
   float va[32], vb[32];
+  __half2 keep[64];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   const int col0 = c.hf * 128;
   const bool tracing = trace_row != nullptr;
-  auto pass1 = [&](float (&v)[32], int col) {
+  auto pass1 = [&](float (&v)[32], int ch) {
+    const int col = col0 + ch * 32;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
       const float a0 = v[i] + pd.x, a1 = v[i + 1] + pd.y, a2 = v[i + 2] + pd.z, a3 = v[i + 3] + pd.w;
       s0 += a0; s1 += a1; s2 += a2; s3 += a3;
       q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+      keep[ch * 16 + (i >> 1)] = __floats2half2_rn(a0, a1);
+      keep[ch * 16 + (i >> 1) + 1] = __floats2half2_rn(a2, a3);
       if (tracing) {
         float* tr = trace_row + col + i;
         tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3;
@@ -309,16 +328,15 @@ __device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* t
   tmem_ld32(c.lane_addr(kColX + col0), va);
   tmem_wait_ld();
   tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
-  pass1(va, col0);
+  pass1(va, 0);
   tmem_wait_ld();
   tmem_ld32(c.lane_addr(kColX + col0 + 64), va);
-  pass1(vb, col0 + 32);
+  pass1(vb, 1);
   tmem_wait_ld();
   tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
-  pass1(va, col0 + 64);
+  pass1(va, 2);
   tmem_wait_ld();
-  tmem_ld32(c.lane_addr(kColX + col0), va);          // first chunk of the second pass
-  pass1(vb, col0 + 96);
+  pass1(vb, 3);
   const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
   float2* stats = reinterpret_cast<float2*>(c.sm + kSmStats);
   stats[c.hf * kRows + c.row] = make_float2(sum, sq);
@@ -329,31 +347,18 @@ __device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* t
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
   // the LayerNorm weight / bias are folded into the Linear that consumes A (see fast_pack)
-  auto pass2 = [&](float (&v)[32], int col) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
-      v[i] = fmaf(v[i] + pd.x, rstd, nmr);
-      v[i + 1] = fmaf(v[i + 1] + pd.y, rstd, nmr);
-      v[i + 2] = fmaf(v[i + 2] + pd.z, rstd, nmr);
-      v[i + 3] = fmaf(v[i + 3] + pd.w, rstd, nmr);
+  for (int ch8 = 0; ch8 < 16; ++ch8) {             // 16 chunks of 8 columns = 16 bytes of bf16 each
+    uint4 u;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(keep[ch8 * 4 + k]);
+      w[k] = pack_bf16x2(fmaf(f.x, rstd, nmr), fmaf(f.y, rstd, nmr));
     }
-    uint8_t* atom = c.sm + kSmA + (col >> 6) * 16384;
-    const int chunk0 = (col & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, chunk0 + q, v + q * 8);
-  };
-  tmem_wait_ld();
-  tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
-  pass2(va, col0);
-  tmem_wait_ld();
-  tmem_ld32(c.lane_addr(kColX + col0 + 64), va);
-  pass2(vb, col0 + 32);
-  tmem_wait_ld();
-  tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
-  pass2(va, col0 + 64);
-  tmem_wait_ld();
-  pass2(vb, col0 + 96);
+    const int col = col0 + ch8 * 8;
+    *reinterpret_cast<uint4*>(c.sm + kSmA + (col >> 6) * 16384 + sw128_offset(c.row, (col & 63) >> 3)) = u;
+  }
   fence_async_smem();
   tc_fence_before();
   c.arrive(B_A_READY);
@@ -572,23 +577,29 @@ __device__ __forceinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uin
   const uint32_t acc = flags & 1u;
   long long t0 = 0, t1 = 0, t2 = 0;
   if (tl != nullptr) t0 = clock64();
-  if (w0 != kNone) {
-    const uint32_t bar = sbase + kSmBars + w0 * 8, par = (phases >> w0) & 1u;
-    if (CG == 2) spin_wait_cluster(bar, par); else spin_wait(bar, par);
-    phases ^= 1u << w0;
-  }
-  if (w1 != kNone) {
-    const uint32_t bar = sbase + kSmBars + w1 * 8, par = (phases >> w1) & 1u;
-    if (CG == 2) spin_wait_cluster(bar, par); else spin_wait(bar, par);
-    phases ^= 1u << w1;
-  }
+  // All barrier tests of this group are issued back to back (their ~100-cycle latencies overlap); the slow
+  // path spins only on those that were not complete yet.
   const uint32_t slot = g & (kSlots - 1), par = (g >> 2) & 1u;
   const bool kk2 = (flags & 4u) != 0;
   const bool two = CG == 1 && (flags & 6u);
+  const uint32_t bw0 = sbase + kSmBars + (w0 != kNone ? w0 : 0u) * 8, pw0 = (phases >> (w0 & 31u)) & 1u;
+  const uint32_t bw1 = sbase + kSmBars + (w1 != kNone ? w1 : 0u) * 8, pw1 = (phases >> (w1 & 31u)) & 1u;
+  const uint32_t bf0 = sbase + kSmBars + (B_FULL0 + slot) * 8, bf1 = bf0 + 8;
+  const uint32_t bpf = sbase + kSmBars + (B_PFULL0 + slot) * 8;
+  bool r_w0 = true, r_w1 = true, r_f1 = true, r_pf = true;
+  if (w0 != kNone) r_w0 = CG == 2 ? mbar_try_wait_cluster(bw0, pw0) : mbar_try_wait(bw0, pw0);
+  if (w1 != kNone) r_w1 = CG == 2 ? mbar_try_wait_cluster(bw1, pw1) : mbar_try_wait(bw1, pw1);
+  const bool r_f0 = mbar_try_wait(bf0, par);
+  if (two) r_f1 = mbar_try_wait(bf1, par);
+  if (CG == 2) r_pf = mbar_try_wait_cluster(bpf, par);
+  if (!r_w0) { if (CG == 2) wait_timeout_cluster(bw0, pw0); else wait_timeout(bw0, pw0); }
+  if (!r_w1) { if (CG == 2) wait_timeout_cluster(bw1, pw1); else wait_timeout(bw1, pw1); }
+  if (w0 != kNone) phases ^= 1u << w0;
+  if (w1 != kNone) phases ^= 1u << w1;
   if (tl != nullptr) t1 = clock64();
-  spin_wait(sbase + kSmBars + (B_FULL0 + slot) * 8, par);
-  if (two) spin_wait(sbase + kSmBars + (B_FULL0 + slot + 1) * 8, par);
-  if (CG == 2) spin_wait_cluster(sbase + kSmBars + (B_PFULL0 + slot) * 8, par);
+  if (!r_f0) wait_timeout(bf0, par);
+  if (!r_f1) wait_timeout(bf1, par);
+  if (!r_pf) wait_timeout_cluster(bpf, par);
   if (tl != nullptr) t2 = clock64();
   tc_fence_after();
   const uint64_t a_desc = smem_desc_sw128(sbase + a_off);
@@ -743,7 +754,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (threadIdx.x == 32) {
+  if (threadIdx.x == kMmaWarp * 32) {
     // group table for [embedding | one layer | head]: the single-warp roles replay it with one LDS per group
     uint4* tab = reinterpret_cast<uint4*>(sm + kSmProg);
     int i = 0;
@@ -753,7 +764,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     });
   }
   if (CG == 2) cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive
-  if (warp == 1) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
+  if (warp == kMmaWarp) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
   for (uint32_t i = threadIdx.x; i < (kSmVecA - kSmU) / 16; i += kThreads)      // padding rows must stay finite
     reinterpret_cast<uint4*>(sm + kSmU)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
@@ -775,7 +786,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     li = li == 51 ? 0 : li + 1;
     return r;
   };
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ======================= weight-tape producer =======================
     uint32_t g = 0;
     for (int it = 0; it < my_tiles * p.evals; ++it) {
@@ -789,7 +800,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         off += n * 128u * (kk2 ? 2u : 1u);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (leader) / full-barrier forwarder (peer CTA of a pair) ==========
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     uint32_t g = 0, phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
@@ -807,43 +818,37 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       } else {
         long long* tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
         int li = 0;
-        if (tl != nullptr) {
-#pragma unroll 1
-          for (int i = 0; i < n_groups_eval; ++i) {
-            const uint4 cur = gtab[table_index(i, li)];
-            const uint64_t r = mma_step<CG, true>(cur.x, cur.y & 0xFFFFu, cur.y >> 16, cur.z, cur.w, sbase, tm, g, phases, tl);
-            tl += (cur.z & 6u) ? 10 : 5;
-            g = (uint32_t)r;
-            phases = (uint32_t)(r >> 32);
-          }
-        } else {
-          // four groups per iteration, as straight-line code: consecutive groups then use different uniform
-          // registers for their descriptors, so setting up group i+1 does not wait for group i's MMAs to issue
-          auto run = [&](const uint4 c) {
-            const uint64_t r = mma_step<CG, false>(c.x, c.y & 0xFFFFu, c.y >> 16, c.z, c.w, sbase, tm, g, phases, nullptr);
-            g = (uint32_t)r;
-            phases = (uint32_t)(r >> 32);
-          };
+        // four groups per iteration, as straight-line code: consecutive groups then use different uniform
+        // registers for their descriptors, so setting up group i+1 does not wait for group i's MMAs to issue
+        auto run = [&](const uint4 c, auto tl_tag) {
+          constexpr bool TLV = decltype(tl_tag)::value;
+          const uint64_t r = mma_step<CG, TLV>(c.x, c.y & 0xFFFFu, c.y >> 16, c.z, c.w, sbase, tm, g, phases, tl);
+          g = (uint32_t)r;
+          phases = (uint32_t)(r >> 32);
+          if (TLV) tl += (c.z & 6u) ? 10 : 5;
+        };
+        auto loop = [&](auto tl_tag) {
           int i = 0;
 #pragma unroll 1
           for (; i + 4 <= n_groups_eval; i += 4) {
             const uint4 c0 = gtab[table_index(i, li)], c1 = gtab[table_index(i + 1, li)];
             const uint4 c2 = gtab[table_index(i + 2, li)], c3 = gtab[table_index(i + 3, li)];
-            run(c0); run(c1); run(c2); run(c3);
+            run(c0, tl_tag); run(c1, tl_tag); run(c2, tl_tag); run(c3, tl_tag);
           }
 #pragma unroll 1
-          for (; i < n_groups_eval; ++i) run(gtab[table_index(i, li)]);
-        }
+          for (; i < n_groups_eval; ++i) run(gtab[table_index(i, li)], tl_tag);
+        };
+        if (tl != nullptr) loop(std::true_type{}); else loop(std::false_type{});
       }
     }
-  } else if (warp < kComputeWarp0) {
-    // ======================= attention helper warps (2, 3) =======================
+  } else if (warp >= kHelperWarp0) {
+    // ======================= attention helper warps (8, 9) =======================
     uint32_t y_phase = 1;
     for (int it = 0; it < my_tiles * p.evals * p.L * kH; ++it) {
       attn_sync();
       spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
       y_phase ^= 1u;
-      attention_head(sm, sbase, 8 + (warp - 2), lane, p.S, p.T);
+      attention_head(sm, sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -936,9 +941,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           c.stamp();
           for (int ch = 0; ch < 8; ++ch) {
             const int b = ch & 1;
-            c.wait(b ? B_ACC_FULL1 : B_ACC_FULL0);
+            c.wait2(b ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
-            c.wait(b ? B_OP_EMPTY1 : B_OP_EMPTY0);          // H[b] consumed by FC2(ch-2)
             c.stamp();
             drain_gelu(c, b, vecM + 3 * kD + ch * 128);
             c.stamp();
@@ -1032,7 +1036,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();          // the pair's MMAs read both CTAs' shared memory and TMEM
-  if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem, 512); else tmem_dealloc(tmem, 512); }
+  if (warp == kMmaWarp) { if (CG == 2) tmem_dealloc_cg2(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 // ================================ tcgen05 issue-rate probe ==========================================

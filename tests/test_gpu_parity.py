@@ -3,8 +3,9 @@ against the oracle on seeded inputs, and through size-independent properties at 
 
 Tolerances (written here, never loosened silently):
   precise mode  rtol 1e-3, atol 1e-5   -- the north-star tolerance, against the fp32 reference
-  fast mode     rtol 2e-2, atol 2e-2   -- bf16 tensor-core operands (the reference's own
-                                          bf16 autocast shows max |err| 4.5e-3..2.3e-2 vs its fp32 self)
+  fast mode     rtol 1e-2, atol 5e-3   -- bf16 tensor-core operands (the reference's own
+                                          bf16 autocast shows max |err| 4.5e-3..2.3e-2 vs its fp32 self;
+                                          this kernel measures max |err| <= 2.2e-3 on every case below)
 """
 import ctypes as C
 
@@ -20,7 +21,7 @@ from beso_b200.synth import synthetic_inputs, synthetic_state_dict
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=2e-2, atol=2e-2)}
+TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=1e-2, atol=5e-3)}
 FAST_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256"}
 FWD = ["fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_kitchen", "fwd_small_push",
        "fwd_mlp_head", "fwd_no_goal"]
@@ -268,3 +269,52 @@ def test_cta_pair_mode_parity(cuda_device):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_cg2.py")], env=env, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "cg2 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_rollout_shapes_batch1_growing_context_and_keep_last(mode, cuda_device):
+    """predict() call shapes: batch 1, t = 1..W (beso_agent.py:323-325), plus keep_last_actions (score_gpts.py:355-356)
+    and ragged batches that do not fill a tile."""
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    from oracle import beso_oracle as O
+    cfg = K256
+    sd = synthetic_state_dict(cfg, 61)
+    oc = to_oracle_cfg(cfg)
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+    for B, t in ((1, 1), (1, 2), (1, 7), (1, 10), (3, 5), (13, 10), (131, 3)):
+        x = synthetic_inputs(cfg, B, seed=62 + t, t=t)
+        g = cuda(x, cuda_device)
+        with torch.no_grad():
+            want = O.denoiser_forward(sd, oc, x["state"], x["action"], x["goal"], x["sigma"])
+        got = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
+        torch.testing.assert_close(got, want, **TOL[mode])
+        if B == 1 and t > 1:
+            with torch.no_grad():
+                want_k = O.denoiser_forward(sd, oc, x["state"], x["action"], x["goal"], x["sigma"], keep_last_actions=True)
+            got_k = m(g["state"], g["action"], g["goal"], g["sigma"], keep_last_actions=True).cpu()
+            torch.testing.assert_close(got_k, want_k, **TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_cfg5_heun_cfg_batch2048_properties(mode, cuda_device):
+    """BASELINE config 5: CFG (lambda = 2) 10-step Heun, batch 2048: determinism, batch-split invariance and a
+    slice against the oracle."""
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    from oracle import beso_oracle as O
+    cfg = K256
+    sd = synthetic_state_dict(cfg, 71)
+    m = ClassifierFreeSampleModel(build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd), cond_lambda=2.0)
+    x = synthetic_inputs(cfg, 2048, seed=72)
+    g = cuda(x, cuda_device)
+    sig = sampling.get_sigmas_exponential(10, 0.005, 1.0)
+    full = sampling.sample_heun(m, g["state"], g["noise"], g["goal"], sig)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, sampling.sample_heun(m, g["state"], g["noise"], g["goal"], sig))
+    parts = torch.cat([sampling.sample_heun(m, g["state"][:777], g["noise"][:777], g["goal"][:777], sig),
+                       sampling.sample_heun(m, g["state"][777:], g["noise"][777:], g["goal"][777:], sig)])
+    assert torch.equal(parts, full)
+    with torch.no_grad():
+        want = O.sample_heun(sd, to_oracle_cfg(cfg), x["state"][:3], x["noise"][:3], x["goal"][:3], sig, cond_lambda=2.0)
+    torch.testing.assert_close(full[:3].cpu(), want, **TOL[mode])
