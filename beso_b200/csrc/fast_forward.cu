@@ -11,13 +11,14 @@
 //    launch: all layers and all sampler steps.  Row r of the tile is TMEM lane r.
 //  * The fp32 residual stream X (128 x 256) lives in TMEM columns [0,256) and never leaves it:
 //    the attention-projection and MLP-down GEMMs accumulate straight into X (residual add for
-//    free); their biases are added by the next LayerNorm pass (tcgen05.ld -> add -> tcgen05.st).
+//    free); their biases are added once, up front, by the embedding GEMM and the LayerNorm passes subtract
+//    the ones that are not due yet.
 //  * TMEM columns [256,512) are two 128-column scratch accumulators (per-head QKV, FC1 chunks).
 //  * Every GEMM B operand comes from one linear "weight tape" in HBM/L2, pre-swizzled into the
 //    UMMA K-major SWIZZLE_128B image and ordered exactly as the MMA warp consumes it; a producer
 //    thread streams it with cp.async.bulk (TMA engine) through a 4 x 16 KB mbarrier ring.
-//  * One elected thread issues every tcgen05.mma, driven by a host-built "fill program" (one
-//    entry per ring fill: A operand, TMEM column, N, barriers to wait on / commit to).
+//  * One elected thread issues every tcgen05.mma, driven by a small group table in shared memory (one
+//    entry per ring group: A operand, TMEM column, N, barriers to wait on / commit to).
 //  * 8 compute warps (2 per TMEM lane quadrant) do the LayerNorms, the QKV drain, causal
 //    attention with mma.sync on bf16 Q/K/V staged in shared memory, erf-GELU, the action head
 //    read-out, the Karras pre-conditioning and the sampler update.
@@ -68,7 +69,6 @@ constexpr uint32_t kSmVecM = kSmVecA + kVecAFloats * 4;   // [bproj | ln2_w | ln
 constexpr uint32_t kVecMFloats = 1792;
 constexpr uint32_t kSmStats = kSmVecM + kVecMFloats * 4;  // [2][128] float2
 constexpr uint32_t kSmProg = kSmStats + 2048;
-constexpr int kProgEntries = 4 + 104 + 4;        // host-side fill program (tape layout): embedding | layer | head
 constexpr int kGroupEntries = 2 + 52 + 4;        // device-side group table in shared memory (uint4 each)
 constexpr uint32_t kXFloats = 832;
 constexpr uint32_t kSmBars = 230400;                // 32 mbarriers + tmem pointer
@@ -76,26 +76,15 @@ constexpr uint32_t kSmemBytes = kSmBars + 512;
 
 // barrier ids used by the fill program
 enum { B_A_READY = 0, B_X_DONE, B_ACC_FULL0, B_ACC_FULL1, B_ACC_EMPTY0, B_ACC_EMPTY1, B_OP_READY0, B_OP_READY1,
-       B_OP_EMPTY0, B_OP_EMPTY1, B_Y_READY, B_Y_EMPTY, B_FULL0, B_EMPTY0 = B_FULL0 + 4, B_PFULL0 = B_EMPTY0 + 4, B_COUNT = B_PFULL0 + 4 };
+       B_OP_EMPTY0, B_OP_EMPTY1, B_Y_READY, B_Y_EMPTY, B_OP_READY0B, B_OP_READY1B, B_FULL0, B_EMPTY0 = B_FULL0 + 4, B_PFULL0 = B_EMPTY0 + 4, B_COUNT = B_PFULL0 + 4 };
 constexpr int kAttnWarps = 10;            // 8 compute warps + warps 2-3 help with attention
 constexpr uint32_t kNone = 0xF;
 
 // TMEM columns
 constexpr uint32_t kColX = 0, kColS0 = 256, kColS1 = 384;
 
-struct __align__(8) Fill {     // one ring fill = rows x 64 bf16 of B operand + the MMAs that consume it
-  uint16_t a_off16;            // A atom, shared-memory offset / 16
-  uint16_t d_col;              // TMEM column of D
-  uint8_t n8;                  // N / 8 (rows of the fill)
-  uint8_t acc;                 // bit 0: accumulate into D on the first k-step; bit 1: this fill and the next one
-                               // sit in adjacent ring slots and are consumed by ONE wider MMA per k-step
-  uint8_t waits;               // two 4-bit barrier ids to wait on before issuing (0xF = none)
-  uint8_t commits;             // two 4-bit barrier ids to commit to afterwards
-};
-
 struct FastParams {
   const uint8_t* tape;         // per-eval weight tape
-  Fill prog[kProgEntries];     // fill program: embedding | one layer | head (kernel-parameter space)
   const float* vec;            // per layer: vecA (1536) | vecM (1792); then final vecA (1536)
   int n_fills, L, G, obs, act, T, t, S, n_tiles, B, evals;
   uint32_t flags;
@@ -159,7 +148,8 @@ __device__ __forceinline__ Group make_group(uint32_t type, uint32_t idx, uint32_
   } else if (type == J_FC2) {           // X += H_idx W2[:, chunk]^T
     const uint32_t b = idx & 1;
     q.a_off = (b ? kSmH1 : kSmH0) + kb * 16384; q.d_col = kColX; q.n = 256; q.acc = 1;
-    if (kb == 0) q.w0 = B_OP_READY0 + b;
+    q.w0 = (kb == 0 ? B_OP_READY0 : B_OP_READY0B) + b;     // one barrier per K atom of H (a parity wait must
+                                                           // never fall two phases behind)
     if (kb == 1) { q.c0 = B_OP_EMPTY0 + b; if (idx == 7) q.c1 = B_X_DONE; }
   } else {                              // action head, N = 16
     q.d_col = kColS0; q.n = 16; q.pair = false;
@@ -186,11 +176,6 @@ __device__ __forceinline__ void walk_eval(int L, F&& f) {
   }
 }
 
-__device__ __forceinline__ int prog_index(int f, int n_fills) {
-  if (f < 4) return f;
-  if (f >= n_fills - 4) return 108 + (f - (n_fills - 4));
-  return 4 + (f - 4) % 104;
-}
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void attn_sync() { asm volatile("bar.sync 2, 320;" ::: "memory"); }   // compute + helper warps
 __device__ __forceinline__ bool elect_one() {
@@ -367,12 +352,17 @@ __device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* t
 
 // Accumulator of head h (Q|K at S0, V at S1[0:64)) -> + bias -> bf16 Q|K|V staging rows.
 __device__ __noinline__ void drain_qkv(const Compute c, const float* bqkv_h) {
-  float v[32];
-#pragma unroll 1
-  for (int ch = 0; ch < 3; ++ch) {
-    const int col = c.hf * 96 + ch * 32;                 // 0..191 within [Q_h | K_h | V_h]
-    tmem_ld32(c.lane_addr(kColS0 + col), v);
-    tmem_wait_ld();
+  // all TMEM reads first, then the accumulator is handed back to the MMA warp (QKV of the next head can
+  // start) while this thread still converts and stores
+  float v0[32], v1[32], v2[32];
+  const int colb = c.hf * 96;                            // 0..191 within [Q_h | K_h | V_h]
+  tmem_ld32(c.lane_addr(kColS0 + colb), v0);
+  tmem_ld32(c.lane_addr(kColS0 + colb + 32), v1);
+  tmem_ld32(c.lane_addr(kColS0 + colb + 64), v2);
+  tmem_wait_ld();
+  tc_fence_before();
+  c.arrive(B_ACC_EMPTY0);
+  auto emit = [&](const float (&v)[32], int col) {
     uint8_t* dst = c.sm + kSmQkv + (uint32_t)c.row * kQkvStride + col * 2;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -385,8 +375,8 @@ __device__ __noinline__ void drain_qkv(const Compute c, const float* bqkv_h) {
       u.w = pack_bf16x2(v[q * 8 + 6] + b1.z, v[q * 8 + 7] + b1.w);
       *reinterpret_cast<uint4*>(dst + q * 16) = u;
     }
-  }
-  tc_fence_before();
+  };
+  emit(v0, colb); emit(v1, colb + 32); emit(v2, colb + 64);
 }
 
 // Causal softmax(Q K^T) V for every sequence of the tile, one warp per sequence, mma.sync bf16.
@@ -500,13 +490,18 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU -> bf16 -> H[b] (two K atoms).
 __device__ __noinline__ void drain_gelu(const Compute c, int b, const float* b1c) {
-  float v[32];
-  uint8_t* atom = c.sm + (b ? kSmH1 : kSmH0) + c.hf * 16384;
-#pragma unroll 1
-  for (int ch = 0; ch < 2; ++ch) {
-    const int col = c.hf * 64 + ch * 32;
-    tmem_ld32(c.lane_addr((b ? kColS1 : kColS0) + col), v);
-    tmem_wait_ld();
+  // Both 32-column pieces of this thread are read first and the accumulator is released at once (FC1 of
+  // chunk c+2 can start).  All 8 warps then finish K atom 0 of H before atom 1, and signal OP_READY after
+  // each: FC2's first k-block overlaps the second half of the GELU work.
+  float va[32], vb[32];
+  const uint32_t s_col = b ? kColS1 : kColS0;
+  tmem_ld32(c.lane_addr(s_col + c.hf * 32), va);
+  tmem_ld32(c.lane_addr(s_col + 64 + c.hf * 32), vb);
+  tmem_wait_ld();
+  tc_fence_before();
+  c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
+  uint8_t* h = c.sm + (b ? kSmH1 : kSmH0);
+  auto emit = [&](float (&v)[32], int col, uint8_t* atom, int ready_id) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 bb = *reinterpret_cast<const float4*>(b1c + col + i);
@@ -514,10 +509,14 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, const float* b1c
       v[i + 2] = gelu_fast(v[i + 2] + bb.z); v[i + 3] = gelu_fast(v[i + 3] + bb.w);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, ch * 4 + q, v + q * 8);
-  }
-  fence_async_smem();
-  tc_fence_before();
+    for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, c.hf * 4 + q, v + q * 8);
+    (void)ready_id;
+  };
+  emit(va, c.hf * 32, h, B_OP_READY0 + b);
+  emit(vb, 64 + c.hf * 32, h + 16384, B_OP_READY0B + b);
+  fence_async_smem();                     // one generic->async proxy fence per chunk (it costs ~400 cycles)
+  c.arrive(B_OP_READY0 + b);
+  c.arrive(B_OP_READY0B + b);
 }
 
 // ---- the single-warp roles: one out-of-line step per ring group (small I-cache footprint).  All state is
@@ -749,7 +748,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
-      const bool by_warps = (i == B_A_READY || i == B_ACC_EMPTY0 || i == B_ACC_EMPTY1 || i == B_OP_READY0 || i == B_OP_READY1);
+      const bool by_warps = (i == B_A_READY || i == B_ACC_EMPTY0 || i == B_ACC_EMPTY1 || i == B_OP_READY0 || i == B_OP_READY1 ||
+                             i == B_OP_READY0B || i == B_OP_READY1B);
       mbar_init(sbase + kSmBars + i * 8, i == B_Y_READY ? kAttnWarps * CG : (by_warps ? 8 * CG : 1));
     }
     fence_barrier_init();
@@ -919,8 +919,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             c.wait(B_ACC_FULL0);
             tc_fence_after();
             c.stamp();
-            drain_qkv(c, vecA + 3 * kD + h * 192);
-            c.arrive(B_ACC_EMPTY0);
+            drain_qkv(c, vecA + 3 * kD + h * 192);            // arrives on ACC_EMPTY0 once its TMEM reads are done
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
             c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
             c.stamp();
@@ -944,10 +943,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             c.wait2(b ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
             c.stamp();
-            drain_gelu(c, b, vecM + 3 * kD + ch * 128);
+            drain_gelu(c, b, vecM + 3 * kD + ch * 128);     // arrives on ACC_EMPTY and (twice) on OP_READY itself
             c.stamp();
-            c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
-            c.arrive(b ? B_OP_READY1 : B_OP_READY0);
           }
           compute_sync();                                   // everyone done with vecM(l)
           const int nl = (l + 1 < p.L) ? l + 1 : 0;
@@ -1228,58 +1225,6 @@ __global__ void pack_vec_kernel(const VecCopy* cp, float* vec) {
   }
 }
 
-// ---- fill program (host) ---------------------------------------------------------------------------
-uint8_t pair(uint8_t a, uint8_t b) { return (uint8_t)((a & 0xF) | ((b & 0xF) << 4)); }
-
-std::vector<Fill> build_program() {
-  std::vector<Fill> v;
-  auto add = [&](uint32_t a_off, uint32_t d_col, int n, int acc, uint8_t w0, uint8_t w1, uint8_t c0, uint8_t c1) {
-    Fill f;
-    f.a_off16 = (uint16_t)(a_off / 16); f.d_col = (uint16_t)d_col; f.n8 = (uint8_t)(n / 8); f.acc = (uint8_t)acc;
-    f.waits = pair(w0, w1); f.commits = pair(c0, c1);
-    v.push_back(f);
-  };
-  // embedding: X = A_emb (atoms 0,1) * W_emb^T
-  for (int kb = 0; kb < 2; ++kb)
-    for (int half = 0; half < 2; ++half)
-      add(kSmA + kb * 16384, kColX + half * 128, 128, (kb > 0) | (half == 0 ? 2 : 0), (kb == 0 && half == 0) ? B_A_READY : kNone, kNone,
-          (kb == 1 && half == 1) ? B_X_DONE : kNone, kNone);
-  auto qkv = [&](int h) {
-    for (int kb = 0; kb < 4; ++kb) {
-      add(kSmA + kb * 16384, kColS0, 128, (kb > 0) | 2, kb == 0 ? B_ACC_EMPTY0 : kNone, (kb == 0 && h == 0) ? B_A_READY : kNone, kNone, kNone);
-      add(kSmA + kb * 16384, kColS1, 64, kb > 0, kNone, kNone, kb == 3 ? B_ACC_FULL0 : kNone, kNone);
-    }
-  };
-  auto proj = [&](int h) {
-    add(kSmY, kColX, 128, 1 | 2, B_Y_READY, kNone, kNone, kNone);
-    add(kSmY, kColX + 128, 128, 1, kNone, kNone, B_Y_EMPTY, h == 3 ? B_X_DONE : kNone);
-  };
-  auto fc1 = [&](int c) {
-    const int b = c & 1;
-    for (int kb = 0; kb < 4; ++kb)
-      add(kSmA + kb * 16384, b ? kColS1 : kColS0, 128, kb > 0, kb == 0 ? (b ? B_ACC_EMPTY1 : B_ACC_EMPTY0) : kNone,
-          (kb == 0 && c == 0) ? B_A_READY : kNone, kb == 3 ? (b ? B_ACC_FULL1 : B_ACC_FULL0) : kNone, kNone);
-  };
-  auto fc2 = [&](int c) {
-    const int b = c & 1;
-    for (int kb = 0; kb < 2; ++kb)
-      for (int half = 0; half < 2; ++half)
-        add((b ? kSmH1 : kSmH0) + kb * 16384, kColX + half * 128, 128, 1 | (half == 0 ? 2 : 0),
-            (kb == 0 && half == 0) ? (b ? B_OP_READY1 : B_OP_READY0) : kNone, kNone,
-            (kb == 1 && half == 1) ? (b ? B_OP_EMPTY1 : B_OP_EMPTY0) : kNone, (kb == 1 && half == 1 && c == 7) ? B_X_DONE : kNone);
-  };
-  {                                 // one transformer block; every layer replays it
-    qkv(0); qkv(1); proj(0); qkv(2); proj(1); qkv(3); proj(2); proj(3);
-    fc1(0); fc1(1); fc2(0);
-    for (int c = 2; c < 8; ++c) { fc1(c); fc2(c - 1); }
-    fc2(7);
-  }
-  for (int kb = 0; kb < 4; ++kb)   // action head, N = 16
-    add(kSmA + kb * 16384, kColS0, 16, kb > 0, kb == 0 ? B_A_READY : kNone, kb == 0 ? B_ACC_EMPTY0 : kNone,
-        kb == 3 ? B_ACC_FULL0 : kNone, kNone);
-  return v;
-}
-
 }  // namespace
 
 // ================================ host API =========================================================
@@ -1308,13 +1253,10 @@ static int p_layer(int l, int k) { return 3 + l * 16 + k; }   // k: 0 ln1w 1 ln1
 
 int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm, cudaStream_t st) {
   const int L = m.n_layers, G = m.goal_conditioned ? m.goal_len : 0;
-  const std::vector<Fill> prog = build_program();
-  if ((int)prog.size() != kProgEntries) { set_error("internal: fill program size"); return BESO_E_INVALID; }
-  size_t tape_bytes = 0;
-  for (int i = 0; i < kProgEntries; ++i)
-    tape_bytes += (size_t)prog[i].n8 * 8 * 128 * ((i >= 4 && i < 108) ? L : 1);
+  // per evaluation: embedding 4 x 16 KB | per layer: QKV 16 x 24 KB, proj 4 x 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
+  const size_t tape_bytes = 4 * 16384 + (size_t)L * (16 * 24576 + 4 * 32768 + 32 * 16384 + 16 * 32768) + 4 * 2048;
   const size_t vec_floats = (size_t)L * (kVecAFloats + kVecMFloats) + kVecAFloats;
-  const size_t prog_bytes = kProgEntries * sizeof(Fill);
+  const size_t prog_bytes = 0;
   if (!w.tape) {
     // tape | program | (scratch tables for the pack kernels)
     BESO_CUDA(cudaMalloc(&w.tape, tape_bytes + prog_bytes + (1 << 20)));
@@ -1323,7 +1265,6 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   }
   uint8_t* tape = reinterpret_cast<uint8_t*>(w.tape);
   uint8_t* scratch = tape + tape_bytes + prog_bytes;
-  BESO_CUDA(cudaMemcpyAsync(tape + tape_bytes, prog.data(), prog_bytes, cudaMemcpyHostToDevice, st));
 
   // ---- tape sub-tiles, in program order ----
   std::vector<PackTile> tiles;
@@ -1417,10 +1358,6 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   const int L = m.n_layers;
   const size_t n_fills = 4 + (size_t)L * 104 + 4;
   p.tape = reinterpret_cast<const uint8_t*>(w.tape);
-  {
-    const std::vector<Fill> prog = build_program();
-    memcpy(p.prog, prog.data(), sizeof(p.prog));
-  }
   p.vec = w.vec;
   p.n_fills = (int)n_fills; p.L = L; p.G = m.goal_conditioned ? m.goal_len : 0; p.obs = m.obs_dim; p.act = m.act_dim;
   p.t = t; p.T = 1 + p.G + 2 * t;
