@@ -104,6 +104,7 @@ struct Group {
   uint32_t w0, w1, c0, c1;           // barrier ids to wait on before / commit to after (kNone = none)
   bool pair;                         // two fills (two adjacent 16 KB ring slots when CG = 1)
   bool kk2;                          // two K blocks (8 MMAs): A atoms a_off, a_off + 16 KB; also two fills
+  bool bf16;                         // operands are bf16 (embedding GEMM), else fp16
 };
 // Job types of the per-evaluation schedule, decoded arithmetically (no tables on the issue path).
 enum { J_EMB = 0, J_QKV, J_PROJ, J_FC1, J_FC2, J_HEAD };
@@ -126,7 +127,7 @@ __device__ __forceinline__ void layer_job(uint32_t lj, uint32_t& type, uint32_t&
 __device__ __forceinline__ Group make_group(uint32_t type, uint32_t idx, uint32_t kb) {
   Group q;
   q.w0 = q.w1 = q.c0 = q.c1 = kNone;
-  q.pair = true; q.kk2 = false; q.acc = kb > 0;
+  q.pair = true; q.kk2 = false; q.acc = kb > 0; q.bf16 = type == J_EMB;
   q.a_off = kSmA + kb * 16384;
   if (type == J_EMB) {                  // X = A_emb W_emb^T
     q.d_col = kColX; q.n = 256;
@@ -190,10 +191,12 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // Bounded wait: a protocol bug must not hang the GPU.  ~4 s at 2 GHz, then trap with the barrier id.
+// (try_wait itself suspends the warp for a hardware-defined interval, the clock is read every 64 polls.)
 __device__ __noinline__ void wait_timeout(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) {
+    if ((++polls & 63u) == 0 && clock64() - t0 > 8000000000ll) {
       printf("beso fast kernel: mbarrier id %u parity %u timed out (block %d thread %d)\n",
              (bar & 0x3FF) / 8, parity, blockIdx.x, threadIdx.x);
       __trap();
@@ -225,22 +228,27 @@ __device__ __forceinline__ void warp_wait(int lane, uint32_t bar, uint32_t parit
   __syncwarp();
 }
 
-// erf-GELU without erff(): with z = |x| / sqrt(2), 0.5 * erfc(z) = 2^q(z) to 2.1e-6 absolute for a
-// degree-5 q fitted on [0, 6] (q -> -inf beyond), so
-//   gelu(x) = x * Phi(x) = max(x, 0) - |x| * 2^q(z)          |error| <= 5.9e-7 absolute
-// 9 instructions (5 FFMA Horner, 1 MUFU.EX2) instead of ~46 for erff().
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float ax = fabsf(x);
-  const float z = ax * 0.70710678118654752440f;
-  float q = fmaf(-2.784754615e-03f, z, 2.889863029e-02f);
-  q = fmaf(q, z, -1.476386487e-01f);
-  q = fmaf(q, z, -9.191277623e-01f);
-  q = fmaf(q, z, -1.627753854e+00f);
-  q = fmaf(q, z, -1.000006080e+00f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
-  return fmaf(-ax, e, fmaxf(x, 0.f));
+// erf-GELU without erff(), two elements per instruction in packed fp16: with a = |x|,
+//   0.5 * erfc(a / sqrt(2)) = 2^q(a)   (degree-5 q fitted on [0, 7], leading coefficient < 0 so q -> -inf beyond)
+//   gelu(x) = x * Phi(x) = max(x, 0) - a * 2^q(a)
+// The fit is exact to 3.8e-6 absolute; evaluated in fp16 the result is as good as the exactly computed GELU
+// rounded to fp16 (mean |error| 7.8e-5 vs 7.2e-5 over [-9, 9]; the fp16 operand rounding dominates).
+// 9 packed instructions per PAIR (abs, 5 HFMA2, MUFU.EX2, max, HFMA2) instead of 11 fp32 instructions per element.
+__device__ __forceinline__ __half2 h2const(float v) { return __float2half2_rn(v); }
+__device__ __forceinline__ __half2 gelu2(__half2 x) {
+  const __half2 ax = __habs2(x);
+  __half2 q = __hfma2(h2const(-3.21299708e-04f), ax, h2const(5.98860442e-03f));
+  q = __hfma2(q, ax, h2const(-4.90046024e-02f));
+  q = __hfma2(q, ax, h2const(-4.63166370e-01f));
+  q = __hfma2(q, ax, h2const(-1.14928188e+00f));
+  q = __hfma2(q, ax, h2const(-1.00026587e+00f));
+  uint32_t e;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(*reinterpret_cast<const uint32_t*>(&q)));
+  const __half2 m = __hmax2(x, h2const(0.f));
+  return __hfma2(__hneg2(ax), *reinterpret_cast<const __half2*>(&e), m);
 }
+__device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -251,7 +259,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -260,9 +268,8 @@ struct Compute {
   uint8_t* sm;
   uint32_t sbase, tmem;
   int wq, lane, hf, row, ctid;       // TMEM lane quadrant, lane, column half, tile row, compute thread id
+  uint32_t row_off, rx4;             // row * 128 and (row & 7) << 4: SW128 address of chunk k = row_off + ((k << 4) ^ rx4)
   uint32_t phases;                   // parity bit per barrier id this role waits on
-  long long* tl;                     // timeline cursor (nullptr = off)
-  __device__ void stamp() { if (tl != nullptr) *tl++ = clock64(); }
   __device__ uint32_t bar(int id) const { return sbase + kSmBars + id * 8; }
   __device__ void wait(int id) { spin_wait(bar(id), (phases >> id) & 1u); phases ^= 1u << id; }
   __device__ void wait2(int a, int b) {          // two barriers, tests issued back to back
@@ -279,48 +286,51 @@ struct Compute {
     if (lane == 0) { if (cg == 2) mbar_arrive_cluster(bar(id), 0); else mbar_arrive(bar(id)); }
   }
   __device__ uint32_t lane_addr(uint32_t col) const { return tmem + ((uint32_t)(wq * 32) << 16) + col; }
+  // shared address of 16-byte chunk k of this thread's row in the SW128 atom at shared address `atom`
+  __device__ uint32_t chunk_addr(uint32_t atom, uint32_t k) const { return atom + row_off + ((k << 4) ^ rx4); }
 };
 
-// A <- bf16(LayerNorm(X + pend) * w + b).   vec = [pend | w | b] in shared memory.
+// A <- fp16(LayerNorm0(X + pend)), LayerNorm0 = (x - mean) * rstd.   vec_s = shared address of pend (fp32).
+// The LayerNorm weight / bias are folded into the Linear that consumes A (see fast_pack).
 // X (TMEM) is only read: every projection / MLP bias is added to X up front by the embedding GEMM and
-// `pend` holds minus the biases that are not due yet at this point of the network (see fast_pack).
-__device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* trace_row) {
-  // X is read from TMEM ONCE (TMEM reads are the scarce resource of this phase, ~64 B/clk per SM): the
-  // 128 values of this thread, with the pending biases already added, wait for the row statistics as
-  // 64 packed fp16 pairs in registers (2^-11 relative, well below the bf16 rounding of the result).
+// `pend` holds minus the biases that are not due yet at this point of the network.
+template <bool DBG>
+__device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float* trace_row) {
+  // X is read from TMEM once: the 128 values of this thread (pending biases added) wait for the row
+  // statistics as 64 packed fp16 pairs in registers; the statistics themselves are fp32 of the unrounded
+  // values.  The normalisation is one packed HFMA2 per pair, straight into the fp16 A operand.
   float va[32], vb[32];
   __half2 keep[64];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   const int col0 = c.hf * 128;
-  const bool tracing = trace_row != nullptr;
   auto pass1 = [&](float (&v)[32], int ch) {
     const int col = col0 + ch * 32;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 pd = *reinterpret_cast<const float4*>(vec + col + i);
+      const float4 pd = lds128f(vec_s + (uint32_t)(col + i) * 4u);
       const float a0 = v[i] + pd.x, a1 = v[i + 1] + pd.y, a2 = v[i + 2] + pd.z, a3 = v[i + 3] + pd.w;
       s0 += a0; s1 += a1; s2 += a2; s3 += a3;
       q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
       keep[ch * 16 + (i >> 1)] = __floats2half2_rn(a0, a1);
       keep[ch * 16 + (i >> 1) + 1] = __floats2half2_rn(a2, a3);
-      if (tracing) {
-        float* tr = trace_row + col + i;
-        tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3;
+      if (DBG) {
+        if (trace_row != nullptr) {
+          float* tr = trace_row + col + i;
+          tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3;
+        }
       }
     }
   };
   // the next chunk's TMEM load is in flight while the current one is reduced
   tmem_ld32(c.lane_addr(kColX + col0), va);
-  tmem_wait_ld();
   tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
-  pass1(va, 0);
   tmem_wait_ld();
+  pass1(va, 0);
   tmem_ld32(c.lane_addr(kColX + col0 + 64), va);
   pass1(vb, 1);
-  tmem_wait_ld();
   tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
-  pass1(va, 2);
   tmem_wait_ld();
+  pass1(va, 2);
   pass1(vb, 3);
   const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
   float2* stats = reinterpret_cast<float2*>(c.sm + kSmStats);
@@ -330,19 +340,14 @@ __device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* t
   const float mean = (sum + o.x) * (1.0f / kD);
   const float var = fmaxf((sq + o.y) * (1.0f / kD) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
-  const float nmr = -mean * rstd;
-  // the LayerNorm weight / bias are folded into the Linear that consumes A (see fast_pack)
+  const __half2 r2 = __float2half2_rn(rstd), n2 = __float2half2_rn(-mean * rstd);
+  const uint32_t a_s = c.sbase + kSmA + (uint32_t)c.hf * 32768u;       // this thread's two K atoms
 #pragma unroll
-  for (int ch8 = 0; ch8 < 16; ++ch8) {             // 16 chunks of 8 columns = 16 bytes of bf16 each
-    uint4 u;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+  for (int ch8 = 0; ch8 < 16; ++ch8) {             // 16 chunks of 8 columns = 16 bytes of fp16 each
+    uint32_t w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = __half22float2(keep[ch8 * 4 + k]);
-      w[k] = pack_bf16x2(fmaf(f.x, rstd, nmr), fmaf(f.y, rstd, nmr));
-    }
-    const int col = col0 + ch8 * 8;
-    *reinterpret_cast<uint4*>(c.sm + kSmA + (col >> 6) * 16384 + sw128_offset(c.row, (col & 63) >> 3)) = u;
+    for (int k = 0; k < 4; ++k) w[k] = h2bits(__hfma2(keep[ch8 * 4 + k], r2, n2));
+    sts128(c.chunk_addr(a_s + (uint32_t)(ch8 >> 3) * 16384u, ch8 & 7), w[0], w[1], w[2], w[3]);
   }
   fence_async_smem();
   tc_fence_before();
@@ -350,8 +355,10 @@ __device__ __noinline__ void ln_pass(const Compute c, const float* vec, float* t
   compute_sync();          // stats buffer may be rewritten by the next pass only after everyone read it
 }
 
-// Accumulator of head h (Q|K at S0, V at S1[0:64)) -> + bias -> bf16 Q|K|V staging rows.
-__device__ __noinline__ void drain_qkv(const Compute c, const float* bqkv_h) {
+// Accumulator of head h (Q|K at S0, V at S1[0:64)) -> fp16 Q|K|V staging rows.  Only Q gets its bias here: the
+// K bias shifts every score of a query row by the same amount (softmax-invariant) and the V bias passes
+// through the softmax average unchanged, so it is folded into the projection bias at pack time.
+__device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
   // all TMEM reads first, then the accumulator is handed back to the MMA warp (QKV of the next head can
   // start) while this thread still converts and stores
   float v0[32], v1[32], v2[32];
@@ -362,24 +369,25 @@ __device__ __noinline__ void drain_qkv(const Compute c, const float* bqkv_h) {
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
-  auto emit = [&](const float (&v)[32], int col) {
-    uint8_t* dst = c.sm + kSmQkv + (uint32_t)c.row * kQkvStride + col * 2;
+  const uint32_t dst0 = c.sbase + kSmQkv + (uint32_t)c.row * kQkvStride + (uint32_t)colb * 2u;
+  if (c.hf == 0) {                                       // v0, v1 = Q (+ bias)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 u;
-      const float4 b0 = *reinterpret_cast<const float4*>(bqkv_h + col + q * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(bqkv_h + col + q * 8 + 4);
-      u.x = pack_bf16x2(v[q * 8 + 0] + b0.x, v[q * 8 + 1] + b0.y);
-      u.y = pack_bf16x2(v[q * 8 + 2] + b0.z, v[q * 8 + 3] + b0.w);
-      u.z = pack_bf16x2(v[q * 8 + 4] + b1.x, v[q * 8 + 5] + b1.y);
-      u.w = pack_bf16x2(v[q * 8 + 6] + b1.z, v[q * 8 + 7] + b1.w);
-      *reinterpret_cast<uint4*>(dst + q * 16) = u;
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b0 = lds128f(bq_s + (uint32_t)i * 4u), b1 = lds128f(bq_s + (uint32_t)(32 + i) * 4u);
+      v0[i] += b0.x; v0[i + 1] += b0.y; v0[i + 2] += b0.z; v0[i + 3] += b0.w;
+      v1[i] += b1.x; v1[i + 1] += b1.y; v1[i + 2] += b1.z; v1[i + 3] += b1.w;
     }
+  }
+  auto emit = [&](const float (&v)[32], uint32_t dst) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      sts128(dst + q * 16, pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]),
+             pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]));
   };
-  emit(v0, colb); emit(v1, colb + 32); emit(v2, colb + 64);
+  emit(v0, dst0); emit(v1, dst0 + 64); emit(v2, dst0 + 128);
 }
 
-// Causal softmax(Q K^T) V for every sequence of the tile, one warp per sequence, mma.sync bf16.
+// Causal softmax(Q K^T) V for every sequence of the tile, one warp per sequence, mma.sync fp16.
 // Q is pre-scaled by 1/sqrt(hs) (folded into the packed weights).  Output -> Y atom (SW128 A layout).
 __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
   const uint32_t qkv = sbase + kSmQkv;
@@ -446,10 +454,10 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
             sum_lo += pv[nb][e]; sum_hi += pv[nb][2 + e];
           }
         }
-        pa[kt][0] = pack_bf16x2(pv[0][0], pv[0][1]);   // (row lo, keys 0-7)
-        pa[kt][1] = pack_bf16x2(pv[0][2], pv[0][3]);   // (row hi, keys 0-7)
-        pa[kt][2] = pack_bf16x2(pv[1][0], pv[1][1]);   // (row lo, keys 8-15)
-        pa[kt][3] = pack_bf16x2(pv[1][2], pv[1][3]);   // (row hi, keys 8-15)
+        pa[kt][0] = pack_f16x2(pv[0][0], pv[0][1]);   // (row lo, keys 0-7)
+        pa[kt][1] = pack_f16x2(pv[0][2], pv[0][3]);   // (row hi, keys 0-7)
+        pa[kt][2] = pack_f16x2(pv[1][0], pv[1][1]);   // (row lo, keys 8-15)
+        pa[kt][3] = pack_f16x2(pv[1][2], pv[1][3]);   // (row hi, keys 8-15)
       }
       sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
       sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
@@ -477,22 +485,22 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
         const int e = n * 8 + (lane & 3) * 2;    // column within the head
         if (i_lo < T) {
           const uint32_t r = row0 + i_lo;
-          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_bf16x2(o[n][0] * inv_lo, o[n][1] * inv_lo);
+          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][0] * inv_lo, o[n][1] * inv_lo);
         }
         if (i_hi < T) {
           const uint32_t r = row0 + i_hi;
-          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_bf16x2(o[n][2] * inv_hi, o[n][3] * inv_hi);
+          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][2] * inv_hi, o[n][3] * inv_hi);
         }
       }
     }
   }
 }
 
-// FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU -> bf16 -> H[b] (two K atoms).
-__device__ __noinline__ void drain_gelu(const Compute c, int b, const float* b1c) {
+// FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
+// b1h_s = shared address of this chunk's 128 biases as fp16.
+__device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) {
   // Both 32-column pieces of this thread are read first and the accumulator is released at once (FC1 of
-  // chunk c+2 can start).  All 8 warps then finish K atom 0 of H before atom 1, and signal OP_READY after
-  // each: FC2's first k-block overlaps the second half of the GELU work.
+  // chunk c+2 can start).
   float va[32], vb[32];
   const uint32_t s_col = b ? kColS1 : kColS0;
   tmem_ld32(c.lane_addr(s_col + c.hf * 32), va);
@@ -500,21 +508,21 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, const float* b1c
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
-  uint8_t* h = c.sm + (b ? kSmH1 : kSmH0);
-  auto emit = [&](float (&v)[32], int col, uint8_t* atom, int ready_id) {
+  const uint32_t h_s = c.sbase + (b ? kSmH1 : kSmH0);
+  auto emit = [&](const float (&v)[32], uint32_t col, uint32_t atom) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(b1c + col + i);
-      v[i] = gelu_fast(v[i] + bb.x); v[i + 1] = gelu_fast(v[i + 1] + bb.y);
-      v[i + 2] = gelu_fast(v[i + 2] + bb.z); v[i + 3] = gelu_fast(v[i + 3] + bb.w);
+    for (int q = 0; q < 4; ++q) {
+      const uint4 bb = lds128(b1h_s + (col + q * 8) * 2u);
+      const __half2 g0 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]), bits2h(bb.x)));
+      const __half2 g1 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]), bits2h(bb.y)));
+      const __half2 g2 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]), bits2h(bb.z)));
+      const __half2 g3 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]), bits2h(bb.w)));
+      sts128(c.chunk_addr(atom, c.hf * 4 + q), h2bits(g0), h2bits(g1), h2bits(g2), h2bits(g3));
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) st_chunk(atom, c.row, c.hf * 4 + q, v + q * 8);
-    (void)ready_id;
   };
-  emit(va, c.hf * 32, h, B_OP_READY0 + b);
-  emit(vb, 64 + c.hf * 32, h + 16384, B_OP_READY0B + b);
-  fence_async_smem();                     // one generic->async proxy fence per chunk (it costs ~400 cycles)
+  emit(va, c.hf * 32, h_s);
+  emit(vb, 64 + c.hf * 32, h_s + 16384);
+  fence_async_smem();                     // one generic->async proxy fence per chunk
   c.arrive(B_OP_READY0 + b);
   c.arrive(B_OP_READY0B + b);
 }
@@ -603,7 +611,10 @@ __device__ __forceinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uin
   tc_fence_after();
   const uint64_t a_desc = smem_desc_sw128(sbase + a_off);
   const uint64_t b_desc = smem_desc_sw128(sbase + kSmRing + slot * kSlotBytes);
-  const uint32_t idesc = CG == 2 ? idesc_bf16_m256(n) : idesc_bf16_m128(n);
+  // fp16 operands everywhere except the embedding GEMM (flag 8): its A operand carries raw, unscaled inputs
+  // and bf16 hi + lo splits of the bias / position tables
+  const uint32_t idesc = (flags & 8u) ? (CG == 2 ? idesc_bf16_m256(n) : idesc_bf16_m128(n))
+                                      : (CG == 2 ? idesc_f16_m256(n) : idesc_f16_m128(n));
   const uint32_t d_addr = tm + d_col;
   if (elect_one()) {
     long long t3 = 0;
@@ -735,7 +746,8 @@ __device__ void load_vec_async(const Compute& c, uint32_t dst_off, const float* 
 // CG = 1: every CTA issues its own M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2) run cta_group::2
 // M = 256 MMAs issued by the leader CTA; each CTA streams and holds only HALF of every B operand, which
 // halves the L2 -> SMEM weight traffic and the shared-memory bandwidth the tensor core needs for B.
-template <int CG>
+// DBG = true compiles in the diagnostics (per-phase clock stamps, LayerNorm trace dump); production is DBG = false.
+template <int CG, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
   extern __shared__ uint8_t smem_raw[];
@@ -759,7 +771,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     uint4* tab = reinterpret_cast<uint4*>(sm + kSmProg);
     int i = 0;
     walk_eval(1, [&](const Group& q) {
-      tab[i++] = make_uint4(q.a_off, q.d_col | (q.n << 16), q.acc | (q.pair ? 2u : 0u) | (q.kk2 ? 4u : 0u),
+      tab[i++] = make_uint4(q.a_off, q.d_col | (q.n << 16), q.acc | (q.pair ? 2u : 0u) | (q.kk2 ? 4u : 0u) | (q.bf16 ? 8u : 0u),
                             q.w0 | (q.w1 << 4) | (q.c0 << 8) | (q.c1 << 12));
     });
   }
@@ -816,7 +828,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           g += 1;
         }
       } else {
-        long long* tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
+        long long* tl = (DBG && p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
         int li = 0;
         // four groups per iteration, as straight-line code: consecutive groups then use different uniform
         // registers for their descriptors, so setting up group i+1 does not wait for group i's MMAs to issue
@@ -838,7 +850,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
 #pragma unroll 1
           for (; i < n_groups_eval; ++i) run(gtab[table_index(i, li)], tl_tag);
         };
-        if (tl != nullptr) loop(std::true_type{}); else loop(std::false_type{});
+        if constexpr (DBG) { if (tl != nullptr) loop(std::true_type{}); else loop(std::false_type{}); }
+        else loop(std::false_type{});
       }
     }
   } else if (warp >= kHelperWarp0) {
@@ -863,9 +876,12 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     c.ctid = threadIdx.x - kComputeWarp0 * 32;
     c.lane = lane; c.wq = warp & 3; c.hf = (warp - kComputeWarp0) >> 2;
     c.row = c.wq * 32 + lane;
+    c.row_off = (uint32_t)c.row * 128u; c.rx4 = ((uint32_t)c.row & 7u) << 4;
+    long long* tlc = nullptr;                                // timeline cursor of compute thread 0
+    auto stamp = [&]() { if constexpr (DBG) { if (tlc != nullptr) *tlc++ = clock64(); } };
+    const uint32_t vecA_s = sbase + kSmVecA, vecM_s = sbase + kSmVecM;
     c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
     float* vecA = reinterpret_cast<float*>(sm + kSmVecA);
-    float* vecM = reinterpret_cast<float*>(sm + kSmVecM);
     float* xbuf = reinterpret_cast<float*>(sm + kSmProg + 1024);
     float* xcur = xbuf, *d1 = xbuf + kXFloats, *x2 = xbuf + 2 * kXFloats, *dU = xbuf + 3 * kXFloats;
     float* sigv = xbuf + 4 * kXFloats;                       // per virtual sequence noise level
@@ -899,12 +915,13 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         compute_sync();
         const float* xsrc = second ? x2 : xcur;
         auto trace_row = [&](int slot) -> float* {
-          return (p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.row) * kD : nullptr;
+          return (DBG && p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.row) * kD : nullptr;
         };
-        c.tl = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
-        c.stamp();
+        if constexpr (DBG)
+          tlc = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
+        stamp();
         build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, xsrc, sigv);
-        c.stamp();
+        stamp();
 
         for (int l = 0; l < p.L; ++l) {
           // ---------------- attention half ----------------
@@ -912,39 +929,39 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           compute_sync();                                   // vecA(l) (and vecM(l)) landed for everyone
           c.wait(B_X_DONE);
           tc_fence_after();
-          c.stamp();
-          ln_pass(c, vecA, trace_row(2 * l));
-          c.stamp();
+          stamp();
+          ln_pass<DBG>(c, vecA_s, trace_row(2 * l));
+          stamp();
           for (int h = 0; h < kH; ++h) {
             c.wait(B_ACC_FULL0);
             tc_fence_after();
-            c.stamp();
-            drain_qkv(c, vecA + 3 * kD + h * 192);            // arrives on ACC_EMPTY0 once its TMEM reads are done
+            stamp();
+            drain_qkv(c, vecA_s + (uint32_t)(3 * kD + h * 192) * 4u);            // arrives on ACC_EMPTY0 once its TMEM reads are done
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
             c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
-            c.stamp();
+            stamp();
             attention_head(sm, sbase, c.ctid >> 5, lane, p.S, p.T);
             fence_async_smem();
             c.arrive(B_Y_READY);
-            c.stamp();
+            stamp();
             attn_sync();                                    // staging may be overwritten by the next drain
-            c.stamp();
+            stamp();
           }
           // vecA is free: prefetch the next layer's (or the final block)
           load_vec_async(c, kSmVecA, p.vec + (size_t)(l + 1) * layer_stride, kVecAFloats);
           // ---------------- MLP half ----------------
           c.wait(B_X_DONE);
           tc_fence_after();
-          c.stamp();
-          ln_pass(c, vecM, trace_row(2 * l + 1));
-          c.stamp();
+          stamp();
+          ln_pass<DBG>(c, vecM_s, trace_row(2 * l + 1));
+          stamp();
           for (int ch = 0; ch < 8; ++ch) {
             const int b = ch & 1;
             c.wait2(b ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
-            c.stamp();
-            drain_gelu(c, b, vecM + 3 * kD + ch * 128);     // arrives on ACC_EMPTY and (twice) on OP_READY itself
-            c.stamp();
+            stamp();
+            drain_gelu(c, b, vecM_s + (uint32_t)kD * 4u + (uint32_t)ch * 256u);     // arrives on ACC_EMPTY and (twice) on OP_READY itself
+            stamp();
           }
           compute_sync();                                   // everyone done with vecM(l)
           const int nl = (l + 1 < p.L) ? l + 1 : 0;
@@ -955,12 +972,12 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         compute_sync();
         c.wait(B_X_DONE);
         tc_fence_after();
-        c.stamp();
-        ln_pass(c, vecA, trace_row(2 * p.L));
-        c.stamp();
+        stamp();
+        ln_pass<DBG>(c, vecA_s, trace_row(2 * p.L));
+        stamp();
         c.wait(B_ACC_FULL0);
         tc_fence_after();
-        c.stamp();
+        stamp();
         float pr[16];
         tmem_ld16(c.lane_addr(kColS0), pr);
         tmem_wait_ld();
@@ -1146,7 +1163,7 @@ __global__ void pack_tiles_kernel(const PackTile* tiles, uint8_t* tape) {
       }
       v[i] = x;
     }
-    st_chunk(tape + t.dst, r, chunk, v);
+    st_chunk_h(tape + t.dst, r, chunk, v);
   }
 }
 
@@ -1211,7 +1228,8 @@ __global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, ui
 
 // Bias of a Linear that follows a LayerNorm whose affine part is folded into it:
 //   W (LN0(x) * g + beta) + b = (W diag(g)) LN0(x) + (b + W beta)        dst[i] = scale * (b[i] + W[i,:] . beta)
-struct VecCopy { const float* src; uint32_t dst; int n; float scale; const float* W; const float* beta; int ld; };
+// half_out: the n results are stored as packed fp16 starting at float index dst.
+struct VecCopy { const float* src; uint32_t dst; int n; float scale; const float* W; const float* beta; int ld; int half_out; };
 __global__ void pack_vec_kernel(const VecCopy* cp, float* vec) {
   const VecCopy c = cp[blockIdx.x];
   for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
@@ -1221,7 +1239,8 @@ __global__ void pack_vec_kernel(const VecCopy* cp, float* vec) {
       for (int k = 0; k < c.ld; ++k) acc = fmaf(c.W[(size_t)i * c.ld + k], c.beta[k], acc);
       b += acc;
     }
-    vec[c.dst + i] = b * c.scale;
+    if (c.half_out) reinterpret_cast<__half*>(vec + c.dst)[i] = __float2half_rn(b * c.scale);
+    else vec[c.dst + i] = b * c.scale;
   }
 }
 
@@ -1256,11 +1275,12 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   // per evaluation: embedding 4 x 16 KB | per layer: QKV 16 x 24 KB, proj 4 x 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
   const size_t tape_bytes = 4 * 16384 + (size_t)L * (16 * 24576 + 4 * 32768 + 32 * 16384 + 16 * 32768) + 4 * 2048;
   const size_t vec_floats = (size_t)L * (kVecAFloats + kVecMFloats) + kVecAFloats;
+  const size_t fold_floats = (size_t)L * 2 * kD;             // per layer: effective V bias | effective proj bias
   const size_t prog_bytes = 0;
   if (!w.tape) {
     // tape | program | (scratch tables for the pack kernels)
     BESO_CUDA(cudaMalloc(&w.tape, tape_bytes + prog_bytes + (1 << 20)));
-    BESO_CUDA(cudaMalloc(&w.vec, vec_floats * sizeof(float)));
+    BESO_CUDA(cudaMalloc(&w.vec, (vec_floats + fold_floats) * sizeof(float)));
     w.tape_bytes = tape_bytes; w.vec_floats = vec_floats;
   }
   uint8_t* tape = reinterpret_cast<uint8_t*>(w.tape);
@@ -1304,34 +1324,43 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   pack_tiles_kernel<<<(unsigned)tiles.size(), 128, 0, st>>>(reinterpret_cast<const PackTile*>(scratch), tape);
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());
+  // ---- fp32 / fp16 vectors ----
+  // Linear biases with the preceding LayerNorm's beta folded in (pack_vec_kernel).  K needs no bias (softmax is
+  // invariant to a per-query shift of the scores); the V bias goes through the softmax average unchanged and is
+  // folded into the projection bias:  bproj_eff = bproj + Wproj (bv + Wv beta1).
+  std::vector<VecCopy> vc, vc2;
+  for (int l = 0; l < L; ++l) {
+    const uint32_t a = (uint32_t)(l * (kVecAFloats + kVecMFloats)), mo = a + kVecAFloats;
+    const uint32_t fo = (uint32_t)(vec_floats + (size_t)l * 2 * kD);
+    const float* ln1b = prm[p_layer(l, 1)];
+    const float* ln2b = prm[p_layer(l, 3)];
+    for (int h = 0; h < kH; ++h)
+      vc.push_back({prm[p_layer(l, 7)] + h * 64, a + 3 * kD + h * 192, 64, qscale, prm[p_layer(l, 6)] + (size_t)h * 64 * kD, ln1b, kD, 0});
+    vc.push_back({prm[p_layer(l, 9)], fo, kD, 1.f, prm[p_layer(l, 8)], ln1b, kD, 0});
+    vc2.push_back({prm[p_layer(l, 11)], fo + kD, kD, 1.f, prm[p_layer(l, 10)], w.vec + fo, kD, 0});
+    vc.push_back({prm[p_layer(l, 13)], mo + kD, kFF, 1.f, prm[p_layer(l, 12)], ln2b, kD, 1});   // b1 as fp16 after pend
+  }
+  const uint32_t fa = (uint32_t)(L * (kVecAFloats + kVecMFloats));
+  vc.push_back({prm[p_tail + 7], fa + 3 * kD, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], kD, 0});
+  vc.push_back({nullptr, fa + 3 * kD + (uint32_t)m.act_dim, 768 - m.act_dim, 1.f, nullptr, nullptr, 0, 0});
+  uint8_t* scratch2 = scratch + (1 << 19);
+  const size_t n1 = vc.size();
+  vc.insert(vc.end(), vc2.begin(), vc2.end());
+  BESO_CUDA(cudaMemcpyAsync(scratch2, vc.data(), vc.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, st));
+  pack_vec_kernel<<<(unsigned)n1, 128, 0, st>>>(reinterpret_cast<const VecCopy*>(scratch2), w.vec);
+  pack_vec_kernel<<<(unsigned)vc2.size(), 128, 0, st>>>(reinterpret_cast<const VecCopy*>(scratch2) + n1, w.vec);
+  g_kernel_launches += 2;
+  BESO_CUDA(cudaGetLastError());
+
   EmbSrc es{};
   es.pos = prm[0]; es.tokw = prm[1]; es.tokb = prm[2]; es.sigw = prm[p_tail + 2]; es.sigb = prm[p_tail + 3];
   es.actw = prm[p_tail + 4]; es.actb = prm[p_tail + 5];
   es.obs = m.obs_dim; es.act = m.act_dim; es.G = G; es.W = m.window; es.L = L;
-  for (int l = 0; l < L; ++l) { es.resid_bias[2 * l] = prm[p_layer(l, 11)]; es.resid_bias[2 * l + 1] = prm[p_layer(l, 15)]; }
-  pack_emb_kernel<<<4, 256, 0, st>>>(es, tape);
-  ++g_kernel_launches;
-  BESO_CUDA(cudaGetLastError());
-
-  // ---- fp32 vectors ----
-  std::vector<VecCopy> vc;
   for (int l = 0; l < L; ++l) {
-    const uint32_t a = (uint32_t)(l * (kVecAFloats + kVecMFloats)), mo = a + kVecAFloats;
-    const float* ln1b = prm[p_layer(l, 1)];
-    const float* ln2b = prm[p_layer(l, 3)];
-    for (int h = 0; h < kH; ++h) {
-      vc.push_back({prm[p_layer(l, 7)] + h * 64, a + 3 * kD + h * 192, 64, qscale, prm[p_layer(l, 6)] + (size_t)h * 64 * kD, ln1b, kD});
-      vc.push_back({prm[p_layer(l, 5)] + h * 64, a + 3 * kD + h * 192 + 64, 64, 1.f, prm[p_layer(l, 4)] + (size_t)h * 64 * kD, ln1b, kD});
-      vc.push_back({prm[p_layer(l, 9)] + h * 64, a + 3 * kD + h * 192 + 128, 64, 1.f, prm[p_layer(l, 8)] + (size_t)h * 64 * kD, ln1b, kD});
-    }
-    vc.push_back({prm[p_layer(l, 13)], mo + 3 * kD, kFF, 1.f, prm[p_layer(l, 12)], ln2b, kD});
+    es.resid_bias[2 * l] = w.vec + vec_floats + (size_t)l * 2 * kD + kD;      // effective projection bias
+    es.resid_bias[2 * l + 1] = prm[p_layer(l, 15)];
   }
-  const uint32_t fa = (uint32_t)(L * (kVecAFloats + kVecMFloats));
-  vc.push_back({prm[p_tail + 7], fa + 3 * kD, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], kD});
-  vc.push_back({nullptr, fa + 3 * kD + (uint32_t)m.act_dim, 768 - m.act_dim, 1.f, nullptr, nullptr, 0});
-  uint8_t* scratch2 = scratch + (1 << 19);
-  BESO_CUDA(cudaMemcpyAsync(scratch2, vc.data(), vc.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, st));
-  pack_vec_kernel<<<(unsigned)vc.size(), 128, 0, st>>>(reinterpret_cast<const VecCopy*>(scratch2), w.vec);
+  pack_emb_kernel<<<4, 256, 0, st>>>(es, tape);
   pack_pend_kernel<<<1, kD, 0, st>>>(es, w.vec, kVecAFloats + kVecMFloats, kVecAFloats);
   g_kernel_launches += 2;
   BESO_CUDA(cudaGetLastError());
@@ -1380,8 +1409,9 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.timeline = g_timeline;
   static bool configured = false;
   if (!configured) {
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
     configured = true;
   }
   // Single-CTA MMAs (CG = 1) are the default: measured faster than CTA pairs on this workload (the pair mode
@@ -1400,10 +1430,11 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfgl.attrs = attr; cfgl.numAttrs = 1;
-    BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2>, p, sa));
+    BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2, false>, p, sa));
   } else {
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    fast_sample_kernel<1><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    if (p.trace != nullptr || p.timeline != nullptr) fast_sample_kernel<1, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    else fast_sample_kernel<1, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
   }
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());

@@ -7,6 +7,7 @@
 // 1024-byte aligned in shared memory.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace beso {
@@ -125,6 +126,14 @@ __host__ __device__ constexpr uint32_t idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// Same, fp16 x fp16 -> fp32 (a/b_format F16 = 0): same tensor-pipe rate as bf16, 11-bit mantissa.
+__host__ __device__ constexpr uint32_t idesc_f16_m128(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_f16_m256(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the whole CTA.
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -204,6 +213,31 @@ __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 16-byte shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic on the hot paths)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// store 8 consecutive K elements (one 16-byte chunk) of one row as fp16
+__device__ __forceinline__ void st_chunk_h(uint8_t* atom, uint32_t row, uint32_t chunk, const float* v) {
+  uint4 u;
+  u.x = pack_f16x2(v[0], v[1]); u.y = pack_f16x2(v[2], v[3]);
+  u.z = pack_f16x2(v[4], v[5]); u.w = pack_f16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(atom + sw128_offset(row, chunk)) = u;
 }
 // store 8 consecutive K elements (one 16-byte chunk) of one row
 __device__ __forceinline__ void st_chunk(uint8_t* atom, uint32_t row, uint32_t chunk, const float* v) {

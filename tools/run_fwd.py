@@ -1,0 +1,39 @@
+"""Runs a few FAST-mode forwards (for ncu captures / quick timing).
+
+    python tools/run_fwd.py [T16|K256] [B] [reps]
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from beso_b200 import K256, T16                                 # noqa: E402
+from beso_b200.denoiser import build_denoiser                 # noqa: E402
+from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "T16"
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    cfg = {"K256": K256, "T16": T16}[name]
+    dev = torch.device("cuda:0")
+    m = build_denoiser(cfg, dev, mode="fast", state_dict=synthetic_state_dict(cfg, 1))
+    x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=2).items()}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    with torch.no_grad():
+        m(x["state"], x["action"], x["goal"], x["sigma"])
+        ev[0].record()
+        for i in range(reps):
+            m(x["state"], x["action"], x["goal"], x["sigma"])
+            ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+    fl = cfg.fwd_flops_per_seq() * B
+    print(f"{name} B={B}: ms per forward {['%.4f' % t for t in ms]}  best {min(ms):.4f} ms = {fl / min(ms) / 1e9:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
