@@ -247,6 +247,31 @@ __device__ __forceinline__ __half2 gelu2(__half2 x) {
   const __half2 m = __hmax2(x, h2const(0.f));
   return __hfma2(__hneg2(ax), *reinterpret_cast<const __half2*>(&e), m);
 }
+// The same over NP independent pairs, written breadth-first (every Horner step across all pairs before the
+// next one): the dependent chain of one pair is ~12 instructions long, so the schedule needs >= 8 chains in
+// flight to keep the issue slot busy with two warps per scheduler.
+template <int NP>
+__device__ __forceinline__ void gelu2_vec(__half2 (&x)[NP]) {
+  __half2 q[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) q[i] = __hfma2(h2const(-3.21299708e-04f), __habs2(x[i]), h2const(5.98860442e-03f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) q[i] = __hfma2(q[i], __habs2(x[i]), h2const(-4.90046024e-02f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) q[i] = __hfma2(q[i], __habs2(x[i]), h2const(-4.63166370e-01f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) q[i] = __hfma2(q[i], __habs2(x[i]), h2const(-1.14928188e+00f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) q[i] = __hfma2(q[i], __habs2(x[i]), h2const(-1.00026587e+00f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    uint32_t e;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(*reinterpret_cast<const uint32_t*>(&q[i])));
+    q[i] = *reinterpret_cast<const __half2*>(&e);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) x[i] = __hfma2(__hneg2(__habs2(x[i])), q[i], __hmax2(x[i], h2const(0.f)));
+}
 __device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
@@ -307,7 +332,7 @@ __device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float* tra
     const int col = col0 + ch * 32;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 pd = lds128f(vec_s + (uint32_t)(col + i) * 4u);
+      const float4 pd = lds128f_ro(vec_s + (uint32_t)(col + i) * 4u);
       const float a0 = v[i] + pd.x, a1 = v[i + 1] + pd.y, a2 = v[i + 2] + pd.z, a3 = v[i + 3] + pd.w;
       s0 += a0; s1 += a1; s2 += a2; s3 += a3;
       q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
@@ -373,7 +398,7 @@ __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
   if (c.hf == 0) {                                       // v0, v1 = Q (+ bias)
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b0 = lds128f(bq_s + (uint32_t)i * 4u), b1 = lds128f(bq_s + (uint32_t)(32 + i) * 4u);
+      const float4 b0 = lds128f_ro(bq_s + (uint32_t)i * 4u), b1 = lds128f_ro(bq_s + (uint32_t)(32 + i) * 4u);
       v0[i] += b0.x; v0[i + 1] += b0.y; v0[i + 2] += b0.z; v0[i + 3] += b0.w;
       v1[i] += b1.x; v1[i + 1] += b1.y; v1[i + 2] += b1.z; v1[i + 3] += b1.w;
     }
@@ -499,29 +524,42 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
 // b1h_s = shared address of this chunk's 128 biases as fp16.
 __device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) {
-  // Both 32-column pieces of this thread are read first and the accumulator is released at once (FC1 of
-  // chunk c+2 can start).
-  float va[32], vb[32];
-  const uint32_t s_col = b ? kColS1 : kColS0;
-  tmem_ld32(c.lane_addr(s_col + c.hf * 32), va);
-  tmem_ld32(c.lane_addr(s_col + 64 + c.hf * 32), vb);
+  // Four steps of 16 columns; the next step's TMEM load is in flight while the current 8 pairs go through the
+  // GELU as 8 independent dependency chains (small live state: ptxas interleaves chains only as far as
+  // registers allow).  The accumulator is released after the last load: FC1 of chunk c+2 is issued behind
+  // FC2 of this chunk anyway, which needs all of H.
+  float v0[16], v1[16];
+  const uint32_t s_col = (b ? kColS1 : kColS0) + c.hf * 32;
+  const uint32_t h_s = c.sbase + (b ? kSmH1 : kSmH0);
+  auto emit = [&](const float (&v)[16], uint32_t col, uint32_t atom, uint32_t k0) {
+    const uint4 bb0 = lds128_ro(b1h_s + col * 2u), bb1 = lds128_ro(b1h_s + col * 2u + 16u);
+    __half2 x[8];
+    x[0] = __hadd2(__floats2half2_rn(v[0], v[1]), bits2h(bb0.x));
+    x[1] = __hadd2(__floats2half2_rn(v[2], v[3]), bits2h(bb0.y));
+    x[2] = __hadd2(__floats2half2_rn(v[4], v[5]), bits2h(bb0.z));
+    x[3] = __hadd2(__floats2half2_rn(v[6], v[7]), bits2h(bb0.w));
+    x[4] = __hadd2(__floats2half2_rn(v[8], v[9]), bits2h(bb1.x));
+    x[5] = __hadd2(__floats2half2_rn(v[10], v[11]), bits2h(bb1.y));
+    x[6] = __hadd2(__floats2half2_rn(v[12], v[13]), bits2h(bb1.z));
+    x[7] = __hadd2(__floats2half2_rn(v[14], v[15]), bits2h(bb1.w));
+    gelu2_vec<8>(x);
+    sts128(c.chunk_addr(atom, k0), h2bits(x[0]), h2bits(x[1]), h2bits(x[2]), h2bits(x[3]));
+    sts128(c.chunk_addr(atom, k0 + 1), h2bits(x[4]), h2bits(x[5]), h2bits(x[6]), h2bits(x[7]));
+  };
+  tmem_ld16(c.lane_addr(s_col), v0);
+  tmem_wait_ld();
+  tmem_ld16(c.lane_addr(s_col + 16), v1);
+  emit(v0, c.hf * 32, h_s, c.hf * 4);
+  tmem_wait_ld();
+  tmem_ld16(c.lane_addr(s_col + 64), v0);
+  emit(v1, c.hf * 32 + 16, h_s, c.hf * 4 + 2);
+  tmem_wait_ld();
+  tmem_ld16(c.lane_addr(s_col + 80), v1);
+  emit(v0, 64 + c.hf * 32, h_s + 16384, c.hf * 4);
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
-  const uint32_t h_s = c.sbase + (b ? kSmH1 : kSmH0);
-  auto emit = [&](const float (&v)[32], uint32_t col, uint32_t atom) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 bb = lds128(b1h_s + (col + q * 8) * 2u);
-      const __half2 g0 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]), bits2h(bb.x)));
-      const __half2 g1 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]), bits2h(bb.y)));
-      const __half2 g2 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]), bits2h(bb.z)));
-      const __half2 g3 = gelu2(__hadd2(__floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]), bits2h(bb.w)));
-      sts128(c.chunk_addr(atom, c.hf * 4 + q), h2bits(g0), h2bits(g1), h2bits(g2), h2bits(g3));
-    }
-  };
-  emit(va, c.hf * 32, h_s);
-  emit(vb, 64 + c.hf * 32, h_s + 16384);
+  emit(v1, 64 + c.hf * 32 + 16, h_s + 16384, c.hf * 4 + 2);
   fence_async_smem();                     // one generic->async proxy fence per chunk
   c.arrive(B_OP_READY0 + b);
   c.arrive(B_OP_READY0B + b);
@@ -743,6 +781,148 @@ __device__ void load_vec_async(const Compute& c, uint32_t dst_off, const float* 
   cp_async_commit();
 }
 
+// ---- cold parts of the compute role, out of line: the layer loop then keeps only a handful of values live
+// across its calls, which leaves the register file to the hot drains (ptxas interleaves their dependent chains
+// only as far as registers allow).  Everything is re-derived from the kernel parameters.
+constexpr uint32_t kSmTlCursor = kSmBars + 400;              // DBG: timeline cursor of compute thread 0
+template <bool DBG>
+__device__ __forceinline__ void stamp(const Compute& c) {
+  if constexpr (DBG) {
+    if (c.ctid == 0) {
+      long long** cur = reinterpret_cast<long long**>(c.sm + kSmTlCursor);
+      if (*cur != nullptr) { **cur = clock64(); ++*cur; }
+    }
+  }
+}
+struct XBufs { float *xcur, *d1, *x2, *dU, *sigv; };
+__device__ __forceinline__ XBufs xbufs(uint8_t* sm) {
+  float* xbuf = reinterpret_cast<float*>(sm + kSmProg + 1024);
+  return {xbuf, xbuf + kXFloats, xbuf + 2 * kXFloats, xbuf + 3 * kXFloats, xbuf + 4 * kXFloats};
+}
+
+// x of this tile's sequences -> shared memory (kept there across all sampler steps)
+__device__ __noinline__ void tile_begin(const Compute c, const FastParams& p, int tile) {
+  const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
+  const int nls = cfg ? p.S / 2 : p.S, n_x = nls * p.t * p.act;
+  const int seq0 = tile * nls, ns = max(0, min(nls, p.B - seq0));
+  const XBufs xb = xbufs(c.sm);
+  compute_sync();                                            // previous tile's x fully written out
+  for (int i = c.ctid; i < n_x; i += kComputeThreads)
+    xb.xcur[i] = (i < ns * p.t * p.act) ? p.xin[(size_t)seq0 * p.t * p.act + i] : 0.f;
+}
+__device__ __noinline__ void tile_end(const Compute c, const FastParams& p, int tile) {
+  const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
+  const int nls = cfg ? p.S / 2 : p.S;
+  const int seq0 = tile * nls, ns = max(0, min(nls, p.B - seq0));
+  const XBufs xb = xbufs(c.sm);
+  compute_sync();
+  for (int i = c.ctid; i < ns * p.t * p.act; i += kComputeThreads) p.out[(size_t)seq0 * p.t * p.act + i] = xb.xcur[i];
+}
+
+// noise levels of this evaluation + the embedding-GEMM A operand
+template <bool DBG>
+__device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p, const SampleArgs& sa, int tile, int step, int second) {
+  const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
+  const int nls = cfg ? p.S / 2 : p.S, seq0 = tile * nls;
+  const XBufs xb = xbufs(c.sm);
+  const float s_hat = sa.n_steps ? sa.sig[step] : 0.f;
+  const float s_next = sa.n_steps ? sa.sig[step + 1] : 0.f;
+  const float s_eval = second ? s_next : s_hat;
+  for (int i = c.ctid; i < p.S; i += kComputeThreads) {
+    const int ls = cfg ? (i >> 1) : i;
+    xb.sigv[i] = sa.n_steps ? s_eval : ((seq0 + ls < p.B) ? __ldg(p.sigma + seq0 + ls) : 1.0f);
+  }
+  compute_sync();
+  const EmbedTask etask = make_embed_task(c, p, tile);
+  stamp<DBG>(c);
+  build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv);
+  stamp<DBG>(c);
+}
+
+// ln_f + action head read-out + pre-conditioning (+ CFG mix) + sampler update of x.  Returns the barrier phases.
+template <bool DBG>
+__device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, const SampleArgs& sa, int tile, int step, int second,
+                                               float* trace_row) {
+  const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
+  const bool inner = (p.flags & BESO_FLAG_INNER) != 0;
+  const int nls = cfg ? p.S / 2 : p.S, seq0 = tile * nls;
+  const int ns = max(0, min(nls, p.B - seq0));
+  const XBufs xb = xbufs(c.sm);
+  float* xcur = xb.xcur; float* d1 = xb.d1; float* x2 = xb.x2; float* dU = xb.dU;
+  const float* xsrc = second ? xb.x2 : xb.xcur;
+  const float s_hat = sa.n_steps ? sa.sig[step] : 0.f;
+  const float s_next = sa.n_steps ? sa.sig[step + 1] : 0.f;
+  const float* vecA = reinterpret_cast<const float*>(c.sm + kSmVecA);
+  cp_async_wait<1>();                                 // final vecA block (vecM(0) may still fly)
+  compute_sync();
+  c.wait(B_X_DONE);
+  tc_fence_after();
+  stamp<DBG>(c);
+  ln_pass<DBG>(c, c.sbase + kSmVecA, trace_row);
+  stamp<DBG>(c);
+  c.wait(B_ACC_FULL0);
+  tc_fence_after();
+  stamp<DBG>(c);
+  float pr[16];
+  tmem_ld16(c.lane_addr(kColS0), pr);
+  tmem_wait_ld();
+  tc_fence_before();
+  c.arrive(B_ACC_EMPTY0);
+  const float* hb = vecA + 3 * kD;
+  const int vs = c.row / p.T, tok = c.row - vs * p.T;
+  const int j = tok - 1 - p.G;
+  const int ls = cfg ? (vs >> 1) : vs;
+  const bool act_row = (c.hf == 0) && vs < p.S && tok > p.G && (j & 1) && (ls < ns);
+  const int xo = (ls * p.t + (j >> 1)) * p.act;
+  float dval[kMaxAct];
+  if (act_row) {
+    const float sg = xb.sigv[vs];
+    const float den = sg * sg + p.sigma_data * p.sigma_data;
+    const float c_skip = p.sigma_data * p.sigma_data / den, c_out = sg * p.sigma_data / sqrtf(den);
+#pragma unroll
+    for (int a = 0; a < kMaxAct; ++a) {
+      if (a < p.act) {
+        const float f = pr[a] + hb[a];
+        dval[a] = inner ? f : __fadd_rn(__fmul_rn(f, c_out), __fmul_rn(xsrc[xo + a], c_skip));
+      }
+    }
+    if (cfg && (vs & 1)) {
+#pragma unroll
+      for (int a = 0; a < kMaxAct; ++a) if (a < p.act) dU[xo + a] = dval[a];
+    }
+  }
+  if (cfg) compute_sync();
+  if (act_row && !(cfg && (vs & 1))) {
+#pragma unroll
+    for (int a = 0; a < kMaxAct; ++a) {
+      if (a < p.act) {
+        float D = dval[a];
+        if (cfg) D = __fadd_rn(dU[xo + a], __fmul_rn(p.lambda, __fsub_rn(D, dU[xo + a])));
+        const int i = xo + a;
+        if (sa.n_steps == 0) {
+          p.out[(size_t)seq0 * p.t * p.act + i] = D;
+        } else if (sa.sampler == BESO_SAMPLER_DDIM) {
+          xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], D));
+        } else {
+          const float dt = __fsub_rn(s_next, s_hat);
+          if (!second) {
+            const float dd = __fdiv_rn(__fsub_rn(xcur[i], D), s_hat);
+            const float xe = __fadd_rn(xcur[i], __fmul_rn(dd, dt));
+            if (sa.sampler == BESO_SAMPLER_HEUN && s_next != 0.0f) { d1[i] = dd; x2[i] = xe; } else xcur[i] = xe;
+          } else {
+            const float d2 = __fdiv_rn(__fsub_rn(x2[i], D), s_next);
+            xcur[i] = __fadd_rn(xcur[i], __fmul_rn(__fdiv_rn(__fadd_rn(d1[i], d2), 2.0f), dt));
+          }
+        }
+      }
+    }
+  }
+  // vecA is free again: first block of the next evaluation
+  compute_sync();
+  load_vec_async(c, kSmVecA, p.vec, kVecAFloats);
+  return c.phases;
+}
+
 // CG = 1: every CTA issues its own M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2) run cta_group::2
 // M = 256 MMAs issued by the leader CTA; each CTA streams and holds only HALF of every B operand, which
 // halves the L2 -> SMEM weight traffic and the shared-memory bandwidth the tensor core needs for B.
@@ -801,6 +981,38 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   if (warp == kProducerWarp) {
     // ======================= weight-tape producer =======================
     uint32_t g = 0;
+    if constexpr (CG == 1) {
+      // Two stages of 32 KB (slots {0,1} and {2,3}), one full / empty barrier pair per stage; the tape is
+      // contiguous in consumption order, so the producer only needs the byte count of each ring group.
+      auto fill = [&](const uint8_t* src, uint32_t bytes) {
+        const uint32_t slot = g & 2u, par = (g >> 2) & 1u;
+        const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8, dst = sbase + kSmRing + slot * kSlotBytes;
+        spin_wait(sbase + kSmBars + (B_EMPTY0 + slot) * 8, par ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(full, bytes);
+          const uint32_t h = bytes >> 1;                     // two requests in flight per group
+          bulk_g2s(dst, src, h, full);
+          bulk_g2s(dst + h, src + h, h, full);
+        }
+        __syncwarp();
+        g += 2;
+      };
+      for (int it = 0; it < my_tiles * p.evals; ++it) {
+        const uint8_t* src = p.tape;
+        fill(src, 32768); fill(src + 32768, 32768); src += 65536;               // embedding
+#pragma unroll 1
+        for (int l = 0; l < p.L; ++l) {
+#pragma unroll 1
+          for (uint32_t i = 0; i < 20; ++i) {                // Q0 Q1 P0 Q2 P1 Q3 P2 P3 (QKV = 4 groups of 24 KB)
+            const uint32_t bytes = ((0xC2100u >> i) & 1u) ? 32768u : 24576u;   // proj groups at 8, 13, 18, 19
+            fill(src, bytes); src += bytes;
+          }
+#pragma unroll 1
+          for (uint32_t i = 0; i < 32; ++i) { fill(src, 32768); src += 32768; }   // FC1 / FC2 groups
+        }
+        fill(src, 8192);                                     // action head: 4 K blocks of [16 x 64]
+      }
+    } else {
     for (int it = 0; it < my_tiles * p.evals; ++it) {
       uint32_t off = 0;
       int li = 0;
@@ -812,10 +1024,129 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         off += n * 128u * (kk2 ? 2u : 1u);
       }
     }
+    }
   } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (leader) / full-barrier forwarder (peer CTA of a pair) ==========
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     uint32_t g = 0, phases = (1u << B_ACC_EMPTY0) | (1u << B_ACC_EMPTY1);   // "empty" barriers pass the first time
+    if constexpr (CG == 1) {
+      // ---- straight-line schedule: shapes, operand offsets and barrier ids are compile-time constants, the
+      // whole warp runs the (uniform) control flow and one elected lane issues tcgen05.mma / commit.  The issuer
+      // has to stay ahead of the tensor pipe: ~50 instructions per ring group instead of a table walk.
+      const uint32_t bars = sbase + kSmBars;
+      const uint32_t dlo = ((sbase >> 4) & 0x3FFFu) | (1u << 16);        // descriptor low word of shared offset 0
+      constexpr uint32_t dhi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      auto desc = [&](uint32_t lo) -> uint64_t { return (uint64_t)lo | ((uint64_t)dhi << 32); };
+      long long* tl = nullptr;
+      long long t_bw = 0, t_rw = 0;
+      auto job_begin = [&]() { if constexpr (DBG) { if (tl != nullptr) { tl[0] = clock64(); t_bw = t_rw = 0; } } };
+      auto job_end = [&]() { if constexpr (DBG) { if (tl != nullptr) { tl[1] = t_bw; tl[2] = t_rw; tl[3] = clock64(); tl += 4; } } };
+      auto jwait = [&](uint32_t id) {                                    // a compute -> MMA barrier
+        const uint32_t par = (phases >> id) & 1u;
+        phases ^= 1u << id;
+        long long t = 0;
+        if constexpr (DBG) t = clock64();
+        spin_wait(bars + id * 8, par);
+        if constexpr (DBG) t_bw += clock64() - t;
+      };
+      auto jcommit = [&](uint32_t id) { if (elect_one()) mma_commit(bars + id * 8); __syncwarp(); };
+      // one ring group (stage of up to 32 KB): NKB K blocks of 64; A atoms 16 KB apart from a_off, B sub-tiles
+      // B_STEP bytes apart in the stage
+      auto group = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, uint32_t a_off, uint32_t d_col, uint32_t acc) {
+        constexpr uint32_t N = decltype(n_tag)::value, NKB = decltype(nkb_tag)::value, B_STEP = decltype(bstep_tag)::value;
+        constexpr uint32_t idesc = decltype(bf16_tag)::value ? idesc_bf16_m128(N) : idesc_f16_m128(N);
+        const uint32_t slot = g & 2u, par = (g >> 2) & 1u;
+        long long t = 0;
+        if constexpr (DBG) t = clock64();
+        spin_wait(bars + (B_FULL0 + slot) * 8, par);
+        if constexpr (DBG) t_rw += clock64() - t;
+        tc_fence_after();
+        const uint32_t a_lo = dlo + (a_off >> 4), b_lo = dlo + ((kSmRing + slot * kSlotBytes) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+              mma_bf16(tm + d_col, desc(a_lo + kb * 1024u + 2u * j), desc(b_lo + kb * (B_STEP >> 4) + 2u * j), idesc,
+                       (acc | kb | j) ? 1u : 0u);
+          mma_commit(bars + (B_EMPTY0 + slot) * 8);
+        }
+        __syncwarp();
+        g += 2;
+      };
+      using std::integral_constant;
+      auto I = [](auto v) { return v; };
+      (void)I;
+#define BESO_IC(v) integral_constant<uint32_t, (v)>{}
+      for (int it = 0; it < my_tiles * p.evals; ++it) {
+        if constexpr (DBG) tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
+        // ---- embedding GEMM (bf16): X = A_emb W_emb^T, K = 128 ----
+        job_begin();
+        jwait(B_A_READY);
+        group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(1), kSmA, kColX, 0);
+        group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(1), kSmA + 16384, kColX, 1);
+        jcommit(B_X_DONE);
+        job_end();
+#pragma unroll 1
+        for (int l = 0; l < p.L; ++l) {
+          // ---- attention half: Q0 Q1 P0 Q2 P1 Q3 P2 P3 ----
+#pragma unroll 1
+          for (int h = 0; h <= kH; ++h) {
+            if (h < kH) {                                    // [Q|K|V] of head h -> S0 (192 columns)
+              job_begin();
+              jwait(B_ACC_EMPTY0);
+              if (h == 0) jwait(B_A_READY);
+#pragma unroll
+              for (uint32_t kb = 0; kb < 4; ++kb)
+                group(BESO_IC(192), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, kColS0, kb);
+              jcommit(B_ACC_FULL0);
+              job_end();
+            }
+            if (h >= 1) {                                    // X += Y_{h-1} Wproj[:, h-1]^T
+              job_begin();
+              jwait(B_Y_READY);
+              group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmY, kColX, 1);
+              jcommit(B_Y_EMPTY);
+              if (h == kH) jcommit(B_X_DONE);
+              job_end();
+            }
+          }
+          // ---- MLP half: F1_0 F1_1 F2_0 (F1_c F2_c-1) F2_7; hidden chunk c lives in accumulator / H buffer c & 1 ----
+#pragma unroll 1
+          for (int c = 0; c <= 8; ++c) {
+            if (c < 8) {
+              const uint32_t b = c & 1;
+              job_begin();
+              jwait(B_ACC_EMPTY0 + b);
+              if (c == 0) jwait(B_A_READY);
+              group(BESO_IC(128), BESO_IC(2), BESO_IC(16384), BESO_IC(0), kSmA, b ? kColS1 : kColS0, 0);
+              group(BESO_IC(128), BESO_IC(2), BESO_IC(16384), BESO_IC(0), kSmA + 32768, b ? kColS1 : kColS0, 1);
+              jcommit(B_ACC_FULL0 + b);
+              job_end();
+            }
+            if (c >= 1) {                                    // X += H_{c-1} W2[:, chunk c-1]^T
+              const uint32_t b = (c - 1) & 1;
+              job_begin();
+              jwait(B_OP_READY0 + b);
+              group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), b ? kSmH1 : kSmH0, kColX, 1);
+              jwait(B_OP_READY0B + b);
+              group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), (b ? kSmH1 : kSmH0) + 16384, kColX, 1);
+              jcommit(B_OP_EMPTY0 + b);
+              if (c == 8) jcommit(B_X_DONE);
+              job_end();
+            }
+          }
+        }
+        // ---- action head (N = 16, K = 256: one 8 KB group) ----
+        job_begin();
+        jwait(B_A_READY);
+        jwait(B_ACC_EMPTY0);
+        group(BESO_IC(16), BESO_IC(4), BESO_IC(2048), BESO_IC(0), kSmA, kColS0, 0);
+        jcommit(B_ACC_FULL0);
+        job_end();
+      }
+#undef BESO_IC
+    } else
     for (int it = 0; it < my_tiles * p.evals; ++it) {
       if (CG == 2 && rank != 0) {
         // peer CTA: tell the leader when this CTA's half of each B operand has landed
@@ -877,51 +1208,28 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     c.lane = lane; c.wq = warp & 3; c.hf = (warp - kComputeWarp0) >> 2;
     c.row = c.wq * 32 + lane;
     c.row_off = (uint32_t)c.row * 128u; c.rx4 = ((uint32_t)c.row & 7u) << 4;
-    long long* tlc = nullptr;                                // timeline cursor of compute thread 0
-    auto stamp = [&]() { if constexpr (DBG) { if (tlc != nullptr) *tlc++ = clock64(); } };
-    const uint32_t vecA_s = sbase + kSmVecA, vecM_s = sbase + kSmVecM;
     c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
-    float* vecA = reinterpret_cast<float*>(sm + kSmVecA);
-    float* xbuf = reinterpret_cast<float*>(sm + kSmProg + 1024);
-    float* xcur = xbuf, *d1 = xbuf + kXFloats, *x2 = xbuf + 2 * kXFloats, *dU = xbuf + 3 * kXFloats;
-    float* sigv = xbuf + 4 * kXFloats;                       // per virtual sequence noise level
-    const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
-    const bool inner = (p.flags & BESO_FLAG_INNER) != 0;
-    const int nls = cfg ? p.S / 2 : p.S;                     // sequences per tile
-    const int n_x = nls * p.t * p.act;
-    const size_t layer_stride = kVecAFloats + kVecMFloats;
+    c.cg = CG;
+    const uint32_t vecA_s = sbase + kSmVecA, vecM_s = sbase + kSmVecM;
+    constexpr uint32_t layer_stride = kVecAFloats + kVecMFloats;
     load_vec_async(c, kSmVecA, p.vec, kVecAFloats);
     load_vec_async(c, kSmVecM, p.vec + kVecAFloats, kVecMFloats);
+    if constexpr (DBG) { if (c.ctid == 0) *reinterpret_cast<long long**>(sm + kSmTlCursor) = nullptr; }
 
-    c.cg = CG;
     for (int tj = 0; tj < my_tiles; ++tj) {
       const int tile = (group + tj * n_groups) * CG + (int)rank;     // >= n_tiles: dummy tile, protocol only
-      const int seq0 = tile * nls;
-      const int ns = max(0, min(nls, p.B - seq0));
-      const EmbedTask etask = make_embed_task(c, p, tile);
-      compute_sync();                                        // previous tile's x fully written out
-      for (int i = c.ctid; i < n_x; i += kComputeThreads)
-        xcur[i] = (i < ns * p.t * p.act) ? p.xin[(size_t)seq0 * p.t * p.act + i] : 0.f;
-      int step = 0;
-      bool second = false;
+      tile_begin(c, p, tile);
+      int step = 0, second = 0;
       for (int ev = 0; ev < p.evals; ++ev) {
-        const float s_hat = sa.n_steps ? sa.sig[step] : 0.f;
-        const float s_next = sa.n_steps ? sa.sig[step + 1] : 0.f;
-        const float s_eval = second ? s_next : s_hat;
-        for (int i = c.ctid; i < p.S; i += kComputeThreads) {
-          const int ls = cfg ? (i >> 1) : i;
-          sigv[i] = sa.n_steps ? s_eval : ((seq0 + ls < p.B) ? __ldg(p.sigma + seq0 + ls) : 1.0f);
-        }
-        compute_sync();
-        const float* xsrc = second ? x2 : xcur;
         auto trace_row = [&](int slot) -> float* {
           return (DBG && p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.row) * kD : nullptr;
         };
-        if constexpr (DBG)
-          tlc = (p.timeline != nullptr && blockIdx.x == 0 && c.ctid == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
-        stamp();
-        build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, xsrc, sigv);
-        stamp();
+        if constexpr (DBG) {
+          if (c.ctid == 0)
+            *reinterpret_cast<long long**>(sm + kSmTlCursor) =
+                (p.timeline != nullptr && blockIdx.x == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
+        }
+        eval_prologue<DBG>(c, p, sa, tile, step, second);
 
         for (int l = 0; l < p.L; ++l) {
           // ---------------- attention half ----------------
@@ -929,121 +1237,52 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           compute_sync();                                   // vecA(l) (and vecM(l)) landed for everyone
           c.wait(B_X_DONE);
           tc_fence_after();
-          stamp();
+          stamp<DBG>(c);
           ln_pass<DBG>(c, vecA_s, trace_row(2 * l));
-          stamp();
+          stamp<DBG>(c);
           for (int h = 0; h < kH; ++h) {
             c.wait(B_ACC_FULL0);
             tc_fence_after();
-            stamp();
-            drain_qkv(c, vecA_s + (uint32_t)(3 * kD + h * 192) * 4u);            // arrives on ACC_EMPTY0 once its TMEM reads are done
+            stamp<DBG>(c);
+            drain_qkv(c, vecA_s + (uint32_t)(3 * kD + h * 192) * 4u);   // arrives on ACC_EMPTY0 once its TMEM reads are done
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
             c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
-            stamp();
+            stamp<DBG>(c);
             attention_head(sm, sbase, c.ctid >> 5, lane, p.S, p.T);
             fence_async_smem();
             c.arrive(B_Y_READY);
-            stamp();
+            stamp<DBG>(c);
             attn_sync();                                    // staging may be overwritten by the next drain
-            stamp();
+            stamp<DBG>(c);
           }
           // vecA is free: prefetch the next layer's (or the final block)
           load_vec_async(c, kSmVecA, p.vec + (size_t)(l + 1) * layer_stride, kVecAFloats);
           // ---------------- MLP half ----------------
           c.wait(B_X_DONE);
           tc_fence_after();
-          stamp();
+          stamp<DBG>(c);
           ln_pass<DBG>(c, vecM_s, trace_row(2 * l + 1));
-          stamp();
+          stamp<DBG>(c);
           for (int ch = 0; ch < 8; ++ch) {
             const int b = ch & 1;
             c.wait2(b ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
-            stamp();
-            drain_gelu(c, b, vecM_s + (uint32_t)kD * 4u + (uint32_t)ch * 256u);     // arrives on ACC_EMPTY and (twice) on OP_READY itself
-            stamp();
+            stamp<DBG>(c);
+            drain_gelu(c, b, vecM_s + (uint32_t)kD * 4u + (uint32_t)ch * 256u);   // arrives on ACC_EMPTY and (twice) on OP_READY itself
+            stamp<DBG>(c);
           }
           compute_sync();                                   // everyone done with vecM(l)
           const int nl = (l + 1 < p.L) ? l + 1 : 0;
           load_vec_async(c, kSmVecM, p.vec + (size_t)nl * layer_stride + kVecAFloats, kVecMFloats);
         }
         // ---------------- ln_f + action head + pre-conditioning + sampler update ----------------
-        cp_async_wait<1>();                                 // final vecA block (vecM(0) may still fly)
-        compute_sync();
-        c.wait(B_X_DONE);
-        tc_fence_after();
-        stamp();
-        ln_pass<DBG>(c, vecA_s, trace_row(2 * p.L));
-        stamp();
-        c.wait(B_ACC_FULL0);
-        tc_fence_after();
-        stamp();
-        float pr[16];
-        tmem_ld16(c.lane_addr(kColS0), pr);
-        tmem_wait_ld();
-        tc_fence_before();
-        c.arrive(B_ACC_EMPTY0);
-        const float* hb = vecA + 3 * kD;
-        const int vs = c.row / p.T, tok = c.row - vs * p.T;
-        const int j = tok - 1 - p.G;
-        const int ls = cfg ? (vs >> 1) : vs;
-        const bool act_row = (c.hf == 0) && vs < p.S && tok > p.G && (j & 1) && (ls < ns);
-        const int xo = (ls * p.t + (j >> 1)) * p.act;
-        float dval[kMaxAct];
-        if (act_row) {
-          const float sg = sigv[vs];
-          const float den = sg * sg + p.sigma_data * p.sigma_data;
-          const float c_skip = p.sigma_data * p.sigma_data / den, c_out = sg * p.sigma_data / sqrtf(den);
-#pragma unroll
-          for (int a = 0; a < kMaxAct; ++a) {
-            if (a < p.act) {
-              const float f = pr[a] + hb[a];
-              dval[a] = inner ? f : __fadd_rn(__fmul_rn(f, c_out), __fmul_rn(xsrc[xo + a], c_skip));
-            }
-          }
-          if (cfg && (vs & 1)) {
-#pragma unroll
-            for (int a = 0; a < kMaxAct; ++a) if (a < p.act) dU[xo + a] = dval[a];
-          }
-        }
-        if (cfg) compute_sync();
-        if (act_row && !(cfg && (vs & 1))) {
-#pragma unroll
-          for (int a = 0; a < kMaxAct; ++a) {
-            if (a < p.act) {
-              float D = dval[a];
-              if (cfg) D = __fadd_rn(dU[xo + a], __fmul_rn(p.lambda, __fsub_rn(D, dU[xo + a])));
-              const int i = xo + a;
-              if (sa.n_steps == 0) {
-                p.out[(size_t)seq0 * p.t * p.act + i] = D;
-              } else if (sa.sampler == BESO_SAMPLER_DDIM) {
-                xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], D));
-              } else {
-                const float dt = __fsub_rn(s_next, s_hat);
-                if (!second) {
-                  const float dd = __fdiv_rn(__fsub_rn(xcur[i], D), s_hat);
-                  const float xe = __fadd_rn(xcur[i], __fmul_rn(dd, dt));
-                  if (sa.sampler == BESO_SAMPLER_HEUN && s_next != 0.0f) { d1[i] = dd; x2[i] = xe; } else xcur[i] = xe;
-                } else {
-                  const float d2 = __fdiv_rn(__fsub_rn(x2[i], D), s_next);
-                  xcur[i] = __fadd_rn(xcur[i], __fmul_rn(__fdiv_rn(__fadd_rn(d1[i], d2), 2.0f), dt));
-                }
-              }
-            }
-          }
-        }
+        c.phases = eval_epilogue<DBG>(c, p, sa, tile, step, second, trace_row(2 * p.L));
         if (sa.n_steps) {
-          if (!second && sa.sampler == BESO_SAMPLER_HEUN && s_next != 0.0f) second = true;
-          else { second = false; ++step; }
+          if (!second && sa.sampler == BESO_SAMPLER_HEUN && sa.sig[step + 1] != 0.0f) second = 1;
+          else { second = 0; ++step; }
         }
-        // vecA is free again: first block of the next evaluation
-        compute_sync();
-        load_vec_async(c, kSmVecA, p.vec, kVecAFloats);
       }
-      if (sa.n_steps) {
-        compute_sync();
-        for (int i = c.ctid; i < ns * p.t * p.act; i += kComputeThreads) p.out[(size_t)seq0 * p.t * p.act + i] = xcur[i];
-      }
+      if (sa.n_steps) tile_end(c, p, tile);
     }
     cp_async_wait<0>();
   }

@@ -14,7 +14,9 @@ for r in rows:
     if len(r) == 2 and r[0] == "File Path":
         cur_file = r[1].split("/")[-1]; continue
     if r and r[0] == "Line No":
-        hdr = r; i_s = hdr.index("# Samples"); i_i = hdr.index("Instructions Executed"); continue
+        hdr = r; i_s = hdr.index("# Samples"); i_i = hdr.index("Instructions Executed")
+        stall_cols = [(j, h[6:]) for j, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+        continue
     if hdr is None or len(r) < len(hdr):
         continue
     if r[0] != "":
@@ -24,7 +26,7 @@ for r in rows:
         except ValueError: return 0
     if not r[2].startswith("0x"):
         continue
-    sass.append((int(r[2], 16), r[3].strip(), num(r[i_s]), num(r[i_i]), cur_file, cur_line))
+    sass.append((int(r[2], 16), r[3].strip(), num(r[i_s]), num(r[i_i]), cur_file, cur_line, {h: num(r[j]) for j, h in stall_cols if num(r[j])}))
 sass.sort()
 regions, cur = [], []
 for s in sass:
@@ -46,4 +48,9 @@ for reg in regions:
         op = s[1].split()[0] if not s[1].startswith("@") else s[1].split()[1]
         ops[op.split(".")[0]] += s[3]
     print(f"region 0x{reg[0][0] & 0xfffff:05x}+{len(reg):5d} sass: inst {ni:10d} {100 * ni / tot_i:5.1f}%  samples {ns:6d} {100 * ns / tot_s:5.1f}%  lines~{[l for l, _ in lines.most_common(4)]}")
+    st = Counter()
+    for s_ in reg:
+        st.update(s_[6])
+    tot_st = max(sum(st.values()), 1)
+    print("      stalls:  " + " ".join(f"{k}={100 * v / tot_st:.0f}%" for k, v in st.most_common(7)))
     print("      top ops: " + " ".join(f"{o}={100 * n / max(ni, 1):.0f}%" for o, n in ops.most_common(12)))

@@ -36,11 +36,11 @@ def main():
     torch.cuda.synchronize()
     _lib.lib().beso_debug_set_timeline(None)
     tl = tl.cpu().tolist()
-    mma = [tl[5 * f:5 * f + 5] for f in range(NF)]
-    prod = tl[5 * NF:6 * NF]
+    NJ = 2 + 24 * L
+    jobs = [tl[4 * j:4 * j + 4] for j in range(NJ)]          # per MMA job: start, barrier-wait, ring-wait, end
     ev = [v for v in tl[6 * NF:] if v]
-    t0 = min(ev[0], mma[0][0])
-    print(f"# {name} B={B}: one evaluation = {max(ev[-1], mma[-1][2]) - t0} cycles")
+    t0 = min(ev[0], jobs[0][0])
+    print(f"# {name} B={B}: one evaluation = {max(ev[-1], jobs[-1][3]) - t0} cycles")
 
     # ---- compute warps ----
     it = iter(ev)
@@ -77,42 +77,23 @@ def main():
     print("compute totals:", tot)
 
     # ---- MMA issuer ----
-    print("## MMA issuer per job: [barrier wait | ring wait | total] cycles")
-    names = ["EMB"] * 4
-    layer = []
-    def qkv(h): return [f"QKV{h}"] * 8
-    def proj(h): return [f"PROJ{h}"] * 2
-    def fc1(c): return [f"FC1_{c}"] * 4
-    def fc2(c): return [f"FC2_{c}"] * 4
-    layer += qkv(0) + qkv(1) + proj(0) + qkv(2) + proj(1) + qkv(3) + proj(2) + proj(3)
-    layer += fc1(0) + fc1(1) + fc2(0)
+    print("## MMA issuer per job: start, cycles waiting on compute barriers / on the weight ring, total issue time, gap to next job")
+    names = ["EMB"]
+    layer = ["QKV0", "QKV1", "PROJ0", "QKV2", "PROJ1", "QKV3", "PROJ2", "PROJ3", "FC1_0", "FC1_1", "FC2_0"]
     for c in range(2, 8):
-        layer += fc1(c) + fc2(c - 1)
-    layer += fc2(7)
+        layer += [f"FC1_{c}", f"FC2_{c - 1}"]
+    layer += ["FC2_7"]
     for l in range(L):
         names += [f"L{l}.{n}" for n in layer]
-    names += ["HEAD"] * 4
-    agg, order = {}, []
-    for f in range(NF):
-        n = names[f]
-        if n not in agg:
-            agg[n] = [0, 0, mma[f][0], 0, 0, 0, 0]
-            order.append(n)
-        agg[n][0] += mma[f][1] - mma[f][0]
-        agg[n][1] += mma[f][2] - mma[f][1]
-        agg[n][3] = (mma[f + 1][0] if f + 1 < NF else mma[f][2]) - agg[n][2]
-        agg[n][4] += mma[f][3] - mma[f][2]          # descriptor set-up + MMA issue
-        agg[n][5] += mma[f][4] - mma[f][3]          # commits
-        agg[n][6] += (mma[f + 1][0] if f + 1 < NF else mma[f][4]) - mma[f][4]   # loop tail
+    names += ["HEAD"]
     tb = tr = 0
-    for n in order:
-        b, r, start, total, iss, com, tail = agg[n]
-        tb += b; tr += r
-        if n.startswith("L0.") or n.startswith("L1.FC") or not n.startswith("L"):
-            print(f"{n:10s} start {start - t0:7d}  barrier {b:6d}  ring {r:6d}  issue {iss:6d}  commit {com:6d}  tail {tail:6d}  total {total:6d}")
-    print(f"MMA issuer totals: barrier-wait {tb}  ring-wait {tr}  of {mma[-1][2] - mma[0][0]}")
-    lat = [mma[f][2] - prod[f] for f in range(NF) if mma[f][2] > prod[f] > 0] or [0]
-    print(f"fill latency (producer issue -> MMA sees full): median {sorted(lat)[len(lat) // 2]} max {max(lat)}")
+    for j, n in enumerate(names):
+        st, bw, rw, en = jobs[j]
+        tb += bw; tr += rw
+        gap = (jobs[j + 1][0] - en) if j + 1 < NJ else 0
+        if n.startswith("L0.") or n.startswith("L1.") or not n.startswith("L"):
+            print(f"{n:10s} start {st - t0:7d}  barrier {bw:6d}  ring {rw:6d}  total {en - st:6d}  busy {en - st - bw - rw:6d}  gap {gap:5d}")
+    print(f"MMA issuer totals: barrier-wait {tb}  ring-wait {tr}  of {jobs[-1][3] - jobs[0][0]}")
 
 
 if __name__ == "__main__":
