@@ -195,7 +195,7 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __noinline__ void wait_timeout(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
     if ((++polls & 63u) == 0 && clock64() - t0 > 8000000000ll) {
       printf("beso fast kernel: mbarrier id %u parity %u timed out (block %d thread %d)\n",
              (bar & 0x3FF) / 8, parity, blockIdx.x, threadIdx.x);
@@ -275,6 +275,11 @@ __device__ __forceinline__ void gelu2_vec(__half2 (&x)[NP]) {
 __device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
+__device__ __forceinline__ float ex2f(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -465,27 +470,30 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
           }
       mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
       mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+      // the scores are in log2 units (log2(e) / sqrt(hs) is folded into W_q): p = 2^(s - max), normalised
+      // before the P V product so that the output needs no scaling
       float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            sc[kt][nb][e] = ex2f(sc[kt][nb][e] - mx_lo);
+            sc[kt][nb][2 + e] = ex2f(sc[kt][nb][2 + e] - mx_hi);
+            sum_lo += sc[kt][nb][e]; sum_hi += sc[kt][nb][2 + e];
+          }
+      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+      const float inv_lo = __frcp_rn(sum_lo), inv_hi = __frcp_rn(sum_hi);
       uint32_t pa[2][4];                         // P as A fragments, one per 16-key step
 #pragma unroll
       for (int kt = 0; kt < 2; ++kt) {
-        float pv[2][4];
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            pv[nb][e] = __expf(sc[kt][nb][e] - mx_lo);
-            pv[nb][2 + e] = __expf(sc[kt][nb][2 + e] - mx_hi);
-            sum_lo += pv[nb][e]; sum_hi += pv[nb][2 + e];
-          }
-        }
-        pa[kt][0] = pack_f16x2(pv[0][0], pv[0][1]);   // (row lo, keys 0-7)
-        pa[kt][1] = pack_f16x2(pv[0][2], pv[0][3]);   // (row hi, keys 0-7)
-        pa[kt][2] = pack_f16x2(pv[1][0], pv[1][1]);   // (row lo, keys 8-15)
-        pa[kt][3] = pack_f16x2(pv[1][2], pv[1][3]);   // (row hi, keys 8-15)
+        pa[kt][0] = pack_f16x2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo);   // (row lo, keys 0-7)
+        pa[kt][1] = pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi);   // (row hi, keys 0-7)
+        pa[kt][2] = pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo);   // (row lo, keys 8-15)
+        pa[kt][3] = pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi);   // (row hi, keys 8-15)
       }
-      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
-      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
       // ---- O = P V ----
       float o[8][4];
 #pragma unroll
@@ -503,18 +511,17 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
           }
         }
       }
-      const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
       uint8_t* y = sm + kSmY;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         const int e = n * 8 + (lane & 3) * 2;    // column within the head
         if (i_lo < T) {
           const uint32_t r = row0 + i_lo;
-          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][0] * inv_lo, o[n][1] * inv_lo);
+          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][0], o[n][1]);
         }
         if (i_hi < T) {
           const uint32_t r = row0 + i_hi;
-          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][2] * inv_hi, o[n][3] * inv_hi);
+          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][2], o[n][3]);
         }
       }
     }
@@ -553,6 +560,8 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) 
   tmem_wait_ld();
   tmem_ld16(c.lane_addr(s_col + 64), v0);
   emit(v1, c.hf * 32 + 16, h_s, c.hf * 4 + 2);
+  fence_async_smem();                     // K atom 0 of H is complete: FC2's first k-block may start
+  c.arrive(B_OP_READY0 + b);
   tmem_wait_ld();
   tmem_ld16(c.lane_addr(s_col + 80), v1);
   emit(v0, 64 + c.hf * 32, h_s + 16384, c.hf * 4);
@@ -560,8 +569,7 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) 
   tc_fence_before();
   c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
   emit(v1, 64 + c.hf * 32 + 16, h_s + 16384, c.hf * 4 + 2);
-  fence_async_smem();                     // one generic->async proxy fence per chunk
-  c.arrive(B_OP_READY0 + b);
+  fence_async_smem();
   c.arrive(B_OP_READY0B + b);
 }
 
@@ -1532,7 +1540,7 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
     tiles.push_back({src, ld, row0, col0, rows, vrows, 64, scale, off, colscale});
     off += rows * 128;
   };
-  const float qscale = 0.125f;                                // 1 / sqrt(64): exact power of two
+  const float qscale = 0.125f * 1.4426950408889634f;          // log2(e) / sqrt(64): the softmax works in base 2
   for (int l = 0; l < L; ++l) {
     const float *wk = prm[p_layer(l, 4)], *wq = prm[p_layer(l, 6)], *wv = prm[p_layer(l, 8)], *wp = prm[p_layer(l, 10)];
     const float *w1 = prm[p_layer(l, 12)], *w2 = prm[p_layer(l, 14)];

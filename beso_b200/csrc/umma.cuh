@@ -37,6 +37,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// Same with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of burning issue slots of its scheduler in a polling loop.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }

@@ -28,6 +28,10 @@ for r in rows:
         continue
     sass.append((int(r[2], 16), r[3].strip(), num(r[i_s]), num(r[i_i]), cur_file, cur_line, {h: num(r[j]) for j, h in stall_cols if num(r[j])}))
 sass.sort()
+dedup = {}
+for s_ in sass:            # the cuda,sass view repeats a SASS row under every inlined source line it belongs to
+    dedup.setdefault(s_[0], s_)
+sass = [dedup[a] for a in sorted(dedup)]
 regions, cur = [], []
 for s in sass:
     cur.append(s)
