@@ -256,12 +256,12 @@ def main():
                 "kernel": "fast_sample_kernel<1>" if mode_name == "fast" else "simt_denoise_kernel",
                 "peak_source": f"bf16_tflops_sustained of {how} (kernel runs for ms inside a long step)",
                 "flops_per_launch": flops_launch,
-                "note": ("bf16 tcgen05 operands, fp32 accumulate" if mode_name == "fast" else
+                "note": ("fp16 tcgen05 (kind::f16) operands at the bf16 rate, fp32 accumulate in TMEM; peak = measured bf16 dense" if mode_name == "fast" else
                          "precise mode computes on the fp32 FMA pipe; the tensor peak is quoted for comparability")}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "bf16" if mode_name == "fast" else "f32", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f16" if mode_name == "fast" else "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "mode": mode_name, "sampler": "ddim", "n_sampling_steps": N_STEPS,
                       "batch_per_gpu": BATCH, "tokens_per_seq": cfg.n_tokens(), "l2": "flushed between timed steps (256 MiB write)",
                       "weights": "synthetic N(0,0.02) seed 1", "parallelism": f"replicas x{world}, no collective"},
