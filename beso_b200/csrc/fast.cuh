@@ -1,4 +1,4 @@
-// FAST mode interface: bf16 tcgen05 fused score-GPT (fast_forward.cu).
+// FAST mode interface: fp16 tcgen05 fused score-GPT (fast_forward.cu).
 #pragma once
 #include "common.cuh"
 

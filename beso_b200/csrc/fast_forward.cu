@@ -1,6 +1,7 @@
 // FAST mode: GCDenoiser -> DiffusionGPT forward and the DDIM / Euler / Heun sample loop as ONE
-// persistent, warp-specialised sm_100a kernel.  bf16 operands on tcgen05 tensor cores, fp32
-// accumulation in TMEM, fp32 LayerNorm / softmax / GELU / residual / pre-conditioning.
+// persistent, warp-specialised sm_100a kernel.  fp16 operands on tcgen05 tensor cores (bf16 for the
+// embedding GEMM), fp32 accumulation in TMEM, fp32 LayerNorm statistics / softmax / residual /
+// pre-conditioning, packed-fp16 GELU and LayerNorm scaling.
 //
 // Reference semantics (beso/agents/diffusion_agents/k_diffusion/): score_wrappers.py:31-43,81-96;
 // score_gpts.py:50-80,96-115,272-358; gc_sampling.py:167-213,259-314,895-924;
@@ -16,12 +17,12 @@
 //  * TMEM columns [256,512) are two 128-column scratch accumulators (per-head QKV, FC1 chunks).
 //  * Every GEMM B operand comes from one linear "weight tape" in HBM/L2, pre-swizzled into the
 //    UMMA K-major SWIZZLE_128B image and ordered exactly as the MMA warp consumes it; a producer
-//    thread streams it with cp.async.bulk (TMA engine) through a 4 x 16 KB mbarrier ring.
-//  * One elected thread issues every tcgen05.mma, driven by a small group table in shared memory (one
-//    entry per ring group: A operand, TMEM column, N, barriers to wait on / commit to).
+//    warp streams it with cp.async.bulk (TMA engine) through a ring of two 32 KB stages.
+//  * One elected thread issues every tcgen05.mma from a straight-line schedule (compile-time shapes,
+//    operand offsets and barrier ids); the cta_group::2 variant still walks a group table in shared memory.
 //  * 8 compute warps (2 per TMEM lane quadrant) do the LayerNorms, the QKV drain, causal
-//    attention with mma.sync on bf16 Q/K/V staged in shared memory, erf-GELU, the action head
-//    read-out, the Karras pre-conditioning and the sampler update.
+//    attention with mma.sync on fp16 Q/K/V staged in shared memory (with two helper warps), erf-GELU,
+//    the action head read-out, the Karras pre-conditioning and the sampler update.
 //  * Embeddings (state / goal / action / sigma / position / biases) are one K=128 GEMM: the A
 //    operand carries the raw inputs plus one-hot token-position columns whose B rows hold
 //    (bias + pos_emb) split into bf16 hi + lo, so X starts exact to ~2^-17.

@@ -16,7 +16,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
 struct WeightSlot {
   float* simt_buf = nullptr;     // transposed fp32 images (PRECISE)
   SimtModel simt{};
-  FastWeights fast{};            // bf16 UMMA tape + fp32 vectors (FAST)
+  FastWeights fast{};            // fp16 UMMA tape + fp32 / fp16 vectors (FAST)
   std::vector<const float*> params;   // raw fp32 parameter tensors, parameters() order (training path)
   bool packed = false;
 };
