@@ -28,6 +28,7 @@ EXPORTS = [
     "beso_loss_fwd_bwd", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
     "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
+    "beso_opt_create", "beso_opt_destroy", "beso_opt_total", "beso_opt_step",
 ]
 
 
@@ -93,6 +94,11 @@ def _declare(lib):
     lib.beso_debug_set_trace.argtypes = [vp]
     lib.beso_debug_set_timeline.argtypes = [vp]
     lib.beso_debug_mma_rate.argtypes = [vp, vp, i32, vp]
+    lib.beso_opt_create.argtypes = [i32, i32, C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(vp)]
+    lib.beso_opt_destroy.argtypes = [vp]
+    lib.beso_opt_total.argtypes = [vp]
+    lib.beso_opt_total.restype = C.c_longlong
+    lib.beso_opt_step.argtypes = [vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, f32, vp]
 
 
 def lib():

@@ -157,6 +157,26 @@ int beso_comm_init(int rank, int world, const char* unique_id128, int device, be
 int beso_comm_destroy(beso_comm* comm);
 int beso_allreduce_grads(beso_comm* comm, float* flat_grad_dev, size_t n, float scale, void* stream);
 
+/* Fused optimiser step.  Replaces, in BesoAgent.train_step (beso_agent.py:238-247),
+ * optimizer.step() of torch.optim.AdamW (configs/agents/beso_kitchen.yaml:9-12) and
+ * ExponentialMovingAverage.update (beso/networks/ema_helper/ema.py:36-53): ONE launch over all parameter
+ * tensors, every element read and written once, arithmetic in the order of torch's single-tensor AdamW.
+ *   beso_opt_create: param_dev_ptrs / numel describe the n_tensors fp32 parameter tensors in
+ *     parameters() order (the order of the flat gradient of beso_loss_fwd_bwd); they are updated in place.
+ *   beso_opt_step: flat_grad_dev, exp_avg_dev, exp_avg_sq_dev, ema_dev are flat fp32 buffers of
+ *     beso_opt_total() elements in the same order, owned by the caller.  step >= 1 is AdamW's step count
+ *     (bias correction), lr the current learning rate (the caller applies StepLR), ema_dev == NULL skips
+ *     the EMA, ema_decay is the decay of THIS update (the caller applies the warm-up min(decay,
+ *     (1+n)/(10+n)) of ema.py:47-50); grad_scale multiplies the gradient first (1/world after an
+ *     all-reduce(sum), 1 otherwise). */
+typedef struct beso_opt beso_opt;
+int beso_opt_create(int device, int n_tensors, float* const* param_dev_ptrs, const long long* numel, beso_opt** out);
+int beso_opt_destroy(beso_opt* opt);
+long long beso_opt_total(const beso_opt* opt);
+int beso_opt_step(beso_opt* opt, const float* flat_grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                  float* ema_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float ema_decay, float grad_scale, void* stream);
+
 /* Introspection used by tests and bench.py. */
 int64_t beso_kernel_launches(void);                /* kernels launched by this library so far   */
 int beso_plan_rows_per_cta(beso_plan* plan, int mode, int t); /* sequences handled per CTA      */
