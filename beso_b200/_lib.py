@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 MODE_PRECISE, MODE_FAST = 0, 1
 SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN = 0, 1, 2
-FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST = 1, 2, 4, 8
+FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_TF32 = 1, 2, 4, 8, 16
 SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN}
 MODE_IDS = {"precise": MODE_PRECISE, "fast": MODE_FAST}
 

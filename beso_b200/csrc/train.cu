@@ -421,7 +421,8 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   float* ones = take((size_t)M);
   cublasHandle_t h = ws->blas;
   BESO_CUBLAS(cublasSetStream(h, st));
-  BESO_CUBLAS(cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH));      // fp32 FMA, no TF32
+  // fp32 FMA by default (the reference's arithmetic); TF32 tensor-core GEMMs only on request
+  BESO_CUBLAS(cublasSetMathMode(h, (flags & BESO_FLAG_TRAIN_TF32) ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH));
 
   // ---- parameter pointers and gradient slots (parameters() order) ----
   std::vector<size_t> goff;

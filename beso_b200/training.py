@@ -33,7 +33,10 @@ def flat_grad_views(model, flat: torch.Tensor):
 
 def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_action_only=False, goal_keep=None,
                        need_grad=True):
-    """Runs ``beso_loss_fwd_bwd``; returns (loss 0-d tensor, flat gradient or None)."""
+    """Runs ``beso_loss_fwd_bwd``; returns (loss 0-d tensor, flat gradient or None).
+
+    ``model.train_math = "tf32"`` (default "fp32", the reference's arithmetic) runs the GEMMs on the tensor
+    cores in TF32."""
     inner = model.inner_model
     if any(p > 0 for p in inner._dropouts) and inner.training:
         raise _lib.BesoLibraryError("the fused training path needs attn_pdrop = resid_pdrop = embed_pdrob = 0")
@@ -51,6 +54,11 @@ def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_actio
     flat = torch.empty(sum(p.numel() for p in params), device=action.device, dtype=torch.float32) if need_grad else None
     keep_ptr = goal_keep.data_ptr() if goal_keep is not None else None
     flags = _lib.FLAG_PRED_LAST if pred_last_action_only else 0
+    math = getattr(model, "train_math", "fp32")
+    if math not in ("fp32", "tf32"):
+        raise ValueError(f"train_math must be 'fp32' or 'tf32', got {math!r}")
+    if math == "tf32":
+        flags |= _lib.FLAG_TRAIN_TF32
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(_lib.lib().beso_loss_fwd_bwd(plan, state.data_ptr(), action.data_ptr(), goal.data_ptr(), noise.data_ptr(),
                                            sigma.data_ptr(), keep_ptr, loss.data_ptr(),

@@ -62,6 +62,10 @@ enum {
                                   last step (score_wrappers.py:59-66, 76-77)                                     */
 #define BESO_FLAG_INNER 4u  /* return DiffusionGPT.forward(state, action, goal, sigma) itself, i.e. without
                                the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
+#define BESO_FLAG_TRAIN_TF32 16u /* beso_loss_fwd_bwd only: run the training GEMMs on the tensor cores in TF32
+                                  (cuBLAS CUBLAS_TF32_TENSOR_OP_MATH).  Opt-in: the reference multiplies in fp32
+                                  (torch.backends.cuda.matmul.allow_tf32 is False by default), which is the default
+                                  here and the mode the gradient-parity tests pin. */
 
 /* Constructor arguments of DiffusionGPT (k_diffusion/score_gpts.py:121-139) and
  * GCDenoiser.sigma_data (k_diffusion/score_wrappers.py:26-29). */

@@ -88,3 +88,35 @@ def test_goal_mask_changes_loss_and_matches_oracle(cuda_device):
                                goal_keep=keep)
     torch.testing.assert_close(loss.cpu(), want, rtol=1e-4, atol=1e-7)
     assert abs(float(loss.cpu()) - float(a["loss"])) > 1e-6
+
+
+def test_tf32_training_math_is_opt_in_and_close(cuda_device):
+    """model.train_math = "tf32": tensor-core GEMMs.  Not the reference's arithmetic (fp32), so it is opt-in and
+    only has to stay close: loss within 1e-3 relative, flat gradient direction within 1e-4 of the fp32 one."""
+    import time
+    cfg = B256
+    sd = synthetic_state_dict(cfg, 41)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd)
+    m.train()
+    g = cuda(synthetic_inputs(cfg, 4096, seed=42, sigma_min=0.05), cuda_device)
+    args = (g["state"], g["clean"], g["goal"], g["noise"], g["sigma"])
+    times = {}
+    out = {}
+    for math in ("fp32", "tf32"):
+        m.train_math = math
+        out[math] = loss_and_flat_grad(m, *args)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            loss_and_flat_grad(m, *args)
+        torch.cuda.synchronize()
+        times[math] = (time.perf_counter() - t0) / 3 * 1e3
+    (l32, f32), (ltf, ftf) = out["fp32"], out["tf32"]
+    torch.testing.assert_close(ltf, l32, rtol=1e-3, atol=1e-7)
+    cos = torch.nn.functional.cosine_similarity(f32, ftf, dim=0)
+    assert float(cos) > 1.0 - 1e-4, float(cos)
+    assert not torch.equal(f32, ftf)                         # the flag really switched the arithmetic
+    print(f"cfg3 fwd+bwd B=4096: fp32 {times['fp32']:.1f} ms, tf32 {times['tf32']:.1f} ms, grad cosine {float(cos):.7f}")
+    m.train_math = "bf16"
+    with pytest.raises(ValueError):
+        loss_and_flat_grad(m, *args)
