@@ -16,15 +16,15 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbeso_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MODE_PRECISE, MODE_FAST = 0, 1
-SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN = 0, 1, 2
+SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN, SAMPLER_EULER_ANCESTRAL = 0, 1, 2, 3
 FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_TF32 = 1, 2, 4, 8, 16
-SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN}
+SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN, "euler_ancestral": SAMPLER_EULER_ANCESTRAL}
 MODE_IDS = {"precise": MODE_PRECISE, "fast": MODE_FAST}
 
 EXPORTS = [
     "beso_last_error", "beso_abi_version", "beso_param_count", "beso_param_numel", "beso_param_total",
     "beso_plan_create", "beso_plan_destroy", "beso_plan_pack_weights", "beso_plan_select_weights", "beso_plan_set_params",
-    "beso_denoise_fwd", "beso_sample_loop", "beso_denoise_fwd_host", "beso_sample_loop_host",
+    "beso_denoise_fwd", "beso_sample_loop", "beso_sample_loop_noise", "beso_denoise_fwd_host", "beso_sample_loop_host",
     "beso_loss_fwd_bwd", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
     "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
@@ -81,6 +81,7 @@ def _declare(lib):
     lib.beso_plan_set_params.argtypes = [vp, i32, C.POINTER(vp), i32]
     lib.beso_denoise_fwd.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_sample_loop.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, i32, i32, u32, f32, vp]
+    lib.beso_sample_loop_noise.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_denoise_fwd_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_sample_loop_host.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp]

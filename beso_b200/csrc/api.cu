@@ -126,7 +126,8 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
 }
 
 static int make_sample_args(int sampler, const float* sig, int n_sigmas, const float* coef, SampleArgs* sa) {
-  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_HEUN) { set_error("unknown sampler"); return BESO_E_INVALID; }
+  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_EULER_ANCESTRAL) { set_error("unknown sampler"); return BESO_E_INVALID; }
+  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL && !coef) { set_error("euler_ancestral needs the (sigma_down, sigma_up) coefficients"); return BESO_E_INVALID; }
   if (!sig || n_sigmas < 2 || n_sigmas - 1 > kMaxSteps) { set_error("n_sigmas must be in [2, 129]"); return BESO_E_INVALID; }
   memset(sa, 0, sizeof(*sa));
   sa->n_steps = n_sigmas - 1;
@@ -278,9 +279,9 @@ int beso_denoise_fwd(beso_plan* p, int mode, const float* state, const float* ac
   return run(p, mode, sa, state, goal, action, sigma, out, B, t, flags, lambda, (cudaStream_t)stream);
 }
 
-int beso_sample_loop(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
-                     const float* state, const float* goal, float* x, int B, int t, uint32_t flags, float lambda,
-                     void* stream) {
+int beso_sample_loop_noise(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
+                           const float* state, const float* goal, float* x, const float* noise, int B, int t,
+                           uint32_t flags, float lambda, void* stream) {
   int rc = check_call(p, mode, B, t, flags);
   if (rc) return rc;
   if (!state || !x || (!goal && p->desc.goal_conditioned && p->desc.goal_len > 0)) {
@@ -290,7 +291,20 @@ int beso_sample_loop(beso_plan* p, int mode, int sampler, const float* sigmas, i
   SampleArgs sa;
   rc = make_sample_args(sampler, sigmas, n_sigmas, coef, &sa);
   if (rc) return rc;
+  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL) {
+    bool needs_noise = false;
+    for (int i = 0; i < sa.n_steps; ++i) needs_noise |= sa.ca[i] > 0.f;
+    if (needs_noise && !noise) { set_error("euler_ancestral needs the per-step noise (beso_sample_loop_noise)"); return BESO_E_INVALID; }
+  }
+  sa.noise = noise;
+  sa.noise_stride = (long long)B * t * p->desc.act_dim;
   return run(p, mode, sa, state, goal, x, nullptr, x, B, t, flags, lambda, (cudaStream_t)stream);
+}
+
+int beso_sample_loop(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
+                     const float* state, const float* goal, float* x, int B, int t, uint32_t flags, float lambda,
+                     void* stream) {
+  return beso_sample_loop_noise(p, mode, sampler, sigmas, n_sigmas, coef, state, goal, x, nullptr, B, t, flags, lambda, stream);
 }
 
 static int ensure_stage(beso_plan* p, size_t floats) {

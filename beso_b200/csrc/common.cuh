@@ -48,8 +48,10 @@ struct SampleArgs {
   int n_steps;   // 0 = single model evaluation with per-sequence sigma
   int sampler;   // BESO_SAMPLER_*
   float sig[kMaxSteps + 1];
-  float ca[kMaxSteps];   // DDIM: sigma_fn(t_next) / sigma_fn(t)
-  float ce[kMaxSteps];   // DDIM: expm1(-h)
+  float ca[kMaxSteps];   // DDIM: sigma_fn(t_next) / sigma_fn(t);  Euler ancestral: sigma_down
+  float ce[kMaxSteps];   // DDIM: expm1(-h);                        Euler ancestral: sigma_up
+  const float* noise;    // ancestral samplers: (n_steps, B, t, act) standard-normal draws of the caller
+  long long noise_stride;   // elements per step = B * t * act
 };
 
 struct SimtLaunch {

@@ -899,6 +899,13 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
           p.out[(size_t)seq0 * p.t * p.act + i] = D;
         } else if (sa.sampler == BESO_SAMPLER_DDIM) {
           xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], D));
+        } else if (sa.sampler == BESO_SAMPLER_EULER_ANCESTRAL) {      // gc_sampling.py:216-256
+          const float s_down = sa.ca[step];
+          const float dd = __fdiv_rn(__fsub_rn(xcur[i], D), s_hat);
+          float xe = __fadd_rn(xcur[i], __fmul_rn(dd, __fsub_rn(s_down, s_hat)));
+          if (s_down > 0.0f)
+            xe = __fadd_rn(xe, __fmul_rn(__ldg(sa.noise + (size_t)step * sa.noise_stride + (size_t)seq0 * p.t * p.act + i), sa.ce[step]));
+          xcur[i] = xe;
         } else {
           const float dt = __fsub_rn(s_next, s_hat);
           if (!second) {

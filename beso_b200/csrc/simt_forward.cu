@@ -346,12 +346,17 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
       for (int i = threadIdx.x; i < n; i += kThreads)
         sm.xcur[i] = __fsub_rn(__fmul_rn(ca, sm.xcur[i]), __fmul_rn(ce, sm.d1[i]));
     } else {
-      const float dt = __fsub_rn(s_next, s_hat);
+      // Euler ancestral (gc_sampling.py:216-256) steps down to sigma_down and adds sigma_up of fresh noise
+      const bool anc = sa.sampler == BESO_SAMPLER_EULER_ANCESTRAL;
+      const float dt = __fsub_rn(anc ? sa.ca[step] : s_next, s_hat);
       const bool heun2 = (sa.sampler == BESO_SAMPLER_HEUN) && (s_next != 0.0f);
+      const bool add_noise = anc && sa.ca[step] > 0.0f;
+      const float* nz = add_noise ? sa.noise + (size_t)step * sa.noise_stride + (size_t)seq0 * t * m.act : nullptr;
       for (int i = threadIdx.x; i < n; i += kThreads) {
         const float dd = __fdiv_rn(__fsub_rn(sm.xcur[i], sm.d1[i]), s_hat);   // to_d
         sm.d1[i] = dd;
-        const float xe = __fadd_rn(sm.xcur[i], __fmul_rn(dd, dt));
+        float xe = __fadd_rn(sm.xcur[i], __fmul_rn(dd, dt));
+        if (add_noise) xe = __fadd_rn(xe, __fmul_rn(__ldg(nz + i), sa.ce[step]));
         if (heun2) sm.x2[i] = xe; else sm.xcur[i] = xe;
       }
       if (heun2) {                            // gc_sampling.py:304-310

@@ -333,8 +333,10 @@ class GCDenoiser(nn.Module):
         return out
 
     def sample(self, sampler: str, sigmas: torch.Tensor, state, x_t, goal, cfg_lambda: Optional[float] = None,
-               uncond: bool = False, coef: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The whole DDIM / Euler / Heun loop as one persistent kernel launch (beso_sample_loop)."""
+               uncond: bool = False, coef: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The whole DDIM / Euler / Heun / Euler-ancestral loop as one persistent kernel launch
+        (beso_sample_loop_noise).  ``noise``: (n_steps, B, t, act) standard-normal draws for the ancestral
+        sampler."""
         dev = self._device_index(x_t)
         state, x_t, goal = map(self._prep, (state, x_t, goal))
         B, t = self._check_shapes(state, x_t, goal)
@@ -348,11 +350,17 @@ class GCDenoiser(nn.Module):
             flags |= _lib.FLAG_CFG
             lam = float(cfg_lambda)
         x = x_t.clone()                                           # samplers never write the caller's x_t
+        noise_ptr = None
+        if noise is not None:
+            noise = self._prep(noise)
+            if tuple(noise.shape) != (len(sig) - 1,) + tuple(x.shape) or noise.device != x.device:
+                raise ValueError(f"noise must be {(len(sig) - 1,) + tuple(x.shape)} on {x.device}")
+            noise_ptr = noise.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.lib().beso_sample_loop(plan, self.resolved_mode(), _lib.SAMPLER_IDS[sampler], sig_arr,
-                                              len(sig), coef_arr, state.data_ptr(), goal.data_ptr(),
-                                              x.data_ptr(), B, t, flags, lam, C.c_void_p(stream)),
-                   "beso_sample_loop")
+        _lib.check(_lib.lib().beso_sample_loop_noise(plan, self.resolved_mode(), _lib.SAMPLER_IDS[sampler], sig_arr,
+                                                    len(sig), coef_arr, state.data_ptr(), goal.data_ptr(),
+                                                    x.data_ptr(), noise_ptr, B, t, flags, lam, C.c_void_p(stream)),
+                   "beso_sample_loop_noise")
         return x
 
 

@@ -70,7 +70,7 @@ def _fusable(model):
     return None
 
 
-def _try_fused(name, model, state, action, goal, sigmas, scaler, extra_args, callback, churn, coef=None):
+def _try_fused(name, model, state, action, goal, sigmas, scaler, extra_args, callback, churn, coef=None, noise=None):
     if callback is not None or scaler is not None or churn or extra_args:
         return None
     f = _fusable(model)
@@ -79,7 +79,7 @@ def _try_fused(name, model, state, action, goal, sigmas, scaler, extra_args, cal
     den, lam, uncond = f
     if den.inner_model.training and den.inner_model.cond_mask_prob > 0:
         return None                       # goal masking draws from the RNG every call
-    return den.sample(name, sigmas, state, action, goal, cfg_lambda=lam, uncond=uncond, coef=coef)
+    return den.sample(name, sigmas, state, action, goal, cfg_lambda=lam, uncond=uncond, coef=coef, noise=noise)
 
 
 def ddim_coefficients(sigmas: torch.Tensor) -> torch.Tensor:
@@ -183,7 +183,65 @@ def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None
     return action
 
 
-SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun}
+def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
+    """(sigma_down, sigma_up) of an ancestral step (gc_sampling.py:108-114), same expression on whatever the
+    arguments are (0-d fp32 tensors in the samplers)."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+def ancestral_coefficients(sigmas: torch.Tensor, eta: float = 1.0) -> torch.Tensor:
+    """Per-step (sigma_down, sigma_up) evaluated with the reference's own fp32 tensor ops on the host."""
+    s = sigmas.detach().float().cpu()
+    rows = []
+    for i in range(len(s) - 1):
+        down, up = get_ancestral_step(s[i], s[i + 1], eta=eta)
+        rows.append([float(down), float(up)])
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+@torch.no_grad()
+def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                           disable=None, eta=1.0, noise=None):
+    """Ancestral sampling with Euler steps (gc_sampling.py:216-256; the kitchen evaluation default,
+    configs/evaluate_kitchen.yaml:12).  The ``torch.randn_like(action)`` draws of the reference -- one per step
+    with ``sigma_down > 0``, in step order -- are made here from the same generator and handed to the persistent
+    kernel, so the fused loop consumes the RNG stream exactly like the reference.  ``noise`` (n_steps, B, t, act)
+    overrides the draws (parity tests)."""
+    coef = ancestral_coefficients(sigmas, eta)
+    n = len(sigmas) - 1
+    fusable = (callback is None and scaler is None and not extra_args and _fusable(model) is not None and action.is_cuda
+               and 2 <= len(sigmas) <= 129)
+    if fusable:
+        if noise is None:
+            noise = torch.zeros((n,) + tuple(action.shape), device=action.device, dtype=torch.float32)
+            for i in range(n):
+                if float(coef[i, 0]) > 0:
+                    noise[i] = torch.randn_like(action)
+        fused = _try_fused("euler_ancestral", model, state, action, goal, sigmas, None, extra_args, callback, 0.0,
+                           coef=coef, noise=noise)
+        if fused is not None:
+            return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    for i in range(n):
+        denoised = model(state, action, goal, sigmas[i] * ones, **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        d = to_d(action, sigmas[i], denoised)
+        action = action + d * (sigma_down - sigmas[i])
+        if sigma_down > 0:
+            action = action + (noise[i] if noise is not None else torch.randn_like(action)) * sigma_up
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "euler_ancestral": sample_euler_ancestral}
 
 
 def n_model_evals(sampler: str, sigmas) -> int:

@@ -51,7 +51,8 @@ enum {
 enum {
   BESO_SAMPLER_DDIM = 0,  /* gc_sampling.py:895-924 */
   BESO_SAMPLER_EULER = 1, /* gc_sampling.py:167-213 (s_churn = 0) */
-  BESO_SAMPLER_HEUN = 2   /* gc_sampling.py:259-314 (s_churn = 0) */
+  BESO_SAMPLER_HEUN = 2,  /* gc_sampling.py:259-314 (s_churn = 0) */
+  BESO_SAMPLER_EULER_ANCESTRAL = 3 /* gc_sampling.py:216-256; needs beso_sample_loop_noise */
 };
 
 /* flags */
@@ -131,6 +132,20 @@ int beso_denoise_fwd(beso_plan* plan, int mode, const float* state_dev, const fl
 int beso_sample_loop(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
                      const float* coef_host, const float* state_dev, const float* goal_dev,
                      float* x_inout_dev, int B, int t, uint32_t flags, float cond_lambda, void* stream);
+
+/* beso_sample_loop with per-step noise, for the ancestral samplers.
+ * BESO_SAMPLER_EULER_ANCESTRAL = sample_euler_ancestral (gc_sampling.py:216-256, the kitchen evaluation default,
+ * configs/evaluate_kitchen.yaml:12):  x += to_d(x, sigma_i, D) * (sigma_down - sigma_i);  if sigma_down > 0:
+ * x += noise_i * sigma_up.
+ *   coef_host: 2*(n_sigmas-1) fp32, [2i] = sigma_down_i, [2i+1] = sigma_up_i as returned by get_ancestral_step
+ *              (gc_sampling.py:108-114), evaluated by the caller with the reference's own fp32 tensor ops.
+ *   noise_dev: (n_sigmas-1, B, t, act) fp32 = the torch.randn_like(action) draws of the reference, one per step
+ *              (entries of steps with sigma_down == 0 are never read).  The caller draws them, in step order,
+ *              so the result is bit-comparable with the reference under the same generator state. */
+int beso_sample_loop_noise(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
+                           const float* coef_host, const float* state_dev, const float* goal_dev,
+                           float* x_inout_dev, const float* noise_dev, int B, int t, uint32_t flags,
+                           float cond_lambda, void* stream);
 
 /* Same two calls with HOST buffers: inputs are staged through plan-owned pinned and device
  * buffers, the kernel runs on `stream`, the result is copied back and the call returns once it

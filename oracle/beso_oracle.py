@@ -275,6 +275,31 @@ def sample_euler(sd, cfg, state, action, goal, sigmas, cond_lambda=None,
     return action
 
 
+# gc_sampling.py:108-114
+def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+# gc_sampling.py:216-256
+def sample_euler_ancestral(sd, cfg, state, action, goal, sigmas, cond_lambda=None, eta=1.0, noise=None):
+    """``noise``: optional (n_steps, B, t, act) draws to use instead of torch.randn_like (same order)."""
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        d = to_d(action, sigmas[i], denoised)
+        dt = sigma_down - sigmas[i]
+        action = action + d * dt
+        if sigma_down > 0:
+            action = action + (noise[i] if noise is not None else torch.randn_like(action)) * sigma_up
+    return action
+
+
 # gc_sampling.py:259-314
 def sample_heun(sd, cfg, state, action, goal, sigmas, cond_lambda=None,
                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, eps_list=None):

@@ -128,6 +128,41 @@ def gen_samplers(ns):
     save("samplers_K256", cfg, seed, sd, **arrays)
 
 
+def gen_ancestral(ns):
+    """sample_euler_ancestral of the real reference under a fixed generator state, plus the randn_like draws
+    it consumed (re-drawn from the same state: the model itself uses no RNG in eval mode)."""
+    gs = ns.gc_sampling
+    cfg, seed, B = K256, 1, 4
+    m, sd = build(ns, cfg, seed)
+    x = synthetic_inputs(cfg, B, seed=201)
+    x_t = x["noise"] * 1.0
+    arrays = dict(state=x["state"], goal=x["goal"], x_t=x_t)
+    for n in (1, 3, 5):
+        sig = gs.get_sigmas_exponential(n, 0.005, 1.0)
+        arrays[f"sigmas_{n}"] = sig
+        torch.manual_seed(7000 + n)
+        arrays[f"euler_ancestral_{n}"] = gs.sample_euler_ancestral(m, x["state"], x_t, x["goal"], sig, disable=True)
+        torch.manual_seed(7000 + n)
+        noise = torch.zeros((n,) + tuple(x_t.shape))
+        for i in range(n):
+            down, _ = gs.get_ancestral_step(sig[i], sig[i + 1])
+            if down > 0:
+                noise[i] = torch.randn_like(x_t)
+        arrays[f"noise_{n}"] = noise
+    sigk = gs.get_sigmas_karras(4, 0.005, 1.0, 5.0)
+    arrays["sigmas_karras_4"] = sigk
+    torch.manual_seed(7104)
+    arrays["euler_ancestral_karras_4"] = gs.sample_euler_ancestral(m, x["state"], x_t, x["goal"], sigk, disable=True)
+    torch.manual_seed(7104)
+    noise = torch.zeros((4,) + tuple(x_t.shape))
+    for i in range(4):
+        down, _ = gs.get_ancestral_step(sigk[i], sigk[i + 1])
+        if down > 0:
+            noise[i] = torch.randn_like(x_t)
+    arrays["noise_karras_4"] = noise
+    save("samplers_ancestral_K256", cfg, seed, sd, **arrays)
+
+
 def gen_schedules(ns):
     gs = ns.gc_sampling
     arrays = {}
@@ -174,6 +209,10 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ns = ref_import.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "ancestral":       # only the fixture added after the first set
+        gen_ancestral(ns)
+        return
+    gen_ancestral(ns)
     gen_schedules(ns)
     gen_forward(ns)
     gen_samplers(ns)

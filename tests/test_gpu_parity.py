@@ -86,6 +86,44 @@ def test_samplers_match_reference_golden(mode, cuda_device):
 
 
 @pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
+    """sample_euler_ancestral (gc_sampling.py:216-256, the kitchen evaluation default) as one persistent launch,
+    fed the randn_like draws the reference consumed (tests/golden/samplers_ancestral_K256.npz)."""
+    if mode == "fast" and not fast_available():
+        pytest.skip("fast mode not built")
+    cfg, meta, a = load_golden("samplers_ancestral_K256")
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=golden_weights(cfg, meta))
+    g = cuda(a, cuda_device)
+    m.refresh_weights()
+    for tag in ("1", "3", "5", "karras_4"):
+        launches = _lib.lib().beso_kernel_launches()
+        got = sampling.sample_euler_ancestral(m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{tag}"], noise=g[f"noise_{tag}"])
+        assert _lib.lib().beso_kernel_launches() == launches + 1
+        torch.testing.assert_close(got.cpu(), a[f"euler_ancestral_{tag}"], **TOL[mode])
+    # without explicit noise the draws come from the device generator, one per step with sigma_down > 0
+    torch.manual_seed(5)
+    r1 = sampling.sample_euler_ancestral(m, g["state"], g["x_t"], g["goal"], a["sigmas_5"])
+    torch.manual_seed(5)
+    draws = torch.stack([torch.randn_like(g["x_t"]) for _ in range(4)] + [torch.zeros_like(g["x_t"])])
+    r2 = sampling.sample_euler_ancestral(m, g["state"], g["x_t"], g["goal"], a["sigmas_5"], noise=draws)
+    assert torch.equal(r1, r2)
+    # step by step (callback) == fused
+    seen = []
+    r3 = sampling.sample_euler_ancestral(m, g["state"], g["x_t"], g["goal"], g["sigmas_5"], noise=draws,
+                                         callback=lambda d: seen.append(int(d["i"])))
+    assert seen == [0, 1, 2, 3, 4]
+    torch.testing.assert_close(r3, r2, rtol=1e-4, atol=1e-5)
+    # classifier-free guidance wrapper goes through the same launch
+    from oracle import beso_oracle as O
+    w = ClassifierFreeSampleModel(m, cond_lambda=2.0)
+    got = sampling.sample_euler_ancestral(w, g["state"], g["x_t"], g["goal"], a["sigmas_3"], noise=g["noise_3"])
+    with torch.no_grad():
+        want = O.sample_euler_ancestral(O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg), a["state"], a["x_t"],
+                                        a["goal"], a["sigmas_3"], cond_lambda=2.0, noise=a["noise_3"])
+    torch.testing.assert_close(got.cpu(), want, **TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
 def test_classifier_free_guidance_matches_reference_golden(mode, cuda_device):
     if mode == "fast" and not fast_available():
         pytest.skip("fast mode not built")

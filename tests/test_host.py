@@ -154,3 +154,26 @@ def test_agent_dispatch_and_errors():
         agent.sample_loop(torch.ones(3), torch.zeros(1, 10, 9), torch.zeros(1, 10, 60), torch.zeros(1, 2, 60),
                           "ddim", {"s_churn": 1})
     assert torch.equal(agent.get_noise_schedule(3, "exponential"), sampling.get_sigmas_exponential(3, 0.005, 1.0))
+
+
+def test_ancestral_coefficients_follow_the_reference_formula():
+    """(sigma_down, sigma_up) per step = get_ancestral_step (gc_sampling.py:108-114) in fp32 tensor ops."""
+    sig = sampling.get_sigmas_exponential(5, 0.005, 1.0)
+    coef = sampling.ancestral_coefficients(sig)
+    assert coef.shape == (5, 2) and coef.dtype == torch.float32
+    for i in range(5):
+        s_from, s_to = sig[i], sig[i + 1]
+        up = min(s_to, (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5)
+        down = (s_to ** 2 - up ** 2) ** 0.5
+        assert float(coef[i, 0]) == float(down) and float(coef[i, 1]) == float(up)
+    assert float(coef[-1, 0]) == 0.0 and float(coef[-1, 1]) == 0.0      # last step: onto sigma = 0, no noise
+    assert "euler_ancestral" in sampling.SAMPLERS and _lib.SAMPLER_IDS["euler_ancestral"] == 3
+
+
+def test_euler_ancestral_refuses_cpu_models_like_every_other_sampler():
+    m = build_denoiser(K256, "cpu")
+    x = torch.zeros(2, K256.window, K256.act_dim)
+    s = torch.zeros(2, K256.window, K256.obs_dim)
+    g = torch.zeros(2, K256.goal_len, K256.obs_dim)
+    with pytest.raises(_lib.BesoLibraryError):
+        sampling.sample_euler_ancestral(m, s, x, g, sampling.get_sigmas_exponential(3, 0.005, 1.0))

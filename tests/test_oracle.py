@@ -63,6 +63,24 @@ def test_samplers_match_golden():
             torch.testing.assert_close(got, a[f"cfg_ddim4_{tag}"], **TOL)
 
 
+def test_euler_ancestral_matches_golden():
+    """The reference's sample_euler_ancestral under a fixed generator state (oracle/make_golden.py ancestral):
+    the oracle reproduces it both from the recorded draws and by re-seeding the generator."""
+    cfg, meta, a = load_golden("samplers_ancestral_K256")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    with torch.no_grad():
+        for n in (1, 3, 5):
+            got = O.sample_euler_ancestral(sd, oc, a["state"], a["x_t"], a["goal"], a[f"sigmas_{n}"], noise=a[f"noise_{n}"])
+            torch.testing.assert_close(got, a[f"euler_ancestral_{n}"], **TOL)
+            torch.manual_seed(7000 + n)
+            got = O.sample_euler_ancestral(sd, oc, a["state"], a["x_t"], a["goal"], a[f"sigmas_{n}"])
+            torch.testing.assert_close(got, a[f"euler_ancestral_{n}"], **TOL)
+        got = O.sample_euler_ancestral(sd, oc, a["state"], a["x_t"], a["goal"], a["sigmas_karras_4"], noise=a["noise_karras_4"])
+        torch.testing.assert_close(got, a["euler_ancestral_karras_4"], **TOL)
+    # the step onto sigma = 0 draws no noise and lands on the denoised sample
+    assert float(a["noise_3"][-1].abs().max()) == 0.0
+
+
 def test_ddim_last_step_returns_denoised():
     """sigma_{n}=0 -> h=+inf -> x <- denoised exactly (gc_sampling.py:921-923)."""
     cfg, meta, a = load_golden("samplers_K256")
