@@ -376,7 +376,8 @@ __device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float* tra
   fence_async_smem();
   tc_fence_before();
   c.arrive(B_A_READY);
-  compute_sync();          // stats buffer may be rewritten by the next pass only after everyone read it
+  // no trailing barrier: every path to the next LayerNorm pass (which rewrites the stats buffer) goes through
+  // another barrier of all compute warps (attention syncs, the end-of-MLP sync, the epilogue syncs)
 }
 
 // Accumulator of head h (Q|K at S0, V at S1[0:64)) -> fp16 Q|K|V staging rows.  Only Q gets its bias here: the
@@ -411,114 +412,115 @@ __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
   emit(v0, dst0); emit(v1, dst0 + 64); emit(v2, dst0 + 128);
 }
 
-// Causal softmax(Q K^T) V for every sequence of the tile, one warp per sequence, mma.sync fp16.
-// Q is pre-scaled by 1/sqrt(hs) (folded into the packed weights).  Output -> Y atom (SW128 A layout).
-__device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
+// Causal softmax(Q K^T) V for every sequence of the tile, one warp per (sequence, 16-query tile), mma.sync fp16.
+// Q is pre-scaled by log2(e) / sqrt(hs) (folded into the packed weights).  Output -> Y atom (SW128 A layout).
+// NKT = number of 16-key steps this query tile sees (causal: later key tiles are fully masked); compile-time so
+// that a 16-token sequence does not pay for the masked second key step.
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+template <int NKT>
+__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T) {
   const uint32_t qkv = sbase + kSmQkv;
+  // ---- S = Q K^T ----
+  float sc[NKT][2][4];
+#pragma unroll
+  for (int a = 0; a < NKT; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) sc[a][b][0] = sc[a][b][1] = sc[a][b][2] = sc[a][b][3] = 0.f;
+  uint32_t qa[4][4];
+  {
+    const int r = min(row0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ldmatrix_x4(qkv + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, qa[k]);
+  }
+#pragma unroll
+  for (int kt = 0; kt < NKT; ++kt) {
+    const int r = min(row0 + kt * 16 + (lane & 7) + (lane >> 4) * 8, kRows - 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t kb[4];
+      ldmatrix_x4(qkv + r * kQkvStride + (64 + k * 16 + ((lane >> 3) & 1) * 8) * 2, kb);
+      mma_16816(sc[kt][0], qa[k], kb[0], kb[1]);
+      mma_16816(sc[kt][1], qa[k], kb[2], kb[3]);
+    }
+  }
+  // ---- mask + softmax (rows i0 = lane/4 and i0 + 8 of this query tile) ----
+  const int i_lo = mt * 16 + (lane >> 2), i_hi = i_lo + 8;
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int kt = 0; kt < NKT; ++kt)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = kt * 16 + nb * 8 + (lane & 3) * 2 + e;
+        if (j > i_lo) sc[kt][nb][e] = -INFINITY;
+        if (j > i_hi) sc[kt][nb][2 + e] = -INFINITY;
+        mx_lo = fmaxf(mx_lo, sc[kt][nb][e]);
+        mx_hi = fmaxf(mx_hi, sc[kt][nb][2 + e]);
+      }
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  // the scores are in log2 units: p = 2^(s - max), normalised before the P V product so that the output needs
+  // no scaling
+  float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NKT; ++kt)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[kt][nb][e] = ex2f(sc[kt][nb][e] - mx_lo);
+        sc[kt][nb][2 + e] = ex2f(sc[kt][nb][2 + e] - mx_hi);
+        sum_lo += sc[kt][nb][e]; sum_hi += sc[kt][nb][2 + e];
+      }
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+  const float inv_lo = __frcp_rn(sum_lo), inv_hi = __frcp_rn(sum_hi);
+  uint32_t pa[NKT][4];                           // P as A fragments, one per 16-key step
+#pragma unroll
+  for (int kt = 0; kt < NKT; ++kt) {
+    pa[kt][0] = pack_f16x2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo);   // (row lo, keys 0-7)
+    pa[kt][1] = pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi);   // (row hi, keys 0-7)
+    pa[kt][2] = pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo);   // (row lo, keys 8-15)
+    pa[kt][3] = pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi);   // (row hi, keys 8-15)
+  }
+  // ---- O = P V ----
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NKT; ++kt) {
+    const int r = min(row0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {             // pairs of 8-wide output column tiles
+      uint32_t vb[4];
+      ldmatrix_x4_trans(qkv + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
+      mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);
+      mma_16816(o[np * 2 + 1], pa[kt], vb[2], vb[3]);
+    }
+  }
+  // column e = n * 8 + (lane & 3) * 2 of the head: 16-byte chunk n of the row, bytes (lane & 3) * 4 within it
+  const uint32_t r_lo = (uint32_t)(row0 + i_lo), r_hi = (uint32_t)(row0 + i_hi);
+  const uint32_t y_lo = sbase + kSmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
+  const uint32_t y_hi = sbase + kSmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
+  if (i_lo < T) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) sts32(y_lo + (((uint32_t)n << 4) ^ x_lo), pack_f16x2(o[n][0], o[n][1]));
+  }
+  if (i_hi < T) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) sts32(y_hi + (((uint32_t)n << 4) ^ x_hi), pack_f16x2(o[n][2], o[n][3]));
+  }
+}
+__device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
+  (void)sm;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
   for (int item = awarp; item < S * MT; item += kAttnWarps) {
     const int mt = MT - 1 - item / S, s = item % S;   // later query tiles see more keys: schedule them first
-    const int row0 = s * T;
-    {
-      // ---- S = Q K^T over keys [0, 16*(mt+1)) (causal: later key tiles are fully masked) ----
-      const int nkt = mt + 1;                    // 16-key steps needed
-      float sc[2][2][4];                         // [key16][n8][frag]
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) sc[a][b][0] = sc[a][b][1] = sc[a][b][2] = sc[a][b][3] = 0.f;
-      uint32_t qa[4][4];
-      {
-        const int r = min(row0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ldmatrix_x4(qkv + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, qa[k]);
-      }
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt) {
-        if (kt < nkt) {
-          const int r = min(row0 + kt * 16 + (lane & 7) + (lane >> 4) * 8, kRows - 1);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t kb[4];
-            ldmatrix_x4(qkv + r * kQkvStride + (64 + k * 16 + ((lane >> 3) & 1) * 8) * 2, kb);
-            mma_16816(sc[kt][0], qa[k], kb[0], kb[1]);
-            mma_16816(sc[kt][1], qa[k], kb[2], kb[3]);
-          }
-        }
-      }
-      // ---- mask + softmax (rows i0 = lane/4 and i0 + 8 of this query tile) ----
-      const int i_lo = mt * 16 + (lane >> 2), i_hi = i_lo + 8;
-      float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = kt * 16 + nb * 8 + (lane & 3) * 2 + e;
-            const bool on = kt < nkt;
-            if (!(on && j <= i_lo)) sc[kt][nb][e] = -INFINITY;
-            if (!(on && j <= i_hi)) sc[kt][nb][2 + e] = -INFINITY;
-            mx_lo = fmaxf(mx_lo, sc[kt][nb][e]);
-            mx_hi = fmaxf(mx_hi, sc[kt][nb][2 + e]);
-          }
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-      // the scores are in log2 units (log2(e) / sqrt(hs) is folded into W_q): p = 2^(s - max), normalised
-      // before the P V product so that the output needs no scaling
-      float sum_lo = 0.f, sum_hi = 0.f;
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            sc[kt][nb][e] = ex2f(sc[kt][nb][e] - mx_lo);
-            sc[kt][nb][2 + e] = ex2f(sc[kt][nb][2 + e] - mx_hi);
-            sum_lo += sc[kt][nb][e]; sum_hi += sc[kt][nb][2 + e];
-          }
-      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
-      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-      const float inv_lo = __frcp_rn(sum_lo), inv_hi = __frcp_rn(sum_hi);
-      uint32_t pa[2][4];                         // P as A fragments, one per 16-key step
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt) {
-        pa[kt][0] = pack_f16x2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo);   // (row lo, keys 0-7)
-        pa[kt][1] = pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi);   // (row hi, keys 0-7)
-        pa[kt][2] = pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo);   // (row lo, keys 8-15)
-        pa[kt][3] = pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi);   // (row hi, keys 8-15)
-      }
-      // ---- O = P V ----
-      float o[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt) {
-        if (kt < nkt) {
-          const int r = min(row0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
-#pragma unroll
-          for (int np = 0; np < 4; ++np) {       // pairs of 8-wide output column tiles
-            uint32_t vb[4];
-            ldmatrix_x4_trans(qkv + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
-            mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);
-            mma_16816(o[np * 2 + 1], pa[kt], vb[2], vb[3]);
-          }
-        }
-      }
-      uint8_t* y = sm + kSmY;
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int e = n * 8 + (lane & 3) * 2;    // column within the head
-        if (i_lo < T) {
-          const uint32_t r = row0 + i_lo;
-          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][0], o[n][1]);
-        }
-        if (i_hi < T) {
-          const uint32_t r = row0 + i_hi;
-          *reinterpret_cast<uint32_t*>(y + sw128_offset(r, e >> 3) + (e & 7) * 2) = pack_f16x2(o[n][2], o[n][3]);
-        }
-      }
-    }
+    if (mt == 0) attention_item<1>(sbase, lane, s * T, 0, T);
+    else attention_item<2>(sbase, lane, s * T, mt, T);
   }
 }
 
