@@ -154,112 +154,261 @@ __global__ void bias_add_kernel(float* __restrict__ C, const float* __restrict__
   const size_t r = idx / N; const int c = (int)(idx % N);
   C[r * ldc + c] += bias[c];
 }
-__global__ void colsum_kernel(const float* __restrict__ A, int M, int N, int lda, float* __restrict__ out) {
-  __shared__ float s[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x, wy = threadIdx.y;
-  float a = 0.f;
-  if (c < N) for (int r = wy; r < M; r += 8) a += A[(size_t)r * lda + c];
-  s[wy][threadIdx.x] = a;
+// dst = src + bias (row broadcast), N % 4 == 0: the residual stream copy and the bias of the following
+// beta = 1 GEMM in one pass
+__global__ void copy_add_bias_kernel(float* __restrict__ dst, const float* __restrict__ src, const float* __restrict__ bias,
+                                     size_t n4, int N) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(src)[i];
+  const float4 b = *reinterpret_cast<const float4*>(bias + (int)((i * 4) % N));
+  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  reinterpret_cast<float4*>(dst)[i] = v;
+}
+// Column sums (bias gradients) in two deterministic stages: partial[rb][c] over row block rb, then the sum over rb.
+// Stage 1: block = 32 columns x 8 row lanes, grid = (N / 32, kColsumRowBlocks): each warp reads 128 contiguous
+// bytes of a row, four rows in flight per thread, ~1200 blocks keep every SM busy (HBM-bound pass over A).
+constexpr int kColsumRowBlocks = 148;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ A, int M, int N, int lda,
+                                                             float* __restrict__ partial) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  const int stride = kColsumRowBlocks * 8;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < N) {
+    int r = blockIdx.y * 8 + ty;
+    for (; r + 3 * stride < M; r += 4 * stride) {
+      a0 += A[(size_t)r * lda + c];
+      a1 += A[(size_t)(r + stride) * lda + c];
+      a2 += A[(size_t)(r + 2 * stride) * lda + c];
+      a3 += A[(size_t)(r + 3 * stride) * lda + c];
+    }
+    for (; r < M; r += stride) a0 += A[(size_t)r * lda + c];
+  }
+  sh[ty][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
-  if (wy == 0 && c < N) { for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x]; out[c] = a; }
+  if (ty == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    partial[(size_t)blockIdx.y * N + c] = t;
+  }
+}
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int N, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float a = 0.f;
+  for (int rb = 0; rb < kColsumRowBlocks; ++rb) a += partial[(size_t)rb * N + c];
+  out[c] = a;
 }
 
 // ---- erf-GELU -----------------------------------------------------------------------------------------------
-__global__ void gelu_fwd_kernel(const float* __restrict__ U, float* __restrict__ G, size_t n) {
+// U += bias (kept for the backward pass), G = gelu(U): one pass over the 4d-wide hidden activations
+__global__ void bias_gelu_fwd_kernel(float* __restrict__ U, const float* __restrict__ bias, float* __restrict__ G, size_t n4, int N) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) { const float x = U[i]; G[i] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+  if (i >= n4) return;
+  float4 u = reinterpret_cast<float4*>(U)[i];
+  const float4 b = *reinterpret_cast<const float4*>(bias + (int)((i * 4) % N));
+  u.x += b.x; u.y += b.y; u.z += b.z; u.w += b.w;
+  reinterpret_cast<float4*>(U)[i] = u;
+  float4 g;
+  g.x = 0.5f * u.x * (1.0f + erff(u.x * 0.70710678118654752440f));
+  g.y = 0.5f * u.y * (1.0f + erff(u.y * 0.70710678118654752440f));
+  g.z = 0.5f * u.z * (1.0f + erff(u.z * 0.70710678118654752440f));
+  g.w = 0.5f * u.w * (1.0f + erff(u.w * 0.70710678118654752440f));
+  reinterpret_cast<float4*>(G)[i] = g;
 }
-__global__ void gelu_bwd_kernel(const float* __restrict__ U, float* __restrict__ dG, size_t n) {   // in place: dU
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ U, float* __restrict__ dG, size_t n4) {   // in place: dU
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) {
-    const float x = U[i];
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
-    dG[i] *= cdf + x * pdf;
-  }
+  if (i >= n4) return;
+  const float4 u = reinterpret_cast<const float4*>(U)[i];
+  float4 g = reinterpret_cast<float4*>(dG)[i];
+  g.x *= gelu_grad(u.x); g.y *= gelu_grad(u.y); g.z *= gelu_grad(u.z); g.w *= gelu_grad(u.w);
+  reinterpret_cast<float4*>(dG)[i] = g;
 }
 
-// ---- causal attention, one warp per (sequence, head, query row) ------------------------------------------------
-// QKV [M][3d] (q | k | v); P [B][H][T][T] saved; Y [M][d]
-__global__ void attn_fwd_kernel(Dims D, const float* __restrict__ QKV, float* __restrict__ P, float* __restrict__ Y) {
-  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (item >= D.B * D.H * D.T) return;
-  const int i = item % D.T, h = (item / D.T) % D.H, b = item / (D.T * D.H);
-  const int ld = 3 * D.d;
-  const float* q = QKV + ((size_t)b * D.T + i) * ld + h * D.hs;
-  const float scale = 1.0f / sqrtf((float)D.hs);
-  float sc[2];
-  for (int u = 0; u < 2; ++u) {
-    const int j = lane + 32 * u;
-    float a = -INFINITY;
-    if (j <= i) {
-      const float* k = QKV + ((size_t)b * D.T + j) * ld + D.d + h * D.hs;
-      a = 0.f;
-      for (int e = 0; e < D.hs; ++e) a = fmaf(q[e], k[e], a);
-      a *= scale;
-    }
-    sc[u] = a;
-  }
-  float mx = fmaxf(sc[0], sc[1]);
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float p0 = (lane <= i) ? expf(sc[0] - mx) : 0.f, p1 = (lane + 32 <= i) ? expf(sc[1] - mx) : 0.f;
-  const float inv = 1.0f / wsum(p0 + p1);
-  p0 *= inv; p1 *= inv;
-  float* prow = P + (((size_t)b * D.H + h) * D.T + i) * D.T;
-  if (lane < D.T) prow[lane] = p0;
-  if (lane + 32 < D.T) prow[lane + 32] = p1;
-  for (int e0 = 0; e0 < D.hs; e0 += 32) {
-    const int e = e0 + lane;
-    float y = 0.f;
-    for (int j = 0; j <= i; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
-      if (e < D.hs) y = fmaf(pj, QKV[((size_t)b * D.T + j) * ld + 2 * D.d + h * D.hs + e], y);
-    }
-    if (e < D.hs) Y[((size_t)b * D.T + i) * D.d + h * D.hs + e] = y;
+// ---- causal attention, one CTA per (sequence, head) -------------------------------------------------------------
+// QKV [M][3d] (q | k | v); P [B][H][T][T] saved; Y [M][d].  T <= 64, head size <= 64.  Q, K, V of the head are
+// staged in shared memory with coalesced loads (the three Linear biases are added on the way in and the biased
+// values written back for the backward pass), then T x T scores, the row softmax and P V are small dot products
+// out of shared memory.  HBM-bound: every activation byte is read once and written once.
+constexpr int kAttnThreads = 128;
+__host__ __device__ inline int attn_lds(int hs) { return ((hs + 3) & ~3) + 4; }   // row pitch: 16-byte rows, conflict-free float4 reads
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
+}
+// out[i0..i0+1][j0..j0+1] (+)= A rows i0, i0+1 . B rows j0, j0+1 over hs4 float4 columns (2 x 2 register tile)
+__device__ __forceinline__ void tile2x2(const float* A, const float* Bm, int lds, int hs4, int i0, int j0, int T, float (&o)[2][2]) {
+  const int i1 = min(i0 + 1, T - 1), j1 = min(j0 + 1, T - 1);
+  const float4* a0 = reinterpret_cast<const float4*>(A + i0 * lds);
+  const float4* a1 = reinterpret_cast<const float4*>(A + i1 * lds);
+  const float4* b0 = reinterpret_cast<const float4*>(Bm + j0 * lds);
+  const float4* b1 = reinterpret_cast<const float4*>(Bm + j1 * lds);
+  for (int e = 0; e < hs4; ++e) {
+    const float4 x0 = a0[e], x1 = a1[e], y0 = b0[e], y1 = b1[e];
+    o[0][0] = dot4(x0, y0, o[0][0]); o[0][1] = dot4(x0, y1, o[0][1]);
+    o[1][0] = dot4(x1, y0, o[1][0]); o[1][1] = dot4(x1, y1, o[1][1]);
   }
 }
-// One block per (sequence, head): dS in shared memory, then dQ, dK, dV.   dQKV [M][3d]
-__global__ void attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__ P,
-                                const float* __restrict__ dY, float* __restrict__ dQKV) {
-  extern __shared__ float sh[];
-  const int T = D.T, hs = D.hs, ld = 3 * D.d;
-  float* dS = sh;                                       // [T][T]
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(Dims D, float* __restrict__ QKV, const float* __restrict__ bq, const float* __restrict__ bk,
+                const float* __restrict__ bv, float* __restrict__ P, float* __restrict__ Y) {
+  extern __shared__ __align__(16) float sh[];
+  const int T = D.T, hs = D.hs, ld = 3 * D.d, lds = attn_lds(hs), hs4 = (hs + 3) >> 2, ldt = T + 1;
+  float* q = sh;                       // [T][lds], columns hs .. lds-1 zero
+  float* k = q + T * lds;
+  float* v = k + T * lds;
+  float* sc = v + T * lds;             // [T][T + 1]
   const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
-  const float* Pm = P + ((size_t)b * D.H + h) * T * T;
-  const float scale = 1.0f / sqrtf((float)hs);
   const size_t row0 = (size_t)b * T;
-  // dP[i][j] = dY_i . V_j ;  dS = P * (dP - sum_j dP * P)
-  for (int idx = threadIdx.x; idx < T * T; idx += blockDim.x) {
-    const int i = idx / T, j = idx % T;
-    float a = 0.f;
-    if (j <= i) {
-      const float* dy = dY + (row0 + i) * D.d + h * hs;
-      const float* v = QKV + (row0 + j) * ld + 2 * D.d + h * hs;
-      for (int e = 0; e < hs; ++e) a = fmaf(dy[e], v[e], a);
+  // hs % 4 == 0 (checked on the host): 16-byte loads, all of a thread's loads issued before its stores (the
+  // write-back aliases the source, so a load-store-load loop would serialise on the memory latency)
+  const int n4 = 3 * T * hs4;
+  for (int base = 0; base < n4; base += 4 * kAttnThreads) {
+    float4 val[4];
+    float4* g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * kAttnThreads + threadIdx.x;
+      g[u] = nullptr;
+      if (idx < n4) {
+        const int part = idx / (T * hs4), r = (idx / hs4) % T, e4 = idx % hs4;
+        g[u] = reinterpret_cast<float4*>(QKV + (row0 + r) * ld + part * D.d + h * hs) + e4;
+        val[u] = *g[u];
+        const float4 bb = reinterpret_cast<const float4*>((part == 0 ? bq : part == 1 ? bk : bv) + h * hs)[e4];
+        val[u].x += bb.x; val[u].y += bb.y; val[u].z += bb.z; val[u].w += bb.w;
+      }
     }
-    dS[idx] = a;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * kAttnThreads + threadIdx.x;
+      if (idx < n4) {
+        const int part = idx / (T * hs4), r = (idx / hs4) % T, e4 = idx % hs4;
+        *g[u] = val[u];
+        reinterpret_cast<float4*>((part == 0 ? q : part == 1 ? k : v) + r * lds)[e4] = val[u];
+      }
+    }
+  }
+  for (int r = threadIdx.x; r < 3 * T; r += kAttnThreads)      // zero the 4 pad columns of every row
+    *reinterpret_cast<float4*>(q + r * lds + hs4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)hs);
+  const int T2 = (T + 1) >> 1;
+  for (int idx = threadIdx.x; idx < T2 * T2; idx += kAttnThreads) {
+    const int i0 = (idx / T2) * 2, j0 = (idx % T2) * 2;
+    if (j0 > i0 + 1) continue;                          // fully masked tile
+    float o[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    tile2x2(q, k, lds, hs4, i0, j0, T, o);
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        const int i = i0 + di, j = j0 + dj;
+        if (i < T && j < T) sc[i * ldt + j] = (j <= i) ? o[di][dj] * scale : -INFINITY;
+      }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
-    float s = 0.f;
-    for (int j = 0; j <= i; ++j) s = fmaf(dS[i * T + j], Pm[i * T + j], s);
-    for (int j = 0; j < T; ++j) dS[i * T + j] = (j <= i) ? Pm[i * T + j] * (dS[i * T + j] - s) * scale : 0.f;
+  float* Pm = P + ((size_t)b * D.H + h) * T * T;
+  for (int i = threadIdx.x >> 5; i < T; i += kAttnThreads / 32) {        // one warp per row
+    const int lane = threadIdx.x & 31;
+    const float a0 = (lane < T && lane <= i) ? sc[i * ldt + lane] : -INFINITY;
+    const float a1 = (lane + 32 < T && lane + 32 <= i) ? sc[i * ldt + lane + 32] : -INFINITY;
+    float mx = fmaxf(a0, a1);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float p0 = (lane <= i) ? expf(a0 - mx) : 0.f, p1 = (lane + 32 <= i) ? expf(a1 - mx) : 0.f;
+    const float inv = 1.0f / wsum(p0 + p1);
+    p0 *= inv; p1 *= inv;
+    if (lane < T) { sc[i * ldt + lane] = p0; Pm[i * T + lane] = p0; }
+    if (lane + 32 < T) { sc[i * ldt + lane + 32] = p1; Pm[i * T + lane + 32] = p1; }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < T * hs; idx += blockDim.x) {
-    const int i = idx / hs, e = idx % hs;
-    float dq = 0.f, dk = 0.f, dv = 0.f;
-    for (int j = 0; j <= i; ++j) dq = fmaf(dS[i * T + j], QKV[(row0 + j) * ld + D.d + h * hs + e], dq);
-    for (int r = i; r < T; ++r) {
-      dk = fmaf(dS[r * T + i], QKV[(row0 + r) * ld + h * hs + e], dk);
-      dv = fmaf(Pm[r * T + i], dY[(row0 + r) * D.d + h * hs + e], dv);
+  for (int idx = threadIdx.x; idx < T * hs4; idx += kAttnThreads) {      // (row, 4 columns) per thread
+    const int i = idx / hs4, e4 = idx % hs4;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j <= i; ++j) {
+      const float pj = sc[i * ldt + j];
+      const float4 vv = reinterpret_cast<const float4*>(v + j * lds)[e4];
+      y.x = fmaf(pj, vv.x, y.x); y.y = fmaf(pj, vv.y, y.y); y.z = fmaf(pj, vv.z, y.z); y.w = fmaf(pj, vv.w, y.w);
     }
-    float* o = dQKV + (row0 + i) * ld + h * hs + e;
-    o[0] = dq; o[D.d] = dk; o[2 * D.d] = dv;
+    reinterpret_cast<float4*>(Y + (row0 + i) * D.d + h * hs)[e4] = y;
   }
 }
+inline size_t attn_fwd_smem(int T, int hs) { return ((size_t)3 * T * attn_lds(hs) + (size_t)T * (T + 1)) * sizeof(float); }
 
-// ---- head gather / scatter, loss ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAttnThreads)
+attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dY,
+                float* __restrict__ dQKV) {
+  extern __shared__ __align__(16) float sh[];
+  const int T = D.T, hs = D.hs, ld = 3 * D.d, lds = attn_lds(hs), hs4 = (hs + 3) >> 2, ldt = T + 1;
+  float* q = sh;                       // [T][lds]
+  float* k = q + T * lds;
+  float* v = k + T * lds;
+  float* dy = v + T * lds;
+  float* Pm = dy + T * lds;            // [T][T + 1]
+  float* dS = Pm + T * ldt;            // [T][T + 1]
+  const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
+  const size_t row0 = (size_t)b * T;
+  const float scale = 1.0f / sqrtf((float)hs);
+  for (int idx = threadIdx.x; idx < 4 * T * hs4; idx += kAttnThreads) {
+    const int part = idx / (T * hs4), r = (idx / hs4) % T, e4 = idx % hs4;
+    const float4 val = part < 3 ? reinterpret_cast<const float4*>(QKV + (row0 + r) * ld + part * D.d + h * hs)[e4]
+                                : reinterpret_cast<const float4*>(dY + (row0 + r) * D.d + h * hs)[e4];
+    reinterpret_cast<float4*>((part == 0 ? q : part == 1 ? k : part == 2 ? v : dy) + r * lds)[e4] = val;
+  }
+  for (int r = threadIdx.x; r < 4 * T; r += kAttnThreads)      // zero the 4 pad columns of every row
+    *reinterpret_cast<float4*>(q + r * lds + hs4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* Pg = P + ((size_t)b * D.H + h) * T * T;
+  for (int idx = threadIdx.x; idx < T * T; idx += kAttnThreads) Pm[(idx / T) * ldt + idx % T] = Pg[idx];
+  __syncthreads();
+  // dP[i][j] = dY_i . V_j ;  dS = P * (dP - sum_j dP * P) * scale
+  const int T2 = (T + 1) >> 1;
+  for (int idx = threadIdx.x; idx < T2 * T2; idx += kAttnThreads) {
+    const int i0 = (idx / T2) * 2, j0 = (idx % T2) * 2;
+    float o[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (j0 <= i0 + 1) tile2x2(dy, v, lds, hs4, i0, j0, T, o);
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        const int i = i0 + di, j = j0 + dj;
+        if (i < T && j < T) dS[i * ldt + j] = (j <= i) ? o[di][dj] : 0.f;
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += kAttnThreads) {
+    float sdp = 0.f;
+    for (int j = 0; j <= i; ++j) sdp = fmaf(dS[i * ldt + j], Pm[i * ldt + j], sdp);
+    for (int j = 0; j < T; ++j) dS[i * ldt + j] = (j <= i) ? Pm[i * ldt + j] * (dS[i * ldt + j] - sdp) * scale : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < T * hs4; idx += kAttnThreads) {      // (row, 4 columns) per thread
+    const int i = idx / hs4, e4 = idx % hs4;
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dk = dq, dv = dq;
+    for (int j = 0; j <= i; ++j) {
+      const float s_ = dS[i * ldt + j];
+      const float4 kk = reinterpret_cast<const float4*>(k + j * lds)[e4];
+      dq.x = fmaf(s_, kk.x, dq.x); dq.y = fmaf(s_, kk.y, dq.y); dq.z = fmaf(s_, kk.z, dq.z); dq.w = fmaf(s_, kk.w, dq.w);
+    }
+    for (int r = i; r < T; ++r) {
+      const float s_ = dS[r * ldt + i], p_ = Pm[r * ldt + i];
+      const float4 qq = reinterpret_cast<const float4*>(q + r * lds)[e4];
+      const float4 dd = reinterpret_cast<const float4*>(dy + r * lds)[e4];
+      dk.x = fmaf(s_, qq.x, dk.x); dk.y = fmaf(s_, qq.y, dk.y); dk.z = fmaf(s_, qq.z, dk.z); dk.w = fmaf(s_, qq.w, dk.w);
+      dv.x = fmaf(p_, dd.x, dv.x); dv.y = fmaf(p_, dd.y, dv.y); dv.z = fmaf(p_, dd.z, dv.z); dv.w = fmaf(p_, dd.w, dv.w);
+    }
+    float* o = dQKV + (row0 + i) * ld + h * hs;
+    reinterpret_cast<float4*>(o)[e4] = dq;
+    reinterpret_cast<float4*>(o + D.d)[e4] = dk;
+    reinterpret_cast<float4*>(o + 2 * D.d)[e4] = dv;
+  }
+}
+inline size_t attn_bwd_smem(int T, int hs) { return ((size_t)4 * T * attn_lds(hs) + (size_t)2 * T * (T + 1)) * sizeof(float); }
+
 __global__ void gather_action_rows_kernel(Dims D, const float* __restrict__ X, float* __restrict__ HA) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= (size_t)D.B * D.t * D.d) return;
@@ -315,18 +464,26 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, fl
 
 // ---- embedding backward --------------------------------------------------------------------------------------------
 // dpos[p][c] = sum over b of dX rows at position p (goal token p < G; state and action token of step p - G)
-__global__ void pos_grad_kernel(Dims D, const float* __restrict__ dX, int n_pos, float* __restrict__ dpos) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_pos * D.d) return;
-  const int c = idx % D.d, p = idx / D.d;
+// d pos_emb[p][c] = sum over sequences of the rows that use position p (one goal row, or a state and an action
+// row): partial sums over kPosChunks sequence chunks, then colsum_reduce-style reduction (deterministic).
+constexpr int kPosChunks = 64;
+__global__ void pos_grad_partial_kernel(Dims D, const float* __restrict__ dX, int n_pos, float* __restrict__ partial) {
+  const int c = threadIdx.x, p = blockIdx.x, chunk = blockIdx.y;      // blockDim.x == d
   float a = 0.f;
   if (p < D.G + D.t) {
-    for (int b = 0; b < D.B; ++b) {
+    for (int b = chunk; b < D.B; b += kPosChunks) {
       const size_t r0 = (size_t)b * D.T;
       if (p < D.G) a += dX[(r0 + 1 + p) * D.d + c];
       else { const int step = p - D.G; a += dX[(r0 + 1 + D.G + 2 * step) * D.d + c] + dX[(r0 + 2 + D.G + 2 * step) * D.d + c]; }
     }
   }
+  partial[((size_t)chunk * n_pos + p) * D.d + c] = a;
+}
+__global__ void pos_grad_reduce_kernel(const float* __restrict__ partial, int n, float* __restrict__ dpos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float a = 0.f;
+  for (int chunk = 0; chunk < kPosChunks; ++chunk) a += partial[(size_t)chunk * n + idx];
   dpos[idx] = a;
 }
 // gathers for the embedding weight gradients: rows of kind 0 = sigma token, 1 = state + goal tokens, 2 = action tokens
@@ -358,6 +515,8 @@ __global__ void gather_embed_rows_kernel(Dims D, int kind, const float* __restri
 }
 
 size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
+// scratch for the two-stage reductions: column sums (64 row blocks x up to 4096 columns), position gradients
+constexpr size_t kPartialFloats = (size_t)148 * 2048;
 
 }  // namespace
 
@@ -402,7 +561,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   const size_t per_layer = 5 * align4(Md) + align4(3 * Md) + align4(nP) + 2 * align4(MF) + 2 * align4(2 * (size_t)M);
   const size_t n_gather = (size_t)B * (D.G + D.t);
   const size_t total = (size_t)L * per_layer + 2 * align4(Md) + align4(2 * (size_t)M) + align4(nBt * d) + 3 * align4(nBt * D.act) +
-                       4 * align4(Md) + align4(MF) + align4(3 * Md) + align4((size_t)M) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + 1024 + 4096;
+                       4 * align4(Md) + align4(MF) + align4(3 * Md) + align4((size_t)M) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + kPartialFloats + 4096;
   int rc = ensure_ws(ws, total);
   if (rc) return rc;
   float* p = ws->buf;
@@ -417,7 +576,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   float *XL = take(Md), *HF = take(Md), *stf = take(2 * (size_t)M), *HA = take(nBt * d), *pred = take(nBt * D.act),
         *dpred = take(nBt * D.act), *xin = take(nBt * D.act);
   float *dX = take(Md), *dT = take(Md), *dH = take(Md), *dY = take(Md), *dBig = take(MF), *dQKV = take(3 * Md);
-  float *gRows = take(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))), *partial = take(1024);
+  float *gRows = take(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))), *partial = take(kPartialFloats);
   float* ones = take((size_t)M);
   cublasHandle_t h = ws->blas;
   BESO_CUBLAS(cublasSetStream(h, st));
@@ -444,6 +603,11 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
 #define GEMM(...) do { if ((rc = gemm_rm(h, __VA_ARGS__))) return rc; } while (0)
 
   // ============================== forward ==============================
+  if (attn_bwd_smem(D.T, D.hs) > 48 * 1024) {
+    BESO_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_fwd_smem(D.T, D.hs)));
+    BESO_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem(D.T, D.hs)));
+  }
+  if ((d & 3) || (F & 3) || (D.hs & 3)) { set_error("training path needs embed_dim % 4 == 0 and head size % 4 == 0"); return BESO_E_UNSUPPORTED; }
   LAUNCH(embed_fwd_kernel, blocks_for(Md), kTB, 0, D, state, action, goal, noise, sigma, goal_keep, pred_last, W(0), W(1), W(2),
          W(pt + 2), W(pt + 3), W(pt + 4), W(pt + 5), A[0].Xin, xin);
   const int ln_grid = (M + 7) / 8;
@@ -454,21 +618,16 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 6)), d, 0.f, a.QKV, 3 * d);
     GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 4)), d, 0.f, a.QKV + d, 3 * d);
     GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 8)), d, 0.f, a.QKV + 2 * d, 3 * d);
-    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.QKV, W(lp(l, 7)), (size_t)M, d, 3 * d);
-    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.QKV + d, W(lp(l, 5)), (size_t)M, d, 3 * d);
-    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.QKV + 2 * d, W(lp(l, 9)), (size_t)M, d, 3 * d);
-    LAUNCH(attn_fwd_kernel, (B * D.H * D.T + 7) / 8, 256, 0, D, a.QKV, a.P, a.Y);
-    BESO_CUDA(cudaMemcpyAsync(a.Xmid, a.Xin, Md * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // q / k / v biases are added (and written back) by the attention kernel's tile load
+    LAUNCH(attn_fwd_kernel, B * D.H, kAttnThreads, attn_fwd_smem(D.T, D.hs), D, a.QKV, W(lp(l, 7)), W(lp(l, 5)), W(lp(l, 9)), a.P, a.Y);
+    LAUNCH(copy_add_bias_kernel, blocks_for(Md / 4), kTB, 0, a.Xmid, a.Xin, W(lp(l, 11)), Md / 4, d);   // X_mid = X_in + b_proj
     GEMM(false, true, M, d, d, 1.f, a.Y, d, W(lp(l, 10)), d, 1.f, a.Xmid, d);
-    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, a.Xmid, W(lp(l, 11)), (size_t)M, d, d);
     LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, a.Xmid, M, d, W(lp(l, 2)), W(lp(l, 3)), a.H2, a.st2);
     GEMM(false, true, M, F, d, 1.f, a.H2, d, W(lp(l, 12)), d, 0.f, a.U, F);
-    LAUNCH(bias_add_kernel, blocks_for(MF), kTB, 0, a.U, W(lp(l, 13)), (size_t)M, F, F);
-    LAUNCH(gelu_fwd_kernel, blocks_for(MF), kTB, 0, a.U, a.Gg, MF);
+    LAUNCH(bias_gelu_fwd_kernel, blocks_for(MF / 4), kTB, 0, a.U, W(lp(l, 13)), a.Gg, MF / 4, F);
     float* Xnext = (l + 1 < L) ? A[l + 1].Xin : XL;
-    BESO_CUDA(cudaMemcpyAsync(Xnext, a.Xmid, Md * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    LAUNCH(copy_add_bias_kernel, blocks_for(Md / 4), kTB, 0, Xnext, a.Xmid, W(lp(l, 15)), Md / 4, d);   // X_next = X_mid + b_2
     GEMM(false, true, M, d, F, 1.f, a.Gg, F, W(lp(l, 14)), F, 1.f, Xnext, d);
-    LAUNCH(bias_add_kernel, blocks_for(Md), kTB, 0, Xnext, W(lp(l, 15)), (size_t)M, d, d);
   }
   LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, XL, M, d, W(pt), W(pt + 1), HF, stf);
   LAUNCH(gather_action_rows_kernel, blocks_for(nBt * d), kTB, 0, D, HF, HA);
@@ -482,10 +641,11 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
 
   // ============================== backward ==============================
   // column sums (bias gradients) as A^T 1 with a library GEMV: bandwidth-bound, full-chip parallel
-  LAUNCH(fill_kernel, blocks_for((size_t)M), kTB, 0, ones, (size_t)M, 1.0f);
-  const float one = 1.f, zero = 0.f;
+  (void)ones;
   auto colsum = [&](const float* Am, int rows, int N, int lda, float* out) -> int {
-    BESO_CUBLAS(cublasSgemv(h, CUBLAS_OP_N, N, rows, &one, Am, lda, ones, 1, &zero, out, 1));
+    if ((size_t)N * kColsumRowBlocks > kPartialFloats) { set_error("internal: column-sum scratch too small"); return BESO_E_INVALID; }
+    LAUNCH(colsum_partial_kernel, dim3((N + 31) / 32, kColsumRowBlocks), dim3(32, 8), 0, Am, rows, N, lda, partial);
+    LAUNCH(colsum_reduce_kernel, (N + 127) / 128, 128, 0, partial, N, out);
     return BESO_OK;
   };
 #define COLSUM(...) do { if ((rc = colsum(__VA_ARGS__))) return rc; } while (0)
@@ -509,7 +669,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     GEMM(true, false, d, F, M, 1.f, dX, d, a.Gg, F, 0.f, Gp(lp(l, 14)), F);                       // dW2 = dX^T G
     COLSUM(dX, M, d, d, Gp(lp(l, 15)));
     GEMM(false, false, M, F, d, 1.f, dX, d, W(lp(l, 14)), F, 0.f, dBig, F);                        // dG = dX W2
-    LAUNCH(gelu_bwd_kernel, blocks_for(MF), kTB, 0, a.U, dBig, MF);                               // dU
+    LAUNCH(gelu_bwd_kernel, blocks_for(MF / 4), kTB, 0, a.U, dBig, MF / 4);                       // dU
     GEMM(true, false, F, d, M, 1.f, dBig, F, a.H2, d, 0.f, Gp(lp(l, 12)), d);                     // dW1 = dU^T H2
     COLSUM(dBig, M, F, F, Gp(lp(l, 13)));
     GEMM(false, false, M, d, F, 1.f, dBig, F, W(lp(l, 12)), d, 0.f, dH, d);                        // dH2 = dU W1
@@ -518,7 +678,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     GEMM(true, false, d, d, M, 1.f, dX, d, a.Y, d, 0.f, Gp(lp(l, 10)), d);                         // dWp
     COLSUM(dX, M, d, d, Gp(lp(l, 11)));
     GEMM(false, false, M, d, d, 1.f, dX, d, W(lp(l, 10)), d, 0.f, dY, d);                          // dY = dX Wp
-    LAUNCH(attn_bwd_kernel, B * D.H, 128, (size_t)D.T * D.T * sizeof(float), D, a.QKV, a.P, dY, dQKV);
+    LAUNCH(attn_bwd_kernel, B * D.H, kAttnThreads, attn_bwd_smem(D.T, D.hs), D, a.QKV, a.P, dY, dQKV);
     GEMM(true, false, d, d, M, 1.f, dQKV, 3 * d, a.H1, d, 0.f, Gp(lp(l, 6)), d);                   // dWq
     GEMM(true, false, d, d, M, 1.f, dQKV + d, 3 * d, a.H1, d, 0.f, Gp(lp(l, 4)), d);               // dWk
     GEMM(true, false, d, d, M, 1.f, dQKV + 2 * d, 3 * d, a.H1, d, 0.f, Gp(lp(l, 8)), d);           // dWv
@@ -532,7 +692,9 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   }
   // ---- embeddings ----
   const int n_pos = D.G + D.t + 1;
-  LAUNCH(pos_grad_kernel, blocks_for((size_t)n_pos * d), kTB, 0, D, dX, n_pos, Gp(0));
+  if ((size_t)kPosChunks * n_pos * d > kPartialFloats || d > 1024) { set_error("internal: position-gradient scratch too small"); return BESO_E_INVALID; }
+  LAUNCH(pos_grad_partial_kernel, dim3(n_pos, kPosChunks), d, 0, D, dX, n_pos, partial);
+  LAUNCH(pos_grad_reduce_kernel, blocks_for((size_t)n_pos * d), kTB, 0, partial, n_pos * d, Gp(0));
   struct Kind { int kind, per, kin, pw, pb; };
   const Kind kinds[3] = {{0, 1, 1, pt + 2, pt + 3}, {1, D.G + D.t, D.obs, 1, 2}, {2, D.t, D.act, pt + 4, pt + 5}};
   for (const Kind& k : kinds) {
