@@ -932,7 +932,11 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
 // M = 256 MMAs issued by the leader CTA; each CTA streams and holds only HALF of every B operand, which
 // halves the L2 -> SMEM weight traffic and the shared-memory bandwidth the tensor core needs for B.
 // DBG = true compiles in the diagnostics (per-phase clock stamps, LayerNorm trace dump); production is DBG = false.
-template <int CG, bool DBG>
+// MC = 2 (with CG = 1): the two CTAs of a cluster run independent tiles but share ONE weight stream: each
+// producer fetches half of every ring stage and multicasts it into both CTAs (TMA .multicast::cluster), a stage
+// is free again when both CTAs' MMAs have read it (multicast commits).  Halves the L2 -> SM request traffic,
+// which at full-chip scale is within a factor 1.5 of the L2 throughput cap.
+template <int CG, bool DBG, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
   extern __shared__ uint8_t smem_raw[];
@@ -941,13 +945,15 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   const uint32_t sbase = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kSmBars + B_COUNT * 8);
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  constexpr int PAIR = CG > MC ? CG : MC;                    // CTAs per cluster
+  const uint32_t rank = (PAIR == 2) ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       const bool by_warps = (i == B_A_READY || i == B_ACC_EMPTY0 || i == B_ACC_EMPTY1 || i == B_OP_READY0 || i == B_OP_READY1 ||
                              i == B_OP_READY0B || i == B_OP_READY1B);
-      mbar_init(sbase + kSmBars + i * 8, i == B_Y_READY ? kAttnWarps * CG : (by_warps ? 8 * CG : 1));
+      const bool ring_empty = i >= B_EMPTY0 && i < B_EMPTY0 + 4;
+      mbar_init(sbase + kSmBars + i * 8, i == B_Y_READY ? kAttnWarps * CG : (by_warps ? 8 * CG : (ring_empty ? MC : 1)));
     }
     fence_barrier_init();
   }
@@ -960,7 +966,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
                             q.w0 | (q.w1 << 4) | (q.c0 << 8) | (q.c1 << 12));
     });
   }
-  if (CG == 2) cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive
+  if (PAIR == 2) cluster_sync_all();        // barriers of both CTAs initialised before any remote arrive / multicast
   if (warp == kMmaWarp) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
   for (uint32_t i = threadIdx.x; i < (kSmVecA - kSmU) / 16; i += kThreads)      // padding rows must stay finite
     reinterpret_cast<uint4*>(sm + kSmU)[i] = make_uint4(0, 0, 0, 0);
@@ -969,8 +975,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // tiles are dealt to MMA groups (CTA or CTA pair) round-robin; the second CTA of a pair may get a dummy tile
-  const int n_groups = (int)gridDim.x / CG, group = (int)blockIdx.x / CG;
-  const int n_group_tiles = (p.n_tiles + CG - 1) / CG;
+  const int n_groups = (int)gridDim.x / PAIR, group = (int)blockIdx.x / PAIR;
+  const int n_group_tiles = (p.n_tiles + PAIR - 1) / PAIR;
   const int my_tiles = (n_group_tiles - group + n_groups - 1) / n_groups;
 
   const uint4* gtab = reinterpret_cast<const uint4*>(sm + kSmProg);
@@ -996,8 +1002,14 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         if (elect_one()) {
           mbar_expect_tx(full, bytes);
           const uint32_t h = bytes >> 1;                     // two requests in flight per group
-          bulk_g2s(dst, src, h, full);
-          bulk_g2s(dst + h, src + h, h, full);
+          if constexpr (MC == 2) {                           // this CTA's half, delivered to both CTAs
+            const uint32_t o = rank * h, q = h >> 1;
+            bulk_g2s_multicast(dst + o, src + o, q, full, 3);
+            bulk_g2s_multicast(dst + o + q, src + o + q, q, full, 3);
+          } else {
+            bulk_g2s(dst, src, h, full);
+            bulk_g2s(dst + h, src + h, h, full);
+          }
         }
         __syncwarp();
         g += 2;
@@ -1074,7 +1086,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             for (uint32_t j = 0; j < 4; ++j)
               mma_bf16(tm + d_col, desc(a_lo + kb * 1024u + 2u * j), desc(b_lo + kb * (B_STEP >> 4) + 2u * j), idesc,
                        (acc | kb | j) ? 1u : 0u);
-          mma_commit(bars + (B_EMPTY0 + slot) * 8);
+          if constexpr (MC == 2) mma_commit_multicast(bars + (B_EMPTY0 + slot) * 8, 3);
+          else mma_commit(bars + (B_EMPTY0 + slot) * 8);
         }
         __syncwarp();
         g += 2;
@@ -1222,7 +1235,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     if constexpr (DBG) { if (c.ctid == 0) *reinterpret_cast<long long**>(sm + kSmTlCursor) = nullptr; }
 
     for (int tj = 0; tj < my_tiles; ++tj) {
-      const int tile = (group + tj * n_groups) * CG + (int)rank;     // >= n_tiles: dummy tile, protocol only
+      const int tile = (group + tj * n_groups) * PAIR + (int)rank;   // >= n_tiles: dummy tile, protocol only
       tile_begin(c, p, tile);
       int step = 0, second = 0;
       for (int ev = 0; ev < p.evals; ++ev) {
@@ -1293,7 +1306,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (CG == 2) cluster_sync_all();          // the pair's MMAs read both CTAs' shared memory and TMEM
+  if (PAIR == 2) cluster_sync_all();        // the pair's MMAs / multicasts touch both CTAs' shared memory and TMEM
   if (warp == kMmaWarp) { if (CG == 2) tmem_dealloc_cg2(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
@@ -1653,9 +1666,10 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.timeline = g_timeline;
   static bool configured = false;
   if (!configured) {
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
     configured = true;
   }
   // Single-CTA MMAs (CG = 1) are the default: measured faster than CTA pairs on this workload (the pair mode
@@ -1663,7 +1677,11 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   // profiles/).  BESO_FAST_CG=2 selects the cta_group::2 path, kept parity-tested for the next round.
   static const int forced_cg = [] { const char* e = getenv("BESO_FAST_CG"); return e ? atoi(e) : 0; }();
   const int cg = (forced_cg == 2 && p.n_tiles >= 2) ? 2 : 1;
-  if (cg == 2) {
+  // BESO_FAST_MC=2: independent CTAs in clusters of 2 sharing the weight stream by TMA multicast
+  static const int forced_mc = [] { const char* e = getenv("BESO_FAST_MC"); return e ? atoi(e) : 0; }();
+  const bool dbg = p.trace != nullptr || p.timeline != nullptr;
+  const int mc = (cg == 1 && !dbg && forced_mc == 2 && p.n_tiles >= 2) ? 2 : 1;
+  if (cg == 2 || mc == 2) {
     const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
     cudaLaunchConfig_t cfgl{};
     cfgl.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
@@ -1674,11 +1692,12 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfgl.attrs = attr; cfgl.numAttrs = 1;
-    BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2, false>, p, sa));
+    if (cg == 2) BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2, false, 1>, p, sa));
+    else BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<1, false, 2>, p, sa));
   } else {
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    if (p.trace != nullptr || p.timeline != nullptr) fast_sample_kernel<1, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
-    else fast_sample_kernel<1, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    if (dbg) fast_sample_kernel<1, true, 1><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    else fast_sample_kernel<1, false, 1><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
   }
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());

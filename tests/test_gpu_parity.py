@@ -296,17 +296,19 @@ def test_error_paths(cuda_device):
 
 
 def test_cta_pair_mode_parity(cuda_device):
-    """The cta_group::2 variant of the FAST kernel (BESO_FAST_CG=2, read once per process) stays parity-tested."""
+    """The cluster variants of the FAST kernel (BESO_FAST_CG=2: cta_group::2 MMAs; BESO_FAST_MC=2: multicast weight
+    ring; both read once per process) stay parity-tested."""
     if not fast_available():
         pytest.skip("fast mode not built")
     import os
     import subprocess
     import sys
     from conftest import ROOT
-    env = dict(os.environ, BESO_FAST_CG="2")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_cg2.py")], env=env, capture_output=True,
-                       text=True, timeout=300)
-    assert r.returncode == 0 and "cg2 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for var in ("BESO_FAST_CG", "BESO_FAST_MC"):           # CTA-pair MMAs; multicast weight ring
+        env = dict(os.environ, **{var: "2"})
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_cg2.py")], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0 and "cg2 ok" in r.stdout, var + r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("mode", ["precise", "fast"])

@@ -1,4 +1,6 @@
-"""Parity of the CTA-pair (cta_group::2) FAST path against the PRECISE kernel; run with BESO_FAST_CG=2."""
+"""Parity of the cluster variants of the FAST path against the PRECISE kernel: run with BESO_FAST_CG=2
+(cta_group::2 MMAs over a CTA pair) or BESO_FAST_MC=2 (independent CTAs sharing the weight stream by TMA
+multicast); odd and even tile counts, so that a cluster with a dummy tile is covered."""
 import os
 import sys
 
@@ -10,9 +12,9 @@ from beso_b200.denoiser import build_denoiser                    # noqa: E402
 from beso_b200.sampling import get_sigmas_exponential, sample_heun  # noqa: E402
 from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
 
-assert os.environ.get("BESO_FAST_CG") == "2"
+assert os.environ.get("BESO_FAST_CG") == "2" or os.environ.get("BESO_FAST_MC") == "2"
 dev = torch.device("cuda:0")
-for cfg, B in ((K256, 37), (T16, 64)):
+for cfg, B in ((K256, 37), (T16, 64), (K256, 1500)):
     sd = synthetic_state_dict(cfg, 31)
     x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=32).items()}
     fast = build_denoiser(cfg, dev, mode="fast", state_dict=sd)
