@@ -87,6 +87,8 @@ class BesoAgent:
             return sampling.sample_euler(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "ddim":
             return sampling.sample_ddim(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "dpmpp_2m":                     # beso_agent.py:450-451
+            return sampling.sample_dpmpp_2m(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "euler_ancestral":              # beso_agent.py:431-432
             return sampling.sample_euler_ancestral(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         raise ValueError("desired sampler type not found!")

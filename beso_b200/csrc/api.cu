@@ -126,8 +126,11 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
 }
 
 static int make_sample_args(int sampler, const float* sig, int n_sigmas, const float* coef, SampleArgs* sa) {
-  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_EULER_ANCESTRAL) { set_error("unknown sampler"); return BESO_E_INVALID; }
-  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL && !coef) { set_error("euler_ancestral needs the (sigma_down, sigma_up) coefficients"); return BESO_E_INVALID; }
+  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_DPMPP_2M) { set_error("unknown sampler"); return BESO_E_INVALID; }
+  if ((sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_DPMPP_2M) && !coef) {
+    set_error("euler_ancestral / dpmpp_2m need their per-step coefficients (coef_host)"); return BESO_E_INVALID;
+  }
+  const int cstride = sampler == BESO_SAMPLER_DPMPP_2M ? 4 : 2;
   if (!sig || n_sigmas < 2 || n_sigmas - 1 > kMaxSteps) { set_error("n_sigmas must be in [2, 129]"); return BESO_E_INVALID; }
   memset(sa, 0, sizeof(*sa));
   sa->n_steps = n_sigmas - 1;
@@ -135,7 +138,10 @@ static int make_sample_args(int sampler, const float* sig, int n_sigmas, const f
   for (int i = 0; i < n_sigmas; ++i) sa->sig[i] = sig[i];
   for (int i = 0; i < n_sigmas - 1; ++i) {
     if (!(sig[i] > 0.f)) { set_error("sigmas must be positive except the last"); return BESO_E_INVALID; }
-    if (coef) { sa->ca[i] = coef[2 * i]; sa->ce[i] = coef[2 * i + 1]; }
+    if (coef) {
+      sa->ca[i] = coef[cstride * i]; sa->ce[i] = coef[cstride * i + 1];
+      if (cstride == 4) { sa->c1[i] = coef[4 * i + 2]; sa->c2[i] = coef[4 * i + 3]; }
+    }
     else {
       // gc_sampling.py:913-923 in fp32: t = -log(sigma), h = t_next - t
       const float t = -logf(sig[i]), tn = -logf(sig[i + 1]);     // -log(0) = +inf

@@ -50,6 +50,8 @@ struct SampleArgs {
   float sig[kMaxSteps + 1];
   float ca[kMaxSteps];   // DDIM: sigma_fn(t_next) / sigma_fn(t);  Euler ancestral: sigma_down
   float ce[kMaxSteps];   // DDIM: expm1(-h);                        Euler ancestral: sigma_up
+  float c1[kMaxSteps];   // DPM-Solver++(2M): 1 + 1/(2r)  (0 on first-order steps)
+  float c2[kMaxSteps];   // DPM-Solver++(2M): 1/(2r)
   const float* noise;    // ancestral samplers: (n_steps, B, t, act) standard-normal draws of the caller
   long long noise_stride;   // elements per step = B * t * act
 };

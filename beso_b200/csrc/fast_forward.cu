@@ -901,6 +901,11 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
           p.out[(size_t)seq0 * p.t * p.act + i] = D;
         } else if (sa.sampler == BESO_SAMPLER_DDIM) {
           xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], D));
+        } else if (sa.sampler == BESO_SAMPLER_DPMPP_2M) {             // gc_sampling.py:726-735; d1 keeps old_denoised
+          const float c2 = sa.c2[step];
+          const float dd = (c2 != 0.0f) ? __fsub_rn(__fmul_rn(sa.c1[step], D), __fmul_rn(c2, d1[i])) : D;
+          xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], dd));
+          d1[i] = D;
         } else if (sa.sampler == BESO_SAMPLER_EULER_ANCESTRAL) {      // gc_sampling.py:216-256
           const float s_down = sa.ca[step];
           const float dd = __fdiv_rn(__fsub_rn(xcur[i], D), s_hat);

@@ -345,6 +345,14 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
       const float ca = sa.ca[step], ce = sa.ce[step];
       for (int i = threadIdx.x; i < n; i += kThreads)
         sm.xcur[i] = __fsub_rn(__fmul_rn(ca, sm.xcur[i]), __fmul_rn(ce, sm.d1[i]));
+    } else if (sa.sampler == BESO_SAMPLER_DPMPP_2M) {   // gc_sampling.py:726-735; d2 keeps old_denoised
+      const float ca = sa.ca[step], ce = sa.ce[step], c1 = sa.c1[step], c2 = sa.c2[step];
+      for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float den = sm.d1[i];
+        const float dd = (c2 != 0.0f) ? __fsub_rn(__fmul_rn(c1, den), __fmul_rn(c2, sm.d2[i])) : den;
+        sm.xcur[i] = __fsub_rn(__fmul_rn(ca, sm.xcur[i]), __fmul_rn(ce, dd));
+        sm.d2[i] = den;
+      }
     } else {
       // Euler ancestral (gc_sampling.py:216-256) steps down to sigma_down and adds sigma_up of fresh noise
       const bool anc = sa.sampler == BESO_SAMPLER_EULER_ANCESTRAL;

@@ -241,7 +241,55 @@ def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extr
     return action
 
 
-SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "euler_ancestral": sample_euler_ancestral}
+def dpmpp_2m_coefficients(sigmas: torch.Tensor) -> torch.Tensor:
+    """Per-step (sigma_fn(t_next)/sigma_fn(t), expm1(-h), 1 + 1/(2r), 1/(2r)) of DPM-Solver++(2M), evaluated with the
+    reference's own fp32 tensor ops (gc_sampling.py:717-734); the last two are 0 on first-order steps."""
+    s = sigmas.detach().float().cpu()
+    t_fn = lambda sigma: sigma.log().neg()          # noqa: E731
+    rows = []
+    for i in range(len(s) - 1):
+        t, t_next = t_fn(s[i]), t_fn(s[i + 1])
+        h = t_next - t
+        ca, ce = t_next.neg().exp() / t.neg().exp(), (-h).expm1()
+        if i == 0 or s[i + 1] == 0:
+            rows.append([float(ca), float(ce), 0.0, 0.0])
+        else:
+            h_last = t - t_fn(s[i - 1])
+            r = h_last / h
+            rows.append([float(ca), float(ce), float(1 + 1 / (2 * r)), float(1 / (2 * r))])
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+@torch.no_grad()
+def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
+    """DPM-Solver++(2M) (gc_sampling.py:703-736); ``scaler`` is ignored there too."""
+    fused = _try_fused("dpmpp_2m", model, state, action, goal, sigmas, None, extra_args, callback, 0.0,
+                       coef=dpmpp_2m_coefficients(sigmas))
+    if fused is not None:
+        return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    t_fn = lambda sigma: sigma.log().neg()          # noqa: E731
+    old_denoised = None
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * ones, **extra_args)
+        if callback is not None:
+            callback({"action": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        h = t_next - t
+        if old_denoised is None or sigmas[i + 1] == 0:
+            action = (t_next.neg().exp() / t.neg().exp()) * action - (-h).expm1() * denoised
+        else:
+            h_last = t - t_fn(sigmas[i - 1])
+            r = h_last / h
+            denoised_d = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised
+            action = (t_next.neg().exp() / t.neg().exp()) * action - (-h).expm1() * denoised_d
+        old_denoised = denoised
+    return action
+
+
+SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "euler_ancestral": sample_euler_ancestral,
+            "dpmpp_2m": sample_dpmpp_2m}
 
 
 def n_model_evals(sampler: str, sigmas) -> int:

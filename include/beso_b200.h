@@ -52,7 +52,8 @@ enum {
   BESO_SAMPLER_DDIM = 0,  /* gc_sampling.py:895-924 */
   BESO_SAMPLER_EULER = 1, /* gc_sampling.py:167-213 (s_churn = 0) */
   BESO_SAMPLER_HEUN = 2,  /* gc_sampling.py:259-314 (s_churn = 0) */
-  BESO_SAMPLER_EULER_ANCESTRAL = 3 /* gc_sampling.py:216-256; needs beso_sample_loop_noise */
+  BESO_SAMPLER_EULER_ANCESTRAL = 3, /* gc_sampling.py:216-256; needs beso_sample_loop_noise */
+  BESO_SAMPLER_DPMPP_2M = 4 /* gc_sampling.py:703-736 (DPM-Solver++(2M)); needs its coefficients in coef_host */
 };
 
 /* flags */
@@ -141,7 +142,11 @@ int beso_sample_loop(beso_plan* plan, int mode, int sampler, const float* sigmas
  *              (gc_sampling.py:108-114), evaluated by the caller with the reference's own fp32 tensor ops.
  *   noise_dev: (n_sigmas-1, B, t, act) fp32 = the torch.randn_like(action) draws of the reference, one per step
  *              (entries of steps with sigma_down == 0 are never read).  The caller draws them, in step order,
- *              so the result is bit-comparable with the reference under the same generator state. */
+ *              so the result is bit-comparable with the reference under the same generator state.
+ * BESO_SAMPLER_DPMPP_2M = sample_dpmpp_2m (gc_sampling.py:703-736): coef_host holds 4*(n_sigmas-1) fp32, per step
+ *   [sigma_fn(t_next)/sigma_fn(t), expm1(-h), 1 + 1/(2r), 1/(2r)] evaluated by the caller with the reference's fp32
+ *   tensor ops; the last two are 0 for the first-order steps (the first step and a step onto sigma = 0).
+ *   noise_dev is not used. */
 int beso_sample_loop_noise(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
                            const float* coef_host, const float* state_dev, const float* goal_dev,
                            float* x_inout_dev, const float* noise_dev, int B, int t, uint32_t flags,

@@ -300,6 +300,28 @@ def sample_euler_ancestral(sd, cfg, state, action, goal, sigmas, cond_lambda=Non
     return action
 
 
+# gc_sampling.py:703-736
+def sample_dpmpp_2m(sd, cfg, state, action, goal, sigmas, cond_lambda=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()              # noqa: E731
+    t_fn = lambda sigma: sigma.log().neg()          # noqa: E731
+    old_denoised = None
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in)
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        h = t_next - t
+        if old_denoised is None or sigmas[i + 1] == 0:
+            action = (sigma_fn(t_next) / sigma_fn(t)) * action - (-h).expm1() * denoised
+        else:
+            h_last = t - t_fn(sigmas[i - 1])
+            r = h_last / h
+            denoised_d = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised
+            action = (sigma_fn(t_next) / sigma_fn(t)) * action - (-h).expm1() * denoised_d
+        old_denoised = denoised
+    return action
+
+
 # gc_sampling.py:259-314
 def sample_heun(sd, cfg, state, action, goal, sigmas, cond_lambda=None,
                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, eps_list=None):

@@ -160,6 +160,10 @@ def gen_ancestral(ns):
         if down > 0:
             noise[i] = torch.randn_like(x_t)
     arrays["noise_karras_4"] = noise
+    # DPM-Solver++(2M) (deterministic), same inputs
+    for n in (1, 3, 5):
+        arrays[f"dpmpp_2m_{n}"] = gs.sample_dpmpp_2m(m, x["state"], x_t, x["goal"], arrays[f"sigmas_{n}"], disable=True)
+    arrays["dpmpp_2m_karras_4"] = gs.sample_dpmpp_2m(m, x["state"], x_t, x["goal"], sigk, disable=True)
     save("samplers_ancestral_K256", cfg, seed, sd, **arrays)
 
 

@@ -113,6 +113,15 @@ def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
                                          callback=lambda d: seen.append(int(d["i"])))
     assert seen == [0, 1, 2, 3, 4]
     torch.testing.assert_close(r3, r2, rtol=1e-4, atol=1e-5)
+    # DPM-Solver++(2M), same fixture: one launch, matches the reference
+    for tag in ("1", "3", "5", "karras_4"):
+        launches = _lib.lib().beso_kernel_launches()
+        got = sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{tag}"])
+        assert _lib.lib().beso_kernel_launches() == launches + 1
+        torch.testing.assert_close(got.cpu(), a[f"dpmpp_2m_{tag}"], **TOL[mode])
+    stepwise = sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], g["sigmas_5"], callback=lambda d: None)
+    torch.testing.assert_close(stepwise, sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], a["sigmas_5"]),
+                               rtol=1e-4, atol=1e-5)
     # classifier-free guidance wrapper goes through the same launch
     from oracle import beso_oracle as O
     w = ClassifierFreeSampleModel(m, cond_lambda=2.0)

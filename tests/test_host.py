@@ -177,3 +177,17 @@ def test_euler_ancestral_refuses_cpu_models_like_every_other_sampler():
     g = torch.zeros(2, K256.goal_len, K256.obs_dim)
     with pytest.raises(_lib.BesoLibraryError):
         sampling.sample_euler_ancestral(m, s, x, g, sampling.get_sigmas_exponential(3, 0.005, 1.0))
+
+
+def test_dpmpp_2m_coefficients_follow_the_reference_formula():
+    sig = sampling.get_sigmas_exponential(4, 0.005, 1.0)
+    coef = sampling.dpmpp_2m_coefficients(sig)
+    assert coef.shape == (4, 4)
+    assert float(coef[0, 2]) == 0.0 and float(coef[0, 3]) == 0.0          # first step: first order
+    assert float(coef[-1, 2]) == 0.0 and float(coef[-1, 3]) == 0.0        # step onto sigma = 0: first order
+    t = sig[:-1].log().neg()
+    h1, h0 = (sig[2].log().neg() - t[1]), (t[1] - t[0])
+    r = h0 / h1
+    assert float(coef[1, 2]) == float(1 + 1 / (2 * r)) and float(coef[1, 3]) == float(1 / (2 * r))
+    assert torch.equal(coef[:, :2], sampling.ddim_coefficients(sig))
+    assert _lib.SAMPLER_IDS["dpmpp_2m"] == 4 and "dpmpp_2m" in sampling.SAMPLERS

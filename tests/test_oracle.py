@@ -81,6 +81,16 @@ def test_euler_ancestral_matches_golden():
     assert float(a["noise_3"][-1].abs().max()) == 0.0
 
 
+def test_dpmpp_2m_matches_golden():
+    """DPM-Solver++(2M) (gc_sampling.py:703-736) of the real reference."""
+    cfg, meta, a = load_golden("samplers_ancestral_K256")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    with torch.no_grad():
+        for tag in ("1", "3", "5", "karras_4"):
+            got = O.sample_dpmpp_2m(sd, oc, a["state"], a["x_t"], a["goal"], a[f"sigmas_{tag}"])
+            torch.testing.assert_close(got, a[f"dpmpp_2m_{tag}"], **TOL)
+
+
 def test_ddim_last_step_returns_denoised():
     """sigma_{n}=0 -> h=+inf -> x <- denoised exactly (gc_sampling.py:921-923)."""
     cfg, meta, a = load_golden("samplers_K256")
