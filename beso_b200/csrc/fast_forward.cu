@@ -222,7 +222,6 @@ __device__ __forceinline__ void spin_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   wait_timeout(bar, parity);
 }
-
 // whole-warp wait with a single polling lane
 __device__ __forceinline__ void warp_wait(int lane, uint32_t bar, uint32_t parity) {
   if (lane == 0) spin_wait(bar, parity);
@@ -1098,8 +1097,6 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         g += 2;
       };
       using std::integral_constant;
-      auto I = [](auto v) { return v; };
-      (void)I;
 #define BESO_IC(v) integral_constant<uint32_t, (v)>{}
       for (int it = 0; it < my_tiles * p.evals; ++it) {
         if constexpr (DBG) tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;

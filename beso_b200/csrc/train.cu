@@ -451,10 +451,6 @@ __global__ void loss_kernel(Dims D, const float* __restrict__ pred, const float*
   __syncthreads();
   if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < kTB / 32; ++i) t += s[i]; partial[blockIdx.x] = t * invN; }
 }
-__global__ void fill_kernel(float* x, size_t n, float v) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) x[i] = v;
-}
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
   float a = 0.f;
   for (int i = threadIdx.x; i < n; i += 32) a += partial[i];
@@ -561,7 +557,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   const size_t per_layer = 5 * align4(Md) + align4(3 * Md) + align4(nP) + 2 * align4(MF) + 2 * align4(2 * (size_t)M);
   const size_t n_gather = (size_t)B * (D.G + D.t);
   const size_t total = (size_t)L * per_layer + 2 * align4(Md) + align4(2 * (size_t)M) + align4(nBt * d) + 3 * align4(nBt * D.act) +
-                       4 * align4(Md) + align4(MF) + align4(3 * Md) + align4((size_t)M) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + kPartialFloats + 4096;
+                       4 * align4(Md) + align4(MF) + align4(3 * Md) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + kPartialFloats + 4096;
   int rc = ensure_ws(ws, total);
   if (rc) return rc;
   float* p = ws->buf;
@@ -577,7 +573,6 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
         *dpred = take(nBt * D.act), *xin = take(nBt * D.act);
   float *dX = take(Md), *dT = take(Md), *dH = take(Md), *dY = take(Md), *dBig = take(MF), *dQKV = take(3 * Md);
   float *gRows = take(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))), *partial = take(kPartialFloats);
-  float* ones = take((size_t)M);
   cublasHandle_t h = ws->blas;
   BESO_CUBLAS(cublasSetStream(h, st));
   // fp32 FMA by default (the reference's arithmetic); TF32 tensor-core GEMMs only on request
@@ -641,7 +636,6 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
 
   // ============================== backward ==============================
   // column sums (bias gradients) as A^T 1 with a library GEMV: bandwidth-bound, full-chip parallel
-  (void)ones;
   auto colsum = [&](const float* Am, int rows, int N, int lda, float* out) -> int {
     if ((size_t)N * kColsumRowBlocks > kPartialFloats) { set_error("internal: column-sum scratch too small"); return BESO_E_INVALID; }
     LAUNCH(colsum_partial_kernel, dim3((N + 31) / 32, kColsumRowBlocks), dim3(32, 8), 0, Am, rows, N, lda, partial);
