@@ -1,13 +1,16 @@
-"""Host-side mirror of the sampling half of ``BesoAgent`` (diffusion_agents/beso_agent.py).
+"""Host-side mirror of the hot-path half of ``BesoAgent`` (diffusion_agents/beso_agent.py).
 
 Only what sits directly on the hot path is here: ``sample_loop`` (beso_agent.py:390-456),
-``get_noise_schedule`` (:580-598), ``evaluate`` (:251-289) and the stateful ``predict``
-(:297-388) with its observation / action context deques.  Hydra, wandb, workspaces, data
-loading and the optimiser stay in the reference shell; to use the reference's own BesoAgent
-instead, point its model ``_target_`` at ``beso_b200.denoiser.GCDenoiser``.
+``get_noise_schedule`` (:580-598), ``evaluate`` (:251-289), the stateful ``predict``
+(:297-388) with its observation / action context deques, and ``train_step`` (:215-248) with
+``make_sample_density`` (:540-578) on top of the fused loss / backward and the fused AdamW + EMA
+step.  Hydra, wandb, workspaces and data loading stay in the reference shell; to use the
+reference's own BesoAgent instead, point its model ``_target_`` at
+``beso_b200.denoiser.GCDenoiser``.
 """
 from __future__ import annotations
 
+import math
 from collections import deque
 from typing import Optional
 
@@ -118,6 +121,79 @@ class BesoAgent:
     def ema_updated(self):
         """Call after the EMA shadow parameters changed so slot 1 is re-packed on next use."""
         self._core()._packed.pop(1, None)
+
+    # ---- training: beso_agent.py:215-248, 540-578; k_diffusion/utils.py:170-200 -------------------------
+    def configure_training(self, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
+                           lr_step_size: int = 100, lr_gamma: float = 0.99, decay: float = 0.999,
+                           update_ema_every_n_steps: int = 1, sigma_sample_density_type: str = "loglogistic",
+                           sigma_sample_density_mean: float = -1.2, sigma_sample_density_std: float = 1.2):
+        """Optimiser, StepLR and EMA of the reference agent (configs/agents/beso_kitchen.yaml:9-17, 26-31;
+        base_agent.py:33-40, beso_agent.py:60-66), with the fused AdamW + EMA step."""
+        from .optim import ExponentialMovingAverage, FusedAdamW
+        core = self._core()
+        params = list(core.get_params())
+        self.optimizer = FusedAdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.lr_scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=lr_step_size, gamma=lr_gamma)
+        self.ema_helper = ExponentialMovingAverage(params, decay, self.device)
+        self.update_ema_every_n_steps = update_ema_every_n_steps
+        self.optimizer.attach_ema(self.ema_helper, update_ema_every_n_steps)
+        self.use_ema, self.ema_params = True, self.ema_helper.shadow_params
+        self.sigma_sample_density_type = sigma_sample_density_type
+        self.sigma_sample_density_mean, self.sigma_sample_density_std = sigma_sample_density_mean, sigma_sample_density_std
+        self.steps = 0
+
+    def make_sample_density(self):
+        """Noise-level distribution for training (beso_agent.py:540-578; the four types the shipped configs use)."""
+        sigma_data = self._core().sigma_data
+        kind = self.sigma_sample_density_type
+        if kind == "lognormal":
+            loc, scale = self.sigma_sample_density_mean, self.sigma_sample_density_std
+            return lambda shape, device: (torch.randn(shape, device=device, dtype=torch.float32) * scale + loc).exp()
+        if kind == "loglogistic":                           # utils.rand_log_logistic, truncated to [sigma_min, sigma_max]
+            loc, scale = math.log(sigma_data), 0.5
+
+            def draw(shape, device):
+                lo = torch.as_tensor(self.sigma_min, device=device, dtype=torch.float64)
+                hi = torch.as_tensor(self.sigma_max, device=device, dtype=torch.float64)
+                min_cdf, max_cdf = lo.log().sub(loc).div(scale).sigmoid(), hi.log().sub(loc).div(scale).sigmoid()
+                u = torch.rand(shape, device=device, dtype=torch.float64) * (max_cdf - min_cdf) + min_cdf
+                return u.logit().mul(scale).add(loc).exp().to(torch.float32)
+            return draw
+        if kind == "loguniform":
+            lo, hi = math.log(self.sigma_min), math.log(self.sigma_max)
+            return lambda shape, device: (torch.rand(shape, device=device, dtype=torch.float32) * (hi - lo) + lo).exp()
+        if kind == "uniform":
+            lo, hi = self.sigma_min, self.sigma_max
+            return lambda shape, device: torch.rand(shape, device=device, dtype=torch.float32) * (hi - lo) + lo
+        raise ValueError("Unknown sample density type")
+
+    def train_step(self, batch: dict) -> float:
+        """One optimisation step (beso_agent.py:215-248): noise and noise levels are drawn with the same torch calls,
+        loss + all gradients come from ONE call of the fused forward / backward, AdamW + EMA are ONE launch."""
+        from .training import loss_and_flat_grad
+        core = self._core()
+        state = self.scaler.scale_input(batch["observation"].to(self.device))
+        goal = self.scaler.scale_input(batch["goal_observation"].to(self.device))
+        action = self.scaler.scale_output(batch["action"].to(self.device))
+        core.train()
+        core.training = True
+        noise = torch.randn_like(action)
+        sigma = self.make_sample_density()(shape=(len(action),), device=self.device)
+        inner = core.inner_model
+        goal_keep = None
+        if inner.cond_mask_prob > 0.0:                      # element-wise goal mask of CFG training (score_gpts.py:360-371)
+            mask = torch.bernoulli(torch.ones(goal.shape, device=goal.device) * inner.cond_mask_prob)
+            goal_keep = (1.0 - mask).contiguous()
+        if self.pred_last_action_only:
+            noise[:, :-1, :] = 0
+        loss, flat = loss_and_flat_grad(core, state, action, goal, noise, sigma, self.pred_last_action_only, goal_keep)
+        self.optimizer.step(flat_grad=flat)                 # zero_grad / backward / step of the reference in one
+        self.lr_scheduler.step()
+        self.steps += 1
+        if self.steps % self.update_ema_every_n_steps == 0:
+            self.ema_helper.update(core.parameters())       # acknowledged: applied inside optimizer.step
+            self.ema_updated()
+        return loss.item()
 
     # ---- beso_agent.py:251-289 --------------------------------------------------------------
     @torch.no_grad()

@@ -191,3 +191,30 @@ def test_dpmpp_2m_coefficients_follow_the_reference_formula():
     assert float(coef[1, 2]) == float(1 + 1 / (2 * r)) and float(coef[1, 3]) == float(1 / (2 * r))
     assert torch.equal(coef[:, :2], sampling.ddim_coefficients(sig))
     assert _lib.SAMPLER_IDS["dpmpp_2m"] == 4 and "dpmpp_2m" in sampling.SAMPLERS
+
+
+def test_sample_density_matches_reference_formulas():
+    """make_sample_density (beso_agent.py:540-578) -> utils.rand_log_logistic / rand_log_normal (utils.py:170-190):
+    same torch calls, so the same generator state gives the same noise levels."""
+    import math
+    m = build_denoiser(K256, "cpu")
+    agent = BesoAgent(m, device="cpu", sigma_min=0.005, sigma_max=1.0)
+    agent.sigma_sample_density_type = "loglogistic"
+    agent.sigma_sample_density_mean, agent.sigma_sample_density_std = -1.2, 1.2
+    torch.manual_seed(3)
+    got = agent.make_sample_density()(shape=(1000,), device="cpu")
+    torch.manual_seed(3)
+    loc, scale = math.log(m.sigma_data), 0.5
+    lo, hi = torch.as_tensor(0.005, dtype=torch.float64), torch.as_tensor(1.0, dtype=torch.float64)
+    min_cdf, max_cdf = lo.log().sub(loc).div(scale).sigmoid(), hi.log().sub(loc).div(scale).sigmoid()
+    u = torch.rand((1000,), dtype=torch.float64) * (max_cdf - min_cdf) + min_cdf
+    want = u.logit().mul(scale).add(loc).exp().to(torch.float32)
+    assert torch.equal(got, want) and float(got.min()) >= 0.005 and float(got.max()) <= 1.0
+    agent.sigma_sample_density_type = "lognormal"
+    torch.manual_seed(4)
+    got = agent.make_sample_density()(shape=(64,), device="cpu")
+    torch.manual_seed(4)
+    assert torch.equal(got, (torch.randn((64,)) * 1.2 - 1.2).exp())
+    agent.sigma_sample_density_type = "nope"
+    with pytest.raises(ValueError):
+        agent.make_sample_density()
