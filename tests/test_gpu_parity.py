@@ -3,9 +3,10 @@ against the oracle on seeded inputs, and through size-independent properties at 
 
 Tolerances (written here, never loosened silently):
   precise mode  rtol 1e-3, atol 1e-5   -- the north-star tolerance, against the fp32 reference
-  fast mode     rtol 1e-2, atol 5e-3   -- bf16 tensor-core operands (the reference's own
-                                          bf16 autocast shows max |err| 4.5e-3..2.3e-2 vs its fp32 self;
-                                          this kernel measures max |err| <= 2.2e-3 on every case below)
+  fast mode     rtol 3e-3, atol 3e-3   -- fp16 tensor-core operands: measured max |err| 1.3e-3 over all fixtures
+                                          (tools/fast_error_report.py, profiles/r1_fast_error_report.txt);
+                                          SURVEY.md H1: the reference's own bf16 autocast shows max |err|
+                                          4.5e-3..2.3e-2 against its fp32 self
 """
 import ctypes as C
 
@@ -21,7 +22,7 @@ from beso_b200.synth import synthetic_inputs, synthetic_state_dict
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=1e-2, atol=5e-3)}
+TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=3e-3, atol=3e-3)}
 FAST_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256"}
 FWD = ["fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_kitchen", "fwd_small_push",
        "fwd_mlp_head", "fwd_no_goal"]
