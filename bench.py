@@ -96,7 +96,7 @@ def time_oracle(batch, reps):
     return times
 
 
-def run_reference(args):
+def run_reference(args, out_fd):
     """--impl reference: the reference's CPU implementation of the same config, rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -107,17 +107,32 @@ def run_reference(args):
     dt = sum(times) / len(times)
     value = sample_b * N_STEPS / dt
     sample = f"oracle port (torch {torch.__version__} CPU fp32) of {sample_b}/{BATCH} sequences x {N_STEPS} DDIM steps per step"
-    print(json.dumps({
+    emit(out_fd, {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
+
+
+def claim_stdout() -> int:
+    """The contract is ONE JSON line on stdout.  Libraries also write there (NCCL prints its version line through
+    C stdio, flushed at exit), so file descriptor 1 is pointed at stderr for the rest of the process and the JSON
+    line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    fd = os.dup(1)
+    os.dup2(2, 1)
+    return fd
+
+
+def emit(fd: int, obj) -> None:
+    os.write(fd, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    out_fd = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -129,7 +144,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_fd)
 
     import ctypes as C
     from beso_b200 import K256, T16, _lib
@@ -303,7 +318,7 @@ def main():
                                "sample": f"{sample_b}/{BATCH} sequences x {N_STEPS} DDIM steps, best of 2 after 1 warm-up, "
                                          f"oracle port on torch {torch.__version__} CPU fp32"}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out_fd, out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
