@@ -87,7 +87,9 @@ class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (single parameter group), one kernel launch per step."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # config systems may hand over strings ("1e-4") or list-like betas
+        super().__init__(params, dict(lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps),
+                                      weight_decay=float(weight_decay)))
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdamW supports a single parameter group (the reference uses one)")
         self._params = [p for p in self.param_groups[0]["params"] if p.requires_grad]
