@@ -418,7 +418,9 @@ __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-template <int NKT>
+// HI = false: query rows 8..15 of this tile lie beyond the sequence (e.g. rows 24..31 of a 23-token sequence):
+// their softmax is skipped and their P rows are zero.
+template <int NKT, bool HI>
 __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T) {
   const uint32_t qkv = sbase + kSmQkv;
   // ---- S = Q K^T ----
@@ -455,12 +457,14 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
       for (int e = 0; e < 2; ++e) {
         const int j = kt * 16 + nb * 8 + (lane & 3) * 2 + e;
         if (j > i_lo) sc[kt][nb][e] = -INFINITY;
-        if (j > i_hi) sc[kt][nb][2 + e] = -INFINITY;
         mx_lo = fmaxf(mx_lo, sc[kt][nb][e]);
-        mx_hi = fmaxf(mx_hi, sc[kt][nb][2 + e]);
+        if (HI) {
+          if (j > i_hi) sc[kt][nb][2 + e] = -INFINITY;
+          mx_hi = fmaxf(mx_hi, sc[kt][nb][2 + e]);
+        }
       }
   mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  if (HI) { mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2)); }
   // the scores are in log2 units: p = 2^(s - max), normalised before the P V product so that the output needs
   // no scaling
   float sum_lo = 0.f, sum_hi = 0.f;
@@ -471,19 +475,19 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         sc[kt][nb][e] = ex2f(sc[kt][nb][e] - mx_lo);
-        sc[kt][nb][2 + e] = ex2f(sc[kt][nb][2 + e] - mx_hi);
-        sum_lo += sc[kt][nb][e]; sum_hi += sc[kt][nb][2 + e];
+        sum_lo += sc[kt][nb][e];
+        if (HI) { sc[kt][nb][2 + e] = ex2f(sc[kt][nb][2 + e] - mx_hi); sum_hi += sc[kt][nb][2 + e]; }
       }
   sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
-  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-  const float inv_lo = __frcp_rn(sum_lo), inv_hi = __frcp_rn(sum_hi);
+  if (HI) { sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2); }
+  const float inv_lo = __frcp_rn(sum_lo), inv_hi = HI ? __frcp_rn(sum_hi) : 0.f;
   uint32_t pa[NKT][4];                           // P as A fragments, one per 16-key step
 #pragma unroll
   for (int kt = 0; kt < NKT; ++kt) {
     pa[kt][0] = pack_f16x2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo);   // (row lo, keys 0-7)
-    pa[kt][1] = pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi);   // (row hi, keys 0-7)
+    pa[kt][1] = HI ? pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi) : 0u;   // (row hi, keys 0-7)
     pa[kt][2] = pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo);   // (row lo, keys 8-15)
-    pa[kt][3] = pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi);   // (row hi, keys 8-15)
+    pa[kt][3] = HI ? pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi) : 0u;   // (row hi, keys 8-15)
   }
   // ---- O = P V ----
   float o[8][4];
@@ -508,7 +512,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
 #pragma unroll
     for (int n = 0; n < 8; ++n) sts32(y_lo + (((uint32_t)n << 4) ^ x_lo), pack_f16x2(o[n][0], o[n][1]));
   }
-  if (i_hi < T) {
+  if (HI && i_hi < T) {
 #pragma unroll
     for (int n = 0; n < 8; ++n) sts32(y_hi + (((uint32_t)n << 4) ^ x_hi), pack_f16x2(o[n][2], o[n][3]));
   }
@@ -518,8 +522,9 @@ __device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awa
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
   for (int item = awarp; item < S * MT; item += kAttnWarps) {
     const int mt = MT - 1 - item / S, s = item % S;   // later query tiles see more keys: schedule them first
-    if (mt == 0) attention_item<1>(sbase, lane, s * T, 0, T);
-    else attention_item<2>(sbase, lane, s * T, mt, T);
+    const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
+    if (mt == 0) { if (hi) attention_item<1, true>(sbase, lane, s * T, 0, T); else attention_item<1, false>(sbase, lane, s * T, 0, T); }
+    else { if (hi) attention_item<2, true>(sbase, lane, s * T, mt, T); else attention_item<2, false>(sbase, lane, s * T, mt, T); }
   }
 }
 
