@@ -418,8 +418,9 @@ __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// HI = false: query rows 8..15 of this tile lie beyond the sequence (e.g. rows 24..31 of a 23-token sequence):
-// their softmax is skipped and their P rows are zero.
+// HI = false: rows 8..15 of the diagonal tile lie beyond the sequence (e.g. tokens 24..31 of a 23-token sequence):
+// as queries their softmax is skipped and their P rows are zero; as keys (columns 8..15 of the last key step)
+// their scores are neither computed nor exponentiated.
 template <int NKT, bool HI>
 __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T) {
   const uint32_t qkv = sbase + kSmQkv;
@@ -443,7 +444,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
       uint32_t kb[4];
       ldmatrix_x4(qkv + r * kQkvStride + (64 + k * 16 + ((lane >> 3) & 1) * 8) * 2, kb);
       mma_16816(sc[kt][0], qa[k], kb[0], kb[1]);
-      mma_16816(sc[kt][1], qa[k], kb[2], kb[3]);
+      if (HI || kt + 1 < NKT) mma_16816(sc[kt][1], qa[k], kb[2], kb[3]);
     }
   }
   // ---- mask + softmax (rows i0 = lane/4 and i0 + 8 of this query tile) ----
@@ -455,6 +456,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
+        if (!HI && kt + 1 == NKT && nb == 1) continue;      // keys beyond the sequence
         const int j = kt * 16 + nb * 8 + (lane & 3) * 2 + e;
         if (j > i_lo) sc[kt][nb][e] = -INFINITY;
         mx_lo = fmaxf(mx_lo, sc[kt][nb][e]);
@@ -474,6 +476,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
+        if (!HI && kt + 1 == NKT && nb == 1) continue;
         sc[kt][nb][e] = ex2f(sc[kt][nb][e] - mx_lo);
         sum_lo += sc[kt][nb][e];
         if (HI) { sc[kt][nb][2 + e] = ex2f(sc[kt][nb][2 + e] - mx_hi); sum_hi += sc[kt][nb][2 + e]; }
@@ -486,7 +489,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   for (int kt = 0; kt < NKT; ++kt) {
     pa[kt][0] = pack_f16x2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo);   // (row lo, keys 0-7)
     pa[kt][1] = HI ? pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi) : 0u;   // (row hi, keys 0-7)
-    pa[kt][2] = pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo);   // (row lo, keys 8-15)
+    pa[kt][2] = (HI || kt + 1 < NKT) ? pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo) : 0u;   // (row lo, keys 8-15)
     pa[kt][3] = HI ? pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi) : 0u;   // (row hi, keys 8-15)
   }
   // ---- O = P V ----
