@@ -383,24 +383,22 @@ __device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float* tra
 // K bias shifts every score of a query row by the same amount (softmax-invariant) and the V bias passes
 // through the softmax average unchanged, so it is folded into the projection bias at pack time.
 __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
-  // all TMEM reads first, then the accumulator is handed back to the MMA warp (QKV of the next head can
-  // start) while this thread still converts and stores
+  // Each thread takes 32 columns of Q, of K and of V of its row (so that both column halves carry the same
+  // share of the Q bias).  All TMEM reads first, then the accumulator is handed back to the MMA warp (QKV of
+  // the next head can start) while this thread still converts and stores.
   float v0[32], v1[32], v2[32];
-  const int colb = c.hf * 96;                            // 0..191 within [Q_h | K_h | V_h]
+  const int colb = c.hf * 32;                            // within each 64-column block of [Q_h | K_h | V_h]
   tmem_ld32(c.lane_addr(kColS0 + colb), v0);
-  tmem_ld32(c.lane_addr(kColS0 + colb + 32), v1);
-  tmem_ld32(c.lane_addr(kColS0 + colb + 64), v2);
+  tmem_ld32(c.lane_addr(kColS0 + 64 + colb), v1);
+  tmem_ld32(c.lane_addr(kColS0 + 128 + colb), v2);
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
   const uint32_t dst0 = c.sbase + kSmQkv + (uint32_t)c.row * kQkvStride + (uint32_t)colb * 2u;
-  if (c.hf == 0) {                                       // v0, v1 = Q (+ bias)
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b0 = lds128f_ro(bq_s + (uint32_t)i * 4u), b1 = lds128f_ro(bq_s + (uint32_t)(32 + i) * 4u);
-      v0[i] += b0.x; v0[i + 1] += b0.y; v0[i + 2] += b0.z; v0[i + 3] += b0.w;
-      v1[i] += b1.x; v1[i + 1] += b1.y; v1[i + 2] += b1.z; v1[i + 3] += b1.w;
-    }
+  for (int i = 0; i < 32; i += 4) {                      // Q (+ bias)
+    const float4 b0 = lds128f_ro(bq_s + (uint32_t)(colb + i) * 4u);
+    v0[i] += b0.x; v0[i + 1] += b0.y; v0[i + 2] += b0.z; v0[i + 3] += b0.w;
   }
   auto emit = [&](const float (&v)[32], uint32_t dst) {
 #pragma unroll
@@ -408,7 +406,7 @@ __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
       sts128(dst + q * 16, pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]),
              pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]));
   };
-  emit(v0, dst0); emit(v1, dst0 + 64); emit(v2, dst0 + 128);
+  emit(v0, dst0); emit(v1, dst0 + 128); emit(v2, dst0 + 256);
 }
 
 // Causal softmax(Q K^T) V for every sequence of the tile, one warp per (sequence, 16-query tile), mma.sync fp16.
@@ -879,29 +877,29 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
   const int ls = cfg ? (vs >> 1) : vs;
   const bool act_row = (c.hf == 0) && vs < p.S && tok > p.G && (j & 1) && (ls < ns);
   const int xo = (ls * p.t + (j >> 1)) * p.act;
-  float dval[kMaxAct];
+  // D = c_out * F + c_skip * x (score_wrappers.py:81-96) of action column a of this row, straight from the
+  // accumulator registers (no per-thread array: it would live in local memory)
+  float c_skip = 0.f, c_out = 1.f;
   if (act_row) {
     const float sg = xb.sigv[vs];
     const float den = sg * sg + p.sigma_data * p.sigma_data;
-    const float c_skip = p.sigma_data * p.sigma_data / den, c_out = sg * p.sigma_data / sqrtf(den);
+    c_skip = p.sigma_data * p.sigma_data / den;
+    c_out = sg * p.sigma_data / sqrtf(den);
+  }
+  auto denoised = [&](float acc, int a) -> float {
+    const float f = acc + hb[a];
+    return inner ? f : __fadd_rn(__fmul_rn(f, c_out), __fmul_rn(xsrc[xo + a], c_skip));
+  };
+  if (cfg && act_row && (vs & 1)) {                 // unconditional branch rows park their result for the mix
 #pragma unroll
-    for (int a = 0; a < kMaxAct; ++a) {
-      if (a < p.act) {
-        const float f = pr[a] + hb[a];
-        dval[a] = inner ? f : __fadd_rn(__fmul_rn(f, c_out), __fmul_rn(xsrc[xo + a], c_skip));
-      }
-    }
-    if (cfg && (vs & 1)) {
-#pragma unroll
-      for (int a = 0; a < kMaxAct; ++a) if (a < p.act) dU[xo + a] = dval[a];
-    }
+    for (int a = 0; a < kMaxAct; ++a) if (a < p.act) dU[xo + a] = denoised(pr[a], a);
   }
   if (cfg) compute_sync();
   if (act_row && !(cfg && (vs & 1))) {
 #pragma unroll
     for (int a = 0; a < kMaxAct; ++a) {
       if (a < p.act) {
-        float D = dval[a];
+        float D = denoised(pr[a], a);
         if (cfg) D = __fadd_rn(dU[xo + a], __fmul_rn(p.lambda, __fsub_rn(D, dU[xo + a])));
         const int i = xo + a;
         if (sa.n_steps == 0) {
