@@ -90,6 +90,14 @@ class BesoAgent:
             return sampling.sample_euler(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "ddim":
             return sampling.sample_ddim(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "dpm":                          # beso_agent.py:434-435 (dispatched without the scaler)
+            return sampling.sample_dpm_2(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == "ancestral":                    # beso_agent.py:428-429
+            return sampling.sample_dpm_2_ancestral(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "dpmpp_2s_ancestral":           # beso_agent.py:445-446
+            return sampling.sample_dpmpp_2s_ancestral(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "dpmpp_2s":                     # beso_agent.py:447-448
+            return sampling.sample_dpmpp_2s(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "dpmpp_2m":                     # beso_agent.py:450-451
             return sampling.sample_dpmpp_2m(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "euler_ancestral":              # beso_agent.py:431-432

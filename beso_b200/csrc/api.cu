@@ -126,11 +126,11 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
 }
 
 static int make_sample_args(int sampler, const float* sig, int n_sigmas, const float* coef, SampleArgs* sa) {
-  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_DPMPP_2M) { set_error("unknown sampler"); return BESO_E_INVALID; }
-  if ((sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_DPMPP_2M) && !coef) {
-    set_error("euler_ancestral / dpmpp_2m need their per-step coefficients (coef_host)"); return BESO_E_INVALID;
+  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_TWO_STAGE) { set_error("unknown sampler"); return BESO_E_INVALID; }
+  if ((sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_DPMPP_2M || sampler == BESO_SAMPLER_TWO_STAGE) && !coef) {
+    set_error("euler_ancestral / dpmpp_2m / two-stage samplers need their per-step coefficients (coef_host)"); return BESO_E_INVALID;
   }
-  const int cstride = sampler == BESO_SAMPLER_DPMPP_2M ? 4 : 2;
+  const int cstride = sampler == BESO_SAMPLER_TWO_STAGE ? 8 : (sampler == BESO_SAMPLER_DPMPP_2M ? 4 : 2);
   if (!sig || n_sigmas < 2 || n_sigmas - 1 > kMaxSteps) { set_error("n_sigmas must be in [2, 129]"); return BESO_E_INVALID; }
   memset(sa, 0, sizeof(*sa));
   sa->n_steps = n_sigmas - 1;
@@ -138,7 +138,11 @@ static int make_sample_args(int sampler, const float* sig, int n_sigmas, const f
   for (int i = 0; i < n_sigmas; ++i) sa->sig[i] = sig[i];
   for (int i = 0; i < n_sigmas - 1; ++i) {
     if (!(sig[i] > 0.f)) { set_error("sigmas must be positive except the last"); return BESO_E_INVALID; }
-    if (coef) {
+    if (coef && cstride == 8) {
+      const float* r = coef + 8 * i;
+      sa->sigb[i] = r[0]; sa->ca[i] = r[1]; sa->ce[i] = r[2]; sa->c1[i] = r[3]; sa->c2[i] = r[4]; sa->c3[i] = r[5]; sa->su[i] = r[6];
+      if (r[0] < 0.f) { set_error("two-stage sampler: sigma_b must be >= 0"); return BESO_E_INVALID; }
+    } else if (coef) {
       sa->ca[i] = coef[cstride * i]; sa->ce[i] = coef[cstride * i + 1];
       if (cstride == 4) { sa->c1[i] = coef[4 * i + 2]; sa->c2[i] = coef[4 * i + 3]; }
     }
@@ -297,10 +301,10 @@ int beso_sample_loop_noise(beso_plan* p, int mode, int sampler, const float* sig
   SampleArgs sa;
   rc = make_sample_args(sampler, sigmas, n_sigmas, coef, &sa);
   if (rc) return rc;
-  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL) {
+  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_TWO_STAGE) {
     bool needs_noise = false;
-    for (int i = 0; i < sa.n_steps; ++i) needs_noise |= sa.ca[i] > 0.f;
-    if (needs_noise && !noise) { set_error("euler_ancestral needs the per-step noise (beso_sample_loop_noise)"); return BESO_E_INVALID; }
+    for (int i = 0; i < sa.n_steps; ++i) needs_noise |= (sampler == BESO_SAMPLER_TWO_STAGE ? sa.su[i] != 0.f : sa.ca[i] > 0.f);
+    if (needs_noise && !noise) { set_error("this sampler needs the per-step noise (beso_sample_loop_noise)"); return BESO_E_INVALID; }
   }
   sa.noise = noise;
   sa.noise_stride = (long long)B * t * p->desc.act_dim;

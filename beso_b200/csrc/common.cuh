@@ -52,6 +52,11 @@ struct SampleArgs {
   float ce[kMaxSteps];   // DDIM: expm1(-h);                        Euler ancestral: sigma_up
   float c1[kMaxSteps];   // DPM-Solver++(2M): 1 + 1/(2r)  (0 on first-order steps)
   float c2[kMaxSteps];   // DPM-Solver++(2M): 1/(2r)
+  // generic two-stage sampler (BESO_SAMPLER_TWO_STAGE): u = a1 x + b1 D1 (a1 = ca, b1 = ce);
+  // x = a2 x + b2 u + c2 D2 + su noise (a2 = c1, b2 = c2)
+  float sigb[kMaxSteps]; // sigma of the second evaluation, 0 = single-stage step
+  float c3[kMaxSteps];   // coefficient of D2
+  float su[kMaxSteps];   // noise scale (0 = no noise)
   const float* noise;    // ancestral samplers: (n_steps, B, t, act) standard-normal draws of the caller
   long long noise_stride;   // elements per step = B * t * act
 };

@@ -830,7 +830,7 @@ __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p,
   const XBufs xb = xbufs(c.sm);
   const float s_hat = sa.n_steps ? sa.sig[step] : 0.f;
   const float s_next = sa.n_steps ? sa.sig[step + 1] : 0.f;
-  const float s_eval = second ? s_next : s_hat;
+  const float s_eval = second ? (sa.sampler == BESO_SAMPLER_TWO_STAGE ? sa.sigb[step] : s_next) : s_hat;
   for (int i = c.ctid; i < p.S; i += kComputeThreads) {
     const int ls = cfg ? (i >> 1) : i;
     xb.sigv[i] = sa.n_steps ? s_eval : ((seq0 + ls < p.B) ? __ldg(p.sigma + seq0 + ls) : 1.0f);
@@ -906,6 +906,15 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
           p.out[(size_t)seq0 * p.t * p.act + i] = D;
         } else if (sa.sampler == BESO_SAMPLER_DDIM) {
           xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], D));
+        } else if (sa.sampler == BESO_SAMPLER_TWO_STAGE) {            // coefficient program (include/beso_b200.h)
+          const float su = sa.su[step];
+          const float nz = su != 0.0f ? __ldg(sa.noise + (size_t)step * sa.noise_stride + (size_t)seq0 * p.t * p.act + i) : 0.f;
+          if (!second) {
+            const float u = fmaf(sa.ca[step], xcur[i], sa.ce[step] * D);
+            if (sa.sigb[step] == 0.0f) xcur[i] = fmaf(su, nz, u); else x2[i] = u;
+          } else {
+            xcur[i] = fmaf(su, nz, fmaf(sa.c1[step], xcur[i], fmaf(sa.c2[step], x2[i], sa.c3[step] * D)));
+          }
         } else if (sa.sampler == BESO_SAMPLER_DPMPP_2M) {             // gc_sampling.py:726-735; d1 keeps old_denoised
           const float c2 = sa.c2[step];
           const float dd = (c2 != 0.0f) ? __fsub_rn(__fmul_rn(sa.c1[step], D), __fmul_rn(c2, d1[i])) : D;
@@ -1304,7 +1313,9 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         // ---------------- ln_f + action head + pre-conditioning + sampler update ----------------
         c.phases = eval_epilogue<DBG>(c, p, sa, tile, step, second, trace_row(2 * p.L));
         if (sa.n_steps) {
-          if (!second && sa.sampler == BESO_SAMPLER_HEUN && sa.sig[step + 1] != 0.0f) second = 1;
+          const bool two = (sa.sampler == BESO_SAMPLER_HEUN && sa.sig[step + 1] != 0.0f) ||
+                           (sa.sampler == BESO_SAMPLER_TWO_STAGE && sa.sigb[step] != 0.0f);
+          if (!second && two) second = 1;
           else { second = 0; ++step; }
         }
       }
@@ -1667,6 +1678,8 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
     p.evals = sa.n_steps;
     if (sa.sampler == BESO_SAMPLER_HEUN)
       for (int i = 0; i < sa.n_steps; ++i) if (sa.sig[i + 1] != 0.0f) ++p.evals;
+    if (sa.sampler == BESO_SAMPLER_TWO_STAGE)
+      for (int i = 0; i < sa.n_steps; ++i) if (sa.sigb[i] != 0.0f) ++p.evals;
   }
   p.flags = flags; p.lambda = lambda; p.sigma_data = m.sigma_data;
   p.state = state; p.goal = goal; p.xin = x; p.sigma = sigma; p.out = out;

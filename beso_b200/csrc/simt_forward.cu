@@ -345,6 +345,28 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
       const float ca = sa.ca[step], ce = sa.ce[step];
       for (int i = threadIdx.x; i < n; i += kThreads)
         sm.xcur[i] = __fsub_rn(__fmul_rn(ca, sm.xcur[i]), __fmul_rn(ce, sm.d1[i]));
+    } else if (sa.sampler == BESO_SAMPLER_TWO_STAGE) {  // coefficient program (include/beso_b200.h)
+      const float a1 = sa.ca[step], b1 = sa.ce[step], sb = sa.sigb[step], su = sa.su[step];
+      const float* nz = su != 0.0f ? sa.noise + (size_t)step * sa.noise_stride + (size_t)seq0 * t * m.act : nullptr;
+      if (sb == 0.0f) {
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+          float xe = fmaf(a1, sm.xcur[i], b1 * sm.d1[i]);
+          if (nz) xe = fmaf(su, __ldg(nz + i), xe);
+          sm.xcur[i] = xe;
+        }
+      } else {
+        for (int i = threadIdx.x; i < n; i += kThreads) sm.x2[i] = fmaf(a1, sm.xcur[i], b1 * sm.d1[i]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ns; i += kThreads) sm.sig[i] = sb;
+        __syncthreads();
+        eval_wrapped(c, sm, sm.x2, sm.sig, flags, lambda, sm.d2);
+        const float a2 = sa.c1[step], b2 = sa.c2[step], c2 = sa.c3[step];
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+          float xe = fmaf(a2, sm.xcur[i], fmaf(b2, sm.x2[i], c2 * sm.d2[i]));
+          if (nz) xe = fmaf(su, __ldg(nz + i), xe);
+          sm.xcur[i] = xe;
+        }
+      }
     } else if (sa.sampler == BESO_SAMPLER_DPMPP_2M) {   // gc_sampling.py:726-735; d2 keeps old_denoised
       const float ca = sa.ca[step], ce = sa.ce[step], c1 = sa.c1[step], c2 = sa.c2[step];
       for (int i = threadIdx.x; i < n; i += kThreads) {

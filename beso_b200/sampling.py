@@ -288,13 +288,191 @@ def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=
     return action
 
 
+# ---- second-order single-step samplers as a two-stage coefficient program (BESO_SAMPLER_TWO_STAGE) ---------------
+# Every step is  D1 = model(x, sigma_i);  single-stage: x = a1 x + b1 D1 + su n_i;  two-stage: u = a1 x + b1 D1,
+# D2 = model(u, sigma_b), x = a2 x + b2 u + c2 D2 + su n_i.  The rows below are [sigma_b, a1, b1, a2, b2, c2, su, 0],
+# derived in float64 from the fp32 noise levels with the reference's formulas.
+def _euler_row(sigma, target, su=0.0):
+    dt = target - sigma                                    # x + (x - D)/sigma * dt
+    return [0.0, 1.0 + dt / sigma, -dt / sigma, 0.0, 0.0, 0.0, su, 0.0]
+
+
+def _dpm2_row(sigma, target, su=0.0):
+    """DPM-Solver-2 step from sigma to target (gc_sampling.py:362-370, 400-408)."""
+    mid = math.exp(0.5 * (math.log(sigma) + math.log(target)))          # log-space lerp at 0.5
+    dt1, dt2 = mid - sigma, target - sigma
+    return [mid, 1.0 + dt1 / sigma, -dt1 / sigma, 1.0, dt2 / mid, -dt2 / mid, su, 0.0]
+
+
+def _dpmpp2s_row(sigma, target, su=0.0):
+    """DPM-Solver++(2S) step from sigma to target (gc_sampling.py:958-964, 1004-1011), r = 1/2."""
+    t, t_next = -math.log(sigma), -math.log(target)
+    h = t_next - t
+    s = t + 0.5 * h
+    return [math.exp(-s), math.exp(-s) / math.exp(-t), -math.expm1(-h * 0.5), math.exp(-t_next) / math.exp(-t), 0.0,
+            -math.expm1(-h), su, 0.0]
+
+
+def two_stage_coefficients(kind: str, sigmas: torch.Tensor, eta: float = 1.0) -> torch.Tensor:
+    s = [float(v) for v in sigmas.detach().float().cpu().tolist()]
+    rows = []
+    for i in range(len(s) - 1):
+        if kind in ("dpm_2", "dpmpp_2s"):
+            step = _dpm2_row if kind == "dpm_2" else _dpmpp2s_row
+            rows.append(_euler_row(s[i], s[i + 1]) if s[i + 1] == 0 else step(s[i], s[i + 1]))
+        elif kind in ("dpm_2_ancestral", "dpmpp_2s_ancestral"):
+            down, up = get_ancestral_step(s[i], s[i + 1], eta=eta)
+            step = _dpm2_row if kind == "dpm_2_ancestral" else _dpmpp2s_row
+            rows.append(_euler_row(s[i], down, 0.0) if down == 0 else step(s[i], down, up))
+        else:
+            raise ValueError(f"unknown two-stage sampler {kind!r}")
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+def _two_stage(kind, model, state, action, goal, sigmas, extra_args, callback, eta, noise, draws):
+    """Fused path of the four samplers; ``draws`` = steps for which the reference calls randn_like (in order)."""
+    coef = two_stage_coefficients(kind, sigmas, eta)
+    n = len(sigmas) - 1
+    if callback is not None or extra_args or _fusable(model) is None or not action.is_cuda or not (2 <= len(sigmas) <= 129):
+        return None
+    if noise is None and any(draws):
+        noise = torch.zeros((n,) + tuple(action.shape), device=action.device, dtype=torch.float32)
+        for i in range(n):
+            if draws[i]:
+                noise[i] = torch.randn_like(action)
+    return _try_fused("two_stage", model, state, action, goal, sigmas, None, extra_args, callback, 0.0, coef=coef, noise=noise)
+
+
+@torch.no_grad()
+def sample_dpm_2(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, rng_parity=False):
+    """DPM-Solver-2 (gc_sampling.py:317-377), s_churn = 0 in the fused path; the last step is an Euler step."""
+    n = len(sigmas) - 1
+    if not s_churn and scaler is None:
+        fused = _two_stage("dpm_2", model, state, action, goal, sigmas, extra_args, callback, 1.0, None, [False] * n)
+        if fused is not None:
+            if rng_parity:                                  # the reference draws eps every step even when unused
+                for _ in range(n):
+                    torch.randn_like(action)
+            return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    for i in range(n):
+        gamma = _gamma(s_churn, n, sigmas[i], s_tmin, s_tmax)
+        eps = torch.randn_like(action) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * ones, **extra_args)
+        d = to_d(action, sigma_hat, denoised)
+        if callback is not None:
+            callback({"action": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        if sigmas[i + 1] == 0:
+            action = action + d * (sigmas[i + 1] - sigma_hat)
+        else:
+            sigma_mid = sigma_hat.log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            action_2 = action + d * (sigma_mid - sigma_hat)
+            denoised_2 = model(state, action_2, goal, sigma_mid * ones, **extra_args)
+            action = action + to_d(action_2, sigma_mid, denoised_2) * (sigmas[i + 1] - sigma_hat)
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                           eta=1.0, noise=None):
+    """Ancestral sampling with DPM-Solver-2 steps (gc_sampling.py:380-413): noise is drawn on the two-stage steps."""
+    n = len(sigmas) - 1
+    downs = [float(get_ancestral_step(float(sigmas[i]), float(sigmas[i + 1]), eta=eta)[0]) for i in range(n)]
+    if scaler is None:
+        fused = _two_stage("dpm_2_ancestral", model, state, action, goal, sigmas, extra_args, callback, eta, noise,
+                           [d != 0 for d in downs])
+        if fused is not None:
+            return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    for i in range(n):
+        denoised = model(state, action, goal, sigmas[i] * ones, **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        d = to_d(action, sigmas[i], denoised)
+        if sigma_down == 0:
+            action = action + d * (sigma_down - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            action_2 = action + d * (sigma_mid - sigmas[i])
+            denoised_2 = model(state, action_2, goal, sigma_mid * ones, **extra_args)
+            action = action + to_d(action_2, sigma_mid, denoised_2) * (sigma_down - sigmas[i])
+            action = action + (noise[i] if noise is not None else torch.randn_like(action)) * sigma_up
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+def _dpmpp_2s_loop(model, state, action, goal, sigmas, scaler, extra_args, callback, eta, s_noise, noise, ancestral):
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()              # noqa: E731
+    t_fn = lambda sigma: sigma.log().neg()          # noqa: E731
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * ones, **extra_args)
+        target, sigma_up = (get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta) if ancestral else (sigmas[i + 1], 0.0))
+        if callback is not None:
+            callback({"action": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        if target == 0:
+            action = action + to_d(action, sigmas[i], denoised) * (target - sigmas[i])
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(target)
+            h = t_next - t
+            s = t + 0.5 * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * action - (-h * 0.5).expm1() * denoised
+            denoised_2 = model(state, x_2, goal, sigma_fn(s) * ones, **extra_args)
+            action = (sigma_fn(t_next) / sigma_fn(t)) * action - (-h).expm1() * denoised_2
+        if ancestral:                                       # the reference draws noise on EVERY step (sigma_up = 0 on the last)
+            action = action + (noise[i] if noise is not None else torch.randn_like(action)) * s_noise * sigma_up
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+@torch.no_grad()
+def sample_dpmpp_2s(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.0):
+    """DPM-Solver++(2S) (gc_sampling.py:928-967)."""
+    if scaler is None:
+        fused = _two_stage("dpmpp_2s", model, state, action, goal, sigmas, extra_args, callback, eta, None,
+                           [False] * (len(sigmas) - 1))
+        if fused is not None:
+            return fused
+    return _dpmpp_2s_loop(model, state, action, goal, sigmas, scaler, extra_args, callback, eta, 1.0, None, False)
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                              eta=1.0, s_noise=1.0, noise_sampler=None, noise=None):
+    """Ancestral sampling with DPM-Solver++(2S) steps (gc_sampling.py:970-1016); default noise sampler only."""
+    if scaler is None and noise_sampler is None and s_noise == 1.0:
+        fused = _two_stage("dpmpp_2s_ancestral", model, state, action, goal, sigmas, extra_args, callback, eta, noise,
+                           [True] * (len(sigmas) - 1))
+        if fused is not None:
+            return fused
+    if noise_sampler is not None:
+        raise NotImplementedError("custom noise samplers are not supported")
+    return _dpmpp_2s_loop(model, state, action, goal, sigmas, scaler, extra_args, callback, eta, s_noise, noise, True)
+
+
 SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "euler_ancestral": sample_euler_ancestral,
-            "dpmpp_2m": sample_dpmpp_2m}
+            "dpmpp_2m": sample_dpmpp_2m, "dpm": sample_dpm_2, "ancestral": sample_dpm_2_ancestral,
+            "dpmpp_2s": sample_dpmpp_2s, "dpmpp_2s_ancestral": sample_dpmpp_2s_ancestral}
 
 
 def n_model_evals(sampler: str, sigmas) -> int:
-    """Model evaluations per sequence for one loop (Heun: 2 per step, 1 on a final sigma = 0 step)."""
+    """Model evaluations per sequence for one loop (second-order single-step samplers: 2 per step, 1 on a final
+    sigma = 0 step; the ancestral variants also take a single evaluation when sigma_down = 0)."""
     n = len(sigmas) - 1
-    if sampler == "heun":
+    if sampler in ("heun", "dpm", "dpmpp_2s"):
         return 2 * n - (1 if float(sigmas[-1]) == 0.0 else 0)
+    if sampler in ("ancestral", "dpmpp_2s_ancestral"):
+        return n + sum(1 for i in range(n) if float(get_ancestral_step(float(sigmas[i]), float(sigmas[i + 1]))[0]) != 0.0)
     return n

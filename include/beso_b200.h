@@ -53,7 +53,10 @@ enum {
   BESO_SAMPLER_EULER = 1, /* gc_sampling.py:167-213 (s_churn = 0) */
   BESO_SAMPLER_HEUN = 2,  /* gc_sampling.py:259-314 (s_churn = 0) */
   BESO_SAMPLER_EULER_ANCESTRAL = 3, /* gc_sampling.py:216-256; needs beso_sample_loop_noise */
-  BESO_SAMPLER_DPMPP_2M = 4 /* gc_sampling.py:703-736 (DPM-Solver++(2M)); needs its coefficients in coef_host */
+  BESO_SAMPLER_DPMPP_2M = 4, /* gc_sampling.py:703-736 (DPM-Solver++(2M)); needs its coefficients in coef_host */
+  BESO_SAMPLER_TWO_STAGE = 5 /* generic single-step second-order sampler as a coefficient program: sample_dpm_2
+                                (:317-377), sample_dpm_2_ancestral (:380-413), sample_dpmpp_2s (:928-967),
+                                sample_dpmpp_2s_ancestral (:970-1016) */
 };
 
 /* flags */
@@ -146,7 +149,13 @@ int beso_sample_loop(beso_plan* plan, int mode, int sampler, const float* sigmas
  * BESO_SAMPLER_DPMPP_2M = sample_dpmpp_2m (gc_sampling.py:703-736): coef_host holds 4*(n_sigmas-1) fp32, per step
  *   [sigma_fn(t_next)/sigma_fn(t), expm1(-h), 1 + 1/(2r), 1/(2r)] evaluated by the caller with the reference's fp32
  *   tensor ops; the last two are 0 for the first-order steps (the first step and a step onto sigma = 0).
- *   noise_dev is not used. */
+ *   noise_dev is not used.
+ * BESO_SAMPLER_TWO_STAGE: every step is   D1 = model(x, sigma_i);   if sigma_b == 0:  x = a1 x + b1 D1 + su noise_i
+ *   else  u = a1 x + b1 D1;  D2 = model(u, sigma_b);  x = a2 x + b2 u + c2 D2 + su noise_i.
+ *   coef_host holds 8*(n_sigmas-1) fp32, per step [sigma_b, a1, b1, a2, b2, c2, su, 0], computed by the caller from
+ *   the sampler's formulas (beso_b200/sampling.py: dpm_2, dpm_2_ancestral, dpmpp_2s, dpmpp_2s_ancestral);
+ *   noise_dev[i] is read only where su != 0.  The kernel applies the combined coefficients, so results agree
+ *   with the reference's step-by-step arithmetic to fp32 rounding, not bit for bit. */
 int beso_sample_loop_noise(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
                            const float* coef_host, const float* state_dev, const float* goal_dev,
                            float* x_inout_dev, const float* noise_dev, int B, int t, uint32_t flags,

@@ -322,6 +322,77 @@ def sample_dpmpp_2m(sd, cfg, state, action, goal, sigmas, cond_lambda=None):
     return action
 
 
+# gc_sampling.py:317-377 (s_churn = 0)
+def sample_dpm_2(sd, cfg, state, action, goal, sigmas, cond_lambda=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        sigma_hat = sigmas[i] * 1.0
+        denoised = model(state, action, goal, sigma_hat * s_in)
+        d = to_d(action, sigma_hat, denoised)
+        if sigmas[i + 1] == 0:
+            action = action + d * (sigmas[i + 1] - sigma_hat)
+        else:
+            sigma_mid = sigma_hat.log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            dt_1 = sigma_mid - sigma_hat
+            dt_2 = sigmas[i + 1] - sigma_hat
+            action_2 = action + d * dt_1
+            denoised_2 = model(state, action_2, goal, sigma_mid * s_in)
+            d_2 = to_d(action_2, sigma_mid, denoised_2)
+            action = action + d_2 * dt_2
+    return action
+
+
+# gc_sampling.py:380-413
+def sample_dpm_2_ancestral(sd, cfg, state, action, goal, sigmas, cond_lambda=None, eta=1.0, noise=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        d = to_d(action, sigmas[i], denoised)
+        if sigma_down == 0:
+            action = action + d * (sigma_down - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            dt_1 = sigma_mid - sigmas[i]
+            dt_2 = sigma_down - sigmas[i]
+            action_2 = action + d * dt_1
+            denoised_2 = model(state, action_2, goal, sigma_mid * s_in)
+            d_2 = to_d(action_2, sigma_mid, denoised_2)
+            action = action + d_2 * dt_2
+            action = action + (noise[i] if noise is not None else torch.randn_like(action)) * sigma_up
+    return action
+
+
+# gc_sampling.py:928-967 and 970-1016 (default noise sampler, s_noise = 1)
+def sample_dpmpp_2s(sd, cfg, state, action, goal, sigmas, cond_lambda=None, eta=1.0, ancestral=False, noise=None):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()              # noqa: E731
+    t_fn = lambda sigma: sigma.log().neg()          # noqa: E731
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in)
+        if ancestral:
+            target, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        else:
+            target, sigma_up = sigmas[i + 1], 0.0
+        if target == 0:
+            d = to_d(action, sigmas[i], denoised)
+            action = action + d * (target - sigmas[i])
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(target)
+            r = 1 / 2
+            h = t_next - t
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * action - (-h * r).expm1() * denoised
+            denoised_2 = model(state, x_2, goal, sigma_fn(s) * s_in)
+            action = (sigma_fn(t_next) / sigma_fn(t)) * action - (-h).expm1() * denoised_2
+        if ancestral:
+            action = action + (noise[i] if noise is not None else torch.randn_like(action)) * 1.0 * sigma_up
+    return action
+
+
 # gc_sampling.py:259-314
 def sample_heun(sd, cfg, state, action, goal, sigmas, cond_lambda=None,
                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, eps_list=None):

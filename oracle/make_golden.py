@@ -164,6 +164,25 @@ def gen_ancestral(ns):
     for n in (1, 3, 5):
         arrays[f"dpmpp_2m_{n}"] = gs.sample_dpmpp_2m(m, x["state"], x_t, x["goal"], arrays[f"sigmas_{n}"], disable=True)
     arrays["dpmpp_2m_karras_4"] = gs.sample_dpmpp_2m(m, x["state"], x_t, x["goal"], sigk, disable=True)
+    # second-order single-step samplers (dpm_2, dpm_2_ancestral, dpmpp_2s, dpmpp_2s_ancestral)
+    for tag, sig in (("3", arrays["sigmas_3"]), ("5", arrays["sigmas_5"]), ("karras_4", sigk)):
+        n = len(sig) - 1
+        torch.manual_seed(7200)                    # sample_dpm_2 draws (and discards) eps every step
+        arrays[f"dpm_2_{tag}"] = gs.sample_dpm_2(m, x["state"], x_t, x["goal"], sig, disable=True)
+        arrays[f"dpmpp_2s_{tag}"] = gs.sample_dpmpp_2s(m, x["state"], x_t, x["goal"], sig, disable=True)
+        torch.manual_seed(7300 + n)
+        arrays[f"dpm_2_ancestral_{tag}"] = gs.sample_dpm_2_ancestral(m, x["state"], x_t, x["goal"], sig, disable=True)
+        torch.manual_seed(7300 + n)
+        nz = torch.zeros((n,) + tuple(x_t.shape))
+        for i in range(n):
+            down, _ = gs.get_ancestral_step(sig[i], sig[i + 1])
+            if down != 0:
+                nz[i] = torch.randn_like(x_t)
+        arrays[f"noise_dpm2a_{tag}"] = nz
+        torch.manual_seed(7400 + n)
+        arrays[f"dpmpp_2s_ancestral_{tag}"] = gs.sample_dpmpp_2s_ancestral(m, x["state"], x_t, x["goal"], sig, disable=True)
+        torch.manual_seed(7400 + n)
+        arrays[f"noise_2sa_{tag}"] = torch.stack([torch.randn_like(x_t) for _ in range(n)])
     save("samplers_ancestral_K256", cfg, seed, sd, **arrays)
 
 

@@ -123,6 +123,22 @@ def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
     stepwise = sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], g["sigmas_5"], callback=lambda d: None)
     torch.testing.assert_close(stepwise, sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], a["sigmas_5"]),
                                rtol=1e-4, atol=1e-5)
+    # second-order single-step samplers: one launch each (two-stage coefficient program), reference goldens
+    second_order = {"dpm_2": (sampling.sample_dpm_2, None), "dpmpp_2s": (sampling.sample_dpmpp_2s, None),
+                    "dpm_2_ancestral": (sampling.sample_dpm_2_ancestral, "noise_dpm2a_"),
+                    "dpmpp_2s_ancestral": (sampling.sample_dpmpp_2s_ancestral, "noise_2sa_")}
+    for kind, (fn, noise_key) in second_order.items():
+        for tag in ("3", "5", "karras_4"):
+            kw = {"noise": g[noise_key + tag]} if noise_key else {}
+            launches = _lib.lib().beso_kernel_launches()
+            got = fn(m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{tag}"], **kw)
+            assert _lib.lib().beso_kernel_launches() == launches + 1, kind
+            tol = TOL[mode] if mode == "fast" else dict(rtol=1e-3, atol=2e-5)   # combined coefficients: fp32 rounding
+            torch.testing.assert_close(got.cpu(), a[f"{kind}_{tag}"], **tol)
+        # step by step (callback) == fused
+        kw = {"noise": g[noise_key + "5"]} if noise_key else {}
+        stepwise = fn(m, g["state"], g["x_t"], g["goal"], g["sigmas_5"], callback=lambda d: None, **kw)
+        torch.testing.assert_close(stepwise, fn(m, g["state"], g["x_t"], g["goal"], a["sigmas_5"], **kw), rtol=1e-4, atol=2e-5)
     # classifier-free guidance wrapper goes through the same launch
     from oracle import beso_oracle as O
     w = ClassifierFreeSampleModel(m, cond_lambda=2.0)

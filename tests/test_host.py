@@ -218,3 +218,25 @@ def test_sample_density_matches_reference_formulas():
     agent.sigma_sample_density_type = "nope"
     with pytest.raises(ValueError):
         agent.make_sample_density()
+
+
+def test_two_stage_coefficient_rows():
+    """[sigma_b, a1, b1, a2, b2, c2, su, 0] per step: last step onto sigma = 0 is a single-stage Euler step, the
+    ancestral variants carry sigma_up, and the agent dispatches the reference's sampler names."""
+    sig = sampling.get_sigmas_exponential(4, 0.005, 1.0)
+    for kind in ("dpm_2", "dpmpp_2s", "dpm_2_ancestral", "dpmpp_2s_ancestral"):
+        coef = sampling.two_stage_coefficients(kind, sig)
+        assert coef.shape == (4, 8)
+        assert float(coef[-1, 0]) == 0.0                                   # last step: one evaluation
+        assert all(float(coef[i, 0]) > 0.0 for i in range(3))              # two evaluations otherwise
+        assert (coef[:, 6] != 0).any().item() == kind.endswith("ancestral")
+        # the last step lands on the denoised sample: x = 0 * x + 1 * D
+        assert float(coef[-1, 1]) == pytest.approx(0.0, abs=1e-6) and float(coef[-1, 2]) == pytest.approx(1.0, abs=1e-6)
+    mid = float(sampling.two_stage_coefficients("dpm_2", sig)[0, 0])
+    assert mid == pytest.approx((float(sig[0]) * float(sig[1])) ** 0.5, rel=1e-6)   # log-space midpoint
+    with pytest.raises(ValueError):
+        sampling.two_stage_coefficients("nope", sig)
+    for name in ("dpm", "ancestral", "dpmpp_2s", "dpmpp_2s_ancestral", "dpmpp_2m", "euler_ancestral"):
+        assert name in sampling.SAMPLERS
+    s10 = sampling.get_sigmas_exponential(10, 0.005, 1.0)
+    assert sampling.n_model_evals("dpm", s10) == 19 and sampling.n_model_evals("ancestral", s10) == 19

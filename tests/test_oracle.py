@@ -159,3 +159,46 @@ def test_oracle_bitexact_on_shipped_checkpoints(env):
             want = ns.gc_sampling.sample_ddim(m, x["state"], x["noise"], x["goal"], sig, disable=True)
             got = O.sample_ddim(sd, oc, x["state"], x["noise"], x["goal"], sig)
             assert torch.equal(want, got), p
+
+
+def _run_two_stage_program(model, state, x, goal, sigmas, coef, noise):
+    """CPU emulation of BESO_SAMPLER_TWO_STAGE (include/beso_b200.h) on top of any model(state, x, goal, sigma)."""
+    ones = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        sb, a1, b1, a2, b2, c2, su, _ = [float(v) for v in coef[i]]
+        d1 = model(state, x, goal, sigmas[i] * ones)
+        nz = noise[i] * su if su != 0.0 else 0.0
+        if sb == 0.0:
+            x = a1 * x + b1 * d1 + nz
+        else:
+            u = a1 * x + b1 * d1
+            d2 = model(state, u, goal, torch.tensor(sb) * ones)
+            x = a2 * x + b2 * u + c2 * d2 + nz
+    return x
+
+
+def test_second_order_samplers_match_golden_and_their_coefficient_programs():
+    """dpm_2 / dpm_2_ancestral / dpmpp_2s / dpmpp_2s_ancestral: the oracle restatements reproduce the real reference,
+    and the two-stage coefficient programs the CUDA kernels execute (beso_b200.sampling.two_stage_coefficients)
+    describe the same samplers."""
+    from beso_b200 import sampling
+    cfg, meta, a = load_golden("samplers_ancestral_K256")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    model = lambda s, x, g, sig: O.denoiser_forward(sd, oc, s, x, g, sig)     # noqa: E731
+    with torch.no_grad():
+        for tag in ("3", "5", "karras_4"):
+            sig = a[f"sigmas_{tag}"]
+            zeros = torch.zeros((len(sig) - 1,) + tuple(a["x_t"].shape))
+            cases = {
+                "dpm_2": (O.sample_dpm_2(sd, oc, a["state"], a["x_t"], a["goal"], sig), zeros),
+                "dpmpp_2s": (O.sample_dpmpp_2s(sd, oc, a["state"], a["x_t"], a["goal"], sig), zeros),
+                "dpm_2_ancestral": (O.sample_dpm_2_ancestral(sd, oc, a["state"], a["x_t"], a["goal"], sig,
+                                                             noise=a[f"noise_dpm2a_{tag}"]), a[f"noise_dpm2a_{tag}"]),
+                "dpmpp_2s_ancestral": (O.sample_dpmpp_2s(sd, oc, a["state"], a["x_t"], a["goal"], sig, ancestral=True,
+                                                         noise=a[f"noise_2sa_{tag}"]), a[f"noise_2sa_{tag}"]),
+            }
+            for kind, (got, noise) in cases.items():
+                torch.testing.assert_close(got, a[f"{kind}_{tag}"], **TOL)
+                prog = _run_two_stage_program(model, a["state"], a["x_t"], a["goal"], sig,
+                                              sampling.two_stage_coefficients(kind, sig), noise)
+                torch.testing.assert_close(prog, a[f"{kind}_{tag}"], rtol=1e-4, atol=2e-6)
