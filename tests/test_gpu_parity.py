@@ -147,6 +147,17 @@ def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
         want = O.sample_euler_ancestral(O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg), a["state"], a["x_t"],
                                         a["goal"], a["sigmas_3"], cond_lambda=2.0, noise=a["noise_3"])
     torch.testing.assert_close(got.cpu(), want, **TOL[mode])
+    # ... and so does a two-stage program: cond / uncond mix on both evaluations of every step, ragged batch
+    x = synthetic_inputs(cfg, 37, seed=77)
+    gx = cuda(x, cuda_device)
+    sig = sampling.get_sigmas_exponential(4, 0.005, 1.0)
+    nz = torch.randn((4, 37, cfg.window, cfg.act_dim), generator=torch.Generator().manual_seed(9))
+    got = sampling.sample_dpm_2_ancestral(w, gx["state"], gx["noise"], gx["goal"], sig, noise=nz.to(cuda_device))
+    with torch.no_grad():
+        want = O.sample_dpm_2_ancestral(O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg), x["state"], x["noise"],
+                                        x["goal"], sig, cond_lambda=2.0, noise=nz)
+    # fast mode: the lambda = 2 mix D_u + 2 (D_c - D_u) carries up to 3x the single-evaluation error
+    torch.testing.assert_close(got.cpu(), want, **(dict(rtol=1e-2, atol=8e-3) if mode == "fast" else dict(rtol=1e-3, atol=2e-5)))
 
 
 @pytest.mark.parametrize("mode", ["precise", "fast"])
