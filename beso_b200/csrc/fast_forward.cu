@@ -1,10 +1,10 @@
-// FAST mode: GCDenoiser -> DiffusionGPT forward and the DDIM / Euler / Heun sample loop as ONE
-// persistent, warp-specialised sm_100a kernel.  fp16 operands on tcgen05 tensor cores (bf16 for the
+// FAST mode: GCDenoiser -> DiffusionGPT forward and the sample loop (DDIM / Euler / Heun / Euler-ancestral /
+// DPM-Solver++(2M) / two-stage coefficient programs) as ONE persistent, warp-specialised sm_100a kernel.  fp16 operands on tcgen05 tensor cores (bf16 for the
 // embedding GEMM), fp32 accumulation in TMEM, fp32 LayerNorm statistics / softmax / residual /
 // pre-conditioning, packed-fp16 GELU and LayerNorm scaling.
 //
 // Reference semantics (beso/agents/diffusion_agents/k_diffusion/): score_wrappers.py:31-43,81-96;
-// score_gpts.py:50-80,96-115,272-358; gc_sampling.py:167-213,259-314,895-924;
+// score_gpts.py:50-80,96-115,272-358; gc_sampling.py:167-413,703-736,895-1016;
 // classifier_free_sampler.py:35-49.
 //
 // Design (DESIGN.md has the long form)
@@ -221,11 +221,6 @@ __device__ __forceinline__ void spin_wait_cluster(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void spin_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   wait_timeout(bar, parity);
-}
-// whole-warp wait with a single polling lane
-__device__ __forceinline__ void warp_wait(int lane, uint32_t bar, uint32_t parity) {
-  if (lane == 0) spin_wait(bar, parity);
-  __syncwarp();
 }
 
 // erf-GELU without erff() and without the special-function unit, two elements per instruction in packed

@@ -250,11 +250,6 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
 // read-only data (bias vectors): not volatile, no memory clobber -- the compiler may hoist / schedule these
 // freely between the (ordered) stores of the surrounding code
 __device__ __forceinline__ uint4 lds128_ro(uint32_t addr) {
@@ -265,11 +260,6 @@ __device__ __forceinline__ uint4 lds128_ro(uint32_t addr) {
 __device__ __forceinline__ float4 lds128f_ro(uint32_t addr) {
   float4 v;
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 // store 8 consecutive K elements (one 16-byte chunk) of one row as fp16
