@@ -16,10 +16,11 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbeso_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MODE_PRECISE, MODE_FAST = 0, 1
-SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN, SAMPLER_EULER_ANCESTRAL, SAMPLER_DPMPP_2M, SAMPLER_TWO_STAGE = 0, 1, 2, 3, 4, 5
+SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN, SAMPLER_EULER_ANCESTRAL, SAMPLER_DPMPP_2M, SAMPLER_TWO_STAGE, SAMPLER_LMS = 0, 1, 2, 3, 4, 5, 6
 FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_TF32 = 1, 2, 4, 8, 16
 SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN, "euler_ancestral": SAMPLER_EULER_ANCESTRAL,
-               "dpmpp_2m": SAMPLER_DPMPP_2M, "two_stage": SAMPLER_TWO_STAGE}
+               "dpmpp_2m": SAMPLER_DPMPP_2M, "two_stage": SAMPLER_TWO_STAGE,
+               "lms": SAMPLER_LMS}
 MODE_IDS = {"precise": MODE_PRECISE, "fast": MODE_FAST}
 
 EXPORTS = [

@@ -90,6 +90,8 @@ class BesoAgent:
             return sampling.sample_euler(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "ddim":
             return sampling.sample_ddim(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "lms":                          # beso_agent.py:419-420
+            return sampling.sample_lms(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "dpm":                          # beso_agent.py:434-435 (dispatched without the scaler)
             return sampling.sample_dpm_2(self.model, state, x_t, goal, sigmas, disable=True)
         if sampler_type == "ancestral":                    # beso_agent.py:428-429

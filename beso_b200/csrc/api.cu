@@ -126,11 +126,11 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
 }
 
 static int make_sample_args(int sampler, const float* sig, int n_sigmas, const float* coef, SampleArgs* sa) {
-  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_TWO_STAGE) { set_error("unknown sampler"); return BESO_E_INVALID; }
-  if ((sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_DPMPP_2M || sampler == BESO_SAMPLER_TWO_STAGE) && !coef) {
-    set_error("euler_ancestral / dpmpp_2m / two-stage samplers need their per-step coefficients (coef_host)"); return BESO_E_INVALID;
+  if (sampler < BESO_SAMPLER_DDIM || sampler > BESO_SAMPLER_LMS) { set_error("unknown sampler"); return BESO_E_INVALID; }
+  if (sampler >= BESO_SAMPLER_EULER_ANCESTRAL && !coef) {
+    set_error("euler_ancestral / dpmpp_2m / lms / two-stage samplers need their per-step coefficients (coef_host)"); return BESO_E_INVALID;
   }
-  const int cstride = sampler == BESO_SAMPLER_TWO_STAGE ? 8 : (sampler == BESO_SAMPLER_DPMPP_2M ? 4 : 2);
+  const int cstride = sampler == BESO_SAMPLER_TWO_STAGE ? 8 : ((sampler == BESO_SAMPLER_DPMPP_2M || sampler == BESO_SAMPLER_LMS) ? 4 : 2);
   if (!sig || n_sigmas < 2 || n_sigmas - 1 > kMaxSteps) { set_error("n_sigmas must be in [2, 129]"); return BESO_E_INVALID; }
   memset(sa, 0, sizeof(*sa));
   sa->n_steps = n_sigmas - 1;
@@ -305,6 +305,9 @@ int beso_sample_loop_noise(beso_plan* p, int mode, int sampler, const float* sig
     bool needs_noise = false;
     for (int i = 0; i < sa.n_steps; ++i) needs_noise |= (sampler == BESO_SAMPLER_TWO_STAGE ? sa.su[i] != 0.f : sa.ca[i] > 0.f);
     if (needs_noise && !noise) { set_error("this sampler needs the per-step noise (beso_sample_loop_noise)"); return BESO_E_INVALID; }
+  }
+  if (sampler == BESO_SAMPLER_LMS && mode == BESO_MODE_FAST && (flags & BESO_FLAG_CFG)) {
+    set_error("lms with classifier-free guidance is not available in fast mode (history buffers)"); return BESO_E_UNSUPPORTED;
   }
   sa.noise = noise;
   sa.noise_stride = (long long)B * t * p->desc.act_dim;

@@ -901,6 +901,14 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
           p.out[(size_t)seq0 * p.t * p.act + i] = D;
         } else if (sa.sampler == BESO_SAMPLER_DDIM) {
           xcur[i] = __fsub_rn(__fmul_rn(sa.ca[step], xcur[i]), __fmul_rn(sa.ce[step], D));
+        } else if (sa.sampler == BESO_SAMPLER_LMS) {                  // gc_sampling.py:454-465; history in d1, x2, dU
+          const float d = __fdiv_rn(__fsub_rn(xcur[i], D), s_hat);
+          float acc = __fmul_rn(sa.ca[step], d);
+          if (sa.ce[step] != 0.0f) acc = __fadd_rn(acc, __fmul_rn(sa.ce[step], d1[i]));
+          if (sa.c1[step] != 0.0f) acc = __fadd_rn(acc, __fmul_rn(sa.c1[step], x2[i]));
+          if (sa.c2[step] != 0.0f) acc = __fadd_rn(acc, __fmul_rn(sa.c2[step], dU[i]));
+          xcur[i] = __fadd_rn(xcur[i], acc);
+          dU[i] = x2[i]; x2[i] = d1[i]; d1[i] = d;
         } else if (sa.sampler == BESO_SAMPLER_TWO_STAGE) {            // coefficient program (include/beso_b200.h)
           const float su = sa.su[step];
           const float nz = su != 0.0f ? __ldg(sa.noise + (size_t)step * sa.noise_stride + (size_t)seq0 * p.t * p.act + i) : 0.f;

@@ -159,7 +159,7 @@ __device__ __noinline__ void attention_rows(const float* qkv, int ldq, int ns, i
 }
 
 struct Smem {
-  float *X, *Hb, *Big, *state, *goal, *xcur, *dC, *dU, *x2, *d1, *d2, *sig;
+  float *X, *Hb, *Big, *state, *goal, *xcur, *dC, *dU, *x2, *d1, *d2, *h3, *sig;
   int ldb;
 };
 
@@ -317,7 +317,7 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
   sm.state = take((size_t)S * t * m.obs);
   sm.goal = take((size_t)S * max(m.G, 1) * m.obs);
   const int nx = S * t * m.act;
-  sm.xcur = take(nx); sm.dC = take(nx); sm.dU = take(nx); sm.x2 = take(nx); sm.d1 = take(nx); sm.d2 = take(nx);
+  sm.xcur = take(nx); sm.dC = take(nx); sm.dU = take(nx); sm.x2 = take(nx); sm.d1 = take(nx); sm.d2 = take(nx); sm.h3 = take(nx);
   sm.sig = take(S);
   Ctx c{m, ns, t, T, ns * T};
 
@@ -345,6 +345,17 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
       const float ca = sa.ca[step], ce = sa.ce[step];
       for (int i = threadIdx.x; i < n; i += kThreads)
         sm.xcur[i] = __fsub_rn(__fmul_rn(ca, sm.xcur[i]), __fmul_rn(ce, sm.d1[i]));
+    } else if (sa.sampler == BESO_SAMPLER_LMS) {        // gc_sampling.py:454-465; history d_{i-1..i-3} in x2, d2, h3
+      const float c0 = sa.ca[step], c1 = sa.ce[step], c2 = sa.c1[step], c3 = sa.c2[step];
+      for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float d = __fdiv_rn(__fsub_rn(sm.xcur[i], sm.d1[i]), s_hat);
+        float acc = __fmul_rn(c0, d);
+        if (c1 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(c1, sm.x2[i]));
+        if (c2 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(c2, sm.d2[i]));
+        if (c3 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(c3, sm.h3[i]));
+        sm.xcur[i] = __fadd_rn(sm.xcur[i], acc);
+        sm.h3[i] = sm.d2[i]; sm.d2[i] = sm.x2[i]; sm.x2[i] = d;
+      }
     } else if (sa.sampler == BESO_SAMPLER_TWO_STAGE) {  // coefficient program (include/beso_b200.h)
       const float a1 = sa.ca[step], b1 = sa.ce[step], sb = sa.sigb[step], su = sa.su[step];
       const float* nz = su != 0.0f ? sa.noise + (size_t)step * sa.noise_stride + (size_t)seq0 * t * m.act : nullptr;
@@ -417,7 +428,7 @@ size_t simt_smem_bytes(const SimtModel& m, int t, int S, int* ldb_out) {
   const int ldb = round_ldb(4 * m.d);
   auto r4 = [](size_t n) { return (n + 3) & ~size_t(3); };
   size_t f = 2 * r4((size_t)S * T * m.d) + r4((size_t)S * T * ldb) + r4((size_t)S * t * m.obs) +
-             r4((size_t)S * (m.G > 0 ? m.G : 1) * m.obs) + 6 * r4((size_t)S * t * m.act) + r4(S);
+             r4((size_t)S * (m.G > 0 ? m.G : 1) * m.obs) + 7 * r4((size_t)S * t * m.act) + r4(S);
   if (ldb_out) *ldb_out = ldb;
   return f * sizeof(float);
 }

@@ -13,6 +13,7 @@ from typing import Optional
 
 import torch
 
+from . import _lib
 from .denoiser import GCDenoiser
 
 
@@ -462,8 +463,66 @@ def sample_dpmpp_2s_ancestral(model, state, action, goal, sigmas, scaler=None, e
     return _dpmpp_2s_loop(model, state, action, goal, sigmas, scaler, extra_args, callback, eta, s_noise, noise, True)
 
 
+def linear_multistep_coeff(order, t, i, j):
+    """Coefficient of the j-th derivative of the i-th step of a linear multistep method (gc_sampling.py:416-428):
+    the same scipy quadrature, with the same tolerance, as the reference."""
+    from scipy import integrate
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+def lms_coefficients(sigmas: torch.Tensor, order: int = 4) -> torch.Tensor:
+    """Per-step [c0, c1, c2, c3] of sample_lms; 0 for derivatives that do not exist yet."""
+    if order > 4:
+        raise ValueError("the fused linear multistep sampler supports order <= 4")
+    t = sigmas.detach().cpu().numpy()
+    rows = []
+    for i in range(len(t) - 1):
+        cur = min(i + 1, order)
+        rows.append([linear_multistep_coeff(cur, t, i, j) for j in range(cur)] + [0.0] * (4 - cur))
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+@torch.no_grad()
+def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, order=4):
+    """Linear multistep sampler (gc_sampling.py:431-468)."""
+    f = _fusable(model)
+    cfg_mix = f is not None and f[1] is not None
+    if scaler is None and order <= 4 and not (cfg_mix and f[0].resolved_mode() == _lib.MODE_FAST):
+        fused = _try_fused("lms", model, state, action, goal, sigmas, None, extra_args, callback, 0.0,
+                           coef=lms_coefficients(sigmas, order))
+        if fused is not None:
+            return fused
+    extra_args = {} if extra_args is None else extra_args
+    ones = action.new_ones([action.shape[0]])
+    sigmas_cpu = sigmas.detach().cpu().numpy()
+    ds = []
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * ones, **extra_args)
+        ds.append(to_d(action, sigmas[i], denoised))
+        if len(ds) > order:
+            ds.pop(0)
+        if callback is not None:
+            callback({"x": action, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sigmas_cpu, i, j) for j in range(cur_order)]
+        action = action + sum(coeff * d for coeff, d in zip(coeffs, reversed(ds)))
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
 SAMPLERS = {"ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "euler_ancestral": sample_euler_ancestral,
-            "dpmpp_2m": sample_dpmpp_2m, "dpm": sample_dpm_2, "ancestral": sample_dpm_2_ancestral,
+            "lms": sample_lms, "dpmpp_2m": sample_dpmpp_2m, "dpm": sample_dpm_2, "ancestral": sample_dpm_2_ancestral,
             "dpmpp_2s": sample_dpmpp_2s, "dpmpp_2s_ancestral": sample_dpmpp_2s_ancestral}
 
 

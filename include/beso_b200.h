@@ -54,6 +54,7 @@ enum {
   BESO_SAMPLER_HEUN = 2,  /* gc_sampling.py:259-314 (s_churn = 0) */
   BESO_SAMPLER_EULER_ANCESTRAL = 3, /* gc_sampling.py:216-256; needs beso_sample_loop_noise */
   BESO_SAMPLER_DPMPP_2M = 4, /* gc_sampling.py:703-736 (DPM-Solver++(2M)); needs its coefficients in coef_host */
+  BESO_SAMPLER_LMS = 6,      /* gc_sampling.py:416-468 (linear multistep, order <= 4); not with BESO_FLAG_CFG in fast mode */
   BESO_SAMPLER_TWO_STAGE = 5 /* generic single-step second-order sampler as a coefficient program: sample_dpm_2
                                 (:317-377), sample_dpm_2_ancestral (:380-413), sample_dpmpp_2s (:928-967),
                                 sample_dpmpp_2s_ancestral (:970-1016) */
@@ -150,6 +151,9 @@ int beso_sample_loop(beso_plan* plan, int mode, int sampler, const float* sigmas
  *   [sigma_fn(t_next)/sigma_fn(t), expm1(-h), 1 + 1/(2r), 1/(2r)] evaluated by the caller with the reference's fp32
  *   tensor ops; the last two are 0 for the first-order steps (the first step and a step onto sigma = 0).
  *   noise_dev is not used.
+ * BESO_SAMPLER_LMS = sample_lms (gc_sampling.py:431-468): x += c0 d_i + c1 d_{i-1} + c2 d_{i-2} + c3 d_{i-3} with
+ *   d = to_d(x, sigma_i, D); coef_host holds 4*(n_sigmas-1) fp32 = linear_multistep_coeff(min(i+1, order), ...)
+ *   (gc_sampling.py:416-428, scipy quad on the host), 0 for the derivatives that do not exist yet.
  * BESO_SAMPLER_TWO_STAGE: every step is   D1 = model(x, sigma_i);   if sigma_b == 0:  x = a1 x + b1 D1 + su noise_i
  *   else  u = a1 x + b1 D1;  D2 = model(u, sigma_b);  x = a2 x + b2 u + c2 D2 + su noise_i.
  *   coef_host holds 8*(n_sigmas-1) fp32, per step [sigma_b, a1, b1, a2, b2, c2, su, 0], computed by the caller from

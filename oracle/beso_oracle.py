@@ -322,6 +322,39 @@ def sample_dpmpp_2m(sd, cfg, state, action, goal, sigmas, cond_lambda=None):
     return action
 
 
+# gc_sampling.py:416-468
+def linear_multistep_coeff(order, t, i, j):
+    from scipy import integrate
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+def sample_lms(sd, cfg, state, action, goal, sigmas, cond_lambda=None, order=4):
+    model = _model(sd, cfg, cond_lambda)
+    s_in = action.new_ones([action.shape[0]])
+    sigmas_cpu = sigmas.detach().cpu().numpy()
+    ds = []
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in)
+        d = to_d(action, sigmas[i], denoised)
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sigmas_cpu, i, j) for j in range(cur_order)]
+        action = action + sum(coeff * d for coeff, d in zip(coeffs, reversed(ds)))
+    return action
+
+
 # gc_sampling.py:317-377 (s_churn = 0)
 def sample_dpm_2(sd, cfg, state, action, goal, sigmas, cond_lambda=None):
     model = _model(sd, cfg, cond_lambda)

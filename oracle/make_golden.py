@@ -164,6 +164,11 @@ def gen_ancestral(ns):
     for n in (1, 3, 5):
         arrays[f"dpmpp_2m_{n}"] = gs.sample_dpmpp_2m(m, x["state"], x_t, x["goal"], arrays[f"sigmas_{n}"], disable=True)
     arrays["dpmpp_2m_karras_4"] = gs.sample_dpmpp_2m(m, x["state"], x_t, x["goal"], sigk, disable=True)
+    # linear multistep (order 4 is reached on the 4th step)
+    sig6 = gs.get_sigmas_exponential(6, 0.005, 1.0)
+    arrays["sigmas_6"] = sig6
+    for tag, sig in (("3", arrays["sigmas_3"]), ("6", sig6), ("karras_4", sigk)):
+        arrays[f"lms_{tag}"] = gs.sample_lms(m, x["state"], x_t, x["goal"], sig, disable=True)
     # second-order single-step samplers (dpm_2, dpm_2_ancestral, dpmpp_2s, dpmpp_2s_ancestral)
     for tag, sig in (("3", arrays["sigmas_3"]), ("5", arrays["sigmas_5"]), ("karras_4", sigk)):
         n = len(sig) - 1

@@ -123,6 +123,12 @@ def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
     stepwise = sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], g["sigmas_5"], callback=lambda d: None)
     torch.testing.assert_close(stepwise, sampling.sample_dpmpp_2m(m, g["state"], g["x_t"], g["goal"], a["sigmas_5"]),
                                rtol=1e-4, atol=1e-5)
+    # linear multistep (orders 1..4): one launch, reference goldens
+    for tag in ("3", "6", "karras_4"):
+        launches = _lib.lib().beso_kernel_launches()
+        got = sampling.sample_lms(m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{tag}"])
+        assert _lib.lib().beso_kernel_launches() == launches + 1
+        torch.testing.assert_close(got.cpu(), a[f"lms_{tag}"], **TOL[mode])
     # second-order single-step samplers: one launch each (two-stage coefficient program), reference goldens
     second_order = {"dpm_2": (sampling.sample_dpm_2, None), "dpmpp_2s": (sampling.sample_dpmpp_2s, None),
                     "dpm_2_ancestral": (sampling.sample_dpm_2_ancestral, "noise_dpm2a_"),

@@ -202,3 +202,18 @@ def test_second_order_samplers_match_golden_and_their_coefficient_programs():
                 prog = _run_two_stage_program(model, a["state"], a["x_t"], a["goal"], sig,
                                               sampling.two_stage_coefficients(kind, sig), noise)
                 torch.testing.assert_close(prog, a[f"{kind}_{tag}"], rtol=1e-4, atol=2e-6)
+
+
+def test_lms_matches_golden():
+    """Linear multistep sampler (gc_sampling.py:416-468) of the real reference, orders 1..4."""
+    from beso_b200 import sampling
+    cfg, meta, a = load_golden("samplers_ancestral_K256")
+    sd, oc = O.as_module_params(golden_weights(cfg, meta)), to_oracle_cfg(cfg)
+    with torch.no_grad():
+        for tag in ("3", "6", "karras_4"):
+            got = O.sample_lms(sd, oc, a["state"], a["x_t"], a["goal"], a[f"sigmas_{tag}"])
+            torch.testing.assert_close(got, a[f"lms_{tag}"], **TOL)
+    coef = sampling.lms_coefficients(a["sigmas_6"])
+    assert coef.shape == (6, 4) and float(coef[0, 1]) == 0.0 and float(coef[2, 3]) == 0.0 and float(coef[3, 3]) != 0.0
+    t = a["sigmas_6"].numpy()
+    assert float(coef[4, 2]) == pytest.approx(O.linear_multistep_coeff(4, t, 4, 2), rel=1e-6)
