@@ -30,7 +30,7 @@ EXPORTS = [
     "beso_loss_fwd_bwd", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
     "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
-    "beso_opt_create", "beso_opt_destroy", "beso_opt_total", "beso_opt_step",
+    "beso_opt_create", "beso_opt_destroy", "beso_opt_total", "beso_opt_step", "beso_window_gather",
 ]
 
 
@@ -102,6 +102,7 @@ def _declare(lib):
     lib.beso_opt_total.argtypes = [vp]
     lib.beso_opt_total.restype = C.c_longlong
     lib.beso_opt_step.argtypes = [vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, f32, vp]
+    lib.beso_window_gather.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp]
 
 
 def lib():

@@ -182,9 +182,12 @@ class BesoAgent:
         loss + all gradients come from ONE call of the fused forward / backward, AdamW + EMA are ONE launch."""
         from .training import loss_and_flat_grad
         core = self._core()
-        state = self.scaler.scale_input(batch["observation"].to(self.device))
-        goal = self.scaler.scale_input(batch["goal_observation"].to(self.device))
-        action = self.scaler.scale_output(batch["action"].to(self.device))
+        if batch.get("scaled", False):                      # DeviceWindowDataset scaled while gathering (dataset.py)
+            state, goal, action = (batch[k].to(self.device) for k in ("observation", "goal_observation", "action"))
+        else:
+            state = self.scaler.scale_input(batch["observation"].to(self.device))
+            goal = self.scaler.scale_input(batch["goal_observation"].to(self.device))
+            action = self.scaler.scale_output(batch["action"].to(self.device))
         core.train()
         core.training = True
         noise = torch.randn_like(action)

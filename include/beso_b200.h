@@ -214,6 +214,20 @@ int beso_opt_step(beso_opt* opt, const float* flat_grad_dev, float* exp_avg_dev,
                   float* ema_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float ema_decay, float grad_scale, void* stream);
 
+/* Windowed batch gather from GPU-resident trajectories.  Replaces TrajectorySlicerDataset.__getitem__
+ * (beso/envs/dataloaders/trajectory_loader.py:160-197) + DataLoader collation + the host-to-device copy of
+ * BesoAgent.train_step's batch with one launch.  obs_dev (n_traj, t_max, obs_dim) and act_dev (n_traj, t_max, act_dim)
+ * are the padded trajectories; for sample b: traj_dev[b], start_dev[b] (window start) and goal_start_dev[b] (start of
+ * the future-observation window, < 0 = the reference's zeros placeholder).  goal_out_dev == NULL: no goal window.
+ * obs_scale_dev (4, obs_dim) / act_scale_dev (4, act_dim), each NULL or rows (sub, div, mul, add): the Scaler's
+ * scale_input / scale_output (beso/networks/scaler/scaler_class.py:79-112, 271-301) applied on the way as
+ * ((x - sub) / div) * mul + add, each step rounded to fp32 like the reference's elementwise ops.
+ * The caller guarantees start + window <= t_max and goal_start + goal_len <= t_max (beso_b200/dataset.py). */
+int beso_window_gather(const float* obs_dev, const float* act_dev, int n_traj, int t_max, int obs_dim, int act_dim,
+                       const int* traj_dev, const int* start_dev, const int* goal_start_dev, int window, int goal_len,
+                       float* state_out_dev, float* action_out_dev, float* goal_out_dev,
+                       const float* obs_scale_dev, const float* act_scale_dev, int B, void* stream);
+
 /* Introspection used by tests and bench.py. */
 int64_t beso_kernel_launches(void);                /* kernels launched by this library so far   */
 int beso_plan_rows_per_cta(beso_plan* plan, int mode, int t); /* sequences handled per CTA      */

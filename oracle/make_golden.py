@@ -233,9 +233,72 @@ def gen_loss(ns):
         save(name, cfg, seed, sd, **arrays)
 
 
+WINDOW_MODES = {
+    "plain": dict(window=5),
+    "future": dict(window=5, future_conditional=True, min_future_sep=1, future_seq_len=2),
+    "tail": dict(window=4, future_conditional=True, min_future_sep=0, future_seq_len=3, only_sample_tail=True),
+    "seq_end": dict(window=4, future_conditional=True, min_future_sep=0, future_seq_len=1, only_sample_seq_end=True),
+}
+
+
+def window_fixture_data():
+    """Padded toy trajectories with ragged lengths (one shorter than every window, one exactly a window long)."""
+    rs = np.random.RandomState(11)
+    lens = np.array([12, 3, 5, 9, 20, 4, 7], dtype=np.int64)
+    obs = rs.randn(len(lens), 20, 6).astype(np.float32)
+    act = rs.randn(len(lens), 20, 3).astype(np.float32)
+    for i, T in enumerate(lens):           # zero padding like the reference's padded datasets
+        obs[i, T:] = 0
+        act[i, T:] = 0
+    return obs, act, lens
+
+
+def reference_window_dataset(tl, obs, act, lens, **kw):
+    """The unmodified TrajectorySlicerDataset over a minimal TrajectoryDataset of the padded arrays."""
+    class Padded(tl.TrajectoryDataset):
+        def __init__(self):
+            self.obs, self.act = torch.from_numpy(obs), torch.from_numpy(act)
+            self.mask = torch.from_numpy((np.arange(obs.shape[1])[None] < lens[:, None]).astype(np.float32))
+
+        def __len__(self):
+            return len(lens)
+
+        def __getitem__(self, i):
+            return self.obs[i], self.act[i], self.mask[i]
+
+        def get_seq_length(self, i):
+            return int(lens[i])
+
+        def get_all_actions(self):
+            return torch.cat([self.act[i, :int(T)] for i, T in enumerate(lens)])
+    return tl.TrajectorySlicerDataset(Padded(), **kw)
+
+
+def gen_windows():
+    """tests/golden/windows.npz: batches of the reference's windowed dataset, every item in a seeded shuffled order."""
+    tl = ref_import.load_trajectory_loader()
+    obs, act, lens = window_fixture_data()
+    arrays = dict(obs=obs, act=act, lens=lens)
+    for mode, kw in WINDOW_MODES.items():
+        ds = reference_window_dataset(tl, obs, act, lens, **kw)
+        order = np.random.RandomState(5).permutation(len(ds))
+        np.random.seed(1234)
+        loader = torch.utils.data.DataLoader(torch.utils.data.Subset(ds, order.tolist()), batch_size=len(ds), shuffle=False)
+        (b,) = list(loader)
+        arrays[f"{mode}::order"] = order
+        arrays[f"{mode}::slices"] = np.array(ds.slices, dtype=np.int64)
+        for k, v in b.items():
+            arrays[f"{mode}::{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "windows.npz"), **arrays)
+    print("wrote windows.npz", {k: v.shape for k, v in arrays.items()})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "windows":         # dataset fixture: needs only trajectory_loader.py
+        gen_windows()
+        return
     ns = ref_import.load()
     if len(sys.argv) > 1 and sys.argv[1] == "ancestral":       # only the fixture added after the first set
         gen_ancestral(ns)

@@ -65,6 +65,23 @@ def load():
     return ns
 
 
+def load_trajectory_loader():
+    """The reference's beso/envs/dataloaders/trajectory_loader.py, loaded as a lone module by file path (its imports are
+    torch / numpy / tqdm only; going through the package would pull in the simulators)."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    import importlib.util
+    import itertools
+    import torch._utils
+    if not hasattr(torch._utils, "_accumulate"):   # private helper the module imports for its split function; removed
+        torch._utils._accumulate = itertools.accumulate  # from current torch, never used on the slicing path
+    path = os.path.join(REF_ROOT, "beso", "envs", "dataloaders", "trajectory_loader.py")
+    spec = importlib.util.spec_from_file_location("_beso_ref_trajectory_loader", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_reference_model(ns, cfg, attn_pdrop=0.0, resid_pdrop=0.0, goal_drop=0.0):
     """Builds the reference GCDenoiser(DiffusionGPT) for an OracleCfg-like object."""
     inner = dict(
