@@ -232,7 +232,8 @@ def test_gather_with_fused_scaling_gpu(gold, cls):
 def test_train_step_on_gathered_batches_gpu():
     """The training slice end to end: window gather with fused scaling -> BesoAgent.train_step.  With the same seeds the
     losses are identical to train_step fed the unscaled batch with the scaler attached to the agent."""
-    from beso_b200 import K256, build_denoiser
+    from beso_b200 import K256
+    from beso_b200.denoiser import build_denoiser
     from beso_b200 import scaler as S
     from beso_b200.agent import BesoAgent
     from beso_b200.synth import synthetic_state_dict
