@@ -122,11 +122,28 @@ class DeviceWindowDataset:
             C.c_void_p(s)), "beso_window_gather")
         return out
 
-    def batches(self, batch_size: int, shuffle: bool = True, drop_last: bool = False, generator=None, rng=None):
-        """Epoch iterator: indices from ``torch.randperm`` (what the DataLoader's RandomSampler draws) or in order."""
+    def epoch_order(self, shuffle: bool = True, generator=None, rank: int = 0, world_size: int = 1) -> np.ndarray:
+        """Window indices of one epoch for this rank.  One rank: ``torch.randperm`` (what the DataLoader's RandomSampler
+        draws) or in order.  Data-parallel training: every rank draws the SAME permutation (same
+        generator seed), pads it by wrapping to a multiple of ``world_size`` and takes ``order[rank::world_size]`` --
+        the rule of ``torch.utils.data.DistributedSampler`` -- so shards are disjoint, equal-sized, and the mean of the
+        per-rank gradients is the global-batch gradient."""
         n = len(self)
         order = torch.randperm(n, generator=generator).numpy() if shuffle else np.arange(n)
-        for lo in range(0, n, batch_size):
+        if world_size > 1:
+            if not 0 <= rank < world_size:
+                raise ValueError("rank must be in [0, world_size)")
+            total = -(-n // world_size) * world_size
+            if total > n:
+                order = np.concatenate([order, np.resize(order, total - n)])
+            order = order[rank:total:world_size]
+        return order
+
+    def batches(self, batch_size: int, shuffle: bool = True, drop_last: bool = False, generator=None, rng=None,
+                rank: int = 0, world_size: int = 1):
+        """Epoch iterator over ``epoch_order``; with ``world_size`` > 1 each rank gathers only its own shard."""
+        order = self.epoch_order(shuffle, generator, rank, world_size)
+        for lo in range(0, order.shape[0], batch_size):
             idx = order[lo:lo + batch_size]
             if drop_last and idx.shape[0] < batch_size:
                 return

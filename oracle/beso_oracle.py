@@ -83,7 +83,7 @@ def causal_self_attention(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: in
     q = F.linear(x, sd[pre + "query.weight"], sd[pre + "query.bias"]).view(B, T, n_head, C // n_head).transpose(1, 2)
     v = F.linear(x, sd[pre + "value.weight"], sd[pre + "value.bias"]).view(B, T, n_head, C // n_head).transpose(1, 2)
     att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(k.size(-1)))
-    mask = torch.tril(torch.ones(T, T)).view(1, 1, T, T)          # score_gpts.py:42-47
+    mask = torch.tril(torch.ones(T, T, device=x.device)).view(1, 1, T, T)  # score_gpts.py:42-47
     att = att.masked_fill(mask == 0, float("-inf"))
     att = F.softmax(att, dim=-1)
     if attn_drop_mask is not None:                                # eval: identity

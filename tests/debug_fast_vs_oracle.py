@@ -1,5 +1,5 @@
 """GPU diagnostics for the FAST (tcgen05) kernel: compares the residual stream of tile 0 at every
-LayerNorm with the oracle's, then the outputs.  Run on the GPU box: python tools/debug_fast.py"""
+LayerNorm with the oracle's, then the outputs.  Run on the GPU box: python tests/debug_fast_vs_oracle.py"""
 import ctypes as C
 import os
 import sys

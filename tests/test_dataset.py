@@ -264,3 +264,23 @@ def test_train_step_on_gathered_batches_gpu():
         losses.append(run)
     assert len(losses[0]) == 4 and losses[0] == losses[1]
     assert all(np.isfinite(losses[0]))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_epoch_order_shards_like_distributed_sampler(gold, world, shuffle):
+    """Data-parallel sharding of the windows follows torch's DistributedSampler (same permutation on every rank,
+    wrap-around padding, rank::world stride): disjoint equal shards that cover every window."""
+    from torch.utils.data import DistributedSampler
+    ds = DeviceWindowDataset(gold["obs"], gold["act"], gold["lens"], device="cpu", **WINDOW_MODES["plain"])
+    n = len(ds)
+    seen = []
+    for rank in range(world):
+        ref = DistributedSampler(range(n), num_replicas=world, rank=rank, shuffle=shuffle, seed=17)
+        got = ds.epoch_order(shuffle, torch.Generator().manual_seed(17), rank, world)
+        assert got.tolist() == list(iter(ref))
+        seen.append(got)
+    assert len({len(s) for s in seen}) == 1
+    assert set(np.concatenate(seen).tolist()) == set(range(n))
+    with pytest.raises(ValueError):
+        ds.epoch_order(True, None, world, world)
