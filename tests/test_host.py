@@ -240,3 +240,20 @@ def test_two_stage_coefficient_rows():
         assert name in sampling.SAMPLERS
     s10 = sampling.get_sigmas_exponential(10, 0.005, 1.0)
     assert sampling.n_model_evals("dpm", s10) == 19 and sampling.n_model_evals("ancestral", s10) == 19
+
+
+def test_product_code_never_imports_the_oracle():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's baseline legs may use
+    it.  The package, the C/CUDA sources and the tools must not mention it as an import."""
+    import pathlib
+    import re
+    root = pathlib.Path(__file__).resolve().parents[1]
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|importlib\.import_module\(\s*['\"]oracle", re.M)
+    offenders = []
+    for sub in ("beso_b200", "tools"):
+        for f in (root / sub).rglob("*.py"):
+            if pat.search(f.read_text()):
+                offenders.append(str(f.relative_to(root)))
+    assert offenders == []
+    for f in (root / "beso_b200" / "csrc").glob("*.cu*"):
+        assert "oracle/" not in f.read_text()
