@@ -71,10 +71,11 @@ static size_t simt_layout(const beso_model_desc& m, float* base, SimtModel* out)
   for (int l = 0; l < m.n_layers; ++l) {
     SimtLayer& L = s.layer[l];
     L.ln1w = take(d); L.ln1b = take(d); L.ln2w = take(d); L.ln2b = take(d);
-    L.wqkv = take((size_t)d * 3 * d); L.bqkv = take(3 * d);
-    L.wproj = take((size_t)d * d); L.bproj = take(d);
-    L.w1 = take((size_t)d * 4 * d); L.b1 = take(4 * d);
-    L.w2 = take((size_t)4 * d * d); L.b2 = take(d);
+    auto tiled = [](int K, int N) { return (size_t)((N + 63) / 64) * K * 64; };   // [ceil(N/64)][K][64]
+    L.wqkv = take(tiled(d, 3 * d)); L.bqkv = take(3 * d);
+    L.wproj = take(tiled(d, d)); L.bproj = take(d);
+    L.w1 = take(tiled(d, 4 * d)); L.b1 = take(4 * d);
+    L.w2 = take(tiled(4 * d, d)); L.b2 = take(d);
   }
   s.lnfw = take(d); s.lnfb = take(d);
   s.sigw = take(d); s.sigb = take(d);
@@ -96,6 +97,7 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
   auto F = [](const float* q) { return const_cast<float*>(q); };
   int i = 0, rc;
 #define TR(dst, N, K, ld, col) if ((rc = pack_transpose(prm[i++], N, K, F(dst), ld, col, st))) return rc
+#define TT(dst, N, K, col) if ((rc = pack_transpose_tiled(prm[i++], N, K, F(dst), col, st))) return rc
 #define CP(dst, n) if ((rc = pack_copy(prm[i++], F(dst), n, st))) return rc
   BESO_CUDA(cudaMemsetAsync(ws.simt_buf, 0, p->simt_floats * sizeof(float), st));
   CP(s.pos, (int64_t)(G + m.window + 1) * d);
@@ -104,12 +106,12 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
     const SimtLayer& L = s.layer[l];
     CP(L.ln1w, d); CP(L.ln1b, d); CP(L.ln2w, d); CP(L.ln2b, d);
     // reference parameter order is key, query, value, proj; packed column order is q | k | v
-    TR(L.wqkv, d, d, 3 * d, d);     CP(L.bqkv + d, d);       // key
-    TR(L.wqkv, d, d, 3 * d, 0);     CP(L.bqkv, d);           // query
-    TR(L.wqkv, d, d, 3 * d, 2 * d); CP(L.bqkv + 2 * d, d);   // value
-    TR(L.wproj, d, d, d, 0);        CP(L.bproj, d);
-    TR(L.w1, 4 * d, d, 4 * d, 0);   CP(L.b1, 4 * d);
-    TR(L.w2, d, 4 * d, d, 0);       CP(L.b2, d);
+    TT(L.wqkv, d, d, d);            CP(L.bqkv + d, d);       // key
+    TT(L.wqkv, d, d, 0);            CP(L.bqkv, d);           // query
+    TT(L.wqkv, d, d, 2 * d);        CP(L.bqkv + 2 * d, d);   // value
+    TT(L.wproj, d, d, 0);           CP(L.bproj, d);
+    TT(L.w1, 4 * d, d, 0);          CP(L.b1, 4 * d);
+    TT(L.w2, d, 4 * d, 0);          CP(L.b2, d);
   }
   CP(s.lnfw, d); CP(s.lnfb, d);
   CP(s.sigw, d); CP(s.sigb, d);                               // (d,1) weight is already a d-vector
@@ -121,6 +123,7 @@ static int pack_simt(beso_plan* p, WeightSlot& ws, const float* const* prm, cuda
     TR(s.hw1, m.act_dim, 100, s.act_pad, 0); CP(s.hb1, m.act_dim);
   }
 #undef TR
+#undef TT
 #undef CP
   return BESO_OK;
 }

@@ -25,10 +25,11 @@ extern long long g_kernel_launches;
 // ---- PRECISE mode: transposed fp32 weights, [K][Npad] row-major ---------------------------
 struct SimtLayer {
   const float *ln1w, *ln1b, *ln2w, *ln2b;
-  const float *wqkv, *bqkv;   // [d][3d]  columns: q | k | v      (score_gpts.py:33-35)
-  const float *wproj, *bproj; // [d][d]
-  const float *w1, *b1;       // [d][4d]                            (mlp.0)
-  const float *w2, *b2;       // [4d][d]                            (mlp.2)
+  // GEMM weights: transposed [K][N] images tiled by 64-column groups, [ceil(N/64)][K][64] (pack.cu)
+  const float *wqkv, *bqkv;   // K = d,  N = 3d  columns: q | k | v  (score_gpts.py:33-35)
+  const float *wproj, *bproj; // K = d,  N = d
+  const float *w1, *b1;       // K = d,  N = 4d                      (mlp.0)
+  const float *w2, *b2;       // K = 4d, N = d                       (mlp.2)
 };
 struct SimtModel {
   int obs, act, W, G, d, L, H, hs, linear_out, act_pad, hid, hid_pad;
@@ -75,6 +76,7 @@ int simt_launch(const SimtModel& m, const SimtLaunch& L, const SampleArgs& sa, c
 
 // weight packing helpers (pack.cu)
 int pack_transpose(const float* src, int N, int K, float* dst, int ld_dst, int col0, cudaStream_t s);
+int pack_transpose_tiled(const float* src, int N, int K, float* dst, int col0, cudaStream_t s);
 int pack_copy(const float* src, float* dst, int64_t n, cudaStream_t s);
 
 }  // namespace beso

@@ -33,68 +33,123 @@ __device__ __forceinline__ float warp_max(float v) {
 
 enum { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2 };
 
-// out[r][n] (=|+=) bias[n] + sum_k A[r][k] * Wt[k][n]      r < R, n < N (N % 4 == 0, K % 4 == 0)
-// A, out in shared memory; Wt, bias in global memory.  A warp owns an 8-row x 128-column item;
-// each lane 8 x 4 accumulators.  Weight rows are prefetched one k-quad ahead.
-template <int EPI>
-__device__ __noinline__ void gemm_rows(const float* A, int lda, int R, const float* __restrict__ Wt,
-                          const float* __restrict__ bias, int K, int N, float* out, int ldo) {
+// Shared-memory accesses of the GEMM go through explicit ld.shared / st.shared: through a plain pointer the
+// compiler emits generic loads with 64-bit address arithmetic and cannot tell they never alias the weights.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// out[r][n] (=|+=) bias[n] + sum_k A[r][k] * W[k][n]       r < R, n < N (N % 2 == 0, K % 4 == 0)
+// A, out in shared memory; bias in global memory; Wt = the weight tiled by 64-column groups, [ceil(N/64)][K][64]
+// (L2-resident).  A warp owns an RT-row x 64-column item, each lane RT x 2 accumulators, so a weight element
+// fetched from L2 feeds RT rows (with R <= 24 and RT = 12 the weight set crosses the L2 -> SM link twice per
+// evaluation).  Weights are requested a whole 8-k trip ahead; the A
+// rows one k-quad ahead.  Every output is one chain of fmaf over k = 0 .. K-1 followed by the bias add, whatever
+// the tiling.
+template <int EPI, int RT>
+__device__ __noinline__ void gemm_rows_rt(const float* A, int lda, int R, const float* __restrict__ Wt,
+                                          const float* __restrict__ bias, int K, int N, float* out, int ldo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ncg = (N + 127) >> 7, nrg = (R + 7) >> 3;
+  const int ncg = (N + 63) >> 6, nrg = (R + RT - 1) / RT;
+  const uint32_t a_s = smem_addr(A), o_s = smem_addr(out);
   for (int item = warp; item < ncg * nrg; item += kWarps) {
     const int cg = item % ncg, rg = item / ncg;
-    const int n0 = cg * 128 + lane * 4;
+    const int n0 = cg * 64 + lane * 2;
     const bool active = n0 < N;
-    const int r0 = rg * 8;
-    const float* arow[8];
+    const int r0 = rg * RT;
+    uint32_t ar[RT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) arow[i] = A + (size_t)min(r0 + i, R - 1) * lda;
-    float acc[8][4];
+    for (int i = 0; i < RT; ++i) ar[i] = a_s + (uint32_t)(min(r0 + i, R - 1) * lda) * 4u;
+    float acc[RT][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    const float* wp = Wt + (active ? n0 : 0);
-    float4 wc[4], wn[4];
+    for (int i = 0; i < RT; ++i) acc[i][0] = acc[i][1] = 0.f;
+    // this lane's column pair of weight row k is wq[k * 32] (padding columns of the last group are zero)
+    const float2* wq = reinterpret_cast<const float2*>(Wt + (size_t)cg * K * 64) + lane;
+    auto ldw4 = [&](float2 (&w)[4], int k) {             // rows k .. k+3 (256 bytes apart)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) wc[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)i * N));
-    for (int k = 0; k < K; k += 4) {
-      if (k + 4 < K) {
+      for (int i = 0; i < 4; ++i) w[i] = __ldg(wq + (size_t)(k + i) * 32);
+    };
+    // one k-quad: row i's 8 FMAs, then row i's A registers are reloaded for the NEXT quad (kn), so a single set of
+    // A registers gives a whole quad of distance between the shared-memory load and its use
+    float4 a[RT];
+    auto quad = [&](const float2 (&w)[4], int kn) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(k + 4 + i) * N));
+      for (int i = 0; i < RT; ++i) {
+        const float4 v = a[i];
+        acc[i][0] = fmaf(v.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(v.x, w[0].y, acc[i][1]);
+        acc[i][0] = fmaf(v.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(v.y, w[1].y, acc[i][1]);
+        acc[i][0] = fmaf(v.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(v.z, w[2].y, acc[i][1]);
+        acc[i][0] = fmaf(v.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(v.w, w[3].y, acc[i][1]);
+        a[i] = lds_f4(ar[i] + (uint32_t)kn * 4u);
       }
+    };
+    // two k-quads per trip.  The weights of the NEXT trip are requested at the top of this one and moved into place
+    // at its end: the moves pin the wait for them there, a whole trip after the request (left free, the scheduler
+    // sinks the loads next to their first use and exposes the L2 round trip).
+    float2 w0[4], w1[4], v0[4], v1[4];
+    ldw4(w0, 0);
+    if (K > 4) ldw4(w1, 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(arow[i] + k);
-        acc[i][0] = fmaf(a.x, wc[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, wc[0].y, acc[i][1]);
-        acc[i][2] = fmaf(a.x, wc[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, wc[0].w, acc[i][3]);
-        acc[i][0] = fmaf(a.y, wc[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, wc[1].y, acc[i][1]);
-        acc[i][2] = fmaf(a.y, wc[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, wc[1].w, acc[i][3]);
-        acc[i][0] = fmaf(a.z, wc[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, wc[2].y, acc[i][1]);
-        acc[i][2] = fmaf(a.z, wc[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, wc[2].w, acc[i][3]);
-        acc[i][0] = fmaf(a.w, wc[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, wc[3].y, acc[i][1]);
-        acc[i][2] = fmaf(a.w, wc[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, wc[3].w, acc[i][3]);
+    for (int i = 0; i < RT; ++i) a[i] = lds_f4(ar[i]);
+    int k = 0;
+#pragma unroll 1
+    for (; k + 16 <= K; k += 8) {
+      ldw4(v0, k + 8);
+      ldw4(v1, k + 12);
+      quad(w0, k + 4);
+      quad(w1, k + 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { w0[i] = v0[i]; w1[i] = v1[i]; }
+    }
+#pragma unroll 1
+    while (k < K) {                                       // the last one to three quads
+      quad(w0, min(k + 4, K - 4));                        // past the end: a harmless reload of the last quad
+      k += 4;
+      if (k < K) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w0[i] = w1[i];
+        if (k + 4 < K) ldw4(w1, k + 4);
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) wc[i] = wn[i];
     }
     if (active) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + n0));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < RT; ++i) {
         const int r = r0 + i;
         if (r < R) {
-          float4 v = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
-          float4* o = reinterpret_cast<float4*>(out + (size_t)r * ldo + n0);
+          float2 v = make_float2(acc[i][0] + b.x, acc[i][1] + b.y);
+          const uint32_t o = o_s + (uint32_t)(r * ldo + n0) * 4u;
           if (EPI == EPI_GELU) {
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y);
           } else if (EPI == EPI_RESID) {
-            const float4 x = *o;
-            v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+            const float2 x = lds_f2(o);
+            v.x += x.x; v.y += x.y;
           }
-          *o = v;
+          sts_f2(o, v);
         }
       }
     }
   }
+}
+
+// Row-tile height by the number of padded rows it costs (R = 23 -> 2 x 12, R = 32 -> 4 x 8).
+template <int EPI>
+__device__ __forceinline__ void gemm_rows(const float* A, int lda, int R, const float* __restrict__ Wt,
+                                          const float* __restrict__ bias, int K, int N, float* out, int ldo) {
+  const int pad12 = (R + 11) / 12 * 12 - R, pad8 = (R + 7) / 8 * 8 - R;
+  if (pad12 <= pad8) gemm_rows_rt<EPI, 12>(A, lda, R, Wt, bias, K, N, out, ldo);
+  else gemm_rows_rt<EPI, 8>(A, lda, R, Wt, bias, K, N, out, ldo);
 }
 
 // nn.LayerNorm(d), eps 1e-5, biased variance: one warp per row.

@@ -1,4 +1,4 @@
-"""Runs a few FAST-mode forwards (for ncu captures / quick timing).
+"""Runs a few forwards (for ncu captures / quick timing); BESO_RUN_MODE=precise selects the fp32 kernel.
 
     python tools/run_fwd.py [T16|K256] [B] [reps]
 """
@@ -20,7 +20,7 @@ def main():
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     cfg = {"K256": K256, "T16": T16}[name]
     dev = torch.device("cuda:0")
-    m = build_denoiser(cfg, dev, mode="fast", state_dict=synthetic_state_dict(cfg, 1))
+    m = build_denoiser(cfg, dev, mode=os.environ.get("BESO_RUN_MODE", "fast"), state_dict=synthetic_state_dict(cfg, 1))
     x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=2).items()}
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     with torch.no_grad():
