@@ -14,7 +14,7 @@
 namespace beso {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;   // 16 warps, 4 per scheduler: at most 128 registers per thread
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ float gelu_erf(float x) {           // nn.GELU() default (score_gpts.py:107)
@@ -54,17 +54,24 @@ __device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
 // A, out in shared memory; bias in global memory; Wt = the weight tiled by 64-column groups, [ceil(N/64)][K][64]
 // (L2-resident).  A warp owns an RT-row x 64-column item, each lane RT x 2 accumulators, so a weight element
 // fetched from L2 feeds RT rows (with R <= 24 and RT = 12 the weight set crosses the L2 -> SM link twice per
-// evaluation).  Weights are requested a whole 8-k trip ahead; the A
-// rows one k-quad ahead.  Every output is one chain of fmaf over k = 0 .. K-1 followed by the bias add, whatever
-// the tiling.
+// evaluation).  Weights are requested one k-quad ahead and moved into place at the end of the quad (the moves pin
+// the wait there; left free, the scheduler sinks the loads next to their first use); the A rows are reloaded in
+// place, also a quad ahead; the other warps of the scheduler cover what latency is left.
+// When a GEMM has fewer items than half the warps (the two N = d GEMMs) and the caller passes a scratch buffer,
+// K is split in two: the second half's partial sums go to the scratch and are added after a CTA barrier.
 template <int EPI, int RT>
 __device__ __noinline__ void gemm_rows_rt(const float* A, int lda, int R, const float* __restrict__ Wt,
-                                          const float* __restrict__ bias, int K, int N, float* out, int ldo) {
+                                          const float* __restrict__ bias, int K, int N, float* out, int ldo,
+                                          float* scratch, int lds) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ncg = (N + 63) >> 6, nrg = (R + RT - 1) / RT;
-  const uint32_t a_s = smem_addr(A), o_s = smem_addr(out);
-  for (int item = warp; item < ncg * nrg; item += kWarps) {
-    const int cg = item % ncg, rg = item / ncg;
+  const int ncg = (N + 63) >> 6, nrg = (R + RT - 1) / RT, tiles = ncg * nrg;
+  const int KS = (scratch != nullptr && tiles * 2 <= kWarps && (K & 7) == 0) ? 2 : 1;
+  const int Kh = K / KS;
+  const uint32_t a_s = smem_addr(A), o_s = smem_addr(out), p_s = scratch ? smem_addr(scratch) : 0u;
+  for (int item = warp; item < tiles * KS; item += kWarps) {
+    const int ks = item / tiles, tile = item - ks * tiles;
+    const int cg = tile % ncg, rg = tile / ncg;
+    const int k0 = ks * Kh, k1 = k0 + Kh;
     const int n0 = cg * 64 + lane * 2;
     const bool active = n0 < N;
     const int r0 = rg * RT;
@@ -94,51 +101,54 @@ __device__ __noinline__ void gemm_rows_rt(const float* A, int lda, int R, const 
         a[i] = lds_f4(ar[i] + (uint32_t)kn * 4u);
       }
     };
-    // two k-quads per trip.  The weights of the NEXT trip are requested at the top of this one and moved into place
-    // at its end: the moves pin the wait for them there, a whole trip after the request (left free, the scheduler
-    // sinks the loads next to their first use and exposes the L2 round trip).
-    float2 w0[4], w1[4], v0[4], v1[4];
-    ldw4(w0, 0);
-    if (K > 4) ldw4(w1, 4);
+    float2 w[4], v[4];
+    ldw4(w, k0);
 #pragma unroll
-    for (int i = 0; i < RT; ++i) a[i] = lds_f4(ar[i]);
-    int k = 0;
+    for (int i = 0; i < RT; ++i) a[i] = lds_f4(ar[i] + (uint32_t)k0 * 4u);
+    int k = k0;
 #pragma unroll 1
-    for (; k + 16 <= K; k += 8) {
-      ldw4(v0, k + 8);
-      ldw4(v1, k + 12);
-      quad(w0, k + 4);
-      quad(w1, k + 8);
+    for (; k + 8 <= k1; k += 4) {
+      ldw4(v, k + 4);
+      quad(w, k + 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { w0[i] = v0[i]; w1[i] = v1[i]; }
+      for (int i = 0; i < 4; ++i) w[i] = v[i];
     }
-#pragma unroll 1
-    while (k < K) {                                       // the last one to three quads
-      quad(w0, min(k + 4, K - 4));                        // past the end: a harmless reload of the last quad
-      k += 4;
-      if (k < K) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w0[i] = w1[i];
-        if (k + 4 < K) ldw4(w1, k + 4);
-      }
-    }
+    quad(w, k);                                           // the last quad (its reload of A is a harmless repeat)
     if (active) {
-      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + n0));
+      if (ks == 0) {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(bias + n0));
 #pragma unroll
-      for (int i = 0; i < RT; ++i) {
-        const int r = r0 + i;
-        if (r < R) {
-          float2 v = make_float2(acc[i][0] + b.x, acc[i][1] + b.y);
-          const uint32_t o = o_s + (uint32_t)(r * ldo + n0) * 4u;
-          if (EPI == EPI_GELU) {
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y);
-          } else if (EPI == EPI_RESID) {
-            const float2 x = lds_f2(o);
-            v.x += x.x; v.y += x.y;
+        for (int i = 0; i < RT; ++i) {
+          const int r = r0 + i;
+          if (r < R) {
+            float2 y = make_float2(acc[i][0] + b.x, acc[i][1] + b.y);
+            const uint32_t o = o_s + (uint32_t)(r * ldo + n0) * 4u;
+            if (EPI == EPI_GELU) {
+              y.x = gelu_erf(y.x); y.y = gelu_erf(y.y);
+            } else if (EPI == EPI_RESID) {
+              const float2 x = lds_f2(o);
+              y.x += x.x; y.y += x.y;
+            }
+            sts_f2(o, y);
           }
-          sts_f2(o, v);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          const int r = r0 + i;
+          if (r < R) sts_f2(p_s + (uint32_t)(r * lds + n0) * 4u, make_float2(acc[i][0], acc[i][1]));
         }
       }
+    }
+  }
+  if (KS == 2) {                                          // CTA-uniform
+    __syncthreads();
+    const int n2 = N >> 1;
+    for (int idx = threadIdx.x; idx < R * n2; idx += kThreads) {
+      const int r = idx / n2, c = (idx - r * n2) * 2;
+      const uint32_t o = o_s + (uint32_t)(r * ldo + c) * 4u;
+      const float2 x = lds_f2(o), p = lds_f2(p_s + (uint32_t)(r * lds + c) * 4u);
+      sts_f2(o, make_float2(x.x + p.x, x.y + p.y));
     }
   }
 }
@@ -146,10 +156,11 @@ __device__ __noinline__ void gemm_rows_rt(const float* A, int lda, int R, const 
 // Row-tile height by the number of padded rows it costs (R = 23 -> 2 x 12, R = 32 -> 4 x 8).
 template <int EPI>
 __device__ __forceinline__ void gemm_rows(const float* A, int lda, int R, const float* __restrict__ Wt,
-                                          const float* __restrict__ bias, int K, int N, float* out, int ldo) {
+                                          const float* __restrict__ bias, int K, int N, float* out, int ldo,
+                                          float* scratch = nullptr, int lds = 0) {
   const int pad12 = (R + 11) / 12 * 12 - R, pad8 = (R + 7) / 8 * 8 - R;
-  if (pad12 <= pad8) gemm_rows_rt<EPI, 12>(A, lda, R, Wt, bias, K, N, out, ldo);
-  else gemm_rows_rt<EPI, 8>(A, lda, R, Wt, bias, K, N, out, ldo);
+  if (pad12 <= pad8) gemm_rows_rt<EPI, 12>(A, lda, R, Wt, bias, K, N, out, ldo, scratch, lds);
+  else gemm_rows_rt<EPI, 8>(A, lda, R, Wt, bias, K, N, out, ldo, scratch, lds);
 }
 
 // nn.LayerNorm(d), eps 1e-5, biased variance: one warp per row.
@@ -275,13 +286,13 @@ __device__ __noinline__ void eval_model(const Ctx& c, const Smem& sm, const floa
     __syncthreads();
     attention_rows(sm.Big, sm.ldb, c.ns, T, d, m.H, m.hs, sm.Hb, d);
     __syncthreads();
-    gemm_rows<EPI_RESID>(sm.Hb, d, R, w.wproj, w.bproj, d, d, sm.X, d);
+    gemm_rows<EPI_RESID>(sm.Hb, d, R, w.wproj, w.bproj, d, d, sm.X, d, sm.Big, sm.ldb);     // qkv is dead: split-K scratch
     __syncthreads();
     layer_norm_rows(sm.X, d, R, d, w.ln2w, w.ln2b, sm.Hb, d);
     __syncthreads();
     gemm_rows<EPI_GELU>(sm.Hb, d, R, w.w1, w.b1, d, 4 * d, sm.Big, sm.ldb);
     __syncthreads();
-    gemm_rows<EPI_RESID>(sm.Big, sm.ldb, R, w.w2, w.b2, 4 * d, d, sm.X, d);
+    gemm_rows<EPI_RESID>(sm.Big, sm.ldb, R, w.w2, w.b2, 4 * d, d, sm.X, d, sm.Hb, d);      // LN2 output is dead
     __syncthreads();
   }
   // ---- ln_f, action-token gather, head, pre-conditioning (score_gpts.py:341-354) -----------
