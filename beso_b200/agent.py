@@ -151,6 +151,17 @@ class BesoAgent:
         self.sigma_sample_density_type = sigma_sample_density_type
         self.sigma_sample_density_mean, self.sigma_sample_density_std = sigma_sample_density_mean, sigma_sample_density_std
         self.steps = 0
+        self.grad_sync = getattr(self, "grad_sync", None)
+
+    def enable_data_parallel(self, transport: str = "nccl"):
+        """Data-parallel training (BASELINE config 4): every rank runs ``train_step`` on its own shard of
+        the global batch (``DeviceWindowDataset.batches(rank=..., world_size=...)``); the flat gradient is summed over
+        the ranks with ONE all-reduce and scaled by 1/world before the optimiser step, so replicas that start equal stay
+        bit-identical.  ``torch.distributed`` must be initialised; ``transport`` as in ``beso_b200.dist``."""
+        from .dist import FlatGradAllReduce
+        dev = torch.device(self.device)
+        self.grad_sync = FlatGradAllReduce(transport, device=dev.index if dev.index is not None else torch.cuda.current_device())
+        return self.grad_sync
 
     def make_sample_density(self):
         """Noise-level distribution for training (beso_agent.py:540-578; the four types the shipped configs use)."""
@@ -200,6 +211,8 @@ class BesoAgent:
         if self.pred_last_action_only:
             noise[:, :-1, :] = 0
         loss, flat = loss_and_flat_grad(core, state, action, goal, noise, sigma, self.pred_last_action_only, goal_keep)
+        if getattr(self, "grad_sync", None) is not None:    # data parallel: mean of the ranks' gradients
+            self.grad_sync(flat)
         self.optimizer.step(flat_grad=flat)                 # zero_grad / backward / step of the reference in one
         self.lr_scheduler.step()
         self.steps += 1
