@@ -104,6 +104,11 @@ class BesoAgent:
             return sampling.sample_dpmpp_2m(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
         if sampler_type == "euler_ancestral":              # beso_agent.py:431-432
             return sampling.sample_euler_ancestral(self.model, state, x_t, goal, sigmas, scaler=scaler, disable=True)
+        if sampler_type == "dpm_adaptive":                 # beso_agent.py:438-439 (step control on the host)
+            return sampling.sample_dpm_adaptive(self.model, state, x_t, goal, sigmas[-2].item(), sigmas[0].item(), disable=True)
+        if sampler_type == "dpm_fast":                     # beso_agent.py:441-442
+            return sampling.sample_dpm_fast(self.model, state, x_t, goal, sigmas[-2].item(), sigmas[0].item(), len(sigmas),
+                                            disable=True)
         raise ValueError("desired sampler type not found!")
 
     def _core(self) -> GCDenoiser:

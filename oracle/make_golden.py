@@ -191,6 +191,30 @@ def gen_ancestral(ns):
     save("samplers_ancestral_K256", cfg, seed, sd, **arrays)
 
 
+def gen_dpm_solver(ns):
+    """sample_dpm_fast / sample_dpm_adaptive of the real reference (host-side step control), K256, B = 4."""
+    gs = ns.gc_sampling
+    cfg, seed, B = K256, 1, 4
+    m, sd = build(ns, cfg, seed)
+    x = synthetic_inputs(cfg, B, seed=301)
+    x_t = x["noise"] * 1.0
+    arrays = dict(state=x["state"], goal=x["goal"], x_t=x_t)
+    for n in (3, 6, 8, 10):                                   # nfe % 3 == 0 and != 0, as BesoAgent passes len(sigmas)
+        torch.manual_seed(7500 + n)
+        arrays[f"dpm_fast_{n}"] = gs.sample_dpm_fast(m, x["state"], x_t, x["goal"], 0.005, 1.0, n, disable=True)
+    torch.manual_seed(7600)
+    arrays["dpm_fast_eta_9"] = gs.sample_dpm_fast(m, x["state"], x_t, x["goal"], 0.005, 1.0, 9, disable=True, eta=0.5)
+    torch.manual_seed(7600)
+    arrays["noise_eta_9"] = torch.stack([torch.randn_like(x_t) for _ in range(4)])
+    for order in (2, 3):
+        torch.manual_seed(7700 + order)
+        out, info = gs.sample_dpm_adaptive(m, x["state"], x_t, x["goal"], 0.005, 1.0, disable=True, order=order,
+                                           return_info=True)
+        arrays[f"dpm_adaptive_{order}"] = out
+        arrays[f"dpm_adaptive_{order}_info"] = np.array([info[k] for k in ("steps", "nfe", "n_accept", "n_reject")])
+    save("samplers_dpm_solver_K256", cfg, seed, sd, **arrays)
+
+
 def gen_schedules(ns):
     gs = ns.gc_sampling
     arrays = {}
@@ -303,7 +327,11 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "ancestral":       # only the fixture added after the first set
         gen_ancestral(ns)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "dpm_solver":
+        gen_dpm_solver(ns)
+        return
     gen_ancestral(ns)
+    gen_dpm_solver(ns)
     gen_schedules(ns)
     gen_forward(ns)
     gen_samplers(ns)
