@@ -60,6 +60,26 @@ class BesoAgent:
         if cond_lambda is not None:
             self.model = ClassifierFreeSampleModel(model, cond_lambda)
 
+    # ---- base_agent.py:111-142 --------------------------------------------------------------
+    GOAL_ZERO_DIMS = [2, 5, 6, 7, 8, 9]   # block-push goals (10 features): only the block positions are a goal
+
+    def process_batch(self, batch: dict, predict: bool = True):
+        """Scaled (state, action, goal) of a batch dict.  Batches from ``DeviceWindowDataset`` with a scaler attached
+        are already scaled (``"scaled": True``).  As in the reference, 10-feature goals get dims [2, 5, 6, 7, 8, 9]
+        zeroed after scaling, and ``predict=True`` without an action returns ``(state, goal, goal_task_name | None)``."""
+        pre = batch.get("scaled", False)
+        state, goal = batch["observation"].to(self.device), batch["goal_observation"].to(self.device)
+        if not pre:
+            state, goal = self.scaler.scale_input(state), self.scaler.scale_input(goal)
+        if goal.shape[-1] == 10:
+            goal[..., self.GOAL_ZERO_DIMS] = 0
+        if "action" in batch:
+            action = batch["action"].to(self.device)
+            return state, (action if pre else self.scaler.scale_output(action)), goal
+        if predict:
+            return state, goal, batch.get("goal_task_name")
+        return state, goal
+
     # ---- beso_agent.py:580-598 --------------------------------------------------------------
     def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):
         s = sampling
@@ -198,12 +218,7 @@ class BesoAgent:
         loss + all gradients come from ONE call of the fused forward / backward, AdamW + EMA are ONE launch."""
         from .training import loss_and_flat_grad
         core = self._core()
-        if batch.get("scaled", False):                      # DeviceWindowDataset scaled while gathering (dataset.py)
-            state, goal, action = (batch[k].to(self.device) for k in ("observation", "goal_observation", "action"))
-        else:
-            state = self.scaler.scale_input(batch["observation"].to(self.device))
-            goal = self.scaler.scale_input(batch["goal_observation"].to(self.device))
-            action = self.scaler.scale_output(batch["action"].to(self.device))
+        state, action, goal = self.process_batch(batch, predict=False)
         core.train()
         core.training = True
         noise = torch.randn_like(action)
@@ -247,8 +262,7 @@ class BesoAgent:
     def predict(self, batch: dict, new_sampler_type=None, get_mean=None, new_sampling_steps=None,
                 extra_args=None, noise_scheduler=None) -> torch.Tensor:
         extra_args = {} if extra_args is None else extra_args
-        state = self.scaler.scale_input(batch["observation"].to(self.device))
-        goal = self.scaler.scale_input(batch["goal_observation"].to(self.device))
+        state, goal, _ = self.process_batch(batch, predict=True)
         n_steps = new_sampling_steps if new_sampling_steps is not None else self.num_sampling_steps
         sampler_type = new_sampler_type if new_sampler_type is not None else self.sampler_type
         self.obs_context.append(state)

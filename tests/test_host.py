@@ -257,3 +257,33 @@ def test_product_code_never_imports_the_oracle():
     assert offenders == []
     for f in (root / "beso_b200" / "csrc").glob("*.cu*"):
         assert "oracle/" not in f.read_text()
+
+
+def test_process_batch_follows_the_reference_rules():
+    """base_agent.py:111-142: scaling, the zeroed block-push goal dims, return conventions, pre-scaled batches."""
+    import numpy as np
+    from beso_b200 import scaler as S
+    rs = np.random.RandomState(0)
+    x, y = rs.randn(40, 10).astype(np.float32) * 3 + 1, rs.randn(40, 2).astype(np.float32)
+    sc = S.Scaler(x, y, True, "cpu")
+    agent = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10, scaler=sc)
+    batch = {"observation": torch.from_numpy(x[:6]).view(2, 3, 10), "goal_observation": torch.from_numpy(x[6:8]).view(2, 1, 10),
+             "action": torch.from_numpy(y[:6]).view(2, 3, 2)}
+    state, action, goal = agent.process_batch(batch, predict=False)
+    assert torch.equal(state, sc.scale_input(batch["observation"])) and torch.equal(action, sc.scale_output(batch["action"]))
+    want_goal = sc.scale_input(batch["goal_observation"])
+    want_goal[..., [2, 5, 6, 7, 8, 9]] = 0
+    assert torch.equal(goal, want_goal) and float(goal[..., [0, 1, 3, 4]].abs().min()) > 0
+    no_action = {k: v for k, v in batch.items() if k != "action"}
+    s2, g2, name = agent.process_batch(dict(no_action, goal_task_name="push"), predict=True)
+    assert name == "push" and torch.equal(g2, want_goal) and torch.equal(s2, state)
+    assert agent.process_batch(no_action, predict=True)[2] is None and len(agent.process_batch(no_action, predict=False)) == 2
+    # pre-scaled batches (DeviceWindowDataset with the scaler fused) are only moved and masked
+    pre = {"observation": state.clone(), "goal_observation": sc.scale_input(batch["goal_observation"]), "action": action.clone(),
+           "scaled": True}
+    s3, a3, g3 = agent.process_batch(pre, predict=False)
+    assert torch.equal(s3, state) and torch.equal(a3, action) and torch.equal(g3, want_goal)
+    # goals with another feature count are left alone
+    agent60 = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10)
+    g = torch.ones(1, 2, 60)
+    assert torch.equal(agent60.process_batch({"observation": torch.ones(1, 10, 60), "goal_observation": g})[1], g)
