@@ -243,12 +243,20 @@ class BesoAgent:
 
     # ---- beso_agent.py:251-289 --------------------------------------------------------------
     @torch.no_grad()
-    def evaluate(self, state, action, goal) -> float:
+    def evaluate(self, batch, action=None, goal=None) -> float:
+        """``evaluate(batch)`` as the reference's workspaces call it (beso_agent.py:251-289: the batch dict goes through
+        ``process_batch``), or ``evaluate(state, action, goal)`` with already scaled tensors."""
+        if isinstance(batch, dict):
+            state, action, goal = self.process_batch(batch, predict=True)
+        else:
+            state = batch
         self._use_ema_weights(True)
         self._core().eval()
         sigmas = sampling.get_sigmas_exponential(self.num_sampling_steps, self.sigma_min, self.sigma_max, self.device)
         x = torch.randn_like(action) * self.sigma_max
         x_0 = self.sample_loop(sigmas, x, state, goal, self.sampler_type)
+        if self.pred_last_action_only and x_0.dim() == 2:
+            x_0 = x_0.unsqueeze(1)
         mse = torch.nn.functional.mse_loss(x_0, action, reduction="none").mean().item()
         self._use_ema_weights(False)
         return mse
