@@ -21,6 +21,7 @@ from .cfg import ClassifierFreeSampleModel
 from .denoiser import GCDenoiser
 
 FUSED_SAMPLERS = ("ddim", "euler", "heun")
+P = "inner_model."   # state_dict prefix of the score network inside GCDenoiser
 
 
 class IdentityScaler:
@@ -79,6 +80,43 @@ class BesoAgent:
         if predict:
             return state, goal, batch.get("goal_task_name")
         return state, goal
+
+    # ---- beso_agent.py:106-117, 458-477: scaler hand-over and the checkpoint files ------------------
+    def get_scaler(self, scaler):
+        self.scaler = scaler
+
+    def set_bounds(self, scaler):
+        self.model.min_action = torch.from_numpy(scaler.y_bounds[0, :]).to(self.device)
+        self.model.max_action = torch.from_numpy(scaler.y_bounds[1, :]).to(self.device)
+
+    def load_pretrained_model(self, weights_path: str, **kwargs) -> None:
+        """``<weights_path>/model_state_dict.pth`` (the EMA weights the reference ships) into the model; the EMA helper
+        restarts from them.  ``map_location`` is set (the shipped files hold CUDA storages)."""
+        import os
+        sd = torch.load(os.path.join(weights_path, "model_state_dict.pth"), map_location="cpu")
+        core = self._core()
+        core.load_state_dict(sd)
+        self.ema_updated()
+        if getattr(self, "ema_helper", None) is not None:
+            from .optim import ExponentialMovingAverage
+            self.ema_helper = ExponentialMovingAverage(list(core.get_params()), self.ema_helper.decay, self.device)
+            self.ema_params = self.ema_helper.shadow_params
+            if getattr(self, "optimizer", None) is not None:
+                self.optimizer.attach_ema(self.ema_helper, self.update_ema_every_n_steps)
+
+    def store_model_weights(self, store_path: str) -> None:
+        """The reference's two files: ``model_state_dict.pth`` with the EMA weights in place of the parameters (when
+        EMA is in use) and ``non_ema_model_state_dict.pth`` with the raw ones.  Nothing is swapped in the live model."""
+        import os
+        core = self._core()
+        raw = {k: v.detach().clone() for k, v in core.state_dict().items()}
+        ema = dict(raw)
+        if self.use_ema and self.ema_params is not None:
+            names = [P + n for n, _ in core.inner_model.named_parameters()]
+            for n, e in zip(names, self.ema_params):
+                ema[n] = e.detach().clone().view_as(raw[n])
+        torch.save(ema, os.path.join(store_path, "model_state_dict.pth"))
+        torch.save(raw, os.path.join(store_path, "non_ema_model_state_dict.pth"))
 
     # ---- beso_agent.py:580-598 --------------------------------------------------------------
     def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):

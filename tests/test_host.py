@@ -287,3 +287,42 @@ def test_process_batch_follows_the_reference_rules():
     agent60 = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10)
     g = torch.ones(1, 2, 60)
     assert torch.equal(agent60.process_batch({"observation": torch.ones(1, 10, 60), "goal_observation": g})[1], g)
+
+
+def test_checkpoint_files_round_trip(tmp_path):
+    """store_model_weights / load_pretrained_model (beso_agent.py:458-477): EMA weights in model_state_dict.pth, raw
+    ones in non_ema_model_state_dict.pth, buffers kept, nothing swapped in the live model."""
+    from beso_b200.synth import synthetic_state_dict
+    cfg = K256
+    m = build_denoiser(cfg, "cpu", state_dict=synthetic_state_dict(cfg, 3))
+    ema = [p.detach() * 0.5 for p in m.get_params()]
+    agent = BesoAgent(m, device="cpu", window_size=cfg.window, use_ema=True, ema_params=ema)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    agent.store_model_weights(str(tmp_path))
+    raw = torch.load(tmp_path / "non_ema_model_state_dict.pth")
+    avg = torch.load(tmp_path / "model_state_dict.pth")
+    assert list(raw) == list(before) == list(avg)
+    for k, v in before.items():
+        assert torch.equal(raw[k], v) and torch.equal(m.state_dict()[k], v)
+        assert torch.equal(avg[k], v if k.endswith("attn.mask") else v * 0.5)
+    other = BesoAgent(build_denoiser(cfg, "cpu"), device="cpu", window_size=cfg.window)
+    other.load_pretrained_model(str(tmp_path))
+    for k, v in other.model.state_dict().items():
+        assert torch.equal(v, avg[k])
+    # scaler hand-over (beso_agent.py:106-117)
+    import numpy as np
+    from beso_b200 import scaler as S
+    sc = S.Scaler(np.random.RandomState(0).randn(20, 60).astype(np.float32), np.random.RandomState(1).randn(20, 9).astype(np.float32),
+                  True, "cpu")
+    other.get_scaler(sc)
+    other.set_bounds(sc)
+    assert other.scaler is sc and other.model.min_action.shape == (9,) and bool((other.model.max_action > other.model.min_action).all())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/trained_models/kitchen/c_beso_1"), reason="shipped checkpoints not present")
+def test_load_shipped_checkpoint():
+    from beso_b200.config import KITCHEN_CKPT
+    agent = BesoAgent(build_denoiser(KITCHEN_CKPT, "cpu"), device="cpu", window_size=KITCHEN_CKPT.window)
+    agent.load_pretrained_model("/root/reference/trained_models/kitchen/c_beso_1")
+    sd = torch.load("/root/reference/trained_models/kitchen/c_beso_1/model_state_dict.pth", map_location="cpu")
+    assert all(torch.equal(v, sd[k]) for k, v in agent.model.state_dict().items())
