@@ -65,19 +65,21 @@ class DeviceWindowDataset:
         (trajectory_loader.py:170-184).  ``rng`` is ``np.random`` (the reference's global generator) or a RandomState;
         one ``randint`` is drawn per item that samples, in order, exactly as iterating the reference dataset does."""
         rng = np.random if rng is None else rng
-        indices = np.asarray(indices, dtype=np.int64)
+        indices = np.asarray(indices, dtype=np.int64).reshape(-1)
         G, t_max = self.future_seq_len, int(self.observations.shape[1])
+        traj = self.slice_traj[indices].astype(np.int64)
+        end = self.slice_start[indices].astype(np.int64) + self.window
+        lo, hi = end + self.min_future_sep, self.seq_lengths[traj] - G
+        ok = lo < hi
         out = np.full(indices.shape[0], -1, dtype=np.int32)
-        for n, idx in enumerate(indices.tolist()):
-            i, end = int(self.slice_traj[idx]), int(self.slice_start[idx]) + self.window
-            lo, hi = end + self.min_future_sep, int(self.seq_lengths[i]) - G
-            if lo < hi:
-                if self.only_sample_tail:
-                    out[n] = t_max - G  # the reference slices the PADDED trajectory's last G frames
-                elif self.only_sample_seq_end:
-                    out[n] = end
-                else:
-                    out[n] = rng.randint(lo, hi)
+        if self.only_sample_tail:
+            out[ok] = t_max - G                              # the reference slices the PADDED trajectory's last G frames
+        elif self.only_sample_seq_end:
+            out[ok] = end[ok]
+        elif ok.any():
+            # one legacy-generator call with array bounds draws exactly what successive scalar randint(lo, hi) calls
+            # draw, element by element, and leaves the generator in the same state (tests/test_dataset.py)
+            out[ok] = rng.randint(lo[ok], hi[ok])
         return out
 
     def attach_scaler(self, scaler) -> None:

@@ -284,3 +284,19 @@ def test_epoch_order_shards_like_distributed_sampler(gold, world, shuffle):
     assert set(np.concatenate(seen).tolist()) == set(range(n))
     with pytest.raises(ValueError):
         ds.epoch_order(True, None, world, world)
+
+
+def test_vectorised_goal_draws_equal_successive_scalar_draws(gold):
+    """goal_starts makes ONE randint call with array bounds; the reference makes one scalar call per item.  Same
+    values, same generator state afterwards (legacy RandomState and the np.random module functions)."""
+    kw = WINDOW_MODES["future"]
+    ds = DeviceWindowDataset(gold["obs"], gold["act"], gold["lens"], device="cpu", **kw)
+    order = np.random.RandomState(1).randint(0, len(ds), size=500)
+    want, ref_rng = [], np.random.RandomState(99)
+    for idx in order:
+        i, end = ds.slice_traj[idx], ds.slice_start[idx] + kw["window"]
+        lo, hi = end + kw["min_future_sep"], gold["lens"][i] - kw["future_seq_len"]
+        want.append(ref_rng.randint(lo, hi) if lo < hi else -1)
+    rng = np.random.RandomState(99)
+    assert ds.goal_starts(order, rng).tolist() == want
+    assert rng.randint(0, 1 << 30) == ref_rng.randint(0, 1 << 30)
