@@ -317,11 +317,44 @@ def gen_windows():
     print("wrote windows.npz", {k: v.shape for k, v in arrays.items()})
 
 
+def scaler_fixture_data():
+    rs = np.random.RandomState(21)
+    x = (rs.randn(12, 30, 6) * np.array([1, 5, 0.1, 2, 1, 3]) + np.array([0, 2, -1, 4, 0, 1])).astype(np.float32)
+    y = (rs.randn(12, 30, 3) * np.array([2, 0.5, 1]) + np.array([1, 0, -3])).astype(np.float32)
+    return x, y
+
+
+def gen_scalers():
+    """tests/golden/scalers.npz: statistics and method outputs of the reference's Scaler / MinMaxScaler."""
+    import importlib.util
+    path = os.path.join(ref_import.REF_ROOT, "beso", "networks", "scaler", "scaler_class.py")
+    spec = importlib.util.spec_from_file_location("_beso_ref_scaler", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    x, y = scaler_fixture_data()
+    xs, ys = torch.from_numpy(x[:4]), torch.from_numpy(y[:4])
+    arrays = {}
+    for cls in ("Scaler", "MinMaxScaler"):
+        for on in (True, False):
+            sc = getattr(ref, cls)(x, y, on, "cpu")
+            tag = f"{cls}::{int(on)}::"
+            for name in ("x_mean", "x_std", "x_max", "x_min", "y_min", "y_max", "y_bounds_tensor", "x_bounds_tensor"):
+                arrays[tag + name] = getattr(sc, name).numpy()
+            for fn, arg in (("scale_input", xs), ("scale_output", ys), ("inverse_scale_input", xs),
+                            ("inverse_scale_output", ys), ("clip_action", ys * 3)):
+                arrays[tag + fn] = getattr(sc, fn)(arg.clone()).numpy()
+    np.savez_compressed(os.path.join(OUT, "scalers.npz"), **arrays)
+    print("wrote scalers.npz", len(arrays), "arrays")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "windows":         # dataset fixture: needs only trajectory_loader.py
         gen_windows()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "scalers":         # needs only scaler_class.py
+        gen_scalers()
         return
     ns = ref_import.load()
     if len(sys.argv) > 1 and sys.argv[1] == "ancestral":       # only the fixture added after the first set

@@ -149,10 +149,28 @@ def test_gather_rejects_bad_arguments_gpu():
 
 # ---- scalers (beso/networks/scaler/scaler_class.py) ------------------------------------------------------------------
 def _scaler_data(dtype=np.float32):
-    rs = np.random.RandomState(21)
-    x = (rs.randn(12, 30, 6) * np.array([1, 5, 0.1, 2, 1, 3]) + np.array([0, 2, -1, 4, 0, 1])).astype(dtype)
-    y = (rs.randn(12, 30, 3) * np.array([2, 0.5, 1]) + np.array([1, 0, -3])).astype(dtype)
-    return x, y
+    from oracle.make_golden import scaler_fixture_data
+    x, y = scaler_fixture_data()
+    return x.astype(dtype), y.astype(dtype)
+
+
+@pytest.mark.parametrize("cls", ["Scaler", "MinMaxScaler"])
+@pytest.mark.parametrize("scale_data", [True, False])
+def test_scaler_mirror_matches_reference_golden(cls, scale_data):
+    """Fixture made with the reference's classes (python -m oracle.make_golden scalers): bit-exact statistics and
+    method outputs, also where /root/reference is absent."""
+    from beso_b200 import scaler as S
+    from oracle.make_golden import scaler_fixture_data
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "scalers.npz"))
+    x, y = scaler_fixture_data()
+    sc = getattr(S, cls)(x, y, scale_data, "cpu")
+    tag = f"{cls}::{int(scale_data)}::"
+    for name in ("x_mean", "x_std", "x_max", "x_min", "y_min", "y_max", "y_bounds_tensor", "x_bounds_tensor"):
+        assert np.array_equal(getattr(sc, name).numpy(), z[tag + name]), name
+    xs, ys = torch.from_numpy(x[:4]), torch.from_numpy(y[:4])
+    for fn, arg in (("scale_input", xs), ("scale_output", ys), ("inverse_scale_input", xs), ("inverse_scale_output", ys),
+                    ("clip_action", ys * 3)):
+        assert np.array_equal(getattr(sc, fn)(arg.clone()).numpy(), z[tag + fn]), fn
 
 
 def _load_ref_scalers():
