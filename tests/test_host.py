@@ -326,3 +326,37 @@ def test_load_shipped_checkpoint():
     agent.load_pretrained_model("/root/reference/trained_models/kitchen/c_beso_1")
     sd = torch.load("/root/reference/trained_models/kitchen/c_beso_1/model_state_dict.pth", map_location="cpu")
     assert all(torch.equal(v, sd[k]) for k, v in agent.model.state_dict().items())
+
+
+def test_train_step_host_flow(monkeypatch):
+    """The host side of BesoAgent.train_step without a GPU: batch processing, RNG draws, the data-parallel hook between
+    gradient and optimiser, scheduler / EMA bookkeeping.  The fused loss + backward is stubbed."""
+    import beso_b200.training as T
+    from beso_b200.synth import synthetic_inputs
+    agent = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10)
+    seen = {}
+
+    def fake(core, state, action, goal, noise, sigma, pred_last, goal_keep):
+        seen["args"] = (state.shape, action.shape, goal.shape, noise.clone(), sigma.clone(), pred_last, goal_keep)
+        return torch.tensor(1.5), torch.arange(10.0)
+    monkeypatch.setattr(T, "loss_and_flat_grad", fake)
+    order = []
+    agent.optimizer = type("O", (), {"step": lambda self, flat_grad=None: order.append(("opt", flat_grad.clone()))})()
+    agent.lr_scheduler = type("S", (), {"step": lambda self: order.append(("sched",))})()
+    agent.ema_helper = type("E", (), {"update": lambda self, p: order.append(("ema",))})()
+    agent.update_ema_every_n_steps, agent.steps = 2, 0
+    agent.sigma_sample_density_type, agent.sigma_sample_density_mean, agent.sigma_sample_density_std = "loglogistic", -1.2, 1.2
+    agent.grad_sync = lambda flat: order.append(("sync",)) or flat.mul_(0.5)
+    x = synthetic_inputs(K256, 4, seed=1)
+    batch = {"observation": x["state"], "goal_observation": x["goal"], "action": x["clean"]}
+    torch.manual_seed(5)
+    assert agent.train_step(batch) == 1.5
+    torch.manual_seed(5)                                     # the reference's draw order: noise first, then sigma
+    noise = torch.randn_like(x["clean"])
+    sigma = agent.make_sample_density()(shape=(4,), device="cpu")
+    assert torch.equal(seen["args"][3], noise) and torch.equal(seen["args"][4], sigma)
+    assert seen["args"][:3] == (x["state"].shape, x["clean"].shape, x["goal"].shape) and seen["args"][5] is False
+    assert [o[0] for o in order] == ["sync", "opt", "sched"]           # EMA every 2nd step only
+    assert torch.equal(order[1][1], torch.arange(10.0) * 0.5)           # the optimiser sees the all-reduced gradient
+    agent.train_step(batch)
+    assert [o[0] for o in order][3:] == ["sync", "opt", "sched", "ema"] and agent.steps == 2
