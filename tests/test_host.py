@@ -360,3 +360,32 @@ def test_train_step_host_flow(monkeypatch):
     assert torch.equal(order[1][1], torch.arange(10.0) * 0.5)           # the optimiser sees the all-reduced gradient
     agent.train_step(batch)
     assert [o[0] for o in order][3:] == ["sync", "opt", "sched", "ema"] and agent.steps == 2
+
+
+def test_predict_host_flow(monkeypatch):
+    """predict() without a GPU (sample loop stubbed): observation / action context deques, the re-denoised action
+    context, scaler clip + inverse scaling (beso_agent.py:297-388)."""
+    import numpy as np
+    from beso_b200 import scaler as S
+    from beso_b200 import T16
+    cfg = T16
+    rs = np.random.RandomState(0)
+    sc = S.Scaler(rs.randn(50, cfg.obs_dim).astype(np.float32), rs.randn(50, cfg.act_dim).astype(np.float32), True, "cpu")
+    agent = BesoAgent(build_denoiser(cfg, "cpu"), device="cpu", window_size=cfg.window, num_sampling_steps=3, scaler=sc)
+    shapes = []
+
+    def fake_loop(sigmas, x_t, state, goal, sampler_type, extra_args={}):
+        shapes.append((tuple(x_t.shape), tuple(state.shape), tuple(goal.shape), sampler_type, len(sigmas)))
+        return torch.full_like(x_t, 100.0)                    # far outside the action bounds: must be clipped
+    monkeypatch.setattr(agent, "sample_loop", fake_loop)
+    for step in range(cfg.window + 2):
+        out = agent.predict({"observation": torch.randn(1, cfg.obs_dim), "goal_observation": torch.randn(cfg.goal_len, cfg.obs_dim)},
+                            new_sampler_type="euler", extra_args={})
+        t = min(step + 1, cfg.window)
+        assert shapes[-1] == ((1, t, cfg.act_dim), (1, t, cfg.obs_dim), (1, cfg.goal_len, cfg.obs_dim), "euler", 4)
+        clipped = sc.y_bounds_tensor[1, :].float() * 1.1
+        assert out.shape == ((1, 1, cfg.act_dim) if step == 0 else (1, cfg.act_dim))   # the reference slices only when t > 1
+        torch.testing.assert_close(out.reshape(1, -1), sc.inverse_scale_output(clipped.view(1, -1)))
+        assert len(agent.action_context) == min(step + 1, cfg.window - 1)
+    agent.reset()
+    assert len(agent.obs_context) == 0 and len(agent.action_context) == 0
