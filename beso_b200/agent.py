@@ -222,8 +222,11 @@ class BesoAgent:
         the ranks with ONE all-reduce and scaled by 1/world before the optimiser step, so replicas that start equal stay
         bit-identical.  ``torch.distributed`` must be initialised; ``transport`` as in ``beso_b200.dist``."""
         from .dist import FlatGradAllReduce
-        dev = torch.device(self.device)
-        self.grad_sync = FlatGradAllReduce(transport, device=dev.index if dev.index is not None else torch.cuda.current_device())
+        index = None
+        if transport == "nccl":
+            dev = torch.device(self.device)
+            index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.grad_sync = FlatGradAllReduce(transport, device=index)
         return self.grad_sync
 
     def make_sample_density(self):

@@ -63,3 +63,39 @@ def test_shard_and_assign():
     assign_grads(params, flat)
     assert params[0].grad.shape == (2, 3) and params[1].grad.tolist() == [6.0, 7.0, 8.0, 9.0]
     assert FlatGradAllReduce("torch")(flat) is flat               # world size 1: no-op
+
+
+def _agent_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import beso_b200.training as T
+    from beso_b200 import K256
+    from beso_b200.agent import BesoAgent
+    from beso_b200.denoiser import build_denoiser
+    agent = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10)
+    T.loss_and_flat_grad = lambda *a: (torch.tensor(float(rank)), torch.arange(6.0) * (rank + 1))   # stub: no GPU here
+    got = {}
+    agent.optimizer = type("O", (), {"step": lambda self, flat_grad=None: got.update(flat=flat_grad.clone())})()
+    agent.lr_scheduler = type("S", (), {"step": lambda self: None})()
+    agent.ema_helper = type("E", (), {"update": lambda self, p: None})()
+    agent.update_ema_every_n_steps, agent.steps = 1, 0
+    agent.sigma_sample_density_type, agent.sigma_sample_density_mean, agent.sigma_sample_density_std = "loglogistic", -1.2, 1.2
+    agent.enable_data_parallel("torch")
+    x = synthetic_inputs(K256, 2, seed=rank)
+    loss = agent.train_step({"observation": x["state"], "goal_observation": x["goal"], "action": x["clean"]})
+    torch.save({"flat": got["flat"], "loss": loss}, os.path.join(out_dir, f"agent{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_agent_train_step_averages_gradients_over_ranks(tmp_path):
+    """BesoAgent.enable_data_parallel: the optimiser of every rank sees the mean of the ranks' flat gradients (the
+    fused loss + backward is stubbed; the exchange is the real torch.distributed all-reduce over gloo)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_agent_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "agent0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "agent1.pt"))
+    want = torch.arange(6.0) * 1.5                                  # mean of 1x and 2x
+    assert torch.equal(r0["flat"], want) and torch.equal(r1["flat"], want)
+    assert (r0["loss"], r1["loss"]) == (0.0, 1.0)                   # the loss each rank reports is its local one
