@@ -389,3 +389,17 @@ def test_predict_host_flow(monkeypatch):
         assert len(agent.action_context) == min(step + 1, cfg.window - 1)
     agent.reset()
     assert len(agent.obs_context) == 0 and len(agent.action_context) == 0
+
+
+def test_library_carries_tcgen05_and_tma_code():
+    """The fast path is tensor-core code, not a recompiled mma.sync kernel: the sm_100a SASS of the library holds
+    tcgen05 MMAs (UTCHMMA), TMEM loads (LDTM) and bulk async copies (UBLKCP), and only sm_100a code."""
+    import shutil
+    import subprocess
+    from beso_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("UTCHMMA") > 100 and sass.count("LDTM") > 10 and sass.count("UBLKCP") > 10
+    archs = set(__import__("re").findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
