@@ -403,3 +403,18 @@ def test_library_carries_tcgen05_and_tma_code():
     assert sass.count("UTCHMMA") > 100 and sass.count("LDTM") > 10 and sass.count("UBLKCP") > 10
     archs = set(__import__("re").findall(r"arch = (sm_\w+)", sass))
     assert archs == {"sm_100a"}, archs
+
+
+def test_public_header_is_plain_c():
+    """include/beso_b200.h is the FFI contract: it must parse as C99 (and C++) on its own, no CUDA or torch headers."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "beso_b200.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    includes = [l for l in open(hdr).read().splitlines() if l.lstrip().startswith("#include")]
+    assert includes and all("cuda" not in l and "torch" not in l for l in includes), includes
