@@ -15,19 +15,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbeso_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-MODE_PRECISE, MODE_FAST = 0, 1
+MODE_PRECISE, MODE_FAST, MODE_SIMT = 0, 1, 2
 SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN, SAMPLER_EULER_ANCESTRAL, SAMPLER_DPMPP_2M, SAMPLER_TWO_STAGE, SAMPLER_LMS = 0, 1, 2, 3, 4, 5, 6
-FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_TF32 = 1, 2, 4, 8, 16
+FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_FAST = 1, 2, 4, 8, 16
+FLAG_TRAIN_TF32 = FLAG_TRAIN_FAST
 SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN, "euler_ancestral": SAMPLER_EULER_ANCESTRAL,
                "dpmpp_2m": SAMPLER_DPMPP_2M, "two_stage": SAMPLER_TWO_STAGE,
                "lms": SAMPLER_LMS}
-MODE_IDS = {"precise": MODE_PRECISE, "fast": MODE_FAST}
+MODE_IDS = {"precise": MODE_PRECISE, "fast": MODE_FAST, "simt": MODE_SIMT}
 
 EXPORTS = [
     "beso_last_error", "beso_abi_version", "beso_param_count", "beso_param_numel", "beso_param_total",
     "beso_plan_create", "beso_plan_destroy", "beso_plan_pack_weights", "beso_plan_select_weights", "beso_plan_set_params",
     "beso_denoise_fwd", "beso_sample_loop", "beso_sample_loop_noise", "beso_denoise_fwd_host", "beso_sample_loop_host",
-    "beso_loss_fwd_bwd", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
+    "beso_loss_fwd_bwd", "beso_loss_fwd_bwd_dropout", "beso_debug_gemm", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
     "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
     "beso_opt_create", "beso_opt_destroy", "beso_opt_total", "beso_opt_step", "beso_window_gather",
@@ -49,6 +50,12 @@ class ModelDesc(C.Structure):
     def from_config(cls, cfg) -> "ModelDesc":
         return cls(cfg.obs_dim, cfg.act_dim, cfg.window, cfg.goal_len, cfg.d, cfg.n_layers, cfg.n_heads,
                    int(cfg.linear_output), int(cfg.goal_conditioned), float(cfg.sigma_data))
+
+
+class DropoutMasks(C.Structure):
+    """beso_dropout_masks of include/beso_b200.h."""
+    _fields_ = [("embed", C.c_void_p), ("attn", C.POINTER(C.c_void_p)), ("resid_attn", C.POINTER(C.c_void_p)),
+                ("resid_mlp", C.POINTER(C.c_void_p))]
 
 
 _lib = None
@@ -87,6 +94,8 @@ def _declare(lib):
     lib.beso_denoise_fwd_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_sample_loop_host.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp]
+    lib.beso_loss_fwd_bwd_dropout.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DropoutMasks), vp, vp, i32, u32, vp]
+    lib.beso_debug_gemm.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.beso_comm_unique_id.argtypes = [C.c_char_p]
     lib.beso_comm_init.argtypes = [i32, i32, C.c_char_p, i32, C.POINTER(vp)]
     lib.beso_comm_destroy.argtypes = [vp]

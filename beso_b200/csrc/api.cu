@@ -1,11 +1,13 @@
 // C ABI of libbeso_b200.so (see include/beso_b200.h for the contract of every entry point).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
 
 #include "common.cuh"
 #include "fast.cuh"
+#include "gemm.cuh"
 #include "plan.cuh"
 
 namespace beso {
@@ -164,10 +166,11 @@ static int check_call(beso_plan* p, int mode, int B, int t, uint32_t flags) {
   if (!p) { set_error("null plan"); return BESO_E_INVALID; }
   if (B < 1 || t < 1 || t > p->desc.window) { set_error("need B >= 1 and 1 <= t <= window"); return BESO_E_INVALID; }
   if (!p->slot[p->active].packed) { set_error("weights not packed (call beso_plan_pack_weights)"); return BESO_E_NOT_PACKED; }
-  if (mode != BESO_MODE_PRECISE && mode != BESO_MODE_FAST) { set_error("unknown mode"); return BESO_E_INVALID; }
+  if (mode != BESO_MODE_PRECISE && mode != BESO_MODE_FAST && mode != BESO_MODE_SIMT) { set_error("unknown mode"); return BESO_E_INVALID; }
   if ((flags & BESO_FLAG_CFG) && (flags & BESO_FLAG_UNCOND)) { set_error("CFG and UNCOND are exclusive"); return BESO_E_INVALID; }
   if (mode == BESO_MODE_FAST && !p->fast_ok) {
-    set_error("fast (tcgen05) mode needs d=256, head_dim=64, linear_output, <=23 tokens; use precise mode");
+    set_error("fast (tcgen05) mode needs embed_dim <= 256, head size <= 64 (<= 6 attention passes), linear_output, <= 24 tokens, "
+              "obs <= 64, act <= 13; use precise mode");
     return BESO_E_UNSUPPORTED;
   }
   return BESO_OK;
@@ -179,7 +182,12 @@ static int run(beso_plan* p, int mode, const SampleArgs& sa, const float* state,
   BESO_CUDA(cudaSetDevice(p->device));
   WeightSlot& ws = p->slot[p->active];
   if (mode == BESO_MODE_FAST)
-    return fast_launch(ws.fast, p->desc, p->sm_count, sa, state, goal, x, sigma, out, B, t, flags, lambda, st);
+    return fast_launch(ws.fast, p->desc, p->sm_count, sa, state, goal, x, sigma, out, B, t, flags, lambda, st, false);
+  // PRECISE: split-operand tensor-core kernel where the shape allows (the CFG + LMS history needs a buffer that
+  // kernel uses as CFG scratch), else the fp32 CUDA-core kernel
+  if (mode == BESO_MODE_PRECISE && p->fast_ok && !p->force_simt &&
+      !(sa.n_steps && sa.sampler == BESO_SAMPLER_LMS && (flags & BESO_FLAG_CFG)))
+    return fast_launch(ws.fastp, p->desc, p->sm_count, sa, state, goal, x, sigma, out, B, t, flags, lambda, st, true);
   SimtLaunch L{};
   int rc = simt_plan_launch(ws.simt, t, p->max_smem, &L);
   if (rc) return rc;
@@ -232,6 +240,7 @@ int beso_plan_create(const beso_model_desc* desc, int device, beso_plan** out) {
   BESO_CUDA(cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   p->simt_floats = simt_layout(*desc, nullptr, nullptr);
   p->fast_ok = fast_supported(*desc);
+  { const char* e = getenv("BESO_PRECISE_SIMT"); p->force_simt = e && atoi(e) != 0; }
   *out = p;
   return BESO_OK;
 }
@@ -242,6 +251,7 @@ int beso_plan_destroy(beso_plan* p) {
   for (auto& s : p->slot) {
     if (s.simt_buf) cudaFree(s.simt_buf);
     fast_free(s.fast);
+    fast_free(s.fastp);
   }
   if (p->h_pin) cudaFreeHost(p->h_pin);
   if (p->d_stage) cudaFree(p->d_stage);
@@ -266,7 +276,9 @@ int beso_plan_pack_weights(beso_plan* p, int slot, const float* const* prm, int 
   int rc = pack_simt(p, ws, prm, st);
   if (rc) return rc;
   if (p->fast_ok) {
-    rc = fast_pack(ws.fast, p->desc, prm, st);
+    rc = fast_pack(ws.fast, p->desc, prm, st, false);
+    if (rc) return rc;
+    rc = fast_pack(ws.fastp, p->desc, prm, st, true);
     if (rc) return rc;
   }
   ws.packed = true;
@@ -396,13 +408,29 @@ int beso_plan_set_params(beso_plan* p, int slot, const float* const* prm, int n_
 int beso_loss_fwd_bwd(beso_plan* p, const float* state, const float* action, const float* goal, const float* noise,
                       const float* sigma, const float* goal_keep, float* loss_dev, float* flat_grad_dev, int B,
                       uint32_t flags, void* stream) {
+  return beso_loss_fwd_bwd_dropout(p, state, action, goal, noise, sigma, goal_keep, nullptr, loss_dev, flat_grad_dev, B, flags, stream);
+}
+
+int beso_debug_gemm(beso_plan* p, const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* Cm,
+                    int ldc, int M, int N, int K, const float* bias, int accumulate, int prec, void* stream) {
+  if (!p) { set_error("null plan"); return BESO_E_INVALID; }
+  BESO_CUDA(cudaSetDevice(p->device));
+  GemmArgs a{};
+  a.A = A; a.lda = lda; a.a_kmajor = a_kmajor; a.B = B; a.ldb = ldb; a.b_kmajor = b_kmajor; a.C = Cm; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.accumulate = accumulate; a.prec = prec;
+  return train_gemm(p->train_ws, a, (cudaStream_t)stream);
+}
+
+int beso_loss_fwd_bwd_dropout(beso_plan* p, const float* state, const float* action, const float* goal, const float* noise,
+                              const float* sigma, const float* goal_keep, const beso_dropout_masks* masks, float* loss_dev,
+                              float* flat_grad_dev, int B, uint32_t flags, void* stream) {
   if (!p || !state || !action || !noise || !sigma || !loss_dev || B < 1) { set_error("null argument or B < 1"); return BESO_E_INVALID; }
   if (!goal && p->desc.goal_conditioned && p->desc.goal_len > 0) { set_error("null goal"); return BESO_E_INVALID; }
   const WeightSlot& ws = p->slot[p->active];
   if (ws.params.empty()) { set_error("no parameters registered (beso_plan_set_params / beso_plan_pack_weights)"); return BESO_E_NOT_PACKED; }
   BESO_CUDA(cudaSetDevice(p->device));
-  return train_loss_fwd_bwd(p->train_ws, p->desc, ws.params.data(), state, action, goal, noise, sigma, goal_keep, loss_dev,
-                            flat_grad_dev, B, flags, (cudaStream_t)stream);
+  return train_loss_fwd_bwd(p->train_ws, p->desc, ws.params.data(), state, action, goal, noise, sigma, goal_keep, masks,
+                            loss_dev, flat_grad_dev, B, flags, (cudaStream_t)stream);
 }
 
 int64_t beso_kernel_launches(void) { return g_kernel_launches; }
@@ -412,7 +440,8 @@ int beso_debug_mma_rate(long long* out_dev, const void* src_dev, int mode, void*
 
 int beso_plan_rows_per_cta(beso_plan* p, int mode, int t) {
   if (!p) return BESO_E_INVALID;
-  if (mode == BESO_MODE_FAST) return p->fast_ok ? fast_seqs_per_tile(p->desc, t) : BESO_E_UNSUPPORTED;
+  if (mode == BESO_MODE_FAST) return p->fast_ok ? fast_seqs_per_tile(p->desc, t, false) : BESO_E_UNSUPPORTED;
+  if (mode == BESO_MODE_PRECISE && p->fast_ok && !p->force_simt) return fast_seqs_per_tile(p->desc, t, true);
   SimtLaunch L{};
   SimtModel tmp{};
   simt_layout(p->desc, nullptr, &tmp);

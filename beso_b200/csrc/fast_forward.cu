@@ -43,8 +43,10 @@ using namespace umma;
 
 namespace {
 
-// ---- fixed geometry (d = 256, 4 heads of 64) ---------------------------------------------------
-constexpr int kD = 256, kH = 4, kHS = 64, kFF = 1024;
+// ---- geometry: embed_dim padded to 256 columns, head dims padded to 32 or 64 and packed 64 columns per
+// attention pass (one 64-wide head, or two 32-wide heads), hidden width padded to 1024 ----------------
+constexpr int kD = 256, kH = 4, kFF = 1024;
+constexpr int kMaxPass = 6;               // attention passes per layer (n_heads * padded head size / 64)
 constexpr int kRows = 128;
 constexpr int kThreads = 384;             // warps 0-7 compute, 8-9 attention helpers, 10 producer, 11 MMA + TMEM alloc
 // The warp scheduler prefers higher warp ids among eligible warps, so the two latency-critical
@@ -64,9 +66,12 @@ constexpr uint32_t kQkvStride = 400;                // bytes per row of the bf16
 constexpr uint32_t kSmQkv = kSmU;                   // [128][400 B]
 constexpr uint32_t kSmY = kSmU + 51200;             // attention output atom [128 x 64] bf16
 constexpr uint32_t kSmH0 = kSmU, kSmH1 = kSmU + 32768;   // FC1 output chunks, 2 atoms each
-constexpr uint32_t kSmVecA = kSmU + 67584;          // 198656: [pend | ln_w | ln_b | bqkv(768)] fp32
+constexpr uint32_t kQkvStrideP = 784;               // PREC: bytes per row of the fp32 [Q|K|V] staging (192 + 4 pad floats), 64 rows
+constexpr uint32_t kSmVecA = kSmU + 67584;          // 198656: [pend(256) | bq: 192 per pass, up to 6 passes | spare] fp32
+constexpr uint32_t kVecBq = 256;                    // float index of the Q biases inside vecA
 constexpr uint32_t kVecAFloats = 1536;
-constexpr uint32_t kSmVecM = kSmVecA + kVecAFloats * 4;   // [bproj | ln2_w | ln2_b | b1(1024)]
+constexpr uint32_t kSmVecM = kSmVecA + kVecAFloats * 4;   // [pend(256) | b1 / 4 as fp16 (512 floats) | b1 fp32 (1024, PREC)]
+constexpr uint32_t kVecB1H = 256, kVecB1F = 768;   // float indices of the two b1 images inside vecM
 constexpr uint32_t kVecMFloats = 1792;
 constexpr uint32_t kSmStats = kSmVecM + kVecMFloats * 4;  // [2][128] float2
 constexpr uint32_t kSmProg = kSmStats + 2048;
@@ -88,8 +93,9 @@ struct FastParams {
   const uint8_t* tape;         // per-eval weight tape
   const float* vec;            // per layer: vecA (1536) | vecM (1792); then final vecA (1536)
   int n_fills, L, G, obs, act, T, t, S, n_tiles, B, evals;
+  int npass, hsp, d_true;      // attention passes per layer, padded head size (32 / 64), true embed_dim
   uint32_t flags;
-  float lambda, sigma_data;
+  float lambda, sigma_data, inv_d;
   const float *state, *goal, *xin, *sigma;
   float* out;
   float* trace;                // optional debug dump of X after every LayerNorm pass (tile 0, eval 0)
@@ -285,7 +291,8 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
 struct Compute {
   uint8_t* sm;
   uint32_t sbase, tmem;
-  int wq, lane, hf, row, ctid;       // TMEM lane quadrant, lane, column half, tile row, compute thread id
+  int wq, lane, hf, row, ctid;       // TMEM lane quadrant, lane, column half, tile row (= TMEM lane), compute thread id
+  int srow, is_lo;                   // sequence row this thread works on; PREC: 1 = this TMEM lane holds the "lo" image
   uint32_t row_off, rx4;             // row * 128 and (row & 7) << 4: SW128 address of chunk k = row_off + ((k << 4) ^ rx4)
   uint32_t phases;                   // parity bit per barrier id this role waits on
   __device__ uint32_t bar(int id) const { return sbase + kSmBars + id * 8; }
@@ -313,7 +320,7 @@ struct Compute {
 // X (TMEM) is only read: every projection / MLP bias is added to X up front by the embedding GEMM and
 // `pend` holds minus the biases that are not due yet at this point of the network.
 template <bool DBG>
-__device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float* trace_row) {
+__device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float inv_d, float* trace_row) {
   // X is read from TMEM once: the 128 values of this thread (pending biases added) wait for the row
   // statistics as 64 packed fp16 pairs in registers; the statistics themselves are fp32 of the unrounded
   // values.  The normalisation is one packed HFMA2 per pair, straight into the fp16 A operand.
@@ -355,8 +362,9 @@ __device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float* tra
   stats[c.hf * kRows + c.row] = make_float2(sum, sq);
   compute_sync();
   const float2 o = stats[(c.hf ^ 1) * kRows + c.row];
-  const float mean = (sum + o.x) * (1.0f / kD);
-  const float var = fmaxf((sq + o.y) * (1.0f / kD) - mean * mean, 0.f);
+  // columns >= embed_dim of X are exactly zero (zero weight rows, zero pend), so the sums run over the true lanes
+  const float mean = (sum + o.x) * inv_d;
+  const float var = fmaxf((sq + o.y) * inv_d - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const __half2 r2 = __float2half2_rn(rstd), n2 = __float2half2_rn(-mean * rstd);
   const uint32_t a_s = c.sbase + kSmA + (uint32_t)c.hf * 32768u;       // this thread's two K atoms
@@ -414,26 +422,29 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // HI = false: rows 8..15 of the diagonal tile lie beyond the sequence (e.g. tokens 24..31 of a 23-token sequence):
 // as queries their softmax is skipped and their P rows are zero; as keys (columns 8..15 of the last key step)
 // their scores are neither computed nor exponentiated.
-template <int NKT, bool HI>
-__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T) {
-  const uint32_t qkv = sbase + kSmQkv;
+// HSP = padded head size: 64 (one head per pass) or 32 (two heads per pass, `co` = column offset of this head inside
+// the 64-column blocks of Q, K, V and Y).
+template <int NKT, bool HI, int HSP>
+__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co) {
+  const uint32_t qkv = sbase + kSmQkv + (uint32_t)co * 2u;
+  constexpr int KS = HSP / 16;                   // 16-wide k steps over the head dimension
   // ---- S = Q K^T ----
   float sc[NKT][2][4];
 #pragma unroll
   for (int a = 0; a < NKT; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) sc[a][b][0] = sc[a][b][1] = sc[a][b][2] = sc[a][b][3] = 0.f;
-  uint32_t qa[4][4];
+  uint32_t qa[KS][4];
   {
     const int r = min(row0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ldmatrix_x4(qkv + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, qa[k]);
+    for (int k = 0; k < KS; ++k) ldmatrix_x4(qkv + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, qa[k]);
   }
 #pragma unroll
   for (int kt = 0; kt < NKT; ++kt) {
     const int r = min(row0 + kt * 16 + (lane & 7) + (lane >> 4) * 8, kRows - 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < KS; ++k) {
       uint32_t kb[4];
       ldmatrix_x4(qkv + r * kQkvStride + (64 + k * 16 + ((lane >> 3) & 1) * 8) * 2, kb);
       mma_16816(sc[kt][0], qa[k], kb[0], kb[1]);
@@ -486,14 +497,15 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     pa[kt][3] = HI ? pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi) : 0u;   // (row hi, keys 8-15)
   }
   // ---- O = P V ----
-  float o[8][4];
+  constexpr int NO = HSP / 8;                    // 8-wide output column tiles
+  float o[NO][4];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
   for (int kt = 0; kt < NKT; ++kt) {
     const int r = min(row0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {             // pairs of 8-wide output column tiles
+    for (int np = 0; np < NO / 2; ++np) {        // pairs of 8-wide output column tiles
       uint32_t vb[4];
       ldmatrix_x4_trans(qkv + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
       mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);
@@ -504,24 +516,32 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   const uint32_t r_lo = (uint32_t)(row0 + i_lo), r_hi = (uint32_t)(row0 + i_hi);
   const uint32_t y_lo = sbase + kSmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
   const uint32_t y_hi = sbase + kSmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
+  const uint32_t n0 = (uint32_t)co >> 3;         // first 16-byte chunk of this head inside the Y row
   if (i_lo < T) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n) sts32(y_lo + (((uint32_t)n << 4) ^ x_lo), pack_f16x2(o[n][0], o[n][1]));
+    for (int n = 0; n < NO; ++n) sts32(y_lo + (((n0 + (uint32_t)n) << 4) ^ x_lo), pack_f16x2(o[n][0], o[n][1]));
   }
   if (HI && i_hi < T) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n) sts32(y_hi + (((uint32_t)n << 4) ^ x_hi), pack_f16x2(o[n][2], o[n][3]));
+    for (int n = 0; n < NO; ++n) sts32(y_hi + (((n0 + (uint32_t)n) << 4) ^ x_hi), pack_f16x2(o[n][2], o[n][3]));
   }
 }
-__device__ __noinline__ void attention_head(uint8_t* sm, uint32_t sbase, int awarp, int lane, int S, int T) {
-  (void)sm;
+template <int HSP>
+__device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T) {
+  constexpr int NSUB = 64 / HSP;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
-  for (int item = awarp; item < S * MT; item += kAttnWarps) {
-    const int mt = MT - 1 - item / S, s = item % S;   // later query tiles see more keys: schedule them first
+  for (int item = awarp; item < S * MT * NSUB; item += kAttnWarps) {
+    const int sub = item % NSUB, it2 = item / NSUB;
+    const int mt = MT - 1 - it2 / S, s = it2 % S;     // later query tiles see more keys: schedule them first
     const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
-    if (mt == 0) { if (hi) attention_item<1, true>(sbase, lane, s * T, 0, T); else attention_item<1, false>(sbase, lane, s * T, 0, T); }
-    else { if (hi) attention_item<2, true>(sbase, lane, s * T, mt, T); else attention_item<2, false>(sbase, lane, s * T, mt, T); }
+    const int co = sub * HSP;
+    if (mt == 0) { if (hi) attention_item<1, true, HSP>(sbase, lane, s * T, 0, T, co); else attention_item<1, false, HSP>(sbase, lane, s * T, 0, T, co); }
+    else { if (hi) attention_item<2, true, HSP>(sbase, lane, s * T, mt, T, co); else attention_item<2, false, HSP>(sbase, lane, s * T, mt, T, co); }
   }
+}
+__device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T, int hsp) {
+  if (hsp == 64) attention_head_t<64>(sbase, awarp, lane, S, T);
+  else attention_head_t<32>(sbase, awarp, lane, S, T);
 }
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
@@ -559,6 +579,269 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) 
   c.arrive(B_OP_READY0 + b);
   emit(vb, 64 + c.hf * 32, h_s + 16384, c.hf * 4);
   emit(vb + 16, 64 + c.hf * 32 + 16, h_s + 16384, c.hf * 4 + 2);
+  fence_async_smem();
+  c.arrive(B_OP_READY0B + b);
+}
+
+// ================================ PREC: fp32-equivalent arithmetic on the tensor pipe ============================
+// The tile holds 64 sequence rows.  Every 16-bit operand is split x = hi + lo (two fp16 values, 22 mantissa bits)
+// and the MMA row dimension carries both images: TMEM lane 32 q + j (j < 16) is the "hi" row of sequence row
+// 16 q + j, lane 32 q + 16 + j its "lo" row.  One M = 128 MMA with the hi image of a weight tile followed by one
+// with its lo image accumulates [A_hi; A_lo] (W_hi + W_lo)^T, so that for every sequence row
+//     D[hi lane] + D[lo lane] = (A_hi + A_lo) (W_hi + W_lo)^T            (all four cross terms, fp32 accumulate).
+// The two lanes of a row belong to the same warp: every drain adds them with one __shfl_xor(16) per element and
+// the two threads then share the row's columns.  LayerNorm is two-pass fp32, GELU is erff, attention is fp32 FMA
+// out of an fp32 staging buffer, the residual stream stays fp32 in TMEM (split over the two lanes).
+// The schedule, the barriers and the shared / tensor memory maps are those of the fp16 mode; the weight tape holds
+// [hi tile | lo tile] per ring group.
+__device__ __forceinline__ float shx16(float v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
+// (a, b) -> packed fp16 hi pair and the packed fp16 rounding of the remainders
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  hi = h2bits(h);
+  lo = h2bits(__floats2half2_rn(a - hf.x, b - hf.y));
+}
+// 8 consecutive K elements -> the 16-byte chunk of the hi row and of the lo row (16 rows = 2048 bytes below)
+__device__ __forceinline__ void st_chunk_split(uint32_t addr_hi, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  sts128(addr_hi, h[0], h[1], h[2], h[3]);
+  sts128(addr_hi + 2048u, l[0], l[1], l[2], l[3]);
+}
+
+// A <- split(LayerNorm0(X + pend)).  Each thread reads 128 columns of its TMEM lane, hands 64 of them to its pair
+// thread and receives the pair's 64 in exchange: afterwards it owns 64 complete columns of the sequence row.
+template <bool DBG>
+__device__ __noinline__ void ln_pass_p(const Compute c, uint32_t vec_s, float inv_d, int d_true, float* trace_row) {
+  float va[32], vb[32], x[64];
+  const int col0 = c.hf * 128;
+  const int keep0 = col0 + c.is_lo * 64;
+  tmem_ld32(c.lane_addr(kColX + col0), va);
+  tmem_ld32(c.lane_addr(kColX + col0 + 64), vb);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = (c.is_lo ? vb[i] : va[i]) + shx16(c.is_lo ? va[i] : vb[i]);
+  tmem_ld32(c.lane_addr(kColX + col0 + 32), va);
+  tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[32 + i] = (c.is_lo ? vb[i] : va[i]) + shx16(c.is_lo ? va[i] : vb[i]);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    const float4 pd = lds128f_ro(vec_s + (uint32_t)(keep0 + i) * 4u);
+    x[i] += pd.x; x[i + 1] += pd.y; x[i + 2] += pd.z; x[i + 3] += pd.w;
+    s += (x[i] + x[i + 1]) + (x[i + 2] + x[i + 3]);
+  }
+  if (DBG) {
+    if (trace_row != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) trace_row[keep0 + i] = x[i];
+    }
+  }
+  s += shx16(s);
+  float* stats = reinterpret_cast<float*>(c.sm + kSmStats);        // [sum: 2 x 64 | squares: 2 x 64]
+  if (!c.is_lo) stats[c.hf * 64 + c.srow] = s;
+  compute_sync();
+  const float mean = (s + stats[(c.hf ^ 1) * 64 + c.srow]) * inv_d;
+  // second pass over the true lanes only (padding columns are zero, not mean)
+  const int nv = min(max(d_true - keep0, 0), 64);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) { const float t = x[i] - mean; x[i] = t; if (i < nv) q = fmaf(t, t, q); }
+  q += shx16(q);
+  if (!c.is_lo) stats[128 + c.hf * 64 + c.srow] = q;
+  compute_sync();
+  const float var = (q + stats[128 + (c.hf ^ 1) * 64 + c.srow]) * inv_d;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  // K atom of this thread's 64 columns; hi row = lane & ~16, the lo row is 16 rows (2048 bytes) further down
+  const uint32_t a_hi = c.sbase + kSmA + (uint32_t)(c.hf * 2 + c.is_lo) * 16384u + c.row_off - (uint32_t)c.is_lo * 2048u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = x[k * 8 + i] * rstd;
+    st_chunk_split(a_hi + (((uint32_t)k << 4) ^ c.rx4), y);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  c.arrive(B_A_READY);
+}
+
+// [Q|K|V] accumulator of one attention pass -> fp32 staging rows (Q gets its bias).  Per 32-column piece the pair
+// threads exchange halves: each ends up with 16 columns of Q, of K and of V of the sequence row.
+__device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
+  float v0[32], v1[32], v2[32];
+  const int colb = c.hf * 32;
+  tmem_ld32(c.lane_addr(kColS0 + colb), v0);
+  tmem_ld32(c.lane_addr(kColS0 + 64 + colb), v1);
+  tmem_ld32(c.lane_addr(kColS0 + 128 + colb), v2);
+  tmem_wait_ld();
+  tc_fence_before();
+  c.arrive(B_ACC_EMPTY0);
+  const int cs = colb + c.is_lo * 16;                     // first of this thread's 16 columns inside each 64-block
+  const uint32_t dst = c.sbase + kSmQkv + (uint32_t)c.srow * kQkvStrideP + (uint32_t)cs * 4u;
+  auto emit = [&](const float (&v)[32], uint32_t d, bool bias) {
+    float r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = (c.is_lo ? v[16 + i] : v[i]) + shx16(c.is_lo ? v[i] : v[16 + i]);
+    if (bias) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b0 = lds128f_ro(bq_s + (uint32_t)(cs + i) * 4u);
+        r[i] += b0.x; r[i + 1] += b0.y; r[i + 2] += b0.z; r[i + 3] += b0.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      sts128(d + i * 4, __float_as_uint(r[i]), __float_as_uint(r[i + 1]), __float_as_uint(r[i + 2]), __float_as_uint(r[i + 3]));
+  };
+  emit(v0, dst, true); emit(v1, dst + 256, false); emit(v2, dst + 512, false);
+}
+
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// Causal softmax(Q K^T) V in fp32 out of the staging buffer: four threads (a lane quad) per (sequence row, head).
+// Quad member m scores keys m, m + 4, ... against the query row held in its registers, the quad reduces the row
+// maximum / sum with two shuffles each, then member m accumulates output columns [m HSP/4, (m + 1) HSP/4) over all
+// keys (probabilities arrive by quad shuffle).  Loop bounds are the warp's longest row (its 8 rows are consecutive,
+// so they differ by at most 7 keys).  Q is pre-scaled by log2(e) / sqrt(hs).  Output: split into the Y atom.
+// Only the 8 compute warps carry rows (64 rows x 4 threads); with two heads per pass they take two rounds.
+template <int HSP>
+__device__ __forceinline__ void attention_head_pt(uint32_t sbase, int awarp, int lane, int S, int T) {
+  constexpr int NSUB = 64 / HSP, QV = HSP / 4, OC = HSP / 4;     // float4 per query row; output columns per quad member
+  constexpr int kMaxJJ = (kMaxTokens + 3) / 4;
+  const uint32_t base = sbase + kSmQkv;
+  if (awarp >= 8) return;
+  const int qm = lane & 3, qbase = lane & ~3;
+  const int rho = awarp * 8 + (lane >> 2);                       // sequence row of this quad
+  const int seq = rho / T, i = rho - seq * T, row0 = seq * T;
+  const bool valid = seq < S;
+  const int i_eff = valid ? i : -1;
+  int imax = i_eff;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+  if (imax < 0) return;                                          // warp-uniform: no row of this warp is inside the tile
+#pragma unroll 1
+  for (int sub = 0; sub < NSUB; ++sub) {
+    const uint32_t co = (uint32_t)(sub * HSP) * 4u;
+    float4 q[QV];
+    const uint32_t qrow = base + (uint32_t)(valid ? rho : 0) * kQkvStrideP + co;
+#pragma unroll
+    for (int e = 0; e < QV; ++e) q[e] = lds128f(qrow + e * 16);
+    float sc[kMaxJJ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < kMaxJJ; ++jj) {
+      sc[jj] = -INFINITY;
+      if (jj * 4 > imax) continue;                               // uniform
+      const int j = jj * 4 + qm;
+      if (j <= i_eff) {
+        const uint32_t krow = base + (uint32_t)(row0 + j) * kQkvStrideP + 256u + co;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < QV; e += 2) {
+          const float4 b0 = lds128f(krow + e * 16), b1 = lds128f(krow + e * 16 + 16);
+          s0 = fmaf(q[e].w, b0.w, fmaf(q[e].z, b0.z, fmaf(q[e].y, b0.y, fmaf(q[e].x, b0.x, s0))));
+          s1 = fmaf(q[e + 1].w, b1.w, fmaf(q[e + 1].z, b1.z, fmaf(q[e + 1].y, b1.y, fmaf(q[e + 1].x, b1.x, s1))));
+        }
+        sc[jj] = s0 + s1;
+        mx = fmaxf(mx, sc[jj]);
+      }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < kMaxJJ; ++jj) {
+      sc[jj] = (jj * 4 + qm <= i_eff) ? exp2f(sc[jj] - mx) : 0.f;
+      sum += sc[jj];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = valid ? __fdiv_rn(1.0f, sum) : 0.f;
+    float o[OC];
+#pragma unroll
+    for (int e = 0; e < OC; ++e) o[e] = 0.f;
+    const uint32_t vcol = base + 512u + co + (uint32_t)(qm * OC) * 4u;
+#pragma unroll
+    for (int jj = 0; jj < kMaxJJ; ++jj) {
+      if (jj * 4 > imax) continue;                               // uniform
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = jj * 4 + m;
+        const float pw = __shfl_sync(0xffffffffu, sc[jj], qbase + m);
+        if (j <= i_eff) {
+          const uint32_t vrow = vcol + (uint32_t)(row0 + j) * kQkvStrideP;
+#pragma unroll
+          for (int e = 0; e < OC / 4; ++e) {
+            const float4 vv = lds128f(vrow + e * 16);
+            o[4 * e] = fmaf(pw, vv.x, o[4 * e]); o[4 * e + 1] = fmaf(pw, vv.y, o[4 * e + 1]);
+            o[4 * e + 2] = fmaf(pw, vv.z, o[4 * e + 2]); o[4 * e + 3] = fmaf(pw, vv.w, o[4 * e + 3]);
+          }
+        }
+      }
+    }
+    if (valid) {
+      const uint32_t ur = (uint32_t)rho, mrow = ((ur >> 4) << 5) | (ur & 15u);      // hi row of the sequence row
+      const uint32_t col = (uint32_t)(sub * HSP + qm * OC);                          // multiple of 8
+      const uint32_t a = sbase + kSmY + mrow * 128u;
+#pragma unroll
+      for (int k = 0; k < OC / 8; ++k) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = o[k * 8 + e] * inv;
+        st_chunk_split(a + ((((col >> 3) + (uint32_t)k) ^ (mrow & 7u)) << 4), y);
+      }
+    }
+  }
+}
+__device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T, int hsp) {
+  if (hsp == 64) attention_head_pt<64>(sbase, awarp, lane, S, T);
+  else attention_head_pt<32>(sbase, awarp, lane, S, T);
+}
+
+__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
+// FC1 chunk accumulator (buffer b) -> + b1 -> exact erf-GELU (fp32) -> split -> H[b] (two K atoms).
+// b1_s = shared address of this chunk's 128 biases (fp32).
+__device__ __noinline__ void drain_gelu_p(const Compute c, int b, uint32_t b1_s) {
+  float va[32], vb[32];
+  const uint32_t s_col = (b ? kColS1 : kColS0) + c.hf * 32;
+  const uint32_t h_hi = c.sbase + (b ? kSmH1 : kSmH0) + c.row_off - (uint32_t)c.is_lo * 2048u;
+  tmem_ld32(c.lane_addr(s_col), va);
+  tmem_ld32(c.lane_addr(s_col + 64), vb);
+  tmem_wait_ld();
+  tc_fence_before();
+  c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
+  const int cs = c.hf * 32 + c.is_lo * 16;                // this thread's 16 columns inside each 64-wide K atom
+  auto emit = [&](const float (&v)[32], uint32_t bias_s, uint32_t atom) {
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] = (c.is_lo ? v[16 + i] : v[i]) + shx16(c.is_lo ? v[i] : v[16 + i]);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b0 = lds128f_ro(bias_s + (uint32_t)(cs + i) * 4u);
+      g[i] = gelu_erf(g[i] + b0.x); g[i + 1] = gelu_erf(g[i + 1] + b0.y);
+      g[i + 2] = gelu_erf(g[i + 2] + b0.z); g[i + 3] = gelu_erf(g[i + 3] + b0.w);
+    }
+    const uint32_t k0 = (uint32_t)cs >> 3;
+    st_chunk_split(atom + ((k0 << 4) ^ c.rx4), g);
+    st_chunk_split(atom + (((k0 + 1) << 4) ^ c.rx4), g + 8);
+  };
+  emit(va, b1_s, h_hi);
+  fence_async_smem();                     // K atom 0 of H is complete: FC2's first k-block may start
+  c.arrive(B_OP_READY0 + b);
+  emit(vb, b1_s + 256u, h_hi + 16384u);
   fence_async_smem();
   c.arrive(B_OP_READY0B + b);
 }
@@ -693,15 +976,19 @@ __device__ __forceinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uin
 struct EmbedTask {
   const float* src;      // obs atom: state / goal vector of this row (nullptr = zeros)
   int row, atom, vs, tok, xoff;   // xoff >= 0: action row, offset of its act values in the tile's x buffer
+  int part;              // PREC: 0 = fp16 hi image of the row, 1 = lo image; -1 = bf16 (fp16-mode embedding GEMM)
   bool valid;
 };
+template <bool PREC>
 __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int tile) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   EmbedTask e;
   e.row = c.ctid & (kRows - 1);
   e.atom = c.ctid >> 7;
-  e.vs = e.row / p.T;
-  e.tok = e.row - e.vs * p.T;
+  const int srow = PREC ? ((e.row >> 5) << 4) | (e.row & 15) : e.row;   // sequence row of this operand row
+  e.part = PREC ? (e.row >> 4) & 1 : -1;
+  e.vs = srow / p.T;
+  e.tok = srow - e.vs * p.T;
   const int ls = cfg ? (e.vs >> 1) : e.vs;
   const int seq = tile * (cfg ? p.S / 2 : p.S) + ls;
   e.valid = e.vs < p.S && seq < p.B;
@@ -740,8 +1027,15 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
         for (int i = 0; i < 64; ++i) if (i < obs) v[i] = __ldg(e.src + i);
       }
     }
+    if (e.part >= 0) {
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) st_chunk(atom, e.row, ch, v + ch * 8);
+      for (int i = 0; i < 64; ++i) if (e.part) v[i] -= __half2float(__float2half_rn(v[i]));
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) st_chunk_h(atom, e.row, ch, v + ch * 8);
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) st_chunk(atom, e.row, ch, v + ch * 8);
+    }
   } else {
     const bool inner = (flags & BESO_FLAG_INNER) != 0;
     const float sg = e.valid ? sigv[e.vs] : 1.0f;
@@ -759,14 +1053,16 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
         if (e.valid) {
           if (k < kOneHot0) {
             if (e.xoff >= 0 && k < act) x = xsrc[e.xoff + k] * c_in;
+            else if (e.part >= 0) { if (e.tok == 0 && k == act) x = cn; }       // split below: [cn] . [sigma_emb.w]
             else if (e.tok == 0 && k >= act && k < act + 3) x = (k == act + 1) ? (cn - cn_hi) : cn_hi;
-          } else if (k == hot || k == hot + 1) {
+          } else if (k == hot || (k == hot + 1 && e.part < 0)) {
             x = 1.0f;
           }
         }
+        if (e.part == 1) x -= __half2float(__float2half_rn(x));
         v[i] = x;
       }
-      st_chunk(atom, e.row, ch, v);
+      if (e.part >= 0) st_chunk_h(atom, e.row, ch, v); else st_chunk(atom, e.row, ch, v);
     }
   }
   fence_async_smem();
@@ -818,7 +1114,7 @@ __device__ __noinline__ void tile_end(const Compute c, const FastParams& p, int 
 }
 
 // noise levels of this evaluation + the embedding-GEMM A operand
-template <bool DBG>
+template <bool DBG, bool PREC>
 __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p, const SampleArgs& sa, int tile, int step, int second) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   const int nls = cfg ? p.S / 2 : p.S, seq0 = tile * nls;
@@ -831,14 +1127,14 @@ __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p,
     xb.sigv[i] = sa.n_steps ? s_eval : ((seq0 + ls < p.B) ? __ldg(p.sigma + seq0 + ls) : 1.0f);
   }
   compute_sync();
-  const EmbedTask etask = make_embed_task(c, p, tile);
+  const EmbedTask etask = make_embed_task<PREC>(c, p, tile);
   stamp<DBG>(c);
   build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv);
   stamp<DBG>(c);
 }
 
 // ln_f + action head read-out + pre-conditioning (+ CFG mix) + sampler update of x.  Returns the barrier phases.
-template <bool DBG>
+template <bool DBG, bool PREC>
 __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, const SampleArgs& sa, int tile, int step, int second,
                                                float* trace_row) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
@@ -856,7 +1152,8 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
   c.wait(B_X_DONE);
   tc_fence_after();
   stamp<DBG>(c);
-  ln_pass<DBG>(c, c.sbase + kSmVecA, trace_row);
+  if constexpr (PREC) ln_pass_p<DBG>(c, c.sbase + kSmVecA, p.inv_d, p.d_true, trace_row);
+  else ln_pass<DBG>(c, c.sbase + kSmVecA, p.inv_d, trace_row);
   stamp<DBG>(c);
   c.wait(B_ACC_FULL0);
   tc_fence_after();
@@ -866,11 +1163,15 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
-  const float* hb = vecA + 3 * kD;
-  const int vs = c.row / p.T, tok = c.row - vs * p.T;
+  if constexpr (PREC) {                             // hi lane + lo lane of the sequence row
+#pragma unroll
+    for (int a = 0; a < 16; ++a) pr[a] += shx16(pr[a]);
+  }
+  const float* hb = vecA + kVecBq;
+  const int vs = c.srow / p.T, tok = c.srow - vs * p.T;
   const int j = tok - 1 - p.G;
   const int ls = cfg ? (vs >> 1) : vs;
-  const bool act_row = (c.hf == 0) && vs < p.S && tok > p.G && (j & 1) && (ls < ns);
+  const bool act_row = (c.hf == 0) && !c.is_lo && vs < p.S && tok > p.G && (j & 1) && (ls < ns);
   const int xo = (ls * p.t + (j >> 1)) * p.act;
   // D = c_out * F + c_skip * x (score_wrappers.py:81-96) of action column a of this row, straight from the
   // accumulator registers (no per-thread array: it would live in local memory)
@@ -958,9 +1259,11 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
 // producer fetches half of every ring stage and multicasts it into both CTAs (TMA .multicast::cluster), a stage
 // is free again when both CTAs' MMAs have read it (multicast commits).  Halves the L2 -> SM request traffic,
 // which at full-chip scale is within a factor 1.5 of the L2 throughput cap.
-template <int CG, bool DBG, int MC>
+// PREC = true: fp32-equivalent mode (split operands, 64 sequence rows per tile; see the PREC section above).
+template <int CG, bool DBG, int MC, bool PREC>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
+  static_assert(!PREC || (CG == 1 && MC == 1), "the precise mode runs single-CTA MMAs");
   extern __shared__ uint8_t smem_raw[];
   // dynamic shared memory is at least 16-byte aligned; the operand tiles need 1024
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1036,20 +1339,25 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         __syncwarp();
         g += 2;
       };
+      // PREC: every ring group is followed by the lo image of the same weights
+      constexpr uint32_t kImages = PREC ? 2u : 1u;
       for (int it = 0; it < my_tiles * p.evals; ++it) {
         const uint8_t* src = p.tape;
-        fill(src, 32768); fill(src + 32768, 32768); src += 65536;               // embedding
+        auto fills = [&](uint32_t n, uint32_t bytes) {
+#pragma unroll 1
+          for (uint32_t i = 0; i < n * kImages; ++i) { fill(src, bytes); src += bytes; }
+        };
+        fills(2, 32768);                                     // embedding
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
-          for (uint32_t i = 0; i < 20; ++i) {                // Q0 Q1 P0 Q2 P1 Q3 P2 P3 (QKV = 4 groups of 24 KB)
-            const uint32_t bytes = ((0xC2100u >> i) & 1u) ? 32768u : 24576u;   // proj groups at 8, 13, 18, 19
-            fill(src, bytes); src += bytes;
+          for (int h = 0; h <= p.npass; ++h) {               // Q0 Q1 P0 Q2 P1 ... P(n-1): QKV = 4 groups of 24 KB, proj = 32 KB
+            if (h < p.npass) fills(4, 24576);
+            if (h >= 1) fills(1, 32768);
           }
-#pragma unroll 1
-          for (uint32_t i = 0; i < 32; ++i) { fill(src, 32768); src += 32768; }   // FC1 / FC2 groups
+          fills(32, 32768);                                  // FC1 / FC2 groups
         }
-        fill(src, 8192);                                     // action head: 4 K blocks of [16 x 64]
+        fills(1, 8192);                                      // action head: 4 K blocks of [16 x 64]
       }
     } else {
     for (int it = 0; it < my_tiles * p.evals; ++it) {
@@ -1114,38 +1422,44 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         __syncwarp();
         g += 2;
       };
+      // PREC: the hi image of the weights, then the lo image, into the same accumulator
+      auto group2 = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, uint32_t a_off, uint32_t d_col, uint32_t acc) {
+        group(n_tag, nkb_tag, bstep_tag, bf16_tag, a_off, d_col, acc);
+        if constexpr (PREC) group(n_tag, nkb_tag, bstep_tag, bf16_tag, a_off, d_col, 1);
+      };
       using std::integral_constant;
+      constexpr uint32_t kEmbBf16 = PREC ? 0u : 1u;          // the precise mode splits the raw inputs into fp16 hi + lo
 #define BESO_IC(v) integral_constant<uint32_t, (v)>{}
       for (int it = 0; it < my_tiles * p.evals; ++it) {
         if constexpr (DBG) tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
         // ---- embedding GEMM (bf16): X = A_emb W_emb^T, K = 128 ----
         job_begin();
         jwait(B_A_READY);
-        group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(1), kSmA, kColX, 0);
-        group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(1), kSmA + 16384, kColX, 1);
+        group2(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(kEmbBf16), kSmA, kColX, 0);
+        group2(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(kEmbBf16), kSmA + 16384, kColX, 1);
         jcommit(B_X_DONE);
         job_end();
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
           // ---- attention half: Q0 Q1 P0 Q2 P1 Q3 P2 P3 ----
 #pragma unroll 1
-          for (int h = 0; h <= kH; ++h) {
-            if (h < kH) {                                    // [Q|K|V] of head h -> S0 (192 columns)
+          for (int h = 0; h <= p.npass; ++h) {
+            if (h < p.npass) {                               // [Q|K|V] of attention pass h -> S0 (192 columns)
               job_begin();
               jwait(B_ACC_EMPTY0);
               if (h == 0) jwait(B_A_READY);
 #pragma unroll
               for (uint32_t kb = 0; kb < 4; ++kb)
-                group(BESO_IC(192), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, kColS0, kb);
+                group2(BESO_IC(192), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, kColS0, kb);
               jcommit(B_ACC_FULL0);
               job_end();
             }
             if (h >= 1) {                                    // X += Y_{h-1} Wproj[:, h-1]^T
               job_begin();
               jwait(B_Y_READY);
-              group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmY, kColX, 1);
+              group2(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmY, kColX, 1);
               jcommit(B_Y_EMPTY);
-              if (h == kH) jcommit(B_X_DONE);
+              if (h == p.npass) jcommit(B_X_DONE);
               job_end();
             }
           }
@@ -1157,8 +1471,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
               job_begin();
               jwait(B_ACC_EMPTY0 + b);
               if (c == 0) jwait(B_A_READY);
-              group(BESO_IC(128), BESO_IC(2), BESO_IC(16384), BESO_IC(0), kSmA, b ? kColS1 : kColS0, 0);
-              group(BESO_IC(128), BESO_IC(2), BESO_IC(16384), BESO_IC(0), kSmA + 32768, b ? kColS1 : kColS0, 1);
+              group2(BESO_IC(128), BESO_IC(2), BESO_IC(16384), BESO_IC(0), kSmA, b ? kColS1 : kColS0, 0);
+              group2(BESO_IC(128), BESO_IC(2), BESO_IC(16384), BESO_IC(0), kSmA + 32768, b ? kColS1 : kColS0, 1);
               jcommit(B_ACC_FULL0 + b);
               job_end();
             }
@@ -1166,9 +1480,9 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
               const uint32_t b = (c - 1) & 1;
               job_begin();
               jwait(B_OP_READY0 + b);
-              group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), b ? kSmH1 : kSmH0, kColX, 1);
+              group2(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), b ? kSmH1 : kSmH0, kColX, 1);
               jwait(B_OP_READY0B + b);
-              group(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), (b ? kSmH1 : kSmH0) + 16384, kColX, 1);
+              group2(BESO_IC(256), BESO_IC(1), BESO_IC(0), BESO_IC(0), (b ? kSmH1 : kSmH0) + 16384, kColX, 1);
               jcommit(B_OP_EMPTY0 + b);
               if (c == 8) jcommit(B_X_DONE);
               job_end();
@@ -1179,7 +1493,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
         job_begin();
         jwait(B_A_READY);
         jwait(B_ACC_EMPTY0);
-        group(BESO_IC(16), BESO_IC(4), BESO_IC(2048), BESO_IC(0), kSmA, kColS0, 0);
+        group2(BESO_IC(16), BESO_IC(4), BESO_IC(2048), BESO_IC(0), kSmA, kColS0, 0);
         jcommit(B_ACC_FULL0);
         job_end();
       }
@@ -1226,11 +1540,12 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   } else if (warp >= kHelperWarp0) {
     // ======================= attention helper warps (8, 9) =======================
     uint32_t y_phase = 1;
-    for (int it = 0; it < my_tiles * p.evals * p.L * kH; ++it) {
+    for (int it = 0; it < my_tiles * p.evals * p.L * p.npass; ++it) {
       attn_sync();
       spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
       y_phase ^= 1u;
-      attention_head(sm, sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
+      if constexpr (PREC) attention_head_p(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T, p.hsp);
+      else attention_head(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T, p.hsp);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -1245,6 +1560,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     c.ctid = threadIdx.x - kComputeWarp0 * 32;
     c.lane = lane; c.wq = warp & 3; c.hf = (warp - kComputeWarp0) >> 2;
     c.row = c.wq * 32 + lane;
+    c.is_lo = PREC ? (lane >> 4) : 0;
+    c.srow = PREC ? c.wq * 16 + (lane & 15) : c.row;
     c.row_off = (uint32_t)c.row * 128u; c.rx4 = ((uint32_t)c.row & 7u) << 4;
     c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
     c.cg = CG;
@@ -1260,14 +1577,14 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       int step = 0, second = 0;
       for (int ev = 0; ev < p.evals; ++ev) {
         auto trace_row = [&](int slot) -> float* {
-          return (DBG && p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.row) * kD : nullptr;
+          return (DBG && p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.srow) * kD : nullptr;
         };
         if constexpr (DBG) {
           if (c.ctid == 0)
             *reinterpret_cast<long long**>(sm + kSmTlCursor) =
                 (p.timeline != nullptr && blockIdx.x == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
         }
-        eval_prologue<DBG>(c, p, sa, tile, step, second);
+        eval_prologue<DBG, PREC>(c, p, sa, tile, step, second);
 
         for (int l = 0; l < p.L; ++l) {
           // ---------------- attention half ----------------
@@ -1276,17 +1593,21 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           c.wait(B_X_DONE);
           tc_fence_after();
           stamp<DBG>(c);
-          ln_pass<DBG>(c, vecA_s, trace_row(2 * l));
+          if constexpr (PREC) ln_pass_p<DBG>(c, vecA_s, p.inv_d, p.d_true, trace_row(2 * l));
+          else ln_pass<DBG>(c, vecA_s, p.inv_d, trace_row(2 * l));
           stamp<DBG>(c);
-          for (int h = 0; h < kH; ++h) {
+          for (int h = 0; h < p.npass; ++h) {
             c.wait(B_ACC_FULL0);
             tc_fence_after();
             stamp<DBG>(c);
-            drain_qkv(c, vecA_s + (uint32_t)(3 * kD + h * 192) * 4u);   // arrives on ACC_EMPTY0 once its TMEM reads are done
+            // arrives on ACC_EMPTY0 once its TMEM reads are done
+            if constexpr (PREC) drain_qkv_p(c, vecA_s + (uint32_t)(kVecBq + h * 192) * 4u);
+            else drain_qkv(c, vecA_s + (uint32_t)(kVecBq + h * 192) * 4u);
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
             c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
             stamp<DBG>(c);
-            attention_head(sm, sbase, c.ctid >> 5, lane, p.S, p.T);
+            if constexpr (PREC) attention_head_p(sbase, c.ctid >> 5, lane, p.S, p.T, p.hsp);
+            else attention_head(sbase, c.ctid >> 5, lane, p.S, p.T, p.hsp);
             fence_async_smem();
             c.arrive(B_Y_READY);
             stamp<DBG>(c);
@@ -1299,14 +1620,17 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           c.wait(B_X_DONE);
           tc_fence_after();
           stamp<DBG>(c);
-          ln_pass<DBG>(c, vecM_s, trace_row(2 * l + 1));
+          if constexpr (PREC) ln_pass_p<DBG>(c, vecM_s, p.inv_d, p.d_true, trace_row(2 * l + 1));
+          else ln_pass<DBG>(c, vecM_s, p.inv_d, trace_row(2 * l + 1));
           stamp<DBG>(c);
           for (int ch = 0; ch < 8; ++ch) {
             const int b = ch & 1;
             c.wait2(b ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
             stamp<DBG>(c);
-            drain_gelu(c, b, vecM_s + (uint32_t)kD * 4u + (uint32_t)ch * 256u);   // arrives on ACC_EMPTY and (twice) on OP_READY itself
+            // arrives on ACC_EMPTY and (twice) on OP_READY itself
+            if constexpr (PREC) drain_gelu_p(c, b, vecM_s + (uint32_t)kVecB1F * 4u + (uint32_t)ch * 512u);
+            else drain_gelu(c, b, vecM_s + (uint32_t)kVecB1H * 4u + (uint32_t)ch * 256u);
             stamp<DBG>(c);
           }
           compute_sync();                                   // everyone done with vecM(l)
@@ -1314,7 +1638,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           load_vec_async(c, kSmVecM, p.vec + (size_t)nl * layer_stride + kVecAFloats, kVecMFloats);
         }
         // ---------------- ln_f + action head + pre-conditioning + sampler update ----------------
-        c.phases = eval_epilogue<DBG>(c, p, sa, tile, step, second, trace_row(2 * p.L));
+        c.phases = eval_epilogue<DBG, PREC>(c, p, sa, tile, step, second, trace_row(2 * p.L));
         if (sa.n_steps) {
           const bool two = (sa.sampler == BESO_SAMPLER_HEUN && sa.sig[step + 1] != 0.0f) ||
                            (sa.sampler == BESO_SAMPLER_TWO_STAGE && sa.sigb[step] != 0.0f);
@@ -1423,23 +1747,36 @@ __global__ void __launch_bounds__(192, 1) mma_rate_kernel(long long* out, const 
 }
 
 // ================================ weight packing ===================================================
-struct PackTile {       // one [rows x 64] bf16 SW128 sub-tile of the tape from a row-major fp32 matrix
-  const float* src; int ld, row0, col0, rows, valid_rows, valid_cols; float scale; uint32_t dst;
+// Row / column index of a packed operand -> index in the reference tensor.  Heads are packed 64 columns per
+// attention pass with the head size padded to hsp (32 or 64): packed index i of a pass whose first head is head0
+// is element i % hsp of head head0 + i / hsp (zero beyond the true head size hs).  hsp == 0: identity.
+struct IndexMap { int hsp, hs, head0, n_heads; };
+__device__ __forceinline__ int map_index(const IndexMap& m, int i, int limit) {
+  if (m.hsp == 0) return i < limit ? i : -1;
+  const int head = m.head0 + i / m.hsp, e = i % m.hsp;
+  return (e < m.hs && head < m.n_heads) ? head * m.hs + e : -1;
+}
+struct PackTile {       // one [rows x 64] fp16 SW128 sub-tile of the tape from a row-major fp32 matrix
+  const float* src; int ld, row0, col0, rows, n_rows, n_cols; float scale; uint32_t dst;
   const float* colscale;   // optional per-input-column factor: the preceding LayerNorm's weight
+  IndexMap rmap, cmap;     // packed row / column -> source row / column (identity: index + row0 / col0 below n_rows / n_cols)
+  int part;                // 0: fp16(x)   1: hi image = fp16(x)   2: lo image = fp16(x - hi)
 };
 __global__ void pack_tiles_kernel(const PackTile* tiles, uint8_t* tape) {
   const PackTile t = tiles[blockIdx.x];
   for (int idx = threadIdx.x; idx < t.rows * 8; idx += blockDim.x) {
     const int r = idx >> 3, chunk = idx & 7;
+    const int sr = map_index(t.rmap, t.row0 + r, t.n_rows);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = chunk * 8 + i;
+      const int sc = map_index(t.cmap, t.col0 + chunk * 8 + i, t.n_cols);
       float x = 0.f;
-      if (r < t.valid_rows && k < t.valid_cols) {
-        x = t.src[(size_t)(t.row0 + r) * t.ld + t.col0 + k] * t.scale;
-        if (t.colscale != nullptr) x *= t.colscale[t.col0 + k];
+      if (sr >= 0 && sc >= 0) {
+        x = t.src[(size_t)sr * t.ld + sc] * t.scale;
+        if (t.colscale != nullptr) x *= t.colscale[sc];
       }
+      if (t.part == 2) x -= __half2float(__float2half_rn(x));
       v[i] = x;
     }
     st_chunk_h(tape + t.dst, r, chunk, v);
@@ -1448,14 +1785,15 @@ __global__ void pack_tiles_kernel(const PackTile* tiles, uint8_t* tape) {
 
 struct EmbSrc {
   const float *pos, *tokw, *tokb, *sigw, *sigb, *actw, *actb;
-  const float* resid_bias[2 * kMaxLayers];     // attn.proj.bias and mlp.2.bias of every layer
-  int obs, act, G, W, L;
+  const float* resid_bias[2 * kMaxLayers];     // effective attn.proj bias (256 padded) and mlp.2.bias (d) of every layer
+  int obs, act, G, W, L, d, prec;
 };
-// Embedding GEMM B operand: W_emb[n][k], n < 256, k < 128 (atom 0 = obs, atom 1 = misc), as 8 fills
-// [128 rows x 64] in (k-atom, row-half) order.
+// Embedding GEMM B operand: W_emb[n][k], n < 256, k < 128 (atom 0 = obs, atom 1 = misc), as fills of
+// [128 rows x 64] in (k-atom, [image,] row-half) order.  fp16 mode: bf16, tables as hi + lo column pairs.
+// PREC: fp16 hi image (blockIdx.y = 0) and lo image (1) of the plain values, one column per table entry.
 __global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape) {
   const int fill = blockIdx.x;                 // 0..3: atom = fill >> 1, rows (fill & 1) * 128 ..
-  const int atom = fill >> 1, n0 = (fill & 1) * 128;
+  const int atom = fill >> 1, n0 = (fill & 1) * 128, image = blockIdx.y;
   for (int idx = threadIdx.x; idx < 128 * 8; idx += blockDim.x) {
     const int r = idx >> 3, chunk = idx & 7, n = n0 + r;
     float v[8];
@@ -1463,30 +1801,41 @@ __global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape) {
     for (int i = 0; i < 8; ++i) {
       const int k = chunk * 8 + i;
       float x = 0.f;
-      if (atom == 0) {
+      if (n >= s.d) {
+      } else if (atom == 0) {
         if (k < s.obs) x = s.tokw[(size_t)n * s.obs + k];
       } else if (k < s.act) {
         x = s.actw[(size_t)n * s.act + k];
       } else if (k < s.act + 3) {
         const float w = s.sigw[n];
-        const float hi = __bfloat162float(__float2bfloat16_rn(w));
-        x = (k == s.act + 2) ? (w - hi) : hi;    // A holds [cn_hi, cn_lo, cn_hi]
+        if (s.prec) {
+          x = (k == s.act) ? w : 0.f;
+        } else {
+          const float hi = __bfloat162float(__float2bfloat16_rn(w));
+          x = (k == s.act + 2) ? (w - hi) : hi;    // A holds [cn_hi, cn_lo, cn_hi]
+        }
       } else if (k >= kOneHot0 && k < kOneHot0 + 2 * kMaxTokens) {
         const int tok = (k - kOneHot0) >> 1;
         float tbl;
         if (tok == 0) tbl = s.sigb[n];
-        else if (tok <= s.G) tbl = s.tokb[n] + s.pos[(size_t)(tok - 1) * kD + n];
+        else if (tok <= s.G) tbl = s.tokb[n] + s.pos[(size_t)(tok - 1) * s.d + n];
         else {
           const int j = tok - 1 - s.G, step = j >> 1;
-          tbl = (step < s.W) ? ((j & 1) ? s.actb[n] : s.tokb[n]) + s.pos[(size_t)(s.G + step) * kD + n] : 0.f;
+          tbl = (step < s.W) ? ((j & 1) ? s.actb[n] : s.tokb[n]) + s.pos[(size_t)(s.G + step) * s.d + n] : 0.f;
         }
         for (int i2 = 0; i2 < 2 * s.L; ++i2) tbl += s.resid_bias[i2][n];   // all residual-branch biases, up front
-        const float hi = __bfloat162float(__float2bfloat16_rn(tbl));
-        x = ((k - kOneHot0) & 1) ? (tbl - hi) : hi;
+        if (s.prec) {
+          x = ((k - kOneHot0) & 1) ? 0.f : tbl;
+        } else {
+          const float hi = __bfloat162float(__float2bfloat16_rn(tbl));
+          x = ((k - kOneHot0) & 1) ? (tbl - hi) : hi;
+        }
       }
+      if (s.prec && image == 1) x -= __half2float(__float2half_rn(x));
       v[i] = x;
     }
-    st_chunk(tape + (size_t)fill * 16384, r, chunk, v);
+    if (s.prec) st_chunk_h(tape + (size_t)atom * 65536 + (size_t)image * 32768 + (size_t)(fill & 1) * 16384, r, chunk, v);
+    else st_chunk(tape + (size_t)fill * 16384, r, chunk, v);
   }
 }
 
@@ -1498,7 +1847,7 @@ __global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, ui
   float r = 0.f;
   vec[(size_t)s.L * layer_stride + n] = 0.f;
   for (int l = s.L - 1; l >= 0; --l) {
-    const float bp = s.resid_bias[2 * l][n], b2 = s.resid_bias[2 * l + 1][n];
+    const float bp = n < s.d ? s.resid_bias[2 * l][n] : 0.f, b2 = n < s.d ? s.resid_bias[2 * l + 1][n] : 0.f;
     vec[(size_t)l * layer_stride + m_off + n] = -(r + b2);
     r += bp + b2;
     vec[(size_t)l * layer_stride + n] = -r;
@@ -1507,16 +1856,20 @@ __global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, ui
 
 // Bias of a Linear that follows a LayerNorm whose affine part is folded into it:
 //   W (LN0(x) * g + beta) + b = (W diag(g)) LN0(x) + (b + W beta)        dst[i] = scale * (b[i] + W[i,:] . beta)
-// half_out: the n results are stored as packed fp16 starting at float index dst.
-struct VecCopy { const float* src; uint32_t dst; int n; float scale; const float* W; const float* beta; int ld; int half_out; };
+// half_out: the n results are stored as packed fp16 starting at float index dst.  map: packed index -> source index.
+struct VecCopy { const float* src; uint32_t dst; int n, n_src; float scale; const float* W; const float* beta; int ld; int half_out; IndexMap map; };
 __global__ void pack_vec_kernel(const VecCopy* cp, float* vec) {
   const VecCopy c = cp[blockIdx.x];
   for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
-    float b = c.src ? c.src[i] : 0.f;
-    if (c.W != nullptr) {
-      float acc = 0.f;
-      for (int k = 0; k < c.ld; ++k) acc = fmaf(c.W[(size_t)i * c.ld + k], c.beta[k], acc);
-      b += acc;
+    const int si = map_index(c.map, i, c.n_src);
+    float b = 0.f;
+    if (si >= 0) {
+      b = c.src ? c.src[si] : 0.f;
+      if (c.W != nullptr) {
+        float acc = 0.f;
+        for (int k = 0; k < c.ld; ++k) acc = fmaf(c.W[(size_t)si * c.ld + k], c.beta[k], acc);
+        b += acc;
+      }
     }
     if (c.half_out) reinterpret_cast<__half*>(vec + c.dst)[i] = __float2half_rn(b * c.scale);
     else vec[c.dst + i] = b * c.scale;
@@ -1526,17 +1879,22 @@ __global__ void pack_vec_kernel(const VecCopy* cp, float* vec) {
 }  // namespace
 
 // ================================ host API =========================================================
+static int padded_head(const beso_model_desc& m) { const int hs = m.d / m.n_heads; return hs <= 32 ? 32 : 64; }
 bool fast_supported(const beso_model_desc& m) {
   const int G = m.goal_conditioned ? m.goal_len : 0;
   const int T = 1 + G + 2 * m.window;
-  return m.d == kD && m.n_heads == kH && m.linear_output && m.n_layers <= kMaxLayers && m.obs_dim <= kMaxObs &&
+  if (m.d > kD || m.d % 8 != 0 || m.n_heads < 1 || m.d % m.n_heads != 0) return false;
+  const int hs = m.d / m.n_heads;
+  if (hs > 64) return false;
+  const int per_pass = 64 / padded_head(m), npass = (m.n_heads + per_pass - 1) / per_pass;
+  return npass <= kMaxPass && m.linear_output && m.n_layers <= kMaxLayers && m.obs_dim <= kMaxObs &&
          m.act_dim <= kMaxAct && T <= kMaxTokens;
 }
 
-int fast_seqs_per_tile(const beso_model_desc& m, int t) {
+int fast_seqs_per_tile(const beso_model_desc& m, int t, bool prec) {
   if (!fast_supported(m)) return 0;
   const int G = m.goal_conditioned ? m.goal_len : 0;
-  return kRows / (1 + G + 2 * t);
+  return (prec ? 64 : kRows) / (1 + G + 2 * t);
 }
 
 void fast_free(FastWeights& w) {
@@ -1549,56 +1907,93 @@ void fast_free(FastWeights& w) {
 static int p_layer(int l, int k) { return 3 + l * 16 + k; }   // k: 0 ln1w 1 ln1b 2 ln2w 3 ln2b 4 key.w 5 key.b 6 query.w 7 query.b
                                                                //    8 value.w 9 value.b 10 proj.w 11 proj.b 12 mlp0.w 13 mlp0.b 14 mlp2.w 15 mlp2.b
 
-int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm, cudaStream_t st) {
+int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm, cudaStream_t st, bool prec) {
   const int L = m.n_layers, G = m.goal_conditioned ? m.goal_len : 0;
-  // per evaluation: embedding 4 x 16 KB | per layer: QKV 16 x 24 KB, proj 4 x 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
-  const size_t tape_bytes = 4 * 16384 + (size_t)L * (16 * 24576 + 4 * 32768 + 32 * 16384 + 16 * 32768) + 4 * 2048;
+  const int d = m.d, H = m.n_heads, hs = d / H, hsp = padded_head(m), per_pass = 64 / hsp, npass = (H + per_pass - 1) / per_pass;
+  const int ff = 4 * d;
+  const size_t images = prec ? 2 : 1;
+  // per evaluation: embedding 4 x 16 KB | per layer: per pass QKV 4 x 24 KB + proj 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
+  // (PREC: every ring group twice, hi image then lo image)
+  const size_t tape_bytes = images * (4 * 16384 + (size_t)L * ((size_t)npass * (4 * 24576 + 32768) + 32 * 16384 + 16 * 32768) + 4 * 2048);
   const size_t vec_floats = (size_t)L * (kVecAFloats + kVecMFloats) + kVecAFloats;
-  const size_t fold_floats = (size_t)L * 2 * kD;             // per layer: effective V bias | effective proj bias
-  const size_t prog_bytes = 0;
+  const size_t fold_floats = (size_t)L * 2 * kD;             // per layer: effective V bias | effective proj bias (256 padded)
   if (!w.tape) {
-    // tape | program | (scratch tables for the pack kernels)
-    BESO_CUDA(cudaMalloc(&w.tape, tape_bytes + prog_bytes + (1 << 20)));
+    // tape | (scratch tables for the pack kernels)
+    BESO_CUDA(cudaMalloc(&w.tape, tape_bytes + (2 << 20)));
     BESO_CUDA(cudaMalloc(&w.vec, (vec_floats + fold_floats) * sizeof(float)));
+    BESO_CUDA(cudaMemsetAsync(w.vec, 0, (vec_floats + fold_floats) * sizeof(float), st));
     w.tape_bytes = tape_bytes; w.vec_floats = vec_floats;
   }
   uint8_t* tape = reinterpret_cast<uint8_t*>(w.tape);
-  uint8_t* scratch = tape + tape_bytes + prog_bytes;
+  uint8_t* scratch = tape + tape_bytes;
 
   // ---- tape sub-tiles, in program order ----
   std::vector<PackTile> tiles;
-  uint32_t off = 4 * 16384;                                   // embedding fills are written by pack_emb_kernel
-  auto tile = [&](const float* src, int ld, int row0, int col0, int rows, int vrows, float scale, const float* colscale) {
-    tiles.push_back({src, ld, row0, col0, rows, vrows, 64, scale, off, colscale});
+  uint32_t off = (uint32_t)(images * 4 * 16384);              // embedding fills are written by pack_emb_kernel
+  size_t group_first = 0;
+  uint32_t group_off = off;
+  const IndexMap ident{0, 0, 0, 0};
+  auto tile = [&](const float* src, int ld, int row0, int col0, int rows, int n_rows, int n_cols, float scale, const float* colscale,
+                  IndexMap rmap, IndexMap cmap) {
+    tiles.push_back({src, ld, row0, col0, rows, n_rows, n_cols, scale, off, colscale, rmap, cmap, prec ? 1 : 0});
     off += rows * 128;
   };
-  const float qscale = 0.125f * 1.4426950408889634f;          // log2(e) / sqrt(64): the softmax works in base 2
+  // closes a ring group: in PREC the lo image of the same tiles follows
+  auto end_group = [&]() {
+    if (prec) {
+      const uint32_t bytes = off - group_off;
+      const size_t n = tiles.size();
+      for (size_t i = group_first; i < n; ++i) { PackTile t = tiles[i]; t.part = 2; t.dst += bytes; tiles.push_back(t); }
+      off += bytes;
+    }
+    group_first = tiles.size();
+    group_off = off;
+  };
+  const float qscale = 1.4426950408889634f / sqrtf((float)hs);   // log2(e) / sqrt(head size): the softmax works in base 2
+  const float s1 = prec ? 1.f : kGeluInScale, s2 = prec ? 1.f : kGeluOutScale;
   for (int l = 0; l < L; ++l) {
     const float *wk = prm[p_layer(l, 4)], *wq = prm[p_layer(l, 6)], *wv = prm[p_layer(l, 8)], *wp = prm[p_layer(l, 10)];
     const float *w1 = prm[p_layer(l, 12)], *w2 = prm[p_layer(l, 14)];
     const float *ln1w = prm[p_layer(l, 0)], *ln2w = prm[p_layer(l, 2)];
-    auto qkv = [&](int h) {
+    auto qkv = [&](int h) {                                   // attention pass h: heads h * per_pass ..
+      const IndexMap hm{hsp, hs, h * per_pass, H};
       for (int kb = 0; kb < 4; ++kb) {
-        tile(wq, kD, h * 64, kb * 64, 64, 64, qscale, ln1w);
-        tile(wk, kD, h * 64, kb * 64, 64, 64, 1.f, ln1w);
-        tile(wv, kD, h * 64, kb * 64, 64, 64, 1.f, ln1w);
+        tile(wq, d, 0, kb * 64, 64, d, d, qscale, ln1w, hm, ident);
+        tile(wk, d, 0, kb * 64, 64, d, d, 1.f, ln1w, hm, ident);
+        tile(wv, d, 0, kb * 64, 64, d, d, 1.f, ln1w, hm, ident);
+        end_group();
       }
     };
-    auto proj = [&](int h) { for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s) tile(wp, kD, half * 128 + s * 64, h * 64, 64, 64, 1.f, nullptr); };
-    auto fc1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) for (int s = 0; s < 2; ++s) tile(w1, kD, c * 128 + s * 64, kb * 64, 64, 64, kGeluInScale, ln2w); };
-    auto fc2 = [&](int c) {
-      for (int kb = 0; kb < 2; ++kb) for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s)
-        tile(w2, kFF, half * 128 + s * 64, c * 128 + kb * 64, 64, 64, kGeluOutScale, nullptr);
+    auto proj = [&](int h) {
+      const IndexMap hm{hsp, hs, h * per_pass, H};
+      for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s) tile(wp, d, half * 128 + s * 64, 0, 64, d, d, 1.f, nullptr, ident, hm);
+      end_group();
     };
-    qkv(0); qkv(1); proj(0); qkv(2); proj(1); qkv(3); proj(2); proj(3);
+    auto fc1 = [&](int c) {
+      for (int kb = 0; kb < 4; ++kb) {
+        for (int s = 0; s < 2; ++s) tile(w1, d, c * 128 + s * 64, kb * 64, 64, ff, d, s1, ln2w, ident, ident);
+        if (kb & 1) end_group();
+      }
+    };
+    auto fc2 = [&](int c) {
+      for (int kb = 0; kb < 2; ++kb) {
+        for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s)
+          tile(w2, ff, half * 128 + s * 64, c * 128 + kb * 64, 64, d, ff, s2, nullptr, ident, ident);
+        end_group();
+      }
+    };
+    qkv(0);
+    for (int h = 1; h < npass; ++h) { qkv(h); proj(h - 1); }
+    proj(npass - 1);
     fc1(0); fc1(1); fc2(0);
     for (int c = 2; c < 8; ++c) { fc1(c); fc2(c - 1); }
     fc2(7);
   }
   const int p_tail = 3 + 16 * L;                              // ln_f.w, ln_f.b, sigma_emb.w/b, action_emb.w/b, action_pred.w/b
-  for (int kb = 0; kb < 4; ++kb) tile(prm[p_tail + 6], kD, 0, kb * 64, 16, m.act_dim, 1.f, prm[p_tail]);
+  for (int kb = 0; kb < 4; ++kb) tile(prm[p_tail + 6], d, 0, kb * 64, 16, m.act_dim, d, 1.f, prm[p_tail], ident, ident);
+  end_group();
   if (off != tape_bytes) { set_error("internal: tape layout mismatch"); return BESO_E_INVALID; }
-  if (tiles.size() * sizeof(PackTile) > (1 << 19)) { set_error("internal: pack table too large"); return BESO_E_INVALID; }
+  if (tiles.size() * sizeof(PackTile) > (1 << 20)) { set_error("internal: pack table too large"); return BESO_E_INVALID; }
   BESO_CUDA(cudaMemcpyAsync(scratch, tiles.data(), tiles.size() * sizeof(PackTile), cudaMemcpyHostToDevice, st));
   pack_tiles_kernel<<<(unsigned)tiles.size(), 128, 0, st>>>(reinterpret_cast<const PackTile*>(scratch), tape);
   ++g_kernel_launches;
@@ -1613,16 +2008,16 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
     const uint32_t fo = (uint32_t)(vec_floats + (size_t)l * 2 * kD);
     const float* ln1b = prm[p_layer(l, 1)];
     const float* ln2b = prm[p_layer(l, 3)];
-    for (int h = 0; h < kH; ++h)
-      vc.push_back({prm[p_layer(l, 7)] + h * 64, a + 3 * kD + h * 192, 64, qscale, prm[p_layer(l, 6)] + (size_t)h * 64 * kD, ln1b, kD, 0});
-    vc.push_back({prm[p_layer(l, 9)], fo, kD, 1.f, prm[p_layer(l, 8)], ln1b, kD, 0});
-    vc2.push_back({prm[p_layer(l, 11)], fo + kD, kD, 1.f, prm[p_layer(l, 10)], w.vec + fo, kD, 0});
-    vc.push_back({prm[p_layer(l, 13)], mo + kD, kFF, kGeluInScale, prm[p_layer(l, 12)], ln2b, kD, 1});   // b1 / 4 as fp16 after pend
+    for (int h = 0; h < npass; ++h)
+      vc.push_back({prm[p_layer(l, 7)], a + kVecBq + h * 192, 64, d, qscale, prm[p_layer(l, 6)], ln1b, d, 0, IndexMap{hsp, hs, h * per_pass, H}});
+    vc.push_back({prm[p_layer(l, 9)], fo, kD, d, 1.f, prm[p_layer(l, 8)], ln1b, d, 0, ident});
+    vc2.push_back({prm[p_layer(l, 11)], fo + kD, kD, d, 1.f, prm[p_layer(l, 10)], w.vec + fo, d, 0, ident});
+    if (prec) vc.push_back({prm[p_layer(l, 13)], mo + kVecB1F, kFF, ff, 1.f, prm[p_layer(l, 12)], ln2b, d, 0, ident});
+    else vc.push_back({prm[p_layer(l, 13)], mo + kVecB1H, kFF, ff, kGeluInScale, prm[p_layer(l, 12)], ln2b, d, 1, ident});   // b1 / 4 as fp16
   }
   const uint32_t fa = (uint32_t)(L * (kVecAFloats + kVecMFloats));
-  vc.push_back({prm[p_tail + 7], fa + 3 * kD, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], kD, 0});
-  vc.push_back({nullptr, fa + 3 * kD + (uint32_t)m.act_dim, 768 - m.act_dim, 1.f, nullptr, nullptr, 0, 0});
-  uint8_t* scratch2 = scratch + (1 << 19);
+  vc.push_back({prm[p_tail + 7], fa + kVecBq, 16, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], d, 0, ident});
+  uint8_t* scratch2 = scratch + (1 << 20);
   const size_t n1 = vc.size();
   vc.insert(vc.end(), vc2.begin(), vc2.end());
   BESO_CUDA(cudaMemcpyAsync(scratch2, vc.data(), vc.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, st));
@@ -1634,12 +2029,12 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   EmbSrc es{};
   es.pos = prm[0]; es.tokw = prm[1]; es.tokb = prm[2]; es.sigw = prm[p_tail + 2]; es.sigb = prm[p_tail + 3];
   es.actw = prm[p_tail + 4]; es.actb = prm[p_tail + 5];
-  es.obs = m.obs_dim; es.act = m.act_dim; es.G = G; es.W = m.window; es.L = L;
+  es.obs = m.obs_dim; es.act = m.act_dim; es.G = G; es.W = m.window; es.L = L; es.d = d; es.prec = prec ? 1 : 0;
   for (int l = 0; l < L; ++l) {
     es.resid_bias[2 * l] = w.vec + vec_floats + (size_t)l * 2 * kD + kD;      // effective projection bias
     es.resid_bias[2 * l + 1] = prm[p_layer(l, 15)];
   }
-  pack_emb_kernel<<<4, 256, 0, st>>>(es, tape);
+  pack_emb_kernel<<<dim3(4, (unsigned)images), 256, 0, st>>>(es, tape);
   pack_pend_kernel<<<1, kD, 0, st>>>(es, w.vec, kVecAFloats + kVecMFloats, kVecAFloats);
   g_kernel_launches += 2;
   BESO_CUDA(cudaGetLastError());
@@ -1660,16 +2055,19 @@ int fast_mma_rate(long long* out_dev, const void* src_dev, int mode, cudaStream_
 
 int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
                 const float* state, const float* goal, const float* x, const float* sigma, float* out,
-                int B, int t, uint32_t flags, float lambda, cudaStream_t st) {
+                int B, int t, uint32_t flags, float lambda, cudaStream_t st, bool prec) {
   if (!w.tape) { set_error("fast weights not packed"); return BESO_E_NOT_PACKED; }
   FastParams p{};
   const int L = m.n_layers;
+  const int hsp = padded_head(m), per_pass = 64 / hsp;
+  p.hsp = hsp; p.npass = (m.n_heads + per_pass - 1) / per_pass;
+  p.d_true = m.d; p.inv_d = 1.0f / (float)m.d;
   const size_t n_fills = 4 + (size_t)L * 104 + 4;
   p.tape = reinterpret_cast<const uint8_t*>(w.tape);
   p.vec = w.vec;
   p.n_fills = (int)n_fills; p.L = L; p.G = m.goal_conditioned ? m.goal_len : 0; p.obs = m.obs_dim; p.act = m.act_dim;
   p.t = t; p.T = 1 + p.G + 2 * t;
-  p.S = kRows / p.T;
+  p.S = (prec ? 64 : kRows) / p.T;
   const bool cfg = flags & BESO_FLAG_CFG;
   if (cfg) p.S &= ~1;                                         // cond / uncond pairs share a tile
   if (p.S < 1) { set_error("sequence does not fit a 128-row tile"); return BESO_E_UNSUPPORTED; }
@@ -1690,21 +2088,24 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.timeline = g_timeline;
   static bool configured = false;
   if (!configured) {
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
+    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
     configured = true;
   }
   // Single-CTA MMAs (CG = 1) are the default: measured faster than CTA pairs on this workload (the pair mode
   // halves L2 -> SMEM weight traffic but pays remote-arrive latency on every compute -> MMA hand-off; see
   // profiles/).  BESO_FAST_CG=2 selects the cta_group::2 path, kept parity-tested for the next round.
   static const int forced_cg = [] { const char* e = getenv("BESO_FAST_CG"); return e ? atoi(e) : 0; }();
-  const int cg = (forced_cg == 2 && p.n_tiles >= 2) ? 2 : 1;
+  const bool pairs_ok = !prec && p.npass == kH && p.n_tiles >= 2;   // the pair modes replay the fixed 4-pass group table
+  const int cg = (forced_cg == 2 && pairs_ok) ? 2 : 1;
   // BESO_FAST_MC=2: independent CTAs in clusters of 2 sharing the weight stream by TMA multicast
   static const int forced_mc = [] { const char* e = getenv("BESO_FAST_MC"); return e ? atoi(e) : 0; }();
   const bool dbg = p.trace != nullptr || p.timeline != nullptr;
-  const int mc = (cg == 1 && !dbg && forced_mc == 2 && p.n_tiles >= 2) ? 2 : 1;
+  const int mc = (cg == 1 && !dbg && forced_mc == 2 && pairs_ok) ? 2 : 1;
   if (cg == 2 || mc == 2) {
     const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
     cudaLaunchConfig_t cfgl{};
@@ -1716,12 +2117,17 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfgl.attrs = attr; cfgl.numAttrs = 1;
-    if (cg == 2) BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2, false, 1>, p, sa));
-    else BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<1, false, 2>, p, sa));
+    if (cg == 2) BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2, false, 1, false>, p, sa));
+    else BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<1, false, 2, false>, p, sa));
   } else {
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    if (dbg) fast_sample_kernel<1, true, 1><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
-    else fast_sample_kernel<1, false, 1><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    if (prec) {
+      if (dbg) fast_sample_kernel<1, true, 1, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+      else fast_sample_kernel<1, false, 1, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    } else {
+      if (dbg) fast_sample_kernel<1, true, 1, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+      else fast_sample_kernel<1, false, 1, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    }
   }
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());

@@ -1,0 +1,428 @@
+// Training GEMMs on the tcgen05 tensor cores (replaces the library SGEMM of round 1).
+//
+//   C[M][N] = A . B^T  (+ bias + residual | + C | erf-GELU second output),   fp32 in HBM, fp32 accumulate in TMEM
+//
+// One persistent, warp-specialised CTA per SM:
+//   warps 4-11  producers: read the fp32 operand tiles from global memory (coalesced along whichever dimension is
+//               contiguous: the "NT" forward products, the "NN" data gradients and the "TN" weight gradients all
+//               arrive here), convert to bf16 -- in the fp32-parity mode to a bf16 hi image and a bf16 lo image of
+//               the remainder -- and store them as K-major SWIZZLE_128B operand tiles ([rows x 64], the layout the
+//               forward kernel uses), through a ring of shared-memory stages guarded by mbarriers;
+//   warp 12     issues tcgen05.mma (M = 128, N = 128 / 256, K = 16 per instruction; parity mode: hi.hi + lo.hi + hi.lo
+//               into the same accumulator) and commits stages / accumulators;
+//   warps 0-3   epilogue: TMEM -> registers -> a padded shared-memory transpose -> coalesced 128-byte row segments
+//               with bias, residual, accumulate or GELU applied on the way; two accumulators (2 x BN TMEM columns)
+//               so the epilogue of tile i overlaps the main loop of tile i + 1.
+// Weight gradients contract over the B * T rows (K ~ 10^5) into small outputs: split-K over CTAs into partial
+// buffers and a second kernel that adds them in a fixed order (deterministic).
+//
+// Why bf16 and not fp16 here: gradients of a batch-mean loss are ~1e-6 and below, outside fp16's range; bf16 keeps
+// fp32's exponent.  hi + lo carries 16 mantissa bits per operand; dropping lo.lo leaves ~2^-16 relative error per
+// product, far inside the gradient-parity tolerance (rtol 2e-3, tests/test_training_gpu.py).
+#include <cuda_bf16.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "umma.cuh"
+
+namespace beso {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kBM = 128, kBK = 64;
+constexpr int kEpiWarps = 4, kProdWarps = 8, kMmaWarpG = 12, kThreadsG = 13 * 32;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr uint32_t kStagePitch = 144;                 // bytes per row of the epilogue transpose buffer (32 floats + 4 pad)
+constexpr uint32_t kStageBufBytes = 32 * kStagePitch; // per epilogue warp
+
+template <int BN, bool PREC>
+struct Cfg {
+  static constexpr uint32_t a_bytes = kBM * 128u, b_bytes = BN * 128u;
+  static constexpr uint32_t images = PREC ? 2u : 1u;
+  static constexpr uint32_t stage_bytes = images * (a_bytes + b_bytes);
+  static constexpr uint32_t stages_raw = 196608u / stage_bytes;
+  static constexpr uint32_t stages = stages_raw > 6u ? 6u : stages_raw;
+  static constexpr uint32_t sm_epi = stages * stage_bytes;
+  static constexpr uint32_t sm_bars = sm_epi + kEpiWarps * kStageBufBytes;
+  static constexpr uint32_t smem = sm_bars + 256u;
+};
+
+struct Tile { int m0, n0, kb0, kb1, ks; };
+__device__ __forceinline__ Tile tile_of(int idx, int nt, int mt, int kb_total, int kb_per) {
+  Tile t;
+  const int n_t = idx % nt, r = idx / nt;
+  const int m_t = r % mt;
+  t.ks = r / mt;
+  t.m0 = m_t * kBM; t.n0 = n_t;                     // n0 is scaled by BN at the use site
+  t.kb0 = t.ks * kb_per;
+  t.kb1 = min(kb_total, t.kb0 + kb_per);
+  return t;
+}
+
+__device__ __forceinline__ bool elect_one_g() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t polls = 0;
+  while (!mbar_try_wait_sleep(bar, parity)) {
+    if ((++polls & 63u) == 0 && clock64() - t0 > 8000000000ll) {
+      printf("beso gemm kernel: mbarrier at %u parity %u timed out (block %d thread %d)\n", bar, parity, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  wait_slow(bar, parity);
+}
+
+// 8 consecutive K values -> one 16-byte chunk of the hi image (and of the lo image)
+template <bool PREC>
+__device__ __forceinline__ void store_chunk(uint32_t hi_addr, uint32_t lo_delta, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&b);
+    if (PREC) {
+      const float2 f = __bfloat1622float2(b);
+      const __nv_bfloat162 r = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+      l[i] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+  }
+  sts128(hi_addr, h[0], h[1], h[2], h[3]);
+  if (PREC) sts128(hi_addr + lo_delta, l[0], l[1], l[2], l[3]);
+}
+
+// One operand tile [ROWS x 64] (element (row, k)) -> shared memory, by the 256 producer threads.
+//   KMAJOR: element at src[(row0 + row) * ld + k]     (k contiguous: 8 lanes read the 256 bytes of one row)
+//  !KMAJOR: element at src[k * ld + row0 + row]       (rows contiguous: a warp reads 32 rows of one k, 128 bytes)
+// Rows >= n_rows and k >= K are zero.  vec: 16-byte loads are legal (ld % 4 == 0, base 16-byte aligned).
+template <int ROWS, bool KMAJOR, bool PREC>
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld, int row0, int n_rows, int k0, int K, bool vec,
+                                          uint32_t smem_hi, uint32_t lo_delta, int ptid) {
+  if (KMAJOR) {
+    constexpr int kTasks = ROWS * 8 / kProdThreads;            // (row, 8-wide chunk) tasks per thread
+    constexpr int kBatch = 4;
+#pragma unroll 1
+    for (int t0 = 0; t0 < kTasks; t0 += kBatch) {
+      float v[kBatch][8];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int task = ptid + (t0 + u) * kProdThreads, row = task >> 3, k = k0 + (task & 7) * 8;
+        const bool rv = row0 + row < n_rows;
+        const float* g = src + (size_t)(row0 + row) * ld + k;
+        if (rv && vec && k + 8 <= K) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g) + 1);
+          v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = (rv && k + j < K) ? __ldg(g + j) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int task = ptid + (t0 + u) * kProdThreads, row = task >> 3, chunk = task & 7;
+        store_chunk<PREC>(smem_hi + sw128_offset((uint32_t)row, (uint32_t)chunk), lo_delta, v[u]);
+      }
+    }
+  } else {
+    constexpr int kTasks = (ROWS / 32) * 8 / kProdWarps;       // (32-row group, chunk) tasks per warp
+    constexpr int kBatch = 4;
+    const int pw = ptid >> 5, lane = ptid & 31;
+#pragma unroll 1
+    for (int t0 = 0; t0 < kTasks; t0 += kBatch) {
+      float v[kBatch][8];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int task = pw + (t0 + u) * kProdWarps, rg = task >> 3, k = k0 + (task & 7) * 8;
+        const int row = rg * 32 + lane;
+        const bool rv = row0 + row < n_rows;
+        const float* g = src + (size_t)k * ld + row0 + row;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = (rv && k + j < K) ? __ldg(g + (size_t)j * ld) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int task = pw + (t0 + u) * kProdWarps, rg = task >> 3, chunk = task & 7;
+        store_chunk<PREC>(smem_hi + sw128_offset((uint32_t)(rg * 32 + lane), (uint32_t)chunk), lo_delta, v[u]);
+      }
+    }
+  }
+}
+
+struct KArgs {
+  GemmArgs g;
+  int mt, nt, ksplit, kb_total, kb_per, n_tiles;
+  int vec_a, vec_b, vec_c;
+  float* partial;          // split-K: [ksplit][M][N]
+};
+
+__device__ __forceinline__ float gelu_erf_g(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
+
+template <int BN, bool PREC, bool AK, bool BK>
+__global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constant__ KArgs ka) {
+  using C = Cfg<BN, PREC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + C::sm_bars;
+  // barrier map: full[s] at s, empty[s] at 8 + s, acc_full[a] at 16 + a, acc_empty[a] at 18 + a
+  auto bar_full = [&](uint32_t s) { return bars + s * 8u; };
+  auto bar_empty = [&](uint32_t s) { return bars + (8u + s) * 8u; };
+  auto bar_accf = [&](uint32_t a) { return bars + (16u + a) * 8u; };
+  auto bar_acce = [&](uint32_t a) { return bars + (18u + a) * 8u; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::sm_bars + 20 * 8);
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < C::stages; ++s) { mbar_init(bar_full(s), kProdWarps); mbar_init(bar_empty(s), 1); }
+    for (uint32_t a = 0; a < 2; ++a) { mbar_init(bar_accf(a), 1); mbar_init(bar_acce(a), kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarpG) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const GemmArgs& g = ka.g;
+
+  if (warp >= kEpiWarps && warp < kMmaWarpG) {
+    // ===================================== producers =====================================
+    const int ptid = threadIdx.x - kEpiWarps * 32;
+    uint32_t it = 0;
+    for (int idx = blockIdx.x; idx < ka.n_tiles; idx += gridDim.x) {
+      const Tile t = tile_of(idx, ka.nt, ka.mt, ka.kb_total, ka.kb_per);
+      for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
+        const uint32_t s = it % C::stages, par = (it / C::stages) & 1u;
+        wait_bar(bar_empty(s), par ^ 1u);
+        const uint32_t st = sbase + s * C::stage_bytes;
+        load_tile<kBM, AK, PREC>(g.A, g.lda, t.m0, g.M, kb * kBK, g.K, ka.vec_a != 0, st, C::a_bytes, ptid);
+        load_tile<BN, BK, PREC>(g.B, g.ldb, t.n0 * BN, g.N, kb * kBK, g.K, ka.vec_b != 0, st + C::images * C::a_bytes, C::b_bytes, ptid);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full(s));
+      }
+    }
+  } else if (warp == kMmaWarpG) {
+    // ===================================== MMA issuer =====================================
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    constexpr uint32_t idesc = idesc_bf16_m128(BN);
+    uint32_t it = 0, tcount = 0;
+    for (int idx = blockIdx.x; idx < ka.n_tiles; idx += gridDim.x, ++tcount) {
+      const Tile t = tile_of(idx, ka.nt, ka.mt, ka.kb_total, ka.kb_per);
+      const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+      wait_bar(bar_acce(acc), apar ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tm + acc * BN;
+      for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
+        const uint32_t s = it % C::stages, par = (it / C::stages) & 1u;
+        wait_bar(bar_full(s), par);
+        tc_fence_after();
+        const uint32_t st = sbase + s * C::stage_bytes;
+        const uint64_t a_hi = smem_desc_sw128(st), b_hi = smem_desc_sw128(st + C::images * C::a_bytes);
+        if (elect_one_g()) {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            mma_bf16(d_addr, a_hi + 2u * j, b_hi + 2u * j, idesc, (kb > t.kb0 || j > 0) ? 1u : 0u);
+            if (PREC) {
+              mma_bf16(d_addr, a_hi + (C::a_bytes >> 4) + 2u * j, b_hi + 2u * j, idesc, 1u);        // lo . hi
+              mma_bf16(d_addr, a_hi + 2u * j, b_hi + (C::b_bytes >> 4) + 2u * j, idesc, 1u);        // hi . lo
+            }
+          }
+          mma_commit(bar_empty(s));
+          if (kb + 1 == t.kb1) mma_commit(bar_accf(acc));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const uint32_t stage_s = sbase + C::sm_epi + (uint32_t)warp * kStageBufBytes;
+    uint32_t tcount = 0;
+    for (int idx = blockIdx.x; idx < ka.n_tiles; idx += gridDim.x, ++tcount) {
+      const Tile t = tile_of(idx, ka.nt, ka.mt, ka.kb_total, ka.kb_per);
+      const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+      wait_bar(bar_accf(acc), apar);
+      tc_fence_after();
+      const uint32_t t_addr = tmem + ((uint32_t)(warp * 32) << 16) + acc * BN;
+      const int n_base = t.n0 * BN;
+      float* outp = ka.partial ? ka.partial + (size_t)t.ks * g.M * g.N : g.C;
+      const int ldo = ka.partial ? g.N : g.ldc;
+      const bool plain = ka.partial != nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n_base + c * 32 >= g.N) break;                      // warp-uniform: the rest of the tile is padding
+        float v[32];
+        tmem_ld32(t_addr + c * 32, v);
+        tmem_wait_ld();
+        if (c == BN / 32 - 1 || n_base + (c + 1) * 32 >= g.N) {  // last read of this accumulator: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acce(acc));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(stage_s + (uint32_t)lane * kStagePitch + j * 16, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                 __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+        __syncwarp();
+        // coalesced phase: 8 lanes cover the 128 bytes of a row segment, 4 rows per instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3), m = t.m0 + warp * 32 + r, n = n_base + c * 32 + (lane & 7) * 4;
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(stage_s + (uint32_t)r * kStagePitch + (uint32_t)(lane & 7) * 16u));
+          if (m >= g.M || n >= g.N) continue;
+          float xv[4] = {x.x, x.y, x.z, x.w};
+          float* cp = outp + (size_t)m * ldo + n;
+          if (ka.vec_c && n + 4 <= g.N) {
+            if (!plain) {
+              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n)); xv[0] += b.x; xv[1] += b.y; xv[2] += b.z; xv[3] += b.w; }
+              if (g.mul) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.mul + (size_t)m * g.ldm + n)); xv[0] *= b.x; xv[1] *= b.y; xv[2] *= b.z; xv[3] *= b.w; }
+              if (g.resid) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.resid + (size_t)m * g.ldr + n)); xv[0] += b.x; xv[1] += b.y; xv[2] += b.z; xv[3] += b.w; }
+              if (g.accumulate) { const float4 b = *reinterpret_cast<const float4*>(cp); xv[0] += b.x; xv[1] += b.y; xv[2] += b.z; xv[3] += b.w; }
+            }
+            *reinterpret_cast<float4*>(cp) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            if (!plain && g.gelu_out)
+              *reinterpret_cast<float4*>(g.gelu_out + (size_t)m * g.ldg + n) =
+                  make_float4(gelu_erf_g(xv[0]), gelu_erf_g(xv[1]), gelu_erf_g(xv[2]), gelu_erf_g(xv[3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (n + e >= g.N) break;
+              float y = xv[e];
+              if (!plain) {
+                if (g.bias) y += __ldg(g.bias + n + e);
+                if (g.mul) y *= __ldg(g.mul + (size_t)m * g.ldm + n + e);
+                if (g.resid) y += __ldg(g.resid + (size_t)m * g.ldr + n + e);
+                if (g.accumulate) y += cp[e];
+              }
+              cp[e] = y;
+              if (!plain && g.gelu_out) g.gelu_out[(size_t)m * g.ldg + n + e] = gelu_erf_g(y);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarpG) tmem_dealloc(tmem, 512);
+}
+
+// C = sum_ks partial[ks] (+ bias + resid | + C), fixed order
+__global__ void splitk_reduce_kernel(GemmArgs g, const float* __restrict__ partial, int ksplit) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t total = (size_t)g.M * g.N;
+  if (idx >= total) return;
+  const int m = (int)(idx / g.N), n = (int)(idx % g.N);
+  float a = 0.f;
+  for (int ks = 0; ks < ksplit; ++ks) a += partial[(size_t)ks * total + idx];
+  if (g.bias) a += g.bias[n];
+  if (g.mul) a *= g.mul[(size_t)m * g.ldm + n];
+  if (g.resid) a += g.resid[(size_t)m * g.ldr + n];
+  float* cp = g.C + (size_t)m * g.ldc + n;
+  if (g.accumulate) a += *cp;
+  *cp = a;
+}
+
+template <int BN, bool PREC>
+int launch(const KArgs& ka, int grid, cudaStream_t st) {
+  using C = Cfg<BN, PREC>;
+  const int smem = (int)C::smem + 1024;
+#define BESO_GEMM_CASE(AK, BK)                                                                                      \
+  do {                                                                                                              \
+    static bool cfgd = false;                                                                                       \
+    if (!cfgd) {                                                                                                    \
+      BESO_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PREC, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      cfgd = true;                                                                                                  \
+    }                                                                                                               \
+    gemm_kernel<BN, PREC, AK, BK><<<grid, kThreadsG, smem, st>>>(ka);                                               \
+  } while (0)
+  if (ka.g.a_kmajor && ka.g.b_kmajor) BESO_GEMM_CASE(true, true);
+  else if (ka.g.a_kmajor) BESO_GEMM_CASE(true, false);
+  else if (ka.g.b_kmajor) BESO_GEMM_CASE(false, true);
+  else BESO_GEMM_CASE(false, false);
+#undef BESO_GEMM_CASE
+  ++g_kernel_launches;
+  BESO_CUDA(cudaGetLastError());
+  return BESO_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+void gemm_ws_free(GemmWs& ws) {
+  if (ws.partial) cudaFree(ws.partial);
+  ws.partial = nullptr; ws.floats = 0;
+}
+
+int gemm_run(const GemmArgs& a, GemmWs& ws, int sm_count, cudaStream_t st) {
+  if (a.M < 1 || a.N < 1 || a.K < 1 || !a.A || !a.B || !a.C) { set_error("gemm: bad arguments"); return BESO_E_INVALID; }
+  KArgs ka{};
+  ka.g = a;
+  const int bn = a.N > 128 ? 256 : 128;
+  ka.mt = (a.M + kBM - 1) / kBM;
+  ka.nt = (a.N + bn - 1) / bn;
+  ka.kb_total = (a.K + kBK - 1) / kBK;
+  // split-K when the output has far fewer tiles than the chip has SMs and the contraction is long
+  const int out_tiles = ka.mt * ka.nt;
+  int ksplit = 1;
+  if (!a.gelu_out && out_tiles * 2 <= sm_count && ka.kb_total >= 16) {
+    ksplit = sm_count / out_tiles;
+    const int max_split = ka.kb_total / 4;                    // at least 4 k-blocks per split
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+  }
+  ka.kb_per = (ka.kb_total + ksplit - 1) / ksplit;
+  ksplit = (ka.kb_total + ka.kb_per - 1) / ka.kb_per;         // no empty splits
+  ka.ksplit = ksplit;
+  ka.n_tiles = out_tiles * ksplit;
+  ka.vec_a = a.a_kmajor ? (a.lda % 4 == 0 && aligned16(a.A)) : 0;
+  ka.vec_b = a.b_kmajor ? (a.ldb % 4 == 0 && aligned16(a.B)) : 0;
+  ka.partial = nullptr;
+  if (ksplit > 1) {
+    const size_t need = (size_t)ksplit * a.M * a.N;
+    if (need > ws.floats) {
+      if (ws.partial) cudaFree(ws.partial);
+      ws.partial = nullptr; ws.floats = 0;
+      BESO_CUDA(cudaMalloc(&ws.partial, need * sizeof(float)));
+      ws.floats = need;
+    }
+    ka.partial = ws.partial;
+    ka.vec_c = (a.N % 4 == 0);
+  } else {
+    ka.vec_c = a.ldc % 4 == 0 && aligned16(a.C) && (!a.resid || (a.ldr % 4 == 0 && aligned16(a.resid))) &&
+               (!a.mul || (a.ldm % 4 == 0 && aligned16(a.mul))) &&
+               (!a.bias || aligned16(a.bias)) && (!a.gelu_out || (a.ldg % 4 == 0 && aligned16(a.gelu_out)));
+  }
+  const int grid = ka.n_tiles < sm_count ? ka.n_tiles : sm_count;
+  int rc;
+  if (bn == 256) rc = a.prec ? launch<256, true>(ka, grid, st) : launch<256, false>(ka, grid, st);
+  else rc = a.prec ? launch<128, true>(ka, grid, st) : launch<128, false>(ka, grid, st);
+  if (rc) return rc;
+  if (ksplit > 1) {
+    const size_t total = (size_t)a.M * a.N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, ws.partial, ksplit);
+    ++g_kernel_launches;
+    BESO_CUDA(cudaGetLastError());
+  }
+  return BESO_OK;
+}
+
+}  // namespace beso

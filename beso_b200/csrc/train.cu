@@ -1,31 +1,28 @@
 // Training path: GCDenoiser.loss (score_wrappers.py:45-79) forward + hand-derived backward, and the
 // data-parallel gradient exchange (one NCCL all-reduce of the flat fp32 gradient over NVLink).
 //
-// fp32 throughout (the loss-parity bar is against the fp32 reference).  The dense products are plain
-// library GEMMs (cuBLAS SGEMM, fp32 math); everything else -- embeddings + interleave, LayerNorm
-// forward/backward, causal attention forward/backward, erf-GELU, bias / column reductions, the Karras
-// pre-conditioned loss -- is hand-written below.  Gradients are written into ONE flat buffer in
-// nn.Module.parameters() order, which is what the all-reduce operates on.
+// Every dense product (forward, data gradient, weight gradient) runs on the tcgen05 tensor cores through the
+// hand-written GEMM of gemm.cu: fp32 tensors in HBM, bf16 hi + lo operand images and three MMAs per product by
+// default (fp32-parity mode, the one the gradient goldens pin), one bf16 MMA per product with
+// BESO_FLAG_TRAIN_FAST.  Bias, residual add and erf-GELU ride in the GEMM epilogues.  Everything else --
+// embeddings + interleave, LayerNorm forward/backward, causal attention forward/backward, GELU backward,
+// bias / column reductions, dropout, the Karras pre-conditioned loss -- is hand-written below in fp32.
+// Gradients are written into ONE flat buffer in nn.Module.parameters() order, which is what the
+// all-reduce operates on.
 //
-// Dropout probabilities must be 0 (the reference draws dropout masks from the global torch RNG in op
-// order).  The element-wise goal mask for CFG training is drawn by the caller.
-#include <cublas_v2.h>
+// Dropout (score_gpts.py:37-38,72,79,109) and the element-wise goal mask of CFG training (:360-371) take their
+// masks from the caller, who draws them with the reference's torch calls in the reference's op order.
 #include <nccl.h>
 #include <string.h>
 
 #include <vector>
 
 #include "common.cuh"
+#include "gemm.cuh"
 #include "plan.cuh"
 
 namespace beso {
 namespace {
-
-#define BESO_CUBLAS(expr)                                                                    \
-  do {                                                                                       \
-    cublasStatus_t _s = (expr);                                                              \
-    if (_s != CUBLAS_STATUS_SUCCESS) { set_error(std::string("cuBLAS error ") + std::to_string((int)_s) + " at " #expr); return BESO_E_CUDA; } \
-  } while (0)
 
 constexpr int kTB = 256;
 inline int blocks_for(size_t n, int per = kTB) { return (int)((n + per - 1) / per); }
@@ -37,14 +34,6 @@ __device__ __forceinline__ float wsum(float v) {
 
 struct Dims { int B, t, T, G, obs, act, d, H, hs, L, F, M; float sigma_data; };
 
-// ---- row-major GEMM helper: C[M][N] = alpha * op(A) * op(B) + beta * C --------------------------------
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, float alpha, const float* A, int lda,
-            const float* B, int ldb, float beta, float* C, int ldc) {
-  BESO_CUBLAS(cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A,
-                          lda, &beta, C, ldc));
-  return BESO_OK;
-}
-
 // ---- embeddings (score_gpts.py:284-337) ---------------------------------------------------------------
 // X[r][c] for row r = (b, tok); also writes the network input x_in = (a + n*sigma) * c_in  [B,t,act].
 __global__ void embed_fwd_kernel(Dims D, const float* __restrict__ state, const float* __restrict__ action,
@@ -52,8 +41,8 @@ __global__ void embed_fwd_kernel(Dims D, const float* __restrict__ state, const 
                                  const float* __restrict__ sigma, const float* __restrict__ goal_keep, int pred_last,
                                  const float* __restrict__ pos, const float* __restrict__ tokw, const float* __restrict__ tokb,
                                  const float* __restrict__ sigw, const float* __restrict__ sigb,
-                                 const float* __restrict__ actw, const float* __restrict__ actb, float* __restrict__ X,
-                                 float* __restrict__ xin) {
+                                 const float* __restrict__ actw, const float* __restrict__ actb,
+                                 const float* __restrict__ drop_mask, float* __restrict__ X, float* __restrict__ xin) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= (size_t)D.M * D.d) return;
   const int c = (int)(idx % D.d);
@@ -89,6 +78,7 @@ __global__ void embed_fwd_kernel(Dims D, const float* __restrict__ state, const 
     }
     v += pos[(size_t)(D.G + step) * D.d + c];
   }
+  if (drop_mask) v *= drop_mask[idx];                   // self.drop(input_seq), score_gpts.py:338
   X[idx] = v;
 }
 
@@ -163,6 +153,15 @@ __global__ void copy_add_bias_kernel(float* __restrict__ dst, const float* __res
   float4 v = reinterpret_cast<const float4*>(src)[i];
   const float4 b = *reinterpret_cast<const float4*>(bias + (int)((i * 4) % N));
   v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  reinterpret_cast<float4*>(dst)[i] = v;
+}
+// dst = a .* m (dropout masks carry the 1 / (1 - p) scale)
+__global__ void mul_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ m, size_t n4) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(a)[i];
+  const float4 w = reinterpret_cast<const float4*>(m)[i];
+  v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
   reinterpret_cast<float4*>(dst)[i] = v;
 }
 // Column sums (bias gradients) in two deterministic stages: partial[rb][c] over row block rb, then the sum over rb.
@@ -257,7 +256,7 @@ __device__ __forceinline__ void tile2x2(const float* A, const float* Bm, int lds
 }
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(Dims D, float* __restrict__ QKV, const float* __restrict__ bq, const float* __restrict__ bk,
-                const float* __restrict__ bv, float* __restrict__ P, float* __restrict__ Y) {
+                const float* __restrict__ bv, const float* __restrict__ drop_mask, float* __restrict__ P, float* __restrict__ Y) {
   extern __shared__ __align__(16) float sh[];
   const int T = D.T, hs = D.hs, ld = 3 * D.d, lds = attn_lds(hs), hs4 = (hs + 3) >> 2, ldt = T + 1;
   float* q = sh;                       // [T][lds], columns hs .. lds-1 zero
@@ -323,8 +322,10 @@ attn_fwd_kernel(Dims D, float* __restrict__ QKV, const float* __restrict__ bq, c
     float p0 = (lane <= i) ? expf(a0 - mx) : 0.f, p1 = (lane + 32 <= i) ? expf(a1 - mx) : 0.f;
     const float inv = 1.0f / wsum(p0 + p1);
     p0 *= inv; p1 *= inv;
-    if (lane < T) { sc[i * ldt + lane] = p0; Pm[i * T + lane] = p0; }
-    if (lane + 32 < T) { sc[i * ldt + lane + 32] = p1; Pm[i * T + lane + 32] = p1; }
+    // P (before attn_drop) is what the softmax backward needs; P V uses the dropped-out probabilities
+    const float* dm = drop_mask ? drop_mask + ((size_t)b * D.H + h) * T * T + (size_t)i * T : nullptr;
+    if (lane < T) { Pm[i * T + lane] = p0; sc[i * ldt + lane] = dm ? p0 * dm[lane] : p0; }
+    if (lane + 32 < T) { Pm[i * T + lane + 32] = p1; sc[i * ldt + lane + 32] = dm ? p1 * dm[lane + 32] : p1; }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < T * hs4; idx += kAttnThreads) {      // (row, 4 columns) per thread
@@ -341,8 +342,8 @@ attn_fwd_kernel(Dims D, float* __restrict__ QKV, const float* __restrict__ bq, c
 inline size_t attn_fwd_smem(int T, int hs) { return ((size_t)3 * T * attn_lds(hs) + (size_t)T * (T + 1)) * sizeof(float); }
 
 __global__ void __launch_bounds__(kAttnThreads)
-attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dY,
-                float* __restrict__ dQKV) {
+attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ drop_mask,
+                const float* __restrict__ dY, float* __restrict__ dQKV) {
   extern __shared__ __align__(16) float sh[];
   const int T = D.T, hs = D.hs, ld = 3 * D.d, lds = attn_lds(hs), hs4 = (hs + 3) >> 2, ldt = T + 1;
   float* q = sh;                       // [T][lds]
@@ -351,6 +352,7 @@ attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__
   float* dy = v + T * lds;
   float* Pm = dy + T * lds;            // [T][T + 1]
   float* dS = Pm + T * ldt;            // [T][T + 1]
+  float* Pd = dS + T * ldt;            // [T][T + 1]: attn_drop(P) (only with a dropout mask)
   const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
   const size_t row0 = (size_t)b * T;
   const float scale = 1.0f / sqrtf((float)hs);
@@ -363,7 +365,12 @@ attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__
   for (int r = threadIdx.x; r < 4 * T; r += kAttnThreads)      // zero the 4 pad columns of every row
     *reinterpret_cast<float4*>(q + r * lds + hs4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* Pg = P + ((size_t)b * D.H + h) * T * T;
-  for (int idx = threadIdx.x; idx < T * T; idx += kAttnThreads) Pm[(idx / T) * ldt + idx % T] = Pg[idx];
+  const float* dm = drop_mask ? drop_mask + ((size_t)b * D.H + h) * T * T : nullptr;
+  for (int idx = threadIdx.x; idx < T * T; idx += kAttnThreads) {
+    Pm[(idx / T) * ldt + idx % T] = Pg[idx];
+    if (dm) Pd[(idx / T) * ldt + idx % T] = Pg[idx] * dm[idx];
+  }
+  if (!dm) Pd = Pm;
   __syncthreads();
   // dP[i][j] = dY_i . V_j ;  dS = P * (dP - sum_j dP * P) * scale
   const int T2 = (T + 1) >> 1;
@@ -376,7 +383,7 @@ attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__
 #pragma unroll
       for (int dj = 0; dj < 2; ++dj) {
         const int i = i0 + di, j = j0 + dj;
-        if (i < T && j < T) dS[i * ldt + j] = (j <= i) ? o[di][dj] : 0.f;
+        if (i < T && j < T) dS[i * ldt + j] = (j <= i) ? (dm ? o[di][dj] * dm[i * T + j] : o[di][dj]) : 0.f;
       }
   }
   __syncthreads();
@@ -395,7 +402,7 @@ attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__
       dq.x = fmaf(s_, kk.x, dq.x); dq.y = fmaf(s_, kk.y, dq.y); dq.z = fmaf(s_, kk.z, dq.z); dq.w = fmaf(s_, kk.w, dq.w);
     }
     for (int r = i; r < T; ++r) {
-      const float s_ = dS[r * ldt + i], p_ = Pm[r * ldt + i];
+      const float s_ = dS[r * ldt + i], p_ = Pd[r * ldt + i];
       const float4 qq = reinterpret_cast<const float4*>(q + r * lds)[e4];
       const float4 dd = reinterpret_cast<const float4*>(dy + r * lds)[e4];
       dk.x = fmaf(s_, qq.x, dk.x); dk.y = fmaf(s_, qq.y, dk.y); dk.z = fmaf(s_, qq.z, dk.z); dk.w = fmaf(s_, qq.w, dk.w);
@@ -407,7 +414,7 @@ attn_bwd_kernel(Dims D, const float* __restrict__ QKV, const float* __restrict__
     reinterpret_cast<float4*>(o + 2 * D.d)[e4] = dv;
   }
 }
-inline size_t attn_bwd_smem(int T, int hs) { return ((size_t)4 * T * attn_lds(hs) + (size_t)2 * T * (T + 1)) * sizeof(float); }
+inline size_t attn_bwd_smem(int T, int hs) { return ((size_t)4 * T * attn_lds(hs) + (size_t)3 * T * (T + 1)) * sizeof(float); }
 
 __global__ void gather_action_rows_kernel(Dims D, const float* __restrict__ X, float* __restrict__ HA) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -520,12 +527,17 @@ constexpr size_t kPartialFloats = (size_t)148 * 2048;
 struct TrainWs {
   float* buf = nullptr;
   size_t floats = 0;
-  cublasHandle_t blas = nullptr;
+  GemmWs gemm{};
+  int sm_count = 0;
 };
 
 static int ensure_ws(TrainWs*& ws, size_t floats) {
   if (!ws) ws = new TrainWs();
-  if (!ws->blas) BESO_CUBLAS(cublasCreate(&ws->blas));
+  if (!ws->sm_count) {
+    int dev = 0;
+    BESO_CUDA(cudaGetDevice(&dev));
+    BESO_CUDA(cudaDeviceGetAttribute(&ws->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
   if (floats > ws->floats) {
     if (ws->buf) cudaFree(ws->buf);
     ws->buf = nullptr; ws->floats = 0;
@@ -537,13 +549,20 @@ static int ensure_ws(TrainWs*& ws, size_t floats) {
 void train_ws_free(TrainWs* ws) {
   if (!ws) return;
   if (ws->buf) cudaFree(ws->buf);
-  if (ws->blas) cublasDestroy(ws->blas);
+  gemm_ws_free(ws->gemm);
   delete ws;
+}
+
+int train_gemm(TrainWs*& ws, const GemmArgs& a, cudaStream_t st) {
+  int rc = ensure_ws(ws, 0);
+  if (rc) return rc;
+  return gemm_run(a, ws->gemm, ws->sm_count, st);
 }
 
 int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* const* prm, const float* state,
                        const float* action, const float* goal, const float* noise, const float* sigma,
-                       const float* goal_keep, float* loss_out, float* grad, int B, uint32_t flags, cudaStream_t st) {
+                       const float* goal_keep, const beso_dropout_masks* drop, float* loss_out, float* grad, int B,
+                       uint32_t flags, cudaStream_t st) {
   if (!m.linear_output) { set_error("training path supports linear_output models only"); return BESO_E_UNSUPPORTED; }
   Dims D;
   D.B = B; D.t = m.window; D.G = m.goal_conditioned ? m.goal_len : 0; D.T = 1 + D.G + 2 * D.t; D.obs = m.obs_dim;
@@ -551,13 +570,14 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   D.M = B * D.T; D.sigma_data = m.sigma_data;
   if (D.T > 64) { set_error("training path supports at most 64 tokens per sequence"); return BESO_E_UNSUPPORTED; }
   const int pred_last = (flags & BESO_FLAG_PRED_LAST) ? 1 : 0;
+  const int prec = (flags & BESO_FLAG_TRAIN_FAST) ? 0 : 1;
   const int d = D.d, F = D.F, M = D.M, L = D.L;
   const size_t Md = (size_t)M * d, MF = (size_t)M * F, nP = (size_t)B * D.H * D.T * D.T, nBt = (size_t)B * D.t;
   // ---- carve the workspace ----
   const size_t per_layer = 5 * align4(Md) + align4(3 * Md) + align4(nP) + 2 * align4(MF) + 2 * align4(2 * (size_t)M);
   const size_t n_gather = (size_t)B * (D.G + D.t);
   const size_t total = (size_t)L * per_layer + 2 * align4(Md) + align4(2 * (size_t)M) + align4(nBt * d) + 3 * align4(nBt * D.act) +
-                       4 * align4(Md) + align4(MF) + align4(3 * Md) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + kPartialFloats + 4096;
+                       5 * align4(Md) + align4(MF) + align4(3 * Md) + align4(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))) + kPartialFloats + 4096;
   int rc = ensure_ws(ws, total);
   if (rc) return rc;
   float* p = ws->buf;
@@ -571,12 +591,8 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   }
   float *XL = take(Md), *HF = take(Md), *stf = take(2 * (size_t)M), *HA = take(nBt * d), *pred = take(nBt * D.act),
         *dpred = take(nBt * D.act), *xin = take(nBt * D.act);
-  float *dX = take(Md), *dT = take(Md), *dH = take(Md), *dY = take(Md), *dBig = take(MF), *dQKV = take(3 * Md);
+  float *dX = take(Md), *dT = take(Md), *dH = take(Md), *dY = take(Md), *dXm = take(Md), *dBig = take(MF), *dQKV = take(3 * Md);
   float *gRows = take(n_gather * (size_t)(d + (D.obs > D.act ? D.obs : D.act))), *partial = take(kPartialFloats);
-  cublasHandle_t h = ws->blas;
-  BESO_CUBLAS(cublasSetStream(h, st));
-  // fp32 FMA by default (the reference's arithmetic); TF32 tensor-core GEMMs only on request
-  BESO_CUBLAS(cublasSetMathMode(h, (flags & BESO_FLAG_TRAIN_TF32) ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH));
 
   // ---- parameter pointers and gradient slots (parameters() order) ----
   std::vector<size_t> goff;
@@ -590,12 +606,30 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   auto Gp = [&](int i) { return grad ? grad + goff[i] : nullptr; };
   auto lp = [&](int l, int k) { return 3 + 16 * l + k; };
   const int pt = 3 + 16 * L;
+  const float* m_embed = drop ? drop->embed : nullptr;
+  auto m_attn = [&](int l) -> const float* { return (drop && drop->attn) ? drop->attn[l] : nullptr; };
+  auto m_res1 = [&](int l) -> const float* { return (drop && drop->resid_attn) ? drop->resid_attn[l] : nullptr; };
+  auto m_res2 = [&](int l) -> const float* { return (drop && drop->resid_mlp) ? drop->resid_mlp[l] : nullptr; };
 #define LAUNCH(kernel, grid, block, smem, ...)                       \
   do {                                                               \
     kernel<<<grid, block, smem, st>>>(__VA_ARGS__);                  \
     ++g_kernel_launches;                                             \
   } while (0)
-#define GEMM(...) do { if ((rc = gemm_rm(h, __VA_ARGS__))) return rc; } while (0)
+  // C[M][N] = op(A) op(B) on the tensor cores.  ta: A is stored [K][M] (lda), tb: B is stored [N][K] (ldb).
+  struct Epi { const float* bias = nullptr; const float* resid = nullptr; int ldr = 0; const float* mul = nullptr; int ldm = 0;
+               int accumulate = 0; float* gelu = nullptr; int ldg = 0; };
+  auto gemm = [&](bool ta, bool tb, int Mm, int Nn, int Kk, const float* Am, int lda, const float* Bm, int ldb, float* Cm, int ldc,
+                  const Epi& e) -> int {
+    GemmArgs a{};
+    a.A = Am; a.lda = lda; a.a_kmajor = ta ? 0 : 1;
+    a.B = Bm; a.ldb = ldb; a.b_kmajor = tb ? 1 : 0;
+    a.C = Cm; a.ldc = ldc; a.M = Mm; a.N = Nn; a.K = Kk;
+    a.bias = e.bias; a.resid = e.resid; a.ldr = e.ldr; a.mul = e.mul; a.ldm = e.ldm; a.accumulate = e.accumulate;
+    a.gelu_out = e.gelu; a.ldg = e.ldg; a.prec = prec;
+    return gemm_run(a, ws->gemm, ws->sm_count, st);
+  };
+#define GEMM(...) do { if ((rc = gemm(__VA_ARGS__))) return rc; } while (0)
+  const Epi none{};
 
   // ============================== forward ==============================
   if (attn_bwd_smem(D.T, D.hs) > 48 * 1024) {
@@ -604,30 +638,30 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   }
   if ((d & 3) || (F & 3) || (D.hs & 3)) { set_error("training path needs embed_dim % 4 == 0 and head size % 4 == 0"); return BESO_E_UNSUPPORTED; }
   LAUNCH(embed_fwd_kernel, blocks_for(Md), kTB, 0, D, state, action, goal, noise, sigma, goal_keep, pred_last, W(0), W(1), W(2),
-         W(pt + 2), W(pt + 3), W(pt + 4), W(pt + 5), A[0].Xin, xin);
+         W(pt + 2), W(pt + 3), W(pt + 4), W(pt + 5), m_embed, A[0].Xin, xin);
   const int ln_grid = (M + 7) / 8;
   for (int l = 0; l < L; ++l) {
     Layer& a = A[l];
     LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, a.Xin, M, d, W(lp(l, 0)), W(lp(l, 1)), a.H1, a.st1);
     // q | k | v column blocks (reference parameter order: key, query, value)
-    GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 6)), d, 0.f, a.QKV, 3 * d);
-    GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 4)), d, 0.f, a.QKV + d, 3 * d);
-    GEMM(false, true, M, d, d, 1.f, a.H1, d, W(lp(l, 8)), d, 0.f, a.QKV + 2 * d, 3 * d);
+    GEMM(false, true, M, d, d, a.H1, d, W(lp(l, 6)), d, a.QKV, 3 * d, none);
+    GEMM(false, true, M, d, d, a.H1, d, W(lp(l, 4)), d, a.QKV + d, 3 * d, none);
+    GEMM(false, true, M, d, d, a.H1, d, W(lp(l, 8)), d, a.QKV + 2 * d, 3 * d, none);
     // q / k / v biases are added (and written back) by the attention kernel's tile load
-    LAUNCH(attn_fwd_kernel, B * D.H, kAttnThreads, attn_fwd_smem(D.T, D.hs), D, a.QKV, W(lp(l, 7)), W(lp(l, 5)), W(lp(l, 9)), a.P, a.Y);
-    LAUNCH(copy_add_bias_kernel, blocks_for(Md / 4), kTB, 0, a.Xmid, a.Xin, W(lp(l, 11)), Md / 4, d);   // X_mid = X_in + b_proj
-    GEMM(false, true, M, d, d, 1.f, a.Y, d, W(lp(l, 10)), d, 1.f, a.Xmid, d);
+    LAUNCH(attn_fwd_kernel, B * D.H, kAttnThreads, attn_fwd_smem(D.T, D.hs), D, a.QKV, W(lp(l, 7)), W(lp(l, 5)), W(lp(l, 9)), m_attn(l), a.P, a.Y);
+    { Epi e; e.bias = W(lp(l, 11)); e.resid = a.Xin; e.ldr = d; e.mul = m_res1(l); e.ldm = d;     // X_mid = X_in + drop(Y Wp^T + b_proj)
+      GEMM(false, true, M, d, d, a.Y, d, W(lp(l, 10)), d, a.Xmid, d, e); }
     LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, a.Xmid, M, d, W(lp(l, 2)), W(lp(l, 3)), a.H2, a.st2);
-    GEMM(false, true, M, F, d, 1.f, a.H2, d, W(lp(l, 12)), d, 0.f, a.U, F);
-    LAUNCH(bias_gelu_fwd_kernel, blocks_for(MF / 4), kTB, 0, a.U, W(lp(l, 13)), a.Gg, MF / 4, F);
+    { Epi e; e.bias = W(lp(l, 13)); e.gelu = a.Gg; e.ldg = F;                                     // U = H2 W1^T + b1 (kept), G = gelu(U)
+      GEMM(false, true, M, F, d, a.H2, d, W(lp(l, 12)), d, a.U, F, e); }
     float* Xnext = (l + 1 < L) ? A[l + 1].Xin : XL;
-    LAUNCH(copy_add_bias_kernel, blocks_for(Md / 4), kTB, 0, Xnext, a.Xmid, W(lp(l, 15)), Md / 4, d);   // X_next = X_mid + b_2
-    GEMM(false, true, M, d, F, 1.f, a.Gg, F, W(lp(l, 14)), F, 1.f, Xnext, d);
+    { Epi e; e.bias = W(lp(l, 15)); e.resid = a.Xmid; e.ldr = d; e.mul = m_res2(l); e.ldm = d;    // X_next = X_mid + drop(G W2^T + b_2)
+      GEMM(false, true, M, d, F, a.Gg, F, W(lp(l, 14)), F, Xnext, d, e); }
   }
   LAUNCH(ln_fwd_kernel, ln_grid, 256, 0, XL, M, d, W(pt), W(pt + 1), HF, stf);
   LAUNCH(gather_action_rows_kernel, blocks_for(nBt * d), kTB, 0, D, HF, HA);
-  GEMM(false, true, (int)nBt, D.act, d, 1.f, HA, d, W(pt + 6), d, 0.f, pred, D.act);
-  LAUNCH(bias_add_kernel, blocks_for(nBt * D.act), kTB, 0, pred, W(pt + 7), nBt, D.act, D.act);
+  { Epi e; e.bias = W(pt + 7);
+    GEMM(false, true, (int)nBt, D.act, d, HA, d, W(pt + 6), d, pred, D.act, e); }
   const int lgrid = (int)(blocks_for(nBt * D.act) < 1024 ? blocks_for(nBt * D.act) : 1024);
   LAUNCH(loss_kernel, lgrid, kTB, 0, D, pred, action, noise, sigma, pred_last, dpred, partial);
   LAUNCH(sum_partials_kernel, 1, 32, 0, partial, lgrid, loss_out);
@@ -635,7 +669,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   if (!grad) return BESO_OK;
 
   // ============================== backward ==============================
-  // column sums (bias gradients) as A^T 1 with a library GEMV: bandwidth-bound, full-chip parallel
+  // column sums (bias gradients): two deterministic stages, bandwidth-bound, full-chip parallel
   auto colsum = [&](const float* Am, int rows, int N, int lda, float* out) -> int {
     if ((size_t)N * kColsumRowBlocks > kPartialFloats) { set_error("internal: column-sum scratch too small"); return BESO_E_INVALID; }
     LAUNCH(colsum_partial_kernel, dim3((N + 31) / 32, kColsumRowBlocks), dim3(32, 8), 0, Am, rows, N, lda, partial);
@@ -651,40 +685,50 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     return colsum(dYv, M, d, d, db);
   };
 #define LNBWD(...) do { if ((rc = ln_bwd(__VA_ARGS__))) return rc; } while (0)
+  // gradient of a dropped-out residual branch: dX .* mask (the branch output was scaled by the mask)
+  auto branch_grad = [&](const float* mask) -> const float* {
+    if (!mask) return dX;
+    LAUNCH(mul_kernel, blocks_for(Md / 4), kTB, 0, dXm, dX, mask, Md / 4);
+    return dXm;
+  };
+  Epi acc1; acc1.accumulate = 1;
   // head
-  GEMM(true, false, D.act, d, (int)nBt, 1.f, dpred, D.act, HA, d, 0.f, Gp(pt + 6), d);
+  GEMM(true, false, D.act, d, (int)nBt, dpred, D.act, HA, d, Gp(pt + 6), d, none);
   COLSUM(dpred, (int)nBt, D.act, D.act, Gp(pt + 7));
-  GEMM(false, false, (int)nBt, d, D.act, 1.f, dpred, D.act, W(pt + 6), d, 0.f, HA, d);           // HA <- dHA
+  GEMM(false, false, (int)nBt, d, D.act, dpred, D.act, W(pt + 6), d, HA, d, none);               // HA <- dHA
   LAUNCH(scatter_action_rows_kernel, blocks_for(Md), kTB, 0, D, HA, dH);                         // dH <- dHF
   LNBWD(dH, XL, stf, W(pt), 0, Gp(pt), Gp(pt + 1));                                              // dX = d loss / d X_L
   for (int l = L - 1; l >= 0; --l) {
     Layer& a = A[l];
-    // ---- MLP branch: X_next = X_mid + gelu(H2 W1^T + b1) W2^T + b2 ----
-    GEMM(true, false, d, F, M, 1.f, dX, d, a.Gg, F, 0.f, Gp(lp(l, 14)), F);                       // dW2 = dX^T G
-    COLSUM(dX, M, d, d, Gp(lp(l, 15)));
-    GEMM(false, false, M, F, d, 1.f, dX, d, W(lp(l, 14)), F, 0.f, dBig, F);                        // dG = dX W2
+    // ---- MLP branch: X_next = X_mid + drop(gelu(H2 W1^T + b1) W2^T + b2) ----
+    const float* dB = branch_grad(m_res2(l));
+    GEMM(true, false, d, F, M, dB, d, a.Gg, F, Gp(lp(l, 14)), F, none);                            // dW2 = dB^T G
+    COLSUM(dB, M, d, d, Gp(lp(l, 15)));
+    GEMM(false, false, M, F, d, dB, d, W(lp(l, 14)), F, dBig, F, none);                            // dG = dB W2
     LAUNCH(gelu_bwd_kernel, blocks_for(MF / 4), kTB, 0, a.U, dBig, MF / 4);                       // dU
-    GEMM(true, false, F, d, M, 1.f, dBig, F, a.H2, d, 0.f, Gp(lp(l, 12)), d);                     // dW1 = dU^T H2
+    GEMM(true, false, F, d, M, dBig, F, a.H2, d, Gp(lp(l, 12)), d, none);                          // dW1 = dU^T H2
     COLSUM(dBig, M, F, F, Gp(lp(l, 13)));
-    GEMM(false, false, M, d, F, 1.f, dBig, F, W(lp(l, 12)), d, 0.f, dH, d);                        // dH2 = dU W1
+    GEMM(false, false, M, d, F, dBig, F, W(lp(l, 12)), d, dH, d, none);                            // dH2 = dU W1
     LNBWD(dH, a.Xmid, a.st2, W(lp(l, 2)), 1, Gp(lp(l, 2)), Gp(lp(l, 3)));                          // dX = d/dX_mid
-    // ---- attention branch: X_mid = X_in + Y Wp^T + bp ----
-    GEMM(true, false, d, d, M, 1.f, dX, d, a.Y, d, 0.f, Gp(lp(l, 10)), d);                         // dWp
-    COLSUM(dX, M, d, d, Gp(lp(l, 11)));
-    GEMM(false, false, M, d, d, 1.f, dX, d, W(lp(l, 10)), d, 0.f, dY, d);                          // dY = dX Wp
-    LAUNCH(attn_bwd_kernel, B * D.H, kAttnThreads, attn_bwd_smem(D.T, D.hs), D, a.QKV, a.P, dY, dQKV);
-    GEMM(true, false, d, d, M, 1.f, dQKV, 3 * d, a.H1, d, 0.f, Gp(lp(l, 6)), d);                   // dWq
-    GEMM(true, false, d, d, M, 1.f, dQKV + d, 3 * d, a.H1, d, 0.f, Gp(lp(l, 4)), d);               // dWk
-    GEMM(true, false, d, d, M, 1.f, dQKV + 2 * d, 3 * d, a.H1, d, 0.f, Gp(lp(l, 8)), d);           // dWv
+    // ---- attention branch: X_mid = X_in + drop(Y Wp^T + bp) ----
+    dB = branch_grad(m_res1(l));
+    GEMM(true, false, d, d, M, dB, d, a.Y, d, Gp(lp(l, 10)), d, none);                             // dWp
+    COLSUM(dB, M, d, d, Gp(lp(l, 11)));
+    GEMM(false, false, M, d, d, dB, d, W(lp(l, 10)), d, dY, d, none);                              // dY = dB Wp
+    LAUNCH(attn_bwd_kernel, B * D.H, kAttnThreads, attn_bwd_smem(D.T, D.hs), D, a.QKV, a.P, m_attn(l), dY, dQKV);
+    GEMM(true, false, d, d, M, dQKV, 3 * d, a.H1, d, Gp(lp(l, 6)), d, none);                       // dWq
+    GEMM(true, false, d, d, M, dQKV + d, 3 * d, a.H1, d, Gp(lp(l, 4)), d, none);                   // dWk
+    GEMM(true, false, d, d, M, dQKV + 2 * d, 3 * d, a.H1, d, Gp(lp(l, 8)), d, none);               // dWv
     COLSUM(dQKV, M, d, 3 * d, Gp(lp(l, 7)));
     COLSUM(dQKV + d, M, d, 3 * d, Gp(lp(l, 5)));
     COLSUM(dQKV + 2 * d, M, d, 3 * d, Gp(lp(l, 9)));
-    GEMM(false, false, M, d, d, 1.f, dQKV, 3 * d, W(lp(l, 6)), d, 0.f, dH, d);                     // dH1
-    GEMM(false, false, M, d, d, 1.f, dQKV + d, 3 * d, W(lp(l, 4)), d, 1.f, dH, d);
-    GEMM(false, false, M, d, d, 1.f, dQKV + 2 * d, 3 * d, W(lp(l, 8)), d, 1.f, dH, d);
+    GEMM(false, false, M, d, d, dQKV, 3 * d, W(lp(l, 6)), d, dH, d, none);                         // dH1
+    GEMM(false, false, M, d, d, dQKV + d, 3 * d, W(lp(l, 4)), d, dH, d, acc1);
+    GEMM(false, false, M, d, d, dQKV + 2 * d, 3 * d, W(lp(l, 8)), d, dH, d, acc1);
     LNBWD(dH, a.Xin, a.st1, W(lp(l, 0)), 1, Gp(lp(l, 0)), Gp(lp(l, 1)));                           // dX = d/dX_in
   }
   // ---- embeddings ----
+  if (m_embed) LAUNCH(mul_kernel, blocks_for(Md / 4), kTB, 0, dX, dX, m_embed, Md / 4);           // X_0 = drop(embeddings)
   const int n_pos = D.G + D.t + 1;
   if ((size_t)kPosChunks * n_pos * d > kPartialFloats || d > 1024) { set_error("internal: position-gradient scratch too small"); return BESO_E_INVALID; }
   LAUNCH(pos_grad_partial_kernel, dim3(n_pos, kPosChunks), d, 0, D, dX, n_pos, partial);
@@ -697,7 +741,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     float* inRows = gRows + rows * d;
     LAUNCH(gather_embed_rows_kernel, blocks_for(rows * (d + k.kin)), kTB, 0, D, k.kind, dX, state, goal, goal_keep, xin, sigma,
            dRows, inRows);
-    GEMM(true, false, d, k.kin, (int)rows, 1.f, dRows, d, inRows, k.kin, 0.f, Gp(k.pw), k.kin);    // dW = dRows^T in
+    GEMM(true, false, d, k.kin, (int)rows, dRows, d, inRows, k.kin, Gp(k.pw), k.kin, none);        // dW = dRows^T in
     COLSUM(dRows, (int)rows, d, d, Gp(k.pb));
   }
   BESO_CUDA(cudaGetLastError());

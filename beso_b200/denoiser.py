@@ -148,8 +148,10 @@ class DiffusionGPT(nn.Module):
 class GCDenoiser(nn.Module):
     """Karras et al. pre-conditioner around the score-GPT (score_wrappers.py:18-99).
 
-    ``mode``: "precise" (fp32 CUDA-core kernel, rtol 1e-3 / atol 1e-5 against the fp32 reference),
-    "fast" (bf16 tcgen05 kernel) or "auto" (fast when the shape is supported, else precise).
+    ``mode``: "precise" (fp32-equivalent arithmetic, rtol 1e-3 / atol 1e-5 against the fp32 reference: the
+    split-operand tcgen05 kernel where the shape is supported, else the fp32 CUDA-core kernel), "fast" (fp16
+    tcgen05 kernel, single pass), "simt" (always the fp32 CUDA-core kernel) or "auto" (fast when the library
+    supports the shape, else precise).
     """
 
     def __init__(self, inner_model, sigma_data: float = 1.0, mode: str = "auto"):
@@ -246,11 +248,19 @@ class GCDenoiser(nn.Module):
         _lib.check(_lib.lib().beso_plan_select_weights(self._plan, slot), "beso_plan_select_weights")
         self._slot = slot
 
+    def fast_supported(self) -> bool:
+        """Whether the tensor-core kernel takes this model's shape -- asked of the library (the one place that
+        knows the kernel's limits), never re-derived here."""
+        if self._plan is None:
+            p0 = next(self.inner_model.parameters())
+            if not p0.is_cuda:
+                return False
+            self._ensure_plan(self._device_index(p0))
+        return _lib.lib().beso_plan_rows_per_cta(self._plan, _lib.MODE_FAST, self.config.window) > 0
+
     def resolved_mode(self) -> int:
-        cfg = self.config
-        fast_ok = (cfg.d == 256 and cfg.head_dim == 64 and cfg.linear_output and cfg.n_tokens() <= 32)
         if self.mode == "auto":
-            return _lib.MODE_FAST if fast_ok else _lib.MODE_PRECISE
+            return _lib.MODE_FAST if self.fast_supported() else _lib.MODE_PRECISE
         return _lib.MODE_IDS[self.mode]
 
     def close(self):

@@ -5,9 +5,15 @@ parameter exactly like the reference's autograd would (beso_agent.py:236-240).  
 in ONE call of the C ABI (``beso_loss_fwd_bwd``), which writes all gradients into one flat fp32 buffer in
 ``parameters()`` order -- the buffer the data-parallel all-reduce (beso_b200/dist.py) operates on.
 
-Dropout must be off (p = 0): the reference draws dropout masks from the global RNG in op order
-(SURVEY.md H5).  The element-wise goal mask of CFG training (score_gpts.py:360-371) is drawn here with
-the same torch call and passed to the kernel.
+Every dense product runs on the tcgen05 tensor cores (csrc/gemm.cu): ``model.train_math = "fp32"`` (default) splits
+the operands into bf16 hi + lo images, three MMAs per product (the fp32-parity mode the gradient goldens pin);
+``"bf16"`` is one MMA per product.
+
+Training-mode randomness: the reference draws the element-wise goal mask of CFG training (score_gpts.py:360-371) and
+its dropout masks (score_gpts.py:338,72,79,109) from torch's global generator in op order.
+``draw_dropout_masks`` makes the same torch calls in the same order here and the kernels apply the masks, so a
+training step consumes the generator exactly like the reference's and -- on the same device type -- sees the same
+masks.
 """
 from __future__ import annotations
 
@@ -31,15 +37,69 @@ def flat_grad_views(model, flat: torch.Tensor):
     return out
 
 
-def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_action_only=False, goal_keep=None,
-                       need_grad=True):
-    """Runs ``beso_loss_fwd_bwd``; returns (loss 0-d tensor, flat gradient or None).
+def draw_dropout_masks(inner, batch: int, t: int, device):
+    """The nn.Dropout draws of one training forward of ``DiffusionGPT`` in the reference's op order:
+    ``self.drop(input_seq)`` (score_gpts.py:338), then per block ``attn_drop`` (:72, shape (B, H, T, T)),
+    ``resid_drop`` (:79) and the mlp's Dropout (:109), both (B, T, d).  Each mask is what F.dropout applies to a tensor
+    of ones (0 or 1 / (1 - p)); F.dropout consumes the generator by shape only, so the global generator advances
+    exactly as in the reference.  p = 0 draws nothing (as in torch).  Returns None when every p is 0."""
+    p_embed, p_attn, p_resid = inner._dropouts
+    if not inner.training or not any(p > 0 for p in (p_embed, p_attn, p_resid)):
+        return None
+    cfg = inner.config
+    T, d, H, L = cfg.n_tokens(t), cfg.d, cfg.n_heads, cfg.n_layers
 
-    ``model.train_math = "tf32"`` (default "fp32", the reference's arithmetic) runs the GEMMs on the tensor
-    cores in TF32."""
-    inner = model.inner_model
-    if any(p > 0 for p in inner._dropouts) and inner.training:
-        raise _lib.BesoLibraryError("the fused training path needs attn_pdrop = resid_pdrop = embed_pdrob = 0")
+    def draw(shape, p):
+        if p <= 0:
+            return None
+        return torch.nn.functional.dropout(torch.ones(shape, device=device, dtype=torch.float32), p, True)
+
+    masks = {"embed": draw((batch, T, d), p_embed), "attn": [], "resid_attn": [], "resid_mlp": []}
+    for _ in range(L):
+        masks["attn"].append(draw((batch, H, T, T), p_attn))
+        masks["resid_attn"].append(draw((batch, T, d), p_resid))
+        masks["resid_mlp"].append(draw((batch, T, d), p_resid))
+    return masks
+
+
+def _masks_struct(masks, n_layers, device):
+    """ctypes view of ``masks`` (beso_dropout_masks); returns (struct or None, keep-alive list)."""
+    if masks is None:
+        return None, []
+    keep = []
+
+    def ptr(t):
+        if t is None:
+            return None
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    def arr(lst):
+        if lst is None or all(m is None for m in lst):
+            return None
+        if len(lst) != n_layers or any(m is None for m in lst):
+            raise ValueError("dropout masks: need one mask per layer")
+        a = (C.c_void_p * n_layers)(*[ptr(m) for m in lst])
+        keep.append(a)
+        return a
+
+    s = _lib.DropoutMasks()
+    s.embed = ptr(masks.get("embed"))
+    for name in ("attn", "resid_attn", "resid_mlp"):
+        a = arr(masks.get(name))
+        if a is not None:
+            setattr(s, name, C.cast(a, C.POINTER(C.c_void_p)))
+    return s, keep
+
+
+def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_action_only=False, goal_keep=None,
+                       need_grad=True, dropout_masks=None):
+    """Runs ``beso_loss_fwd_bwd_dropout``; returns (loss 0-d tensor, flat gradient or None).
+
+    ``model.train_math``: "fp32" (default: split bf16 hi + lo operands, three MMAs per product, the fp32-parity mode)
+    or "bf16" (one MMA per product; "tf32" is accepted as the round-1 name of the opt-in fast mode).
+    ``dropout_masks``: see ``draw_dropout_masks`` (None = no dropout)."""
     params = _param_list(model)
     dev = model._device_index(action)
     state, action, goal, noise, sigma = map(model._prep, (state, action, goal, noise, sigma))
@@ -55,23 +115,28 @@ def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_actio
     keep_ptr = goal_keep.data_ptr() if goal_keep is not None else None
     flags = _lib.FLAG_PRED_LAST if pred_last_action_only else 0
     math = getattr(model, "train_math", "fp32")
-    if math not in ("fp32", "tf32"):
-        raise ValueError(f"train_math must be 'fp32' or 'tf32', got {math!r}")
-    if math == "tf32":
-        flags |= _lib.FLAG_TRAIN_TF32
+    if math not in ("fp32", "bf16", "tf32"):
+        raise ValueError(f"train_math must be 'fp32' or 'bf16', got {math!r}")
+    if math != "fp32":
+        flags |= _lib.FLAG_TRAIN_FAST
+    mstruct, keep = _masks_struct(dropout_masks, cfg.n_layers, action.device)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(_lib.lib().beso_loss_fwd_bwd(plan, state.data_ptr(), action.data_ptr(), goal.data_ptr(), noise.data_ptr(),
-                                           sigma.data_ptr(), keep_ptr, loss.data_ptr(),
-                                           flat.data_ptr() if flat is not None else None, B, flags, C.c_void_p(stream)),
-               "beso_loss_fwd_bwd")
+    _lib.check(_lib.lib().beso_loss_fwd_bwd_dropout(plan, state.data_ptr(), action.data_ptr(), goal.data_ptr(),
+                                                   noise.data_ptr(), sigma.data_ptr(), keep_ptr,
+                                                   C.byref(mstruct) if mstruct is not None else None, loss.data_ptr(),
+                                                   flat.data_ptr() if flat is not None else None, B, flags,
+                                                   C.c_void_p(stream)),
+               "beso_loss_fwd_bwd_dropout")
+    del keep
     return loss, flat
 
 
 class _LossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, state, action, goal, noise, sigma, pred_last, goal_keep, *params):
+    def forward(ctx, model, state, action, goal, noise, sigma, pred_last, goal_keep, drop, *params):
         need = any(p.requires_grad for p in params) and torch.is_grad_enabled()
-        loss, flat = loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last, goal_keep, need_grad=True)
+        loss, flat = loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last, goal_keep, need_grad=True,
+                                        dropout_masks=drop)
         ctx.model = model
         ctx.flat = flat
         model.last_flat_grad = flat            # exposed for the data-parallel exchange
@@ -82,7 +147,7 @@ class _LossFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         views = flat_grad_views(ctx.model, ctx.flat)
         grads = tuple(v * grad_out for v in views)
-        return (None,) * 8 + grads
+        return (None,) * 9 + grads
 
 
 def denoiser_loss(model, state, action, goal, noise, sigma, **kwargs):
@@ -97,5 +162,6 @@ def denoiser_loss(model, state, action, goal, noise, sigma, **kwargs):
     if inner.training and inner.cond_mask_prob > 0.0:
         mask = torch.bernoulli(torch.ones(goal.shape, device=goal.device) * inner.cond_mask_prob)
         goal_keep = (1.0 - mask).contiguous()
+    drop = draw_dropout_masks(inner, action.shape[0], action.shape[1], action.device)   # after mask_cond, in op order
     params = _param_list(model)
-    return _LossFn.apply(model, state, action, goal, noise, sigma, pred_last, goal_keep, *params)
+    return _LossFn.apply(model, state, action, goal, noise, sigma, pred_last, goal_keep, drop, *params)

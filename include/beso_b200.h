@@ -42,9 +42,16 @@ enum {
 
 /* Arithmetic mode of the score-GPT GEMMs. */
 enum {
-  BESO_MODE_PRECISE = 0, /* fp32 CUDA-core FMA; meets rtol 1e-3 / atol 1e-5 vs the fp32 reference   */
-  BESO_MODE_FAST = 1     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM;
-                            fp32 LayerNorm / softmax / GELU / residual.  d=256, head_dim=64 only.   */
+  BESO_MODE_PRECISE = 0, /* fp32-equivalent arithmetic; meets rtol 1e-3 / atol 1e-5 vs the fp32 reference.  On shapes
+                            the tensor-core kernel supports (below) every product runs on tcgen05 with both
+                            operands split into fp16 hi + lo images (all four cross terms, fp32 accumulate in
+                            TMEM), fp32 two-pass LayerNorm, erff GELU, fp32 attention; other shapes run the fp32
+                            CUDA-core kernel.                                                            */
+  BESO_MODE_FAST = 1,    /* fp16 operands on tcgen05 tensor cores (single pass), fp32 accumulate in TMEM; fp32
+                            LayerNorm statistics / softmax / residual.  Shapes: embed_dim <= 256 (multiple of 8),
+                            head size <= 64 with n_heads * padded head size (32 or 64) <= 384, <= 24 tokens,
+                            obs <= 64, act <= 13, linear action head.                                    */
+  BESO_MODE_SIMT = 2     /* force the fp32 CUDA-core kernel (any shape); same tolerance as PRECISE        */
 };
 
 /* gc_sampling.py sampler selected by BesoAgent.sample_loop (beso_agent.py:419-455). */
@@ -68,10 +75,12 @@ enum {
                                   last step (score_wrappers.py:59-66, 76-77)                                     */
 #define BESO_FLAG_INNER 4u  /* return DiffusionGPT.forward(state, action, goal, sigma) itself, i.e. without
                                the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
-#define BESO_FLAG_TRAIN_TF32 16u /* beso_loss_fwd_bwd only: run the training GEMMs on the tensor cores in TF32
-                                  (cuBLAS CUBLAS_TF32_TENSOR_OP_MATH).  Opt-in: the reference multiplies in fp32
-                                  (torch.backends.cuda.matmul.allow_tf32 is False by default), which is the default
-                                  here and the mode the gradient-parity tests pin. */
+#define BESO_FLAG_TRAIN_FAST 16u /* beso_loss_fwd_bwd only: one bf16 tcgen05 MMA per product in the training GEMMs
+                                  (the arithmetic of bf16 mixed-precision training).  Opt-in: by default every
+                                  operand is split into bf16 hi + lo images and every product is three MMAs
+                                  (hi.hi + lo.hi + hi.lo, fp32 accumulate) -- the fp32-parity mode the gradient
+                                  goldens pin (the reference multiplies in fp32). */
+#define BESO_FLAG_TRAIN_TF32 BESO_FLAG_TRAIN_FAST /* round-1 name of the opt-in tensor-core training mode */
 
 /* Constructor arguments of DiffusionGPT (k_diffusion/score_gpts.py:121-139) and
  * GCDenoiser.sigma_data (k_diffusion/score_wrappers.py:26-29). */
@@ -180,11 +189,38 @@ int beso_sample_loop_host(beso_plan* plan, int mode, int sampler, const float* s
  *   action = clean action a; noise n; sigma (B).  goal_keep_dev: optional (B,G,obs) {0,1} mask =
  *   1 - Bernoulli(cond_mask_prob) drawn by the caller (score_gpts.py:360-371), NULL = keep all.
  *   loss_dev: 1 fp32.  flat_grad_dev: beso_param_total() fp32 in parameters() order, overwritten
- *   (NULL = forward only).  Dropout probabilities must be 0. */
+ *   (NULL = forward only).  All dense products run on tcgen05 (BESO_FLAG_TRAIN_FAST selects single-pass bf16). */
 int beso_loss_fwd_bwd(beso_plan* plan, const float* state_dev, const float* action_dev,
                       const float* goal_dev, const float* noise_dev, const float* sigma_dev,
                       const float* goal_keep_dev, float* loss_dev, float* flat_grad_dev, int B,
                       uint32_t flags, void* stream);
+
+/* Training-mode dropout of the reference (score_gpts.py:37-38,72,79,109,338): nn.Dropout draws from torch's global
+ * generator in op order, so the caller draws the masks with the same torch calls in the same order (SURVEY.md H5;
+ * beso_b200/training.py does) and hands them over.  Every mask holds 0 or 1 / (1 - p) (what F.dropout applies to a
+ * tensor of ones).  Any pointer (or the struct itself) may be NULL = that dropout is off (p = 0).
+ *   embed:       (B, T, d)      self.drop(input_seq)                       embed_pdrob
+ *   attn[l]:     (B, H, T, T)   attn_drop(softmax(...)) of block l          attn_pdrop
+ *   resid_attn:  (B, T, d)      resid_drop(proj(y)) of block l              resid_pdrop
+ *   resid_mlp:   (B, T, d)      the Dropout that ends block l's mlp         resid_pdrop
+ * T = 1 + G + 2 W tokens; attn / resid_attn / resid_mlp are arrays of n_layers device pointers. */
+typedef struct beso_dropout_masks {
+  const float* embed;
+  const float* const* attn;
+  const float* const* resid_attn;
+  const float* const* resid_mlp;
+} beso_dropout_masks;
+int beso_loss_fwd_bwd_dropout(beso_plan* plan, const float* state_dev, const float* action_dev,
+                              const float* goal_dev, const float* noise_dev, const float* sigma_dev,
+                              const float* goal_keep_dev, const beso_dropout_masks* masks, float* loss_dev,
+                              float* flat_grad_dev, int B, uint32_t flags, void* stream);
+
+/* The training GEMM by itself (tests and tools): C[M][N] = A . B^T + bias, fp32 row-major device tensors.
+ *   a_kmajor: A element (m, k) at A[m * lda + k], else at A[k * lda + m]; b_kmajor likewise for B (n, k).
+ *   prec: 1 = split bf16 hi + lo, three MMAs per product (fp32-parity); 0 = one bf16 MMA.  bias may be NULL. */
+int beso_debug_gemm(beso_plan* plan, const float* A_dev, int lda, int a_kmajor, const float* B_dev, int ldb,
+                    int b_kmajor, float* C_dev, int ldc, int M, int N, int K, const float* bias_dev, int accumulate,
+                    int prec, void* stream);
 
 /* Data-parallel gradient step (BASELINE config 4): one all-reduce(sum) of the flat fp32 gradient
  * over NCCL on NVLink, scaled by 1/world.  The reference has no distributed path; this is the

@@ -94,27 +94,37 @@ def causal_self_attention(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: in
 
 
 # score_gpts.py:96-115
-def block(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int, trace=None) -> Tensor:
+def block(x: Tensor, sd: Dict[str, Tensor], pre: str, n_head: int, trace=None, drop=None) -> Tensor:
+    """``drop``: training-mode dropout of this block with the masks drawn by the caller (0 or 1 / (1 - p), what
+    F.dropout applies): (attn_drop :72, resid_drop :79, the mlp's Dropout :109); None = eval."""
     d = x.shape[-1]
     if trace is not None:
         trace.append(x)
     h = F.layer_norm(x, (d,), sd[pre + "ln1.weight"], sd[pre + "ln1.bias"], 1e-5)
-    x = x + causal_self_attention(h, sd, pre + "attn.", n_head)
+    a = causal_self_attention(h, sd, pre + "attn.", n_head, None if drop is None else drop[0])
+    if drop is not None and drop[1] is not None:
+        a = a * drop[1]
+    x = x + a
     if trace is not None:
         trace.append(x)
     h = F.layer_norm(x, (d,), sd[pre + "ln2.weight"], sd[pre + "ln2.bias"], 1e-5)
     h = F.linear(h, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"])
     h = F.gelu(h)                                                 # nn.GELU() default = exact erf
     h = F.linear(h, sd[pre + "mlp.2.weight"], sd[pre + "mlp.2.bias"])
+    if drop is not None and drop[2] is not None:
+        h = h * drop[2]
     return x + h
 
 
 # score_gpts.py:272-358
 def gpt_forward(sd: Dict[str, Tensor], cfg: OracleCfg, states: Tensor, actions: Tensor,
                 goals: Tensor, sigma: Tensor, uncond: bool = False,
-                keep_last_actions: bool = False, goal_keep: Optional[Tensor] = None, trace=None) -> Tensor:
+                keep_last_actions: bool = False, goal_keep: Optional[Tensor] = None, trace=None,
+                drop_masks=None) -> Tensor:
     """``goal_keep`` (B,G,obs) in {0,1} restates mask_cond (score_gpts.py:360-371)
-    with the Bernoulli draw made by the caller: goals * goal_keep, goal_keep = 1 - mask."""
+    with the Bernoulli draw made by the caller: goals * goal_keep, goal_keep = 1 - mask.
+    ``drop_masks``: dict(embed=mask or None, attn=[...], resid_attn=[...], resid_mlp=[...]) restates the
+    nn.Dropout calls of training mode (score_gpts.py:338,72,79,109) with caller-drawn masks."""
     b, t, _ = states.size()
     assert t <= cfg.block_size, "Cannot forward, model block size is exhausted."
     G = cfg.goal_len if cfg.goal_conditioned else 0
@@ -138,8 +148,13 @@ def gpt_forward(sd: Dict[str, Tensor], cfg: OracleCfg, states: Tensor, actions: 
         x = torch.cat([emb_t, goal_x, sa_seq], dim=1)             # :335
     else:
         x = torch.cat([emb_t, sa_seq], dim=1)
+    if drop_masks is not None and drop_masks.get("embed") is not None:
+        x = x * drop_masks["embed"]                               # :338 self.drop(input_seq)
     for l in range(cfg.n_layers):                                 # :340
-        x = block(x, sd, f"{P}blocks.{l}.", cfg.n_heads, trace)
+        dm = None
+        if drop_masks is not None:
+            dm = tuple((drop_masks.get(k) or [None] * cfg.n_layers)[l] for k in ("attn", "resid_attn", "resid_mlp"))
+        x = block(x, sd, f"{P}blocks.{l}.", cfg.n_heads, trace, dm)
     if trace is not None:
         trace.append(x)       # residual stream entering ln_f
     x = F.layer_norm(x, (cfg.d,), sd[P + "ln_f.weight"], sd[P + "ln_f.bias"], 1e-5)       # :341

@@ -257,6 +257,42 @@ def gen_loss(ns):
         save(name, cfg, seed, sd, **arrays)
 
 
+DROPOUT_CASES = (("loss_dropout_K256", K256, 1, 8, dict(attn_pdrop=0.3, resid_pdrop=0.0, goal_drop=0.0)),      # kitchen config
+                 ("loss_dropout_B256", B256, 3, 16, dict(attn_pdrop=0.05, resid_pdrop=0.05, goal_drop=0.1)))   # block-push + CFG mask
+DROPOUT_SEED = 1234
+
+
+def gen_loss_dropout(ns):
+    """GCDenoiser.loss in training mode WITH dropout (configs/franka_kitchen_main_config.yaml:56-57 attn_pdrop 0.3;
+    configs/block_push_main_config.yaml:57-58 attn/resid 0.05) under torch.manual_seed(DROPOUT_SEED) on CPU: the
+    reference draws its masks from the global generator in op order.  The tests re-draw them with
+    beso_b200.training.draw_dropout_masks under the same seed."""
+    for name, cfg, seed, B, kw in DROPOUT_CASES:
+        m = ref_import.make_reference_model(ns, cfg, **kw)
+        sd = synthetic_state_dict(cfg, seed)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        m.training = True
+        x = synthetic_inputs(cfg, B, seed=300 + seed, sigma_min=0.05)
+        torch.manual_seed(DROPOUT_SEED)
+        loss = m.loss(x["state"], x["clean"], x["goal"], x["noise"].clone(), x["sigma"])
+        m.zero_grad()
+        loss.backward()
+        arrays = dict(state=x["state"], action=x["clean"], goal=x["goal"], noise=x["noise"], sigma=x["sigma"],
+                      loss=loss.detach(), attn_pdrop=kw["attn_pdrop"], resid_pdrop=kw["resid_pdrop"],
+                      goal_drop=kw["goal_drop"], rng_seed=DROPOUT_SEED)
+        norms, names = [], []
+        for n, p in m.named_parameters():
+            g = p.grad
+            names.append(n)
+            norms.append(g.double().norm().item())
+            flat = g.reshape(-1)
+            arrays["grad::" + n] = flat if flat.numel() <= 4096 else flat[::97][:4096]
+        arrays["grad_norms"] = np.array(norms)
+        arrays["grad_names"] = np.array(names)
+        save(name, cfg, seed, sd, **arrays)
+
+
 WINDOW_MODES = {
     "plain": dict(window=5),
     "future": dict(window=5, future_conditional=True, min_future_sep=1, future_seq_len=2),
@@ -363,12 +399,16 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "dpm_solver":
         gen_dpm_solver(ns)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "loss_dropout":    # added in round 2
+        gen_loss_dropout(ns)
+        return
     gen_ancestral(ns)
     gen_dpm_solver(ns)
     gen_schedules(ns)
     gen_forward(ns)
     gen_samplers(ns)
     gen_loss(ns)
+    gen_loss_dropout(ns)
 
 
 if __name__ == "__main__":

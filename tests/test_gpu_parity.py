@@ -22,24 +22,29 @@ from beso_b200.synth import synthetic_inputs, synthetic_state_dict
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=3e-3, atol=3e-3)}
-FAST_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256"}
+TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "simt": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=3e-3, atol=3e-3)}
+# shapes the tensor-core kernel must take (checked against what the library reports): every d <= 256 fixture with a
+# linear head, including the block-push checkpoint shape (d = 240, 12 heads of 20) and the no-goal model (d = 64)
+TENSOR_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_push", "fwd_no_goal"}
 FWD = ["fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_kitchen", "fwd_small_push",
        "fwd_mlp_head", "fwd_no_goal"]
 
 
-def fast_available():
+def fast_available(cfg=K256):
     lib = _lib.lib()
     h = C.c_void_p()
-    desc = _lib.ModelDesc.from_config(K256)
+    desc = _lib.ModelDesc.from_config(cfg)
     _lib.check(lib.beso_plan_create(C.byref(desc), 0, C.byref(h)))
-    ok = lib.beso_plan_rows_per_cta(h, _lib.MODE_FAST, 10) > 0
+    ok = lib.beso_plan_rows_per_cta(h, _lib.MODE_FAST, cfg.window) > 0
     lib.beso_plan_destroy(h)
     return ok
 
 
-def modes_for(name):
-    return ["precise"] + (["fast"] if name in FAST_SHAPES else [])
+def modes_for(name, cfg):
+    """precise = the split-operand tensor-core kernel where the shape is supported (else the CUDA-core kernel),
+    simt = the CUDA-core kernel on every shape, fast = single-pass fp16 tensor-core kernel."""
+    assert fast_available(cfg) == (name in TENSOR_SHAPES), name
+    return ["precise", "simt"] + (["fast"] if name in TENSOR_SHAPES else [])
 
 
 def cuda(a, dev):
@@ -51,9 +56,7 @@ def test_forward_matches_reference_golden(name, cuda_device):
     cfg, meta, a = load_golden(name)
     sd = golden_weights(cfg, meta)
     g = cuda(a, cuda_device)
-    for mode in modes_for(name):
-        if mode == "fast" and not fast_available():
-            pytest.skip("fast mode not built")
+    for mode in modes_for(name, cfg):
         m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
         m.refresh_weights()                                               # weight packing is not part of a step
         launches = _lib.lib().beso_kernel_launches()

@@ -217,3 +217,42 @@ def test_lms_matches_golden():
     assert coef.shape == (6, 4) and float(coef[0, 1]) == 0.0 and float(coef[2, 3]) == 0.0 and float(coef[3, 3]) != 0.0
     t = a["sigmas_6"].numpy()
     assert float(coef[4, 2]) == pytest.approx(O.linear_multistep_coeff(4, t, 4, 2), rel=1e-6)
+
+
+# ---- training-mode dropout: the product's mask draws replay the reference's generator consumption ----------------
+def _replay_training_draws(name):
+    """Re-draws, under the fixture's seed on the CPU, what the reference drew inside GCDenoiser.loss: the CFG goal mask
+    (score_gpts.py:366) and then the nn.Dropout masks in op order (beso_b200.training.draw_dropout_masks)."""
+    from conftest import golden_weights, load_golden
+    from beso_b200.denoiser import build_denoiser
+    from beso_b200.training import draw_dropout_masks
+    cfg, meta, a = load_golden(name)
+    sd = golden_weights(cfg, meta)
+    m = build_denoiser(cfg, "cpu", state_dict=sd, attn_pdrop=float(a["attn_pdrop"]), resid_pdrop=float(a["resid_pdrop"]),
+                       goal_drop=float(a["goal_drop"]))
+    m.train()
+    torch.manual_seed(int(a["rng_seed"]))
+    goal_keep = None
+    if float(a["goal_drop"]) > 0:
+        goal_keep = 1.0 - torch.bernoulli(torch.ones(a["goal"].shape) * float(a["goal_drop"]))
+    masks = draw_dropout_masks(m.inner_model, a["action"].shape[0], a["action"].shape[1], "cpu")
+    return cfg, sd, a, goal_keep, masks
+
+
+@pytest.mark.parametrize("name", ["loss_dropout_K256", "loss_dropout_B256"])
+def test_dropout_masks_replay_the_reference_generator(name):
+    """Golden = the UNMODIFIED reference in training mode with dropout under torch.manual_seed; the oracle fed with the
+    product's re-drawn masks must give the same loss and gradients (same masks <=> same generator consumption)."""
+    from conftest import to_oracle_cfg
+    cfg, sd, a, goal_keep, masks = _replay_training_draws(name)
+    assert masks is not None and (masks["attn"][0] is not None)
+    kw = dict(drop_masks=masks)
+    if goal_keep is not None:
+        kw["goal_keep"] = goal_keep
+    loss, grads = O.loss_and_grads(sd, to_oracle_cfg(cfg), a["state"], a["action"], a["goal"], a["noise"].clone(), a["sigma"], **kw)
+    torch.testing.assert_close(loss, a["loss"], rtol=1e-5, atol=1e-7)
+    for n in [str(x) for x in a["grad_names"]]:
+        flat = grads[n].reshape(-1)
+        got = flat if flat.numel() <= 4096 else flat[::97][:4096]
+        want = a["grad::" + n]
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-6 * float(want.abs().max()) + 2e-8)

@@ -90,9 +90,10 @@ def test_goal_mask_changes_loss_and_matches_oracle(cuda_device):
     assert abs(float(loss.cpu()) - float(a["loss"])) > 1e-6
 
 
-def test_tf32_training_math_is_opt_in_and_close(cuda_device):
-    """model.train_math = "tf32": tensor-core GEMMs.  Not the reference's arithmetic (fp32), so it is opt-in and
-    only has to stay close: loss within 1e-3 relative, flat gradient direction within 1e-4 of the fp32 one."""
+def test_single_pass_bf16_training_math_is_opt_in_and_close(cuda_device):
+    """model.train_math = "bf16": one bf16 MMA per product (mixed-precision training arithmetic) instead of the default
+    split bf16 hi + lo / three MMAs.  Not the reference's arithmetic (fp32), so it is opt-in and only has to stay
+    close: loss within 2e-3 relative, flat gradient direction within 1e-3 of the fp32-parity one."""
     import time
     cfg = B256
     sd = synthetic_state_dict(cfg, 41)
@@ -102,7 +103,7 @@ def test_tf32_training_math_is_opt_in_and_close(cuda_device):
     args = (g["state"], g["clean"], g["goal"], g["noise"], g["sigma"])
     times = {}
     out = {}
-    for math in ("fp32", "tf32"):
+    for math in ("fp32", "bf16"):
         m.train_math = math
         out[math] = loss_and_flat_grad(m, *args)
         torch.cuda.synchronize()
@@ -111,13 +112,13 @@ def test_tf32_training_math_is_opt_in_and_close(cuda_device):
             loss_and_flat_grad(m, *args)
         torch.cuda.synchronize()
         times[math] = (time.perf_counter() - t0) / 3 * 1e3
-    (l32, f32), (ltf, ftf) = out["fp32"], out["tf32"]
-    torch.testing.assert_close(ltf, l32, rtol=1e-3, atol=1e-7)
+    (l32, f32), (ltf, ftf) = out["fp32"], out["bf16"]
+    torch.testing.assert_close(ltf, l32, rtol=2e-3, atol=1e-7)
     cos = torch.nn.functional.cosine_similarity(f32, ftf, dim=0)
-    assert float(cos) > 1.0 - 1e-4, float(cos)
+    assert float(cos) > 1.0 - 1e-3, float(cos)
     assert not torch.equal(f32, ftf)                         # the flag really switched the arithmetic
-    print(f"cfg3 fwd+bwd B=4096: fp32 {times['fp32']:.1f} ms, tf32 {times['tf32']:.1f} ms, grad cosine {float(cos):.7f}")
-    m.train_math = "bf16"
+    print(f"cfg3 fwd+bwd B=4096: fp32-parity {times['fp32']:.1f} ms, bf16 {times['bf16']:.1f} ms, grad cosine {float(cos):.7f}")
+    m.train_math = "fp8"
     with pytest.raises(ValueError):
         loss_and_flat_grad(m, *args)
 
@@ -178,3 +179,82 @@ def test_agent_train_step_matches_manual_reference_sequence(cuda_device):
     assert last < losses[0]
     mse = agent.evaluate(x["state"], x["clean"], x["goal"])
     assert mse == mse and mse >= 0.0
+
+
+@pytest.mark.parametrize("name", ["loss_dropout_K256", "loss_dropout_B256"])
+def test_loss_with_dropout_matches_reference_golden(name, cuda_device):
+    """Training mode WITH dropout (attn_pdrop 0.3: configs/franka_kitchen_main_config.yaml:56; 0.05 / 0.05 + CFG goal
+    mask: configs/block_push_main_config.yaml:57-58).  The golden is the unmodified reference under a fixed seed on the
+    CPU; the masks are re-drawn here with the product's draw routine under the same seed (tests/test_oracle.py shows
+    that this replays the reference's generator) and applied by the CUDA kernels."""
+    from test_oracle import _replay_training_draws
+    cfg, sd, a, goal_keep, masks = _replay_training_draws(name)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd, attn_pdrop=float(a["attn_pdrop"]),
+                       resid_pdrop=float(a["resid_pdrop"]), goal_drop=float(a["goal_drop"]))
+    m.train()
+    g = cuda(a, cuda_device)
+    loss, flat = loss_and_flat_grad(m, g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"],
+                                    goal_keep=None if goal_keep is None else goal_keep.to(cuda_device).contiguous(),
+                                    dropout_masks=masks)
+    torch.testing.assert_close(loss.cpu(), a["loss"], rtol=1e-4, atol=1e-7)
+    from beso_b200.training import flat_grad_views
+    views = dict(zip([n for n, _ in m.named_parameters()], flat_grad_views(m, flat)))
+    for n, ref_norm in zip([str(x) for x in a["grad_names"]], a["grad_norms"]):
+        gr = views[n]
+        got_norm = gr.double().norm().item()
+        assert abs(got_norm - ref_norm) <= 2e-3 * ref_norm + 1e-7, (n, got_norm, ref_norm)
+        fl = gr.reshape(-1).cpu()
+        got = fl if fl.numel() <= 4096 else fl[::97][:4096]
+        want = a["grad::" + n]
+        torch.testing.assert_close(got, want, rtol=2e-3, atol=1e-6 * float(want.abs().max()) + 2e-8)
+    # through the module API: the draws come from the device generator in the same op order; two steps under the same
+    # seed see the same masks, a different seed a different loss
+    torch.manual_seed(3)
+    l1 = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"])
+    torch.manual_seed(3)
+    l2 = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"])
+    torch.manual_seed(4)
+    l3 = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"])
+    assert torch.equal(l1, l2) and not torch.equal(l1, l3)
+    m.eval()                                                       # eval: no dropout, no goal mask
+    l_eval = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"])
+    assert not torch.equal(l_eval, l1)
+
+
+GEMM_CASES = [  # M, N, K, a_kmajor, b_kmajor  (forward NT, data-gradient NN, weight-gradient TN, ragged edges)
+    (1000, 256, 256, 1, 1), (777, 1024, 256, 1, 1), (513, 256, 1024, 1, 1), (300, 9, 256, 1, 1),
+    (640, 1024, 256, 1, 0), (515, 256, 1024, 1, 0), (256, 1024, 5000, 0, 0), (1024, 256, 3001, 0, 0),
+    (256, 60, 2000, 0, 0), (256, 1, 700, 0, 0), (240, 240, 900, 0, 0), (130, 240, 240, 1, 1), (9, 256, 333, 0, 0),
+]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+def test_tcgen05_training_gemm_against_fp64(prec, cuda_device):
+    """csrc/gemm.cu by itself against a float64 product of the same fp32 inputs: the split (fp32-parity) mode to 2e-5 of
+    the output scale, the single-pass bf16 mode to 1e-2; bias and accumulate epilogues; deterministic split-K."""
+    import ctypes as C
+    from beso_b200 import K256, _lib
+    lib = _lib.lib()
+    m = build_denoiser(K256, cuda_device, mode="precise", state_dict=synthetic_state_dict(K256, 1))
+    m.refresh_weights()
+    plan = m._plan
+    gen = torch.Generator().manual_seed(5)
+    for (M, N, K, ak, bk) in GEMM_CASES:
+        A = torch.randn((M, K) if ak else (K, M), generator=gen).to(cuda_device)
+        Bm = torch.randn((N, K) if bk else (K, N), generator=gen).to(cuda_device)
+        bias = torch.randn(N, generator=gen).to(cuda_device)
+        C0 = torch.randn(M, N, generator=gen).to(cuda_device)
+        Am = A.double() if ak else A.double().t()
+        Bt = Bm.double().t() if bk else Bm.double()
+        want = Am @ Bt + bias.double() + C0.double()
+        out = C0.clone()
+        _lib.check(lib.beso_debug_gemm(plan, A.data_ptr(), A.shape[1], ak, Bm.data_ptr(), Bm.shape[1], bk, out.data_ptr(), N,
+                                       M, N, K, bias.data_ptr(), 1, prec, None), "beso_debug_gemm")
+        scale = float(want.abs().max())
+        err = float((out.double() - want).abs().max())
+        tol = (2e-5 if prec else 1e-2) * scale
+        assert err <= tol, ((M, N, K, ak, bk), err, scale)
+        out2 = C0.clone()
+        _lib.check(lib.beso_debug_gemm(plan, A.data_ptr(), A.shape[1], ak, Bm.data_ptr(), Bm.shape[1], bk, out2.data_ptr(), N,
+                                       M, N, K, bias.data_ptr(), 1, prec, None), "beso_debug_gemm")
+        assert torch.equal(out, out2)                              # deterministic (fixed split-K reduction order)

@@ -72,7 +72,7 @@ def main():
         fl = 4096 * c.fwd_flops_per_seq()
         res[name] = {"ms": ms, "denoise_steps_per_s": 4096 / ms * 1e3, "tflops": fl / ms / 1e9, "frac_sustained": fl / ms / 1e9 / PEAK}
     # cfg3: block-push training step, batch 4096 (loss + backward + fused AdamW/EMA step)
-    for math in ("fp32", "tf32"):
+    for math in ("fp32", "bf16"):
         mt = build_denoiser(B256, dev, mode="precise", state_dict=synthetic_state_dict(B256, 41))
         mt.train(); mt.train_math = math
         g = {k: v.to(dev) for k, v in synthetic_inputs(B256, 4096, seed=42, sigma_min=0.05).items()}

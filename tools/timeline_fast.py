@@ -1,6 +1,6 @@
 """GPU diagnostics: where one CTA of the FAST kernel spends its second model evaluation.
 
-    python tools/timeline_fast.py [T16|K256] > gpurun_out/timeline.txt
+    python tools/timeline_fast.py [T16|K256] [batch] [fast|precise] > gpurun_out/timeline.txt
 
 Prints, in SM clock cycles, (a) the compute warps' phase durations and waits, (b) for the MMA
 issuer, per GEMM job, time spent waiting on barriers (compute) vs on the weight ring (producer).
@@ -24,7 +24,8 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     cfg = {"K256": K256, "T16": T16}[name]
     dev = torch.device("cuda:0")
-    m = build_denoiser(cfg, dev, mode="fast", state_dict=synthetic_state_dict(cfg, 1))
+    mode = sys.argv[3] if len(sys.argv) > 3 else "fast"
+    m = build_denoiser(cfg, dev, mode=mode, state_dict=synthetic_state_dict(cfg, 1))
     x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=2).items()}
     sig = get_sigmas_exponential(4, 0.005, 1.0)
     L = cfg.n_layers
@@ -40,7 +41,7 @@ def main():
     jobs = [tl[4 * j:4 * j + 4] for j in range(NJ)]          # per MMA job: start, barrier-wait, ring-wait, end
     ev = [v for v in tl[6 * NF:] if v]
     t0 = min(ev[0], jobs[0][0])
-    print(f"# {name} B={B}: one evaluation = {max(ev[-1], jobs[-1][3]) - t0} cycles")
+    print(f"# {name} B={B} mode={mode}: one evaluation = {max(ev[-1], jobs[-1][3]) - t0} cycles")
 
     # ---- compute warps ----
     it = iter(ev)

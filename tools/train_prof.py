@@ -1,4 +1,4 @@
-"""One cfg3 training step (fwd + bwd, B = 4096) for kernel-level profiling.  python tools/train_prof.py [fp32|tf32]"""
+"""One cfg3 training step (fwd + bwd, B = 4096) for kernel-level profiling.  python tools/train_prof.py [fp32|bf16]"""
 import os
 import sys
 
