@@ -179,21 +179,19 @@ class BesoAgent:
             return
         core = self._core()
         if on:
-            if 1 not in core._packed:
-                live = [p.data.clone() for p in core.inner_model.parameters()]
-                for p, e in zip(core.inner_model.parameters(), self.ema_params):
-                    p.data.copy_(e)
-                core.refresh_weights(slot=1, force=True)
-                for p, v in zip(core.inner_model.parameters(), live):
-                    p.data.copy_(v)
-                core.refresh_weights(slot=0, force=True)
+            # Slot 1 is packed straight from the EMA shadow tensors and stamped with the EMA generation it was packed
+            # at; optimiser steps that do not update the EMA (update_ema_every_n_steps > 1) change neither.
+            gen = getattr(self, "_ema_generation", 0)
+            if 1 not in core._packed or core.packed_tag(1) != ("ema", gen):
+                core.refresh_weights(slot=0, force=False)          # plan exists, raw slot current
+                core.pack_tensors(1, list(self.ema_params), tag=("ema", gen))
             core.select_weights(1)
         else:
             core.select_weights(0)
 
     def ema_updated(self):
-        """Call after the EMA shadow parameters changed so slot 1 is re-packed on next use."""
-        self._core()._packed.pop(1, None)
+        """Call after the EMA shadow parameters changed: slot 1 is re-packed from them on next use."""
+        self._ema_generation = getattr(self, "_ema_generation", 0) + 1
 
     # ---- training: beso_agent.py:215-248, 540-578; k_diffusion/utils.py:170-200 -------------------------
     def configure_training(self, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,

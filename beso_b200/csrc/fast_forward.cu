@@ -66,7 +66,6 @@ constexpr uint32_t kQkvStride = 400;                // bytes per row of the bf16
 constexpr uint32_t kSmQkv = kSmU;                   // [128][400 B]
 constexpr uint32_t kSmY = kSmU + 51200;             // attention output atom [128 x 64] bf16
 constexpr uint32_t kSmH0 = kSmU, kSmH1 = kSmU + 32768;   // FC1 output chunks, 2 atoms each
-constexpr uint32_t kQkvStrideP = 784;               // PREC: bytes per row of the fp32 [Q|K|V] staging (192 + 4 pad floats), 64 rows
 constexpr uint32_t kSmVecA = kSmU + 67584;          // 198656: [pend(256) | bq: 192 per pass, up to 6 passes | spare] fp32
 constexpr uint32_t kVecBq = 256;                    // float index of the Q biases inside vecA
 constexpr uint32_t kVecAFloats = 1536;
@@ -268,6 +267,13 @@ __device__ __forceinline__ void gelu2_vec(__half2 (&x)[NP]) {
 }
 __device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+// (a, b) -> packed fp16 hi pair and the packed fp16 rounding of the remainders
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  hi = h2bits(h);
+  lo = h2bits(__floats2half2_rn(a - hf.x, b - hf.y));
+}
 
 __device__ __forceinline__ float ex2f(float x) {
   float e;
@@ -424,31 +430,46 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // their scores are neither computed nor exponentiated.
 // HSP = padded head size: 64 (one head per pass) or 32 (two heads per pass, `co` = column offset of this head inside
 // the 64-column blocks of Q, K, V and Y).
-template <int NKT, bool HI, int HSP>
+// SPLIT (the precise mode): staging rows [0, 64) hold the fp16 hi image of Q|K|V and rows [64, 128) the lo image;
+// every product is three mma.sync (hi.hi + lo.hi + hi.lo, fp32 accumulate), the probabilities are split the same way
+// and the output goes to the hi / lo rows of the Y atom.
+template <int NKT, bool HI, int HSP, bool SPLIT>
 __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co) {
   const uint32_t qkv = sbase + kSmQkv + (uint32_t)co * 2u;
   constexpr int KS = HSP / 16;                   // 16-wide k steps over the head dimension
+  constexpr int kLastRow = SPLIT ? 63 : kRows - 1;
+  constexpr uint32_t kLo = 64u * kQkvStride;     // byte offset of the lo image
   // ---- S = Q K^T ----
   float sc[NKT][2][4];
 #pragma unroll
   for (int a = 0; a < NKT; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) sc[a][b][0] = sc[a][b][1] = sc[a][b][2] = sc[a][b][3] = 0.f;
-  uint32_t qa[KS][4];
+  uint32_t qa[KS][4], ql[SPLIT ? KS : 1][4];
   {
-    const int r = min(row0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
+    const int r = min(row0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kLastRow);
 #pragma unroll
-    for (int k = 0; k < KS; ++k) ldmatrix_x4(qkv + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, qa[k]);
+    for (int k = 0; k < KS; ++k) {
+      ldmatrix_x4(qkv + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, qa[k]);
+      if constexpr (SPLIT) ldmatrix_x4(qkv + kLo + r * kQkvStride + (k * 16 + (lane >> 4) * 8) * 2, ql[k]);
+    }
   }
 #pragma unroll
   for (int kt = 0; kt < NKT; ++kt) {
-    const int r = min(row0 + kt * 16 + (lane & 7) + (lane >> 4) * 8, kRows - 1);
+    const int r = min(row0 + kt * 16 + (lane & 7) + (lane >> 4) * 8, kLastRow);
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       uint32_t kb[4];
       ldmatrix_x4(qkv + r * kQkvStride + (64 + k * 16 + ((lane >> 3) & 1) * 8) * 2, kb);
       mma_16816(sc[kt][0], qa[k], kb[0], kb[1]);
       if (HI || kt + 1 < NKT) mma_16816(sc[kt][1], qa[k], kb[2], kb[3]);
+      if constexpr (SPLIT) {
+        mma_16816(sc[kt][0], ql[k], kb[0], kb[1]);                              // lo . hi
+        if (HI || kt + 1 < NKT) mma_16816(sc[kt][1], ql[k], kb[2], kb[3]);
+        ldmatrix_x4(qkv + kLo + r * kQkvStride + (64 + k * 16 + ((lane >> 3) & 1) * 8) * 2, kb);
+        mma_16816(sc[kt][0], qa[k], kb[0], kb[1]);                              // hi . lo
+        if (HI || kt + 1 < NKT) mma_16816(sc[kt][1], qa[k], kb[2], kb[3]);
+      }
     }
   }
   // ---- mask + softmax (rows i0 = lane/4 and i0 + 8 of this query tile) ----
@@ -488,13 +509,22 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
   if (HI) { sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2); }
   const float inv_lo = __frcp_rn(sum_lo), inv_hi = HI ? __frcp_rn(sum_hi) : 0.f;
-  uint32_t pa[NKT][4];                           // P as A fragments, one per 16-key step
+  uint32_t pa[NKT][4], pl[SPLIT ? NKT : 1][4];   // P as A fragments, one per 16-key step (and the lo image)
 #pragma unroll
   for (int kt = 0; kt < NKT; ++kt) {
+    if constexpr (SPLIT) {
+      split2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo, pa[kt][0], pl[kt][0]);
+      split2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi, pa[kt][1], pl[kt][1]);
+      split2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo, pa[kt][2], pl[kt][2]);
+      split2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi, pa[kt][3], pl[kt][3]);
+      if (!HI) { pa[kt][1] = pa[kt][3] = pl[kt][1] = pl[kt][3] = 0u; }
+      if (!(HI || kt + 1 < NKT)) { pa[kt][2] = pl[kt][2] = 0u; }
+    } else {
     pa[kt][0] = pack_f16x2(sc[kt][0][0] * inv_lo, sc[kt][0][1] * inv_lo);   // (row lo, keys 0-7)
     pa[kt][1] = HI ? pack_f16x2(sc[kt][0][2] * inv_hi, sc[kt][0][3] * inv_hi) : 0u;   // (row hi, keys 0-7)
     pa[kt][2] = (HI || kt + 1 < NKT) ? pack_f16x2(sc[kt][1][0] * inv_lo, sc[kt][1][1] * inv_lo) : 0u;   // (row lo, keys 8-15)
     pa[kt][3] = HI ? pack_f16x2(sc[kt][1][2] * inv_hi, sc[kt][1][3] * inv_hi) : 0u;   // (row hi, keys 8-15)
+    }
   }
   // ---- O = P V ----
   constexpr int NO = HSP / 8;                    // 8-wide output column tiles
@@ -503,30 +533,49 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
   for (int kt = 0; kt < NKT; ++kt) {
-    const int r = min(row0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kRows - 1);
+    const int r = min(row0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kLastRow);
 #pragma unroll
     for (int np = 0; np < NO / 2; ++np) {        // pairs of 8-wide output column tiles
       uint32_t vb[4];
       ldmatrix_x4_trans(qkv + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
       mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);
       mma_16816(o[np * 2 + 1], pa[kt], vb[2], vb[3]);
+      if constexpr (SPLIT) {
+        mma_16816(o[np * 2], pl[kt], vb[0], vb[1]);                             // lo . hi
+        mma_16816(o[np * 2 + 1], pl[kt], vb[2], vb[3]);
+        ldmatrix_x4_trans(qkv + kLo + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
+        mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);                             // hi . lo
+        mma_16816(o[np * 2 + 1], pa[kt], vb[2], vb[3]);
+      }
     }
   }
   // column e = n * 8 + (lane & 3) * 2 of the head: 16-byte chunk n of the row, bytes (lane & 3) * 4 within it
-  const uint32_t r_lo = (uint32_t)(row0 + i_lo), r_hi = (uint32_t)(row0 + i_hi);
+  uint32_t r_lo = (uint32_t)(row0 + i_lo), r_hi = (uint32_t)(row0 + i_hi);
+  if constexpr (SPLIT) {                          // sequence row -> its hi operand row (the lo row is 16 rows below)
+    r_lo = ((r_lo >> 4) << 5) | (r_lo & 15u);
+    r_hi = ((r_hi >> 4) << 5) | (r_hi & 15u);
+  }
   const uint32_t y_lo = sbase + kSmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
   const uint32_t y_hi = sbase + kSmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
   const uint32_t n0 = (uint32_t)co >> 3;         // first 16-byte chunk of this head inside the Y row
   if (i_lo < T) {
 #pragma unroll
-    for (int n = 0; n < NO; ++n) sts32(y_lo + (((n0 + (uint32_t)n) << 4) ^ x_lo), pack_f16x2(o[n][0], o[n][1]));
+    for (int n = 0; n < NO; ++n) {
+      const uint32_t a = y_lo + (((n0 + (uint32_t)n) << 4) ^ x_lo);
+      if constexpr (SPLIT) { uint32_t h, l; split2(o[n][0], o[n][1], h, l); sts32(a, h); sts32(a + 2048u, l); }
+      else sts32(a, pack_f16x2(o[n][0], o[n][1]));
+    }
   }
   if (HI && i_hi < T) {
 #pragma unroll
-    for (int n = 0; n < NO; ++n) sts32(y_hi + (((n0 + (uint32_t)n) << 4) ^ x_hi), pack_f16x2(o[n][2], o[n][3]));
+    for (int n = 0; n < NO; ++n) {
+      const uint32_t a = y_hi + (((n0 + (uint32_t)n) << 4) ^ x_hi);
+      if constexpr (SPLIT) { uint32_t h, l; split2(o[n][2], o[n][3], h, l); sts32(a, h); sts32(a + 2048u, l); }
+      else sts32(a, pack_f16x2(o[n][2], o[n][3]));
+    }
   }
 }
-template <int HSP>
+template <int HSP, bool SPLIT>
 __device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T) {
   constexpr int NSUB = 64 / HSP;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
@@ -535,13 +584,13 @@ __device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int 
     const int mt = MT - 1 - it2 / S, s = it2 % S;     // later query tiles see more keys: schedule them first
     const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
     const int co = sub * HSP;
-    if (mt == 0) { if (hi) attention_item<1, true, HSP>(sbase, lane, s * T, 0, T, co); else attention_item<1, false, HSP>(sbase, lane, s * T, 0, T, co); }
-    else { if (hi) attention_item<2, true, HSP>(sbase, lane, s * T, mt, T, co); else attention_item<2, false, HSP>(sbase, lane, s * T, mt, T, co); }
+    if (mt == 0) { if (hi) attention_item<1, true, HSP, SPLIT>(sbase, lane, s * T, 0, T, co); else attention_item<1, false, HSP, SPLIT>(sbase, lane, s * T, 0, T, co); }
+    else { if (hi) attention_item<2, true, HSP, SPLIT>(sbase, lane, s * T, mt, T, co); else attention_item<2, false, HSP, SPLIT>(sbase, lane, s * T, mt, T, co); }
   }
 }
 __device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T, int hsp) {
-  if (hsp == 64) attention_head_t<64>(sbase, awarp, lane, S, T);
-  else attention_head_t<32>(sbase, awarp, lane, S, T);
+  if (hsp == 64) attention_head_t<64, false>(sbase, awarp, lane, S, T);
+  else attention_head_t<32, false>(sbase, awarp, lane, S, T);
 }
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
@@ -595,13 +644,6 @@ __device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) 
 // The schedule, the barriers and the shared / tensor memory maps are those of the fp16 mode; the weight tape holds
 // [hi tile | lo tile] per ring group.
 __device__ __forceinline__ float shx16(float v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
-// (a, b) -> packed fp16 hi pair and the packed fp16 rounding of the remainders
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  hi = h2bits(h);
-  lo = h2bits(__floats2half2_rn(a - hf.x, b - hf.y));
-}
 // 8 consecutive K elements -> the 16-byte chunk of the hi row and of the lo row (16 rows = 2048 bytes below)
 __device__ __forceinline__ void st_chunk_split(uint32_t addr_hi, const float* v) {
   uint32_t h[4], l[4];
@@ -670,8 +712,9 @@ __device__ __noinline__ void ln_pass_p(const Compute c, uint32_t vec_s, float in
   c.arrive(B_A_READY);
 }
 
-// [Q|K|V] accumulator of one attention pass -> fp32 staging rows (Q gets its bias).  Per 32-column piece the pair
-// threads exchange halves: each ends up with 16 columns of Q, of K and of V of the sequence row.
+// [Q|K|V] accumulator of one attention pass -> fp16 staging, hi image in rows [0, 64) and lo image in rows [64, 128)
+// (Q gets its bias).  Per 32-column piece the pair threads exchange halves: each ends up with 16 columns of Q, of K
+// and of V of the sequence row.
 __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
   float v0[32], v1[32], v2[32];
   const int colb = c.hf * 32;
@@ -682,7 +725,7 @@ __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
   const int cs = colb + c.is_lo * 16;                     // first of this thread's 16 columns inside each 64-block
-  const uint32_t dst = c.sbase + kSmQkv + (uint32_t)c.srow * kQkvStrideP + (uint32_t)cs * 4u;
+  const uint32_t dst = c.sbase + kSmQkv + (uint32_t)c.srow * kQkvStride + (uint32_t)cs * 2u;
   auto emit = [&](const float (&v)[32], uint32_t d, bool bias) {
     float r[16];
 #pragma unroll
@@ -694,121 +737,23 @@ __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
         r[i] += b0.x; r[i + 1] += b0.y; r[i + 2] += b0.z; r[i + 3] += b0.w;
       }
     }
+    uint32_t h[8], l[8];
 #pragma unroll
-    for (int i = 0; i < 16; i += 4)
-      sts128(d + i * 4, __float_as_uint(r[i]), __float_as_uint(r[i + 1]), __float_as_uint(r[i + 2]), __float_as_uint(r[i + 3]));
+    for (int i = 0; i < 8; ++i) split2(r[2 * i], r[2 * i + 1], h[i], l[i]);
+    sts128(d, h[0], h[1], h[2], h[3]);
+    sts128(d + 16, h[4], h[5], h[6], h[7]);
+    sts128(d + 64u * kQkvStride, l[0], l[1], l[2], l[3]);
+    sts128(d + 64u * kQkvStride + 16, l[4], l[5], l[6], l[7]);
   };
-  emit(v0, dst, true); emit(v1, dst + 256, false); emit(v2, dst + 512, false);
+  emit(v0, dst, true); emit(v1, dst + 128, false); emit(v2, dst + 256, false);
 }
 
-__device__ __forceinline__ float2 lds64f(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-// Causal softmax(Q K^T) V in fp32 out of the staging buffer: four threads (a lane quad) per (sequence row, head).
-// Quad member m scores keys m, m + 4, ... against the query row held in its registers, the quad reduces the row
-// maximum / sum with two shuffles each, then member m accumulates output columns [m HSP/4, (m + 1) HSP/4) over all
-// keys (probabilities arrive by quad shuffle).  Loop bounds are the warp's longest row (its 8 rows are consecutive,
-// so they differ by at most 7 keys).  Q is pre-scaled by log2(e) / sqrt(hs).  Output: split into the Y atom.
-// Only the 8 compute warps carry rows (64 rows x 4 threads); with two heads per pass they take two rounds.
-template <int HSP>
-__device__ __forceinline__ void attention_head_pt(uint32_t sbase, int awarp, int lane, int S, int T) {
-  constexpr int NSUB = 64 / HSP, QV = HSP / 4, OC = HSP / 4;     // float4 per query row; output columns per quad member
-  constexpr int kMaxJJ = (kMaxTokens + 3) / 4;
-  const uint32_t base = sbase + kSmQkv;
-  if (awarp >= 8) return;
-  const int qm = lane & 3, qbase = lane & ~3;
-  const int rho = awarp * 8 + (lane >> 2);                       // sequence row of this quad
-  const int seq = rho / T, i = rho - seq * T, row0 = seq * T;
-  const bool valid = seq < S;
-  const int i_eff = valid ? i : -1;
-  int imax = i_eff;
-#pragma unroll
-  for (int o = 4; o < 32; o <<= 1) imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
-  if (imax < 0) return;                                          // warp-uniform: no row of this warp is inside the tile
-#pragma unroll 1
-  for (int sub = 0; sub < NSUB; ++sub) {
-    const uint32_t co = (uint32_t)(sub * HSP) * 4u;
-    float4 q[QV];
-    const uint32_t qrow = base + (uint32_t)(valid ? rho : 0) * kQkvStrideP + co;
-#pragma unroll
-    for (int e = 0; e < QV; ++e) q[e] = lds128f(qrow + e * 16);
-    float sc[kMaxJJ];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < kMaxJJ; ++jj) {
-      sc[jj] = -INFINITY;
-      if (jj * 4 > imax) continue;                               // uniform
-      const int j = jj * 4 + qm;
-      if (j <= i_eff) {
-        const uint32_t krow = base + (uint32_t)(row0 + j) * kQkvStrideP + 256u + co;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int e = 0; e < QV; e += 2) {
-          const float4 b0 = lds128f(krow + e * 16), b1 = lds128f(krow + e * 16 + 16);
-          s0 = fmaf(q[e].w, b0.w, fmaf(q[e].z, b0.z, fmaf(q[e].y, b0.y, fmaf(q[e].x, b0.x, s0))));
-          s1 = fmaf(q[e + 1].w, b1.w, fmaf(q[e + 1].z, b1.z, fmaf(q[e + 1].y, b1.y, fmaf(q[e + 1].x, b1.x, s1))));
-        }
-        sc[jj] = s0 + s1;
-        mx = fmaxf(mx, sc[jj]);
-      }
-    }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < kMaxJJ; ++jj) {
-      sc[jj] = (jj * 4 + qm <= i_eff) ? exp2f(sc[jj] - mx) : 0.f;
-      sum += sc[jj];
-    }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const float inv = valid ? __fdiv_rn(1.0f, sum) : 0.f;
-    float o[OC];
-#pragma unroll
-    for (int e = 0; e < OC; ++e) o[e] = 0.f;
-    const uint32_t vcol = base + 512u + co + (uint32_t)(qm * OC) * 4u;
-#pragma unroll
-    for (int jj = 0; jj < kMaxJJ; ++jj) {
-      if (jj * 4 > imax) continue;                               // uniform
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int j = jj * 4 + m;
-        const float pw = __shfl_sync(0xffffffffu, sc[jj], qbase + m);
-        if (j <= i_eff) {
-          const uint32_t vrow = vcol + (uint32_t)(row0 + j) * kQkvStrideP;
-#pragma unroll
-          for (int e = 0; e < OC / 4; ++e) {
-            const float4 vv = lds128f(vrow + e * 16);
-            o[4 * e] = fmaf(pw, vv.x, o[4 * e]); o[4 * e + 1] = fmaf(pw, vv.y, o[4 * e + 1]);
-            o[4 * e + 2] = fmaf(pw, vv.z, o[4 * e + 2]); o[4 * e + 3] = fmaf(pw, vv.w, o[4 * e + 3]);
-          }
-        }
-      }
-    }
-    if (valid) {
-      const uint32_t ur = (uint32_t)rho, mrow = ((ur >> 4) << 5) | (ur & 15u);      // hi row of the sequence row
-      const uint32_t col = (uint32_t)(sub * HSP + qm * OC);                          // multiple of 8
-      const uint32_t a = sbase + kSmY + mrow * 128u;
-#pragma unroll
-      for (int k = 0; k < OC / 8; ++k) {
-        float y[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = o[k * 8 + e] * inv;
-        st_chunk_split(a + ((((col >> 3) + (uint32_t)k) ^ (mrow & 7u)) << 4), y);
-      }
-    }
-  }
-}
+// Causal attention of the precise mode: the mma.sync kernel of the fp16 mode with every product split three ways
+// (attention_item<..., SPLIT = true>): the operands come out of shared memory once per 16 x 8 tile, which keeps the
+// attention phase off the shared-memory port the tensor pipe is streaming its operands through.
 __device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T, int hsp) {
-  if (hsp == 64) attention_head_pt<64>(sbase, awarp, lane, S, T);
-  else attention_head_pt<32>(sbase, awarp, lane, S, T);
+  if (hsp == 64) attention_head_t<64, true>(sbase, awarp, lane, S, T);
+  else attention_head_t<32, true>(sbase, awarp, lane, S, T);
 }
 
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }

@@ -17,8 +17,10 @@
 // buffers and a second kernel that adds them in a fixed order (deterministic).
 //
 // Why bf16 and not fp16 here: gradients of a batch-mean loss are ~1e-6 and below, outside fp16's range; bf16 keeps
-// fp32's exponent.  hi + lo carries 16 mantissa bits per operand; dropping lo.lo leaves ~2^-16 relative error per
-// product, far inside the gradient-parity tolerance (rtol 2e-3, tests/test_training_gpu.py).
+// fp32's exponent.  Operand precision is bought with images: x = h + m + l (three bf16 values, 24 mantissa bits,
+// exact remainders) and the product keeps every cross term down to 2^-24 (hh, hm, mh, mm, hl, lh: six MMAs) -- the
+// fp32-parity mode the gradient goldens pin; two images / three MMAs carry 16 bits (~1e-5 of the output scale), one
+// image is plain bf16 mixed-precision arithmetic.
 #include <cuda_bf16.h>
 
 #include <string>
@@ -39,10 +41,11 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr uint32_t kStagePitch = 144;                 // bytes per row of the epilogue transpose buffer (32 floats + 4 pad)
 constexpr uint32_t kStageBufBytes = 32 * kStagePitch; // per epilogue warp
 
-template <int BN, bool PREC>
+// IMG = bf16 images per operand: 1 (x ~ h), 2 (x ~ h + m: 16 mantissa bits), 3 (x ~ h + m + l: 24 bits = fp32)
+template <int BN, int IMG>
 struct Cfg {
   static constexpr uint32_t a_bytes = kBM * 128u, b_bytes = BN * 128u;
-  static constexpr uint32_t images = PREC ? 2u : 1u;
+  static constexpr uint32_t images = (uint32_t)IMG;
   static constexpr uint32_t stage_bytes = images * (a_bytes + b_bytes);
   static constexpr uint32_t stages_raw = 196608u / stage_bytes;
   static constexpr uint32_t stages = stages_raw > 6u ? 6u : stages_raw;
@@ -89,29 +92,34 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
   wait_slow(bar, parity);
 }
 
-// 8 consecutive K values -> one 16-byte chunk of the hi image (and of the lo image)
-template <bool PREC>
-__device__ __forceinline__ void store_chunk(uint32_t hi_addr, uint32_t lo_delta, const float (&v)[8]) {
-  uint32_t h[4], l[4];
+// 8 consecutive K values -> one 16-byte chunk of each bf16 image: h = bf16(x), m = bf16(x - h), l = bf16(x - h - m)
+// (the remainders are exact in fp32); image i of the tile lies i * img_delta bytes after the first
+template <int IMG>
+__device__ __forceinline__ void store_chunk(uint32_t addr, uint32_t img_delta, const float (&v)[8]) {
+  float r[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    h[i] = *reinterpret_cast<const uint32_t*>(&b);
-    if (PREC) {
-      const float2 f = __bfloat1622float2(b);
-      const __nv_bfloat162 r = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
-      l[i] = *reinterpret_cast<const uint32_t*>(&r);
+  for (int i = 0; i < 8; ++i) r[i] = v[i];
+#pragma unroll
+  for (int im = 0; im < IMG; ++im) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&b);
+      if (im + 1 < IMG) {
+        const float2 f = __bfloat1622float2(b);
+        r[2 * i] -= f.x; r[2 * i + 1] -= f.y;
+      }
     }
+    sts128(addr + (uint32_t)im * img_delta, w[0], w[1], w[2], w[3]);
   }
-  sts128(hi_addr, h[0], h[1], h[2], h[3]);
-  if (PREC) sts128(hi_addr + lo_delta, l[0], l[1], l[2], l[3]);
 }
 
 // One operand tile [ROWS x 64] (element (row, k)) -> shared memory, by the 256 producer threads.
 //   KMAJOR: element at src[(row0 + row) * ld + k]     (k contiguous: 8 lanes read the 256 bytes of one row)
 //  !KMAJOR: element at src[k * ld + row0 + row]       (rows contiguous: a warp reads 32 rows of one k, 128 bytes)
 // Rows >= n_rows and k >= K are zero.  vec: 16-byte loads are legal (ld % 4 == 0, base 16-byte aligned).
-template <int ROWS, bool KMAJOR, bool PREC>
+template <int ROWS, bool KMAJOR, int IMG>
 __device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld, int row0, int n_rows, int k0, int K, bool vec,
                                           uint32_t smem_hi, uint32_t lo_delta, int ptid) {
   if (KMAJOR) {
@@ -136,7 +144,7 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld,
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int task = ptid + (t0 + u) * kProdThreads, row = task >> 3, chunk = task & 7;
-        store_chunk<PREC>(smem_hi + sw128_offset((uint32_t)row, (uint32_t)chunk), lo_delta, v[u]);
+        store_chunk<IMG>(smem_hi + sw128_offset((uint32_t)row, (uint32_t)chunk), lo_delta, v[u]);
       }
     }
   } else {
@@ -158,7 +166,7 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld,
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int task = pw + (t0 + u) * kProdWarps, rg = task >> 3, chunk = task & 7;
-        store_chunk<PREC>(smem_hi + sw128_offset((uint32_t)(rg * 32 + lane), (uint32_t)chunk), lo_delta, v[u]);
+        store_chunk<IMG>(smem_hi + sw128_offset((uint32_t)(rg * 32 + lane), (uint32_t)chunk), lo_delta, v[u]);
       }
     }
   }
@@ -173,9 +181,9 @@ struct KArgs {
 
 __device__ __forceinline__ float gelu_erf_g(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
 
-template <int BN, bool PREC, bool AK, bool BK>
+template <int BN, int IMG, bool AK, bool BK>
 __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constant__ KArgs ka) {
-  using C = Cfg<BN, PREC>;
+  using C = Cfg<BN, IMG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(sm);
@@ -209,8 +217,8 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
         const uint32_t s = it % C::stages, par = (it / C::stages) & 1u;
         wait_bar(bar_empty(s), par ^ 1u);
         const uint32_t st = sbase + s * C::stage_bytes;
-        load_tile<kBM, AK, PREC>(g.A, g.lda, t.m0, g.M, kb * kBK, g.K, ka.vec_a != 0, st, C::a_bytes, ptid);
-        load_tile<BN, BK, PREC>(g.B, g.ldb, t.n0 * BN, g.N, kb * kBK, g.K, ka.vec_b != 0, st + C::images * C::a_bytes, C::b_bytes, ptid);
+        load_tile<kBM, AK, IMG>(g.A, g.lda, t.m0, g.M, kb * kBK, g.K, ka.vec_a != 0, st, C::a_bytes, ptid);
+        load_tile<BN, BK, IMG>(g.B, g.ldb, t.n0 * BN, g.N, kb * kBK, g.K, ka.vec_b != 0, st + C::images * C::a_bytes, C::b_bytes, ptid);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full(s));
@@ -236,11 +244,13 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
         if (elect_one_g()) {
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) {
-            mma_bf16(d_addr, a_hi + 2u * j, b_hi + 2u * j, idesc, (kb > t.kb0 || j > 0) ? 1u : 0u);
-            if (PREC) {
-              mma_bf16(d_addr, a_hi + (C::a_bytes >> 4) + 2u * j, b_hi + 2u * j, idesc, 1u);        // lo . hi
-              mma_bf16(d_addr, a_hi + 2u * j, b_hi + (C::b_bytes >> 4) + 2u * j, idesc, 1u);        // hi . lo
-            }
+            // image pairs (a, b) with a + b < IMG: every cross term down to 2^-8 IMG of the product
+#pragma unroll
+            for (uint32_t ia = 0; ia < (uint32_t)IMG; ++ia)
+#pragma unroll
+              for (uint32_t ib = 0; ia + ib < (uint32_t)IMG; ++ib)
+                mma_bf16(d_addr, a_hi + ia * (C::a_bytes >> 4) + 2u * j, b_hi + ib * (C::b_bytes >> 4) + 2u * j, idesc,
+                         (kb > t.kb0 || j > 0 || ia > 0 || ib > 0) ? 1u : 0u);
           }
           mma_commit(bar_empty(s));
           if (kb + 1 == t.kb1) mma_commit(bar_accf(acc));
@@ -340,18 +350,18 @@ __global__ void splitk_reduce_kernel(GemmArgs g, const float* __restrict__ parti
   *cp = a;
 }
 
-template <int BN, bool PREC>
+template <int BN, int IMG>
 int launch(const KArgs& ka, int grid, cudaStream_t st) {
-  using C = Cfg<BN, PREC>;
+  using C = Cfg<BN, IMG>;
   const int smem = (int)C::smem + 1024;
 #define BESO_GEMM_CASE(AK, BK)                                                                                      \
   do {                                                                                                              \
     static bool cfgd = false;                                                                                       \
     if (!cfgd) {                                                                                                    \
-      BESO_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PREC, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      BESO_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, IMG, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       cfgd = true;                                                                                                  \
     }                                                                                                               \
-    gemm_kernel<BN, PREC, AK, BK><<<grid, kThreadsG, smem, st>>>(ka);                                               \
+    gemm_kernel<BN, IMG, AK, BK><<<grid, kThreadsG, smem, st>>>(ka);                                                \
   } while (0)
   if (ka.g.a_kmajor && ka.g.b_kmajor) BESO_GEMM_CASE(true, true);
   else if (ka.g.a_kmajor) BESO_GEMM_CASE(true, false);
@@ -376,7 +386,9 @@ int gemm_run(const GemmArgs& a, GemmWs& ws, int sm_count, cudaStream_t st) {
   if (a.M < 1 || a.N < 1 || a.K < 1 || !a.A || !a.B || !a.C) { set_error("gemm: bad arguments"); return BESO_E_INVALID; }
   KArgs ka{};
   ka.g = a;
-  const int bn = a.N > 128 ? 256 : 128;
+  if (a.prec < 0 || a.prec > 2) { set_error("gemm: prec must be 0, 1 or 2"); return BESO_E_INVALID; }
+  // three images per operand fill shared memory twice as fast: 128-wide tiles keep two pipeline stages
+  const int bn = (a.N > 128 && a.prec < 2) ? 256 : 128;
   ka.mt = (a.M + kBM - 1) / kBM;
   ka.nt = (a.N + bn - 1) / bn;
   ka.kb_total = (a.K + kBK - 1) / kBK;
@@ -413,8 +425,8 @@ int gemm_run(const GemmArgs& a, GemmWs& ws, int sm_count, cudaStream_t st) {
   }
   const int grid = ka.n_tiles < sm_count ? ka.n_tiles : sm_count;
   int rc;
-  if (bn == 256) rc = a.prec ? launch<256, true>(ka, grid, st) : launch<256, false>(ka, grid, st);
-  else rc = a.prec ? launch<128, true>(ka, grid, st) : launch<128, false>(ka, grid, st);
+  if (bn == 256) rc = a.prec ? launch<256, 2>(ka, grid, st) : launch<256, 1>(ka, grid, st);
+  else rc = a.prec == 2 ? launch<128, 3>(ka, grid, st) : (a.prec ? launch<128, 2>(ka, grid, st) : launch<128, 1>(ka, grid, st));
   if (rc) return rc;
   if (ksplit > 1) {
     const size_t total = (size_t)a.M * a.N;

@@ -9,8 +9,9 @@ namespace beso {
 // C[M][N] = (A . B^T + bias) .* mul + resid (+ C), all fp32 row-major in global memory:
 //   A element (m, k):  a_kmajor ? A[m * lda + k] : A[k * lda + m]
 //   B element (n, k):  b_kmajor ? B[n * ldb + k] : B[k * ldb + n]
-// prec = 1: both operands are split into bf16 hi + lo images inside the kernel and every product is three MMAs
-// (hi.hi + lo.hi + hi.lo, 16 mantissa bits per operand: the fp32-parity mode); prec = 0: one bf16 MMA.
+// prec = 2: both operands are split into three bf16 images inside the kernel (24 mantissa bits) and every product is
+// six MMAs (all cross terms down to 2^-24: the fp32-parity mode); prec = 1: two images, three MMAs (16 bits);
+// prec = 0: one bf16 MMA.
 struct GemmArgs {
   const float* A; int lda; int a_kmajor;
   const float* B; int ldb; int b_kmajor;

@@ -229,19 +229,44 @@ class GCDenoiser(nn.Module):
             raise _lib.BesoLibraryError("model parameters must live on a CUDA device (call .to('cuda'))")
         dev = self._device_index(params[0])
         plan = self._ensure_plan(dev)
+        # Slot 1 holds weights handed over explicitly (pack_tensors: the EMA copy).  It is never re-packed behind
+        # the caller's back from the live parameters: a stale fingerprint there would silently replace the EMA
+        # weights by the raw ones.  Only an explicit refresh_weights(slot=1, force=True) packs the live values into it.
+        external = slot in self._packed and self._packed[slot][0] == "external"
         fp = self._fingerprint()
-        if force or self._packed.get(slot) != fp:
-            for p in params:
-                if p.dtype != torch.float32 or not p.is_contiguous():
-                    raise _lib.BesoLibraryError("parameters must be contiguous fp32")
-            ptrs = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib().beso_plan_pack_weights(plan, slot, ptrs, len(params), C.c_void_p(stream)),
-                       "beso_plan_pack_weights")
+        if force or (not external and self._packed.get(slot) != fp):
+            self._pack(plan, dev, slot, params)
             self._packed[slot] = fp
         _lib.check(_lib.lib().beso_plan_select_weights(plan, slot), "beso_plan_select_weights")
         self._slot = slot
         return plan
+
+    def _pack(self, plan, dev, slot, tensors):
+        for p in tensors:
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+                raise _lib.BesoLibraryError("weights must be contiguous fp32 CUDA tensors")
+        ptrs = (C.c_void_p * len(tensors))(*[p.data_ptr() for p in tensors])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().beso_plan_pack_weights(plan, slot, ptrs, len(tensors), C.c_void_p(stream)),
+                   "beso_plan_pack_weights")
+
+    def pack_tensors(self, slot: int, tensors, tag=None):
+        """Pack ``tensors`` (parameters() order and shapes; e.g. the EMA shadow copy) into weight slot ``slot`` straight
+        from where they live -- the live parameters are not touched -- and mark the slot as externally owned: it is
+        re-packed only by another ``pack_tensors`` call, never automatically.  ``tag`` is remembered for the caller's
+        staleness bookkeeping (``packed_tag``)."""
+        params = list(self.inner_model.parameters())
+        tensors = [t.detach() for t in tensors]
+        if len(tensors) != len(params) or any(t.numel() != p.numel() for t, p in zip(tensors, params)):
+            raise ValueError("pack_tensors: tensors must match parameters() in number and size")
+        dev = self._device_index(params[0])
+        plan = self._ensure_plan(dev)
+        self._pack(plan, dev, slot, tensors)
+        self._packed[slot] = ("external", tag)
+
+    def packed_tag(self, slot: int):
+        e = self._packed.get(slot)
+        return e[1] if e is not None and e[0] == "external" else None
 
     def select_weights(self, slot: int):
         """Switch between resident packed weight sets without re-packing."""

@@ -77,9 +77,11 @@ enum {
                                the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
 #define BESO_FLAG_TRAIN_FAST 16u /* beso_loss_fwd_bwd only: one bf16 tcgen05 MMA per product in the training GEMMs
                                   (the arithmetic of bf16 mixed-precision training).  Opt-in: by default every
-                                  operand is split into bf16 hi + lo images and every product is three MMAs
-                                  (hi.hi + lo.hi + hi.lo, fp32 accumulate) -- the fp32-parity mode the gradient
-                                  goldens pin (the reference multiplies in fp32). */
+                                  operand is split into three bf16 images (24 mantissa bits) and every product is
+                                  six MMAs (all cross terms down to 2^-24, fp32 accumulate) -- the fp32-parity mode
+                                  the gradient goldens pin (the reference multiplies in fp32). */
+#define BESO_FLAG_TRAIN_SPLIT2 32u /* beso_loss_fwd_bwd only: two bf16 images per operand, three MMAs per product
+                                  (16 mantissa bits: ~1e-5 of the gradient scale); opt-in middle ground */
 #define BESO_FLAG_TRAIN_TF32 BESO_FLAG_TRAIN_FAST /* round-1 name of the opt-in tensor-core training mode */
 
 /* Constructor arguments of DiffusionGPT (k_diffusion/score_gpts.py:121-139) and
@@ -217,7 +219,8 @@ int beso_loss_fwd_bwd_dropout(beso_plan* plan, const float* state_dev, const flo
 
 /* The training GEMM by itself (tests and tools): C[M][N] = A . B^T + bias, fp32 row-major device tensors.
  *   a_kmajor: A element (m, k) at A[m * lda + k], else at A[k * lda + m]; b_kmajor likewise for B (n, k).
- *   prec: 1 = split bf16 hi + lo, three MMAs per product (fp32-parity); 0 = one bf16 MMA.  bias may be NULL. */
+ *   prec: 2 = three bf16 images, six MMAs per product (fp32-parity); 1 = two images, three MMAs; 0 = one bf16 MMA.
+ *   bias may be NULL. */
 int beso_debug_gemm(beso_plan* plan, const float* A_dev, int lda, int a_kmajor, const float* B_dev, int ldb,
                     int b_kmajor, float* C_dev, int ldc, int M, int N, int K, const float* bias_dev, int accumulate,
                     int prec, void* stream);
