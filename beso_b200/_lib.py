@@ -19,7 +19,7 @@ MODE_PRECISE, MODE_FAST, MODE_SIMT = 0, 1, 2
 SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN, SAMPLER_EULER_ANCESTRAL, SAMPLER_DPMPP_2M, SAMPLER_TWO_STAGE, SAMPLER_LMS = 0, 1, 2, 3, 4, 5, 6
 FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_FAST = 1, 2, 4, 8, 16
 FLAG_TRAIN_TF32 = FLAG_TRAIN_FAST
-FLAG_TRAIN_SPLIT2 = 32
+FLAG_TRAIN_SPLIT3 = 32
 SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN, "euler_ancestral": SAMPLER_EULER_ANCESTRAL,
                "dpmpp_2m": SAMPLER_DPMPP_2M, "two_stage": SAMPLER_TWO_STAGE,
                "lms": SAMPLER_LMS}
@@ -28,7 +28,7 @@ MODE_IDS = {"precise": MODE_PRECISE, "fast": MODE_FAST, "simt": MODE_SIMT}
 EXPORTS = [
     "beso_last_error", "beso_abi_version", "beso_param_count", "beso_param_numel", "beso_param_total",
     "beso_plan_create", "beso_plan_destroy", "beso_plan_pack_weights", "beso_plan_select_weights", "beso_plan_set_params",
-    "beso_denoise_fwd", "beso_sample_loop", "beso_sample_loop_noise", "beso_denoise_fwd_host", "beso_sample_loop_host",
+    "beso_denoise_fwd", "beso_sample_loop", "beso_sample_loop_noise", "beso_sample_loop_scaled", "beso_denoise_fwd_host", "beso_sample_loop_host",
     "beso_loss_fwd_bwd", "beso_loss_fwd_bwd_dropout", "beso_debug_gemm", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
     "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
@@ -51,6 +51,12 @@ class ModelDesc(C.Structure):
     def from_config(cls, cfg) -> "ModelDesc":
         return cls(cfg.obs_dim, cfg.act_dim, cfg.window, cfg.goal_len, cfg.d, cfg.n_layers, cfg.n_heads,
                    int(cfg.linear_output), int(cfg.goal_conditioned), float(cfg.sigma_data))
+
+
+class IoScaling(C.Structure):
+    """beso_io_scaling of include/beso_b200.h."""
+    _fields_ = [("in_table", C.c_void_p), ("goal_keep", C.c_void_p), ("out_clip", C.c_void_p), ("out_table", C.c_void_p),
+                ("unscaled_out", C.c_void_p)]
 
 
 class DropoutMasks(C.Structure):
@@ -92,6 +98,7 @@ def _declare(lib):
     lib.beso_denoise_fwd.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_sample_loop.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_sample_loop_noise.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
+    lib.beso_sample_loop_scaled.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, vp, C.POINTER(IoScaling), i32, i32, u32, f32, vp]
     lib.beso_denoise_fwd_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_sample_loop_host.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp]

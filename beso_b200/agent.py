@@ -81,6 +81,31 @@ class BesoAgent:
             return state, goal, batch.get("goal_task_name")
         return state, goal
 
+    def _rollout_scaling(self, batch: dict):
+        """``RolloutScaling`` for this batch when its scaler calls can ride inside the sampling kernel:
+        a scaler with ``rollout_tables`` (beso_b200.scaler), fp32 statistics, states and goals with the model's
+        feature count (the 4-feature block-push goals and one-hot kitchen goals of scaler_class.py:88-93 keep the torch
+        path), batch not pre-scaled.  None otherwise."""
+        from .denoiser import RolloutScaling
+        if batch.get("scaled", False) or not hasattr(self.scaler, "rollout_tables"):
+            return None
+        obs = self._core().config.obs_dim
+        if batch["observation"].shape[-1] != obs or batch["goal_observation"].shape[-1] != obs:
+            return None
+        try:
+            in_table, out_table, clip = self.scaler.rollout_tables()
+        except TypeError:                                    # float64 statistics: the fp32 kernel cannot replay them
+            return None
+        if in_table is not None and in_table.shape[-1] != obs:
+            return None
+        goal_keep = None
+        if obs == 10:                                        # base_agent.py:119-120
+            goal_keep = torch.ones(obs, device=self.device, dtype=torch.float32)
+            goal_keep[self.GOAL_ZERO_DIMS] = 0
+        dev = torch.device(self.device)
+        mv = lambda t: None if t is None else t.to(dev).contiguous()   # noqa: E731
+        return RolloutScaling(mv(in_table), goal_keep, mv(clip), mv(out_table))
+
     # ---- beso_agent.py:106-117, 458-477: scaler hand-over and the checkpoint files ------------------
     def get_scaler(self, scaler):
         self.scaler = scaler
@@ -309,7 +334,15 @@ class BesoAgent:
     def predict(self, batch: dict, new_sampler_type=None, get_mean=None, new_sampling_steps=None,
                 extra_args=None, noise_scheduler=None) -> torch.Tensor:
         extra_args = {} if extra_args is None else extra_args
-        state, goal, _ = self.process_batch(batch, predict=True)
+        # scaler prologue / epilogue inside the sampling kernel when the scaler allows it; decided once per episode so
+        # that the observation context holds either raw or scaled states, never a mix
+        if len(self.obs_context) == 0:
+            self._fused_io = self._rollout_scaling(batch)
+        io = getattr(self, "_fused_io", None)
+        if io is not None:
+            state, goal = batch["observation"].to(self.device), batch["goal_observation"].to(self.device)   # raw
+        else:
+            state, goal, _ = self.process_batch(batch, predict=True)
         n_steps = new_sampling_steps if new_sampling_steps is not None else self.num_sampling_steps
         sampler_type = new_sampler_type if new_sampler_type is not None else self.sampler_type
         self.obs_context.append(state)
@@ -322,12 +355,25 @@ class BesoAgent:
         x = torch.randn((len(input_state), 1, self._core().config.act_dim), device=self.device) * self.sigma_max
         if len(self.action_context) > 0:                     # previously executed actions are re-denoised
             x = torch.cat([torch.cat(tuple(self.action_context), dim=1), x], dim=1)
-        x_0 = self.sample_loop(sigmas, x, input_state, goal, sampler_type, extra_args)
-        if x_0.dim() == 3 and x_0.size(1) > 1:
-            x_0 = x_0[:, -1, :]
-        x_0 = self.scaler.clip_action(x_0)
+        core = self._core()
+        if io is not None:
+            io.consumed, io.unscaled = False, None
+            core.io_scaling = io
+        try:
+            x_0 = self.sample_loop(sigmas, x, input_state, goal, sampler_type, extra_args)
+        finally:
+            core.__dict__.pop("io_scaling", None)
+        last = lambda v: v[:, -1, :] if (v.dim() == 3 and v.size(1) > 1) else v  # noqa: E731  (beso_agent.py:373-374)
+        if io is not None and io.consumed:                  # clipped in the kernel; unscaled copy written beside it
+            x_0, model_pred = last(x_0), last(io.unscaled)
+        elif io is not None:                                 # step-wise loop (callback / churn): finish in torch
+            x_0, model_pred = io.finish(last(x_0))
+        else:
+            if x_0.dim() == 3 and x_0.size(1) > 1:
+                x_0 = x_0[:, -1, :]
+            x_0 = self.scaler.clip_action(x_0)
+            model_pred = self.scaler.inverse_scale_output(x_0)
         self._use_ema_weights(False)
-        model_pred = self.scaler.inverse_scale_output(x_0)
         if model_pred.dim() == 2:
             x_0 = x_0.unsqueeze(1)
         self.action_context.append(x_0)

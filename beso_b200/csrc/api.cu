@@ -304,29 +304,49 @@ int beso_denoise_fwd(beso_plan* p, int mode, const float* state, const float* ac
   return run(p, mode, sa, state, goal, action, sigma, out, B, t, flags, lambda, (cudaStream_t)stream);
 }
 
-int beso_sample_loop_noise(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
-                           const float* state, const float* goal, float* x, const float* noise, int B, int t,
-                           uint32_t flags, float lambda, void* stream) {
+// Validation shared by every sample-loop entry point (device and host buffers): a sampler that would read noise it was
+// not given, or a mode / sampler combination a kernel cannot run, is an error code here, never a fault on the device.
+static int check_sampler(beso_plan* p, int mode, int sampler, const SampleArgs& sa, bool have_noise, uint32_t flags) {
+  if (flags & BESO_FLAG_INNER) { set_error("INNER is not meaningful for a sample loop"); return BESO_E_INVALID; }
+  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_TWO_STAGE) {
+    bool needs_noise = false;
+    for (int i = 0; i < sa.n_steps; ++i) needs_noise |= (sampler == BESO_SAMPLER_TWO_STAGE ? sa.su[i] != 0.f : sa.ca[i] > 0.f);
+    if (needs_noise && !have_noise) { set_error("this sampler needs the per-step noise (beso_sample_loop_noise)"); return BESO_E_INVALID; }
+  }
+  if (sampler == BESO_SAMPLER_LMS && mode == BESO_MODE_FAST && (flags & BESO_FLAG_CFG)) {
+    set_error("lms with classifier-free guidance is not available in fast mode (history buffers)"); return BESO_E_UNSUPPORTED;
+  }
+  (void)p;
+  return BESO_OK;
+}
+
+int beso_sample_loop_scaled(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
+                            const float* state, const float* goal, float* x, const float* noise, const beso_io_scaling* io,
+                            int B, int t, uint32_t flags, float lambda, void* stream) {
   int rc = check_call(p, mode, B, t, flags);
   if (rc) return rc;
   if (!state || !x || (!goal && p->desc.goal_conditioned && p->desc.goal_len > 0)) {
     set_error("null tensor pointer"); return BESO_E_INVALID;
   }
-  if (flags & BESO_FLAG_INNER) { set_error("INNER is not meaningful for a sample loop"); return BESO_E_INVALID; }
   SampleArgs sa;
   rc = make_sample_args(sampler, sigmas, n_sigmas, coef, &sa);
   if (rc) return rc;
-  if (sampler == BESO_SAMPLER_EULER_ANCESTRAL || sampler == BESO_SAMPLER_TWO_STAGE) {
-    bool needs_noise = false;
-    for (int i = 0; i < sa.n_steps; ++i) needs_noise |= (sampler == BESO_SAMPLER_TWO_STAGE ? sa.su[i] != 0.f : sa.ca[i] > 0.f);
-    if (needs_noise && !noise) { set_error("this sampler needs the per-step noise (beso_sample_loop_noise)"); return BESO_E_INVALID; }
-  }
-  if (sampler == BESO_SAMPLER_LMS && mode == BESO_MODE_FAST && (flags & BESO_FLAG_CFG)) {
-    set_error("lms with classifier-free guidance is not available in fast mode (history buffers)"); return BESO_E_UNSUPPORTED;
-  }
+  rc = check_sampler(p, mode, sampler, sa, noise != nullptr, flags);
+  if (rc) return rc;
   sa.noise = noise;
   sa.noise_stride = (long long)B * t * p->desc.act_dim;
+  if (io) {
+    if (io->out_table_dev && !io->unscaled_out_dev) { set_error("io scaling: out_table_dev needs unscaled_out_dev"); return BESO_E_INVALID; }
+    sa.in_tab = io->in_table_dev; sa.goal_keep = io->goal_keep_dev; sa.clip = io->out_clip_dev;
+    sa.out_tab = io->out_table_dev; sa.unscaled = io->unscaled_out_dev;
+  }
   return run(p, mode, sa, state, goal, x, nullptr, x, B, t, flags, lambda, (cudaStream_t)stream);
+}
+
+int beso_sample_loop_noise(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
+                           const float* state, const float* goal, float* x, const float* noise, int B, int t,
+                           uint32_t flags, float lambda, void* stream) {
+  return beso_sample_loop_scaled(p, mode, sampler, sigmas, n_sigmas, coef, state, goal, x, noise, nullptr, B, t, flags, lambda, stream);
 }
 
 int beso_sample_loop(beso_plan* p, int mode, int sampler, const float* sigmas, int n_sigmas, const float* coef,
@@ -394,6 +414,8 @@ int beso_sample_loop_host(beso_plan* p, int mode, int sampler, const float* sigm
   if (!state || !x) { set_error("null tensor pointer"); return BESO_E_INVALID; }
   SampleArgs sa;
   rc = make_sample_args(sampler, sigmas, n_sigmas, coef, &sa);
+  if (rc) return rc;
+  rc = check_sampler(p, mode, sampler, sa, false, flags);       // no noise argument here: noisy samplers are refused
   if (rc) return rc;
   return host_call(p, mode, sa, state, x, goal, nullptr, x, B, t, flags, lambda, (cudaStream_t)stream);
 }

@@ -60,7 +60,25 @@ struct SampleArgs {
   float su[kMaxSteps];   // noise scale (0 = no noise)
   const float* noise;    // ancestral samplers: (n_steps, B, t, act) standard-normal draws of the caller
   long long noise_stride;   // elements per step = B * t * act
+  // rollout I/O scaling fused into the loop's first read and last write (beso_io_scaling of the C ABI); all NULL = off
+  const float* in_tab;      // (4, obs): sub, div, mul, add -- scale_input of states and goals
+  const float* goal_keep;   // (obs): goal features multiplied after scaling (0 = zeroed goal dimension)
+  const double* clip;       // (2, act): lo, hi of clip_action
+  const float* out_tab;     // (4, act): inverse_scale_output as ((x - sub) / div) * mul + add
+  float* unscaled;          // (B, t, act): clip + inverse scale of the final x
 };
+
+// ((x - sub) / div) * mul + add with separately rounded fp32 steps: bit-identical to the reference scaler's
+// element-wise torch ops (networks/scaler/scaler_class.py:69-166); tab is (4, dim) row-major
+__device__ __forceinline__ float io_scale(float x, const float* __restrict__ tab, int dim, int f) {
+  const float q = __fdiv_rn(__fsub_rn(x, __ldg(tab + f)), __ldg(tab + dim + f));
+  return __fadd_rn(__fmul_rn(q, __ldg(tab + 2 * dim + f)), __ldg(tab + 3 * dim + f));
+}
+// torch.clamp(y, lo, hi) with float64 bounds (y_bounds_tensor * 1.1 is float64), result rounded to fp32
+__device__ __forceinline__ float io_clip(float y, const double* __restrict__ clip, int act, int a) {
+  const double lo = clip[a], hi = clip[act + a], v = (double)y;
+  return (float)(v < lo ? lo : (v > hi ? hi : v));
+}
 
 struct SimtLaunch {
   int B, t, S;           // S = sequences per CTA

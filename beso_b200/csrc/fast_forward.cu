@@ -920,6 +920,7 @@ __device__ __forceinline__ uint64_t mma_step(uint32_t a_off, uint32_t d_col, uin
 // Per-thread description of the embedding-input task it owns for the whole tile: one (row, atom).
 struct EmbedTask {
   const float* src;      // obs atom: state / goal vector of this row (nullptr = zeros)
+  bool is_goal;          // src is a goal vector (rollout scaling zeroes goal dimensions)
   int row, atom, vs, tok, xoff;   // xoff >= 0: action row, offset of its act values in the tile's x buffer
   int part;              // PREC: 0 = fp16 hi image of the row, 1 = lo image; -1 = bf16 (fp16-mode embedding GEMM)
   bool valid;
@@ -938,11 +939,12 @@ __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int 
   const int seq = tile * (cfg ? p.S / 2 : p.S) + ls;
   e.valid = e.vs < p.S && seq < p.B;
   e.src = nullptr;
+  e.is_goal = false;
   e.xoff = -1;
   if (e.valid) {
     const bool uncond = cfg ? ((e.vs & 1) != 0) : ((p.flags & BESO_FLAG_UNCOND) != 0);
     const int j = e.tok - 1 - p.G;
-    if (e.tok >= 1 && e.tok <= p.G) { if (!uncond) e.src = p.goal + ((size_t)seq * p.G + (e.tok - 1)) * p.obs; }
+    if (e.tok >= 1 && e.tok <= p.G) { e.is_goal = true; if (!uncond) e.src = p.goal + ((size_t)seq * p.G + (e.tok - 1)) * p.obs; }
     else if (j >= 0 && (j & 1) == 0) e.src = p.state + ((size_t)seq * p.t + (j >> 1)) * p.obs;
     else if (j >= 0) e.xoff = (ls * p.t + (j >> 1)) * p.act;
   }
@@ -952,7 +954,8 @@ __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int 
 // A <- embedding-GEMM input rows: [obs atom | misc atom] (see file header), atoms 2..3 untouched.
 // One (row, atom) per thread; all global loads of a row are issued before any is used.
 __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask e, int obs, int act, uint32_t flags,
-                                               float sigma_data, const float* xsrc, const float* sigv) {
+                                               float sigma_data, const float* xsrc, const float* sigv,
+                                               const float* in_tab, const float* goal_keep) {
   uint8_t* atom = c.sm + kSmA + e.atom * 16384;
   if (e.atom == 0) {
     float v[64];
@@ -970,6 +973,14 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
       } else {
 #pragma unroll
         for (int i = 0; i < 64; ++i) if (i < obs) v[i] = __ldg(e.src + i);
+      }
+      if (in_tab != nullptr) {                       // scale_input of the rollout path, fused (uniform branch)
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i < obs) v[i] = io_scale(v[i], in_tab, obs, i);
+      }
+      if (goal_keep != nullptr && e.is_goal) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i < obs) v[i] = __fmul_rn(v[i], __ldg(goal_keep + i));
       }
     }
     if (e.part >= 0) {
@@ -1049,13 +1060,18 @@ __device__ __noinline__ void tile_begin(const Compute c, const FastParams& p, in
   for (int i = c.ctid; i < n_x; i += kComputeThreads)
     xb.xcur[i] = (i < ns * p.t * p.act) ? p.xin[(size_t)seq0 * p.t * p.act + i] : 0.f;
 }
-__device__ __noinline__ void tile_end(const Compute c, const FastParams& p, int tile) {
+__device__ __noinline__ void tile_end(const Compute c, const FastParams& p, const SampleArgs& sa, int tile) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   const int nls = cfg ? p.S / 2 : p.S;
   const int seq0 = tile * nls, ns = max(0, min(nls, p.B - seq0));
   const XBufs xb = xbufs(c.sm);
   compute_sync();
-  for (int i = c.ctid; i < ns * p.t * p.act; i += kComputeThreads) p.out[(size_t)seq0 * p.t * p.act + i] = xb.xcur[i];
+  for (int i = c.ctid; i < ns * p.t * p.act; i += kComputeThreads) {
+    float v = xb.xcur[i];
+    if (sa.clip) v = io_clip(v, sa.clip, p.act, i % p.act);             // clip_action, fused
+    p.out[(size_t)seq0 * p.t * p.act + i] = v;
+    if (sa.unscaled) sa.unscaled[(size_t)seq0 * p.t * p.act + i] = sa.out_tab ? io_scale(v, sa.out_tab, p.act, i % p.act) : v;
+  }
 }
 
 // noise levels of this evaluation + the embedding-GEMM A operand
@@ -1074,7 +1090,7 @@ __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p,
   compute_sync();
   const EmbedTask etask = make_embed_task<PREC>(c, p, tile);
   stamp<DBG>(c);
-  build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv);
+  build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv, sa.in_tab, sa.goal_keep);
   stamp<DBG>(c);
 }
 
@@ -1591,7 +1607,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           else { second = 0; ++step; }
         }
       }
-      if (sa.n_steps) tile_end(c, p, tile);
+      if (sa.n_steps) tile_end(c, p, sa, tile);
     }
     cp_async_wait<0>();
   }

@@ -387,8 +387,16 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
   sm.sig = take(S);
   Ctx c{m, ns, t, T, ns * T};
 
-  for (int i = threadIdx.x; i < ns * t * m.obs; i += kThreads) sm.state[i] = state[(size_t)seq0 * t * m.obs + i];
-  for (int i = threadIdx.x; i < ns * m.G * m.obs; i += kThreads) sm.goal[i] = goal[(size_t)seq0 * m.G * m.obs + i];
+  for (int i = threadIdx.x; i < ns * t * m.obs; i += kThreads) {
+    const float v = state[(size_t)seq0 * t * m.obs + i];
+    sm.state[i] = sa.in_tab ? io_scale(v, sa.in_tab, m.obs, i % m.obs) : v;
+  }
+  for (int i = threadIdx.x; i < ns * m.G * m.obs; i += kThreads) {
+    float v = goal[(size_t)seq0 * m.G * m.obs + i];
+    if (sa.in_tab) v = io_scale(v, sa.in_tab, m.obs, i % m.obs);
+    if (sa.goal_keep) v = __fmul_rn(v, __ldg(sa.goal_keep + i % m.obs));
+    sm.goal[i] = v;
+  }
   const int n = ns * t * m.act;
   for (int i = threadIdx.x; i < n; i += kThreads) sm.xcur[i] = action[(size_t)seq0 * t * m.act + i];
   float* gout = out + (size_t)seq0 * t * m.act;
@@ -480,7 +488,12 @@ simt_denoise_kernel(const __grid_constant__ SimtModel m, const __grid_constant__
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += kThreads) gout[i] = sm.xcur[i];
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    float v = sm.xcur[i];
+    if (sa.clip) v = io_clip(v, sa.clip, m.act, i % m.act);
+    gout[i] = v;
+    if (sa.unscaled) sa.unscaled[(size_t)seq0 * t * m.act + i] = sa.out_tab ? io_scale(v, sa.out_tab, m.act, i % m.act) : v;
+  }
 }
 
 inline int round_ldb(int n) {   // smallest ld >= n with ld % 8 == 4: conflict-free float4 rows

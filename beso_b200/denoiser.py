@@ -343,6 +343,9 @@ class GCDenoiser(nn.Module):
         if self.inner_model.training and (self.inner_model.cond_mask_prob > 0 and not uncond):
             goal = self.inner_model.mask_cond(goal)              # score_gpts.py:298-299
         state, action, goal, sigma = map(self._prep, (state, action, goal, sigma))
+        io = self.__dict__.get("io_scaling")
+        if io is not None:                      # step-wise (Python loop) sampling under rollout scaling: raw inputs
+            state, goal = io.scale_inputs(state, goal)
         B, t = self._check_shapes(state, action, goal)
         if sigma.dim() == 0:
             sigma = sigma.expand(B).contiguous()
@@ -370,8 +373,10 @@ class GCDenoiser(nn.Module):
     def sample(self, sampler: str, sigmas: torch.Tensor, state, x_t, goal, cfg_lambda: Optional[float] = None,
                uncond: bool = False, coef: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The whole DDIM / Euler / Heun / Euler-ancestral loop as one persistent kernel launch
-        (beso_sample_loop_noise).  ``noise``: (n_steps, B, t, act) standard-normal draws for the ancestral
-        sampler."""
+        (beso_sample_loop_scaled).  ``noise``: (n_steps, B, t, act) standard-normal draws for the ancestral
+        sampler.  With ``self.io_scaling`` set (``RolloutScaling``; the agent does for predict / evaluate) ``state`` and
+        ``goal`` are RAW observations: the kernel scales them on its first read, clips the final actions and writes
+        their inverse-scaled copy to ``io_scaling.unscaled``."""
         dev = self._device_index(x_t)
         state, x_t, goal = map(self._prep, (state, x_t, goal))
         B, t = self._check_shapes(state, x_t, goal)
@@ -391,12 +396,63 @@ class GCDenoiser(nn.Module):
             if tuple(noise.shape) != (len(sig) - 1,) + tuple(x.shape) or noise.device != x.device:
                 raise ValueError(f"noise must be {(len(sig) - 1,) + tuple(x.shape)} on {x.device}")
             noise_ptr = noise.data_ptr()
+        io = self.__dict__.get("io_scaling")
+        io_struct = None
+        if io is not None:
+            io.unscaled = torch.empty_like(x)
+            io_struct = io.struct(io.unscaled)
+            io.consumed = True
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.lib().beso_sample_loop_noise(plan, self.resolved_mode(), _lib.SAMPLER_IDS[sampler], sig_arr,
-                                                    len(sig), coef_arr, state.data_ptr(), goal.data_ptr(),
-                                                    x.data_ptr(), noise_ptr, B, t, flags, lam, C.c_void_p(stream)),
-                   "beso_sample_loop_noise")
+        _lib.check(_lib.lib().beso_sample_loop_scaled(plan, self.resolved_mode(), _lib.SAMPLER_IDS[sampler], sig_arr,
+                                                     len(sig), coef_arr, state.data_ptr(), goal.data_ptr(),
+                                                     x.data_ptr(), noise_ptr,
+                                                     C.byref(io_struct) if io_struct is not None else None, B, t, flags,
+                                                     lam, C.c_void_p(stream)),
+                   "beso_sample_loop_scaled")
         return x
+
+
+class RolloutScaling:
+    """The scaler calls around ``sample_loop`` in ``BesoAgent.predict`` / ``evaluate`` (beso_agent.py:322-329,373-387,
+    base_agent.py:111-142) as tables for the sampling kernel (``beso_io_scaling``): ``scale_input`` of states and goals,
+    the zeroed block-push goal dimensions, ``clip_action`` and ``inverse_scale_output``.
+
+    ``in_table`` / ``out_table``: (4, dim) fp32 device tensors with rows (sub, div, mul, add); ``goal_keep``: (obs,) fp32;
+    ``clip``: (2, act) float64.  After a fused loop ``consumed`` is True and ``unscaled`` holds the clipped,
+    inverse-scaled actions; a step-wise (Python) loop leaves ``consumed`` False and the caller applies clip / inverse
+    scaling itself (``scale_inputs`` is applied by the model's forward in that case)."""
+
+    def __init__(self, in_table=None, goal_keep=None, clip=None, out_table=None):
+        self.in_table, self.goal_keep, self.clip, self.out_table = in_table, goal_keep, clip, out_table
+        self.unscaled = None
+        self.consumed = False
+
+    def struct(self, unscaled):
+        s = _lib.IoScaling()
+        s.in_table = self.in_table.data_ptr() if self.in_table is not None else None
+        s.goal_keep = self.goal_keep.data_ptr() if self.goal_keep is not None else None
+        s.out_clip = self.clip.data_ptr() if self.clip is not None else None
+        s.out_table = self.out_table.data_ptr() if self.out_table is not None else None
+        s.unscaled_out = unscaled.data_ptr()
+        return s
+
+    @staticmethod
+    def _apply(x, tab):
+        return ((x - tab[0]) / tab[1]) * tab[2] + tab[3]
+
+    def scale_inputs(self, state, goal):
+        if self.in_table is not None:
+            state, goal = self._apply(state, self.in_table), self._apply(goal, self.in_table)
+        if self.goal_keep is not None:
+            goal = goal * self.goal_keep
+        return state, goal
+
+    def finish(self, x):
+        """clip + inverse scaling in torch, for the step-wise path."""
+        if self.clip is not None:
+            x = torch.clamp(x, self.clip[0], self.clip[1]).to(torch.float32)
+        y = self._apply(x, self.out_table) if self.out_table is not None else x
+        return x, y
 
 
 def build_denoiser(cfg: ModelConfig, device="cuda", mode: str = "auto", state_dict=None,

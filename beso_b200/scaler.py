@@ -101,6 +101,22 @@ class _ScalerBase:
         return self._gather_tables
 
 
+    def _inverse_output_rows(self):
+        raise NotImplementedError
+
+    def rollout_tables(self):
+        """(in_table, out_table, clip) for the sampling kernel's fused rollout scaling (``beso_io_scaling``):
+        ``scale_input`` and ``inverse_scale_output`` as (4, dim) fp32 tables with rows (sub, div, mul, add) -- None when
+        ``scale_data`` is off -- and the float64 (2, act) bounds of ``clip_action``."""
+        clip = torch.stack([self.y_bounds_tensor[0, :] * 1.1, self.y_bounds_tensor[1, :] * 1.1]).to(torch.float64).contiguous()
+        if not self.scale_data:
+            return None, None, clip
+        in_table, _ = self.gather_tables()
+        if getattr(self, "_inverse_table", None) is None:
+            self._inverse_table = torch.stack(self._inverse_output_rows()).to(torch.float32).contiguous()
+        return in_table, self._inverse_table, clip
+
+
 class Scaler(_ScalerBase):
     """Standardises inputs and outputs with the data's mean and standard deviation (scaler_class.py:10-182)."""
 
@@ -132,6 +148,10 @@ class Scaler(_ScalerBase):
         one, zero = torch.ones_like, torch.zeros_like
         return ([self.x_mean, self._x_den(), one(self.x_mean), zero(self.x_mean)],
                 [self.y_mean, self._y_den(), one(self.y_mean), zero(self.y_mean)])
+
+    def _inverse_output_rows(self):          # y * den + mean
+        one, zero = torch.ones_like, torch.zeros_like
+        return [zero(self.y_mean), one(self.y_mean), self._y_den(), self.y_mean]
 
 
 class MinMaxScaler(_ScalerBase):
@@ -169,3 +189,6 @@ class MinMaxScaler(_ScalerBase):
         one, zero = torch.ones_like, torch.zeros_like
         return ([self.x_mean, self._x_den(), one(self.x_mean), zero(self.x_mean)],
                 [self.y_min, self.y_max - self.y_min, self.new_max_y - self.new_min_y, self.new_min_y])
+
+    def _inverse_output_rows(self):          # (y - new_min) / (new_max - new_min) * (y_max - y_min) + y_min
+        return [self.new_min_y, self.new_max_y - self.new_min_y, self.y_max - self.y_min, self.y_min]

@@ -77,11 +77,14 @@ enum {
                                the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
 #define BESO_FLAG_TRAIN_FAST 16u /* beso_loss_fwd_bwd only: one bf16 tcgen05 MMA per product in the training GEMMs
                                   (the arithmetic of bf16 mixed-precision training).  Opt-in: by default every
-                                  operand is split into three bf16 images (24 mantissa bits) and every product is
-                                  six MMAs (all cross terms down to 2^-24, fp32 accumulate) -- the fp32-parity mode
-                                  the gradient goldens pin (the reference multiplies in fp32). */
-#define BESO_FLAG_TRAIN_SPLIT2 32u /* beso_loss_fwd_bwd only: two bf16 images per operand, three MMAs per product
-                                  (16 mantissa bits: ~1e-5 of the gradient scale); opt-in middle ground */
+                                  operand is split into two bf16 images (hi + lo, 16 mantissa bits) and every product
+                                  is three MMAs (hi.hi + lo.hi + hi.lo, fp32 accumulate in TMEM) -- the fp32-parity
+                                  mode the gradient goldens pin (the reference multiplies in fp32).  Measured: results
+                                  within ~5e-6 of the output scale of an fp64 product. */
+#define BESO_FLAG_TRAIN_SPLIT3 32u /* beso_loss_fwd_bwd only: three bf16 images per operand (24 mantissa bits), six MMAs
+                                  per product; measured ~2.5e-6 of the output scale -- what is left is the tensor
+                                  core's own fp32 accumulation, so this buys little over the default for twice the
+                                  tensor time; opt-in */
 #define BESO_FLAG_TRAIN_TF32 BESO_FLAG_TRAIN_FAST /* round-1 name of the opt-in tensor-core training mode */
 
 /* Constructor arguments of DiffusionGPT (k_diffusion/score_gpts.py:121-139) and
@@ -186,6 +189,30 @@ int beso_sample_loop_host(beso_plan* plan, int mode, int sampler, const float* s
                           const float* coef_host, const float* state_host, const float* goal_host,
                           float* x_inout_host, int B, int t, uint32_t flags, float cond_lambda,
                           void* stream);
+
+/* The rollout path's scaler calls fused into the sample loop.  Replaces, around
+ * BesoAgent.sample_loop in predict() / evaluate() (beso_agent.py:322-329,373-387; base_agent.py:111-142):
+ * scaler.scale_input(state / goal) and the zeroed block-push goal dimensions (base_agent.py:119-120) on the loop's
+ * first read, scaler.clip_action and scaler.inverse_scale_output (networks/scaler/scaler_class.py:69-166) on its last
+ * write.  Tables are (4, dim) row-major fp32 with rows (sub, div, mul, add): y = ((x - sub) / div) * mul + add in
+ * separately rounded fp32 steps (bit-identical to the scaler's element-wise ops).  Any member may be NULL = skipped.
+ *   in_table_dev    (4, obs_dim)  applied to every state and goal feature
+ *   goal_keep_dev   (obs_dim)     goal features are multiplied by it after scaling (0 = zeroed dimension)
+ *   out_clip_dev    (2, act_dim)  float64 lo, hi: x_inout is clamped to [lo, hi] before it is written back
+ *   out_table_dev   (4, act_dim)  inverse output scaling, written to unscaled_out_dev
+ *   unscaled_out_dev (B, t, act)  clip + inverse scaling of the final x (x_inout itself stays in scaled units: the
+ *                                 agent feeds it back as action context) */
+typedef struct beso_io_scaling {
+  const float* in_table_dev;
+  const float* goal_keep_dev;
+  const double* out_clip_dev;
+  const float* out_table_dev;
+  float* unscaled_out_dev;
+} beso_io_scaling;
+int beso_sample_loop_scaled(beso_plan* plan, int mode, int sampler, const float* sigmas_host, int n_sigmas,
+                            const float* coef_host, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                            const float* noise_dev, const beso_io_scaling* io, int B, int t, uint32_t flags,
+                            float cond_lambda, void* stream);
 
 /* Replaces: GCDenoiser.loss (score_wrappers.py:45-79) + loss.backward() (beso_agent.py:236-240).
  *   action = clean action a; noise n; sigma (B).  goal_keep_dev: optional (B,G,obs) {0,1} mask =

@@ -404,3 +404,43 @@ def test_cfg5_heun_cfg_batch2048_properties(mode, cuda_device):
     with torch.no_grad():
         want = O.sample_heun(sd, to_oracle_cfg(cfg), x["state"][:3], x["noise"][:3], x["goal"][:3], sig, cond_lambda=2.0)
     torch.testing.assert_close(full[:3].cpu(), want, **TOL[mode])
+
+
+@pytest.mark.parametrize("kind", ["standard", "minmax"])
+@pytest.mark.parametrize("mode", ["precise", "fast", "simt"])
+def test_rollout_scaling_fused_into_the_sampling_kernel(kind, mode, cuda_device):
+    """predict(): scale_input of state / goal, the zeroed block-push goal dimensions, clip_action and
+    inverse_scale_output run inside the sampling kernel (beso_sample_loop_scaled) and must give exactly what the torch
+    ops around the kernel give (beso_agent.py:322-329,373-387; scaler_class.py:69-166)."""
+    import numpy as np
+    from beso_b200.config import ModelConfig
+    from beso_b200.scaler import MinMaxScaler, Scaler
+    cfg = ModelConfig(obs_dim=10, act_dim=2, window=5, goal_len=1, d=240, n_layers=2, n_heads=12)   # block-push shape: 10-d goals
+    rs = np.random.RandomState(3)
+    xs = (rs.randn(400, 10) * 3 + 1).astype(np.float32)
+    ys = (rs.randn(400, 2) * 0.5).astype(np.float32)
+    cls = Scaler if kind == "standard" else MinMaxScaler
+    sd = synthetic_state_dict(cfg, 91)
+    acts = []
+    for fused in (True, False):
+        scaler = cls(xs, ys, True, cuda_device)
+        m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+        agent = BesoAgent(m, device=cuda_device, window_size=cfg.window, num_sampling_steps=3, scaler=scaler)
+        if not fused:
+            agent._rollout_scaling = lambda batch: None
+        torch.manual_seed(17)
+        gen = torch.Generator().manual_seed(18)
+        out = []
+        for step in range(cfg.window + 2):
+            obs = torch.randn(1, cfg.obs_dim, generator=gen) * 4
+            goal = torch.randn(cfg.goal_len, cfg.obs_dim, generator=gen) * 4
+            out.append(agent.predict({"observation": obs, "goal_observation": goal}, extra_args={}))
+        if fused:
+            assert agent._fused_io is not None
+        acts.append(out)
+    for a, b in zip(*acts):
+        assert a.shape == b.shape and torch.equal(a, b)
+    # the clamp is live: actions far outside the data bounds come back clipped
+    lo, hi = scaler.y_bounds_tensor[0] * 1.1, scaler.y_bounds_tensor[1] * 1.1
+    assert all(bool(((scaler.scale_output(a.reshape(-1, cfg.act_dim)).double() >= lo - 1e-4) &
+                     (scaler.scale_output(a.reshape(-1, cfg.act_dim)).double() <= hi + 1e-4)).all()) for a in acts[0])
