@@ -29,7 +29,7 @@ EXPORTS = [
     "beso_last_error", "beso_abi_version", "beso_param_count", "beso_param_numel", "beso_param_total",
     "beso_plan_create", "beso_plan_destroy", "beso_plan_pack_weights", "beso_plan_select_weights", "beso_plan_set_params",
     "beso_denoise_fwd", "beso_sample_loop", "beso_sample_loop_noise", "beso_sample_loop_scaled", "beso_denoise_fwd_host", "beso_sample_loop_host",
-    "beso_loss_fwd_bwd", "beso_loss_fwd_bwd_dropout", "beso_debug_gemm", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
+    "beso_loss_fwd_bwd", "beso_loss_fwd_bwd_dropout", "beso_loss_fwd_bwd_dp", "beso_debug_gemm", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
     "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
     "beso_opt_create", "beso_opt_destroy", "beso_opt_total", "beso_opt_step", "beso_window_gather",
@@ -103,6 +103,7 @@ def _declare(lib):
     lib.beso_sample_loop_host.argtypes = [vp, i32, i32, fp, i32, fp, vp, vp, vp, i32, i32, u32, f32, vp]
     lib.beso_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp]
     lib.beso_loss_fwd_bwd_dropout.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DropoutMasks), vp, vp, i32, u32, vp]
+    lib.beso_loss_fwd_bwd_dp.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DropoutMasks), vp, f32, vp, vp, i32, u32, vp]
     lib.beso_debug_gemm.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.beso_comm_unique_id.argtypes = [C.c_char_p]
     lib.beso_comm_init.argtypes = [i32, i32, C.c_char_p, i32, C.POINTER(vp)]

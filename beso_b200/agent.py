@@ -294,9 +294,15 @@ class BesoAgent:
             goal_keep = (1.0 - mask).contiguous()
         if self.pred_last_action_only:
             noise[:, :-1, :] = 0
-        loss, flat = loss_and_flat_grad(core, state, action, goal, noise, sigma, self.pred_last_action_only, goal_keep)
-        if getattr(self, "grad_sync", None) is not None:    # data parallel: mean of the ranks' gradients
-            self.grad_sync(flat)
+        from .training import draw_dropout_masks
+        drop = draw_dropout_masks(inner, action.shape[0], action.shape[1], action.device)   # nn.Dropout draws, in op order
+        # data parallel: the mean of the ranks' gradients, all-reduced per block from inside the backward pass
+        gs = getattr(self, "grad_sync", None)
+        overlapped = gs is not None and getattr(gs, "comm_handle", lambda: None)() is not None
+        loss, flat = loss_and_flat_grad(core, state, action, goal, noise, sigma, self.pred_last_action_only, goal_keep,
+                                        dropout_masks=drop, grad_sync=gs if overlapped else None)
+        if gs is not None and not overlapped:               # torch.distributed transport: one all-reduce after the call
+            gs(flat)
         self.optimizer.step(flat_grad=flat)                 # zero_grad / backward / step of the reference in one
         self.lr_scheduler.step()
         self.steps += 1

@@ -446,13 +446,20 @@ int beso_debug_gemm(beso_plan* p, const float* A, int lda, int a_kmajor, const f
 int beso_loss_fwd_bwd_dropout(beso_plan* p, const float* state, const float* action, const float* goal, const float* noise,
                               const float* sigma, const float* goal_keep, const beso_dropout_masks* masks, float* loss_dev,
                               float* flat_grad_dev, int B, uint32_t flags, void* stream) {
+  return beso_loss_fwd_bwd_dp(p, state, action, goal, noise, sigma, goal_keep, masks, nullptr, 1.0f, loss_dev, flat_grad_dev, B,
+                              flags, stream);
+}
+
+int beso_loss_fwd_bwd_dp(beso_plan* p, const float* state, const float* action, const float* goal, const float* noise,
+                         const float* sigma, const float* goal_keep, const beso_dropout_masks* masks, beso_comm* comm,
+                         float grad_scale, float* loss_dev, float* flat_grad_dev, int B, uint32_t flags, void* stream) {
   if (!p || !state || !action || !noise || !sigma || !loss_dev || B < 1) { set_error("null argument or B < 1"); return BESO_E_INVALID; }
   if (!goal && p->desc.goal_conditioned && p->desc.goal_len > 0) { set_error("null goal"); return BESO_E_INVALID; }
   const WeightSlot& ws = p->slot[p->active];
   if (ws.params.empty()) { set_error("no parameters registered (beso_plan_set_params / beso_plan_pack_weights)"); return BESO_E_NOT_PACKED; }
   BESO_CUDA(cudaSetDevice(p->device));
   return train_loss_fwd_bwd(p->train_ws, p->desc, ws.params.data(), state, action, goal, noise, sigma, goal_keep, masks,
-                            loss_dev, flat_grad_dev, B, flags, (cudaStream_t)stream);
+                            loss_dev, flat_grad_dev, B, flags, (cudaStream_t)stream, comm, grad_scale);
 }
 
 int64_t beso_kernel_launches(void) { return g_kernel_launches; }

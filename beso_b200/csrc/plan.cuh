@@ -12,7 +12,7 @@ void train_ws_free(TrainWs* ws);
 int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* const* prm, const float* state,
                        const float* action, const float* goal, const float* noise, const float* sigma,
                        const float* goal_keep, const beso_dropout_masks* drop, float* loss_out, float* grad, int B,
-                       uint32_t flags, cudaStream_t st);
+                       uint32_t flags, cudaStream_t st, beso_comm* comm = nullptr, float grad_scale = 1.0f);
 struct GemmArgs;
 int train_gemm(TrainWs*& ws, const GemmArgs& a, cudaStream_t st);   // the training GEMM by itself (tests, tools)
 

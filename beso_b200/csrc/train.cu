@@ -523,6 +523,56 @@ constexpr size_t kPartialFloats = (size_t)148 * 2048;
 
 }  // namespace
 
+}  // namespace beso
+
+// ================================ NCCL communicator (data-parallel gradient exchange) ============================
+struct beso_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  cudaStream_t stream = nullptr;        // the exchange runs here, behind the backward kernels of the compute stream
+  std::vector<cudaEvent_t> events;      // one per gradient bucket + the join event
+  int next_event = 0;
+};
+
+namespace beso {
+namespace {
+__global__ void scale_kernel(float* x, size_t n, float s) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
+}
+int nccl_fail(ncclResult_t r, const char* what) {
+  set_error(std::string("NCCL error: ") + ncclGetErrorString(r) + " at " + what);
+  return BESO_E_NCCL;
+}
+}  // namespace
+#define BESO_NCCL(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) return nccl_fail(_r, #expr); } while (0)
+
+// One gradient bucket [off, off + n) of the flat buffer is final on the compute stream `st`: all-reduce(sum) it on the
+// communicator's stream (then * scale), behind an event, while `st` goes on with the next layer's backward.
+static int sync_bucket(beso_comm* c, float* grad, size_t off, size_t n, float scale, cudaStream_t st) {
+  if (!c || c->world <= 1 || n == 0) return BESO_OK;
+  if (c->next_event >= (int)c->events.size()) { set_error("internal: out of gradient-bucket events"); return BESO_E_INVALID; }
+  cudaEvent_t ev = c->events[c->next_event++];
+  BESO_CUDA(cudaEventRecord(ev, st));
+  BESO_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+  BESO_NCCL(ncclAllReduce(grad + off, grad + off, n, ncclFloat, ncclSum, c->comm, c->stream));
+  if (scale != 1.0f) {
+    const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    scale_kernel<<<grid, 256, 0, c->stream>>>(grad + off, n, scale);
+    ++g_kernel_launches;
+    BESO_CUDA(cudaGetLastError());
+  }
+  return BESO_OK;
+}
+// the compute stream waits for every bucket issued since the last join
+static int join_buckets(beso_comm* c, cudaStream_t st) {
+  if (!c || c->world <= 1) return BESO_OK;
+  cudaEvent_t ev = c->events.back();
+  BESO_CUDA(cudaEventRecord(ev, c->stream));
+  BESO_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  c->next_event = 0;
+  return BESO_OK;
+}
+
 // ================================ training workspace =======================================================
 struct TrainWs {
   float* buf = nullptr;
@@ -562,7 +612,7 @@ int train_gemm(TrainWs*& ws, const GemmArgs& a, cudaStream_t st) {
 int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* const* prm, const float* state,
                        const float* action, const float* goal, const float* noise, const float* sigma,
                        const float* goal_keep, const beso_dropout_masks* drop, float* loss_out, float* grad, int B,
-                       uint32_t flags, cudaStream_t st) {
+                       uint32_t flags, cudaStream_t st, beso_comm* comm, float grad_scale) {
   if (!m.linear_output) { set_error("training path supports linear_output models only"); return BESO_E_UNSUPPORTED; }
   Dims D;
   D.B = B; D.t = m.window; D.G = m.goal_conditioned ? m.goal_len : 0; D.T = 1 + D.G + 2 * D.t; D.obs = m.obs_dim;
@@ -726,6 +776,8 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     GEMM(false, false, M, d, d, dQKV + d, 3 * d, W(lp(l, 4)), d, dH, d, acc1);
     GEMM(false, false, M, d, d, dQKV + 2 * d, 3 * d, W(lp(l, 8)), d, dH, d, acc1);
     LNBWD(dH, a.Xin, a.st1, W(lp(l, 0)), 1, Gp(lp(l, 0)), Gp(lp(l, 1)));                           // dX = d/dX_in
+    // data parallel: this block's 16 gradient tensors are final -- their all-reduce overlaps the blocks below
+    if ((rc = sync_bucket(comm, grad, goff[lp(l, 0)], goff[lp(l + 1, 0)] - goff[lp(l, 0)], grad_scale, st))) return rc;
   }
   // ---- embeddings ----
   if (m_embed) LAUNCH(mul_kernel, blocks_for(Md / 4), kTB, 0, dX, dX, m_embed, Md / 4);           // X_0 = drop(embeddings)
@@ -745,6 +797,11 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
     COLSUM(dRows, (int)rows, d, d, Gp(k.pb));
   }
   BESO_CUDA(cudaGetLastError());
+  if (comm && comm->world > 1) {        // embeddings (first 3 tensors) and the tail (ln_f, sigma / action embeddings, head)
+    if ((rc = sync_bucket(comm, grad, 0, goff[3], grad_scale, st))) return rc;
+    if ((rc = sync_bucket(comm, grad, goff[pt], acc_off - goff[pt], grad_scale, st))) return rc;
+    if ((rc = join_buckets(comm, st))) return rc;
+  }
 #undef LAUNCH
 #undef GEMM
 #undef COLSUM
@@ -754,19 +811,9 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
 
 }  // namespace beso
 
-// ================================ NCCL gradient exchange ======================================================
-struct beso_comm { ncclComm_t comm = nullptr; int rank = 0, world = 1, device = 0; };
-
-namespace {
-__global__ void scale_kernel(float* x, size_t n, float s) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
-}
-int nccl_fail(ncclResult_t r, const char* what) {
-  beso::set_error(std::string("NCCL error: ") + ncclGetErrorString(r) + " at " + what);
-  return BESO_E_NCCL;
-}
-}  // namespace
-#define BESO_NCCL(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) return nccl_fail(_r, #expr); } while (0)
+// ================================ NCCL gradient exchange: C ABI ================================================
+using beso::nccl_fail;
+using beso::scale_kernel;
 
 extern "C" {
 
@@ -788,6 +835,9 @@ int beso_comm_init(int rank, int world, const char* unique_id128, int device, be
   c->rank = rank; c->world = world; c->device = device;
   ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
   if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
+  BESO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->events.resize(beso::kMaxLayers + 4);
+  for (auto& e : c->events) BESO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = c;
   return BESO_OK;
 }
@@ -795,6 +845,8 @@ int beso_comm_init(int rank, int world, const char* unique_id128, int device, be
 int beso_comm_destroy(beso_comm* c) {
   if (!c) return BESO_OK;
   if (c->comm) ncclCommDestroy(c->comm);
+  for (auto& e : c->events) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return BESO_OK;
 }

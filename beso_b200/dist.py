@@ -46,6 +46,11 @@ class FlatGradAllReduce:
             _lib.check(_lib.lib().beso_comm_init(self.rank, self.world, obj[0], device, C.byref(handle)), "beso_comm_init")
             self._comm = handle
 
+    def comm_handle(self):
+        """The NCCL communicator of the C ABI when this exchange can run inside ``beso_loss_fwd_bwd_dp`` (overlapped
+        with the backward pass), else None."""
+        return self._comm if (self.transport == "nccl" and self.world > 1) else None
+
     def __call__(self, flat: torch.Tensor) -> torch.Tensor:
         """In place: flat <- sum over ranks(flat) / world."""
         if self.world == 1:

@@ -94,13 +94,16 @@ def _masks_struct(masks, n_layers, device):
 
 
 def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_action_only=False, goal_keep=None,
-                       need_grad=True, dropout_masks=None):
+                       need_grad=True, dropout_masks=None, grad_sync=None):
     """Runs ``beso_loss_fwd_bwd_dropout``; returns (loss 0-d tensor, flat gradient or None).
 
     ``model.train_math``: "fp32" (default: bf16 hi + lo images of every operand, three MMAs per product, the
     fp32-parity mode), "bf16x3" (three images, six MMAs) or "bf16" (one MMA per product; "tf32" is accepted as the
     round-1 name of the opt-in fast mode).
-    ``dropout_masks``: see ``draw_dropout_masks`` (None = no dropout)."""
+    ``dropout_masks``: see ``draw_dropout_masks`` (None = no dropout).
+    ``grad_sync``: a ``beso_b200.dist.FlatGradAllReduce``; with the NCCL transport the gradient all-reduce is issued per
+    transformer block from inside the backward pass on the communicator's stream (``beso_loss_fwd_bwd_dp``) and the
+    returned flat gradient is already the mean over the ranks; other transports reduce it after the call."""
     params = _param_list(model)
     dev = model._device_index(action)
     state, action, goal, noise, sigma = map(model._prep, (state, action, goal, noise, sigma))
@@ -124,13 +127,17 @@ def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_actio
         flags |= _lib.FLAG_TRAIN_FAST
     mstruct, keep = _masks_struct(dropout_masks, cfg.n_layers, action.device)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(_lib.lib().beso_loss_fwd_bwd_dropout(plan, state.data_ptr(), action.data_ptr(), goal.data_ptr(),
-                                                   noise.data_ptr(), sigma.data_ptr(), keep_ptr,
-                                                   C.byref(mstruct) if mstruct is not None else None, loss.data_ptr(),
-                                                   flat.data_ptr() if flat is not None else None, B, flags,
-                                                   C.c_void_p(stream)),
-               "beso_loss_fwd_bwd_dropout")
+    comm = grad_sync.comm_handle() if (grad_sync is not None and flat is not None) else None
+    _lib.check(_lib.lib().beso_loss_fwd_bwd_dp(plan, state.data_ptr(), action.data_ptr(), goal.data_ptr(),
+                                              noise.data_ptr(), sigma.data_ptr(), keep_ptr,
+                                              C.byref(mstruct) if mstruct is not None else None, comm,
+                                              1.0 / grad_sync.world if comm is not None else 1.0, loss.data_ptr(),
+                                              flat.data_ptr() if flat is not None else None, B, flags,
+                                              C.c_void_p(stream)),
+               "beso_loss_fwd_bwd_dp")
     del keep
+    if grad_sync is not None and comm is None and flat is not None:
+        grad_sync(flat)                                     # torch.distributed transport (or world 1): after the call
     return loss, flat
 
 

@@ -260,6 +260,17 @@ int beso_comm_init(int rank, int world, const char* unique_id128, int device, be
 int beso_comm_destroy(beso_comm* comm);
 int beso_allreduce_grads(beso_comm* comm, float* flat_grad_dev, size_t n, float scale, void* stream);
 
+/* beso_loss_fwd_bwd_dropout with the gradient exchange overlapped with the backward pass: as soon as a transformer
+ * block's 16 gradient tensors are final (blocks finish last-to-first) their slice of the flat buffer is all-reduced
+ * (sum, then * grad_scale: pass 1 / world) on the communicator's own stream behind an event, while `stream` goes on with
+ * the next block's backward; the embedding and tail tensors follow at the end.  On return `stream` is ordered after
+ * every bucket, so flat_grad_dev holds the global-batch mean gradient for whatever is launched on it next.
+ * comm == NULL or world 1: identical to beso_loss_fwd_bwd_dropout. */
+int beso_loss_fwd_bwd_dp(beso_plan* plan, const float* state_dev, const float* action_dev, const float* goal_dev,
+                         const float* noise_dev, const float* sigma_dev, const float* goal_keep_dev,
+                         const beso_dropout_masks* masks, beso_comm* comm, float grad_scale, float* loss_dev,
+                         float* flat_grad_dev, int B, uint32_t flags, void* stream);
+
 /* Fused optimiser step.  Replaces, in BesoAgent.train_step (beso_agent.py:238-247),
  * optimizer.step() of torch.optim.AdamW (configs/agents/beso_kitchen.yaml:9-12) and
  * ExponentialMovingAverage.update (beso/networks/ema_helper/ema.py:36-53): ONE launch over all parameter

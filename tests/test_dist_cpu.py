@@ -73,7 +73,7 @@ def _agent_worker(rank, world, port, out_dir):
     from beso_b200.agent import BesoAgent
     from beso_b200.denoiser import build_denoiser
     agent = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10)
-    T.loss_and_flat_grad = lambda *a: (torch.tensor(float(rank)), torch.arange(6.0) * (rank + 1))   # stub: no GPU here
+    T.loss_and_flat_grad = lambda *a, **k: (torch.tensor(float(rank)), torch.arange(6.0) * (rank + 1))   # stub: no GPU here
     got = {}
     agent.optimizer = type("O", (), {"step": lambda self, flat_grad=None: got.update(flat=flat_grad.clone())})()
     agent.lr_scheduler = type("S", (), {"step": lambda self: None})()

@@ -336,7 +336,7 @@ def test_train_step_host_flow(monkeypatch):
     agent = BesoAgent(build_denoiser(K256, "cpu"), device="cpu", window_size=10)
     seen = {}
 
-    def fake(core, state, action, goal, noise, sigma, pred_last, goal_keep):
+    def fake(core, state, action, goal, noise, sigma, pred_last, goal_keep, dropout_masks=None, grad_sync=None):
         seen["args"] = (state.shape, action.shape, goal.shape, noise.clone(), sigma.clone(), pred_last, goal_keep)
         return torch.tensor(1.5), torch.arange(10.0)
     monkeypatch.setattr(T, "loss_and_flat_grad", fake)
