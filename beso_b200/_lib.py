@@ -19,7 +19,7 @@ MODE_PRECISE, MODE_FAST, MODE_SIMT = 0, 1, 2
 SAMPLER_DDIM, SAMPLER_EULER, SAMPLER_HEUN, SAMPLER_EULER_ANCESTRAL, SAMPLER_DPMPP_2M, SAMPLER_TWO_STAGE, SAMPLER_LMS = 0, 1, 2, 3, 4, 5, 6
 FLAG_UNCOND, FLAG_CFG, FLAG_INNER, FLAG_PRED_LAST, FLAG_TRAIN_FAST = 1, 2, 4, 8, 16
 FLAG_TRAIN_TF32 = FLAG_TRAIN_FAST
-FLAG_TRAIN_SPLIT3 = 32
+FLAG_TRAIN_SPLIT2 = 32
 SAMPLER_IDS = {"ddim": SAMPLER_DDIM, "euler": SAMPLER_EULER, "heun": SAMPLER_HEUN, "euler_ancestral": SAMPLER_EULER_ANCESTRAL,
                "dpmpp_2m": SAMPLER_DPMPP_2M, "two_stage": SAMPLER_TWO_STAGE,
                "lms": SAMPLER_LMS}

@@ -19,10 +19,9 @@
 // Why bf16 and not fp16 here: gradients of a batch-mean loss are ~1e-6 and below, outside fp16's range; bf16 keeps
 // fp32's exponent.  Operand precision is bought with images: x = h + m + l (three bf16 values, 24 mantissa bits,
 // exact remainders) keeps every cross term down to 2^-24 (hh, hm, mh, mm, hl, lh: six MMAs); x = h + m (three MMAs)
-// carries 16 bits; one image is plain bf16 mixed-precision arithmetic.  Measured against fp64 products: 2.5e-6 of the
-// output scale with three images -- that floor is the tensor core's own fp32 accumulation -- and 5e-6 with two, so
-// the two-image mode is the default fp32-parity mode (the gradient goldens hold at rtol 2e-3) and three images are
-// an option.
+// carries 16 bits; one image is plain bf16 mixed-precision arithmetic.  Measured on the gradient goldens: within
+// 1.5e-6 of each tensor's scale with three images (the default, fp32-parity mode) and 1.5e-5 with two; against fp64
+// products of random matrices 2.5e-6 / 6e-6 of the output scale (the floor is the tensor core's fp32 accumulation).
 #include <cuda_bf16.h>
 
 #include <string>
@@ -44,14 +43,21 @@ constexpr uint32_t kStagePitch = 144;                 // bytes per row of the ep
 constexpr uint32_t kStageBufBytes = 32 * kStagePitch; // per epilogue warp
 
 // IMG = bf16 images per operand: 1 (x ~ h), 2 (x ~ h + m: 16 mantissa bits), 3 (x ~ h + m + l: 24 bits = fp32)
-template <int BN, int IMG>
+// BRES: the B operand of this CTA's column tile (all of K <= 256) is converted once and stays resident in shared
+// memory; the pipeline stages then carry A tiles only.  The GEMMs with K = embed_dim (QKV, projection, FC1 and the
+// data gradients through W2 / the d x d weights) stream the activations exactly once this way instead of re-reading
+// and re-converting the same 256 x 256 weight tile for every 128-row tile.
+constexpr uint32_t kResKb = 4;                        // k-blocks the resident B operand holds (K <= 256)
+template <int BN, int IMG, bool BRES>
 struct Cfg {
   static constexpr uint32_t a_bytes = kBM * 128u, b_bytes = BN * 128u;
   static constexpr uint32_t images = (uint32_t)IMG;
-  static constexpr uint32_t stage_bytes = images * (a_bytes + b_bytes);
-  static constexpr uint32_t stages_raw = 196608u / stage_bytes;
+  static constexpr uint32_t b_res = BRES ? kResKb * images * b_bytes : 0u;       // [kb][image][BN x 64]
+  static constexpr uint32_t stage_bytes = images * (a_bytes + (BRES ? 0u : b_bytes));
+  static constexpr uint32_t stages_raw = (196608u - b_res) / stage_bytes;
   static constexpr uint32_t stages = stages_raw > 6u ? 6u : stages_raw;
-  static constexpr uint32_t sm_epi = stages * stage_bytes;
+  static constexpr uint32_t sm_stage0 = b_res;
+  static constexpr uint32_t sm_epi = b_res + stages * stage_bytes;
   static constexpr uint32_t sm_bars = sm_epi + kEpiWarps * kStageBufBytes;
   static constexpr uint32_t smem = sm_bars + 256u;
 };
@@ -117,60 +123,52 @@ __device__ __forceinline__ void store_chunk(uint32_t addr, uint32_t img_delta, c
   }
 }
 
-// One operand tile [ROWS x 64] (element (row, k)) -> shared memory, by the 256 producer threads.
+// One operand tile [ROWS x 64] (element (row, k)) by the 256 producer threads, in two halves so that a whole pipeline
+// stage of global loads (ROWS / 32 tasks of 8 values per thread: 96 KB per SM for a 128 + 256 row stage) is in flight
+// while the producers wait for their shared-memory slot -- the memory latency is paid once per stage, not per batch.
 //   KMAJOR: element at src[(row0 + row) * ld + k]     (k contiguous: 8 lanes read the 256 bytes of one row)
 //  !KMAJOR: element at src[k * ld + row0 + row]       (rows contiguous: a warp reads 32 rows of one k, 128 bytes)
 // Rows >= n_rows and k >= K are zero.  vec: 16-byte loads are legal (ld % 4 == 0, base 16-byte aligned).
-template <int ROWS, bool KMAJOR, int IMG>
-__device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld, int row0, int n_rows, int k0, int K, bool vec,
-                                          uint32_t smem_hi, uint32_t lo_delta, int ptid) {
+template <int ROWS, bool KMAJOR>
+__device__ __forceinline__ void tile_issue(float (&v)[ROWS / 32][8], const float* __restrict__ src, int ld, int row0, int n_rows,
+                                           int k0, int K, bool vec, int ptid) {
+  constexpr int kTasks = ROWS / 32;
   if (KMAJOR) {
-    constexpr int kTasks = ROWS * 8 / kProdThreads;            // (row, 8-wide chunk) tasks per thread
-    constexpr int kBatch = 4;
-#pragma unroll 1
-    for (int t0 = 0; t0 < kTasks; t0 += kBatch) {
-      float v[kBatch][8];
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int task = ptid + (t0 + u) * kProdThreads, row = task >> 3, k = k0 + (task & 7) * 8;
-        const bool rv = row0 + row < n_rows;
-        const float* g = src + (size_t)(row0 + row) * ld + k;
-        if (rv && vec && k + 8 <= K) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g) + 1);
-          v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-        } else {
+    for (int u = 0; u < kTasks; ++u) {
+      const int task = ptid + u * kProdThreads, row = task >> 3, k = k0 + (task & 7) * 8;
+      const bool rv = row0 + row < n_rows;
+      const float* g = src + (size_t)(row0 + row) * ld + k;
+      if (rv && vec && k + 8 <= K) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g) + 1);
+        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+      } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] = (rv && k + j < K) ? __ldg(g + j) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int task = ptid + (t0 + u) * kProdThreads, row = task >> 3, chunk = task & 7;
-        store_chunk<IMG>(smem_hi + sw128_offset((uint32_t)row, (uint32_t)chunk), lo_delta, v[u]);
+        for (int j = 0; j < 8; ++j) v[u][j] = (rv && k + j < K) ? __ldg(g + j) : 0.f;
       }
     }
   } else {
-    constexpr int kTasks = (ROWS / 32) * 8 / kProdWarps;       // (32-row group, chunk) tasks per warp
-    constexpr int kBatch = 4;
-    const int pw = ptid >> 5, lane = ptid & 31;
-#pragma unroll 1
-    for (int t0 = 0; t0 < kTasks; t0 += kBatch) {
-      float v[kBatch][8];
+    const int pw = ptid >> 5, lane = ptid & 31;            // task u of warp pw: 32-row group u, k chunk pw
+    const int k = k0 + pw * 8;
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int task = pw + (t0 + u) * kProdWarps, rg = task >> 3, k = k0 + (task & 7) * 8;
-        const int row = rg * 32 + lane;
-        const bool rv = row0 + row < n_rows;
-        const float* g = src + (size_t)k * ld + row0 + row;
+    for (int u = 0; u < kTasks; ++u) {
+      const int row = u * 32 + lane;
+      const bool rv = row0 + row < n_rows;
+      const float* g = src + (size_t)k * ld + row0 + row;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[u][j] = (rv && k + j < K) ? __ldg(g + (size_t)j * ld) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int task = pw + (t0 + u) * kProdWarps, rg = task >> 3, chunk = task & 7;
-        store_chunk<IMG>(smem_hi + sw128_offset((uint32_t)(rg * 32 + lane), (uint32_t)chunk), lo_delta, v[u]);
-      }
+      for (int j = 0; j < 8; ++j) v[u][j] = (rv && k + j < K) ? __ldg(g + (size_t)j * ld) : 0.f;
     }
+  }
+}
+template <int ROWS, bool KMAJOR, int IMG>
+__device__ __forceinline__ void tile_store(const float (&v)[ROWS / 32][8], uint32_t smem_hi, uint32_t img_delta, int ptid) {
+  constexpr int kTasks = ROWS / 32;
+#pragma unroll
+  for (int u = 0; u < kTasks; ++u) {
+    uint32_t row, chunk;
+    if (KMAJOR) { const int task = ptid + u * kProdThreads; row = (uint32_t)(task >> 3); chunk = (uint32_t)(task & 7); }
+    else { row = (uint32_t)(u * 32 + (ptid & 31)); chunk = (uint32_t)(ptid >> 5); }
+    store_chunk<IMG>(smem_hi + sw128_offset(row, chunk), img_delta, v[u]);
   }
 }
 
@@ -183,9 +181,10 @@ struct KArgs {
 
 __device__ __forceinline__ float gelu_erf_g(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
 
-template <int BN, int IMG, bool AK, bool BK>
+template <int BN, int IMG, bool AK, bool BK, bool BRES>
 __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constant__ KArgs ka) {
-  using C = Cfg<BN, IMG>;
+  using C = Cfg<BN, IMG, BRES>;
+  static_assert(C::stages >= 2, "pipeline needs two stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(sm);
@@ -196,10 +195,12 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
   auto bar_empty = [&](uint32_t s) { return bars + (8u + s) * 8u; };
   auto bar_accf = [&](uint32_t a) { return bars + (16u + a) * 8u; };
   auto bar_acce = [&](uint32_t a) { return bars + (18u + a) * 8u; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::sm_bars + 20 * 8);
+  const uint32_t bar_bres = bars + 20u * 8u;          // resident B operand complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::sm_bars + 21 * 8);
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < C::stages; ++s) { mbar_init(bar_full(s), kProdWarps); mbar_init(bar_empty(s), 1); }
     for (uint32_t a = 0; a < 2; ++a) { mbar_init(bar_accf(a), 1); mbar_init(bar_acce(a), kEpiWarps); }
+    mbar_init(bar_bres, kProdWarps);
     fence_barrier_init();
   }
   if (warp == kMmaWarpG) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -211,19 +212,71 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
 
   if (warp >= kEpiWarps && warp < kMmaWarpG) {
     // ===================================== producers =====================================
+    // The global loads of the next kDepth pipeline steps are in flight in registers while the producers wait for
+    // shared-memory slots and convert: with a resident B operand a step is one 32 KB A tile, so three steps
+    // (96 registers per thread, 96 KB per SM) are kept in flight; with A + B per step (96 registers) one.
+    constexpr int kDepth = BRES ? 3 : 1;
     const int ptid = threadIdx.x - kEpiWarps * 32;
+    float va[kDepth][kBM / 32][8], vb[BRES ? 1 : kDepth][BN / 32][8];
+    struct Cur { int idx, kb; Tile t; bool have; };
+    auto start = [&]() {
+      Cur c;
+      c.idx = blockIdx.x;
+      c.have = c.idx < ka.n_tiles;
+      c.t = tile_of(c.have ? c.idx : 0, ka.nt, ka.mt, ka.kb_total, ka.kb_per);
+      c.kb = c.t.kb0;
+      return c;
+    };
+    auto advance = [&](Cur& c) {
+      if (++c.kb >= c.t.kb1) {
+        c.idx += gridDim.x;
+        c.have = c.idx < ka.n_tiles;
+        if (c.have) { c.t = tile_of(c.idx, ka.nt, ka.mt, ka.kb_total, ka.kb_per); c.kb = c.t.kb0; }
+      }
+    };
+    Cur ci = start(), cs = ci;
+    if constexpr (BRES) {
+      // every tile of this CTA has the same column tile (grid % nt == 0): its B operand, once
+      if (ci.have) {
+        for (int rk = 0; rk < ka.kb_total; ++rk) {
+          tile_issue<BN, BK>(vb[0], g.B, g.ldb, ci.t.n0 * BN, g.N, rk * kBK, g.K, ka.vec_b != 0, ptid);
+          tile_store<BN, BK, IMG>(vb[0], sbase + (uint32_t)rk * C::images * C::b_bytes, C::b_bytes, ptid);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_bres);
+    }
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+      if (ci.have) {
+        tile_issue<kBM, AK>(va[d], g.A, g.lda, ci.t.m0, g.M, ci.kb * kBK, g.K, ka.vec_a != 0, ptid);
+        if constexpr (!BRES) tile_issue<BN, BK>(vb[d], g.B, g.ldb, ci.t.n0 * BN, g.N, ci.kb * kBK, g.K, ka.vec_b != 0, ptid);
+        advance(ci);
+      }
+    }
     uint32_t it = 0;
-    for (int idx = blockIdx.x; idx < ka.n_tiles; idx += gridDim.x) {
-      const Tile t = tile_of(idx, ka.nt, ka.mt, ka.kb_total, ka.kb_per);
-      for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
+    while (cs.have) {
+#pragma unroll
+      for (int d = 0; d < kDepth; ++d) {
+        if (!cs.have) break;
         const uint32_t s = it % C::stages, par = (it / C::stages) & 1u;
         wait_bar(bar_empty(s), par ^ 1u);
-        const uint32_t st = sbase + s * C::stage_bytes;
-        load_tile<kBM, AK, IMG>(g.A, g.lda, t.m0, g.M, kb * kBK, g.K, ka.vec_a != 0, st, C::a_bytes, ptid);
-        load_tile<BN, BK, IMG>(g.B, g.ldb, t.n0 * BN, g.N, kb * kBK, g.K, ka.vec_b != 0, st + C::images * C::a_bytes, C::b_bytes, ptid);
-        fence_async_smem();
+        const uint32_t st = sbase + C::sm_stage0 + s * C::stage_bytes;
+        tile_store<kBM, AK, IMG>(va[d], st, C::a_bytes, ptid);
+        if constexpr (!BRES) tile_store<BN, BK, IMG>(vb[d], st + C::images * C::a_bytes, C::b_bytes, ptid);
+        // No proxy fence here: fence.proxy.async compiles to MEMBAR.ALL.CTA, which would wait for this thread's
+        // prefetched global loads of the following steps and serialise the pipeline on the memory latency.  The
+        // stores are released by the mbarrier arrive below and the MMA warp fences the proxies after its acquire.
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full(s));
+        ++it;
+        advance(cs);
+        if (ci.have) {
+          tile_issue<kBM, AK>(va[d], g.A, g.lda, ci.t.m0, g.M, ci.kb * kBK, g.K, ka.vec_a != 0, ptid);
+          if constexpr (!BRES) tile_issue<BN, BK>(vb[d], g.B, g.ldb, ci.t.n0 * BN, g.N, ci.kb * kBK, g.K, ka.vec_b != 0, ptid);
+          advance(ci);
+        }
       }
     }
   } else if (warp == kMmaWarpG) {
@@ -231,6 +284,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     constexpr uint32_t idesc = idesc_bf16_m128(BN);
     uint32_t it = 0, tcount = 0;
+    if constexpr (BRES) wait_bar(bar_bres, 0);
     for (int idx = blockIdx.x; idx < ka.n_tiles; idx += gridDim.x, ++tcount) {
       const Tile t = tile_of(idx, ka.nt, ka.mt, ka.kb_total, ka.kb_per);
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
@@ -240,9 +294,11 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
       for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
         const uint32_t s = it % C::stages, par = (it / C::stages) & 1u;
         wait_bar(bar_full(s), par);
+        fence_async_smem();                 // generic-proxy operand stores (acquired above) -> async proxy (tcgen05.mma)
         tc_fence_after();
-        const uint32_t st = sbase + s * C::stage_bytes;
-        const uint64_t a_hi = smem_desc_sw128(st), b_hi = smem_desc_sw128(st + C::images * C::a_bytes);
+        const uint32_t st = sbase + C::sm_stage0 + s * C::stage_bytes;
+        const uint64_t a_hi = smem_desc_sw128(st);
+        const uint64_t b_hi = smem_desc_sw128(BRES ? sbase + (uint32_t)kb * C::images * C::b_bytes : st + C::images * C::a_bytes);
         if (elect_one_g()) {
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) {
@@ -352,18 +408,18 @@ __global__ void splitk_reduce_kernel(GemmArgs g, const float* __restrict__ parti
   *cp = a;
 }
 
-template <int BN, int IMG>
+template <int BN, int IMG, bool BRES>
 int launch(const KArgs& ka, int grid, cudaStream_t st) {
-  using C = Cfg<BN, IMG>;
+  using C = Cfg<BN, IMG, BRES>;
   const int smem = (int)C::smem + 1024;
 #define BESO_GEMM_CASE(AK, BK)                                                                                      \
   do {                                                                                                              \
     static bool cfgd = false;                                                                                       \
     if (!cfgd) {                                                                                                    \
-      BESO_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, IMG, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      BESO_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, IMG, AK, BK, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       cfgd = true;                                                                                                  \
     }                                                                                                               \
-    gemm_kernel<BN, IMG, AK, BK><<<grid, kThreadsG, smem, st>>>(ka);                                                \
+    gemm_kernel<BN, IMG, AK, BK, BRES><<<grid, kThreadsG, smem, st>>>(ka);                                          \
   } while (0)
   if (ka.g.a_kmajor && ka.g.b_kmajor) BESO_GEMM_CASE(true, true);
   else if (ka.g.a_kmajor) BESO_GEMM_CASE(true, false);
@@ -389,15 +445,18 @@ int gemm_run(const GemmArgs& a, GemmWs& ws, int sm_count, cudaStream_t st) {
   KArgs ka{};
   ka.g = a;
   if (a.prec < 0 || a.prec > 2) { set_error("gemm: prec must be 0, 1 or 2"); return BESO_E_INVALID; }
+  // resident-B mode: K <= 256, enough row tiles to keep the chip busy, one or two images (see Cfg); its column tile
+  // is 256 wide with one image and 128 with two so that the resident operand stays within 128 KB
+  const bool bres = a.K <= (int)(kResKb * kBK) && a.prec < 2 && (a.M + kBM - 1) / kBM >= 2 * sm_count;
   // three images per operand fill shared memory twice as fast: 128-wide tiles keep two pipeline stages
-  const int bn = (a.N > 128 && a.prec < 2) ? 256 : 128;
+  const int bn = (a.N > 128 && a.prec < 2 && !(bres && a.prec == 1)) ? 256 : 128;
   ka.mt = (a.M + kBM - 1) / kBM;
   ka.nt = (a.N + bn - 1) / bn;
   ka.kb_total = (a.K + kBK - 1) / kBK;
   // split-K when the output has far fewer tiles than the chip has SMs and the contraction is long
   const int out_tiles = ka.mt * ka.nt;
   int ksplit = 1;
-  if (!a.gelu_out && out_tiles * 2 <= sm_count && ka.kb_total >= 16) {
+  if (!bres && !a.gelu_out && out_tiles * 2 <= sm_count && ka.kb_total >= 16) {
     ksplit = sm_count / out_tiles;
     const int max_split = ka.kb_total / 4;                    // at least 4 k-blocks per split
     if (ksplit > max_split) ksplit = max_split;
@@ -425,10 +484,14 @@ int gemm_run(const GemmArgs& a, GemmWs& ws, int sm_count, cudaStream_t st) {
                (!a.mul || (a.ldm % 4 == 0 && aligned16(a.mul))) &&
                (!a.bias || aligned16(a.bias)) && (!a.gelu_out || (a.ldg % 4 == 0 && aligned16(a.gelu_out)));
   }
-  const int grid = ka.n_tiles < sm_count ? ka.n_tiles : sm_count;
+  int grid = ka.n_tiles < sm_count ? ka.n_tiles : sm_count;
   int rc;
-  if (bn == 256) rc = a.prec ? launch<256, 2>(ka, grid, st) : launch<256, 1>(ka, grid, st);
-  else rc = a.prec == 2 ? launch<128, 3>(ka, grid, st) : (a.prec ? launch<128, 2>(ka, grid, st) : launch<128, 1>(ka, grid, st));
+  if (bres) {
+    grid = (sm_count / ka.nt) * ka.nt;                         // every CTA keeps one column tile: grid % nt == 0
+    if (grid < ka.nt) grid = ka.nt;
+    rc = a.prec ? launch<128, 2, true>(ka, grid, st) : (bn == 256 ? launch<256, 1, true>(ka, grid, st) : launch<128, 1, true>(ka, grid, st));
+  } else if (bn == 256) rc = a.prec ? launch<256, 2, false>(ka, grid, st) : launch<256, 1, false>(ka, grid, st);
+  else rc = a.prec == 2 ? launch<128, 3, false>(ka, grid, st) : (a.prec ? launch<128, 2, false>(ka, grid, st) : launch<128, 1, false>(ka, grid, st));
   if (rc) return rc;
   if (ksplit > 1) {
     const size_t total = (size_t)a.M * a.N;

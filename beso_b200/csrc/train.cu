@@ -2,9 +2,9 @@
 // data-parallel gradient exchange (one NCCL all-reduce of the flat fp32 gradient over NVLink).
 //
 // Every dense product (forward, data gradient, weight gradient) runs on the tcgen05 tensor cores through the
-// hand-written GEMM of gemm.cu: fp32 tensors in HBM, two bf16 operand images (hi + lo) and three MMAs per product
-// by default (fp32-parity mode, the one the gradient goldens pin), three images / six MMAs with
-// BESO_FLAG_TRAIN_SPLIT3, one bf16 MMA per product with BESO_FLAG_TRAIN_FAST.  Bias, residual add and erf-GELU ride in the GEMM epilogues.  Everything else --
+// hand-written GEMM of gemm.cu: fp32 tensors in HBM, three bf16 operand images and six MMAs per product by
+// default (fp32-parity mode, the one the gradient goldens pin), two images / three MMAs with
+// BESO_FLAG_TRAIN_SPLIT2, one bf16 MMA per product with BESO_FLAG_TRAIN_FAST.  Bias, residual add and erf-GELU ride in the GEMM epilogues.  Everything else --
 // embeddings + interleave, LayerNorm forward/backward, causal attention forward/backward, GELU backward,
 // bias / column reductions, dropout, the Karras pre-conditioned loss -- is hand-written below in fp32.
 // Gradients are written into ONE flat buffer in nn.Module.parameters() order, which is what the
@@ -620,7 +620,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   D.M = B * D.T; D.sigma_data = m.sigma_data;
   if (D.T > 64) { set_error("training path supports at most 64 tokens per sequence"); return BESO_E_UNSUPPORTED; }
   const int pred_last = (flags & BESO_FLAG_PRED_LAST) ? 1 : 0;
-  const int prec = (flags & BESO_FLAG_TRAIN_FAST) ? 0 : ((flags & BESO_FLAG_TRAIN_SPLIT3) ? 2 : 1);
+  const int prec = (flags & BESO_FLAG_TRAIN_FAST) ? 0 : ((flags & BESO_FLAG_TRAIN_SPLIT2) ? 1 : 2);
   const int d = D.d, F = D.F, M = D.M, L = D.L;
   const size_t Md = (size_t)M * d, MF = (size_t)M * F, nP = (size_t)B * D.H * D.T * D.T, nBt = (size_t)B * D.t;
   // ---- carve the workspace ----

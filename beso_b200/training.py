@@ -6,8 +6,8 @@ in ONE call of the C ABI (``beso_loss_fwd_bwd``), which writes all gradients int
 ``parameters()`` order -- the buffer the data-parallel all-reduce (beso_b200/dist.py) operates on.
 
 Every dense product runs on the tcgen05 tensor cores (csrc/gemm.cu): ``model.train_math = "fp32"`` (default) splits
-the operands into bf16 hi + lo images, three MMAs per product (the fp32-parity mode the gradient goldens pin);
-``"bf16x3"`` is three images / six MMAs, ``"bf16"`` one MMA per product.
+the operands into three bf16 images, six MMAs per product (the fp32-parity mode the gradient goldens pin);
+``"bf16x2"`` is two images / three MMAs, ``"bf16"`` one MMA per product.
 
 Training-mode randomness: the reference draws the element-wise goal mask of CFG training (score_gpts.py:360-371) and
 its dropout masks (score_gpts.py:338,72,79,109) from torch's global generator in op order.
@@ -97,9 +97,9 @@ def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_actio
                        need_grad=True, dropout_masks=None, grad_sync=None):
     """Runs ``beso_loss_fwd_bwd_dropout``; returns (loss 0-d tensor, flat gradient or None).
 
-    ``model.train_math``: "fp32" (default: bf16 hi + lo images of every operand, three MMAs per product, the
-    fp32-parity mode), "bf16x3" (three images, six MMAs) or "bf16" (one MMA per product; "tf32" is accepted as the
-    round-1 name of the opt-in fast mode).
+    ``model.train_math``: "fp32" (default: three bf16 images per operand, six MMAs per product, the fp32-parity mode),
+    "bf16x2" (two images, three MMAs) or "bf16" (one MMA per product; "tf32" is accepted as the round-1 name of the
+    opt-in fast mode).
     ``dropout_masks``: see ``draw_dropout_masks`` (None = no dropout).
     ``grad_sync``: a ``beso_b200.dist.FlatGradAllReduce``; with the NCCL transport the gradient all-reduce is issued per
     transformer block from inside the backward pass on the communicator's stream (``beso_loss_fwd_bwd_dp``) and the
@@ -119,10 +119,10 @@ def loss_and_flat_grad(model, state, action, goal, noise, sigma, pred_last_actio
     keep_ptr = goal_keep.data_ptr() if goal_keep is not None else None
     flags = _lib.FLAG_PRED_LAST if pred_last_action_only else 0
     math = getattr(model, "train_math", "fp32")
-    if math not in ("fp32", "bf16x3", "bf16", "tf32"):
-        raise ValueError(f"train_math must be 'fp32', 'bf16x3' or 'bf16', got {math!r}")
-    if math == "bf16x3":
-        flags |= _lib.FLAG_TRAIN_SPLIT3
+    if math not in ("fp32", "bf16x2", "bf16", "tf32"):
+        raise ValueError(f"train_math must be 'fp32', 'bf16x2' or 'bf16', got {math!r}")
+    if math == "bf16x2":
+        flags |= _lib.FLAG_TRAIN_SPLIT2
     elif math != "fp32":
         flags |= _lib.FLAG_TRAIN_FAST
     mstruct, keep = _masks_struct(dropout_masks, cfg.n_layers, action.device)

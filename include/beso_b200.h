@@ -77,14 +77,12 @@ enum {
                                the c_in / c_out / c_skip pre-conditioning of GCDenoiser.forward             */
 #define BESO_FLAG_TRAIN_FAST 16u /* beso_loss_fwd_bwd only: one bf16 tcgen05 MMA per product in the training GEMMs
                                   (the arithmetic of bf16 mixed-precision training).  Opt-in: by default every
-                                  operand is split into two bf16 images (hi + lo, 16 mantissa bits) and every product
-                                  is three MMAs (hi.hi + lo.hi + hi.lo, fp32 accumulate in TMEM) -- the fp32-parity
-                                  mode the gradient goldens pin (the reference multiplies in fp32).  Measured: results
-                                  within ~5e-6 of the output scale of an fp64 product. */
-#define BESO_FLAG_TRAIN_SPLIT3 32u /* beso_loss_fwd_bwd only: three bf16 images per operand (24 mantissa bits), six MMAs
-                                  per product; measured ~2.5e-6 of the output scale -- what is left is the tensor
-                                  core's own fp32 accumulation, so this buys little over the default for twice the
-                                  tensor time; opt-in */
+                                  operand is split into three bf16 images (24 mantissa bits) and every product is
+                                  six MMAs (all cross terms down to 2^-24, fp32 accumulate in TMEM) -- the
+                                  fp32-parity mode the gradient goldens pin (the reference multiplies in fp32).
+                                  Measured: gradients within ~1.5e-6 of their tensor's scale of the reference's. */
+#define BESO_FLAG_TRAIN_SPLIT2 32u /* beso_loss_fwd_bwd only: two bf16 images per operand (16 mantissa bits), three
+                                  MMAs per product; measured ~1.5e-5 of the gradient scale; opt-in */
 #define BESO_FLAG_TRAIN_TF32 BESO_FLAG_TRAIN_FAST /* round-1 name of the opt-in tensor-core training mode */
 
 /* Constructor arguments of DiffusionGPT (k_diffusion/score_gpts.py:121-139) and

@@ -1,9 +1,9 @@
 """GPU: GCDenoiser.loss + backward through the C ABI against the reference's loss and autograd gradients
 (golden fixtures), and size-independent properties at BASELINE config 3 size (batch 4096).
 
-Tolerance: fp32-parity path (split bf16 operands on the tensor cores, fp32 accumulate in TMEM); loss rtol 1e-4,
-gradients rtol 2e-3 / atol 1e-5 * max|grad| (the tensor core's fp32 accumulation and a different summation order over
-up to 4096 x 23 rows than ATen's: measured ~5e-6 of the gradient scale)."""
+Tolerance: fp32-parity path (three bf16 images per operand on the tensor cores, fp32 accumulate in TMEM); loss rtol 1e-4,
+gradients rtol 2e-3 / atol 6e-6 * max|grad| (the tensor core's fp32 accumulation and a different summation order over
+up to 4096 x 23 rows than ATen's: measured up to 4e-6 of a tensor's gradient scale)."""
 import pytest
 import torch
 
@@ -43,7 +43,7 @@ def test_loss_and_gradients_match_reference_golden(name, cuda_device):
         want = a["grad::" + n]
         # floor: gradients that are analytically zero (attn.key.bias: softmax is shift-invariant) are pure
         # fp32 round-off (~1e-10) in both implementations
-        torch.testing.assert_close(got, want, rtol=2e-3, atol=1e-5 * float(want.abs().max()) + 2e-8)
+        torch.testing.assert_close(got, want, rtol=2e-3, atol=6e-6 * float(want.abs().max()) + 2e-8)
     loss_last = m.loss(g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"], pred_last_action_only=True)
     torch.testing.assert_close(loss_last.cpu(), a["loss_pred_last"], rtol=1e-4, atol=1e-7)
 
@@ -93,7 +93,7 @@ def test_goal_mask_changes_loss_and_matches_oracle(cuda_device):
 
 def test_single_pass_bf16_training_math_is_opt_in_and_close(cuda_device):
     """model.train_math = "bf16": one bf16 MMA per product (mixed-precision training arithmetic) instead of the default
-    split bf16 hi + lo / three MMAs.  Not the reference's arithmetic (fp32), so it is opt-in and only has to stay
+    three bf16 images / six MMAs ("bf16x2": two images / three MMAs).  Not the reference's arithmetic (fp32), so it is opt-in and only has to stay
     close: loss within 2e-3 relative, flat gradient direction within 1e-3 of the fp32-parity one."""
     import time
     cfg = B256
@@ -104,7 +104,7 @@ def test_single_pass_bf16_training_math_is_opt_in_and_close(cuda_device):
     args = (g["state"], g["clean"], g["goal"], g["noise"], g["sigma"])
     times = {}
     out = {}
-    for math in ("fp32", "bf16x3", "bf16"):
+    for math in ("fp32", "bf16x2", "bf16"):
         m.train_math = math
         out[math] = loss_and_flat_grad(m, *args)
         torch.cuda.synchronize()
@@ -118,10 +118,10 @@ def test_single_pass_bf16_training_math_is_opt_in_and_close(cuda_device):
     cos = torch.nn.functional.cosine_similarity(f32, ftf, dim=0)
     assert float(cos) > 1.0 - 1e-3, float(cos)
     assert not torch.equal(f32, ftf)                         # the flag really switched the arithmetic
-    cos2 = torch.nn.functional.cosine_similarity(f32, out["bf16x3"][1], dim=0)
+    cos2 = torch.nn.functional.cosine_similarity(f32, out["bf16x2"][1], dim=0)
     assert float(cos2) > 1.0 - 1e-6, float(cos2)
-    print(f"cfg3 fwd+bwd B=4096: fp32-parity {times['fp32']:.1f} ms, bf16x3 {times['bf16x3']:.1f} ms, bf16 {times['bf16']:.1f} ms, "
-          f"grad cosine bf16 {float(cos):.7f} bf16x3 {float(cos2):.9f}")
+    print(f"cfg3 fwd+bwd B=4096: fp32-parity {times['fp32']:.1f} ms, bf16x2 {times['bf16x2']:.1f} ms, bf16 {times['bf16']:.1f} ms, "
+          f"grad cosine bf16 {float(cos):.7f} bf16x2 {float(cos2):.9f}")
     m.train_math = "fp8"
     with pytest.raises(ValueError):
         loss_and_flat_grad(m, *args)
@@ -210,7 +210,7 @@ def test_loss_with_dropout_matches_reference_golden(name, cuda_device):
         fl = gr.reshape(-1).cpu()
         got = fl if fl.numel() <= 4096 else fl[::97][:4096]
         want = a["grad::" + n]
-        torch.testing.assert_close(got, want, rtol=2e-3, atol=1e-5 * float(want.abs().max()) + 2e-8)
+        torch.testing.assert_close(got, want, rtol=2e-3, atol=6e-6 * float(want.abs().max()) + 2e-8)
     # through the module API: the draws come from the device generator in the same op order; two steps under the same
     # seed see the same masks, a different seed a different loss
     torch.manual_seed(3)
@@ -229,13 +229,15 @@ GEMM_CASES = [  # M, N, K, a_kmajor, b_kmajor  (forward NT, data-gradient NN, we
     (1000, 256, 256, 1, 1), (777, 1024, 256, 1, 1), (513, 256, 1024, 1, 1), (300, 9, 256, 1, 1),
     (640, 1024, 256, 1, 0), (515, 256, 1024, 1, 0), (256, 1024, 5000, 0, 0), (1024, 256, 3001, 0, 0),
     (256, 60, 2000, 0, 0), (256, 1, 700, 0, 0), (240, 240, 900, 0, 0), (130, 240, 240, 1, 1), (9, 256, 333, 0, 0),
+    # enough row tiles for the resident-B mode (K <= 256): full and ragged column tiles, both B layouts
+    (40000, 256, 256, 1, 1), (38100, 1024, 256, 1, 0), (39000, 300, 200, 1, 1), (38000, 240, 240, 1, 0),
 ]
 
 
 @pytest.mark.parametrize("prec", [2, 1, 0])
 def test_tcgen05_training_gemm_against_fp64(prec, cuda_device):
     """csrc/gemm.cu by itself against a float64 product of the same fp32 inputs: the three-image (fp32-parity) mode to
-    5e-6 of the output scale (the floor is the tensor core's fp32 accumulation), two images to 2e-5, single-pass bf16 to 1e-2; bias and accumulate epilogues;
+    1e-5 of the output scale (the floor is the tensor core's fp32 accumulation), two images to 3e-5, single-pass bf16 to 1e-2; bias and accumulate epilogues;
     deterministic split-K."""
     import ctypes as C
     from beso_b200 import K256, _lib
@@ -257,7 +259,7 @@ def test_tcgen05_training_gemm_against_fp64(prec, cuda_device):
                                        M, N, K, bias.data_ptr(), 1, prec, None), "beso_debug_gemm")
         scale = float(want.abs().max())
         err = float((out.double() - want).abs().max())
-        tol = {2: 5e-6, 1: 2e-5, 0: 1e-2}[prec] * scale
+        tol = {2: 1e-5, 1: 3e-5, 0: 1e-2}[prec] * scale
         assert err <= tol, ((M, N, K, ak, bk), err, scale)
         out2 = C0.clone()
         _lib.check(lib.beso_debug_gemm(plan, A.data_ptr(), A.shape[1], ak, Bm.data_ptr(), Bm.shape[1], bk, out2.data_ptr(), N,

@@ -27,7 +27,7 @@ def errors():
         m = build_denoiser(cfg, dev, mode="precise", state_dict=golden_weights(cfg, meta))
         m.train()
         g = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in a.items()}
-        for math in ("fp32", "bf16x3", "bf16"):
+        for math in ("fp32", "bf16x2", "bf16"):
             m.train_math = math
             loss, flat = loss_and_flat_grad(m, g["state"], g["action"], g["goal"], g["noise"].clone(), g["sigma"])
             views = dict(zip([n for n, _ in m.named_parameters()], flat_grad_views(m, flat)))
