@@ -521,165 +521,18 @@ def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None,
     return action
 
 
-# ---- DPM-Solver with host-side step control (gc_sampling.py:498-699, 856-892) ---------------------------------------
-# dpm_fast / dpm_adaptive decide their step sequence on the host (the adaptive one from an error norm of every trial
-# step), so the loop stays in Python; every model evaluation is still ONE fused launch of the denoiser.
-class PIDStepSizeController:
-    """PID step-size control of the adaptive solver (gc_sampling.py:498-524)."""
-
-    def __init__(self, h, pcoeff, icoeff, dcoeff, order=1, accept_safety=0.81, eps=1e-8):
-        self.h = h
-        self.b1, self.b2, self.b3 = (pcoeff + icoeff + dcoeff) / order, -(pcoeff + 2 * dcoeff) / order, dcoeff / order
-        self.accept_safety, self.eps = accept_safety, eps
-        self.errs = []
-
-    def limiter(self, x):
-        return 1 + math.atan(x - 1)
-
-    def propose_step(self, error):
-        inv = 1 / (float(error) + self.eps)
-        if not self.errs:
-            self.errs = [inv, inv, inv]
-        self.errs[0] = inv
-        factor = self.limiter(self.errs[0] ** self.b1 * self.errs[1] ** self.b2 * self.errs[2] ** self.b3)
-        accept = factor >= self.accept_safety
-        if accept:
-            self.errs[2], self.errs[1] = self.errs[1], self.errs[0]
-        self.h *= factor
-        return accept
-
-
-class DPMSolver:
-    """DPM-Solver-1/2/3 steps in t = -log(sigma) (gc_sampling.py:527-672).  One instance per sampling call; ``_eps`` is
-    the per-step cache of noise predictions the reference threads through its step functions."""
-
-    def __init__(self, model, extra_args=None, eps_callback=None, info_callback=None):
-        self.model = model
-        self.extra_args = {} if extra_args is None else extra_args
-        self.eps_callback, self.info_callback = eps_callback, info_callback
-        self._eps = {}
-
-    @staticmethod
-    def t(sigma):
-        return -sigma.log()
-
-    @staticmethod
-    def sigma(t):
-        return t.neg().exp()
-
-    def eps(self, key, state, action, goal, t):
-        if key not in self._eps:
-            sig = self.sigma(t) * action.new_ones([action.shape[0]])
-            self._eps[key] = (action - self.model(state, action, goal, sig, **self.extra_args)) / self.sigma(t)
-            if self.eps_callback is not None:
-                self.eps_callback()
-        return self._eps[key]
-
-    def step1(self, state, action, goal, t, t_next):
-        h = t_next - t
-        return action - self.sigma(t_next) * h.expm1() * self.eps("eps", state, action, goal, t)
-
-    def step2(self, state, action, goal, t, t_next, r1=1 / 2):
-        h = t_next - t
-        e0 = self.eps("eps", state, action, goal, t)
-        s1 = t + r1 * h
-        u1 = action - self.sigma(s1) * (r1 * h).expm1() * e0
-        e1 = self.eps("eps_r1", state, u1, goal, s1)
-        return action - self.sigma(t_next) * h.expm1() * e0 - self.sigma(t_next) / (2 * r1) * h.expm1() * (e1 - e0)
-
-    def step3(self, state, action, goal, t, t_next, r1=1 / 3, r2=2 / 3):
-        h = t_next - t
-        e0 = self.eps("eps", state, action, goal, t)
-        s1, s2 = t + r1 * h, t + r2 * h
-        u1 = action - self.sigma(s1) * (r1 * h).expm1() * e0
-        e1 = self.eps("eps_r1", state, u1, goal, s1)
-        u2 = (action - self.sigma(s2) * (r2 * h).expm1() * e0
-              - self.sigma(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1) * (e1 - e0))
-        e2 = self.eps("eps_r2", state, u2, goal, s2)
-        return action - self.sigma(t_next) * h.expm1() * e0 - self.sigma(t_next) / r2 * (h.expm1() / h - 1) * (e2 - e0)
-
-    def _noise_step(self, t, t_next, t_end, eta):
-        """(t the step really goes to, sigma_up) of an ancestral step; eta = 0: the plain ODE step."""
-        if not eta:
-            return t_next, 0.0
-        sd, _ = get_ancestral_step(self.sigma(t), self.sigma(t_next), eta)
-        t_to = torch.minimum(t_end, self.t(sd))
-        return t_to, (self.sigma(t_next) ** 2 - self.sigma(t_to) ** 2) ** 0.5
-
-    def fast(self, state, action, goal, t_start, t_end, nfe, eta=0.0, s_noise=1.0):
-        """Fixed step sizes, ``nfe`` model evaluations split into order-3 steps plus a remainder (gc_sampling.py:582-619)."""
-        if not t_end > t_start and eta:
-            raise ValueError('eta must be 0 for reverse sampling')
-        m = math.floor(nfe / 3) + 1
-        ts = torch.linspace(t_start, t_end, m + 1, device=action.device)
-        orders = [3] * (m - 2) + [2, 1] if nfe % 3 == 0 else [3] * (m - 1) + [nfe % 3]
-        steps = {1: self.step1, 2: self.step2, 3: self.step3}
-        for i, order in enumerate(orders):
-            self._eps = {}
-            t, t_next = ts[i], ts[i + 1]
-            t_to, su = self._noise_step(t, t_next, t_end, eta)
-            e0 = self.eps("eps", state, action, goal, t)
-            if self.info_callback is not None:
-                self.info_callback({'x': action, 'i': i, 't': ts[i], 't_up': t, 'denoised': action - self.sigma(t) * e0})
-            action = steps[order](state, action, goal, t, t_to)
-            action = action + su * s_noise * torch.randn_like(action)      # drawn even when su = 0, as the reference does
-        return action
-
-    def adaptive(self, state, action, goal, t_start, t_end, order=3, rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0.0,
-                 icoeff=1.0, dcoeff=0.0, accept_safety=0.81, eta=0.0, s_noise=1.0):
-        """Embedded pairs 1(2) / 2(3) with PID step control (gc_sampling.py:621-672)."""
-        if order not in {2, 3}:
-            raise ValueError('order should be 2 or 3')
-        forward = t_end > t_start
-        if not forward and eta:
-            raise ValueError('eta must be 0 for reverse sampling')
-        h_init = abs(h_init) * (1 if forward else -1)
-        atol, rtol = torch.tensor(atol), torch.tensor(rtol)
-        s, action_prev = t_start, action
-        pid = PIDStepSizeController(h_init, pcoeff, icoeff, dcoeff, 1.5 if eta else order, accept_safety)
-        info = {'steps': 0, 'nfe': 0, 'n_accept': 0, 'n_reject': 0}
-        while (s < t_end - 1e-5) if forward else (s > t_end + 1e-5):
-            self._eps = {}
-            t = torch.minimum(t_end, s + pid.h) if forward else torch.maximum(t_end, s + pid.h)
-            t_to, su = self._noise_step(s, t, t_end, eta)
-            e0 = self.eps("eps", state, action, goal, s)
-            denoised = action - self.sigma(s) * e0
-            if order == 2:
-                low, high = self.step1(state, action, goal, s, t_to), self.step2(state, action, goal, s, t_to)
-            else:
-                low, high = self.step2(state, action, goal, s, t_to, r1=1 / 3), self.step3(state, action, goal, s, t_to)
-            delta = torch.maximum(atol.to(low.device), rtol.to(low.device) * torch.maximum(low.abs(), action_prev.abs()))
-            error = torch.linalg.norm((low - high) / delta) / action.numel() ** 0.5
-            if pid.propose_step(error):
-                action_prev = low
-                action = high + su * s_noise * torch.randn_like(action)
-                s = t
-                info['n_accept'] += 1
-            else:
-                info['n_reject'] += 1
-            info['nfe'] += order
-            info['steps'] += 1
-            if self.info_callback is not None:
-                self.info_callback({'x': action, 'i': info['steps'] - 1, 't': s, 't_up': s, 'denoised': denoised,
-                                    'error': error, 'h': pid.h, **info})
-        return action, info
-
-
-def _dpm_solver(model, extra_args, callback):
-    solver = DPMSolver(model, extra_args)
-    if callback is not None:
-        solver.info_callback = lambda info: callback({'sigma': solver.sigma(info['t']), 'sigma_hat': solver.sigma(info['t_up']), **info})
-    return solver
-
-
+# ---- DPM-Solver-Fast / -Adaptive (gc_sampling.py:675-699, 855-892) ---------------------------------------------------
+# Their step sequence is decided on the host (the adaptive one from an error norm of every trial step), so the loop
+# cannot live in the persistent kernel; beso_b200/exp_integrator.py runs them as exponential Runge-Kutta tableaux with
+# ONE fused denoiser launch per stage.  These two wrappers only carry the reference's call signatures.
 @torch.no_grad()
 def sample_dpm_fast(model, state, action, goal, sigma_min, sigma_max, n, scaler=None, extra_args=None, callback=None,
                     disable=None, eta=0.0, s_noise=1.0, noise_sampler=None):
     """DPM-Solver-Fast (gc_sampling.py:675-699); ``scaler`` and ``noise_sampler`` are ignored there too."""
+    from .exp_integrator import integrate_fixed
     if sigma_min <= 0 or sigma_max <= 0:
         raise ValueError('sigma_min and sigma_max must not be 0')
-    solver = _dpm_solver(model, extra_args, callback)
-    return solver.fast(state, action, goal, solver.t(torch.tensor(sigma_max)), solver.t(torch.tensor(sigma_min)), n, eta, s_noise)
+    return integrate_fixed(model, state, action, goal, sigma_max, sigma_min, n, eta, s_noise, extra_args, callback)
 
 
 @torch.no_grad()
@@ -687,11 +540,11 @@ def sample_dpm_adaptive(model, state, action, goal, sigma_min, sigma_max, extra_
                         order=3, rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0.0, icoeff=1.0, dcoeff=0.0,
                         accept_safety=0.81, eta=0.0, s_noise=1.0, return_info=False):
     """DPM-Solver-12 / 23 with adaptive step size (gc_sampling.py:855-892)."""
+    from .exp_integrator import integrate_adaptive
     if sigma_min <= 0 or sigma_max <= 0:
         raise ValueError('sigma_min and sigma_max must not be 0')
-    solver = _dpm_solver(model, extra_args, callback)
-    action, info = solver.adaptive(state, action, goal, solver.t(torch.tensor(sigma_max)), solver.t(torch.tensor(sigma_min)),
-                                   order, rtol, atol, h_init, pcoeff, icoeff, dcoeff, accept_safety, eta, s_noise)
+    action, info = integrate_adaptive(model, state, action, goal, sigma_max, sigma_min, order, rtol, atol, h_init,
+                                      (pcoeff, icoeff, dcoeff), accept_safety, eta, s_noise, extra_args, callback)
     return (action, info) if return_info else action
 
 

@@ -474,3 +474,86 @@ def n_model_evals(sampler: str, n_steps: int, last_sigma_zero: bool = True) -> i
     if sampler == "heun":
         return 2 * n_steps - (1 if last_sigma_zero else 0)
     return n_steps
+
+
+# ---- 16-bit-faithful oracle of the FAST mode ------------------------------------------------------------
+# The reference's forward with exactly the operand roundings the fp16 tensor-core kernel makes (beso_b200/csrc/
+# fast_forward.cu), everything else in fp32 torch ops: tensor-core operands rounded to fp16 (the
+# embedding operands to bf16), LayerNorm affine folded into the following Linear before the weight is rounded, the
+# softmax scale folded into W_q, K bias dropped / V bias folded into the projection bias, GELU input and output in
+# fp16.  What it does NOT imitate -- and what therefore shows up as kernel-vs-faithful-oracle error -- is the kernel's
+# arithmetic inside an op: the packed-fp16 LayerNorm scaling, the degree-5 GELU polynomial, ex2.approx, the order of
+# the fp32 accumulations.  Test infrastructure only.
+def _h(x: Tensor) -> Tensor:
+    return x.to(torch.float16).to(torch.float32)
+
+
+def _b(x: Tensor) -> Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _b2(x: Tensor) -> Tensor:           # bf16 hi + lo: what the embedding GEMM carries for tables and c_noise
+    hi = _b(x)
+    return hi + _b(x - hi)
+
+
+def _ln0(x: Tensor) -> Tensor:          # LayerNorm without affine, eps 1e-5, biased variance
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + 1e-5)
+
+
+def faithful16_gpt_forward(sd, cfg: OracleCfg, states, actions, goals, sigma, uncond: bool = False) -> Tensor:
+    b, t, _ = states.shape
+    G = cfg.goal_len if cfg.goal_conditioned else 0
+    d, H = cfg.d, cfg.n_heads
+    hs = d // H
+    if uncond:
+        goals = torch.zeros_like(goals)
+    cn = (sigma.log() / 4).view(b, 1, 1)
+    pos = sd[P + "pos_emb"][:, :(t + G), :]
+    tw, aw, sw = _b(sd[P + "tok_emb.weight"]), _b(sd[P + "action_emb.weight"]), _b2(sd[P + "sigma_emb.weight"])
+    emb_t = _b2(cn) * sw.view(1, 1, d) + _b2(sd[P + "sigma_emb.bias"]).view(1, 1, d)
+    state_x = _b(states) @ tw.t() + _b2(sd[P + "tok_emb.bias"] + pos[:, G:, :])
+    action_x = _b(actions) @ aw.t() + _b2(sd[P + "action_emb.bias"] + pos[:, G:, :])
+    sa = torch.stack([state_x, action_x], dim=1).permute(0, 2, 1, 3).reshape(b, 2 * t, d)
+    if cfg.goal_conditioned:
+        goal_x = _b(goals) @ tw.t() + _b2(sd[P + "tok_emb.bias"] + pos[:, :G, :])
+        x = torch.cat([emb_t, goal_x, sa], dim=1)
+    else:
+        x = torch.cat([emb_t, sa], dim=1)
+    T = x.shape[1]
+    qscale = math.log2(math.e) / math.sqrt(hs)
+    causal = torch.tril(torch.ones(T, T, dtype=torch.bool))
+    for l in range(cfg.n_layers):
+        pre = f"{P}blocks.{l}."
+        g1, b1_ = sd[pre + "ln1.weight"], sd[pre + "ln1.bias"]
+        a = _h(_ln0(x))
+        wq = _h(sd[pre + "attn.query.weight"] * g1 * qscale)
+        wk, wv = _h(sd[pre + "attn.key.weight"] * g1), _h(sd[pre + "attn.value.weight"] * g1)
+        bq = (sd[pre + "attn.query.bias"] + sd[pre + "attn.query.weight"] @ b1_) * qscale
+        bv = sd[pre + "attn.value.bias"] + sd[pre + "attn.value.weight"] @ b1_
+        q = _h(a @ wq.t() + bq).view(b, T, H, hs).transpose(1, 2)
+        k = _h(a @ wk.t()).view(b, T, H, hs).transpose(1, 2)
+        v = _h(a @ wv.t()).view(b, T, H, hs).transpose(1, 2)
+        s = (q @ k.transpose(-2, -1)).masked_fill(~causal, float("-inf"))
+        p = torch.exp2(s - s.max(-1, keepdim=True).values)
+        p = _h(p / p.sum(-1, keepdim=True))
+        y = _h(p @ v).transpose(1, 2).reshape(b, T, d)
+        wp = sd[pre + "attn.proj.weight"]
+        x = x + y @ _h(wp).t() + (sd[pre + "attn.proj.bias"] + wp @ bv)
+        g2, b2_ = sd[pre + "ln2.weight"], sd[pre + "ln2.bias"]
+        a = _h(_ln0(x))
+        w1, w2 = sd[pre + "mlp.0.weight"], sd[pre + "mlp.2.weight"]
+        u4 = _h(a @ _h(w1 * g2 * 0.25).t()) + _h((sd[pre + "mlp.0.bias"] + w1 @ b2_) * 0.25)      # x / 4, fp16 add
+        u4 = _h(u4)
+        hact = _h(F.gelu(4.0 * u4) * 0.25)                                                         # gelu(x) / 4 in fp16
+        x = x + hact @ _h(w2 * 4.0).t() + sd[pre + "mlp.2.bias"]
+    a = _h(_ln0(x))[:, G + 1:, :].reshape(b, t, 2, d)[:, :, 1]
+    wh = sd[P + "action_pred.weight"]
+    return a @ _h(wh * sd[P + "ln_f.weight"]).t() + (sd[P + "action_pred.bias"] + wh @ sd[P + "ln_f.bias"])
+
+
+def faithful16_denoiser_forward(sd, cfg: OracleCfg, state, action, goal, sigma, **kwargs) -> Tensor:
+    c_skip, c_out, c_in = [append_dims(x, action.ndim) for x in get_scalings(sigma, cfg.sigma_data)]
+    return faithful16_gpt_forward(sd, cfg, state, action * c_in, goal, sigma, **kwargs) * c_out + action * c_skip

@@ -293,6 +293,51 @@ def gen_loss_dropout(ns):
         save(name, cfg, seed, sd, **arrays)
 
 
+CKPT_CASES = (  # name, shipped checkpoint dir, config, layers kept
+    ("ckpt_push", "trained_models/block_push/c_beso_1", "BLOCKPUSH_CKPT", None),
+    ("ckpt_kitchen2", "trained_models/kitchen/c_beso_1", "KITCHEN_CKPT", 2),
+)
+
+
+def gen_real_checkpoints(ns):
+    """TRAINED weights (the reference's shipped EMA checkpoints, trained_models/*/c_beso_1/model_state_dict.pth) through
+    the unmodified reference: forward, unconditional forward, 3-step DDIM and 3-step Euler-ancestral.  So that the
+    weights can travel as a fixture they are rounded to fp16 (stored as fp16, widened back to fp32 before the reference
+    and every implementation under test load them: the same values everywhere); the kitchen model (9.4 M parameters)
+    additionally keeps only its first two of six blocks.  Trained weights have the heavy-tailed statistics that make
+    16-bit operand error 5x larger than on N(0, 0.02) initialisations."""
+    import dataclasses
+    from beso_b200 import config as C
+    gs = ns.gc_sampling
+    for name, rel, cfg_name, keep_layers in CKPT_CASES:
+        cfg = getattr(C, cfg_name)
+        sd = torch.load(os.path.join(ref_import.REF_ROOT, rel, "model_state_dict.pth"), map_location="cpu")
+        if keep_layers is not None:
+            cfg = dataclasses.replace(cfg, n_layers=keep_layers)
+            sd = {k: v for k, v in sd.items() if not (k.startswith("inner_model.blocks.") and int(k.split(".")[2]) >= keep_layers)}
+        sd = {k: (v.to(torch.float16).to(torch.float32) if not k.endswith("attn.mask") else v.float()) for k, v in sd.items()}
+        m = ref_import.make_reference_model(ns, cfg)
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        x = synthetic_inputs(cfg, 6, seed=900)
+        with torch.no_grad():
+            out = m(x["state"], x["action"], x["goal"], x["sigma"])
+            out_u = m(x["state"], x["action"], x["goal"], x["sigma"], uncond=True)
+            sig = gs.get_sigmas_exponential(3, 0.05, 1.0)
+            ddim = gs.sample_ddim(m, x["state"], x["noise"], x["goal"], sig, disable=True)
+            torch.manual_seed(901)
+            noise = torch.stack([torch.randn_like(x["noise"]) for _ in range(3)])
+            torch.manual_seed(901)
+            anc = gs.sample_euler_ancestral(m, x["state"], x["noise"], x["goal"], sig, disable=True)
+        arrays = dict(state=x["state"], action=x["action"], goal=x["goal"], sigma=x["sigma"], x_t=x["noise"], out=out,
+                      out_uncond=out_u, sigmas_3=sig, ddim_3=ddim, noise_3=noise, euler_ancestral_3=anc)
+        meta = dict(cfg_dict(cfg), checkpoint=rel, kept_layers=keep_layers, torch=torch.__version__)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=np.array(repr(meta)),
+                            **{k: v.numpy() for k, v in arrays.items()},
+                            **{"w::" + k: v.to(torch.float16).numpy() for k, v in sd.items() if not k.endswith("attn.mask")})
+        print("wrote", name, {k: tuple(v.shape) for k, v in arrays.items()}, f"{sum(v.numel() for v in sd.values()) / 1e6:.2f} M weights")
+
+
 WINDOW_MODES = {
     "plain": dict(window=5),
     "future": dict(window=5, future_conditional=True, min_future_sep=1, future_seq_len=2),
@@ -399,6 +444,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "dpm_solver":
         gen_dpm_solver(ns)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "real_ckpt":       # added in round 2
+        gen_real_checkpoints(ns)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "loss_dropout":    # added in round 2
         gen_loss_dropout(ns)
         return
@@ -409,6 +457,7 @@ def main():
     gen_samplers(ns)
     gen_loss(ns)
     gen_loss_dropout(ns)
+    gen_real_checkpoints(ns)
 
 
 if __name__ == "__main__":

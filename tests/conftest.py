@@ -54,3 +54,20 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def load_checkpoint_golden(name):
+    """tests/golden/ckpt_*.npz: trained weights of a shipped reference checkpoint (rounded to fp16 so that they can
+    travel, widened back to fp32 here exactly as oracle/make_golden.py did before the reference loaded them) plus the
+    reference's outputs.  Returns (ModelConfig, meta, arrays, state_dict without the attn.mask buffers)."""
+    cfg, meta, arrays = load_golden(name)
+    sd = {k[3:]: v.to(torch.float32) for k, v in arrays.items() if k.startswith("w::")}
+    arrays = {k: v for k, v in arrays.items() if not k.startswith("w::")}
+    return cfg, meta, arrays, sd
+
+
+def with_masks(model, sd):
+    """state_dict for a strict load: the checkpoint weights plus the model's own (deterministic) attn.mask buffers."""
+    full = {k: v for k, v in model.state_dict().items() if k.endswith("attn.mask")}
+    full.update(sd)
+    return full

@@ -256,3 +256,22 @@ def test_dropout_masks_replay_the_reference_generator(name):
         got = flat if flat.numel() <= 4096 else flat[::97][:4096]
         want = a["grad::" + n]
         torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-6 * float(want.abs().max()) + 2e-8)
+
+
+@pytest.mark.parametrize("name", ["ckpt_push", "ckpt_kitchen2"])
+def test_oracle_reproduces_trained_checkpoint_fixture(name):
+    """The checkpoint fixtures (trained weights + the reference's outputs) are self-consistent: the oracle run on the
+    stored weights gives the stored outputs, with or without /root/reference."""
+    from conftest import load_checkpoint_golden
+    cfg, meta, a, sd = load_checkpoint_golden(name)
+    oc = to_oracle_cfg(cfg)
+    with torch.no_grad():
+        out = O.denoiser_forward(sd, oc, a["state"], a["action"], a["goal"], a["sigma"])
+        ddim = O.sample_ddim(sd, oc, a["state"], a["x_t"], a["goal"], a["sigmas_3"])
+        anc = O.sample_euler_ancestral(sd, oc, a["state"], a["x_t"], a["goal"], a["sigmas_3"], noise=a["noise_3"])
+        f16 = O.faithful16_denoiser_forward(sd, oc, a["state"], a["action"], a["goal"], a["sigma"])
+    for got, key in ((out, "out"), (ddim, "ddim_3"), (anc, "euler_ancestral_3")):   # fp32 round-off: ATen blocks its GEMMs
+        torch.testing.assert_close(got, a[key], rtol=1e-5, atol=2e-6)               # by thread count
+    # the 16-bit-faithful oracle is a perturbation of the fp32 one of the size 16-bit operands cause, no more
+    err = (f16 - a["out"]).abs().max()
+    assert 1e-6 < float(err) < 3e-2

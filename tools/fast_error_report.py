@@ -1,4 +1,6 @@
-"""Measured error of the FAST mode against the reference golden fixtures (forward, samplers).  python tools/fast_error_report.py"""
+"""Measured error of the tensor-core kernel's two arithmetic modes on the B200: against the reference goldens (random
+init and TRAINED checkpoint weights) and, for the fp16 mode, against the 16-bit-faithful oracle (the reference with the
+kernel's operand roundings, oracle/beso_oracle.py).  python tools/fast_error_report.py > profiles/r2_error_report.txt"""
 import glob
 import os
 import sys
@@ -8,33 +10,76 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from conftest import golden_weights, load_golden                 # noqa: E402
+from conftest import golden_weights, load_checkpoint_golden, load_golden, to_oracle_cfg, with_masks  # noqa: E402
 from beso_b200 import sampling                                   # noqa: E402
 from beso_b200.denoiser import build_denoiser                    # noqa: E402
+from oracle import beso_oracle as O                              # noqa: E402
 
 dev = torch.device("cuda:0")
-worst = 0.0
+
+
+def line(tag, got, want):
+    err = (got - want).abs()
+    need = (err / (1e-3 * want.abs() + 1e-5)).max()
+    print(f"{tag}: max|err| {float(err.max()):.2e} mean {float(err.mean()):.2e} max|ref| {float(want.abs().max()):.2f} "
+          f"inside 1e-3/1e-5: {float((err <= 1e-5 + 1e-3 * want.abs()).float().mean()):.3f} worst err/tol {float(need):.1f}")
+    return float(err.max())
+
+
+def models_for(cfg, sd, strict_masks=False):
+    out = {}
+    for mode in ("precise", "fast"):
+        m = build_denoiser(cfg, dev, mode=mode)
+        m.load_state_dict(with_masks(m, sd) if strict_masks else sd, strict=True)
+        m.eval()
+        if mode == "fast" and not m.fast_supported():
+            continue
+        out[mode] = m
+    return out
+
+
+print("== forward goldens (random-init weights, N(0, 0.02)) ==")
 for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "fwd_*.npz"))):
     name = os.path.basename(path)[:-4]
     cfg, meta, a = load_golden(name)
-    try:
-        m = build_denoiser(cfg, dev, mode="fast", state_dict=golden_weights(cfg, meta))
-        out = m(a["state"].to(dev), a["action"].to(dev), a["goal"].to(dev), a["sigma"].to(dev)).cpu()
-    except Exception as e:                                       # shapes the fast kernel does not support
-        print(f"{name}: skipped ({type(e).__name__})")
-        continue
-    err = (out - a["out"]).abs()
-    need = (err / (1e-3 * a["out"].abs() + 1e-5)).max()
-    print(f"{name}: max|err| {float(err.max()):.2e} mean {float(err.mean()):.2e} max|ref| {float(a['out'].abs().max()):.2f} "
-          f"inside 1e-3/1e-5: {float((err <= 1e-5 + 1e-3 * a['out'].abs()).float().mean()):.2f} worst err/(tol) {float(need):.1f}")
-    worst = max(worst, float(err.max()))
+    sd = golden_weights(cfg, meta)
+    g = {k: v.to(dev) for k, v in a.items() if isinstance(v, torch.Tensor)}
+    for mode, m in models_for(cfg, sd).items():
+        kind = "tensor-core split" if (mode == "precise" and m.fast_supported()) else ("CUDA-core fp32" if mode == "precise" else "tensor-core fp16")
+        out = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
+        line(f"{name} [{mode}: {kind}] vs reference", out, a["out"])
+        if mode == "fast":
+            with torch.no_grad():
+                f16 = O.faithful16_denoiser_forward(sd, to_oracle_cfg(cfg), a["state"], a["action"], a["goal"], a["sigma"])
+            line(f"{name} [fast] vs 16-bit-faithful oracle", out, f16)
+            line(f"{name} (16-bit-faithful oracle vs reference)", f16, a["out"])
+
+print("== TRAINED checkpoint weights (trained_models/*/c_beso_1, fp16-rounded fixture) ==")
+for name in ("ckpt_push", "ckpt_kitchen2"):
+    cfg, meta, a, sd = load_checkpoint_golden(name)
+    g = {k: v.to(dev) for k, v in a.items() if isinstance(v, torch.Tensor)}
+    for mode, m in models_for(cfg, sd, strict_masks=True).items():
+        kind = "tensor-core split" if (mode == "precise" and m.fast_supported()) else ("CUDA-core fp32" if mode == "precise" else "tensor-core fp16")
+        out = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
+        line(f"{name} forward [{mode}: {kind}] vs reference", out, a["out"])
+        got = sampling.sample_ddim(m, g["state"], g["x_t"], g["goal"], a["sigmas_3"]).cpu()
+        line(f"{name} ddim_3 [{mode}] vs reference", got, a["ddim_3"])
+        got = sampling.sample_euler_ancestral(m, g["state"], g["x_t"], g["goal"], a["sigmas_3"], noise=g["noise_3"]).cpu()
+        line(f"{name} euler_ancestral_3 [{mode}] vs reference", got, a["euler_ancestral_3"])
+        if mode == "fast":
+            full = with_masks(m, sd)
+            with torch.no_grad():
+                f16 = O.faithful16_denoiser_forward(full, to_oracle_cfg(cfg), a["state"], a["action"], a["goal"], a["sigma"])
+            line(f"{name} forward [fast] vs 16-bit-faithful oracle", out, f16)
+            line(f"{name} (16-bit-faithful oracle vs reference)", f16, a["out"])
+
+print("== samplers (K256 goldens) ==")
 cfg, meta, a = load_golden("samplers_K256")
-m = build_denoiser(cfg, dev, mode="fast", state_dict=golden_weights(cfg, meta))
 g = {k: v.to(dev) for k, v in a.items() if isinstance(v, torch.Tensor)}
-for n in (1, 3, 5):
-    for s in ("ddim", "euler", "heun"):
-        got = sampling.SAMPLERS[s](m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{n}"]).cpu()
-        err = (got - a[f"{s}_{n}"]).abs()
-        worst = max(worst, float(err.max()))
-        print(f"{s}_{n}: max|err| {float(err.max()):.2e} mean {float(err.mean()):.2e}")
-print(f"worst max|err| {worst:.2e}")
+for mode, m in models_for(cfg, golden_weights(cfg, meta)).items():
+    worst = 0.0
+    for n in (1, 3, 5):
+        for s in ("ddim", "euler", "heun"):
+            got = sampling.SAMPLERS[s](m, g["state"], g["x_t"], g["goal"], a[f"sigmas_{n}"]).cpu()
+            worst = max(worst, float((got - a[f"{s}_{n}"]).abs().max()))
+    print(f"[{mode}] ddim / euler / heun at 1, 3, 5 steps: worst max|err| {worst:.2e}")
