@@ -1,6 +1,7 @@
 """Measured error of the tensor-core kernel's two arithmetic modes on the B200: against the reference goldens (random
 init and TRAINED checkpoint weights) and, for the fp16 mode, against the 16-bit-faithful oracle (the reference with the
-kernel's operand roundings, oracle/beso_oracle.py).  python tools/fast_error_report.py > profiles/r2_error_report.txt"""
+kernel's operand roundings, oracle/beso_oracle.py).  A checker script, not a pytest module (it lives under tests/
+because only tests/ may import the oracle).  python tests/report_errors.py > profiles/r2_error_report.txt"""
 import glob
 import os
 import sys

@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "simt": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=3e-3, atol=3e-3)}
 # fast mode against the 16-bit-faithful oracle (the reference with the kernel's operand roundings): measured max |err|
-# 4e-4 (profiles/r2_error_report.txt); SURVEY.md H1 asked for 1e-3
+# 5.7e-4 on random-init and 7.6e-4 on trained weights (profiles/r2_error_report.txt); SURVEY.md H1 asked for 1e-3
 TOL_FAITHFUL = dict(rtol=1e-3, atol=1e-3)
 # shapes the tensor-core kernel must take (checked against what the library reports): every d <= 256 fixture with a
 # linear head, including the block-push checkpoint shape (d = 240, 12 heads of 20) and the no-goal model (d = 64)
@@ -467,7 +467,10 @@ def test_trained_checkpoint_weights_match_reference(name, cuda_device):
         full = with_masks(m, sd)
         m.load_state_dict(full, strict=True)
         m.eval()
-        tol = TOL[mode]
+        # fp16 operands on TRAINED weights: the 16-bit-faithful oracle itself sits 2.7e-3 from the fp32 reference and the
+        # kernel 3.1e-3 (forward) / 7.9e-3 (3 ancestral steps) (profiles/r2_error_report.txt) -- 5x the random-init
+        # figures, as SURVEY.md H1 measured for bf16 autocast; its bound for the fast mode is 2e-2
+        tol = TOL[mode] if mode != "fast" else dict(rtol=2e-2, atol=2e-2)
         out = m(g["state"], g["action"], g["goal"], g["sigma"])
         torch.testing.assert_close(out.cpu(), a["out"], **tol)
         torch.testing.assert_close(m(g["state"], g["action"], g["goal"], g["sigma"], uncond=True).cpu(), a["out_uncond"], **tol)
