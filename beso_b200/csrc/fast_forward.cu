@@ -184,7 +184,10 @@ __device__ __forceinline__ void walk_eval(int L, F&& f) {
 }
 
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void attn_sync() { asm volatile("bar.sync 2, 320;" ::: "memory"); }   // compute + helper warps
+// compute + helper warps.  Out of line on purpose: the two roles then execute the SAME bar instruction (one program
+// counter), which is what compute-sanitizer's synccheck expects of the participants of a barrier -- inlined, the tool
+// reports the legal "same named barrier from two call sites" pattern as divergence.
+__device__ __noinline__ void attn_sync() { asm volatile("bar.sync 2, 320;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
