@@ -591,9 +591,11 @@ __device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int 
     else { if (hi) attention_item<2, true, HSP, SPLIT>(sbase, lane, s * T, mt, T, co); else attention_item<2, false, HSP, SPLIT>(sbase, lane, s * T, mt, T, co); }
   }
 }
-__device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T, int hsp) {
-  if (hsp == 64) attention_head_t<64, false>(sbase, awarp, lane, S, T);
-  else attention_head_t<32, false>(sbase, awarp, lane, S, T);
+// The padded head size is a template parameter of the kernel: only the attention code of the model's head size is in
+// the kernel image (the fused kernel is ~13 k instructions; its hot paths have to stay resident in the instruction cache).
+template <int HSP>
+__device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T) {
+  attention_head_t<HSP, false>(sbase, awarp, lane, S, T);
 }
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
@@ -754,9 +756,9 @@ __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
 // Causal attention of the precise mode: the mma.sync kernel of the fp16 mode with every product split three ways
 // (attention_item<..., SPLIT = true>): the operands come out of shared memory once per 16 x 8 tile, which keeps the
 // attention phase off the shared-memory port the tensor pipe is streaming its operands through.
-__device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T, int hsp) {
-  if (hsp == 64) attention_head_t<64, true>(sbase, awarp, lane, S, T);
-  else attention_head_t<32, true>(sbase, awarp, lane, S, T);
+template <int HSP>
+__device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T) {
+  attention_head_t<HSP, true>(sbase, awarp, lane, S, T);
 }
 
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
@@ -956,6 +958,7 @@ __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int 
 
 // A <- embedding-GEMM input rows: [obs atom | misc atom] (see file header), atoms 2..3 untouched.
 // One (row, atom) per thread; all global loads of a row are issued before any is used.
+template <bool PREC>
 __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask e, int obs, int act, uint32_t flags,
                                                float sigma_data, const float* xsrc, const float* sigv,
                                                const float* in_tab, const float* goal_keep) {
@@ -986,7 +989,7 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
         for (int i = 0; i < 64; ++i) if (i < obs) v[i] = __fmul_rn(v[i], __ldg(goal_keep + i));
       }
     }
-    if (e.part >= 0) {
+    if constexpr (PREC) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) if (e.part) v[i] -= __half2float(__float2half_rn(v[i]));
 #pragma unroll
@@ -1012,16 +1015,16 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
         if (e.valid) {
           if (k < kOneHot0) {
             if (e.xoff >= 0 && k < act) x = xsrc[e.xoff + k] * c_in;
-            else if (e.part >= 0) { if (e.tok == 0 && k == act) x = cn; }       // split below: [cn] . [sigma_emb.w]
+            else if (PREC) { if (e.tok == 0 && k == act) x = cn; }              // split below: [cn] . [sigma_emb.w]
             else if (e.tok == 0 && k >= act && k < act + 3) x = (k == act + 1) ? (cn - cn_hi) : cn_hi;
-          } else if (k == hot || (k == hot + 1 && e.part < 0)) {
+          } else if (k == hot || (k == hot + 1 && !PREC)) {
             x = 1.0f;
           }
         }
-        if (e.part == 1) x -= __half2float(__float2half_rn(x));
+        if (PREC && e.part == 1) x -= __half2float(__float2half_rn(x));
         v[i] = x;
       }
-      if (e.part >= 0) st_chunk_h(atom, e.row, ch, v); else st_chunk(atom, e.row, ch, v);
+      if constexpr (PREC) st_chunk_h(atom, e.row, ch, v); else st_chunk(atom, e.row, ch, v);
     }
   }
   fence_async_smem();
@@ -1093,7 +1096,7 @@ __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p,
   compute_sync();
   const EmbedTask etask = make_embed_task<PREC>(c, p, tile);
   stamp<DBG>(c);
-  build_embed_input(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv, sa.in_tab, sa.goal_keep);
+  build_embed_input<PREC>(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv, sa.in_tab, sa.goal_keep);
   stamp<DBG>(c);
 }
 
@@ -1224,7 +1227,7 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
 // is free again when both CTAs' MMAs have read it (multicast commits).  Halves the L2 -> SM request traffic,
 // which at full-chip scale is within a factor 1.5 of the L2 throughput cap.
 // PREC = true: fp32-equivalent mode (split operands, 64 sequence rows per tile; see the PREC section above).
-template <int CG, bool DBG, int MC, bool PREC>
+template <int CG, bool DBG, int MC, bool PREC, int HSP>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
   static_assert(!PREC || (CG == 1 && MC == 1), "the precise mode runs single-CTA MMAs");
@@ -1508,8 +1511,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       attn_sync();
       spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
       y_phase ^= 1u;
-      if constexpr (PREC) attention_head_p(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T, p.hsp);
-      else attention_head(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T, p.hsp);
+      if constexpr (PREC) attention_head_p<HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
+      else attention_head<HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -1570,8 +1573,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
             c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
             stamp<DBG>(c);
-            if constexpr (PREC) attention_head_p(sbase, c.ctid >> 5, lane, p.S, p.T, p.hsp);
-            else attention_head(sbase, c.ctid >> 5, lane, p.S, p.T, p.hsp);
+            if constexpr (PREC) attention_head_p<HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
+            else attention_head<HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
             fence_async_smem();
             c.arrive(B_Y_READY);
             stamp<DBG>(c);
@@ -2035,6 +2038,18 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   const bool cfg = flags & BESO_FLAG_CFG;
   if (cfg) p.S &= ~1;                                         // cond / uncond pairs share a tile
   if (p.S < 1) { set_error("sequence does not fit a 128-row tile"); return BESO_E_UNSUPPORTED; }
+  if (cfg && p.S < 2) { set_error("a cond / uncond pair does not fit a tile"); return BESO_E_UNSUPPORTED; }
+  // A tile's time hardly depends on how many of its rows are used (one thread per row, M = 128 MMAs either way) except
+  // for attention, which is per sequence.  So among the packings that need the same number of waves over the SMs take
+  // the one with the FEWEST sequences per tile: it spreads the batch over more SMs (BASELINE config 2: 512 sequences
+  // are 103 tiles of 5 or 128 tiles of 4 on 148 SMs -- one wave either way, with 20 % less attention work per tile).
+  {
+    const int step = cfg ? 2 : 1, s_max = p.S;
+    auto waves = [&](int S) { const int per = cfg ? S / 2 : S; const int tiles = (B + per - 1) / per; return (tiles + sm_count - 1) / sm_count; };
+    const int w_min = waves(s_max);
+    for (int S = step; S < s_max; S += step)
+      if (waves(S) == w_min) { p.S = S; break; }
+  }
   const int per_tile = cfg ? p.S / 2 : p.S;
   p.n_tiles = (B + per_tile - 1) / per_tile;
   p.B = B;
@@ -2050,49 +2065,51 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.state = state; p.goal = goal; p.xin = x; p.sigma = sigma; p.out = out;
   p.trace = g_trace;
   p.timeline = g_timeline;
-  static bool configured = false;
-  if (!configured) {
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<2, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    BESO_CUDA(cudaFuncSetAttribute(fast_sample_kernel<1, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes + 1024));
-    configured = true;
-  }
   // Single-CTA MMAs (CG = 1) are the default: measured faster than CTA pairs on this workload (the pair mode
   // halves L2 -> SMEM weight traffic but pays remote-arrive latency on every compute -> MMA hand-off; see
-  // profiles/).  BESO_FAST_CG=2 selects the cta_group::2 path, kept parity-tested for the next round.
+  // profiles/).  BESO_FAST_CG=2 selects the cta_group::2 path, kept parity-tested.
   static const int forced_cg = [] { const char* e = getenv("BESO_FAST_CG"); return e ? atoi(e) : 0; }();
-  const bool pairs_ok = !prec && p.npass == kH && p.n_tiles >= 2;   // the pair modes replay the fixed 4-pass group table
+  const bool pairs_ok = !prec && p.npass == kH && hsp == 64 && p.n_tiles >= 2;   // the pair modes replay the fixed 4-pass group table
   const int cg = (forced_cg == 2 && pairs_ok) ? 2 : 1;
   // BESO_FAST_MC=2: independent CTAs in clusters of 2 sharing the weight stream by TMA multicast
   static const int forced_mc = [] { const char* e = getenv("BESO_FAST_MC"); return e ? atoi(e) : 0; }();
   const bool dbg = p.trace != nullptr || p.timeline != nullptr;
   const int mc = (cg == 1 && !dbg && forced_mc == 2 && pairs_ok) ? 2 : 1;
-  if (cg == 2 || mc == 2) {
-    const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
+  const int smem = (int)kSmemBytes + 1024;
+  auto launch = [&](auto kernel, int grid, bool cluster) -> int {
+    BESO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // cheap, idempotent
     cudaLaunchConfig_t cfgl{};
-    cfgl.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    cfgl.gridDim = dim3(grid);
     cfgl.blockDim = dim3(kThreads);
-    cfgl.dynamicSmemBytes = kSmemBytes + 1024;
+    cfgl.dynamicSmemBytes = smem;
     cfgl.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfgl.attrs = attr; cfgl.numAttrs = 1;
-    if (cg == 2) BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<2, false, 1, false>, p, sa));
-    else BESO_CUDA(cudaLaunchKernelEx(&cfgl, fast_sample_kernel<1, false, 2, false>, p, sa));
+    cfgl.attrs = attr; cfgl.numAttrs = cluster ? 1 : 0;
+    BESO_CUDA(cudaLaunchKernelEx(&cfgl, kernel, p, sa));
+    return BESO_OK;
+  };
+  int rc;
+  if (cg == 2 || mc == 2) {
+    const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
+    const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    rc = cg == 2 ? launch(fast_sample_kernel<2, false, 1, false, 64>, grid, true) : launch(fast_sample_kernel<1, false, 2, false, 64>, grid, true);
   } else {
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    if (prec) {
-      if (dbg) fast_sample_kernel<1, true, 1, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
-      else fast_sample_kernel<1, false, 1, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
-    } else {
-      if (dbg) fast_sample_kernel<1, true, 1, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
-      else fast_sample_kernel<1, false, 1, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p, sa);
+    const int sel = (prec ? 4 : 0) | (dbg ? 2 : 0) | (hsp == 32 ? 1 : 0);
+    switch (sel) {
+      case 0: rc = launch(fast_sample_kernel<1, false, 1, false, 64>, grid, false); break;
+      case 1: rc = launch(fast_sample_kernel<1, false, 1, false, 32>, grid, false); break;
+      case 2: rc = launch(fast_sample_kernel<1, true, 1, false, 64>, grid, false); break;
+      case 3: rc = launch(fast_sample_kernel<1, true, 1, false, 32>, grid, false); break;
+      case 4: rc = launch(fast_sample_kernel<1, false, 1, true, 64>, grid, false); break;
+      case 5: rc = launch(fast_sample_kernel<1, false, 1, true, 32>, grid, false); break;
+      case 6: rc = launch(fast_sample_kernel<1, true, 1, true, 64>, grid, false); break;
+      default: rc = launch(fast_sample_kernel<1, true, 1, true, 32>, grid, false); break;
     }
   }
+  if (rc) return rc;
   ++g_kernel_launches;
   BESO_CUDA(cudaGetLastError());
   return BESO_OK;

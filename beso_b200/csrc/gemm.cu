@@ -330,6 +330,13 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
       float* outp = ka.partial ? ka.partial + (size_t)t.ks * g.M * g.N : g.C;
       const int ldo = ka.partial ? g.N : g.ldc;
       const bool plain = ka.partial != nullptr;
+      // this thread's part of the coalesced phase: row (lane >> 3) + 4 i of the warp's 32, columns 4 (lane & 7) .. + 3 of
+      // every 32-column chunk; everything that does not depend on i or c is computed once per tile
+      const int r0 = lane >> 3, cq = (lane & 7) * 4;
+      const int m_first = t.m0 + warp * 32 + r0;
+      const bool use_bias = !plain && g.bias != nullptr, use_mul = !plain && g.mul != nullptr, use_res = !plain && g.resid != nullptr,
+                 use_acc = !plain && g.accumulate != 0, use_gelu = !plain && g.gelu_out != nullptr;
+      const uint32_t rd_s = stage_s + (uint32_t)r0 * kStagePitch + (uint32_t)cq * 4u;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         if (n_base + c * 32 >= g.N) break;                      // warp-uniform: the rest of the tile is padding
@@ -347,43 +354,55 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_kernel(const __grid_constan
                  __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
         __syncwarp();
         // coalesced phase: 8 lanes cover the 128 bytes of a row segment, 4 rows per instruction
+        const int n = n_base + c * 32 + cq;
+        float4 x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3), m = t.m0 + warp * 32 + r, n = n_base + c * 32 + (lane & 7) * 4;
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                       : "r"(stage_s + (uint32_t)r * kStagePitch + (uint32_t)(lane & 7) * 16u));
-          if (m >= g.M || n >= g.N) continue;
-          float xv[4] = {x.x, x.y, x.z, x.w};
-          float* cp = outp + (size_t)m * ldo + n;
+        for (int i = 0; i < 8; ++i)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                       : "r"(rd_s + (uint32_t)i * 4u * kStagePitch));
+        __syncwarp();                                            // the staging buffer may be overwritten by the next chunk
+        if (n < g.N) {
           if (ka.vec_c && n + 4 <= g.N) {
-            if (!plain) {
-              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n)); xv[0] += b.x; xv[1] += b.y; xv[2] += b.z; xv[3] += b.w; }
-              if (g.mul) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.mul + (size_t)m * g.ldm + n)); xv[0] *= b.x; xv[1] *= b.y; xv[2] *= b.z; xv[3] *= b.w; }
-              if (g.resid) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.resid + (size_t)m * g.ldr + n)); xv[0] += b.x; xv[1] += b.y; xv[2] += b.z; xv[3] += b.w; }
-              if (g.accumulate) { const float4 b = *reinterpret_cast<const float4*>(cp); xv[0] += b.x; xv[1] += b.y; xv[2] += b.z; xv[3] += b.w; }
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+            float* cp = outp + (size_t)m_first * ldo + n;
+            const float* mp = use_mul ? g.mul + (size_t)m_first * g.ldm + n : nullptr;
+            const float* rp = use_res ? g.resid + (size_t)m_first * g.ldr + n : nullptr;
+            float* gp = use_gelu ? g.gelu_out + (size_t)m_first * g.ldg + n : nullptr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (m_first + 4 * i < g.M) {
+                float4 y = make_float4(x[i].x + b4.x, x[i].y + b4.y, x[i].z + b4.z, x[i].w + b4.w);
+                if (use_mul) { const float4 q = __ldg(reinterpret_cast<const float4*>(mp + (size_t)(4 * i) * g.ldm)); y.x *= q.x; y.y *= q.y; y.z *= q.z; y.w *= q.w; }
+                if (use_res) { const float4 q = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * g.ldr)); y.x += q.x; y.y += q.y; y.z += q.z; y.w += q.w; }
+                float4* o = reinterpret_cast<float4*>(cp + (size_t)(4 * i) * ldo);
+                if (use_acc) { const float4 q = *o; y.x += q.x; y.y += q.y; y.z += q.z; y.w += q.w; }
+                *o = y;
+                if (use_gelu)
+                  *reinterpret_cast<float4*>(gp + (size_t)(4 * i) * g.ldg) = make_float4(gelu_erf_g(y.x), gelu_erf_g(y.y), gelu_erf_g(y.z), gelu_erf_g(y.w));
+              }
             }
-            *reinterpret_cast<float4*>(cp) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-            if (!plain && g.gelu_out)
-              *reinterpret_cast<float4*>(g.gelu_out + (size_t)m * g.ldg + n) =
-                  make_float4(gelu_erf_g(xv[0]), gelu_erf_g(xv[1]), gelu_erf_g(xv[2]), gelu_erf_g(xv[3]));
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e >= g.N) break;
-              float y = xv[e];
-              if (!plain) {
-                if (g.bias) y += __ldg(g.bias + n + e);
-                if (g.mul) y *= __ldg(g.mul + (size_t)m * g.ldm + n + e);
-                if (g.resid) y += __ldg(g.resid + (size_t)m * g.ldr + n + e);
-                if (g.accumulate) y += cp[e];
+            for (int i = 0; i < 8; ++i) {                        // static indices: x stays in registers
+              const int m = m_first + 4 * i;
+              if (m >= g.M) continue;
+              const float xv[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+              float* cp = outp + (size_t)m * ldo + n;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e >= g.N) break;
+                float y = xv[e];
+                if (use_bias) y += __ldg(g.bias + n + e);
+                if (use_mul) y *= __ldg(g.mul + (size_t)m * g.ldm + n + e);
+                if (use_res) y += __ldg(g.resid + (size_t)m * g.ldr + n + e);
+                if (use_acc) y += cp[e];
+                cp[e] = y;
+                if (use_gelu) g.gelu_out[(size_t)m * g.ldg + n + e] = gelu_erf_g(y);
               }
-              cp[e] = y;
-              if (!plain && g.gelu_out) g.gelu_out[(size_t)m * g.ldg + n + e] = gelu_erf_g(y);
             }
           }
         }
-        __syncwarp();
       }
     }
   }
