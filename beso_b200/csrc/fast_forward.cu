@@ -436,8 +436,10 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // SPLIT (the precise mode): staging rows [0, 64) hold the fp16 hi image of Q|K|V and rows [64, 128) the lo image;
 // every product is three mma.sync (hi.hi + lo.hi + hi.lo, fp32 accumulate), the probabilities are split the same way
 // and the output goes to the hi / lo rows of the Y atom.
-template <int NKT, bool HI, int HSP, bool SPLIT>
-__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co) {
+// NH = 2: two warps share one item -- both compute the scores and the softmax, each the P V product of half of the
+// output columns (`half`); used when a tile has so few (sequence, query tile) items that warps would idle.
+template <int NKT, bool HI, int HSP, bool SPLIT, int NH>
+__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co, int half) {
   const uint32_t qkv = sbase + kSmQkv + (uint32_t)co * 2u;
   constexpr int KS = HSP / 16;                   // 16-wide k steps over the head dimension
   constexpr int kLastRow = SPLIT ? 63 : kRows - 1;
@@ -530,7 +532,8 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     }
   }
   // ---- O = P V ----
-  constexpr int NO = HSP / 8;                    // 8-wide output column tiles
+  constexpr int NO = HSP / 8 / NH;               // 8-wide output column tiles of this warp
+  const int nfirst = half * NO;                  // first of them inside the head
   float o[NO][4];
 #pragma unroll
   for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
@@ -540,13 +543,13 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
 #pragma unroll
     for (int np = 0; np < NO / 2; ++np) {        // pairs of 8-wide output column tiles
       uint32_t vb[4];
-      ldmatrix_x4_trans(qkv + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
+      ldmatrix_x4_trans(qkv + r * kQkvStride + (128 + (nfirst + np * 2) * 8 + (lane >> 4) * 8) * 2, vb);
       mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);
       mma_16816(o[np * 2 + 1], pa[kt], vb[2], vb[3]);
       if constexpr (SPLIT) {
         mma_16816(o[np * 2], pl[kt], vb[0], vb[1]);                             // lo . hi
         mma_16816(o[np * 2 + 1], pl[kt], vb[2], vb[3]);
-        ldmatrix_x4_trans(qkv + kLo + r * kQkvStride + (128 + np * 16 + (lane >> 4) * 8) * 2, vb);
+        ldmatrix_x4_trans(qkv + kLo + r * kQkvStride + (128 + (nfirst + np * 2) * 8 + (lane >> 4) * 8) * 2, vb);
         mma_16816(o[np * 2], pa[kt], vb[0], vb[1]);                             // hi . lo
         mma_16816(o[np * 2 + 1], pa[kt], vb[2], vb[3]);
       }
@@ -560,7 +563,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   }
   const uint32_t y_lo = sbase + kSmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
   const uint32_t y_hi = sbase + kSmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
-  const uint32_t n0 = (uint32_t)co >> 3;         // first 16-byte chunk of this head inside the Y row
+  const uint32_t n0 = ((uint32_t)co >> 3) + (uint32_t)nfirst;   // first 16-byte chunk of this warp's columns inside the Y row
   if (i_lo < T) {
 #pragma unroll
     for (int n = 0; n < NO; ++n) {
@@ -578,18 +581,30 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     }
   }
 }
-template <int HSP, bool SPLIT>
-__device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T) {
+template <int HSP, bool SPLIT, int NH>
+__device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_slots, int half, int lane, int S, int T) {
   constexpr int NSUB = 64 / HSP;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
-  for (int item = awarp; item < S * MT * NSUB; item += kAttnWarps) {
+  for (int item = slot; item < S * MT * NSUB; item += n_slots) {
     const int sub = item % NSUB, it2 = item / NSUB;
     const int mt = MT - 1 - it2 / S, s = it2 % S;     // later query tiles see more keys: schedule them first
     const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
     const int co = sub * HSP;
-    if (mt == 0) { if (hi) attention_item<1, true, HSP, SPLIT>(sbase, lane, s * T, 0, T, co); else attention_item<1, false, HSP, SPLIT>(sbase, lane, s * T, 0, T, co); }
-    else { if (hi) attention_item<2, true, HSP, SPLIT>(sbase, lane, s * T, mt, T, co); else attention_item<2, false, HSP, SPLIT>(sbase, lane, s * T, mt, T, co); }
+    if (mt == 0) { if (hi) attention_item<1, true, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); else attention_item<1, false, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); }
+    else { if (hi) attention_item<2, true, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); else attention_item<2, false, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); }
   }
+}
+template <int HSP, bool SPLIT>
+__device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T) {
+  // The precise mode's tiles hold at most 64 rows = 4 items for the 10 attention warps: pairs of warps share an item.
+  // (Only there: the single-pass fp16 kernel has 8-10 items, and a second item body would only grow its image.)
+  if constexpr (SPLIT) {
+    if (S * ((T + 15) >> 4) * (64 / HSP) * 2 <= kAttnWarps) {
+      attention_items<HSP, SPLIT, 2>(sbase, awarp >> 1, kAttnWarps / 2, awarp & 1, lane, S, T);
+      return;
+    }
+  }
+  attention_items<HSP, SPLIT, 1>(sbase, awarp, kAttnWarps, 0, lane, S, T);
 }
 // The padded head size is a template parameter of the kernel: only the attention code of the model's head size is in
 // the kernel image (the fused kernel is ~13 k instructions; its hot paths have to stay resident in the instruction cache).

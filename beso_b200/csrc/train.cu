@@ -12,6 +12,7 @@
 //
 // Dropout (score_gpts.py:37-38,72,79,109) and the element-wise goal mask of CFG training (:360-371) take their
 // masks from the caller, who draws them with the reference's torch calls in the reference's op order.
+#include <math.h>
 #include <nccl.h>
 #include <string.h>
 
@@ -548,17 +549,27 @@ int nccl_fail(ncclResult_t r, const char* what) {
 
 // One gradient bucket [off, off + n) of the flat buffer is final on the compute stream `st`: all-reduce(sum) it on the
 // communicator's stream (then * scale), behind an event, while `st` goes on with the next layer's backward.
-static int sync_bucket(beso_comm* c, float* grad, size_t off, size_t n, float scale, cudaStream_t st) {
+// A second range (off2, n2) rides in the same NCCL group (one launch).  scale == 1 / world uses the collective's own
+// averaging (ncclAvg); any other scale is a separate pass over the bucket.
+static int sync_bucket(beso_comm* c, float* grad, size_t off, size_t n, float scale, cudaStream_t st, size_t off2 = 0, size_t n2 = 0) {
   if (!c || c->world <= 1 || n == 0) return BESO_OK;
   if (c->next_event >= (int)c->events.size()) { set_error("internal: out of gradient-bucket events"); return BESO_E_INVALID; }
   cudaEvent_t ev = c->events[c->next_event++];
   BESO_CUDA(cudaEventRecord(ev, st));
   BESO_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
-  BESO_NCCL(ncclAllReduce(grad + off, grad + off, n, ncclFloat, ncclSum, c->comm, c->stream));
-  if (scale != 1.0f) {
-    const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
-    scale_kernel<<<grid, 256, 0, c->stream>>>(grad + off, n, scale);
-    ++g_kernel_launches;
+  const bool avg = fabsf(scale * (float)c->world - 1.0f) < 1e-6f;
+  const ncclRedOp_t op = avg ? ncclAvg : ncclSum;
+  BESO_NCCL(ncclGroupStart());
+  BESO_NCCL(ncclAllReduce(grad + off, grad + off, n, ncclFloat, op, c->comm, c->stream));
+  if (n2) BESO_NCCL(ncclAllReduce(grad + off2, grad + off2, n2, ncclFloat, op, c->comm, c->stream));
+  BESO_NCCL(ncclGroupEnd());
+  if (!avg && scale != 1.0f) {
+    for (int k = 0; k < (n2 ? 2 : 1); ++k) {
+      const size_t o = k ? off2 : off, cnt = k ? n2 : n;
+      const int grid = (int)((cnt + 255) / 256 < 1024 ? (cnt + 255) / 256 : 1024);
+      scale_kernel<<<grid, 256, 0, c->stream>>>(grad + o, cnt, scale);
+      ++g_kernel_launches;
+    }
     BESO_CUDA(cudaGetLastError());
   }
   return BESO_OK;
@@ -798,8 +809,7 @@ int train_loss_fwd_bwd(TrainWs*& ws, const beso_model_desc& m, const float* cons
   }
   BESO_CUDA(cudaGetLastError());
   if (comm && comm->world > 1) {        // embeddings (first 3 tensors) and the tail (ln_f, sigma / action embeddings, head)
-    if ((rc = sync_bucket(comm, grad, 0, goff[3], grad_scale, st))) return rc;
-    if ((rc = sync_bucket(comm, grad, goff[pt], acc_off - goff[pt], grad_scale, st))) return rc;
+    if ((rc = sync_bucket(comm, grad, 0, goff[3], grad_scale, st, goff[pt], acc_off - goff[pt]))) return rc;
     if ((rc = join_buckets(comm, st))) return rc;
   }
 #undef LAUNCH
