@@ -498,3 +498,27 @@ def test_fast_mode_against_16bit_faithful_oracle(name, cuda_device):
     with torch.no_grad():
         f16 = O.faithful16_denoiser_forward(sd, to_oracle_cfg(cfg), a["state"], a["action"], a["goal"], a["sigma"])
     torch.testing.assert_close(out, f16, **TOL_FAITHFUL)
+
+
+@pytest.mark.parametrize("kw", [dict(window=12, goal_len=1), dict(obs_dim=100), dict(act_dim=14)])
+def test_shapes_outside_the_tensor_core_kernel_fall_back_to_the_cuda_core_kernel(kw, cuda_device):
+    """The library decides what the tensor-core kernel takes (26 tokens, 100 observation features, 14 action dims are
+    outside it); the default / precise mode then runs the fp32 CUDA-core kernel and still matches the oracle, the
+    explicit fast mode reports the shape as unsupported instead of failing later."""
+    from beso_b200.config import ModelConfig
+    from oracle import beso_oracle as O
+    base = dict(obs_dim=20, act_dim=4, window=5, goal_len=2, d=256, n_layers=1, n_heads=4)
+    base.update(kw)
+    cfg = ModelConfig(**base)
+    assert not fast_available(cfg)
+    sd = synthetic_state_dict(cfg, 31)
+    x = synthetic_inputs(cfg, 3, seed=32)
+    g = cuda(x, cuda_device)
+    with torch.no_grad():
+        want = O.denoiser_forward(sd, to_oracle_cfg(cfg), x["state"], x["action"], x["goal"], x["sigma"])
+    for mode in ("auto", "precise"):
+        m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+        torch.testing.assert_close(m(g["state"], g["action"], g["goal"], g["sigma"]).cpu(), want, **TOL["precise"])
+    m = build_denoiser(cfg, cuda_device, mode="fast", state_dict=sd)
+    with pytest.raises(NotImplementedError):
+        m(g["state"], g["action"], g["goal"], g["sigma"])
