@@ -131,6 +131,10 @@ class DeviceWindowDataset:
         the rule of ``torch.utils.data.DistributedSampler`` -- so shards are disjoint, equal-sized, and the mean of the
         per-rank gradients is the global-batch gradient."""
         n = len(self)
+        if shuffle and world_size > 1 and generator is None:
+            # the global generator differs between ranks: their "same" permutation would not be the same and the
+            # shards would overlap silently
+            raise ValueError("data-parallel shuffling needs an explicit generator seeded identically on every rank")
         order = torch.randperm(n, generator=generator).numpy() if shuffle else np.arange(n)
         if world_size > 1:
             if not 0 <= rank < world_size:

@@ -120,7 +120,7 @@ int beso_plan_destroy(beso_plan* plan);
 /* Replaces: load_state_dict / optimizer.step / EMA copy_to making new weights visible to
  * forward (beso_agent.py:343-345,380-381,462).  `params_dev` holds beso_param_count()
  * device pointers to the fp32 parameter tensors in parameters() order.  Re-callable; the
- * packed images (transposed fp32 for PRECISE, bf16 UMMA tape for FAST) are rebuilt on
+ * packed images (fp16 UMMA tapes for FAST and -- as hi / lo pairs -- for PRECISE, transposed fp32 for the CUDA-core kernel) are rebuilt on
  * `stream`.  `slot` selects one of two resident weight sets (0 = raw, 1 = EMA) so that the
  * EMA swap in predict()/evaluate() does not force a re-pack. */
 int beso_plan_pack_weights(beso_plan* plan, int slot, const float* const* params_dev, int n_params,
