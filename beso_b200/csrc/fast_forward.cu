@@ -88,6 +88,47 @@ constexpr uint32_t kNone = 0xF;
 // TMEM columns
 constexpr uint32_t kColX = 0, kColS0 = 256, kColS1 = 384;
 
+// ---- the two geometries of the kernel --------------------------------------------------------------------------
+// G256: embed_dim <= 256 (everything above).  G384: embed_dim <= 384 (the reference's kitchen models: d = 360, 6 heads
+// of 60; configs/franka_kitchen_main_config.yaml:38,58).  The wide geometry keeps the SAME roles, barriers and drains but
+//  * X takes 384 of the 512 TMEM columns, so there is ONE 128-column scratch accumulator: an attention pass is a
+//    [Q|K] job (N = 128) and a V job (N = 64), FC1 chunks do not ping-pong (FC2 of the previous chunk runs while the
+//    current one is drained), every GEMM into X is three N = 128 column blocks;
+//  * the A operand is six K atoms (96 KB), the ring is 16 KB slots (three; five during the MLP half, see RingW), the
+//    hidden width is padded to 1536 (12 chunks), and the sampler's x / d buffers live in a global scratch.
+struct G256 {
+  static constexpr int DP = 256, NA = 4, FF = 1024, NCH = 8;
+  static constexpr uint32_t ColS0 = 256, ColS1 = 384;
+  static constexpr uint32_t SmRing = kSmRing, SmU = kSmU, SmQkv = kSmQkv, SmY = kSmY, SmH0 = kSmH0, SmH1 = kSmH1;
+  static constexpr uint32_t SmVecA = kSmVecA, VecBq = kVecBq, BqStride = 192, VecAFloats = kVecAFloats;
+  static constexpr uint32_t SmVecM = kSmVecM, VecB1H = kVecB1H, VecB1F = kVecB1F, VecMFloats = kVecMFloats;
+  static constexpr uint32_t SmStats = kSmStats, SmProg = kSmProg, SmSigv = kSmProg + 1024 + 4 * kXFloats * 4;
+  static constexpr bool XGlobal = false;
+};
+struct G384 {
+  static constexpr int DP = 384, NA = 6, FF = 1536, NCH = 12;
+  static constexpr uint32_t ColS0 = 384, ColS1 = 384;
+  static constexpr uint32_t SmRing = 98304, SmU = 147456;            // A: 6 x 16 KB | ring: 3 x 16 KB | union
+  static constexpr uint32_t SmQkv = SmU, SmY = SmU + 51200, SmH0 = SmU, SmH1 = SmU + 32768;
+  static constexpr uint32_t SmVecA = SmU + 67584, VecBq = 384, BqStride = 64, VecAFloats = 768;   // [pend(384) | bq: 64 per pass]
+  // [pend(384) | b1: fp16 image / 4 (768 floats, fast) or fp32 image (1536 floats, PREC)]
+  static constexpr uint32_t SmVecM = SmVecA + VecAFloats * 4, VecB1H = 384, VecB1F = 384, VecMFloats = 1920;
+  static constexpr uint32_t SmStats = SmVecM + VecMFloats * 4, SmProg = SmStats + 2048, SmSigv = SmProg;
+  static constexpr bool XGlobal = true;
+};
+static_assert(G384::SmSigv + 512 <= kSmBars, "wide geometry does not fit shared memory");
+// G384 weight ring: 16 KB slots, one ring group per slot; full barriers B_FULL0 + s, empty barriers B_WEMPTY0 + s (s < 6).
+// Producer and MMA issuer replay the same slot sequence; n_slots may differ between phases of the schedule.
+constexpr uint32_t kWSlots = 3;
+constexpr int B_WEMPTY0 = B_FULL0 + 6;
+struct RingW {
+  uint32_t cur, par;                 // next slot; bit s of par = parity of slot s's next use
+  __device__ __forceinline__ uint32_t begin(uint32_t n_slots) { if (cur >= n_slots) cur = 0; return cur; }
+  __device__ __forceinline__ uint32_t parity(uint32_t s) const { return (par >> s) & 1u; }
+  __device__ __forceinline__ void end(uint32_t s) { par ^= 1u << s; cur = s + 1; }
+  template <class G> static __device__ __forceinline__ uint32_t slot_off(uint32_t s) { return G::SmRing + s * 16384u; }
+};
+
 struct FastParams {
   const uint8_t* tape;         // per-eval weight tape
   const float* vec;            // per layer: vecA (1536) | vecM (1792); then final vecA (1536)
@@ -97,6 +138,7 @@ struct FastParams {
   float lambda, sigma_data, inv_d;
   const float *state, *goal, *xin, *sigma;
   float* out;
+  float* xscratch;             // G384: per-CTA x / d1 / x2 / dU buffers (4 x kXFloats floats each)
   float* trace;                // optional debug dump of X after every LayerNorm pass (tile 0, eval 0)
   long long* timeline;         // optional clock64 stamps of block 0, second evaluation (see tools/timeline_fast.py)
 };
@@ -391,26 +433,102 @@ __device__ __noinline__ void ln_pass(const Compute c, uint32_t vec_s, float inv_
   // another barrier of all compute warps (attention syncs, the end-of-MLP sync, the epilogue syncs)
 }
 
+// G384: 192 columns per thread.  Two sweeps over X in TMEM (statistics, then normalise in fp32 and round once) instead of
+// parking the row in registers: 96 packed pairs plus the load buffers do not fit the 168-register budget, and a TMEM
+// sweep costs a few hundred cycles.
+template <bool DBG>
+__device__ __noinline__ void ln_pass_w(const Compute c, uint32_t vec_s, float inv_d, float* trace_row) {
+  float va[32], vb[32];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  const int col0 = c.hf * 192;
+  auto pass1 = [&](float (&v)[32], int ch) {
+    const int col = col0 + ch * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 pd = lds128f_ro(vec_s + (uint32_t)(col + i) * 4u);
+      const float a0 = v[i] + pd.x, a1 = v[i + 1] + pd.y, a2 = v[i + 2] + pd.z, a3 = v[i + 3] + pd.w;
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+      if (DBG) {
+        if (trace_row != nullptr) {
+          float* tr = trace_row + col + i;
+          tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3;
+        }
+      }
+    }
+  };
+  tmem_ld32(c.lane_addr(kColX + col0), va);
+  tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
+  tmem_wait_ld();
+#pragma unroll
+  for (int ch = 0; ch < 6; ch += 2) {
+    pass1(va, ch);
+    if (ch + 2 < 6) tmem_ld32(c.lane_addr(kColX + col0 + (ch + 2) * 32), va);
+    pass1(vb, ch + 1);
+    if (ch + 2 < 6) { tmem_ld32(c.lane_addr(kColX + col0 + (ch + 3) * 32), vb); tmem_wait_ld(); }
+  }
+  const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
+  float2* stats = reinterpret_cast<float2*>(c.sm + G384::SmStats);
+  stats[c.hf * kRows + c.row] = make_float2(sum, sq);
+  // the second sweep's first loads fly while the statistics are exchanged
+  tmem_ld32(c.lane_addr(kColX + col0), va);
+  tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
+  compute_sync();
+  const float2 o = stats[(c.hf ^ 1) * kRows + c.row];
+  const float mean = (sum + o.x) * inv_d;
+  const float var = fmaxf((sq + o.y) * inv_d - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f), nm = -mean * rstd;
+  auto pass2 = [&](float (&v)[32], int ch) {
+    const int col = col0 + ch * 32;                      // 32 columns = chunks k0 .. k0 + 3 of one K atom
+    const uint32_t atom = c.sbase + kSmA + (uint32_t)(col >> 6) * 16384u, k0 = (uint32_t)(col & 63) >> 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // (volatile loads: identical to the first sweep's, they must not be merged with them and kept live across it)
+      const float4 p0 = lds128f_v(vec_s + (uint32_t)(col + k * 8) * 4u), p1 = lds128f_v(vec_s + (uint32_t)(col + k * 8 + 4) * 4u);
+      const float* e = v + k * 8;
+      sts128(c.chunk_addr(atom, k0 + k),
+             pack_f16x2(fmaf(e[0] + p0.x, rstd, nm), fmaf(e[1] + p0.y, rstd, nm)), pack_f16x2(fmaf(e[2] + p0.z, rstd, nm), fmaf(e[3] + p0.w, rstd, nm)),
+             pack_f16x2(fmaf(e[4] + p1.x, rstd, nm), fmaf(e[5] + p1.y, rstd, nm)), pack_f16x2(fmaf(e[6] + p1.z, rstd, nm), fmaf(e[7] + p1.w, rstd, nm)));
+    }
+  };
+  tmem_wait_ld();
+#pragma unroll
+  for (int ch = 0; ch < 6; ch += 2) {
+    pass2(va, ch);
+    if (ch + 2 < 6) tmem_ld32(c.lane_addr(kColX + col0 + (ch + 2) * 32), va);
+    pass2(vb, ch + 1);
+    if (ch + 2 < 6) { tmem_ld32(c.lane_addr(kColX + col0 + (ch + 3) * 32), vb); tmem_wait_ld(); }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  c.arrive(B_A_READY);
+}
+
 // Accumulator of head h (Q|K at S0, V at S1[0:64)) -> fp16 Q|K|V staging rows.  Only Q gets its bias here: the
 // K bias shifts every score of a query row by the same amount (softmax-invariant) and the V bias passes
 // through the softmax average unchanged, so it is folded into the projection bias at pack time.
+// PARTS: bit 0 = Q, bit 1 = K, bit 2 = V are in the accumulator.  7: one [Q|K|V] job (G256).  G384 has a single 128-column
+// scratch accumulator: 3 = the [Q|K] job, 4 = the V job (V then sits at the start of the accumulator).
+template <class G, int PARTS>
 __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
   // Each thread takes 32 columns of Q, of K and of V of its row (so that both column halves carry the same
   // share of the Q bias).  All TMEM reads first, then the accumulator is handed back to the MMA warp (QKV of
   // the next head can start) while this thread still converts and stores.
   float v0[32], v1[32], v2[32];
   const int colb = c.hf * 32;                            // within each 64-column block of [Q_h | K_h | V_h]
-  tmem_ld32(c.lane_addr(kColS0 + colb), v0);
-  tmem_ld32(c.lane_addr(kColS0 + 64 + colb), v1);
-  tmem_ld32(c.lane_addr(kColS0 + 128 + colb), v2);
+  if constexpr ((PARTS & 1) != 0) tmem_ld32(c.lane_addr(G::ColS0 + colb), v0);
+  if constexpr ((PARTS & 2) != 0) tmem_ld32(c.lane_addr(G::ColS0 + 64 + colb), v1);
+  if constexpr ((PARTS & 4) != 0) tmem_ld32(c.lane_addr(G::ColS0 + (PARTS == 7 ? 128 : 0) + colb), v2);
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
-  const uint32_t dst0 = c.sbase + kSmQkv + (uint32_t)c.row * kQkvStride + (uint32_t)colb * 2u;
+  const uint32_t dst0 = c.sbase + G::SmQkv + (uint32_t)c.row * kQkvStride + (uint32_t)colb * 2u;
+  if constexpr ((PARTS & 1) != 0) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {                      // Q (+ bias)
     const float4 b0 = lds128f_ro(bq_s + (uint32_t)(colb + i) * 4u);
     v0[i] += b0.x; v0[i + 1] += b0.y; v0[i + 2] += b0.z; v0[i + 3] += b0.w;
+  }
   }
   auto emit = [&](const float (&v)[32], uint32_t dst) {
 #pragma unroll
@@ -418,7 +536,9 @@ __device__ __noinline__ void drain_qkv(const Compute c, uint32_t bq_s) {
       sts128(dst + q * 16, pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]),
              pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]));
   };
-  emit(v0, dst0); emit(v1, dst0 + 128); emit(v2, dst0 + 256);
+  if constexpr ((PARTS & 1) != 0) emit(v0, dst0);
+  if constexpr ((PARTS & 2) != 0) emit(v1, dst0 + 128);
+  if constexpr ((PARTS & 4) != 0) emit(v2, dst0 + 256);
 }
 
 // Causal softmax(Q K^T) V for every sequence of the tile, one warp per (sequence, 16-query tile), mma.sync fp16.
@@ -438,9 +558,9 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // and the output goes to the hi / lo rows of the Y atom.
 // NH = 2: two warps share one item -- both compute the scores and the softmax, each the P V product of half of the
 // output columns (`half`); used when a tile has so few (sequence, query tile) items that warps would idle.
-template <int NKT, bool HI, int HSP, bool SPLIT, int NH>
+template <class G, int NKT, bool HI, int HSP, bool SPLIT, int NH>
 __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co, int half) {
-  const uint32_t qkv = sbase + kSmQkv + (uint32_t)co * 2u;
+  const uint32_t qkv = sbase + G::SmQkv + (uint32_t)co * 2u;
   constexpr int KS = HSP / 16;                   // 16-wide k steps over the head dimension
   constexpr int kLastRow = SPLIT ? 63 : kRows - 1;
   constexpr uint32_t kLo = 64u * kQkvStride;     // byte offset of the lo image
@@ -561,8 +681,8 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     r_lo = ((r_lo >> 4) << 5) | (r_lo & 15u);
     r_hi = ((r_hi >> 4) << 5) | (r_hi & 15u);
   }
-  const uint32_t y_lo = sbase + kSmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
-  const uint32_t y_hi = sbase + kSmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
+  const uint32_t y_lo = sbase + G::SmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
+  const uint32_t y_hi = sbase + G::SmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
   const uint32_t n0 = ((uint32_t)co >> 3) + (uint32_t)nfirst;   // first 16-byte chunk of this warp's columns inside the Y row
   if (i_lo < T) {
 #pragma unroll
@@ -581,7 +701,7 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
     }
   }
 }
-template <int HSP, bool SPLIT, int NH>
+template <class G, int HSP, bool SPLIT, int NH>
 __device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_slots, int half, int lane, int S, int T) {
   constexpr int NSUB = 64 / HSP;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
@@ -590,43 +710,45 @@ __device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_
     const int mt = MT - 1 - it2 / S, s = it2 % S;     // later query tiles see more keys: schedule them first
     const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
     const int co = sub * HSP;
-    if (mt == 0) { if (hi) attention_item<1, true, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); else attention_item<1, false, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); }
-    else { if (hi) attention_item<2, true, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); else attention_item<2, false, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); }
+    if (mt == 0) { if (hi) attention_item<G, 1, true, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); else attention_item<G, 1, false, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); }
+    else { if (hi) attention_item<G, 2, true, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); else attention_item<G, 2, false, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); }
   }
 }
-template <int HSP, bool SPLIT>
+template <class G, int HSP, bool SPLIT>
 __device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T) {
   // The precise mode's tiles hold at most 64 rows = 4 items for the 10 attention warps: pairs of warps share an item.
   // (Only there: the single-pass fp16 kernel has 8-10 items, and a second item body would only grow its image.)
   if constexpr (SPLIT) {
     if (S * ((T + 15) >> 4) * (64 / HSP) * 2 <= kAttnWarps) {
-      attention_items<HSP, SPLIT, 2>(sbase, awarp >> 1, kAttnWarps / 2, awarp & 1, lane, S, T);
+      attention_items<G, HSP, SPLIT, 2>(sbase, awarp >> 1, kAttnWarps / 2, awarp & 1, lane, S, T);
       return;
     }
   }
-  attention_items<HSP, SPLIT, 1>(sbase, awarp, kAttnWarps, 0, lane, S, T);
+  attention_items<G, HSP, SPLIT, 1>(sbase, awarp, kAttnWarps, 0, lane, S, T);
 }
 // The padded head size is a template parameter of the kernel: only the attention code of the model's head size is in
 // the kernel image (the fused kernel is ~13 k instructions; its hot paths have to stay resident in the instruction cache).
-template <int HSP>
+template <class G, int HSP>
 __device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T) {
-  attention_head_t<HSP, false>(sbase, awarp, lane, S, T);
+  attention_head_t<G, HSP, false>(sbase, awarp, lane, S, T);
 }
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
 // b1h_s = shared address of this chunk's 128 biases as fp16.
-__device__ __noinline__ void drain_gelu(const Compute c, int b, uint32_t b1h_s) {
+// tb = scratch accumulator the chunk sits in, b = H buffer it goes to (G256: the same index; G384: tb = 0 always).
+template <class G>
+__device__ __noinline__ void drain_gelu(const Compute c, int tb, int b, uint32_t b1h_s) {
   // Both 32-column pieces of this thread are read first (one exposed TMEM round trip per chunk) and the
   // accumulator is released at once; then 8 pairs at a time go through the GELU.  FC2's first k-block only
   // needs K atom 0 of H, which is signalled as soon as it is written.
   float va[32], vb[32];
-  const uint32_t s_col = (b ? kColS1 : kColS0) + c.hf * 32;
-  const uint32_t h_s = c.sbase + (b ? kSmH1 : kSmH0);
+  const uint32_t s_col = (tb ? G::ColS1 : G::ColS0) + c.hf * 32;
+  const uint32_t h_s = c.sbase + (b ? G::SmH1 : G::SmH0);
   tmem_ld32(c.lane_addr(s_col), va);
   tmem_ld32(c.lane_addr(s_col + 64), vb);
   tmem_wait_ld();
   tc_fence_before();
-  c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
+  c.arrive(tb ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
   auto emit = [&](const float* v, uint32_t col, uint32_t atom, uint32_t k0) {
     const uint4 bb0 = lds128_ro(b1h_s + col * 2u), bb1 = lds128_ro(b1h_s + col * 2u + 16u);
     __half2 x[8];
@@ -732,20 +854,91 @@ __device__ __noinline__ void ln_pass_p(const Compute c, uint32_t vec_s, float in
   c.arrive(B_A_READY);
 }
 
+// G384: 192 columns per TMEM lane.  In 16-column pieces: the even pieces stay with the hi-lane thread, the odd pieces with
+// the lo-lane thread, so that each of them ends up with 96 complete columns in 16-column (two-chunk) runs.
+template <bool DBG>
+__device__ __noinline__ void ln_pass_pw(const Compute c, uint32_t vec_s, float inv_d, int d_true, float* trace_row) {
+  float x[96];
+  const int col0 = c.hf * 192;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    float va[16], vb[16];
+    tmem_ld16(c.lane_addr(kColX + col0 + r * 32), va);
+    tmem_ld16(c.lane_addr(kColX + col0 + r * 32 + 16), vb);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[r * 16 + i] = (c.is_lo ? vb[i] : va[i]) + shx16(c.is_lo ? va[i] : vb[i]);
+  }
+  const int cbase = col0 + c.is_lo * 16;                  // piece r of this thread = columns cbase + 32 r .. + 16
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 pd = lds128f_ro(vec_s + (uint32_t)(cbase + r * 32 + i) * 4u);
+      float* e = x + r * 16 + i;
+      e[0] += pd.x; e[1] += pd.y; e[2] += pd.z; e[3] += pd.w;
+      s += (e[0] + e[1]) + (e[2] + e[3]);
+    }
+  if (DBG) {
+    if (trace_row != nullptr) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) trace_row[cbase + r * 32 + i] = x[r * 16 + i];
+    }
+  }
+  s += shx16(s);
+  float* stats = reinterpret_cast<float*>(c.sm + G384::SmStats);  // [sum: 2 x 64 | squares: 2 x 64]
+  if (!c.is_lo) stats[c.hf * 64 + c.srow] = s;
+  compute_sync();
+  const float mean = (s + stats[(c.hf ^ 1) * 64 + c.srow]) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int nv = d_true - (cbase + r * 32);            // true lanes of this piece (padding columns are zero, not mean)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float t = x[r * 16 + i] - mean; x[r * 16 + i] = t; if (i < nv) q = fmaf(t, t, q); }
+  }
+  q += shx16(q);
+  if (!c.is_lo) stats[128 + c.hf * 64 + c.srow] = q;
+  compute_sync();
+  const float var = (q + stats[128 + (c.hf ^ 1) * 64 + c.srow]) * inv_d;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  // hi row = lane & ~16, the lo row is 16 rows (2048 bytes) further down
+  const uint32_t a_row = c.sbase + kSmA + c.row_off - (uint32_t)c.is_lo * 2048u;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int col = cbase + r * 32;
+    const uint32_t a_hi = a_row + (uint32_t)(col >> 6) * 16384u, k0 = (uint32_t)(col & 63) >> 3;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = x[r * 16 + k * 8 + i] * rstd;
+      st_chunk_split(a_hi + (((k0 + (uint32_t)k) << 4) ^ c.rx4), y);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  c.arrive(B_A_READY);
+}
+
 // [Q|K|V] accumulator of one attention pass -> fp16 staging, hi image in rows [0, 64) and lo image in rows [64, 128)
 // (Q gets its bias).  Per 32-column piece the pair threads exchange halves: each ends up with 16 columns of Q, of K
 // and of V of the sequence row.
+template <class G, int PARTS>
 __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
   float v0[32], v1[32], v2[32];
   const int colb = c.hf * 32;
-  tmem_ld32(c.lane_addr(kColS0 + colb), v0);
-  tmem_ld32(c.lane_addr(kColS0 + 64 + colb), v1);
-  tmem_ld32(c.lane_addr(kColS0 + 128 + colb), v2);
+  if constexpr ((PARTS & 1) != 0) tmem_ld32(c.lane_addr(G::ColS0 + colb), v0);
+  if constexpr ((PARTS & 2) != 0) tmem_ld32(c.lane_addr(G::ColS0 + 64 + colb), v1);
+  if constexpr ((PARTS & 4) != 0) tmem_ld32(c.lane_addr(G::ColS0 + (PARTS == 7 ? 128 : 0) + colb), v2);
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
   const int cs = colb + c.is_lo * 16;                     // first of this thread's 16 columns inside each 64-block
-  const uint32_t dst = c.sbase + kSmQkv + (uint32_t)c.srow * kQkvStride + (uint32_t)cs * 2u;
+  const uint32_t dst = c.sbase + G::SmQkv + (uint32_t)c.srow * kQkvStride + (uint32_t)cs * 2u;
   auto emit = [&](const float (&v)[32], uint32_t d, bool bias) {
     float r[16];
 #pragma unroll
@@ -765,29 +958,32 @@ __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
     sts128(d + 64u * kQkvStride, l[0], l[1], l[2], l[3]);
     sts128(d + 64u * kQkvStride + 16, l[4], l[5], l[6], l[7]);
   };
-  emit(v0, dst, true); emit(v1, dst + 128, false); emit(v2, dst + 256, false);
+  if constexpr ((PARTS & 1) != 0) emit(v0, dst, true);
+  if constexpr ((PARTS & 2) != 0) emit(v1, dst + 128, false);
+  if constexpr ((PARTS & 4) != 0) emit(v2, dst + 256, false);
 }
 
 // Causal attention of the precise mode: the mma.sync kernel of the fp16 mode with every product split three ways
 // (attention_item<..., SPLIT = true>): the operands come out of shared memory once per 16 x 8 tile, which keeps the
 // attention phase off the shared-memory port the tensor pipe is streaming its operands through.
-template <int HSP>
+template <class G, int HSP>
 __device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T) {
-  attention_head_t<HSP, true>(sbase, awarp, lane, S, T);
+  attention_head_t<G, HSP, true>(sbase, awarp, lane, S, T);
 }
 
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
 // FC1 chunk accumulator (buffer b) -> + b1 -> exact erf-GELU (fp32) -> split -> H[b] (two K atoms).
 // b1_s = shared address of this chunk's 128 biases (fp32).
-__device__ __noinline__ void drain_gelu_p(const Compute c, int b, uint32_t b1_s) {
+template <class G>
+__device__ __noinline__ void drain_gelu_p(const Compute c, int tb, int b, uint32_t b1_s) {
   float va[32], vb[32];
-  const uint32_t s_col = (b ? kColS1 : kColS0) + c.hf * 32;
-  const uint32_t h_hi = c.sbase + (b ? kSmH1 : kSmH0) + c.row_off - (uint32_t)c.is_lo * 2048u;
+  const uint32_t s_col = (tb ? G::ColS1 : G::ColS0) + c.hf * 32;
+  const uint32_t h_hi = c.sbase + (b ? G::SmH1 : G::SmH0) + c.row_off - (uint32_t)c.is_lo * 2048u;
   tmem_ld32(c.lane_addr(s_col), va);
   tmem_ld32(c.lane_addr(s_col + 64), vb);
   tmem_wait_ld();
   tc_fence_before();
-  c.arrive(b ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
+  c.arrive(tb ? B_ACC_EMPTY1 : B_ACC_EMPTY0);
   const int cs = c.hf * 32 + c.is_lo * 16;                // this thread's 16 columns inside each 64-wide K atom
   auto emit = [&](const float (&v)[32], uint32_t bias_s, uint32_t atom) {
     float g[16];
@@ -1066,26 +1262,32 @@ __device__ __forceinline__ void stamp(const Compute& c) {
   }
 }
 struct XBufs { float *xcur, *d1, *x2, *dU, *sigv; };
-__device__ __forceinline__ XBufs xbufs(uint8_t* sm) {
-  float* xbuf = reinterpret_cast<float*>(sm + kSmProg + 1024);
-  return {xbuf, xbuf + kXFloats, xbuf + 2 * kXFloats, xbuf + 3 * kXFloats, xbuf + 4 * kXFloats};
+template <class G>
+__device__ __forceinline__ XBufs xbufs(uint8_t* sm, const FastParams& p) {
+  float* sigv = reinterpret_cast<float*>(sm + G::SmSigv);
+  float* xbuf;
+  if constexpr (G::XGlobal) xbuf = p.xscratch + (size_t)blockIdx.x * (4 * kXFloats);   // no shared memory left for them
+  else xbuf = reinterpret_cast<float*>(sm + G::SmProg + 1024);
+  return {xbuf, xbuf + kXFloats, xbuf + 2 * kXFloats, xbuf + 3 * kXFloats, sigv};
 }
 
 // x of this tile's sequences -> shared memory (kept there across all sampler steps)
+template <class G>
 __device__ __noinline__ void tile_begin(const Compute c, const FastParams& p, int tile) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   const int nls = cfg ? p.S / 2 : p.S, n_x = nls * p.t * p.act;
   const int seq0 = tile * nls, ns = max(0, min(nls, p.B - seq0));
-  const XBufs xb = xbufs(c.sm);
+  const XBufs xb = xbufs<G>(c.sm, p);
   compute_sync();                                            // previous tile's x fully written out
   for (int i = c.ctid; i < n_x; i += kComputeThreads)
     xb.xcur[i] = (i < ns * p.t * p.act) ? p.xin[(size_t)seq0 * p.t * p.act + i] : 0.f;
 }
+template <class G>
 __device__ __noinline__ void tile_end(const Compute c, const FastParams& p, const SampleArgs& sa, int tile) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   const int nls = cfg ? p.S / 2 : p.S;
   const int seq0 = tile * nls, ns = max(0, min(nls, p.B - seq0));
-  const XBufs xb = xbufs(c.sm);
+  const XBufs xb = xbufs<G>(c.sm, p);
   compute_sync();
   for (int i = c.ctid; i < ns * p.t * p.act; i += kComputeThreads) {
     float v = xb.xcur[i];
@@ -1096,11 +1298,11 @@ __device__ __noinline__ void tile_end(const Compute c, const FastParams& p, cons
 }
 
 // noise levels of this evaluation + the embedding-GEMM A operand
-template <bool DBG, bool PREC>
+template <class G, bool DBG, bool PREC>
 __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p, const SampleArgs& sa, int tile, int step, int second) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   const int nls = cfg ? p.S / 2 : p.S, seq0 = tile * nls;
-  const XBufs xb = xbufs(c.sm);
+  const XBufs xb = xbufs<G>(c.sm, p);
   const float s_hat = sa.n_steps ? sa.sig[step] : 0.f;
   const float s_next = sa.n_steps ? sa.sig[step + 1] : 0.f;
   const float s_eval = second ? (sa.sampler == BESO_SAMPLER_TWO_STAGE ? sa.sigb[step] : s_next) : s_hat;
@@ -1116,32 +1318,37 @@ __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p,
 }
 
 // ln_f + action head read-out + pre-conditioning (+ CFG mix) + sampler update of x.  Returns the barrier phases.
-template <bool DBG, bool PREC>
+template <class G, bool DBG, bool PREC>
 __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, const SampleArgs& sa, int tile, int step, int second,
                                                float* trace_row) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   const bool inner = (p.flags & BESO_FLAG_INNER) != 0;
   const int nls = cfg ? p.S / 2 : p.S, seq0 = tile * nls;
   const int ns = max(0, min(nls, p.B - seq0));
-  const XBufs xb = xbufs(c.sm);
+  const XBufs xb = xbufs<G>(c.sm, p);
   float* xcur = xb.xcur; float* d1 = xb.d1; float* x2 = xb.x2; float* dU = xb.dU;
   const float* xsrc = second ? xb.x2 : xb.xcur;
   const float s_hat = sa.n_steps ? sa.sig[step] : 0.f;
   const float s_next = sa.n_steps ? sa.sig[step + 1] : 0.f;
-  const float* vecA = reinterpret_cast<const float*>(c.sm + kSmVecA);
+  const float* vecA = reinterpret_cast<const float*>(c.sm + G::SmVecA);
   cp_async_wait<1>();                                 // final vecA block (vecM(0) may still fly)
   compute_sync();
   c.wait(B_X_DONE);
   tc_fence_after();
   stamp<DBG>(c);
-  if constexpr (PREC) ln_pass_p<DBG>(c, c.sbase + kSmVecA, p.inv_d, p.d_true, trace_row);
-  else ln_pass<DBG>(c, c.sbase + kSmVecA, p.inv_d, trace_row);
+  if constexpr (G::DP == 384) {
+    if constexpr (PREC) ln_pass_pw<DBG>(c, c.sbase + G::SmVecA, p.inv_d, p.d_true, trace_row);
+    else ln_pass_w<DBG>(c, c.sbase + G::SmVecA, p.inv_d, trace_row);
+  } else {
+    if constexpr (PREC) ln_pass_p<DBG>(c, c.sbase + G::SmVecA, p.inv_d, p.d_true, trace_row);
+    else ln_pass<DBG>(c, c.sbase + G::SmVecA, p.inv_d, trace_row);
+  }
   stamp<DBG>(c);
   c.wait(B_ACC_FULL0);
   tc_fence_after();
   stamp<DBG>(c);
   float pr[16];
-  tmem_ld16(c.lane_addr(kColS0), pr);
+  tmem_ld16(c.lane_addr(G::ColS0), pr);
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
@@ -1149,7 +1356,7 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
 #pragma unroll
     for (int a = 0; a < 16; ++a) pr[a] += shx16(pr[a]);
   }
-  const float* hb = vecA + kVecBq;
+  const float* hb = vecA + G::VecBq;
   const int vs = c.srow / p.T, tok = c.srow - vs * p.T;
   const int j = tok - 1 - p.G;
   const int ls = cfg ? (vs >> 1) : vs;
@@ -1229,7 +1436,7 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
   }
   // vecA is free again: first block of the next evaluation
   compute_sync();
-  load_vec_async(c, kSmVecA, p.vec, kVecAFloats);
+  load_vec_async(c, G::SmVecA, p.vec, G::VecAFloats);
   return c.phases;
 }
 
@@ -1242,10 +1449,14 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
 // is free again when both CTAs' MMAs have read it (multicast commits).  Halves the L2 -> SM request traffic,
 // which at full-chip scale is within a factor 1.5 of the L2 throughput cap.
 // PREC = true: fp32-equivalent mode (split operands, 64 sequence rows per tile; see the PREC section above).
-template <int CG, bool DBG, int MC, bool PREC, int HSP>
+// DP = 256 / 384: geometry (G256 / G384 above).
+template <int CG, bool DBG, int MC, bool PREC, int HSP, int DP>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
   static_assert(!PREC || (CG == 1 && MC == 1), "the precise mode runs single-CTA MMAs");
+  static_assert(DP == 256 || (DP == 384 && CG == 1 && MC == 1), "the wide geometry runs single-CTA MMAs");
+  using G = std::conditional_t<DP == 384, G384, G256>;
+  constexpr bool WIDE = DP == 384;
   extern __shared__ uint8_t smem_raw[];
   // dynamic shared memory is at least 16-byte aligned; the operand tiles need 1024
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1264,7 +1475,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (threadIdx.x == kMmaWarp * 32) {
+  if (!WIDE && threadIdx.x == kMmaWarp * 32) {
     // group table for [embedding | one layer | head]: the single-warp roles replay it with one LDS per group
     uint4* tab = reinterpret_cast<uint4*>(sm + kSmProg);
     int i = 0;
@@ -1275,8 +1486,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   }
   if (PAIR == 2) cluster_sync_all();        // barriers of both CTAs initialised before any remote arrive / multicast
   if (warp == kMmaWarp) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
-  for (uint32_t i = threadIdx.x; i < (kSmVecA - kSmU) / 16; i += kThreads)      // padding rows must stay finite
-    reinterpret_cast<uint4*>(sm + kSmU)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x; i < (G::SmVecA - G::SmU) / 16; i += kThreads)      // padding rows must stay finite
+    reinterpret_cast<uint4*>(sm + G::SmU)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1299,7 +1510,39 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
   if (warp == kProducerWarp) {
     // ======================= weight-tape producer =======================
     uint32_t g = 0;
-    if constexpr (CG == 1) {
+    if constexpr (WIDE) {
+      // 16 KB slots, every ring group is one slot (RingW); the tape is contiguous in consumption order
+      RingW ring{0u, 0u};
+      constexpr uint32_t kImages = PREC ? 2u : 1u;
+      const uint32_t per_layer_attn = 12u * (uint32_t)p.npass, per_layer_mlp = 12u * (uint32_t)G::NCH;
+      for (int it = 0; it < my_tiles * p.evals; ++it) {
+        const uint8_t* src = p.tape;
+        auto fills = [&](uint32_t n, uint32_t bytes, uint32_t n_slots) {
+#pragma unroll 1
+          for (uint32_t i = 0; i < n * kImages; ++i) {
+            const uint32_t slot = ring.begin(n_slots), par = ring.parity(slot);
+            const uint32_t full = sbase + kSmBars + (B_FULL0 + slot) * 8, dst = sbase + RingW::slot_off<G>(slot);
+            spin_wait(sbase + kSmBars + (B_WEMPTY0 + slot) * 8, par ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(full, bytes);
+              const uint32_t h = bytes >> 1;                 // two requests in flight per group
+              bulk_g2s(dst, src, h, full);
+              bulk_g2s(dst + h, src + h, h, full);
+            }
+            __syncwarp();
+            ring.end(slot);
+            src += bytes;
+          }
+        };
+        fills(6, 16384, kWSlots);                            // embedding: 2 K atoms x 3 column blocks
+#pragma unroll 1
+        for (int l = 0; l < p.L; ++l) {
+          fills(per_layer_attn, 16384, kWSlots);             // per pass: [Q|K] 6, V 3, proj 3
+          fills(per_layer_mlp, 16384, kWSlots);              // per chunk: FC1 6, FC2 6
+        }
+        fills(1, 12288, kWSlots);                            // action head: 6 K blocks of [16 x 64]
+      }
+    } else if constexpr (CG == 1) {
       // Two stages of 32 KB (slots {0,1} and {2,3}), one full / empty barrier pair per stage; the tape is
       // contiguous in consumption order, so the producer only needs the byte count of each ring group.
       auto fill = [&](const uint8_t* src, uint32_t bytes) {
@@ -1412,6 +1655,118 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       using std::integral_constant;
       constexpr uint32_t kEmbBf16 = PREC ? 0u : 1u;          // the precise mode splits the raw inputs into fp16 hi + lo
 #define BESO_IC(v) integral_constant<uint32_t, (v)>{}
+      if constexpr (WIDE) {
+      // ---- G384: one ring group = one 16 KB slot; every GEMM into X is three N = 128 column blocks ----
+      RingW ring{0u, 0u};
+      uint32_t n_slots = kWSlots;
+      auto groupw = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, uint32_t a_off, uint32_t d_col, uint32_t acc) {
+        constexpr uint32_t N = decltype(n_tag)::value, NKB = decltype(nkb_tag)::value, B_STEP = decltype(bstep_tag)::value;
+        constexpr uint32_t idesc = decltype(bf16_tag)::value ? idesc_bf16_m128(N) : idesc_f16_m128(N);
+        const uint32_t slot = ring.begin(n_slots), par = ring.parity(slot);
+        long long t = 0;
+        if constexpr (DBG) t = clock64();
+        spin_wait(bars + (B_FULL0 + slot) * 8, par);
+        if constexpr (DBG) t_rw += clock64() - t;
+        tc_fence_after();
+        const uint32_t a_lo = dlo + (a_off >> 4), b_lo = dlo + (RingW::slot_off<G>(slot) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+              mma_bf16(tm + d_col, desc(a_lo + kb * 1024u + 2u * j), desc(b_lo + kb * (B_STEP >> 4) + 2u * j), idesc,
+                       (acc | kb | j) ? 1u : 0u);
+          mma_commit(bars + (B_WEMPTY0 + slot) * 8);
+        }
+        __syncwarp();
+        ring.end(slot);
+      };
+      auto group2w = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, uint32_t a_off, uint32_t d_col, uint32_t acc) {
+        groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, a_off, d_col, acc);
+        if constexpr (PREC) groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, a_off, d_col, 1);
+      };
+      // X (+)= A[a_off: one K atom] W^T, the 384 output columns as three N = 128 groups
+      auto into_x = [&](auto bf16_tag, uint32_t a_off, uint32_t acc) {
+#pragma unroll
+        for (uint32_t nb = 0; nb < 3; ++nb) group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), bf16_tag, a_off, kColX + nb * 128u, acc);
+      };
+      for (int it = 0; it < my_tiles * p.evals; ++it) {
+        if constexpr (DBG) tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
+        // ---- embedding GEMM: X = A_emb W_emb^T, K = 128 ----
+        job_begin();
+        jwait(B_A_READY);
+        into_x(BESO_IC(kEmbBf16), kSmA, 0);
+        into_x(BESO_IC(kEmbBf16), kSmA + 16384, 1);
+        jcommit(B_X_DONE);
+        job_end();
+#pragma unroll 1
+        for (int l = 0; l < p.L; ++l) {
+          // ---- attention half: QK0 V0 | QK1 P0 V1 | ... | P(n-1) ----
+#pragma unroll 1
+          for (int h = 0; h <= p.npass; ++h) {
+            if (h < p.npass) {                               // [Q|K] of attention pass h -> S (128 columns)
+              job_begin();
+              jwait(B_ACC_EMPTY0);
+              if (h == 0) jwait(B_A_READY);
+#pragma unroll
+              for (uint32_t kb = 0; kb < 6; ++kb)
+                group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, G::ColS0, kb);
+              jcommit(B_ACC_FULL0);
+              job_end();
+            }
+            if (h >= 1) {                                    // X += Y_{h-1} Wproj[:, h-1]^T
+              job_begin();
+              jwait(B_Y_READY);
+              into_x(BESO_IC(0), G::SmY, 1);
+              jcommit(B_Y_EMPTY);
+              if (h == p.npass) jcommit(B_X_DONE);
+              job_end();
+            }
+            if (h < p.npass) {                               // V of pass h -> S[0:64) once [Q|K] has been drained
+              job_begin();
+              jwait(B_ACC_EMPTY0);
+#pragma unroll
+              for (uint32_t kp = 0; kp < 3; ++kp)
+                group2w(BESO_IC(64), BESO_IC(2), BESO_IC(8192), BESO_IC(0), kSmA + kp * 32768, G::ColS0, kp);
+              jcommit(B_ACC_FULL0);
+              job_end();
+            }
+          }
+          // ---- MLP half: F1_0 | F1_c F2_c-1 | F2_11; one accumulator, hidden chunk c goes to H buffer c & 1 ----
+#pragma unroll 1
+          for (int c = 0; c <= G::NCH; ++c) {
+            if (c < G::NCH) {
+              job_begin();
+              jwait(B_ACC_EMPTY0);
+              if (c == 0) jwait(B_A_READY);
+#pragma unroll
+              for (uint32_t kb = 0; kb < 6; ++kb)
+                group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, G::ColS0, kb);
+              jcommit(B_ACC_FULL0);
+              job_end();
+            }
+            if (c >= 1) {                                    // X += H_{c-1} W2[:, chunk c-1]^T
+              const uint32_t b = (c - 1) & 1;
+              job_begin();
+              jwait(B_OP_READY0 + b);
+              into_x(BESO_IC(0), b ? G::SmH1 : G::SmH0, 1);
+              jwait(B_OP_READY0B + b);
+              into_x(BESO_IC(0), (b ? G::SmH1 : G::SmH0) + 16384, 1);
+              jcommit(B_OP_EMPTY0 + b);
+              if (c == G::NCH) jcommit(B_X_DONE);
+              job_end();
+            }
+          }
+        }
+        // ---- action head (N = 16, K = 384: one 12 KB group) ----
+        job_begin();
+        jwait(B_A_READY);
+        jwait(B_ACC_EMPTY0);
+        group2w(BESO_IC(16), BESO_IC(6), BESO_IC(2048), BESO_IC(0), kSmA, G::ColS0, 0);
+        jcommit(B_ACC_FULL0);
+        job_end();
+      }
+      } else
       for (int it = 0; it < my_tiles * p.evals; ++it) {
         if constexpr (DBG) tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
         // ---- embedding GEMM (bf16): X = A_emb W_emb^T, K = 128 ----
@@ -1526,8 +1881,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       attn_sync();
       spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
       y_phase ^= 1u;
-      if constexpr (PREC) attention_head_p<HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
-      else attention_head<HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
+      if constexpr (PREC) attention_head_p<G, HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
+      else attention_head<G, HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -1547,26 +1902,35 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     c.row_off = (uint32_t)c.row * 128u; c.rx4 = ((uint32_t)c.row & 7u) << 4;
     c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
     c.cg = CG;
-    const uint32_t vecA_s = sbase + kSmVecA, vecM_s = sbase + kSmVecM;
-    constexpr uint32_t layer_stride = kVecAFloats + kVecMFloats;
-    load_vec_async(c, kSmVecA, p.vec, kVecAFloats);
-    load_vec_async(c, kSmVecM, p.vec + kVecAFloats, kVecMFloats);
+    const uint32_t vecA_s = sbase + G::SmVecA, vecM_s = sbase + G::SmVecM;
+    constexpr uint32_t layer_stride = G::VecAFloats + G::VecMFloats;
+    load_vec_async(c, G::SmVecA, p.vec, G::VecAFloats);
+    load_vec_async(c, G::SmVecM, p.vec + G::VecAFloats, G::VecMFloats);
+    auto ln = [&](uint32_t vec_s, float* tr) {
+      if constexpr (WIDE) {
+        if constexpr (PREC) ln_pass_pw<DBG>(c, vec_s, p.inv_d, p.d_true, tr);
+        else ln_pass_w<DBG>(c, vec_s, p.inv_d, tr);
+      } else {
+        if constexpr (PREC) ln_pass_p<DBG>(c, vec_s, p.inv_d, p.d_true, tr);
+        else ln_pass<DBG>(c, vec_s, p.inv_d, tr);
+      }
+    };
     if constexpr (DBG) { if (c.ctid == 0) *reinterpret_cast<long long**>(sm + kSmTlCursor) = nullptr; }
 
     for (int tj = 0; tj < my_tiles; ++tj) {
       const int tile = (group + tj * n_groups) * PAIR + (int)rank;   // >= n_tiles: dummy tile, protocol only
-      tile_begin(c, p, tile);
+      tile_begin<G>(c, p, tile);
       int step = 0, second = 0;
       for (int ev = 0; ev < p.evals; ++ev) {
         auto trace_row = [&](int slot) -> float* {
-          return (DBG && p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.srow) * kD : nullptr;
+          return (DBG && p.trace != nullptr && blockIdx.x == 0 && ev == 0 && tj == 0) ? p.trace + ((size_t)slot * kRows + c.srow) * G::DP : nullptr;
         };
         if constexpr (DBG) {
           if (c.ctid == 0)
             *reinterpret_cast<long long**>(sm + kSmTlCursor) =
                 (p.timeline != nullptr && blockIdx.x == 0 && tile == 0 && ev == 1) ? p.timeline + 6 * p.n_fills : nullptr;
         }
-        eval_prologue<DBG, PREC>(c, p, sa, tile, step, second);
+        eval_prologue<G, DBG, PREC>(c, p, sa, tile, step, second);
 
         for (int l = 0; l < p.L; ++l) {
           // ---------------- attention half ----------------
@@ -1575,21 +1939,27 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           c.wait(B_X_DONE);
           tc_fence_after();
           stamp<DBG>(c);
-          if constexpr (PREC) ln_pass_p<DBG>(c, vecA_s, p.inv_d, p.d_true, trace_row(2 * l));
-          else ln_pass<DBG>(c, vecA_s, p.inv_d, trace_row(2 * l));
+          ln(vecA_s, trace_row(2 * l));
           stamp<DBG>(c);
           for (int h = 0; h < p.npass; ++h) {
             c.wait(B_ACC_FULL0);
             tc_fence_after();
             stamp<DBG>(c);
             // arrives on ACC_EMPTY0 once its TMEM reads are done
-            if constexpr (PREC) drain_qkv_p(c, vecA_s + (uint32_t)(kVecBq + h * 192) * 4u);
-            else drain_qkv(c, vecA_s + (uint32_t)(kVecBq + h * 192) * 4u);
+            const uint32_t bq_s = vecA_s + (uint32_t)(G::VecBq + h * G::BqStride) * 4u;
+            if constexpr (WIDE) {                           // [Q|K] job, then the V job into the same accumulator
+              if constexpr (PREC) drain_qkv_p<G, 3>(c, bq_s); else drain_qkv<G, 3>(c, bq_s);
+              c.wait(B_ACC_FULL0);
+              tc_fence_after();
+              if constexpr (PREC) drain_qkv_p<G, 4>(c, bq_s); else drain_qkv<G, 4>(c, bq_s);
+            } else {
+              if constexpr (PREC) drain_qkv_p<G, 7>(c, bq_s); else drain_qkv<G, 7>(c, bq_s);
+            }
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
             c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
             stamp<DBG>(c);
-            if constexpr (PREC) attention_head_p<HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
-            else attention_head<HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
+            if constexpr (PREC) attention_head_p<G, HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
+            else attention_head<G, HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
             fence_async_smem();
             c.arrive(B_Y_READY);
             stamp<DBG>(c);
@@ -1597,30 +1967,29 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             stamp<DBG>(c);
           }
           // vecA is free: prefetch the next layer's (or the final block)
-          load_vec_async(c, kSmVecA, p.vec + (size_t)(l + 1) * layer_stride, kVecAFloats);
+          load_vec_async(c, G::SmVecA, p.vec + (size_t)(l + 1) * layer_stride, G::VecAFloats);
           // ---------------- MLP half ----------------
           c.wait(B_X_DONE);
           tc_fence_after();
           stamp<DBG>(c);
-          if constexpr (PREC) ln_pass_p<DBG>(c, vecM_s, p.inv_d, p.d_true, trace_row(2 * l + 1));
-          else ln_pass<DBG>(c, vecM_s, p.inv_d, trace_row(2 * l + 1));
+          ln(vecM_s, trace_row(2 * l + 1));
           stamp<DBG>(c);
-          for (int ch = 0; ch < 8; ++ch) {
-            const int b = ch & 1;
-            c.wait2(b ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
+          for (int ch = 0; ch < G::NCH; ++ch) {
+            const int b = ch & 1, tb = WIDE ? 0 : b;
+            c.wait2(tb ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
             stamp<DBG>(c);
             // arrives on ACC_EMPTY and (twice) on OP_READY itself
-            if constexpr (PREC) drain_gelu_p(c, b, vecM_s + (uint32_t)kVecB1F * 4u + (uint32_t)ch * 512u);
-            else drain_gelu(c, b, vecM_s + (uint32_t)kVecB1H * 4u + (uint32_t)ch * 256u);
+            if constexpr (PREC) drain_gelu_p<G>(c, tb, b, vecM_s + (uint32_t)G::VecB1F * 4u + (uint32_t)ch * 512u);
+            else drain_gelu<G>(c, tb, b, vecM_s + (uint32_t)G::VecB1H * 4u + (uint32_t)ch * 256u);
             stamp<DBG>(c);
           }
           compute_sync();                                   // everyone done with vecM(l)
           const int nl = (l + 1 < p.L) ? l + 1 : 0;
-          load_vec_async(c, kSmVecM, p.vec + (size_t)nl * layer_stride + kVecAFloats, kVecMFloats);
+          load_vec_async(c, G::SmVecM, p.vec + (size_t)nl * layer_stride + G::VecAFloats, G::VecMFloats);
         }
         // ---------------- ln_f + action head + pre-conditioning + sampler update ----------------
-        c.phases = eval_epilogue<DBG, PREC>(c, p, sa, tile, step, second, trace_row(2 * p.L));
+        c.phases = eval_epilogue<G, DBG, PREC>(c, p, sa, tile, step, second, trace_row(2 * p.L));
         if (sa.n_steps) {
           const bool two = (sa.sampler == BESO_SAMPLER_HEUN && sa.sig[step + 1] != 0.0f) ||
                            (sa.sampler == BESO_SAMPLER_TWO_STAGE && sa.sigb[step] != 0.0f);
@@ -1628,7 +1997,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           else { second = 0; ++step; }
         }
       }
-      if (sa.n_steps) tile_end(c, p, sa, tile);
+      if (sa.n_steps) tile_end<G>(c, p, sa, tile);
     }
     cp_async_wait<0>();
   }
@@ -1770,12 +2139,14 @@ struct EmbSrc {
   const float* resid_bias[2 * kMaxLayers];     // effective attn.proj bias (256 padded) and mlp.2.bias (d) of every layer
   int obs, act, G, W, L, d, prec;
 };
-// Embedding GEMM B operand: W_emb[n][k], n < 256, k < 128 (atom 0 = obs, atom 1 = misc), as fills of
-// [128 rows x 64] in (k-atom, [image,] row-half) order.  fp16 mode: bf16, tables as hi + lo column pairs.
-// PREC: fp16 hi image (blockIdx.y = 0) and lo image (1) of the plain values, one column per table entry.
-__global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape) {
-  const int fill = blockIdx.x;                 // 0..3: atom = fill >> 1, rows (fill & 1) * 128 ..
-  const int atom = fill >> 1, n0 = (fill & 1) * 128, image = blockIdx.y;
+// Embedding GEMM B operand: W_emb[n][k], n < 256 (384), k < 128 (atom 0 = obs, atom 1 = misc), as fills of
+// [128 rows x 64] in (k-atom, row-block) order; a ring group holds `group_blocks` consecutive fills (G256: 2 = all rows
+// of a K atom, G384: 1).  fp16 mode: bf16, tables as hi + lo column pairs.
+// PREC: fp16 hi image (blockIdx.y = 0) and lo image (1) of the plain values, one column per table entry, stored
+// [hi group | lo group].
+__global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape, int nblk, int group_blocks) {
+  const int fill = blockIdx.x;                 // atom = fill / nblk, rows (fill % nblk) * 128 ..
+  const int atom = fill / nblk, n0 = (fill % nblk) * 128, image = blockIdx.y;
   for (int idx = threadIdx.x; idx < 128 * 8; idx += blockDim.x) {
     const int r = idx >> 3, chunk = idx & 7, n = n0 + r;
     float v[8];
@@ -1816,16 +2187,16 @@ __global__ void pack_emb_kernel(EmbSrc s, uint8_t* tape) {
       if (s.prec && image == 1) x -= __half2float(__float2half_rn(x));
       v[i] = x;
     }
-    if (s.prec) st_chunk_h(tape + (size_t)atom * 65536 + (size_t)image * 32768 + (size_t)(fill & 1) * 16384, r, chunk, v);
+    if (s.prec) st_chunk_h(tape + ((size_t)((fill / group_blocks) * 2 + image) * group_blocks + fill % group_blocks) * 16384, r, chunk, v);
     else st_chunk(tape + (size_t)fill * 16384, r, chunk, v);
   }
 }
 
 // pend vectors: minus the residual-branch biases that the embedding GEMM added too early.
 //   LN1(l): -(sum_{l' >= l} bproj + b2)     LN2(l): LN1(l) + bproj_l      ln_f: 0
-__global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, uint32_t m_off) {
+__global__ void pack_pend_kernel(EmbSrc s, float* vec, uint32_t layer_stride, uint32_t m_off, int dp) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= kD) return;
+  if (n >= dp) return;
   float r = 0.f;
   vec[(size_t)s.L * layer_stride + n] = 0.f;
   for (int l = s.L - 1; l >= 0; --l) {
@@ -1865,7 +2236,7 @@ static int padded_head(const beso_model_desc& m) { const int hs = m.d / m.n_head
 bool fast_supported(const beso_model_desc& m) {
   const int G = m.goal_conditioned ? m.goal_len : 0;
   const int T = 1 + G + 2 * m.window;
-  if (m.d > kD || m.d % 8 != 0 || m.n_heads < 1 || m.d % m.n_heads != 0) return false;
+  if (m.d > G384::DP || m.d % 8 != 0 || m.n_heads < 1 || m.d % m.n_heads != 0) return false;
   const int hs = m.d / m.n_heads;
   if (hs > 64) return false;
   const int per_pass = 64 / padded_head(m), npass = (m.n_heads + per_pass - 1) / per_pass;
@@ -1894,14 +2265,23 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   const int d = m.d, H = m.n_heads, hs = d / H, hsp = padded_head(m), per_pass = 64 / hsp, npass = (H + per_pass - 1) / per_pass;
   const int ff = 4 * d;
   const size_t images = prec ? 2 : 1;
-  // per evaluation: embedding 4 x 16 KB | per layer: per pass QKV 4 x 24 KB + proj 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
+  // geometry (G256 / G384): padded width, K atoms, hidden chunks, vector block layout
+  const bool wide = d > G256::DP;
+  const int DP = wide ? G384::DP : G256::DP, NA = DP / 64, NB = DP / 128, FFP = 4 * DP, NCH = FFP / 128;
+  const uint32_t vA = wide ? G384::VecAFloats : G256::VecAFloats, vM = wide ? G384::VecMFloats : G256::VecMFloats;
+  const uint32_t vBq = wide ? G384::VecBq : G256::VecBq, vBqStride = wide ? G384::BqStride : G256::BqStride;
+  const uint32_t vB1H = wide ? G384::VecB1H : G256::VecB1H, vB1F = wide ? G384::VecB1F : G256::VecB1F;
+  // G256 per evaluation: embedding 4 x 16 KB | per layer: per pass QKV 4 x 24 KB + proj 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
+  // G384 per evaluation: embedding 6 x 16 KB | per layer: per pass ([Q|K] 6 + V 3 + proj 3) x 16 KB, (FC1 6 + FC2 6) x 16 KB per chunk | head 6 x 2 KB
   // (PREC: every ring group twice, hi image then lo image)
-  const size_t tape_bytes = images * (4 * 16384 + (size_t)L * ((size_t)npass * (4 * 24576 + 32768) + 32 * 16384 + 16 * 32768) + 4 * 2048);
-  const size_t vec_floats = (size_t)L * (kVecAFloats + kVecMFloats) + kVecAFloats;
-  const size_t fold_floats = (size_t)L * 2 * kD;             // per layer: effective V bias | effective proj bias (256 padded)
+  const size_t tape_bytes = wide
+      ? images * (6 * 16384 + (size_t)L * ((size_t)npass * 12 * 16384 + (size_t)NCH * 12 * 16384) + 6 * 2048)
+      : images * (4 * 16384 + (size_t)L * ((size_t)npass * (4 * 24576 + 32768) + 32 * 16384 + 16 * 32768) + 4 * 2048);
+  const size_t vec_floats = (size_t)L * (vA + vM) + vA;
+  const size_t fold_floats = (size_t)L * 2 * DP;             // per layer: effective V bias | effective proj bias (padded)
   if (!w.tape) {
     // tape | (scratch tables for the pack kernels)
-    BESO_CUDA(cudaMalloc(&w.tape, tape_bytes + (2 << 20)));
+    BESO_CUDA(cudaMalloc(&w.tape, tape_bytes + (4 << 20)));
     BESO_CUDA(cudaMalloc(&w.vec, (vec_floats + fold_floats) * sizeof(float)));
     BESO_CUDA(cudaMemsetAsync(w.vec, 0, (vec_floats + fold_floats) * sizeof(float), st));
     w.tape_bytes = tape_bytes; w.vec_floats = vec_floats;
@@ -1911,7 +2291,7 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
 
   // ---- tape sub-tiles, in program order ----
   std::vector<PackTile> tiles;
-  uint32_t off = (uint32_t)(images * 4 * 16384);              // embedding fills are written by pack_emb_kernel
+  uint32_t off = (uint32_t)(images * 2 * NB * 16384);         // embedding fills are written by pack_emb_kernel
   size_t group_first = 0;
   uint32_t group_off = off;
   const IndexMap ident{0, 0, 0, 0};
@@ -1946,36 +2326,61 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
         end_group();
       }
     };
-    auto proj = [&](int h) {
+    auto qk_w = [&](int h) {                                  // G384: [Q|K] of pass h, one group per K atom
       const IndexMap hm{hsp, hs, h * per_pass, H};
-      for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s) tile(wp, d, half * 128 + s * 64, 0, 64, d, d, 1.f, nullptr, ident, hm);
-      end_group();
+      for (int kb = 0; kb < NA; ++kb) {
+        tile(wq, d, 0, kb * 64, 64, d, d, qscale, ln1w, hm, ident);
+        tile(wk, d, 0, kb * 64, 64, d, d, 1.f, ln1w, hm, ident);
+        end_group();
+      }
     };
-    auto fc1 = [&](int c) {
-      for (int kb = 0; kb < 4; ++kb) {
-        for (int s = 0; s < 2; ++s) tile(w1, d, c * 128 + s * 64, kb * 64, 64, ff, d, s1, ln2w, ident, ident);
+    auto v_w = [&](int h) {                                   // G384: V of pass h, two K atoms per group
+      const IndexMap hm{hsp, hs, h * per_pass, H};
+      for (int kb = 0; kb < NA; ++kb) {
+        tile(wv, d, 0, kb * 64, 64, d, d, 1.f, ln1w, hm, ident);
         if (kb & 1) end_group();
+      }
+    };
+    auto proj = [&](int h) {                                  // G256: one group of 256 rows; G384: one group per 128 rows
+      const IndexMap hm{hsp, hs, h * per_pass, H};
+      for (int nb = 0; nb < NB; ++nb) {
+        for (int s = 0; s < 2; ++s) tile(wp, d, nb * 128 + s * 64, 0, 64, d, d, 1.f, nullptr, ident, hm);
+        if (wide) end_group();
+      }
+      if (!wide) end_group();
+    };
+    auto fc1 = [&](int c) {                                   // G256: two K atoms per group; G384: one
+      for (int kb = 0; kb < NA; ++kb) {
+        for (int s = 0; s < 2; ++s) tile(w1, d, c * 128 + s * 64, kb * 64, 64, ff, d, s1, ln2w, ident, ident);
+        if (wide || (kb & 1)) end_group();
       }
     };
     auto fc2 = [&](int c) {
       for (int kb = 0; kb < 2; ++kb) {
-        for (int half = 0; half < 2; ++half) for (int s = 0; s < 2; ++s)
-          tile(w2, ff, half * 128 + s * 64, c * 128 + kb * 64, 64, d, ff, s2, nullptr, ident, ident);
-        end_group();
+        for (int nb = 0; nb < NB; ++nb) {
+          for (int s = 0; s < 2; ++s) tile(w2, ff, nb * 128 + s * 64, c * 128 + kb * 64, 64, d, ff, s2, nullptr, ident, ident);
+          if (wide) end_group();
+        }
+        if (!wide) end_group();
       }
     };
-    qkv(0);
-    for (int h = 1; h < npass; ++h) { qkv(h); proj(h - 1); }
+    if (wide) {
+      qk_w(0); v_w(0);
+      for (int h = 1; h < npass; ++h) { qk_w(h); proj(h - 1); v_w(h); }
+    } else {
+      qkv(0);
+      for (int h = 1; h < npass; ++h) { qkv(h); proj(h - 1); }
+    }
     proj(npass - 1);
     fc1(0); fc1(1); fc2(0);
-    for (int c = 2; c < 8; ++c) { fc1(c); fc2(c - 1); }
-    fc2(7);
+    for (int c = 2; c < NCH; ++c) { fc1(c); fc2(c - 1); }
+    fc2(NCH - 1);
   }
   const int p_tail = 3 + 16 * L;                              // ln_f.w, ln_f.b, sigma_emb.w/b, action_emb.w/b, action_pred.w/b
-  for (int kb = 0; kb < 4; ++kb) tile(prm[p_tail + 6], d, 0, kb * 64, 16, m.act_dim, d, 1.f, prm[p_tail], ident, ident);
+  for (int kb = 0; kb < NA; ++kb) tile(prm[p_tail + 6], d, 0, kb * 64, 16, m.act_dim, d, 1.f, prm[p_tail], ident, ident);
   end_group();
   if (off != tape_bytes) { set_error("internal: tape layout mismatch"); return BESO_E_INVALID; }
-  if (tiles.size() * sizeof(PackTile) > (1 << 20)) { set_error("internal: pack table too large"); return BESO_E_INVALID; }
+  if (tiles.size() * sizeof(PackTile) > (3 << 20)) { set_error("internal: pack table too large"); return BESO_E_INVALID; }
   BESO_CUDA(cudaMemcpyAsync(scratch, tiles.data(), tiles.size() * sizeof(PackTile), cudaMemcpyHostToDevice, st));
   pack_tiles_kernel<<<(unsigned)tiles.size(), 128, 0, st>>>(reinterpret_cast<const PackTile*>(scratch), tape);
   ++g_kernel_launches;
@@ -1986,20 +2391,20 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   // folded into the projection bias:  bproj_eff = bproj + Wproj (bv + Wv beta1).
   std::vector<VecCopy> vc, vc2;
   for (int l = 0; l < L; ++l) {
-    const uint32_t a = (uint32_t)(l * (kVecAFloats + kVecMFloats)), mo = a + kVecAFloats;
-    const uint32_t fo = (uint32_t)(vec_floats + (size_t)l * 2 * kD);
+    const uint32_t a = (uint32_t)(l * (vA + vM)), mo = a + vA;
+    const uint32_t fo = (uint32_t)(vec_floats + (size_t)l * 2 * DP);
     const float* ln1b = prm[p_layer(l, 1)];
     const float* ln2b = prm[p_layer(l, 3)];
     for (int h = 0; h < npass; ++h)
-      vc.push_back({prm[p_layer(l, 7)], a + kVecBq + h * 192, 64, d, qscale, prm[p_layer(l, 6)], ln1b, d, 0, IndexMap{hsp, hs, h * per_pass, H}});
-    vc.push_back({prm[p_layer(l, 9)], fo, kD, d, 1.f, prm[p_layer(l, 8)], ln1b, d, 0, ident});
-    vc2.push_back({prm[p_layer(l, 11)], fo + kD, kD, d, 1.f, prm[p_layer(l, 10)], w.vec + fo, d, 0, ident});
-    if (prec) vc.push_back({prm[p_layer(l, 13)], mo + kVecB1F, kFF, ff, 1.f, prm[p_layer(l, 12)], ln2b, d, 0, ident});
-    else vc.push_back({prm[p_layer(l, 13)], mo + kVecB1H, kFF, ff, kGeluInScale, prm[p_layer(l, 12)], ln2b, d, 1, ident});   // b1 / 4 as fp16
+      vc.push_back({prm[p_layer(l, 7)], a + vBq + h * vBqStride, 64, d, qscale, prm[p_layer(l, 6)], ln1b, d, 0, IndexMap{hsp, hs, h * per_pass, H}});
+    vc.push_back({prm[p_layer(l, 9)], fo, DP, d, 1.f, prm[p_layer(l, 8)], ln1b, d, 0, ident});
+    vc2.push_back({prm[p_layer(l, 11)], fo + DP, DP, d, 1.f, prm[p_layer(l, 10)], w.vec + fo, d, 0, ident});
+    if (prec) vc.push_back({prm[p_layer(l, 13)], mo + vB1F, FFP, ff, 1.f, prm[p_layer(l, 12)], ln2b, d, 0, ident});
+    else vc.push_back({prm[p_layer(l, 13)], mo + vB1H, FFP, ff, kGeluInScale, prm[p_layer(l, 12)], ln2b, d, 1, ident});   // b1 / 4 as fp16
   }
-  const uint32_t fa = (uint32_t)(L * (kVecAFloats + kVecMFloats));
-  vc.push_back({prm[p_tail + 7], fa + kVecBq, 16, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], d, 0, ident});
-  uint8_t* scratch2 = scratch + (1 << 20);
+  const uint32_t fa = (uint32_t)(L * (vA + vM));
+  vc.push_back({prm[p_tail + 7], fa + vBq, 16, m.act_dim, 1.f, prm[p_tail + 6], prm[p_tail + 1], d, 0, ident});
+  uint8_t* scratch2 = scratch + (3 << 20);
   const size_t n1 = vc.size();
   vc.insert(vc.end(), vc2.begin(), vc2.end());
   BESO_CUDA(cudaMemcpyAsync(scratch2, vc.data(), vc.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, st));
@@ -2013,11 +2418,11 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   es.actw = prm[p_tail + 4]; es.actb = prm[p_tail + 5];
   es.obs = m.obs_dim; es.act = m.act_dim; es.G = G; es.W = m.window; es.L = L; es.d = d; es.prec = prec ? 1 : 0;
   for (int l = 0; l < L; ++l) {
-    es.resid_bias[2 * l] = w.vec + vec_floats + (size_t)l * 2 * kD + kD;      // effective projection bias
+    es.resid_bias[2 * l] = w.vec + vec_floats + (size_t)l * 2 * DP + DP;      // effective projection bias
     es.resid_bias[2 * l + 1] = prm[p_layer(l, 15)];
   }
-  pack_emb_kernel<<<dim3(4, (unsigned)images), 256, 0, st>>>(es, tape);
-  pack_pend_kernel<<<1, kD, 0, st>>>(es, w.vec, kVecAFloats + kVecMFloats, kVecAFloats);
+  pack_emb_kernel<<<dim3(2 * NB, (unsigned)images), 256, 0, st>>>(es, tape, NB, wide ? 1 : 2);
+  pack_pend_kernel<<<1, DP, 0, st>>>(es, w.vec, vA + vM, vA, DP);
   g_kernel_launches += 2;
   BESO_CUDA(cudaGetLastError());
   BESO_CUDA(cudaStreamSynchronize(st));                       // the host tables above go out of scope
@@ -2044,7 +2449,9 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   const int hsp = padded_head(m), per_pass = 64 / hsp;
   p.hsp = hsp; p.npass = (m.n_heads + per_pass - 1) / per_pass;
   p.d_true = m.d; p.inv_d = 1.0f / (float)m.d;
-  const size_t n_fills = 4 + (size_t)L * 104 + 4;
+  const bool wide = m.d > G256::DP;
+  // (timeline buffer layout only: the issuer's per-job stamps come first, 6 * n_fills slots are reserved for them)
+  const size_t n_fills = wide ? 8 + (size_t)L * 64 : 4 + (size_t)L * 104 + 4;
   p.tape = reinterpret_cast<const uint8_t*>(w.tape);
   p.vec = w.vec;
   p.n_fills = (int)n_fills; p.L = L; p.G = m.goal_conditioned ? m.goal_len : 0; p.obs = m.obs_dim; p.act = m.act_dim;
@@ -2084,7 +2491,7 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   // halves L2 -> SMEM weight traffic but pays remote-arrive latency on every compute -> MMA hand-off; see
   // profiles/).  BESO_FAST_CG=2 selects the cta_group::2 path, kept parity-tested.
   static const int forced_cg = [] { const char* e = getenv("BESO_FAST_CG"); return e ? atoi(e) : 0; }();
-  const bool pairs_ok = !prec && p.npass == kH && hsp == 64 && p.n_tiles >= 2;   // the pair modes replay the fixed 4-pass group table
+  const bool pairs_ok = !wide && !prec && p.npass == kH && hsp == 64 && p.n_tiles >= 2;   // the pair modes replay the fixed 4-pass group table
   const int cg = (forced_cg == 2 && pairs_ok) ? 2 : 1;
   // BESO_FAST_MC=2: independent CTAs in clusters of 2 sharing the weight stream by TMA multicast
   static const int forced_mc = [] { const char* e = getenv("BESO_FAST_MC"); return e ? atoi(e) : 0; }();
@@ -2109,19 +2516,36 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   if (cg == 2 || mc == 2) {
     const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-    rc = cg == 2 ? launch(fast_sample_kernel<2, false, 1, false, 64>, grid, true) : launch(fast_sample_kernel<1, false, 2, false, 64>, grid, true);
+    rc = cg == 2 ? launch(fast_sample_kernel<2, false, 1, false, 64, 256>, grid, true) : launch(fast_sample_kernel<1, false, 2, false, 64, 256>, grid, true);
   } else {
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    const int sel = (prec ? 4 : 0) | (dbg ? 2 : 0) | (hsp == 32 ? 1 : 0);
+    if (wide) {
+      // the sampler's x / d1 / x2 / dU buffers of every CTA: stream-ordered scratch (the wide geometry has no shared
+      // memory left for them), freed behind the kernel
+      BESO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p.xscratch), (size_t)grid * 4 * kXFloats * sizeof(float), st));
+    }
+    const int sel = (wide ? 8 : 0) | (prec ? 4 : 0) | (dbg ? 2 : 0) | (hsp == 32 ? 1 : 0);
     switch (sel) {
-      case 0: rc = launch(fast_sample_kernel<1, false, 1, false, 64>, grid, false); break;
-      case 1: rc = launch(fast_sample_kernel<1, false, 1, false, 32>, grid, false); break;
-      case 2: rc = launch(fast_sample_kernel<1, true, 1, false, 64>, grid, false); break;
-      case 3: rc = launch(fast_sample_kernel<1, true, 1, false, 32>, grid, false); break;
-      case 4: rc = launch(fast_sample_kernel<1, false, 1, true, 64>, grid, false); break;
-      case 5: rc = launch(fast_sample_kernel<1, false, 1, true, 32>, grid, false); break;
-      case 6: rc = launch(fast_sample_kernel<1, true, 1, true, 64>, grid, false); break;
-      default: rc = launch(fast_sample_kernel<1, true, 1, true, 32>, grid, false); break;
+      case 0: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 256>, grid, false); break;
+      case 1: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 256>, grid, false); break;
+      case 2: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 256>, grid, false); break;
+      case 3: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 256>, grid, false); break;
+      case 4: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 256>, grid, false); break;
+      case 5: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 256>, grid, false); break;
+      case 6: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 256>, grid, false); break;
+      case 7: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 256>, grid, false); break;
+      case 8: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 384>, grid, false); break;
+      case 9: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 384>, grid, false); break;
+      case 10: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 384>, grid, false); break;
+      case 11: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 384>, grid, false); break;
+      case 12: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 384>, grid, false); break;
+      case 13: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 384>, grid, false); break;
+      case 14: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 384>, grid, false); break;
+      default: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 384>, grid, false); break;
+    }
+    if (wide) {
+      const cudaError_t fe = cudaFreeAsync(p.xscratch, st);
+      if (rc == BESO_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(xscratch)");
     }
   }
   if (rc) return rc;

@@ -262,6 +262,11 @@ __device__ __forceinline__ float4 lds128f_ro(uint32_t addr) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float4 lds128f_v(uint32_t addr) {       // ordered: never merged with an identical earlier load
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 // store 8 consecutive K elements (one 16-byte chunk) of one row as fp16
 __device__ __forceinline__ void st_chunk_h(uint8_t* atom, uint32_t row, uint32_t chunk, const float* v) {
   uint4 u;

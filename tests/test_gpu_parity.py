@@ -26,9 +26,11 @@ TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "simt": dict(rtol=1e-3, atol=1e-5)
 # fast mode against the 16-bit-faithful oracle (the reference with the kernel's operand roundings): measured max |err|
 # 5.7e-4 on random-init and 7.6e-4 on trained weights (profiles/r2_error_report.txt); SURVEY.md H1 asked for 1e-3
 TOL_FAITHFUL = dict(rtol=1e-3, atol=1e-3)
-# shapes the tensor-core kernel must take (checked against what the library reports): every d <= 256 fixture with a
-# linear head, including the block-push checkpoint shape (d = 240, 12 heads of 20) and the no-goal model (d = 64)
-TENSOR_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_push", "fwd_no_goal"}
+# shapes the tensor-core kernel must take (checked against what the library reports): every fixture with a linear head,
+# including the checkpoint shapes of both reference configs -- block-push (d = 240, 12 heads of 20: padded 256 / 32) and
+# kitchen (d = 360, 6 heads of 60: the 384-column geometry, heads padded to 64) -- and the no-goal model (d = 64)
+TENSOR_SHAPES = {"fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_push", "fwd_no_goal",
+                 "fwd_small_kitchen"}
 FWD = ["fwd_K256", "fwd_K256_t1", "fwd_K256_t4", "fwd_T16", "fwd_B256", "fwd_small_kitchen", "fwd_small_push",
        "fwd_mlp_head", "fwd_no_goal"]
 
@@ -460,8 +462,8 @@ def test_trained_checkpoint_weights_match_reference(name, cuda_device):
     from oracle import beso_oracle as O
     cfg, meta, a, sd = load_checkpoint_golden(name)
     g = cuda(a, cuda_device)
-    modes = ["precise", "simt"] + (["fast"] if fast_available(cfg) else [])
-    assert ("fast" in modes) == (name == "ckpt_push")
+    assert fast_available(cfg)                      # both checkpoint shapes run on the tensor cores
+    modes = ["precise", "simt", "fast"]
     for mode in modes:
         m = build_denoiser(cfg, cuda_device, mode=mode)
         full = with_masks(m, sd)
@@ -484,7 +486,7 @@ def test_trained_checkpoint_weights_match_reference(name, cuda_device):
             torch.testing.assert_close(out.cpu(), f16, **TOL_FAITHFUL)
 
 
-@pytest.mark.parametrize("name", ["fwd_K256", "fwd_T16", "fwd_B256", "fwd_small_push"])
+@pytest.mark.parametrize("name", ["fwd_K256", "fwd_T16", "fwd_B256", "fwd_small_push", "fwd_small_kitchen"])
 def test_fast_mode_against_16bit_faithful_oracle(name, cuda_device):
     """The fp16 tensor-core kernel against the reference WITH the kernel's operand roundings (fp16 GEMM operands, bf16
     embedding operands, folded LayerNorm affine): what is left is the kernel's in-op arithmetic (packed-fp16 LayerNorm
@@ -500,7 +502,7 @@ def test_fast_mode_against_16bit_faithful_oracle(name, cuda_device):
     torch.testing.assert_close(out, f16, **TOL_FAITHFUL)
 
 
-@pytest.mark.parametrize("kw", [dict(window=12, goal_len=1), dict(obs_dim=100), dict(act_dim=14)])
+@pytest.mark.parametrize("kw", [dict(window=12, goal_len=1), dict(obs_dim=100), dict(act_dim=14), dict(d=512, n_heads=8)])
 def test_shapes_outside_the_tensor_core_kernel_fall_back_to_the_cuda_core_kernel(kw, cuda_device):
     """The library decides what the tensor-core kernel takes (26 tokens, 100 observation features, 14 action dims are
     outside it); the default / precise mode then runs the fp32 CUDA-core kernel and still matches the oracle, the
