@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -2429,6 +2430,29 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   return BESO_OK;
 }
 
+// Stream-ordered scratch for the wide geometry's x buffers: a private memory pool that keeps its pages between launches
+// (the device's default pool hands freed memory back to the driver at every synchronisation, which makes each launch
+// pay a real allocation -- measured ~1 ms).
+static cudaMemPool_t scratch_pool(int device, cudaError_t* err) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  *err = cudaSuccess;
+  if (device < 0 || device >= 64) { *err = cudaErrorInvalidDevice; return nullptr; }
+  if (pools[device] == nullptr) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    *err = cudaMemPoolCreate(&pools[device], &props);
+    if (*err != cudaSuccess) { pools[device] = nullptr; return nullptr; }
+    unsigned long long keep = ~0ull;
+    *err = cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return pools[device];
+}
+
 static float* g_trace = nullptr;
 static long long* g_timeline = nullptr;
 void fast_set_trace(float* trace_dev) { g_trace = trace_dev; }
@@ -2522,7 +2546,12 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
     if (wide) {
       // the sampler's x / d1 / x2 / dU buffers of every CTA: stream-ordered scratch (the wide geometry has no shared
       // memory left for them), freed behind the kernel
-      BESO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p.xscratch), (size_t)grid * 4 * kXFloats * sizeof(float), st));
+      int device = 0;
+      BESO_CUDA(cudaGetDevice(&device));
+      cudaError_t pe;
+      cudaMemPool_t pool = scratch_pool(device, &pe);
+      if (pe != cudaSuccess) return cuda_fail(pe, "scratch memory pool");
+      BESO_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&p.xscratch), (size_t)grid * 4 * kXFloats * sizeof(float), pool, st));
     }
     const int sel = (wide ? 8 : 0) | (prec ? 4 : 0) | (dbg ? 2 : 0) | (hsp == 32 ? 1 : 0);
     switch (sel) {

@@ -1,6 +1,6 @@
 """GPU diagnostics: where one CTA of the FAST kernel spends its second model evaluation.
 
-    python tools/timeline_fast.py [T16|K256] [batch] [fast|precise] > gpurun_out/timeline.txt
+    python tools/timeline_fast.py [T16|K256|KITCHEN|PUSH] [batch] [fast|precise] > gpurun_out/timeline.txt
 
 Prints, in SM clock cycles, (a) the compute warps' phase durations and waits, (b) for the MMA
 issuer, per GEMM job, time spent waiting on barriers (compute) vs on the weight ring (producer).
@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from beso_b200 import K256, T16, _lib                          # noqa: E402
+from beso_b200 import BLOCKPUSH_CKPT, K256, KITCHEN_CKPT, T16, _lib   # noqa: E402
 from beso_b200.denoiser import build_denoiser                 # noqa: E402
 from beso_b200.sampling import get_sigmas_exponential, sample_ddim  # noqa: E402
 from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
@@ -22,14 +22,18 @@ from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "K256"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-    cfg = {"K256": K256, "T16": T16}[name]
+    cfg = {"K256": K256, "T16": T16, "KITCHEN": KITCHEN_CKPT, "PUSH": BLOCKPUSH_CKPT}[name]
     dev = torch.device("cuda:0")
     mode = sys.argv[3] if len(sys.argv) > 3 else "fast"
     m = build_denoiser(cfg, dev, mode=mode, state_dict=synthetic_state_dict(cfg, 1))
     x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=2).items()}
     sig = get_sigmas_exponential(4, 0.005, 1.0)
     L = cfg.n_layers
-    NF = 4 + 104 * L + 4
+    wide = cfg.d > 256                                       # the 384-column geometry: [Q|K] + V jobs, 12 FC1 chunks
+    hsp = 32 if cfg.d // cfg.n_heads <= 32 else 64
+    npass = -(-cfg.n_heads // (64 // hsp))
+    nch = 12 if wide else 8
+    NF = 8 + 64 * L if wide else 4 + 104 * L + 4
     tl = torch.zeros(6 * NF + 4096, dtype=torch.int64, device=dev)
     sample_ddim(m, x["state"], x["noise"], x["goal"], sig)            # warm-up
     _lib.lib().beso_debug_set_timeline(C.c_void_p(tl.data_ptr()))
@@ -37,7 +41,7 @@ def main():
     torch.cuda.synchronize()
     _lib.lib().beso_debug_set_timeline(None)
     tl = tl.cpu().tolist()
-    NJ = 2 + 24 * L
+    NJ = 2 + L * ((3 if wide else 2) * npass + 2 * nch)
     jobs = [tl[4 * j:4 * j + 4] for j in range(NJ)]          # per MMA job: start, barrier-wait, ring-wait, end
     ev = [v for v in tl[6 * NF:] if v]
     t0 = min(ev[0], jobs[0][0])
@@ -57,7 +61,7 @@ def main():
         print(f"L{l} LN1: wait {s - last:6d}  run {e - s:6d}")
         tot["wait"] += s - last; tot["ln"] += e - s
         last = e
-        for h in range(4):
+        for h in range(npass):
             d0, a0, a1, a2 = nxt(), nxt(), nxt(), nxt()
             print(f"L{l} head{h}: wait_acc {d0 - last:6d}  drain+sync {a0 - d0:6d}  attention {a1 - a0:6d}  sync {a2 - a1:6d}")
             tot["wait"] += d0 - last; tot["drain"] += a0 - d0; tot["attn"] += a1 - a0; tot["sync"] += a2 - a1
@@ -67,7 +71,7 @@ def main():
         tot["wait"] += s - last; tot["ln"] += e - s
         last = e
         row = []
-        for ch in range(8):
+        for ch in range(nch):
             s, e = nxt(), nxt()
             row.append(f"w{s - last}/g{e - s}")
             tot["wait"] += s - last; tot["gelu"] += e - s
@@ -80,10 +84,19 @@ def main():
     # ---- MMA issuer ----
     print("## MMA issuer per job: start, cycles waiting on compute barriers / on the weight ring, total issue time, gap to next job")
     names = ["EMB"]
-    layer = ["QKV0", "QKV1", "PROJ0", "QKV2", "PROJ1", "QKV3", "PROJ2", "PROJ3", "FC1_0", "FC1_1", "FC2_0"]
-    for c in range(2, 8):
-        layer += [f"FC1_{c}", f"FC2_{c - 1}"]
-    layer += ["FC2_7"]
+    layer = []
+    for h in range(npass + 1):
+        if h < npass:
+            layer.append(f"QK{h}" if wide else f"QKV{h}")
+        if h >= 1:
+            layer.append(f"PROJ{h - 1}")
+        if wide and h < npass:
+            layer.append(f"V{h}")
+    for c in range(nch + 1):
+        if c < nch:
+            layer.append(f"FC1_{c}")
+        if c >= 1:
+            layer.append(f"FC2_{c - 1}")
     for l in range(L):
         names += [f"L{l}.{n}" for n in layer]
     names += ["HEAD"]
