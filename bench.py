@@ -371,6 +371,26 @@ def main():
         extras["rollout_b1_ddim10_ms"] = {
             mname: timed(lambda: sample_ddim(models[mname], xr["state"], xr["noise"], xr["goal"], sig10), 20, 5, sync_ranks=False)
             for mname in ("fast", "precise")}
+        # the reference's REAL model shapes (frozen configs beside the shipped checkpoints): kitchen d = 360 / 6 heads of
+        # 60 / 6 layers (the 384-column geometry of the tensor-core kernel) and block-push d = 240 / 12 heads of 20 / 4
+        # layers (padded 256 / 32); one forward at batch 4096 and the predict()-shaped rollout call at batch 1
+        from beso_b200 import BLOCKPUSH_CKPT, KITCHEN_CKPT
+        ck = {}
+        for label, c in (("kitchen_d360", KITCHEN_CKPT), ("blockpush_d240", BLOCKPUSH_CKPT)):
+            csd = synthetic_state_dict(c, seed=7)
+            xi = {k: v.to(dev) for k, v in synthetic_inputs(c, 4096, seed=8).items()}
+            x1 = {k: v.to(dev) for k, v in synthetic_inputs(c, 1, seed=9).items()}
+            row = {}
+            for mname in ("fast", "precise"):
+                fm = build_denoiser(c, dev, mode=mname, state_dict=csd)
+                assert fm.fast_supported()                                # both shapes run the tensor-core kernel
+                ms = timed(lambda: fm(xi["state"], xi["action"], xi["goal"], xi["sigma"]), 10, 3, sync_ranks=False)
+                tf = 4096 * c.fwd_flops_per_seq() / (ms * 1e-3) / 1e12
+                ms1 = timed(lambda: sample_ddim(fm, x1["state"], x1["noise"], x1["goal"], sig10), 10, 3, sync_ranks=False)
+                row[mname] = {"fwd_b4096_ms": ms, "denoise_steps_per_s": 4096 / (ms * 1e-3), "tflops": tf,
+                              "frac_of_burst_peak": tf / burst, "rollout_b1_ddim10_ms": ms1}
+            ck[label] = row
+        extras["checkpoint_shapes"] = ck
         # training step (BASELINE config 3: block-push shape, batch 4096): fused loss + backward, tcgen05 GEMMs
         from beso_b200.training import loss_and_flat_grad
         tm = build_denoiser(B256, dev, mode="precise", state_dict=synthetic_state_dict(B256, 41))

@@ -31,7 +31,7 @@ EXPORTS = [
     "beso_denoise_fwd", "beso_sample_loop", "beso_sample_loop_noise", "beso_sample_loop_scaled", "beso_denoise_fwd_host", "beso_sample_loop_host",
     "beso_loss_fwd_bwd", "beso_loss_fwd_bwd_dropout", "beso_loss_fwd_bwd_dp", "beso_debug_gemm", "beso_comm_unique_id", "beso_comm_init", "beso_comm_destroy",
     "beso_allreduce_grads", "beso_kernel_launches", "beso_plan_rows_per_cta", "beso_device_sm_count",
-    "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate",
+    "beso_debug_set_trace", "beso_debug_set_timeline", "beso_debug_mma_rate", "beso_debug_set_precise_layout",
     "beso_opt_create", "beso_opt_destroy", "beso_opt_total", "beso_opt_step", "beso_window_gather",
 ]
 
@@ -112,6 +112,7 @@ def _declare(lib):
     lib.beso_kernel_launches.restype = C.c_int64
     lib.beso_plan_rows_per_cta.argtypes = [vp, i32, i32]
     lib.beso_device_sm_count.argtypes = [i32]
+    lib.beso_debug_set_precise_layout.argtypes = [i32]
     lib.beso_debug_set_trace.argtypes = [vp]
     lib.beso_debug_set_timeline.argtypes = [vp]
     lib.beso_debug_mma_rate.argtypes = [vp, vp, i32, vp]

@@ -169,7 +169,7 @@ static int check_call(beso_plan* p, int mode, int B, int t, uint32_t flags) {
   if (mode != BESO_MODE_PRECISE && mode != BESO_MODE_FAST && mode != BESO_MODE_SIMT) { set_error("unknown mode"); return BESO_E_INVALID; }
   if ((flags & BESO_FLAG_CFG) && (flags & BESO_FLAG_UNCOND)) { set_error("CFG and UNCOND are exclusive"); return BESO_E_INVALID; }
   if (mode == BESO_MODE_FAST && !p->fast_ok) {
-    set_error("fast (tcgen05) mode needs embed_dim <= 256, head size <= 64 (<= 6 attention passes), linear_output, <= 24 tokens, "
+    set_error("fast (tcgen05) mode needs embed_dim <= 384, head size <= 64 (<= 6 attention passes), linear_output, <= 24 tokens, "
               "obs <= 64, act <= 13; use precise mode");
     return BESO_E_UNSUPPORTED;
   }
@@ -187,7 +187,8 @@ static int run(beso_plan* p, int mode, const SampleArgs& sa, const float* state,
   // kernel uses as CFG scratch), else the fp32 CUDA-core kernel
   if (mode == BESO_MODE_PRECISE && p->fast_ok && !p->force_simt &&
       !(sa.n_steps && sa.sampler == BESO_SAMPLER_LMS && (flags & BESO_FLAG_CFG)))
-    return fast_launch(ws.fastp, p->desc, p->sm_count, sa, state, goal, x, sigma, out, B, t, flags, lambda, st, true);
+    return fast_launch(ws.fastp, p->desc, p->sm_count, sa, state, goal, x, sigma, out, B, t, flags, lambda, st, true,
+                       ws.fastq.tape ? &ws.fastq : nullptr);
   SimtLaunch L{};
   int rc = simt_plan_launch(ws.simt, t, p->max_smem, &L);
   if (rc) return rc;
@@ -252,6 +253,7 @@ int beso_plan_destroy(beso_plan* p) {
     if (s.simt_buf) cudaFree(s.simt_buf);
     fast_free(s.fast);
     fast_free(s.fastp);
+    fast_free(s.fastq);
   }
   if (p->h_pin) cudaFreeHost(p->h_pin);
   if (p->d_stage) cudaFree(p->d_stage);
@@ -276,10 +278,14 @@ int beso_plan_pack_weights(beso_plan* p, int slot, const float* const* prm, int 
   int rc = pack_simt(p, ws, prm, st);
   if (rc) return rc;
   if (p->fast_ok) {
-    rc = fast_pack(ws.fast, p->desc, prm, st, false);
+    rc = fast_pack(ws.fast, p->desc, prm, st, FAST_LAYOUT_F16);
     if (rc) return rc;
-    rc = fast_pack(ws.fastp, p->desc, prm, st, true);
+    rc = fast_pack(ws.fastp, p->desc, prm, st, FAST_LAYOUT_STACKED);
     if (rc) return rc;
+    if (fast_p128_supported(p->desc)) {
+      rc = fast_pack(ws.fastq, p->desc, prm, st, FAST_LAYOUT_P128);
+      if (rc) return rc;
+    }
   }
   ws.packed = true;
   return BESO_OK;
@@ -463,6 +469,7 @@ int beso_loss_fwd_bwd_dp(beso_plan* p, const float* state, const float* action, 
 }
 
 int64_t beso_kernel_launches(void) { return g_kernel_launches; }
+int beso_debug_set_precise_layout(int layout) { fast_set_prec_layout(layout); return BESO_OK; }
 int beso_debug_set_trace(float* trace_dev) { fast_set_trace(trace_dev); return BESO_OK; }
 int beso_debug_set_timeline(long long* dev) { fast_set_timeline(dev); return BESO_OK; }
 int beso_debug_mma_rate(long long* out_dev, const void* src_dev, int mode, void* stream) { return fast_mma_rate(out_dev, src_dev, mode, (cudaStream_t)stream); }

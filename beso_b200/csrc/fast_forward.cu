@@ -104,7 +104,8 @@ struct G256 {
   static constexpr uint32_t SmVecA = kSmVecA, VecBq = kVecBq, BqStride = 192, VecAFloats = kVecAFloats;
   static constexpr uint32_t SmVecM = kSmVecM, VecB1H = kVecB1H, VecB1F = kVecB1F, VecMFloats = kVecMFloats;
   static constexpr uint32_t SmStats = kSmStats, SmProg = kSmProg, SmSigv = kSmProg + 1024 + 4 * kXFloats * 4;
-  static constexpr bool XGlobal = false;
+  static constexpr bool XGlobal = false, HSingle = false;
+  static constexpr uint32_t ColAL = 0, SmYLo = 0, SmHLo = 0;          // (G256P only)
 };
 struct G384 {
   static constexpr int DP = 384, NA = 6, FF = 1536, NCH = 12;
@@ -115,8 +116,33 @@ struct G384 {
   // [pend(384) | b1: fp16 image / 4 (768 floats, fast) or fp32 image (1536 floats, PREC)]
   static constexpr uint32_t SmVecM = SmVecA + VecAFloats * 4, VecB1H = 384, VecB1F = 384, VecMFloats = 1920;
   static constexpr uint32_t SmStats = SmVecM + VecMFloats * 4, SmProg = SmStats + 2048, SmSigv = SmProg;
-  static constexpr bool XGlobal = true;
+  static constexpr bool XGlobal = true, HSingle = false;
+  static constexpr uint32_t ColAL = 0, SmYLo = 0, SmHLo = 0;          // (G256P only)
 };
+// G256P: the precise mode for embed_dim <= 256 on FULL 128-row tiles ("P128").  Every product is three MMAs,
+//     A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T          (fp16 images, fp32 accumulate; the lo.lo term is below 2^-22)
+// instead of the stacked layout's two MMAs per 64 sequence rows: 25 % fewer tensor-pipe cycles per row and, because the
+// weights now stream once per 128 rows instead of once per 64, half the weight traffic per row.  What makes it fit:
+//  * the lo image of the LayerNorm output (the A operand of QKV and FC1, K = 256) lives in TENSOR memory -- 128 columns
+//    of packed fp16 pairs, read by tcgen05.mma with a TMEM A operand -- so TMEM is X 256 | one scratch accumulator 128 |
+//    A_lo 128, and the schedule is the single-accumulator one of G384;
+//  * the lo images of the small A operands (embedding input, attention output Y, hidden chunk H) are shared-memory atoms;
+//    H is single-buffered (hi + lo = 64 KB), the ring is three 16 KB slots;
+//  * attention runs per 64-row half of the tile through the 64-row hi / lo staging buffer of the stacked mode: the warps
+//    that own rows 64..127 keep their Q | K | V in registers while the first half is processed.  Sequences never straddle
+//    row 64: a tile holds 2 x floor(64 / T) sequences.
+struct G256P {
+  static constexpr int DP = 256, NA = 4, FF = 1024, NCH = 8;
+  static constexpr uint32_t ColS0 = 256, ColS1 = 256, ColAL = 384;
+  static constexpr uint32_t SmRing = 65536, SmU = 114688;             // A_hi: 4 x 16 KB | ring: 3 x 16 KB | union
+  static constexpr uint32_t SmQkv = SmU, SmY = SmU + 51200, SmYLo = SmY + 16384;
+  static constexpr uint32_t SmH0 = SmU, SmH1 = SmU, SmHLo = SmU + 32768;
+  static constexpr uint32_t SmVecA = SmU + 83968, VecBq = kVecBq, BqStride = 192, VecAFloats = kVecAFloats;
+  static constexpr uint32_t SmVecM = SmVecA + VecAFloats * 4, VecB1H = kVecB1H, VecB1F = kVecB1F, VecMFloats = kVecMFloats;
+  static constexpr uint32_t SmStats = SmVecM + VecMFloats * 4, SmProg = SmStats + 2048, SmSigv = SmProg + 1024 + 4 * kXFloats * 4;
+  static constexpr bool XGlobal = false, HSingle = true;
+};
+static_assert(G256P::SmVecA == kSmVecA && G256P::SmSigv + 512 <= kSmBars, "P128 geometry: vectors and x buffers sit where G256 has them");
 static_assert(G384::SmSigv + 512 <= kSmBars, "wide geometry does not fit shared memory");
 // G384 weight ring: 16 KB slots, one ring group per slot; full barriers B_FULL0 + s, empty barriers B_WEMPTY0 + s (s < 6).
 // Producer and MMA issuer replay the same slot sequence; n_slots may differ between phases of the schedule.
@@ -559,8 +585,14 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // and the output goes to the hi / lo rows of the Y atom.
 // NH = 2: two warps share one item -- both compute the scores and the softmax, each the P V product of half of the
 // output columns (`half`); used when a tile has so few (sequence, query tile) items that warps would idle.
-template <class G, int NKT, bool HI, int HSP, bool SPLIT, int NH>
-__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co, int half) {
+// LAY: 0 = single fp16 image; 1 = split, stacked operand rows (SPLIT above); 2 = split, one 64-row half of a 128-row
+// tile (P128): Y row = yrow0 + staging row, the lo image of Y is a separate atom.
+template <class G, int NKT, bool HI, int HSP, int LAY, int NH>
+// ybar != 0: mbarrier (shared address) / parity to pass before Y is written -- "the previous pass's projection MMAs have
+// read Y" -- for the schedules that let that projection run under this pass's attention (single-accumulator geometries).
+__device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row0, int mt, int T, int co, int half, int yrow0,
+                                               uint32_t ybar, uint32_t ypar) {
+  constexpr bool SPLIT = LAY != 0;
   const uint32_t qkv = sbase + G::SmQkv + (uint32_t)co * 2u;
   constexpr int KS = HSP / 16;                   // 16-wide k steps over the head dimension
   constexpr int kLastRow = SPLIT ? 63 : kRows - 1;
@@ -678,18 +710,21 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   }
   // column e = n * 8 + (lane & 3) * 2 of the head: 16-byte chunk n of the row, bytes (lane & 3) * 4 within it
   uint32_t r_lo = (uint32_t)(row0 + i_lo), r_hi = (uint32_t)(row0 + i_hi);
-  if constexpr (SPLIT) {                          // sequence row -> its hi operand row (the lo row is 16 rows below)
+  if constexpr (LAY == 1) {                       // sequence row -> its hi operand row (the lo row is 16 rows below)
     r_lo = ((r_lo >> 4) << 5) | (r_lo & 15u);
     r_hi = ((r_hi >> 4) << 5) | (r_hi & 15u);
   }
+  if constexpr (LAY == 2) { r_lo += (uint32_t)yrow0; r_hi += (uint32_t)yrow0; }
+  constexpr uint32_t kYLo = LAY == 2 ? G::SmYLo - G::SmY : 2048u;   // byte distance of the lo image of a Y element
   const uint32_t y_lo = sbase + G::SmY + r_lo * 128u + (uint32_t)(lane & 3) * 4u, x_lo = (r_lo & 7u) << 4;
   const uint32_t y_hi = sbase + G::SmY + r_hi * 128u + (uint32_t)(lane & 3) * 4u, x_hi = (r_hi & 7u) << 4;
   const uint32_t n0 = ((uint32_t)co >> 3) + (uint32_t)nfirst;   // first 16-byte chunk of this warp's columns inside the Y row
+  if (ybar != 0u) spin_wait(ybar, ypar);          // (stays complete for the rest of the pass: later items pass at once)
   if (i_lo < T) {
 #pragma unroll
     for (int n = 0; n < NO; ++n) {
       const uint32_t a = y_lo + (((n0 + (uint32_t)n) << 4) ^ x_lo);
-      if constexpr (SPLIT) { uint32_t h, l; split2(o[n][0], o[n][1], h, l); sts32(a, h); sts32(a + 2048u, l); }
+      if constexpr (SPLIT) { uint32_t h, l; split2(o[n][0], o[n][1], h, l); sts32(a, h); sts32(a + kYLo, l); }
       else sts32(a, pack_f16x2(o[n][0], o[n][1]));
     }
   }
@@ -697,13 +732,14 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
 #pragma unroll
     for (int n = 0; n < NO; ++n) {
       const uint32_t a = y_hi + (((n0 + (uint32_t)n) << 4) ^ x_hi);
-      if constexpr (SPLIT) { uint32_t h, l; split2(o[n][2], o[n][3], h, l); sts32(a, h); sts32(a + 2048u, l); }
+      if constexpr (SPLIT) { uint32_t h, l; split2(o[n][2], o[n][3], h, l); sts32(a, h); sts32(a + kYLo, l); }
       else sts32(a, pack_f16x2(o[n][2], o[n][3]));
     }
   }
 }
-template <class G, int HSP, bool SPLIT, int NH>
-__device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_slots, int half, int lane, int S, int T) {
+template <class G, int HSP, int LAY, int NH>
+__device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_slots, int half, int lane, int S, int T, int yrow0,
+                                                uint32_t ybar, uint32_t ypar) {
   constexpr int NSUB = 64 / HSP;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
   for (int item = slot; item < S * MT * NSUB; item += n_slots) {
@@ -711,27 +747,27 @@ __device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_
     const int mt = MT - 1 - it2 / S, s = it2 % S;     // later query tiles see more keys: schedule them first
     const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
     const int co = sub * HSP;
-    if (mt == 0) { if (hi) attention_item<G, 1, true, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); else attention_item<G, 1, false, HSP, SPLIT, NH>(sbase, lane, s * T, 0, T, co, half); }
-    else { if (hi) attention_item<G, 2, true, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); else attention_item<G, 2, false, HSP, SPLIT, NH>(sbase, lane, s * T, mt, T, co, half); }
+    if (mt == 0) { if (hi) attention_item<G, 1, true, HSP, LAY, NH>(sbase, lane, s * T, 0, T, co, half, yrow0, ybar, ypar); else attention_item<G, 1, false, HSP, LAY, NH>(sbase, lane, s * T, 0, T, co, half, yrow0, ybar, ypar); }
+    else { if (hi) attention_item<G, 2, true, HSP, LAY, NH>(sbase, lane, s * T, mt, T, co, half, yrow0, ybar, ypar); else attention_item<G, 2, false, HSP, LAY, NH>(sbase, lane, s * T, mt, T, co, half, yrow0, ybar, ypar); }
   }
 }
 template <class G, int HSP, bool SPLIT>
-__device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T) {
+__device__ __forceinline__ void attention_head_t(uint32_t sbase, int awarp, int lane, int S, int T, uint32_t ybar, uint32_t ypar) {
   // The precise mode's tiles hold at most 64 rows = 4 items for the 10 attention warps: pairs of warps share an item.
   // (Only there: the single-pass fp16 kernel has 8-10 items, and a second item body would only grow its image.)
   if constexpr (SPLIT) {
     if (S * ((T + 15) >> 4) * (64 / HSP) * 2 <= kAttnWarps) {
-      attention_items<G, HSP, SPLIT, 2>(sbase, awarp >> 1, kAttnWarps / 2, awarp & 1, lane, S, T);
+      attention_items<G, HSP, SPLIT ? 1 : 0, 2>(sbase, awarp >> 1, kAttnWarps / 2, awarp & 1, lane, S, T, 0, ybar, ypar);
       return;
     }
   }
-  attention_items<G, HSP, SPLIT, 1>(sbase, awarp, kAttnWarps, 0, lane, S, T);
+  attention_items<G, HSP, SPLIT ? 1 : 0, 1>(sbase, awarp, kAttnWarps, 0, lane, S, T, 0, ybar, ypar);
 }
 // The padded head size is a template parameter of the kernel: only the attention code of the model's head size is in
 // the kernel image (the fused kernel is ~13 k instructions; its hot paths have to stay resident in the instruction cache).
 template <class G, int HSP>
-__device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T) {
-  attention_head_t<G, HSP, false>(sbase, awarp, lane, S, T);
+__device__ __noinline__ void attention_head(uint32_t sbase, int awarp, int lane, int S, int T, uint32_t ybar, uint32_t ypar) {
+  attention_head_t<G, HSP, false>(sbase, awarp, lane, S, T, ybar, ypar);
 }
 
 // FC1 chunk accumulator (buffer b) -> + b1 -> erf-GELU (packed fp16) -> H[b] (two K atoms, fp16).
@@ -968,11 +1004,31 @@ __device__ __noinline__ void drain_qkv_p(const Compute c, uint32_t bq_s) {
 // (attention_item<..., SPLIT = true>): the operands come out of shared memory once per 16 x 8 tile, which keeps the
 // attention phase off the shared-memory port the tensor pipe is streaming its operands through.
 template <class G, int HSP>
-__device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T) {
-  attention_head_t<G, HSP, true>(sbase, awarp, lane, S, T);
+__device__ __noinline__ void attention_head_p(uint32_t sbase, int awarp, int lane, int S, int T, uint32_t ybar, uint32_t ypar) {
+  attention_head_t<G, HSP, true>(sbase, awarp, lane, S, T, ybar, ypar);
 }
 
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)); }
+// The same function in 17 fp32 instructions + 2 MUFU instead of erff's ~40 with a divergent branch:
+//   gelu(x) = x Phi(x),  Phi(x) = 1 - erfc(a) / 2 (x >= 0),  erfc(a) / 2 (x < 0),  a = |x| / sqrt 2,
+//   erfc(a) = t q(t) exp(-a^2),  t = 1 / (1 + 0.3275911 a)        (the form of Abramowitz & Stegun 7.1.26)
+// with a degree-6 q fitted to erfc (weighted least squares on [0, 7]): |erfc error| < 1.2e-8, and evaluated in fp32 the
+// GELU is within 6.1e-7 of the exact one over [-10, 10], where 0.5 x (1 + erf(x / sqrt 2)) in fp32 is within 6.8e-7 (tools/fit_gelu.py prints the fit and both errors).  No cancellation on either
+// side: the negative branch never forms 1 - (1 - small).
+__device__ __forceinline__ float gelu_fast32(float x) {
+  const float a = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+  float q = fmaf(-0.295823318f, t, 1.49200876f);
+  q = fmaf(q, t, -2.05966192f);
+  q = fmaf(q, t, 2.01235594f);
+  q = fmaf(q, t, -0.73243192f);
+  q = fmaf(q, t, 0.425816119f);
+  q = fmaf(q, t, 0.157736351f);
+  const float e = ex2f(a * a * -1.4426950408889634f);
+  const float half_erfc = 0.5f * (q * t) * e;
+  return x * (x >= 0.0f ? 1.0f - half_erfc : half_erfc);
+}
 // FC1 chunk accumulator (buffer b) -> + b1 -> exact erf-GELU (fp32) -> split -> H[b] (two K atoms).
 // b1_s = shared address of this chunk's 128 biases (fp32).
 template <class G>
@@ -993,8 +1049,8 @@ __device__ __noinline__ void drain_gelu_p(const Compute c, int tb, int b, uint32
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       const float4 b0 = lds128f_ro(bias_s + (uint32_t)(cs + i) * 4u);
-      g[i] = gelu_erf(g[i] + b0.x); g[i + 1] = gelu_erf(g[i + 1] + b0.y);
-      g[i + 2] = gelu_erf(g[i + 2] + b0.z); g[i + 3] = gelu_erf(g[i + 3] + b0.w);
+      g[i] = gelu_fast32(g[i] + b0.x); g[i + 1] = gelu_fast32(g[i + 1] + b0.y);
+      g[i + 2] = gelu_fast32(g[i + 2] + b0.z); g[i + 3] = gelu_fast32(g[i + 3] + b0.w);
     }
     const uint32_t k0 = (uint32_t)cs >> 3;
     st_chunk_split(atom + ((k0 << 4) ^ c.rx4), g);
@@ -1006,6 +1062,216 @@ __device__ __noinline__ void drain_gelu_p(const Compute c, int tb, int b, uint32
   emit(vb, b1_s + 256u, h_hi + 16384u);
   fence_async_smem();
   c.arrive(B_OP_READY0B + b);
+}
+
+// ================================ P128: the precise mode on full 128-row tiles (geometry G256P) =================
+// One thread per (row, column half) as in the fp16 mode; every operand is written as an fp16 hi image and an fp16 lo
+// image (x = hi + lo).  Row -> sequence mapping: rows [0, 64) hold the first S / 2 sequences, rows [64, 128) the rest.
+__device__ __forceinline__ void st_words16(uint32_t dst, const uint32_t (&w)[16]) {       // 32 fp16 = 64 contiguous bytes
+  sts128(dst, w[0], w[1], w[2], w[3]); sts128(dst + 16, w[4], w[5], w[6], w[7]);
+  sts128(dst + 32, w[8], w[9], w[10], w[11]); sts128(dst + 48, w[12], w[13], w[14], w[15]);
+}
+__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+}
+
+// A <- split(LayerNorm0(X + pend)): hi image -> the shared-memory A atoms, lo image -> tensor memory (A_lo, packed
+// pairs).  Exact two-pass statistics in three sweeps over X (mean | centred squares | normalise): a sweep is four
+// tcgen05.ld of 32 columns, cheaper than parking 128 values per thread.
+template <bool DBG>
+__device__ __noinline__ void ln_pass_p128(const Compute c, uint32_t vec_s, float inv_d, int d_true, float* trace_row) {
+  using G = G256P;
+  float va[32], vb[32];
+  const int col0 = c.hf * 128;
+  float* stats = reinterpret_cast<float*>(c.sm + G::SmStats);        // [sum: 2 x 128 | squares: 2 x 128]
+  auto start = [&]() {
+    tmem_ld32(c.lane_addr(kColX + col0), va);
+    tmem_ld32(c.lane_addr(kColX + col0 + 32), vb);
+  };
+  auto sweep = [&](auto&& f) {                                       // chunks 0, 1 are in flight on entry
+    tmem_wait_ld();
+    f(va, 0);
+    tmem_ld32(c.lane_addr(kColX + col0 + 64), va);
+    f(vb, 1);
+    tmem_ld32(c.lane_addr(kColX + col0 + 96), vb);
+    tmem_wait_ld();
+    f(va, 2);
+    f(vb, 3);
+  };
+  // (volatile loads of pend: the three sweeps must not share them and keep 128 values live)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  start();
+  sweep([&](float (&v)[32], int ch) {
+    const int col = col0 + ch * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 pd = lds128f_v(vec_s + (uint32_t)(col + i) * 4u);
+      const float a0 = v[i] + pd.x, a1 = v[i + 1] + pd.y, a2 = v[i + 2] + pd.z, a3 = v[i + 3] + pd.w;
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      if (DBG) {
+        if (trace_row != nullptr) { float* tr = trace_row + col + i; tr[0] = a0; tr[1] = a1; tr[2] = a2; tr[3] = a3; }
+      }
+    }
+  });
+  const float sum = (s0 + s1) + (s2 + s3);
+  stats[c.hf * kRows + c.row] = sum;
+  start();
+  compute_sync();
+  const float mean = (sum + stats[(c.hf ^ 1) * kRows + c.row]) * inv_d;
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  sweep([&](float (&v)[32], int ch) {
+    const int col = col0 + ch * 32, nv = d_true - col;               // true lanes of this chunk (padding columns are zero, not mean)
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 pd = lds128f_v(vec_s + (uint32_t)(col + i) * 4u);
+      const float t0 = (v[i] + pd.x) - mean, t1 = (v[i + 1] + pd.y) - mean, t2 = (v[i + 2] + pd.z) - mean, t3 = (v[i + 3] + pd.w) - mean;
+      if (i < nv) q0 = fmaf(t0, t0, q0);
+      if (i + 1 < nv) q1 = fmaf(t1, t1, q1);
+      if (i + 2 < nv) q2 = fmaf(t2, t2, q2);
+      if (i + 3 < nv) q3 = fmaf(t3, t3, q3);
+    }
+  });
+  const float sq = (q0 + q1) + (q2 + q3);
+  stats[256 + c.hf * kRows + c.row] = sq;
+  start();
+  compute_sync();
+  const float var = (sq + stats[256 + (c.hf ^ 1) * kRows + c.row]) * inv_d;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  sweep([&](float (&v)[32], int ch) {
+    const int col = col0 + ch * 32;                                  // 32 columns = chunks k0 .. k0 + 3 of one K atom
+    const uint32_t atom = c.sbase + kSmA + (uint32_t)(col >> 6) * 16384u, k0 = (uint32_t)(col & 63) >> 3;
+    uint32_t lo[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 p0 = lds128f_v(vec_s + (uint32_t)(col + k * 8) * 4u), p1 = lds128f_v(vec_s + (uint32_t)(col + k * 8 + 4) * 4u);
+      const float* e = v + k * 8;
+      uint32_t h[4];
+      split2(((e[0] + p0.x) - mean) * rstd, ((e[1] + p0.y) - mean) * rstd, h[0], lo[k * 4 + 0]);
+      split2(((e[2] + p0.z) - mean) * rstd, ((e[3] + p0.w) - mean) * rstd, h[1], lo[k * 4 + 1]);
+      split2(((e[4] + p1.x) - mean) * rstd, ((e[5] + p1.y) - mean) * rstd, h[2], lo[k * 4 + 2]);
+      split2(((e[6] + p1.z) - mean) * rstd, ((e[7] + p1.w) - mean) * rstd, h[3], lo[k * 4 + 3]);
+      sts128(c.chunk_addr(atom, k0 + (uint32_t)k), h[0], h[1], h[2], h[3]);
+    }
+    tmem_st16(c.lane_addr(G::ColAL + (uint32_t)(col >> 1)), lo);     // K element k -> column k / 2
+  });
+  tmem_wait_st();
+  fence_async_smem();
+  tc_fence_before();
+  c.arrive(B_A_READY);
+}
+
+// Causal attention of one 64-row half of the tile out of the hi / lo staging buffer; Y rows yrow0 .. yrow0 + 63.
+template <int HSP>
+__device__ __noinline__ void attention_half_p128(uint32_t sbase, int slot, int n_slots, int lane, int Sh, int T, int yrow0,
+                                                 uint32_t ybar, uint32_t ypar) {
+  using G = G256P;
+  if (Sh * ((T + 15) >> 4) * (64 / HSP) * 2 <= n_slots) attention_items<G, HSP, 2, 2>(sbase, slot >> 1, n_slots >> 1, slot & 1, lane, Sh, T, yrow0, ybar, ypar);
+  else attention_items<G, HSP, 2, 1>(sbase, slot, n_slots, 0, lane, Sh, T, yrow0, ybar, ypar);
+}
+
+// One attention pass of the compute warps: [Q|K] accumulator, then V accumulator -> registers (hi / lo packed) ->
+// staging and attention, half by half.  The warps of rows 64..127 hold their 96 packed words while the first half
+// is processed by the warps of rows 0..63 and the helpers.  Barriers of the 10 attention warps per pass:
+//   S1 staging(half 0) complete | S2 attention(half 0) done | S3 staging(half 1) complete | S4 attention(half 1) done
+template <int HSP>
+__device__ __noinline__ uint32_t attention_pass_p128(Compute c, uint32_t bq_s, int S, int T) {
+  using G = G256P;
+  const int colb = c.hf * 32, Sh = S >> 1;
+  const bool upper = c.wq >= 2;                                      // warp-uniform
+  uint32_t qh[16], ql[16], kh[16], kl[16], vh[16], vl[16];
+  const uint32_t dst = c.sbase + G::SmQkv + (uint32_t)(c.row & 63) * kQkvStride + (uint32_t)colb * 2u;
+  constexpr uint32_t kLoImg = 64u * kQkvStride;
+  {
+    float v0[32], v1[32];
+    c.wait(B_ACC_FULL0);
+    tc_fence_after();
+    tmem_ld32(c.lane_addr(G::ColS0 + colb), v0);
+    tmem_ld32(c.lane_addr(G::ColS0 + 64 + colb), v1);
+    tmem_wait_ld();
+    tc_fence_before();
+    c.arrive(B_ACC_EMPTY0);                                          // the V job may overwrite the accumulator
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {                                // Q (+ bias)
+      const float4 b0 = lds128f_ro(bq_s + (uint32_t)(colb + i) * 4u);
+      v0[i] += b0.x; v0[i + 1] += b0.y; v0[i + 2] += b0.z; v0[i + 3] += b0.w;
+    }
+    split32(v0, qh, ql);
+    split32(v1, kh, kl);
+    if (!upper) {                                                    // (the V job is running)
+      st_words16(dst, qh); st_words16(dst + kLoImg, ql);
+      st_words16(dst + 128, kh); st_words16(dst + 128 + kLoImg, kl);
+    }
+    c.wait(B_ACC_FULL0);
+    tc_fence_after();
+    tmem_ld32(c.lane_addr(G::ColS0 + colb), v0);
+    tmem_wait_ld();
+    tc_fence_before();
+    c.arrive(B_ACC_EMPTY0);
+    split32(v0, vh, vl);
+  }
+  const int awarp = c.ctid >> 5;                                     // 0..7; rows 0..63 are warps 0, 1, 4, 5
+  if (!upper) { st_words16(dst + 256, vh); st_words16(dst + 256 + kLoImg, vl); }
+  // the previous pass's projection (issued behind this pass's V job) must have read Y before Y is rewritten: the
+  // attention items wait for it right before their output stores
+  const uint32_t ybar = c.bar(B_Y_EMPTY), ypar = (c.phases >> B_Y_EMPTY) & 1u;
+  c.phases ^= 1u << B_Y_EMPTY;
+  attn_sync();                                                       // S1
+  if (!upper) attention_half_p128<HSP>(c.sbase, (awarp & 1) | ((awarp >> 2) << 1), 6, c.lane, Sh, T, 0, ybar, ypar);
+  attn_sync();                                                       // S2
+  if (upper) {
+    st_words16(dst, qh); st_words16(dst + kLoImg, ql);
+    st_words16(dst + 128, kh); st_words16(dst + 128 + kLoImg, kl);
+    st_words16(dst + 256, vh); st_words16(dst + 256 + kLoImg, vl);
+  }
+  attn_sync();                                                       // S3
+  attention_half_p128<HSP>(c.sbase, awarp, kAttnWarps, c.lane, Sh, T, 64, ybar, ypar);
+  fence_async_smem();
+  c.arrive(B_Y_READY);
+  attn_sync();                                                       // S4: staging may be overwritten by the next pass
+  return c.phases;
+}
+
+// FC1 chunk accumulator -> + b1 -> exact erf-GELU (fp32) -> hi / lo images of H (one buffer: FC2 of the previous
+// chunk must have read it before it is overwritten).  b1_s = shared address of this chunk's 128 biases (fp32).
+__device__ __noinline__ uint32_t drain_gelu_p128(Compute c, uint32_t b1_s) {
+  using G = G256P;
+  float va[32], vb[32];
+  const uint32_t s_col = G::ColS0 + c.hf * 32;
+  tmem_ld32(c.lane_addr(s_col), va);
+  tmem_ld32(c.lane_addr(s_col + 64), vb);
+  tmem_wait_ld();
+  tc_fence_before();
+  c.arrive(B_ACC_EMPTY0);
+  auto gelu32 = [&](float (&v)[32], uint32_t bias_s, uint32_t (&h)[16], uint32_t (&l)[16]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b0 = lds128f_ro(bias_s + (uint32_t)i * 4u);
+      v[i] = gelu_fast32(v[i] + b0.x); v[i + 1] = gelu_fast32(v[i + 1] + b0.y);
+      v[i + 2] = gelu_fast32(v[i + 2] + b0.z); v[i + 3] = gelu_fast32(v[i + 3] + b0.w);
+    }
+    split32(v, h, l);
+  };
+  // this thread's 32 columns of a K atom = its chunks hf * 4 .. hf * 4 + 3
+  auto store = [&](uint32_t atom_off, const uint32_t (&h)[16], const uint32_t (&l)[16]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a = c.chunk_addr(c.sbase + G::SmH0 + atom_off, (uint32_t)(c.hf * 4 + k));
+      sts128(a, h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+      sts128(a + (G::SmHLo - G::SmH0), l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+    }
+  };
+  uint32_t h[16], l[16];
+  gelu32(va, b1_s + (uint32_t)(c.hf * 32) * 4u, h, l);
+  c.wait(B_OP_EMPTY0);                    // FC2 of the previous chunk has consumed H
+  store(0, h, l);
+  fence_async_smem();                     // K atom 0 of H is complete: FC2's first k-block may start
+  c.arrive(B_OP_READY0);
+  gelu32(vb, b1_s + (uint32_t)(64 + c.hf * 32) * 4u, h, l);
+  store(16384, h, l);
+  fence_async_smem();
+  c.arrive(B_OP_READY0B);
+  return c.phases;
 }
 
 // ---- the single-warp roles: one out-of-line step per ring group (small I-cache footprint).  All state is
@@ -1139,19 +1405,33 @@ struct EmbedTask {
   const float* src;      // obs atom: state / goal vector of this row (nullptr = zeros)
   bool is_goal;          // src is a goal vector (rollout scaling zeroes goal dimensions)
   int row, atom, vs, tok, xoff;   // xoff >= 0: action row, offset of its act values in the tile's x buffer
-  int part;              // PREC: 0 = fp16 hi image of the row, 1 = lo image; -1 = bf16 (fp16-mode embedding GEMM)
+  int part;              // PREC: 0 = fp16 hi image of the row, 1 = lo image, 2 = both (P128); -1 = bf16 (fp16-mode embedding GEMM)
   bool valid;
 };
-template <bool PREC>
+// Sequence row -> (virtual sequence of the tile, token).  LAY 2 (P128): rows [0, 64) hold the first S / 2 sequences,
+// rows [64, 128) the others (a sequence never straddles row 64); rows beyond them get vs = S (invalid).
+template <int LAY>
+__device__ __forceinline__ void row_to_seq(int srow, int T, int S, int& vs, int& tok) {
+  if constexpr (LAY == 2) {
+    const int Sh = S >> 1, r = srow & 63, q = r / T;
+    tok = r - q * T;
+    vs = q < Sh ? (srow >> 6) * Sh + q : S;
+  } else {
+    vs = srow / T;
+    tok = srow - vs * T;
+  }
+}
+// LAY: 0 = fp16 mode (bf16 embedding operand), 1 = precise, stacked hi / lo operand rows, 2 = precise, P128 (the thread
+// writes both images of its row)
+template <int LAY>
 __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int tile) {
   const bool cfg = (p.flags & BESO_FLAG_CFG) != 0;
   EmbedTask e;
   e.row = c.ctid & (kRows - 1);
   e.atom = c.ctid >> 7;
-  const int srow = PREC ? ((e.row >> 5) << 4) | (e.row & 15) : e.row;   // sequence row of this operand row
-  e.part = PREC ? (e.row >> 4) & 1 : -1;
-  e.vs = srow / p.T;
-  e.tok = srow - e.vs * p.T;
+  const int srow = LAY == 1 ? ((e.row >> 5) << 4) | (e.row & 15) : e.row;   // sequence row of this operand row
+  e.part = LAY == 1 ? (e.row >> 4) & 1 : (LAY == 2 ? 2 : -1);
+  row_to_seq<LAY>(srow, p.T, p.S, e.vs, e.tok);
   const int ls = cfg ? (e.vs >> 1) : e.vs;
   const int seq = tile * (cfg ? p.S / 2 : p.S) + ls;
   e.valid = e.vs < p.S && seq < p.B;
@@ -1170,10 +1450,12 @@ __device__ EmbedTask make_embed_task(const Compute& c, const FastParams& p, int 
 
 // A <- embedding-GEMM input rows: [obs atom | misc atom] (see file header), atoms 2..3 untouched.
 // One (row, atom) per thread; all global loads of a row are issued before any is used.
-template <bool PREC>
+template <int LAY>
 __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask e, int obs, int act, uint32_t flags,
                                                float sigma_data, const float* xsrc, const float* sigv,
                                                const float* in_tab, const float* goal_keep) {
+  constexpr bool PREC = LAY != 0;
+  constexpr uint32_t kLoAtom = 32768;              // P128: the lo image of A atom a is atom a + 2
   uint8_t* atom = c.sm + kSmA + e.atom * 16384;
   if (e.atom == 0) {
     float v[64];
@@ -1201,7 +1483,14 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
         for (int i = 0; i < 64; ++i) if (i < obs) v[i] = __fmul_rn(v[i], __ldg(goal_keep + i));
       }
     }
-    if constexpr (PREC) {
+    if constexpr (LAY == 2) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) st_chunk_h(atom, e.row, ch, v + ch * 8);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] -= __half2float(__float2half_rn(v[i]));
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) st_chunk_h(atom + kLoAtom, e.row, ch, v + ch * 8);
+    } else if constexpr (PREC) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) if (e.part) v[i] -= __half2float(__float2half_rn(v[i]));
 #pragma unroll
@@ -1237,6 +1526,11 @@ __device__ __noinline__ void build_embed_input(const Compute c, const EmbedTask 
         v[i] = x;
       }
       if constexpr (PREC) st_chunk_h(atom, e.row, ch, v); else st_chunk(atom, e.row, ch, v);
+      if constexpr (LAY == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] -= __half2float(__float2half_rn(v[i]));
+        st_chunk_h(atom + kLoAtom, e.row, ch, v);
+      }
     }
   }
   fence_async_smem();
@@ -1312,9 +1606,10 @@ __device__ __noinline__ void eval_prologue(const Compute c, const FastParams& p,
     xb.sigv[i] = sa.n_steps ? s_eval : ((seq0 + ls < p.B) ? __ldg(p.sigma + seq0 + ls) : 1.0f);
   }
   compute_sync();
-  const EmbedTask etask = make_embed_task<PREC>(c, p, tile);
+  constexpr int LAY = !PREC ? 0 : (std::is_same_v<G, G256P> ? 2 : 1);
+  const EmbedTask etask = make_embed_task<LAY>(c, p, tile);
   stamp<DBG>(c);
-  build_embed_input<PREC>(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv, sa.in_tab, sa.goal_keep);
+  build_embed_input<LAY>(c, etask, p.obs, p.act, p.flags, p.sigma_data, second ? xb.x2 : xb.xcur, xb.sigv, sa.in_tab, sa.goal_keep);
   stamp<DBG>(c);
 }
 
@@ -1337,7 +1632,11 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
   c.wait(B_X_DONE);
   tc_fence_after();
   stamp<DBG>(c);
-  if constexpr (G::DP == 384) {
+  constexpr bool P128 = std::is_same_v<G, G256P>;
+  constexpr int LAY = !PREC ? 0 : (P128 ? 2 : 1);
+  if constexpr (P128) {
+    ln_pass_p128<DBG>(c, c.sbase + G::SmVecA, p.inv_d, p.d_true, trace_row);
+  } else if constexpr (G::DP == 384) {
     if constexpr (PREC) ln_pass_pw<DBG>(c, c.sbase + G::SmVecA, p.inv_d, p.d_true, trace_row);
     else ln_pass_w<DBG>(c, c.sbase + G::SmVecA, p.inv_d, trace_row);
   } else {
@@ -1353,12 +1652,13 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
   tmem_wait_ld();
   tc_fence_before();
   c.arrive(B_ACC_EMPTY0);
-  if constexpr (PREC) {                             // hi lane + lo lane of the sequence row
+  if constexpr (LAY == 1) {                         // hi lane + lo lane of the sequence row
 #pragma unroll
     for (int a = 0; a < 16; ++a) pr[a] += shx16(pr[a]);
   }
   const float* hb = vecA + G::VecBq;
-  const int vs = c.srow / p.T, tok = c.srow - vs * p.T;
+  int vs, tok;
+  row_to_seq<LAY>(c.srow, p.T, p.S, vs, tok);
   const int j = tok - 1 - p.G;
   const int ls = cfg ? (vs >> 1) : vs;
   const bool act_row = (c.hf == 0) && !c.is_lo && vs < p.S && tok > p.G && (j & 1) && (ls < ns);
@@ -1450,14 +1750,17 @@ __device__ __noinline__ uint32_t eval_epilogue(Compute c, const FastParams& p, c
 // is free again when both CTAs' MMAs have read it (multicast commits).  Halves the L2 -> SM request traffic,
 // which at full-chip scale is within a factor 1.5 of the L2 throughput cap.
 // PREC = true: fp32-equivalent mode (split operands, 64 sequence rows per tile; see the PREC section above).
-// DP = 256 / 384: geometry (G256 / G384 above).
-template <int CG, bool DBG, int MC, bool PREC, int HSP, int DP>
+// GEO = 0 / 1 / 2: geometry G256 / G384 / G256P above (G256P is the precise mode on full tiles, "P128").
+template <int CG, bool DBG, int MC, bool PREC, int HSP, int GEO>
 __global__ void __launch_bounds__(kThreads, 1)
 fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__ SampleArgs sa) {
   static_assert(!PREC || (CG == 1 && MC == 1), "the precise mode runs single-CTA MMAs");
-  static_assert(DP == 256 || (DP == 384 && CG == 1 && MC == 1), "the wide geometry runs single-CTA MMAs");
-  using G = std::conditional_t<DP == 384, G384, G256>;
-  constexpr bool WIDE = DP == 384;
+  static_assert(GEO == 0 || (CG == 1 && MC == 1), "the single-accumulator geometries run single-CTA MMAs");
+  static_assert(GEO != 2 || PREC, "G256P is a precise-mode geometry");
+  using G = std::conditional_t<GEO == 1, G384, std::conditional_t<GEO == 2, G256P, G256>>;
+  constexpr bool WIDE = GEO != 0;                    // single scratch accumulator, 16 KB ring groups
+  constexpr bool P128 = GEO == 2;
+  constexpr uint32_t NB = G::DP / 128;               // 128-column blocks of X
   extern __shared__ uint8_t smem_raw[];
   // dynamic shared memory is at least 16-byte aligned; the operand tiles need 1024
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1515,7 +1818,8 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       // 16 KB slots, every ring group is one slot (RingW); the tape is contiguous in consumption order
       RingW ring{0u, 0u};
       constexpr uint32_t kImages = PREC ? 2u : 1u;
-      const uint32_t per_layer_attn = 12u * (uint32_t)p.npass, per_layer_mlp = 12u * (uint32_t)G::NCH;
+      // per pass: [Q|K] NA, V NA / 2, proj NB groups; per hidden chunk: FC1 NA, FC2 2 NB
+      const uint32_t per_layer_attn = (uint32_t)(G::NA + G::NA / 2 + NB) * (uint32_t)p.npass, per_layer_mlp = (uint32_t)(G::NA + 2 * NB) * (uint32_t)G::NCH;
       for (int it = 0; it < my_tiles * p.evals; ++it) {
         const uint8_t* src = p.tape;
         auto fills = [&](uint32_t n, uint32_t bytes, uint32_t n_slots) {
@@ -1535,13 +1839,13 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             src += bytes;
           }
         };
-        fills(6, 16384, kWSlots);                            // embedding: 2 K atoms x 3 column blocks
+        fills(2 * NB, 16384, kWSlots);                       // embedding: 2 K atoms x NB column blocks
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
-          fills(per_layer_attn, 16384, kWSlots);             // per pass: [Q|K] 6, V 3, proj 3
-          fills(per_layer_mlp, 16384, kWSlots);              // per chunk: FC1 6, FC2 6
+          fills(per_layer_attn, 16384, kWSlots);
+          fills(per_layer_mlp, 16384, kWSlots);
         }
-        fills(1, 12288, kWSlots);                            // action head: 6 K blocks of [16 x 64]
+        fills(1, 2048 * G::NA, kWSlots);                     // action head: NA K blocks of [16 x 64]
       }
     } else if constexpr (CG == 1) {
       // Two stages of 32 KB (slots {0,1} and {2,3}), one full / empty barrier pair per stage; the tape is
@@ -1660,9 +1964,12 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
       // ---- G384: one ring group = one 16 KB slot; every GEMM into X is three N = 128 column blocks ----
       RingW ring{0u, 0u};
       uint32_t n_slots = kWSlots;
-      auto groupw = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, uint32_t a_off, uint32_t d_col, uint32_t acc) {
+      // One ring group: D (+)= A W^T, then (A2 != 0) D += A2 W^T with the same weights.  A2 = 1: second A operand in
+      // shared memory (byte offset a2), A2 = 2: in tensor memory (column a2; one K atom = 32 columns).
+      auto groupw = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, auto a2_tag, uint32_t a_off, uint32_t a2, uint32_t d_col, uint32_t acc) {
         constexpr uint32_t N = decltype(n_tag)::value, NKB = decltype(nkb_tag)::value, B_STEP = decltype(bstep_tag)::value;
         constexpr uint32_t idesc = decltype(bf16_tag)::value ? idesc_bf16_m128(N) : idesc_f16_m128(N);
+        constexpr uint32_t A2 = decltype(a2_tag)::value;
         const uint32_t slot = ring.begin(n_slots), par = ring.parity(slot);
         long long t = 0;
         if constexpr (DBG) t = clock64();
@@ -1677,32 +1984,55 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             for (uint32_t j = 0; j < 4; ++j)
               mma_bf16(tm + d_col, desc(a_lo + kb * 1024u + 2u * j), desc(b_lo + kb * (B_STEP >> 4) + 2u * j), idesc,
                        (acc | kb | j) ? 1u : 0u);
+          if constexpr (A2 == 1) {
+            const uint32_t a2_lo = dlo + (a2 >> 4);
+#pragma unroll
+            for (uint32_t kb = 0; kb < NKB; ++kb)
+#pragma unroll
+              for (uint32_t j = 0; j < 4; ++j)
+                mma_bf16(tm + d_col, desc(a2_lo + kb * 1024u + 2u * j), desc(b_lo + kb * (B_STEP >> 4) + 2u * j), idesc, 1u);
+          }
+          if constexpr (A2 == 2) {
+#pragma unroll
+            for (uint32_t kb = 0; kb < NKB; ++kb)
+#pragma unroll
+              for (uint32_t j = 0; j < 4; ++j)
+                mma_f16_ts(tm + d_col, tm + a2 + kb * 32u + 8u * j, desc(b_lo + kb * (B_STEP >> 4) + 2u * j), idesc, 1u);
+          }
           mma_commit(bars + (B_WEMPTY0 + slot) * 8);
         }
         __syncwarp();
         ring.end(slot);
       };
-      auto group2w = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, uint32_t a_off, uint32_t d_col, uint32_t acc) {
-        groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, a_off, d_col, acc);
-        if constexpr (PREC) groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, a_off, d_col, 1);
+      // One GEMM group in the mode's arithmetic.  fp16 mode: A W^T.  Stacked precise mode: the hi image of the weights,
+      // then the lo image (A holds both images of the rows).  P128: (A_hi + A_lo) W_hi^T, then A_hi W_lo^T.
+      auto group2w = [&](auto n_tag, auto nkb_tag, auto bstep_tag, auto bf16_tag, auto a2_tag, uint32_t a_off, uint32_t a2, uint32_t d_col, uint32_t acc) {
+        if constexpr (P128) {
+          groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, a2_tag, a_off, a2, d_col, acc);
+          groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, BESO_IC(0), a_off, 0u, d_col, 1);
+        } else {
+          groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, BESO_IC(0), a_off, 0u, d_col, acc);
+          if constexpr (PREC) groupw(n_tag, nkb_tag, bstep_tag, bf16_tag, BESO_IC(0), a_off, 0u, d_col, 1);
+        }
       };
-      // X (+)= A[a_off: one K atom] W^T, the 384 output columns as three N = 128 groups
-      auto into_x = [&](auto bf16_tag, uint32_t a_off, uint32_t acc) {
+      // X (+)= A[a_off: one K atom] W^T, the output columns as NB groups of N = 128 (a2: shared-memory lo image of A)
+      auto into_x = [&](auto bf16_tag, uint32_t a_off, uint32_t a2, uint32_t acc) {
 #pragma unroll
-        for (uint32_t nb = 0; nb < 3; ++nb) group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), bf16_tag, a_off, kColX + nb * 128u, acc);
+        for (uint32_t nb = 0; nb < NB; ++nb) group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), bf16_tag, BESO_IC(1), a_off, a2, kColX + nb * 128u, acc);
       };
       for (int it = 0; it < my_tiles * p.evals; ++it) {
         if constexpr (DBG) tl = (p.timeline != nullptr && blockIdx.x == 0 && it == 1) ? p.timeline : nullptr;
         // ---- embedding GEMM: X = A_emb W_emb^T, K = 128 ----
         job_begin();
         jwait(B_A_READY);
-        into_x(BESO_IC(kEmbBf16), kSmA, 0);
-        into_x(BESO_IC(kEmbBf16), kSmA + 16384, 1);
+        into_x(BESO_IC(kEmbBf16), kSmA, kSmA + 32768, 0);             // (P128: lo images of atoms 0, 1 are atoms 2, 3)
+        into_x(BESO_IC(kEmbBf16), kSmA + 16384, kSmA + 49152, 1);
         jcommit(B_X_DONE);
         job_end();
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
-          // ---- attention half: QK0 V0 | QK1 P0 V1 | ... | P(n-1) ----
+          // ---- attention half: QK0 V0 | QK1 V1 P0 | ... | P(n-1): the projection of pass h - 1 goes behind the V job
+          // of pass h (which the compute warps are waiting for), it then runs under the attention of pass h ----
 #pragma unroll 1
           for (int h = 0; h <= p.npass; ++h) {
             if (h < p.npass) {                               // [Q|K] of attention pass h -> S (128 columns)
@@ -1710,26 +2040,26 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
               jwait(B_ACC_EMPTY0);
               if (h == 0) jwait(B_A_READY);
 #pragma unroll
-              for (uint32_t kb = 0; kb < 6; ++kb)
-                group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, G::ColS0, kb);
+              for (uint32_t kb = 0; kb < G::NA; ++kb)
+                group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), BESO_IC(0), BESO_IC(2), kSmA + kb * 16384, G::ColAL + kb * 32u, G::ColS0, kb);
               jcommit(B_ACC_FULL0);
-              job_end();
-            }
-            if (h >= 1) {                                    // X += Y_{h-1} Wproj[:, h-1]^T
-              job_begin();
-              jwait(B_Y_READY);
-              into_x(BESO_IC(0), G::SmY, 1);
-              jcommit(B_Y_EMPTY);
-              if (h == p.npass) jcommit(B_X_DONE);
               job_end();
             }
             if (h < p.npass) {                               // V of pass h -> S[0:64) once [Q|K] has been drained
               job_begin();
               jwait(B_ACC_EMPTY0);
 #pragma unroll
-              for (uint32_t kp = 0; kp < 3; ++kp)
-                group2w(BESO_IC(64), BESO_IC(2), BESO_IC(8192), BESO_IC(0), kSmA + kp * 32768, G::ColS0, kp);
+              for (uint32_t kp = 0; kp < G::NA / 2; ++kp)
+                group2w(BESO_IC(64), BESO_IC(2), BESO_IC(8192), BESO_IC(0), BESO_IC(2), kSmA + kp * 32768, G::ColAL + kp * 64u, G::ColS0, kp);
               jcommit(B_ACC_FULL0);
+              job_end();
+            }
+            if (h >= 1) {                                    // X += Y_{h-1} Wproj[:, h-1]^T
+              job_begin();
+              jwait(B_Y_READY);
+              into_x(BESO_IC(0), G::SmY, G::SmYLo, 1);
+              jcommit(B_Y_EMPTY);
+              if (h == p.npass) jcommit(B_X_DONE);
               job_end();
             }
           }
@@ -1741,29 +2071,29 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
               jwait(B_ACC_EMPTY0);
               if (c == 0) jwait(B_A_READY);
 #pragma unroll
-              for (uint32_t kb = 0; kb < 6; ++kb)
-                group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), BESO_IC(0), kSmA + kb * 16384, G::ColS0, kb);
+              for (uint32_t kb = 0; kb < G::NA; ++kb)
+                group2w(BESO_IC(128), BESO_IC(1), BESO_IC(0), BESO_IC(0), BESO_IC(2), kSmA + kb * 16384, G::ColAL + kb * 32u, G::ColS0, kb);
               jcommit(B_ACC_FULL0);
               job_end();
             }
             if (c >= 1) {                                    // X += H_{c-1} W2[:, chunk c-1]^T
-              const uint32_t b = (c - 1) & 1;
+              const uint32_t b = G::HSingle ? 0u : (uint32_t)(c - 1) & 1u;
               job_begin();
               jwait(B_OP_READY0 + b);
-              into_x(BESO_IC(0), b ? G::SmH1 : G::SmH0, 1);
+              into_x(BESO_IC(0), b ? G::SmH1 : G::SmH0, G::SmHLo, 1);
               jwait(B_OP_READY0B + b);
-              into_x(BESO_IC(0), (b ? G::SmH1 : G::SmH0) + 16384, 1);
+              into_x(BESO_IC(0), (b ? G::SmH1 : G::SmH0) + 16384, G::SmHLo + 16384, 1);
               jcommit(B_OP_EMPTY0 + b);
               if (c == G::NCH) jcommit(B_X_DONE);
               job_end();
             }
           }
         }
-        // ---- action head (N = 16, K = 384: one 12 KB group) ----
+        // ---- action head (N = 16, all K atoms in one group) ----
         job_begin();
         jwait(B_A_READY);
         jwait(B_ACC_EMPTY0);
-        group2w(BESO_IC(16), BESO_IC(6), BESO_IC(2048), BESO_IC(0), kSmA, G::ColS0, 0);
+        group2w(BESO_IC(16), BESO_IC(G::NA), BESO_IC(2048), BESO_IC(0), BESO_IC(2), kSmA, G::ColAL, G::ColS0, 0);
         jcommit(B_ACC_FULL0);
         job_end();
       }
@@ -1879,11 +2209,21 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     // ======================= attention helper warps (8, 9) =======================
     uint32_t y_phase = 1;
     for (int it = 0; it < my_tiles * p.evals * p.L * p.npass; ++it) {
-      attn_sync();
-      spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
+      attn_sync();                                          // (P128: S1)
+      // Y of the previous pass consumed by its projection MMAs: waited for here, or (single-accumulator schedules, where
+      // that projection runs under this pass's attention) by the attention items right before they write Y
+      uint32_t ybar = 0u;
+      const uint32_t ypar = y_phase;
+      if constexpr (WIDE) ybar = sbase + kSmBars + B_Y_EMPTY * 8;
+      else spin_wait(sbase + kSmBars + B_Y_EMPTY * 8, y_phase);
       y_phase ^= 1u;
-      if constexpr (PREC) attention_head_p<G, HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
-      else attention_head<G, HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T);
+      if constexpr (P128) {                                 // the two 64-row halves (attention_pass_p128)
+        attention_half_p128<HSP>(sbase, 4 + (warp - kHelperWarp0), 6, lane, p.S >> 1, p.T, 0, ybar, ypar);
+        attn_sync();                                        // S2
+        attn_sync();                                        // S3
+        attention_half_p128<HSP>(sbase, 8 + (warp - kHelperWarp0), kAttnWarps, lane, p.S >> 1, p.T, 64, ybar, ypar);
+      } else if constexpr (PREC) attention_head_p<G, HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T, ybar, ypar);
+      else attention_head<G, HSP>(sbase, 8 + (warp - kHelperWarp0), lane, p.S, p.T, ybar, ypar);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -1898,8 +2238,9 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     c.ctid = threadIdx.x - kComputeWarp0 * 32;
     c.lane = lane; c.wq = warp & 3; c.hf = (warp - kComputeWarp0) >> 2;
     c.row = c.wq * 32 + lane;
-    c.is_lo = PREC ? (lane >> 4) : 0;
-    c.srow = PREC ? c.wq * 16 + (lane & 15) : c.row;
+    constexpr bool STACKED = PREC && !P128;                  // hi / lo images of a sequence row on two TMEM lanes
+    c.is_lo = STACKED ? (lane >> 4) : 0;
+    c.srow = STACKED ? c.wq * 16 + (lane & 15) : c.row;
     c.row_off = (uint32_t)c.row * 128u; c.rx4 = ((uint32_t)c.row & 7u) << 4;
     c.phases = (1u << B_OP_EMPTY0) | (1u << B_OP_EMPTY1) | (1u << B_Y_EMPTY);
     c.cg = CG;
@@ -1908,7 +2249,9 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
     load_vec_async(c, G::SmVecA, p.vec, G::VecAFloats);
     load_vec_async(c, G::SmVecM, p.vec + G::VecAFloats, G::VecMFloats);
     auto ln = [&](uint32_t vec_s, float* tr) {
-      if constexpr (WIDE) {
+      if constexpr (P128) {
+        ln_pass_p128<DBG>(c, vec_s, p.inv_d, p.d_true, tr);
+      } else if constexpr (WIDE) {
         if constexpr (PREC) ln_pass_pw<DBG>(c, vec_s, p.inv_d, p.d_true, tr);
         else ln_pass_w<DBG>(c, vec_s, p.inv_d, tr);
       } else {
@@ -1943,11 +2286,16 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           ln(vecA_s, trace_row(2 * l));
           stamp<DBG>(c);
           for (int h = 0; h < p.npass; ++h) {
+            const uint32_t bq_s = vecA_s + (uint32_t)(G::VecBq + h * G::BqStride) * 4u;
+            if constexpr (P128) {                           // both drains, both attention halves, all their barriers
+              stamp<DBG>(c); stamp<DBG>(c);
+              c.phases = attention_pass_p128<HSP>(c, bq_s, p.S, p.T);
+              stamp<DBG>(c); stamp<DBG>(c);
+            } else {
             c.wait(B_ACC_FULL0);
             tc_fence_after();
             stamp<DBG>(c);
             // arrives on ACC_EMPTY0 once its TMEM reads are done
-            const uint32_t bq_s = vecA_s + (uint32_t)(G::VecBq + h * G::BqStride) * 4u;
             if constexpr (WIDE) {                           // [Q|K] job, then the V job into the same accumulator
               if constexpr (PREC) drain_qkv_p<G, 3>(c, bq_s); else drain_qkv<G, 3>(c, bq_s);
               c.wait(B_ACC_FULL0);
@@ -1957,15 +2305,19 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
               if constexpr (PREC) drain_qkv_p<G, 7>(c, bq_s); else drain_qkv<G, 7>(c, bq_s);
             }
             attn_sync();                                    // Q|K|V of this head visible to all 10 attention warps
-            c.wait(B_Y_EMPTY);                              // previous head's Y consumed by its proj MMAs
+            uint32_t ybar = 0u;
+            const uint32_t ypar = (c.phases >> B_Y_EMPTY) & 1u;
+            if constexpr (WIDE) { ybar = c.bar(B_Y_EMPTY); c.phases ^= 1u << B_Y_EMPTY; }   // waited for inside the attention
+            else c.wait(B_Y_EMPTY);                         // previous head's Y consumed by its proj MMAs
             stamp<DBG>(c);
-            if constexpr (PREC) attention_head_p<G, HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
-            else attention_head<G, HSP>(sbase, c.ctid >> 5, lane, p.S, p.T);
+            if constexpr (PREC) attention_head_p<G, HSP>(sbase, c.ctid >> 5, lane, p.S, p.T, ybar, ypar);
+            else attention_head<G, HSP>(sbase, c.ctid >> 5, lane, p.S, p.T, ybar, ypar);
             fence_async_smem();
             c.arrive(B_Y_READY);
             stamp<DBG>(c);
             attn_sync();                                    // staging may be overwritten by the next drain
             stamp<DBG>(c);
+            }
           }
           // vecA is free: prefetch the next layer's (or the final block)
           load_vec_async(c, G::SmVecA, p.vec + (size_t)(l + 1) * layer_stride, G::VecAFloats);
@@ -1977,6 +2329,13 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
           stamp<DBG>(c);
           for (int ch = 0; ch < G::NCH; ++ch) {
             const int b = ch & 1, tb = WIDE ? 0 : b;
+            if constexpr (P128) {                           // one H buffer: the drain itself waits for FC2(ch - 1)
+              c.wait(B_ACC_FULL0);
+              tc_fence_after();
+              stamp<DBG>(c);
+              c.phases = drain_gelu_p128(c, vecM_s + (uint32_t)G::VecB1F * 4u + (uint32_t)ch * 512u);
+              stamp<DBG>(c);
+            } else {
             c.wait2(tb ? B_ACC_FULL1 : B_ACC_FULL0, b ? B_OP_EMPTY1 : B_OP_EMPTY0);   // accumulator ready, H[b] consumed by FC2(ch-2)
             tc_fence_after();
             stamp<DBG>(c);
@@ -1984,6 +2343,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             if constexpr (PREC) drain_gelu_p<G>(c, tb, b, vecM_s + (uint32_t)G::VecB1F * 4u + (uint32_t)ch * 512u);
             else drain_gelu<G>(c, tb, b, vecM_s + (uint32_t)G::VecB1H * 4u + (uint32_t)ch * 256u);
             stamp<DBG>(c);
+            }
           }
           compute_sync();                                   // everyone done with vecM(l)
           const int nl = (l + 1 < p.L) ? l + 1 : 0;
@@ -2245,6 +2605,32 @@ bool fast_supported(const beso_model_desc& m) {
          m.act_dim <= kMaxAct && T <= kMaxTokens;
 }
 
+// Precise mode on full 128-row tiles (geometry G256P): embed_dim <= 256.
+bool fast_p128_supported(const beso_model_desc& m) { return fast_supported(m) && m.d <= G256::DP; }
+
+// Which precise layout a launch uses.  One evaluation of a P128 tile (128 rows) costs about kP128Cost evaluations of a
+// stacked tile (64 rows) (in-kernel timelines, K256: 669 k against 385 k cycles; profiles/): the batch goes to whichever needs less time over the SMs, so
+// a batch-1 rollout keeps the short stacked tile and a batch that fills the chip takes the half as many, fuller P128
+// tiles.  BESO_PREC_LAYOUT=stacked|p128 forces one (A / B measurements).
+constexpr double kP128Cost = 1.7;
+static int tile_waves(int B, int per_tile, int sm_count) { const int tiles = (B + per_tile - 1) / per_tile; return (tiles + sm_count - 1) / sm_count; }
+static int g_prec_layout = -1;                  // -1: not set yet (environment), 0 auto, 1 stacked, 2 P128
+void fast_set_prec_layout(int layout) { g_prec_layout = (layout == FAST_LAYOUT_STACKED || layout == FAST_LAYOUT_P128) ? layout : 0; }
+static bool choose_p128(const beso_model_desc& m, int T, int B, bool cfg, int sm_count) {
+  if (g_prec_layout < 0) {
+    const char* e = getenv("BESO_PREC_LAYOUT");
+    g_prec_layout = !e ? 0 : (!strcmp(e, "stacked") ? 1 : (!strcmp(e, "p128") ? 2 : 0));
+  }
+  const int forced = g_prec_layout;
+  const int unit = cfg ? 2 : 1;
+  int s_st = 64 / T, s_p = 2 * (64 / T);
+  s_st -= s_st % unit; s_p -= s_p % (2 * unit);
+  if (s_p < 2 * unit) return false;
+  if (forced) return forced == 2;
+  if (s_st < unit) return true;
+  return kP128Cost * tile_waves(B, s_p / unit, sm_count) < (double)tile_waves(B, s_st / unit, sm_count);
+}
+
 int fast_seqs_per_tile(const beso_model_desc& m, int t, bool prec) {
   if (!fast_supported(m)) return 0;
   const int G = m.goal_conditioned ? m.goal_len : 0;
@@ -2261,13 +2647,16 @@ void fast_free(FastWeights& w) {
 static int p_layer(int l, int k) { return 3 + l * 16 + k; }   // k: 0 ln1w 1 ln1b 2 ln2w 3 ln2b 4 key.w 5 key.b 6 query.w 7 query.b
                                                                //    8 value.w 9 value.b 10 proj.w 11 proj.b 12 mlp0.w 13 mlp0.b 14 mlp2.w 15 mlp2.b
 
-int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm, cudaStream_t st, bool prec) {
+int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm, cudaStream_t st, int layout) {
+  const bool prec = layout != FAST_LAYOUT_F16;
+  if (layout == FAST_LAYOUT_P128 && !fast_p128_supported(m)) { set_error("P128 layout needs embed_dim <= 256"); return BESO_E_UNSUPPORTED; }
   const int L = m.n_layers, G = m.goal_conditioned ? m.goal_len : 0;
   const int d = m.d, H = m.n_heads, hs = d / H, hsp = padded_head(m), per_pass = 64 / hsp, npass = (H + per_pass - 1) / per_pass;
   const int ff = 4 * d;
   const size_t images = prec ? 2 : 1;
   // geometry (G256 / G384): padded width, K atoms, hidden chunks, vector block layout
   const bool wide = d > G256::DP;
+  const bool oneacc = wide || layout == FAST_LAYOUT_P128;  // single-accumulator schedules: 16 KB ring groups
   const int DP = wide ? G384::DP : G256::DP, NA = DP / 64, NB = DP / 128, FFP = 4 * DP, NCH = FFP / 128;
   const uint32_t vA = wide ? G384::VecAFloats : G256::VecAFloats, vM = wide ? G384::VecMFloats : G256::VecMFloats;
   const uint32_t vBq = wide ? G384::VecBq : G256::VecBq, vBqStride = wide ? G384::BqStride : G256::BqStride;
@@ -2275,8 +2664,8 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
   // G256 per evaluation: embedding 4 x 16 KB | per layer: per pass QKV 4 x 24 KB + proj 32 KB, FC1 32 x 16 KB, FC2 16 x 32 KB | head 4 x 2 KB
   // G384 per evaluation: embedding 6 x 16 KB | per layer: per pass ([Q|K] 6 + V 3 + proj 3) x 16 KB, (FC1 6 + FC2 6) x 16 KB per chunk | head 6 x 2 KB
   // (PREC: every ring group twice, hi image then lo image)
-  const size_t tape_bytes = wide
-      ? images * (6 * 16384 + (size_t)L * ((size_t)npass * 12 * 16384 + (size_t)NCH * 12 * 16384) + 6 * 2048)
+  const size_t tape_bytes = oneacc
+      ? images * ((size_t)2 * NB * 16384 + (size_t)L * ((size_t)npass * (NA + NA / 2 + NB) + (size_t)NCH * (NA + 2 * NB)) * 16384 + (size_t)NA * 2048)
       : images * (4 * 16384 + (size_t)L * ((size_t)npass * (4 * 24576 + 32768) + 32 * 16384 + 16 * 32768) + 4 * 2048);
   const size_t vec_floats = (size_t)L * (vA + vM) + vA;
   const size_t fold_floats = (size_t)L * 2 * DP;             // per layer: effective V bias | effective proj bias (padded)
@@ -2346,28 +2735,28 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
       const IndexMap hm{hsp, hs, h * per_pass, H};
       for (int nb = 0; nb < NB; ++nb) {
         for (int s = 0; s < 2; ++s) tile(wp, d, nb * 128 + s * 64, 0, 64, d, d, 1.f, nullptr, ident, hm);
-        if (wide) end_group();
+        if (oneacc) end_group();
       }
-      if (!wide) end_group();
+      if (!oneacc) end_group();
     };
-    auto fc1 = [&](int c) {                                   // G256: two K atoms per group; G384: one
+    auto fc1 = [&](int c) {                                   // G256: two K atoms per group; single-accumulator: one
       for (int kb = 0; kb < NA; ++kb) {
         for (int s = 0; s < 2; ++s) tile(w1, d, c * 128 + s * 64, kb * 64, 64, ff, d, s1, ln2w, ident, ident);
-        if (wide || (kb & 1)) end_group();
+        if (oneacc || (kb & 1)) end_group();
       }
     };
     auto fc2 = [&](int c) {
       for (int kb = 0; kb < 2; ++kb) {
         for (int nb = 0; nb < NB; ++nb) {
           for (int s = 0; s < 2; ++s) tile(w2, ff, nb * 128 + s * 64, c * 128 + kb * 64, 64, d, ff, s2, nullptr, ident, ident);
-          if (wide) end_group();
+          if (oneacc) end_group();
         }
-        if (!wide) end_group();
+        if (!oneacc) end_group();
       }
     };
-    if (wide) {
+    if (oneacc) {
       qk_w(0); v_w(0);
-      for (int h = 1; h < npass; ++h) { qk_w(h); proj(h - 1); v_w(h); }
+      for (int h = 1; h < npass; ++h) { qk_w(h); v_w(h); proj(h - 1); }
     } else {
       qkv(0);
       for (int h = 1; h < npass; ++h) { qkv(h); proj(h - 1); }
@@ -2422,7 +2811,7 @@ int fast_pack(FastWeights& w, const beso_model_desc& m, const float* const* prm,
     es.resid_bias[2 * l] = w.vec + vec_floats + (size_t)l * 2 * DP + DP;      // effective projection bias
     es.resid_bias[2 * l + 1] = prm[p_layer(l, 15)];
   }
-  pack_emb_kernel<<<dim3(2 * NB, (unsigned)images), 256, 0, st>>>(es, tape, NB, wide ? 1 : 2);
+  pack_emb_kernel<<<dim3(2 * NB, (unsigned)images), 256, 0, st>>>(es, tape, NB, oneacc ? 1 : 2);
   pack_pend_kernel<<<1, DP, 0, st>>>(es, w.vec, vA + vM, vA, DP);
   g_kernel_launches += 2;
   BESO_CUDA(cudaGetLastError());
@@ -2464,9 +2853,13 @@ int fast_mma_rate(long long* out_dev, const void* src_dev, int mode, cudaStream_
   return BESO_OK;
 }
 
-int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
+int fast_launch(const FastWeights& w_in, const beso_model_desc& m, int sm_count, const SampleArgs& sa,
                 const float* state, const float* goal, const float* x, const float* sigma, float* out,
-                int B, int t, uint32_t flags, float lambda, cudaStream_t st, bool prec) {
+                int B, int t, uint32_t flags, float lambda, cudaStream_t st, bool prec, const FastWeights* w_p128) {
+  const int T_tok = 1 + (m.goal_conditioned ? m.goal_len : 0) + 2 * t;
+  const bool p128 = prec && w_p128 != nullptr && w_p128->tape != nullptr &&
+                    choose_p128(m, T_tok, B, (flags & BESO_FLAG_CFG) != 0, sm_count);
+  const FastWeights& w = p128 ? *w_p128 : w_in;
   if (!w.tape) { set_error("fast weights not packed"); return BESO_E_NOT_PACKED; }
   FastParams p{};
   const int L = m.n_layers;
@@ -2475,14 +2868,17 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   p.d_true = m.d; p.inv_d = 1.0f / (float)m.d;
   const bool wide = m.d > G256::DP;
   // (timeline buffer layout only: the issuer's per-job stamps come first, 6 * n_fills slots are reserved for them)
-  const size_t n_fills = wide ? 8 + (size_t)L * 64 : 4 + (size_t)L * 104 + 4;
+  const size_t n_fills = (wide || p128) ? 8 + (size_t)L * 64 : 4 + (size_t)L * 104 + 4;
   p.tape = reinterpret_cast<const uint8_t*>(w.tape);
   p.vec = w.vec;
   p.n_fills = (int)n_fills; p.L = L; p.G = m.goal_conditioned ? m.goal_len : 0; p.obs = m.obs_dim; p.act = m.act_dim;
   p.t = t; p.T = 1 + p.G + 2 * t;
-  p.S = (prec ? 64 : kRows) / p.T;
   const bool cfg = flags & BESO_FLAG_CFG;
-  if (cfg) p.S &= ~1;                                         // cond / uncond pairs share a tile
+  // sequences per tile come in units of `unit`: P128 fills the two 64-row halves of a tile alike, CFG keeps the
+  // cond / uncond copies of a sequence together (in the same half)
+  const int unit = (p128 ? 2 : 1) * (cfg ? 2 : 1);
+  p.S = p128 ? 2 * (64 / p.T) : (prec ? 64 : kRows) / p.T;
+  p.S -= p.S % unit;
   if (p.S < 1) { set_error("sequence does not fit a 128-row tile"); return BESO_E_UNSUPPORTED; }
   if (cfg && p.S < 2) { set_error("a cond / uncond pair does not fit a tile"); return BESO_E_UNSUPPORTED; }
   // A tile's time hardly depends on how many of its rows are used (one thread per row, M = 128 MMAs either way) except
@@ -2490,7 +2886,7 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   // the one with the FEWEST sequences per tile: it spreads the batch over more SMs (BASELINE config 2: 512 sequences
   // are 103 tiles of 5 or 128 tiles of 4 on 148 SMs -- one wave either way, with 20 % less attention work per tile).
   {
-    const int step = cfg ? 2 : 1, s_max = p.S;
+    const int step = unit, s_max = p.S;
     auto waves = [&](int S) { const int per = cfg ? S / 2 : S; const int tiles = (B + per - 1) / per; return (tiles + sm_count - 1) / sm_count; };
     const int w_min = waves(s_max);
     for (int S = step; S < s_max; S += step)
@@ -2540,7 +2936,7 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
   if (cg == 2 || mc == 2) {
     const int pairs = (p.n_tiles + 1) / 2, max_pairs = sm_count / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-    rc = cg == 2 ? launch(fast_sample_kernel<2, false, 1, false, 64, 256>, grid, true) : launch(fast_sample_kernel<1, false, 2, false, 64, 256>, grid, true);
+    rc = cg == 2 ? launch(fast_sample_kernel<2, false, 1, false, 64, 0>, grid, true) : launch(fast_sample_kernel<1, false, 2, false, 64, 0>, grid, true);
   } else {
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
     if (wide) {
@@ -2553,24 +2949,30 @@ int fast_launch(const FastWeights& w, const beso_model_desc& m, int sm_count, co
       if (pe != cudaSuccess) return cuda_fail(pe, "scratch memory pool");
       BESO_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&p.xscratch), (size_t)grid * 4 * kXFloats * sizeof(float), pool, st));
     }
-    const int sel = (wide ? 8 : 0) | (prec ? 4 : 0) | (dbg ? 2 : 0) | (hsp == 32 ? 1 : 0);
+    const int geo = wide ? 1 : (p128 ? 2 : 0);
+    const int sel = geo * 8 + ((prec ? 4 : 0) | (dbg ? 2 : 0) | (hsp == 32 ? 1 : 0));
     switch (sel) {
-      case 0: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 256>, grid, false); break;
-      case 1: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 256>, grid, false); break;
-      case 2: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 256>, grid, false); break;
-      case 3: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 256>, grid, false); break;
-      case 4: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 256>, grid, false); break;
-      case 5: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 256>, grid, false); break;
-      case 6: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 256>, grid, false); break;
-      case 7: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 256>, grid, false); break;
-      case 8: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 384>, grid, false); break;
-      case 9: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 384>, grid, false); break;
-      case 10: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 384>, grid, false); break;
-      case 11: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 384>, grid, false); break;
-      case 12: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 384>, grid, false); break;
-      case 13: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 384>, grid, false); break;
-      case 14: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 384>, grid, false); break;
-      default: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 384>, grid, false); break;
+      case 0: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 0>, grid, false); break;
+      case 1: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 0>, grid, false); break;
+      case 2: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 0>, grid, false); break;
+      case 3: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 0>, grid, false); break;
+      case 4: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 0>, grid, false); break;
+      case 5: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 0>, grid, false); break;
+      case 6: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 0>, grid, false); break;
+      case 7: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 0>, grid, false); break;
+      case 8: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 1>, grid, false); break;
+      case 9: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 1>, grid, false); break;
+      case 10: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 1>, grid, false); break;
+      case 11: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 1>, grid, false); break;
+      case 12: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 1>, grid, false); break;
+      case 13: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 1>, grid, false); break;
+      case 14: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 1>, grid, false); break;
+      case 15: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 1>, grid, false); break;
+      case 20: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 2>, grid, false); break;
+      case 21: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 2>, grid, false); break;
+      case 22: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 2>, grid, false); break;
+      case 23: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 2>, grid, false); break;
+      default: set_error("internal: no kernel image for this mode"); rc = BESO_E_INVALID; break;
     }
     if (wide) {
       const cudaError_t fe = cudaFreeAsync(p.xscratch, st);

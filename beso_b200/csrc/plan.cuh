@@ -20,7 +20,8 @@ struct WeightSlot {
   float* simt_buf = nullptr;     // transposed fp32 images (PRECISE)
   SimtModel simt{};
   FastWeights fast{};            // fp16 UMMA tape + fp32 / fp16 vectors (FAST)
-  FastWeights fastp{};           // [hi | lo] fp16 tape + fp32 vectors (PRECISE on the tensor pipe)
+  FastWeights fastp{};           // [hi | lo] fp16 tape + fp32 vectors (PRECISE on the tensor pipe, stacked 64-row tiles)
+  FastWeights fastq{};           // the same for the 128-row tile layout (P128; embed_dim <= 256)
   std::vector<const float*> params;   // raw fp32 parameter tensors, parameters() order (training path)
   bool packed = false;
 };

@@ -44,13 +44,16 @@ enum {
 enum {
   BESO_MODE_PRECISE = 0, /* fp32-equivalent arithmetic; meets rtol 1e-3 / atol 1e-5 vs the fp32 reference.  On shapes
                             the tensor-core kernel supports (below) every product runs on tcgen05 with both
-                            operands split into fp16 hi + lo images (all four cross terms, fp32 accumulate in
-                            TMEM), fp32 two-pass LayerNorm, erff GELU, fp32 attention; other shapes run the fp32
-                            CUDA-core kernel.                                                            */
+                            operands split into fp16 hi + lo images (fp32 accumulate in TMEM; two tile layouts,
+                            chosen per launch: 128-row tiles with three MMAs per product for embed_dim <= 256,
+                            or 64 sequence rows with both images stacked on the MMA row dimension), fp32
+                            two-pass LayerNorm, erf GELU in fp32, split-operand attention; other shapes run the
+                            fp32 CUDA-core kernel.                                                       */
   BESO_MODE_FAST = 1,    /* fp16 operands on tcgen05 tensor cores (single pass), fp32 accumulate in TMEM; fp32
-                            LayerNorm statistics / softmax / residual.  Shapes: embed_dim <= 256 (multiple of 8),
-                            head size <= 64 with n_heads * padded head size (32 or 64) <= 384, <= 24 tokens,
-                            obs <= 64, act <= 13, linear action head.                                    */
+                            LayerNorm statistics / softmax / residual.  Shapes: embed_dim <= 384 (multiple of 8;
+                            a 256-column and a 384-column geometry of the kernel -- the reference's block-push
+                            (d = 240) and kitchen (d = 360) checkpoints), head size <= 64 with n_heads * padded
+                            head size (32 or 64) <= 384, <= 24 tokens, obs <= 64, act <= 13, linear action head. */
   BESO_MODE_SIMT = 2     /* force the fp32 CUDA-core kernel (any shape); same tolerance as PRECISE        */
 };
 
@@ -307,6 +310,10 @@ int beso_window_gather(const float* obs_dev, const float* act_dev, int n_traj, i
 int64_t beso_kernel_launches(void);                /* kernels launched by this library so far   */
 int beso_plan_rows_per_cta(beso_plan* plan, int mode, int t); /* sequences handled per CTA      */
 int beso_device_sm_count(int device);
+/* Diagnostics / tests: tile layout of the PRECISE mode's tensor-core kernel.  0 = chosen per launch (whichever needs
+ * less time for the batch), 1 = stacked (64 sequence rows per tile, any supported shape), 2 = 128-row tiles
+ * (embed_dim <= 256; ignored where unsupported).  Also settable as BESO_PREC_LAYOUT=stacked|p128. */
+int beso_debug_set_precise_layout(int layout);
 /* Diagnostics: when trace_dev != NULL, FAST-mode launches dump the fp32 residual stream of tile 0,
  * first evaluation, as seen by every LayerNorm pass: (2 * n_layers + 1) x 128 x 256 floats. */
 int beso_debug_set_trace(float* trace_dev);

@@ -71,3 +71,26 @@ def with_masks(model, sd):
     full = {k: v for k, v in model.state_dict().items() if k.endswith("attn.mask")}
     full.update(sd)
     return full
+
+
+def build_for_mode(cfg, device, mode="auto", **kw):
+    """The tests' ``build_denoiser``.  Two extra mode names select the tile layout of the precise mode's tensor-core kernel
+    through the library's test hook (``beso_debug_set_precise_layout``): ``precise128`` = 128-row tiles (three MMAs per
+    product, embed_dim <= 256), ``precise64`` = stacked 64-row tiles; plain ``precise`` lets the launch choose (small test
+    batches take the stacked layout, chip-filling batches the 128-row one).  The hook is global: it is set here for the
+    model being built and reset after every test."""
+    from beso_b200 import _lib
+    from beso_b200.denoiser import build_denoiser
+    if device is not None and str(device).startswith("cuda"):
+        _lib.lib().beso_debug_set_precise_layout({"precise128": 2, "precise64": 1}.get(mode, 0))
+    return build_denoiser(cfg, device, mode="precise" if mode in ("precise128", "precise64") else mode, **kw)
+
+
+@pytest.fixture(autouse=True)
+def _reset_precise_layout():
+    yield
+    import torch
+    if torch.cuda.is_available():
+        from beso_b200 import _lib
+        _lib.lib().beso_debug_set_precise_layout(0)
+

@@ -13,16 +13,18 @@ import ctypes as C
 import pytest
 import torch
 
-from conftest import golden_weights, load_golden, to_oracle_cfg
+from conftest import build_for_mode as build_denoiser, golden_weights, load_golden, to_oracle_cfg
 from beso_b200 import K256, T16, _lib, sampling
 from beso_b200.agent import BesoAgent
 from beso_b200.cfg import ClassifierFreeSampleModel
-from beso_b200.denoiser import build_denoiser
 from beso_b200.synth import synthetic_inputs, synthetic_state_dict
 
 pytestmark = pytest.mark.gpu
 
 TOL = {"precise": dict(rtol=1e-3, atol=1e-5), "simt": dict(rtol=1e-3, atol=1e-5), "fast": dict(rtol=3e-3, atol=3e-3)}
+# the precise mode with the 128-row tile layout forced (conftest.build_for_mode): the same north-star tolerance
+TOL["precise128"] = TOL["precise"]
+PRECISE_AND_FAST = ["precise", "precise128", "fast"]
 # fast mode against the 16-bit-faithful oracle (the reference with the kernel's operand roundings): measured max |err|
 # 5.7e-4 on random-init and 7.6e-4 on trained weights (profiles/r2_error_report.txt); SURVEY.md H1 asked for 1e-3
 TOL_FAITHFUL = dict(rtol=1e-3, atol=1e-3)
@@ -49,7 +51,7 @@ def modes_for(name, cfg):
     """precise = the split-operand tensor-core kernel where the shape is supported (else the CUDA-core kernel),
     simt = the CUDA-core kernel on every shape, fast = single-pass fp16 tensor-core kernel."""
     assert fast_available(cfg) == (name in TENSOR_SHAPES), name
-    return ["precise", "simt"] + (["fast"] if name in TENSOR_SHAPES else [])
+    return ["precise", "simt"] + (["fast"] if name in TENSOR_SHAPES else []) + (["precise128"] if name in TENSOR_SHAPES and cfg.d <= 256 else [])
 
 
 def cuda(a, dev):
@@ -75,7 +77,7 @@ def test_forward_matches_reference_golden(name, cuda_device):
             torch.testing.assert_close(inner.cpu(), a["inner"], **TOL[mode])
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_samplers_match_reference_golden(mode, cuda_device):
     if mode == "fast" and not fast_available():
         pytest.skip("fast mode not built")
@@ -94,7 +96,7 @@ def test_samplers_match_reference_golden(mode, cuda_device):
     assert torch.equal(g["x_t"].cpu(), a["x_t"])                          # caller's x_t is never written
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
     """sample_euler_ancestral (gc_sampling.py:216-256, the kitchen evaluation default) as one persistent launch,
     fed the randn_like draws the reference consumed (tests/golden/samplers_ancestral_K256.npz)."""
@@ -174,7 +176,7 @@ def test_euler_ancestral_matches_reference_golden(mode, cuda_device):
     torch.testing.assert_close(got.cpu(), want, **(dict(rtol=1e-2, atol=8e-3) if mode == "fast" else dict(rtol=1e-3, atol=2e-5)))
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_classifier_free_guidance_matches_reference_golden(mode, cuda_device):
     if mode == "fast" and not fast_available():
         pytest.skip("fast mode not built")
@@ -195,7 +197,7 @@ def test_classifier_free_guidance_matches_reference_golden(mode, cuda_device):
         torch.testing.assert_close(got.cpu(), a[f"cfg_ddim4_{tag}"], **TOL[mode])
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_cfg1_batch64_against_oracle(mode, cuda_device):
     """BASELINE config 1: K256 single denoise step, batch 64, parity against the CPU oracle."""
     if mode == "fast" and not fast_available():
@@ -215,7 +217,7 @@ def test_cfg1_batch64_against_oracle(mode, cuda_device):
           f"within(1e-3,1e-5)={(err <= 1e-5 + 1e-3 * want.abs()).float().mean():.4f}")
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_python_loop_fallback_equals_fused_loop(mode, cuda_device):
     """With a callback the sampler runs step by step (one fused launch per model call) and must
     agree with the persistent kernel; the callback sees every step."""
@@ -234,7 +236,7 @@ def test_python_loop_fallback_equals_fused_loop(mode, cuda_device):
         torch.testing.assert_close(fused, loop, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_full_size_properties_cfg2(mode, cuda_device):
     """BASELINE config 2 (50-step DDIM, batch 512): sequences are independent, so the result must be
     (a) deterministic, (b) equivariant under a batch permutation, (c) unchanged when the batch is
@@ -256,7 +258,13 @@ def test_full_size_properties_cfg2(mode, cuda_device):
     assert torch.equal(permuted, full[perm])
     halves = torch.cat([sampling.sample_ddim(m, g["state"][:200], g["noise"][:200], g["goal"][:200], sig),
                         sampling.sample_ddim(m, g["state"][200:], g["noise"][200:], g["goal"][200:], sig)])
-    assert torch.equal(halves, full)
+    if mode == "precise":
+        # The launch picks the precise mode's tile layout from the batch (512 sequences fill the chip with 128-row tiles,
+        # the 200 / 312 split may take the stacked layout): both are inside the tolerance of the reference, not
+        # bit-identical to each other.  With a layout forced ("precise128", and the fp16 mode) the split is bit-exact.
+        torch.testing.assert_close(halves, full, rtol=1e-3, atol=2e-5)
+    else:
+        assert torch.equal(halves, full)
     with torch.no_grad():
         want = O.sample_ddim(sd, to_oracle_cfg(cfg), x["state"][:4], x["noise"][:4], x["goal"][:4], sig)
     torch.testing.assert_close(full[:4].cpu(), want, **TOL[mode])
@@ -362,7 +370,7 @@ def test_cta_pair_mode_parity(cuda_device):
         assert r.returncode == 0 and "cg2 ok" in r.stdout, var + r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_rollout_shapes_batch1_growing_context_and_keep_last(mode, cuda_device):
     """predict() call shapes: batch 1, t = 1..W (beso_agent.py:323-325), plus keep_last_actions (score_gpts.py:355-356)
     and ragged batches that do not fill a tile."""
@@ -387,7 +395,7 @@ def test_rollout_shapes_batch1_growing_context_and_keep_last(mode, cuda_device):
             torch.testing.assert_close(got_k, want_k, **TOL[mode])
 
 
-@pytest.mark.parametrize("mode", ["precise", "fast"])
+@pytest.mark.parametrize("mode", PRECISE_AND_FAST)
 def test_cfg5_heun_cfg_batch2048_properties(mode, cuda_device):
     """BASELINE config 5: CFG (lambda = 2) 10-step Heun, batch 2048: determinism, batch-split invariance and a
     slice against the oracle."""
@@ -412,7 +420,7 @@ def test_cfg5_heun_cfg_batch2048_properties(mode, cuda_device):
 
 
 @pytest.mark.parametrize("kind", ["standard", "minmax"])
-@pytest.mark.parametrize("mode", ["precise", "fast", "simt"])
+@pytest.mark.parametrize("mode", ["precise", "precise128", "fast", "simt"])
 def test_rollout_scaling_fused_into_the_sampling_kernel(kind, mode, cuda_device):
     """predict(): scale_input of state / goal, the zeroed block-push goal dimensions, clip_action and
     inverse_scale_output run inside the sampling kernel (beso_sample_loop_scaled) and must give exactly what the torch
@@ -463,7 +471,7 @@ def test_trained_checkpoint_weights_match_reference(name, cuda_device):
     cfg, meta, a, sd = load_checkpoint_golden(name)
     g = cuda(a, cuda_device)
     assert fast_available(cfg)                      # both checkpoint shapes run on the tensor cores
-    modes = ["precise", "simt", "fast"]
+    modes = ["precise", "simt", "fast"] + (["precise128"] if cfg.d <= 256 else [])
     for mode in modes:
         m = build_denoiser(cfg, cuda_device, mode=mode)
         full = with_masks(m, sd)

@@ -1,6 +1,9 @@
 """GPU diagnostics: where one CTA of the FAST kernel spends its second model evaluation.
 
-    python tools/timeline_fast.py [T16|K256|KITCHEN|PUSH] [batch] [fast|precise] > gpurun_out/timeline.txt
+    python tools/timeline_fast.py [T16|K256|KITCHEN|PUSH] [batch] [fast|precise|stacked] > gpurun_out/timeline.txt
+
+(precise = the precise mode with the 128-row tile layout forced where the shape has it, stacked = with the stacked 64-row
+layout forced.)
 
 Prints, in SM clock cycles, (a) the compute warps' phase durations and waits, (b) for the MMA
 issuer, per GEMM job, time spent waiting on barriers (compute) vs on the weight ring (producer).
@@ -25,14 +28,19 @@ def main():
     cfg = {"K256": K256, "T16": T16, "KITCHEN": KITCHEN_CKPT, "PUSH": BLOCKPUSH_CKPT}[name]
     dev = torch.device("cuda:0")
     mode = sys.argv[3] if len(sys.argv) > 3 else "fast"
+    stacked = mode == "stacked" or cfg.d > 256
+    if mode in ("precise", "stacked"):
+        os.environ["BESO_PREC_LAYOUT"] = "stacked" if stacked else "p128"      # read by the library at its first launch
+        mode = "precise"
     m = build_denoiser(cfg, dev, mode=mode, state_dict=synthetic_state_dict(cfg, 1))
     x = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, seed=2).items()}
     sig = get_sigmas_exponential(4, 0.005, 1.0)
     L = cfg.n_layers
-    wide = cfg.d > 256                                       # the 384-column geometry: [Q|K] + V jobs, 12 FC1 chunks
+    # single-accumulator schedules ([Q|K] + V jobs): the 384-column geometry and the precise mode on full tiles (P128)
+    wide = cfg.d > 256 or (mode == "precise" and not stacked)
     hsp = 32 if cfg.d // cfg.n_heads <= 32 else 64
     npass = -(-cfg.n_heads // (64 // hsp))
-    nch = 12 if wide else 8
+    nch = 12 if cfg.d > 256 else 8
     NF = 8 + 64 * L if wide else 4 + 104 * L + 4
     tl = torch.zeros(6 * NF + 4096, dtype=torch.int64, device=dev)
     sample_ddim(m, x["state"], x["noise"], x["goal"], sig)            # warm-up
@@ -88,10 +96,10 @@ def main():
     for h in range(npass + 1):
         if h < npass:
             layer.append(f"QK{h}" if wide else f"QKV{h}")
-        if h >= 1:
-            layer.append(f"PROJ{h - 1}")
         if wide and h < npass:
             layer.append(f"V{h}")
+        if h >= 1:
+            layer.append(f"PROJ{h - 1}")
     for c in range(nch + 1):
         if c < nch:
             layer.append(f"FC1_{c}")
