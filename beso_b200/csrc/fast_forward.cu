@@ -1174,8 +1174,10 @@ __device__ __noinline__ void attention_half_p128(uint32_t sbase, int slot, int n
 // staging and attention, half by half.  The warps of rows 64..127 hold their 96 packed words while the first half
 // is processed by the warps of rows 0..63 and the helpers.  Barriers of the 10 attention warps per pass:
 //   S1 staging(half 0) complete | S2 attention(half 0) done | S3 staging(half 1) complete | S4 attention(half 1) done
+// (Inlined into the compute role's loop: compute-sanitizer's synccheck wants the attn_sync() calls of all ten warps at
+// the same call depth -- with this function out of line it reports the first barrier of a pass as divergent.)
 template <int HSP>
-__device__ __noinline__ uint32_t attention_pass_p128(Compute c, uint32_t bq_s, int S, int T) {
+__device__ __forceinline__ uint32_t attention_pass_p128(Compute c, uint32_t bq_s, int S, int T) {
   using G = G256P;
   const int colb = c.hf * 32, Sh = S >> 1;
   const bool upper = c.wq >= 2;                                      // warp-uniform

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out/sanitizer
 TOOLS=${@:-"memcheck racecheck synccheck"}
 for tool in $TOOLS; do
-  for target in fast precise train "fast:BESO_FAST_CG=2" "fast:BESO_FAST_MC=2"; do
+  for target in fast "precise:BESO_PREC_LAYOUT=stacked" "precise:BESO_PREC_LAYOUT=p128" wide_fast wide_precise train "fast:BESO_FAST_CG=2" "fast:BESO_FAST_MC=2"; do
     name=${target%%:*}; envs=${target#*:}; [ "$envs" = "$target" ] && envs=""
     tag=${name}${envs:+_${envs//=/}}
     log=gpurun_out/sanitizer/${tool}_${tag}.log

@@ -1,8 +1,9 @@
 """Small workloads for compute-sanitizer (memcheck / racecheck / synccheck): one forward and one 2-step sample loop of the
 tensor-core kernel in the selected arithmetic mode, or one small training step (tcgen05 GEMMs + backward kernels).
 
-    compute-sanitizer --tool racecheck python tools/sanitize_target.py fast|precise|simt|train
-    BESO_FAST_CG=2 / BESO_FAST_MC=2 select the cluster variants of the fp16 kernel.
+    compute-sanitizer --tool racecheck python tools/sanitize_target.py fast|precise|simt|train|wide_fast|wide_precise
+    BESO_FAST_CG=2 / BESO_FAST_MC=2 select the cluster variants of the fp16 kernel; BESO_PREC_LAYOUT=stacked|p128 the tile
+    layout of the precise mode (p128 = 128-row tiles, three MMAs per product); wide_* = the 384-column geometry (d = 360).
 """
 import os
 import sys
@@ -19,6 +20,10 @@ from beso_b200.synth import synthetic_inputs, synthetic_state_dict  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "fast"
 dev = torch.device("cuda:0")
+if what.startswith("wide_"):                                   # the reference's kitchen checkpoint width, two layers
+    from beso_b200.config import ModelConfig
+    K256 = ModelConfig(obs_dim=30, act_dim=9, window=4, goal_len=2, d=360, n_layers=2, n_heads=6)
+    what = what[5:]
 sd = synthetic_state_dict(K256, 1)
 if what == "train":
     from beso_b200.training import loss_and_flat_grad
