@@ -304,7 +304,8 @@ def main():
     achieved = flops_launch / (ms_step * 1e-3) / 1e12
     traffic, traffic_src = committed_traffic(mode_name)
     kernel_name = {"fast": "fast_sample_kernel<1,false,1,false> (fp16 tcgen05, single pass)",
-                   "precise": "fast_sample_kernel<1,false,1,true> (split fp16 operands on tcgen05: 2 MMAs per 64-row tile and k-step)",
+                   "precise": "fast_sample_kernel<1,false,1,true,64,2> (split fp16 operands on tcgen05, 128-row tiles: A_hi W_hi + A_lo W_hi + A_hi W_lo "
+                              "per product, the lo image of the LayerNorm output read as a tensor-memory A operand)",
                    "simt": "simt_denoise_kernel (fp32 FMA)"}[mode_name]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
                 "frac": achieved / burst, "frac_of_sustained": achieved / sustained, "peak_sustained": sustained,
@@ -312,11 +313,14 @@ def main():
                 "kernel": kernel_name,
                 "peak_source": f"bf16_tflops (burst) of {how} MEASURED_PEAKS.json: the kernel is timed alone, ms-long launches at max clock",
                 "flops_per_launch": flops_launch,
-                "tensor_flops_executed_per_algorithmic": {"fast": 1.0 * 128 / 115, "precise": 4.0 * 64 / 46, "simt": 0.0}[mode_name],
+                # tile rows used by this workload: 512 sequences of 23 tokens go out as 128 tiles of 4 sequences (92 of 128 rows)
+                # in both modes (one wave over the 148 SMs)
+                "tensor_flops_executed_per_algorithmic": {"fast": 1.0 * 128 / 92, "precise": 3.0 * 128 / 92, "simt": 0.0}[mode_name],
                 "note": "algorithmic FLOPs (SURVEY.md 8d: every product counted once, no padding) / device time.  The precise mode "
-                        "runs every product as hi / lo operand images: 2 M=128 MMAs per 64-row tile where the fp16 mode runs 1 per "
-                        "128 rows, i.e. 4 tensor FLOPs per algorithmic FLOP (x 64/46 row padding at 23 tokens), so its tensor pipe is "
-                        "as busy as the fp16 mode's (ncu: 47 % of elapsed) at a quarter of the algorithmic rate"}
+                        "runs every product as fp16 hi / lo operand images, three M=128 MMAs per product (the lo.lo term is below "
+                        "2^-22) where the fp16 mode runs one: 3 tensor FLOPs per algorithmic FLOP (x 128/92 row padding at 4 "
+                        "sequences of 23 tokens per tile), so the algorithmic fraction of the precise mode is bounded by 1/3 of "
+                        "the fp16 mode's; its tensor-pipe activity is in profiles/r2_precise_kernel.md"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -27,10 +27,21 @@ def line(tag, got, want):
     return float(err.max())
 
 
+def use(mode):
+    """The layout hook is global and read at launch time: set it before every use of a model."""
+    from beso_b200 import _lib
+    _lib.lib().beso_debug_set_precise_layout({"precise128": 2}.get(mode, 0))
+
+
 def models_for(cfg, sd, strict_masks=False):
+    """precise = the precise mode as launched (small batches: stacked 64-row tiles), precise128 = its 128-row tile layout
+    forced (embed_dim <= 256), fast = fp16 mode."""
+    from conftest import build_for_mode
     out = {}
-    for mode in ("precise", "fast"):
-        m = build_denoiser(cfg, dev, mode=mode)
+    for mode in ("precise", "precise128", "fast"):
+        if mode == "precise128" and cfg.d > 256:
+            continue
+        m = build_for_mode(cfg, dev, mode=mode)
         m.load_state_dict(with_masks(m, sd) if strict_masks else sd, strict=True)
         m.eval()
         if mode == "fast" and not m.fast_supported():
@@ -46,7 +57,9 @@ for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "fwd_*.npz"))
     sd = golden_weights(cfg, meta)
     g = {k: v.to(dev) for k, v in a.items() if isinstance(v, torch.Tensor)}
     for mode, m in models_for(cfg, sd).items():
-        kind = "tensor-core split" if (mode == "precise" and m.fast_supported()) else ("CUDA-core fp32" if mode == "precise" else "tensor-core fp16")
+        use(mode)
+        kind = ("tensor-core fp16" if mode == "fast" else
+                ("CUDA-core fp32" if not m.fast_supported() else ("tensor-core split, 128-row tiles" if mode == "precise128" else "tensor-core split, stacked tiles")))
         out = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
         line(f"{name} [{mode}: {kind}] vs reference", out, a["out"])
         if mode == "fast":
@@ -60,7 +73,9 @@ for name in ("ckpt_push", "ckpt_kitchen2"):
     cfg, meta, a, sd = load_checkpoint_golden(name)
     g = {k: v.to(dev) for k, v in a.items() if isinstance(v, torch.Tensor)}
     for mode, m in models_for(cfg, sd, strict_masks=True).items():
-        kind = "tensor-core split" if (mode == "precise" and m.fast_supported()) else ("CUDA-core fp32" if mode == "precise" else "tensor-core fp16")
+        use(mode)
+        kind = ("tensor-core fp16" if mode == "fast" else
+                ("CUDA-core fp32" if not m.fast_supported() else ("tensor-core split, 128-row tiles" if mode == "precise128" else "tensor-core split, stacked tiles")))
         out = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
         line(f"{name} forward [{mode}: {kind}] vs reference", out, a["out"])
         got = sampling.sample_ddim(m, g["state"], g["x_t"], g["goal"], a["sigmas_3"]).cpu()
@@ -78,6 +93,7 @@ print("== samplers (K256 goldens) ==")
 cfg, meta, a = load_golden("samplers_K256")
 g = {k: v.to(dev) for k, v in a.items() if isinstance(v, torch.Tensor)}
 for mode, m in models_for(cfg, golden_weights(cfg, meta)).items():
+    use(mode)
     worst = 0.0
     for n in (1, 3, 5):
         for s in ("ddim", "euler", "heun"):
