@@ -2917,7 +2917,9 @@ int fast_launch(const FastWeights& w_in, const beso_model_desc& m, int sm_count,
   const int cg = (forced_cg == 2 && pairs_ok) ? 2 : 1;
   // BESO_FAST_MC=2: independent CTAs in clusters of 2 sharing the weight stream by TMA multicast
   static const int forced_mc = [] { const char* e = getenv("BESO_FAST_MC"); return e ? atoi(e) : 0; }();
-  const bool dbg = p.trace != nullptr || p.timeline != nullptr;
+  // diagnostics (LayerNorm trace dump, clock stamps) are compiled for the 64-wide head images only (build time: every
+  // image of this kernel is ~15 k instructions); with 32-wide heads the request is ignored
+  const bool dbg = (p.trace != nullptr || p.timeline != nullptr) && hsp == 64;
   const int mc = (cg == 1 && !dbg && forced_mc == 2 && pairs_ok) ? 2 : 1;
   const int smem = (int)kSmemBytes + 1024;
   auto launch = [&](auto kernel, int grid, bool cluster) -> int {
@@ -2957,23 +2959,18 @@ int fast_launch(const FastWeights& w_in, const beso_model_desc& m, int sm_count,
       case 0: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 0>, grid, false); break;
       case 1: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 0>, grid, false); break;
       case 2: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 0>, grid, false); break;
-      case 3: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 0>, grid, false); break;
       case 4: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 0>, grid, false); break;
       case 5: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 0>, grid, false); break;
       case 6: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 0>, grid, false); break;
-      case 7: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 0>, grid, false); break;
       case 8: rc = launch(fast_sample_kernel<1, false, 1, false, 64, 1>, grid, false); break;
       case 9: rc = launch(fast_sample_kernel<1, false, 1, false, 32, 1>, grid, false); break;
       case 10: rc = launch(fast_sample_kernel<1, true, 1, false, 64, 1>, grid, false); break;
-      case 11: rc = launch(fast_sample_kernel<1, true, 1, false, 32, 1>, grid, false); break;
       case 12: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 1>, grid, false); break;
       case 13: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 1>, grid, false); break;
       case 14: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 1>, grid, false); break;
-      case 15: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 1>, grid, false); break;
       case 20: rc = launch(fast_sample_kernel<1, false, 1, true, 64, 2>, grid, false); break;
       case 21: rc = launch(fast_sample_kernel<1, false, 1, true, 32, 2>, grid, false); break;
       case 22: rc = launch(fast_sample_kernel<1, true, 1, true, 64, 2>, grid, false); break;
-      case 23: rc = launch(fast_sample_kernel<1, true, 1, true, 32, 2>, grid, false); break;
       default: set_error("internal: no kernel image for this mode"); rc = BESO_E_INVALID; break;
     }
     if (wide) {
