@@ -738,11 +738,13 @@ __device__ __forceinline__ void attention_item(uint32_t sbase, int lane, int row
   }
 }
 template <class G, int HSP, int LAY, int NH>
+// Items [item0, item1) of the S * MT * NSUB items of a pass (heaviest first), dealt to n_slots slots.
 __device__ __forceinline__ void attention_items(uint32_t sbase, int slot, int n_slots, int half, int lane, int S, int T, int yrow0,
-                                                uint32_t ybar, uint32_t ypar) {
+                                                uint32_t ybar, uint32_t ypar, int item0 = 0, int item1 = 1 << 30) {
   constexpr int NSUB = 64 / HSP;
   const int MT = (T + 15) >> 4;                  // 16-row query tiles == 16-key steps
-  for (int item = slot; item < S * MT * NSUB; item += n_slots) {
+  item1 = min(item1, S * MT * NSUB);
+  for (int item = item0 + slot; item < item1; item += n_slots) {
     const int sub = item % NSUB, it2 = item / NSUB;
     const int mt = MT - 1 - it2 / S, s = it2 % S;     // later query tiles see more keys: schedule them first
     const bool hi = mt * 16 + 8 < T;              // any of the query rows 8..15 of this tile inside the sequence?
@@ -1166,8 +1168,13 @@ template <int HSP>
 __device__ __noinline__ void attention_half_p128(uint32_t sbase, int slot, int n_slots, int lane, int Sh, int T, int yrow0,
                                                  uint32_t ybar, uint32_t ypar) {
   using G = G256P;
-  if (Sh * ((T + 15) >> 4) * (64 / HSP) * 2 <= n_slots) attention_items<G, HSP, 2, 2>(sbase, slot >> 1, n_slots >> 1, slot & 1, lane, Sh, T, yrow0, ybar, ypar);
-  else attention_items<G, HSP, 2, 1>(sbase, slot, n_slots, 0, lane, Sh, T, yrow0, ybar, ypar);
+  // One round when the items fit the slots: the n2 heaviest items (later query tiles: more keys) are shared by two
+  // warps each, the rest take one warp (BASELINE config 2, first half: 4 items on 6 warps -> the two 23-key items are
+  // split).  More items than slots: several rounds of whole items.
+  const int n_items = Sh * ((T + 15) >> 4) * (64 / HSP);
+  const int n2 = n_items <= n_slots ? min(n_items, n_slots - n_items) : 0;
+  if (slot < 2 * n2) attention_items<G, HSP, 2, 2>(sbase, slot >> 1, n2, slot & 1, lane, Sh, T, yrow0, ybar, ypar, 0, n2);
+  else attention_items<G, HSP, 2, 1>(sbase, slot - 2 * n2, n_slots - 2 * n2, 0, lane, Sh, T, yrow0, ybar, ypar, n2);
 }
 
 // One attention pass of the compute warps: [Q|K] accumulator, then V accumulator -> registers (hi / lo packed) ->
