@@ -354,6 +354,12 @@ def main():
         for mname in ("fast", "precise"):
             mm = models[mname]
             e = {"parity_vs_oracle_ddim50_b8": parity(mm)}
+            if mname == "precise":
+                # 8 sequences would take the stacked 64-row tiles; the timed workload (512 sequences) runs the 128-row
+                # layout: check that one too (test hook of the C ABI), then hand the choice back to the launch
+                lib.beso_debug_set_precise_layout(2)
+                e["parity_vs_oracle_ddim50_b8_128row_tiles"] = parity(mm)
+                lib.beso_debug_set_precise_layout(0)
             if mname != mode_name:
                 ms = timed(lambda: sample_ddim(mm, g_state, g_x, g_goal, sig), max(3, args.steps // 4), 3, sync_ranks=False)
                 e.update({"ms_per_step": ms, "value": steps_per_batch / (ms * 1e-3), "unit": UNIT,

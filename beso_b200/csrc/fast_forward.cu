@@ -106,6 +106,7 @@ struct G256 {
   static constexpr uint32_t SmStats = kSmStats, SmProg = kSmProg, SmSigv = kSmProg + 1024 + 4 * kXFloats * 4;
   static constexpr bool XGlobal = false, HSingle = false;
   static constexpr uint32_t ColAL = 0, SmYLo = 0, SmHLo = 0;          // (G256P only)
+  static constexpr uint32_t MlpSlots = 3, SmXSlot = 0;
 };
 struct G384 {
   static constexpr int DP = 384, NA = 6, FF = 1536, NCH = 12;
@@ -118,6 +119,7 @@ struct G384 {
   static constexpr uint32_t SmStats = SmVecM + VecMFloats * 4, SmProg = SmStats + 2048, SmSigv = SmProg;
   static constexpr bool XGlobal = true, HSingle = false;
   static constexpr uint32_t ColAL = 0, SmYLo = 0, SmHLo = 0;          // (G256P only)
+  static constexpr uint32_t MlpSlots = 3, SmXSlot = 0;                // no spare shared memory in the MLP half
 };
 // G256P: the precise mode for embed_dim <= 256 on FULL 128-row tiles ("P128").  Every product is three MMAs,
 //     A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T          (fp16 images, fp32 accumulate; the lo.lo term is below 2^-22)
@@ -141,7 +143,12 @@ struct G256P {
   static constexpr uint32_t SmVecM = SmVecA + VecAFloats * 4, VecB1H = kVecB1H, VecB1F = kVecB1F, VecMFloats = kVecMFloats;
   static constexpr uint32_t SmStats = SmVecM + VecMFloats * 4, SmProg = SmStats + 2048, SmSigv = SmProg + 1024 + 4 * kXFloats * 4;
   static constexpr bool XGlobal = false, HSingle = true;
+  // The MLP half needs 64 KB of the 82 KB union region (H hi + lo): a fourth ring slot lives behind H while it runs --
+  // with three slots the weight stream of the MLP half is latency-bound (two 16 KB requests in flight).  The bytes belong
+  // to the Y atoms during the attention half: the producer takes the slot only after that half's last projection.
+  static constexpr uint32_t MlpSlots = 4, SmXSlot = SmU + 65536;
 };
+static_assert(G256P::SmXSlot + 16384 <= G256P::SmVecA, "extra ring slot must fit behind H");
 static_assert(G256P::SmVecA == kSmVecA && G256P::SmSigv + 512 <= kSmBars, "P128 geometry: vectors and x buffers sit where G256 has them");
 static_assert(G384::SmSigv + 512 <= kSmBars, "wide geometry does not fit shared memory");
 // G384 weight ring: 16 KB slots, one ring group per slot; full barriers B_FULL0 + s, empty barriers B_WEMPTY0 + s (s < 6).
@@ -153,7 +160,11 @@ struct RingW {
   __device__ __forceinline__ uint32_t begin(uint32_t n_slots) { if (cur >= n_slots) cur = 0; return cur; }
   __device__ __forceinline__ uint32_t parity(uint32_t s) const { return (par >> s) & 1u; }
   __device__ __forceinline__ void end(uint32_t s) { par ^= 1u << s; cur = s + 1; }
-  template <class G> static __device__ __forceinline__ uint32_t slot_off(uint32_t s) { return G::SmRing + s * 16384u; }
+  // slots 0 .. kWSlots - 1: the ring proper; further slots (MLP half only, G::MlpSlots) live in the part of the union
+  // region that the MLP half leaves free (G::SmXSlot)
+  template <class G> static __device__ __forceinline__ uint32_t slot_off(uint32_t s) {
+    return s < kWSlots ? G::SmRing + s * 16384u : G::SmXSlot + (s - kWSlots) * 16384u;
+  }
 };
 
 struct FastParams {
@@ -1852,7 +1863,15 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
           fills(per_layer_attn, 16384, kWSlots);
-          fills(per_layer_mlp, 16384, kWSlots);
+          if constexpr (G::MlpSlots > kWSlots) {
+            // The extra slot overlays the Y atoms: wait for this layer's attention half to be over (X_DONE completion
+            // number 1 + 2 l of this evaluation; 1 + 2 L completions per evaluation).  The wait cannot be a full phase
+            // early: the issuer is at most a ring of groups behind, i.e. well inside this layer's attention half, which
+            // only began after the previous completion.  It costs nothing: LayerNorm 2 runs before the first FC1 group.
+            const uint32_t n = (uint32_t)it * (1u + 2u * (uint32_t)p.L) + 1u + 2u * (uint32_t)l;
+            spin_wait(sbase + kSmBars + B_X_DONE * 8, n & 1u);
+          }
+          fills(per_layer_mlp, 16384, G::MlpSlots);
         }
         fills(1, 2048 * G::NA, kWSlots);                     // action head: NA K blocks of [16 x 64]
       }
@@ -2073,6 +2092,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
             }
           }
           // ---- MLP half: F1_0 | F1_c F2_c-1 | F2_11; one accumulator, hidden chunk c goes to H buffer c & 1 ----
+          n_slots = G::MlpSlots;
 #pragma unroll 1
           for (int c = 0; c <= G::NCH; ++c) {
             if (c < G::NCH) {
@@ -2097,6 +2117,7 @@ fast_sample_kernel(const __grid_constant__ FastParams p, const __grid_constant__
               job_end();
             }
           }
+          n_slots = kWSlots;
         }
         // ---- action head (N = 16, all K atoms in one group) ----
         job_begin();
