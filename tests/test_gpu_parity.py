@@ -532,3 +532,47 @@ def test_shapes_outside_the_tensor_core_kernel_fall_back_to_the_cuda_core_kernel
     m = build_denoiser(cfg, cuda_device, mode="fast", state_dict=sd)
     with pytest.raises(NotImplementedError):
         m(g["state"], g["action"], g["goal"], g["sigma"])
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_wide_geometry_samplers_and_cfg_against_oracle(mode, cuda_device):
+    """The 384-column geometry (the reference's kitchen width: d = 360, 6 heads of 60) keeps the sampler's x / d1 / x2 /
+    dU buffers in a global scratch instead of shared memory: every sampler family -- single evaluation per step (DDIM,
+    Euler ancestral, DPM-Solver++(2M) with its history), two evaluations (Heun, DPM-2), LMS (three history buffers) -- and
+    the classifier-free-guidance mix (cond / uncond rows of a tile meeting in dU) against the oracle, on a ragged
+    multi-tile batch, each as ONE launch."""
+    from beso_b200.config import ModelConfig
+    from oracle import beso_oracle as O
+    cfg = ModelConfig(obs_dim=30, act_dim=9, window=4, goal_len=2, d=360, n_layers=2, n_heads=6)
+    assert fast_available(cfg)
+    sd = synthetic_state_dict(cfg, 101)
+    osd, oc = O.as_module_params(sd), to_oracle_cfg(cfg)
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+    m.refresh_weights()                                                   # weight packing is not part of a step
+    B = 37
+    x = synthetic_inputs(cfg, B, seed=102)
+    g = cuda(x, cuda_device)
+    sig = sampling.get_sigmas_exponential(4, 0.005, 1.0)
+    nz = torch.randn((4, B, cfg.window, cfg.act_dim), generator=torch.Generator().manual_seed(103))
+    tol = TOL[mode] if mode == "fast" else dict(rtol=1e-3, atol=2e-5)
+    cases = [("ddim", sampling.sample_ddim, O.sample_ddim, {}), ("euler", sampling.sample_euler, O.sample_euler, {}),
+             ("heun", sampling.sample_heun, O.sample_heun, {}), ("dpmpp_2m", sampling.sample_dpmpp_2m, O.sample_dpmpp_2m, {}),
+             ("lms", sampling.sample_lms, O.sample_lms, {}), ("dpm_2", sampling.sample_dpm_2, O.sample_dpm_2, {}),
+             ("euler_ancestral", sampling.sample_euler_ancestral, O.sample_euler_ancestral, {"noise": nz})]
+    for name, fn, ofn, kw in cases:
+        launches = _lib.lib().beso_kernel_launches()
+        got = fn(m, g["state"], g["noise"], g["goal"], sig, **{k: v.to(cuda_device) for k, v in kw.items()})
+        assert _lib.lib().beso_kernel_launches() == launches + 1, name
+        with torch.no_grad():
+            want = ofn(osd, oc, x["state"], x["noise"], x["goal"], sig, **kw)
+        torch.testing.assert_close(got.cpu(), want, **tol, msg=lambda s, n=name: f"{n}: {s}")
+    # classifier-free guidance: single forward, then Heun (two evaluations per step, both mixed)
+    w = ClassifierFreeSampleModel(m, cond_lambda=1.5)
+    tol_cfg = dict(rtol=1e-2, atol=8e-3) if mode == "fast" else dict(rtol=1e-3, atol=2e-5)
+    with torch.no_grad():
+        want = O.cfg_forward(osd, oc, 1.5, x["state"], x["action"], x["goal"], x["sigma"])
+    torch.testing.assert_close(w(g["state"], g["action"], g["goal"], g["sigma"]).cpu(), want, **tol_cfg)
+    got = sampling.sample_heun(w, g["state"], g["noise"], g["goal"], sig)
+    with torch.no_grad():
+        want = O.sample_heun(osd, oc, x["state"], x["noise"], x["goal"], sig, cond_lambda=1.5)
+    torch.testing.assert_close(got.cpu(), want, **tol_cfg)
