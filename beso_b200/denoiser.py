@@ -216,8 +216,42 @@ class GCDenoiser(nn.Module):
             self._plan, self._plan_key, self._packed = handle, key, {}
         return self._plan
 
-    def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.inner_model.parameters())
+    def _params(self):
+        """The inner model's parameters in ``parameters()`` order WITHOUT walking the module tree on every call (the walk
+        costs more host time than a whole batch-1 forward takes on the GPU): the ``(module._parameters, name)`` slots are
+        cached, so a re-assigned Parameter object is still seen; the cache is dropped by ``_apply`` (``.to`` / ``.cuda``
+        / ``.float``), ``load_state_dict`` and when ``inner_model`` is replaced."""
+        slots = self.__dict__.get("_pslots")
+        if slots is None:
+            slots, seen = [], set()
+            for mod in self.inner_model.modules():
+                for name, prm in mod._parameters.items():
+                    if prm is not None and id(prm) not in seen:
+                        seen.add(id(prm))
+                        slots.append((mod._parameters, name))
+            if [id(d[n]) for d, n in slots] != [id(q) for q in self.inner_model.parameters()]:      # pragma: no cover
+                raise _lib.BesoLibraryError("internal: cached parameter slots are not in parameters() order")
+            self.__dict__["_pslots"] = slots
+        return [d[n] for d, n in slots]
+
+    def _drop_param_cache(self):
+        self.__dict__.pop("_pslots", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._drop_param_cache()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._drop_param_cache()
+        return super().load_state_dict(*args, **kwargs)
+
+    def __setattr__(self, name, value):
+        if name == "inner_model":
+            self.__dict__.pop("_pslots", None)
+        super().__setattr__(name, value)
+
+    def _fingerprint(self, params=None):
+        return tuple((p.data_ptr(), p._version) for p in (self._params() if params is None else params))
 
     def refresh_weights(self, slot: Optional[int] = None, force: bool = True):
         """(Re)pack the current parameter values into weight slot ``slot`` (0 = raw, 1 = EMA) and
@@ -225,7 +259,7 @@ class GCDenoiser(nn.Module):
         call it by hand after writing through ``param.data`` (e.g. the reference EMA helper's
         ``copy_to`` / ``restore``), which PyTorch's version counters do not see."""
         slot = self._slot if slot is None else slot
-        params = list(self.inner_model.parameters())
+        params = self._params()
         if not params or not params[0].is_cuda:
             raise _lib.BesoLibraryError("model parameters must live on a CUDA device (call .to('cuda'))")
         dev = self._device_index(params[0])
@@ -234,7 +268,7 @@ class GCDenoiser(nn.Module):
         # the caller's back from the live parameters: a stale fingerprint there would silently replace the EMA
         # weights by the raw ones.  Only an explicit refresh_weights(slot=1, force=True) packs the live values into it.
         external = slot in self._packed and self._packed[slot][0] == "external"
-        fp = self._fingerprint()
+        fp = self._fingerprint(params)
         if force or (not external and self._packed.get(slot) != fp):
             self._pack(plan, dev, slot, params)
             self._packed[slot] = fp

@@ -418,3 +418,27 @@ def test_public_header_is_plain_c():
         assert r.returncode == 0, r.stderr
     includes = [l for l in open(hdr).read().splitlines() if l.lstrip().startswith("#include")]
     assert includes and all("cuda" not in l and "torch" not in l for l in includes), includes
+
+
+def test_parameter_slot_cache_tracks_what_the_module_tree_walk_would():
+    """GCDenoiser._params() avoids walking the module tree on every call (the walk cost more host time than a batch-1
+    forward takes on the GPU).  It must stay equal to parameters() through every way the reference touches a model:
+    in-place updates (optimizer, EMA copy), load_state_dict, dtype / device conversion, a re-assigned Parameter object."""
+    import torch.nn as nn
+    m = build_denoiser(K256, "cpu")
+
+    def same():
+        return [id(p) for p in m._params()] == [id(p) for p in m.inner_model.parameters()]
+    assert same() and len(m._params()) == len(K256.param_shapes())
+    fp0 = m._fingerprint()
+    with torch.no_grad():
+        m.inner_model.ln_f.weight.add_(1.0)                      # in-place update bumps the version counter
+    assert same() and m._fingerprint() != fp0
+    m.load_state_dict(m.state_dict())
+    assert same()
+    m.double()
+    m.float()
+    assert same()
+    fp1 = m._fingerprint()
+    m.inner_model.ln_f.weight = nn.Parameter(torch.ones_like(m.inner_model.ln_f.weight))   # new Parameter object
+    assert same() and m._fingerprint() != fp1
