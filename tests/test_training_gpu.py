@@ -295,3 +295,47 @@ def test_ema_slot_survives_optimizer_steps_without_ema_update(cuda_device):
     agent.train_step(batch)                                                       # step 2: EMA updates
     torch.manual_seed(0)
     assert agent.evaluate(x["state"], x["clean"], x["goal"]) != want
+
+
+def test_cfg4_per_rank_shape_properties(cuda_device):
+    """BASELINE config 4 as one rank sees it (kitchen training: K256, 1024 sequences per rank of a global batch of 8192,
+    dropout 0.3 on the attention probabilities as in configs/franka_kitchen_main_config.yaml:56): loss against the
+    oracle WITHOUT dropout, then with fixed dropout masks the properties a data-parallel step relies on -- the mean of the
+    shard gradients (same masks, sliced) is the full-batch gradient, and the step is deterministic.  The exchange itself
+    is covered by the world-size-2 tests (tests/test_dist_cpu.py) and measured by bench.py --gpus N."""
+    from beso_b200 import K256
+    from beso_b200.training import draw_dropout_masks
+    from oracle import beso_oracle as O
+    cfg = K256
+    sd = synthetic_state_dict(cfg, 51)
+    x = synthetic_inputs(cfg, 1024, seed=52, sigma_min=0.05)
+    g = cuda(x, cuda_device)
+    args = (g["state"], g["clean"], g["goal"], g["noise"], g["sigma"])
+    m0 = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd)
+    m0.train()
+    loss0, flat0 = loss_and_flat_grad(m0, *args)
+    with torch.no_grad():
+        want = O.denoiser_loss(sd, to_oracle_cfg(cfg), x["state"], x["clean"], x["goal"], x["noise"].clone(), x["sigma"])
+    torch.testing.assert_close(loss0.cpu(), want, rtol=1e-4, atol=1e-7)
+    m = build_denoiser(cfg, cuda_device, mode="precise", state_dict=sd, attn_pdrop=0.3)
+    m.train()
+    torch.manual_seed(53)
+    masks = draw_dropout_masks(m.inner_model, 1024, cfg.window, cuda_device)
+    loss, flat = loss_and_flat_grad(m, *args, dropout_masks=masks)
+    assert torch.isfinite(loss) and torch.isfinite(flat).all() and not torch.equal(loss, loss0)
+    loss2, flat2 = loss_and_flat_grad(m, *args, dropout_masks=masks)
+    assert torch.equal(loss, loss2) and torch.equal(flat, flat2)
+
+    def shard(mk, sl):                                            # the same draws, restricted to a shard's sequences
+        if isinstance(mk, torch.Tensor):
+            return mk[sl].contiguous() if mk.dim() > 0 and mk.shape[0] == 1024 else mk
+        if isinstance(mk, (list, tuple)):
+            return type(mk)(shard(v, sl) for v in mk)
+        if isinstance(mk, dict):
+            return {k: shard(v, sl) for k, v in mk.items()}
+        return mk
+    parts = []
+    for sl in (slice(0, 512), slice(512, 1024)):
+        parts.append(loss_and_flat_grad(m, *(a[sl] for a in args), dropout_masks=shard(masks, sl)))
+    torch.testing.assert_close(0.5 * (parts[0][0] + parts[1][0]), loss, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(0.5 * (parts[0][1] + parts[1][1]), flat, rtol=1e-3, atol=1e-5 * float(flat.abs().max()))
