@@ -580,3 +580,53 @@ def test_wide_geometry_samplers_and_cfg_against_oracle(mode, cuda_device):
     with torch.no_grad():
         want = O.sample_heun(osd, oc, x["state"], x["noise"], x["goal"], sig, cond_lambda=1.5)
     torch.testing.assert_close(got.cpu(), want, **tol_cfg)
+
+
+SWEEP = [
+    # (obs, act, window, goal_len, d, layers, heads, goal_conditioned): the edges of what the tensor-core kernel takes
+    (64, 13, 11, 1, 256, 1, 4, True),      # 24 tokens, widest observation / action vectors
+    (7, 1, 1, 2, 64, 2, 8, True),          # head size 8 (padded to 32), single time step
+    (20, 4, 6, 1, 136, 2, 2, True),        # d not a multiple of 64, head size 68 > 64: NOT supported (CUDA-core kernel)
+    (20, 4, 6, 1, 144, 2, 4, True),        # d = 144, head size 36 (padded to 64): 4 passes
+    (16, 2, 5, 1, 200, 1, 5, True),        # head size 40, 5 heads: 5 passes
+    (12, 3, 4, 2, 192, 1, 12, False),      # no goal, head size 16: 6 passes of two heads
+    (30, 9, 4, 2, 264, 1, 3, True),        # just over 256: 384-column geometry, head size 88: NOT supported
+    (30, 9, 4, 2, 264, 2, 6, True),        # 384-column geometry, head size 44 (padded to 64)
+    (30, 9, 4, 2, 320, 1, 5, True),        # 5 heads of 64
+    (10, 2, 8, 1, 384, 1, 12, True),       # full width, 12 heads of 32: 6 passes of two heads
+    (10, 2, 8, 1, 384, 2, 6, True),        # full width, 6 heads of 64, 18 tokens
+    (10, 2, 3, 1, 392, 1, 7, True),        # wider than the kernel: CUDA-core kernel
+]
+
+
+@pytest.mark.parametrize("shape", SWEEP, ids=lambda s: "obs%d_act%d_w%d_g%d_d%d_L%d_h%d_%s" % (s[:7] + ("goal" if s[7] else "nogoal",)))
+def test_shape_sweep_every_mode_against_oracle(shape, cuda_device):
+    """Edges of the tensor-core kernel's envelope (both geometries, padded head sizes 32 / 64, 1 .. 6 attention passes,
+    24 tokens, the widest input vectors) and shapes just outside it: what the library reports must agree with the
+    envelope, every mode that runs must match the oracle on a forward and a 2-step DDIM loop (ragged batch), and shapes
+    outside the envelope must still run (CUDA-core kernel) in the default mode."""
+    from beso_b200.config import ModelConfig
+    from oracle import beso_oracle as O
+    obs, act, window, goal_len, d, layers, heads, gc = shape
+    cfg = ModelConfig(obs_dim=obs, act_dim=act, window=window, goal_len=goal_len, d=d, n_layers=layers, n_heads=heads,
+                      goal_conditioned=gc)
+    hs = d // heads
+    per_pass = 64 // (32 if hs <= 32 else 64)
+    expect = d <= 384 and d % 8 == 0 and hs <= 64 and -(-heads // per_pass) <= 6 and cfg.n_tokens() <= 24
+    assert fast_available(cfg) == expect
+    sd = synthetic_state_dict(cfg, 200 + d)
+    osd, oc = O.as_module_params(sd), to_oracle_cfg(cfg)
+    B = 7
+    x = synthetic_inputs(cfg, B, seed=300 + d)
+    g = cuda(x, cuda_device)
+    sig = sampling.get_sigmas_exponential(2, 0.005, 1.0)
+    with torch.no_grad():
+        want = O.denoiser_forward(osd, oc, x["state"], x["action"], x["goal"], x["sigma"])
+        want_s = O.sample_ddim(osd, oc, x["state"], x["noise"], x["goal"], sig)
+    modes = ["precise"] + (["fast"] + (["precise128"] if d <= 256 else []) if expect else [])
+    for mode in modes:
+        m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+        got = m(g["state"], g["action"], g["goal"], g["sigma"]).cpu()
+        torch.testing.assert_close(got, want, **TOL[mode], msg=lambda s, mo=mode: f"{mo} forward: {s}")
+        got_s = sampling.sample_ddim(m, g["state"], g["noise"], g["goal"], sig).cpu()
+        torch.testing.assert_close(got_s, want_s, **TOL[mode], msg=lambda s, mo=mode: f"{mo} ddim: {s}")
