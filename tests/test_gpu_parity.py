@@ -630,3 +630,28 @@ def test_shape_sweep_every_mode_against_oracle(shape, cuda_device):
         torch.testing.assert_close(got, want, **TOL[mode], msg=lambda s, mo=mode: f"{mo} forward: {s}")
         got_s = sampling.sample_ddim(m, g["state"], g["noise"], g["goal"], sig).cpu()
         torch.testing.assert_close(got_s, want_s, **TOL[mode], msg=lambda s, mo=mode: f"{mo} ddim: {s}")
+
+
+@pytest.mark.parametrize("mode", ["precise", "fast"])
+def test_wide_geometry_many_tiles_per_cta_properties(mode, cuda_device):
+    """384-column geometry with more tiles than SMs (2000 sequences of 11 tokens: every CTA runs several tiles through
+    the same global x-buffer scratch) and a two-evaluation sampler: deterministic, batch-split invariant (bit-exact: one
+    tile layout per mode at this width), and a slice against the oracle."""
+    from beso_b200.config import ModelConfig
+    from oracle import beso_oracle as O
+    cfg = ModelConfig(obs_dim=30, act_dim=9, window=4, goal_len=2, d=360, n_layers=2, n_heads=6)
+    sd = synthetic_state_dict(cfg, 111)
+    m = build_denoiser(cfg, cuda_device, mode=mode, state_dict=sd)
+    B = 2000
+    x = synthetic_inputs(cfg, B, seed=112)
+    g = cuda(x, cuda_device)
+    sig = sampling.get_sigmas_exponential(3, 0.005, 1.0)
+    full = sampling.sample_heun(m, g["state"], g["noise"], g["goal"], sig)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, sampling.sample_heun(m, g["state"], g["noise"], g["goal"], sig))
+    parts = torch.cat([sampling.sample_heun(m, g["state"][:777], g["noise"][:777], g["goal"][:777], sig),
+                       sampling.sample_heun(m, g["state"][777:], g["noise"][777:], g["goal"][777:], sig)])
+    assert torch.equal(parts, full)
+    with torch.no_grad():
+        want = O.sample_heun(O.as_module_params(sd), to_oracle_cfg(cfg), x["state"][-5:], x["noise"][-5:], x["goal"][-5:], sig)
+    torch.testing.assert_close(full[-5:].cpu(), want, **TOL[mode])
