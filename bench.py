@@ -174,9 +174,13 @@ def committed_traffic(mode_name):
         def _bytes(k):
             v, u = float(str(d[k]["value"]).replace(",", "")), d[k]["unit"].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        committed_traffic.tensor_active = float(str(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]["value"]).replace(",", ""))
         return _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum"), os.path.relpath(prof, ROOT)
     except Exception:
         return None, None
+
+
+committed_traffic.tensor_active = None
 
 
 def main():
@@ -310,6 +314,9 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
                 "frac": achieved / burst, "frac_of_sustained": achieved / sustained, "peak_sustained": sustained,
                 "traffic": traffic, "traffic_source": traffic_src,
+                # tensor-pipe active cycles (% of elapsed) of the same committed ncu capture: what the pipe was busy with,
+                # padding rows and the precise mode's extra MMAs included
+                "tensor_pipe_active_pct_of_elapsed_ncu": committed_traffic.tensor_active,
                 "kernel": kernel_name,
                 "peak_source": f"bf16_tflops (burst) of {how} MEASURED_PEAKS.json: the kernel is timed alone, ms-long launches at max clock",
                 "flops_per_launch": flops_launch,
