@@ -26,6 +26,15 @@
 //  * Embeddings (state / goal / action / sigma / position / biases) are one K=128 GEMM: the A
 //    operand carries the raw inputs plus one-hot token-position columns whose B rows hold
 //    (bias + pos_emb) split into bf16 hi + lo, so X starts exact to ~2^-17.
+//
+// Variants of the one kernel template (fast_sample_kernel<CG, DBG, MC, PREC, HSP, GEO>):
+//  * GEO 0 (G256): embed_dim <= 256, everything above.  GEO 1 (G384): embed_dim <= 384 (the reference's kitchen models):
+//    X takes 384 TMEM columns, ONE scratch accumulator ([Q|K] job + V job, FC1 without ping-pong), 16 KB ring slots,
+//    the sampler's x buffers in a global scratch.  GEO 2 (G256P): the precise mode on full 128-row tiles.
+//  * PREC: fp32-equivalent arithmetic from fp16 hi / lo operand images -- stacked on the MMA row dimension (64
+//    sequence rows per tile; GEO 0 / 1) or as three MMAs per product with the lo image of the LayerNorm output read
+//    as a tensor-memory A operand (GEO 2).  fast_launch picks the layout per batch.
+//  * HSP: padded head size (32 / 64); CG / MC: CTA-pair MMAs / multicast weight ring (GEO 0, fp16 mode, opt-in).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
